@@ -1,0 +1,256 @@
+/* vxgpu.h -- C-ABI of the B200-native Voxelyze timestep engine (libvxgpu.so).
+ *
+ * This is the drop-in boundary for the one hot path the engine replaces:
+ *     CVX_Sim::Integrate()                       evosoro/_voxcad/Voxelyze/VX_Sim.cpp:1763-1933
+ *       -> CVXS_BondInternal::UpdateBond()       evosoro/_voxcad/Voxelyze/VXS_BondInternal.cpp:35-346
+ *       -> CVXS_Voxel::EulerStep()               evosoro/_voxcad/Voxelyze/VXS_Voxel.cpp:169-427, 482-758
+ * batched over a population of independent robots.  The reference has no FFI of its own (SURVEY.md
+ * section 8b); these are the entry points a `CVX_Sim` adapter binds: the host keeps
+ * parsing the .vxa, building voxel/bond lists and computing the import-time constants
+ * (CVX_Bond::UpdateConstants VX_Bond.cpp:123-173, CVX_Voxel::SetMaterial VX_Voxel.cpp:94-128) and hands
+ * them over as a flat descriptor; the library owns all device memory behind an opaque handle.
+ *
+ * Plain C, no torch / CUDA types in any signature.  Return value: 0 = ok, negative = argument / CUDA
+ * error, positive = the model uses a feature the kernels do not implement (the caller must abort --
+ * there is NO CPU fallback).  vxg_last_error() gives a thread-local message for the last failure.
+ * Any thread may call; one handle is not re-entrant; different handles may be driven concurrently.
+ */
+#ifndef VXGPU_H
+#define VXGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VXG_ABI_VERSION 1
+
+/* ---- return codes ------------------------------------------------------------------------------ */
+enum {
+    VXG_OK = 0,
+    VXG_ERR_ARG = -1,        /* bad argument / descriptor inconsistent                               */
+    VXG_ERR_CUDA = -2,       /* CUDA runtime error (message has the cudaError string)                */
+    VXG_ERR_NOMEM = -3,
+    VXG_ERR_STATE = -4,      /* call order (e.g. step before all robots are uploaded)                */
+    VXG_ERR_NO_DEVICE = -5,  /* no CUDA device: the engine never falls back to the CPU               */
+    VXG_UNSUPPORTED_FEATURE = 1, /* descriptor asks for something outside the implemented path      */
+    VXG_UNSUPPORTED_SIZE = 2     /* robot exceeds the limits given to vxg_create                     */
+};
+
+/* ---- feature flags (vxg_sim_params.flags) -------------------------------------------------------- */
+#define VXG_F_FLOOR        0x0001u /* VXSFEAT_FLOOR        VXS_Voxel.cpp:635-639                       */
+#define VXG_F_TEMPERATURE  0x0002u /* VXSFEAT_TEMPERATURE  VXS_Voxel.cpp:292-305 (thermal actuation)   */
+#define VXG_F_LW_SCALE     0x0004u /* _voxcad_land_water scale law, LW/VXS_Voxel.cpp:211-235           */
+#define VXG_F_STICKY_FLOOR 0x0008u /* getUsingStickyFloor() VXS_Voxel.cpp:736-739                      */
+#define VXG_F_FLUID        0x0010u /* LW fluid environment: gravity and floor inert, LW/VXS_Voxel.cpp:357,467 */
+#define VXG_F_COLLISIONS   0x0020u /* VXSFEAT_COLLISIONS: contact bonds given through vxg_set_collision_pairs */
+
+/* degrees of freedom, same bit values as the reference (VX_FRegion.h DOF_*) */
+#define VXG_DOF_X  0x01
+#define VXG_DOF_Y  0x02
+#define VXG_DOF_Z  0x04
+#define VXG_DOF_TX 0x08
+#define VXG_DOF_TY 0x10
+#define VXG_DOF_TZ 0x20
+#define VXG_DOF_ALL 0x3F
+
+/* ---- precision of the device arithmetic -------------------------------------------------------- */
+#define VXG_PREC_F32 0  /* fp32 forces/moments/quaternions, fp64 positions and time (production)     */
+#define VXG_PREC_F64 1  /* everything fp64 (logic-parity / high-accuracy mode; slower)               */
+
+/* Per-voxel constants, de-duplicated into classes by the host (a class = one palette material in
+ * evosoro-written files; per-voxel phase offsets or evolved stiffness simply make more classes).
+ * All values are what the reference caches at import: VX_Voxel.cpp:109-125, VX_Voxel.h:64,
+ * VX_Sim.cpp:878-991 (per-voxel actuation parameters). */
+typedef struct vxg_vox_class {
+    double mass;          /* rho s^3                                  VX_Voxel.cpp:110               */
+    double mass_inv;      /* _massInv                                 VX_Voxel.cpp:121               */
+    double inertia;       /* m s^2/6                                  VX_Voxel.cpp:111               */
+    double inertia_inv;   /* _inertiaInv                              VX_Voxel.cpp:122               */
+    double damp_lin;      /* _2xSqMxExS     = 2 sqrt(m E s)           VX_Voxel.cpp:123               */
+    double damp_ang;      /* _2xSqIxExSxSxS = 2 sqrt(I E s^3)         VX_Voxel.cpp:124               */
+    double k_floor;       /* GetLinearStiffness() = 2 E s             VX_Voxel.h:64                  */
+    double mu_static;     /* uStatic                                  VXS_Voxel.cpp:717              */
+    double mu_dynamic;    /* uDynamic                                 VXS_Voxel.cpp:716              */
+    double nom_size;      /* NominalSize                              VX_Sim.cpp:527                 */
+    double cte;           /* Vox_CTE                                  VXS_Voxel.cpp:295              */
+    double temp_amp_damp; /* TempAmpDamp (1 unless evolved)           VX_Sim.cpp:885                 */
+    double phase_offset;  /* phaseOffset (stored as float upstream)   VX_Sim.cpp:882                 */
+    double e_mod;         /* Vox_E (information only)                                                */
+    double init_size;     /* initialVoxelSize -- a `float` upstream (VXS_Voxel.h:100), so it differs  */
+                          /* from nom_size by float rounding and feeds PreNatalTempFrac VXS_Voxel.cpp:237-238 */
+    double ext_force[3];  /* ExternalForce                            VX_Sim.cpp:573                 */
+    double ext_torque[3]; /* ExternalTorque                           VX_Sim.cpp:574                 */
+    double ext_disp[3];   /* ExternalDisp  (fixed DOFs)               VX_Sim.cpp:576-578             */
+    double ext_tdisp[3];  /* ExternalTDisp (fixed rot. DOFs)          VX_Sim.cpp:579-581             */
+    int32_t dof_fixed;    /* VXG_DOF_* mask                           VX_Voxel.h:90                  */
+    int32_t mat_index;    /* palette index (fitness probes key on 5/6/7, VX_Sim.cpp:2626)            */
+} vxg_vox_class;
+
+/* Per-bond constants, de-duplicated into classes (a class = an ordered material pair in
+ * evosoro-written files).  VX_Bond.cpp:65-109 (LinkVoxels), :123-173 (UpdateConstants).
+ * Voxels are cubes, so the y and z beam constants coincide (Iy == Iz). */
+typedef struct vxg_bond_class {
+    double a1;        /* E A / L        (axial; used by CalcMaxDt and contact bonds)                 */
+    double a2;        /* G J / L        (torsion)                                                    */
+    double b1;        /* 12 E I / L^3                                                                */
+    double b2;        /* 6 E I / L^2                                                                 */
+    double b3;        /* 2 E I / L                                                                   */
+    double len;       /* L.x: nominal bond length used for strain      VXS_BondInternal.cpp:120      */
+    double area;      /* (CSArea1 + CSArea2)/2 = s^2                   VXS_BondInternal.cpp:127      */
+    double e1;        /* modulus the stress model uses for voxel 1     VXS_Voxel.cpp:831, VX_Object.cpp:1477 */
+    double e2;        /* ... for voxel 2 (== e1 when homogeneous)                                    */
+    double nom_dist;  /* nominal centre distance along the bond axis (|NominalPos2 - NominalPos1|)    */
+    double c_a1m1, c_a1m2;   /* _2xSqA1xM1/2     VX_Bond.cpp:159                                     */
+    double c_a2i1, c_a2i2;   /* _2xSqA2xI1/2     VX_Bond.cpp:160                                     */
+    double c_b1m1, c_b1m2;   /* _2xSqB1{Y,Z}xM1/2  :161-162                                          */
+    double c_b2fm1, c_b2fm2; /* _2xSqB2{Y,Z}xFM1/2 :163-164                                          */
+    double c_b3i1, c_b3i2;   /* _2xSqB3{Y,Z}xI1/2  :169-170                                          */
+    int32_t homogeneous;     /* HomogenousBond   VX_Bond.cpp:75                                      */
+    int32_t reserved;
+} vxg_bond_class;
+
+/* Per-robot simulation constants: what CVX_Sim / CVX_Environment hold that the step reads. */
+typedef struct vxg_sim_params {
+    double dt;              /* DtFrac * OptimalDt, constant in scope   VX_Sim.cpp:1793, :1693-1727   */
+    double bond_damp_z;     /* GetBondDampZ()       VXS_BondInternal.cpp:313                         */
+    double col_damp_z;      /* GetCollisionDampZ()  VXS_Voxel.cpp:725                                */
+    double slow_damp_z;     /* GetSlowDampZ()       VXS_Voxel.cpp:487, :206                          */
+    double grav_acc;        /* GetGravityAccel(), 0 when VXSFEAT_GRAVITY is off  VXS_Voxel.cpp:536   */
+    double init_cm_time;    /* GetInitCmTime()      VXS_Voxel.cpp:292                                */
+    double temp_period;     /* TempPeriod (float upstream)  VXS_Voxel.cpp:302                        */
+    double temp_amplitude;  /* TempAmplitude = TempAmp - TempBase (float upstream)                   */
+    double min_scale_fact;  /* getMinTempFact()     VXS_Voxel.cpp:226                                */
+    double max_scale_fact;  /* 1 + getGrowthAmplitude()  VXS_Voxel.cpp:225                           */
+    double lattice_dim;     /* LocalVXC.GetLatticeDim()                                              */
+    double drag_coeff;      /* LW AggregateDragCoefficient (VXG_F_FLUID)                             */
+    uint32_t flags;         /* VXG_F_*                                                               */
+    uint32_t reserved;
+} vxg_sim_params;
+
+/* One imported robot, flat.  Voxel i is the reference's simulation index i (rank among occupied
+ * lattice cells, x fastest: VX_Sim.cpp:530-600).  Bond j joins voxel bond_v1[j] (negative side) to
+ * bond_v2[j] (positive side) along bond_axis[j] (0 = X, 1 = Y, 2 = Z: VX_Sim.cpp:621-641,
+ * :726-751).  A voxel has at most one bond per direction.  The host keeps ownership of every array;
+ * vxg_upload copies. */
+typedef struct vxg_robot_desc {
+    int32_t n_vox, n_bond, n_vclass, n_bclass;
+    const double* nom_pos;        /* [n_vox][3] NominalPosition, metres                               */
+    const int32_t* vox_class;     /* [n_vox]                                                          */
+    const int32_t* bond_v1;       /* [n_bond]                                                         */
+    const int32_t* bond_v2;       /* [n_bond]                                                         */
+    const int32_t* bond_axis;     /* [n_bond] 0/1/2                                                   */
+    const int32_t* bond_class;    /* [n_bond]                                                         */
+    const vxg_vox_class* vclasses;   /* [n_vclass]                                                    */
+    const vxg_bond_class* bclasses;  /* [n_bclass]                                                    */
+    vxg_sim_params sim;
+} vxg_robot_desc;
+
+/* Dynamic state of one robot in the reference's own terms (fp64 on the host side whatever the device
+ * precision).  Any pointer may be NULL to skip that field.  Used by vxg_download_state (device ->
+ * CVX_Sim::VoxArray / BondArrayInternal write-back for the GUI and for parity tests) and
+ * vxg_upload_state (resume / perturbation tests). */
+typedef struct vxg_robot_state {
+    double* pos;        /* [n_vox][3]  Pos        VXS_Voxel.h:122                                     */
+    double* quat;       /* [n_vox][4]  Angle (w,x,y,z)                                                */
+    double* lin_mom;    /* [n_vox][3]  LinMom                                                         */
+    double* ang_mom;    /* [n_vox][3]  AngMom                                                         */
+    double* scale;      /* [n_vox]     Scale                                                          */
+    int32_t* static_fric; /* [n_vox]   StaticFricFlag of the last step                                */
+    double* bond_force1;  /* [n_bond][3] Force1 of the last step      VXS_Bond.h:54                   */
+    double* bond_force2;  /* [n_bond][3]                                                              */
+    double* bond_moment1; /* [n_bond][3]                                                              */
+    double* bond_moment2; /* [n_bond][3]                                                              */
+    double* bond_strain;  /* [n_bond]  CurStrainTot                                                   */
+    int32_t* bond_small_angle; /* [n_bond] SmallAngle                                                 */
+} vxg_robot_state;
+
+/* Sizing of a batch: every robot slot gets the same stride so a slot is one contiguous blob. */
+typedef struct vxg_limits {
+    int32_t max_vox;      /* >= n_vox of every robot in the batch                                    */
+    int32_t max_vclass;   /* >= n_vclass                                                             */
+    int32_t max_bclass;   /* >= n_bclass                                                             */
+    int32_t precision;    /* VXG_PREC_F32 / VXG_PREC_F64                                             */
+    int32_t max_col_pairs;/* capacity for contact bonds per robot (0 = self-collision unused)        */
+    int32_t reserved[3];
+} vxg_limits;
+
+/* status bits written by vxg_sync */
+#define VXG_ST_DIVERGED 0x1u /* a bond strain exceeded 100: Integrate() returned false, VX_Sim.cpp:1775-1777 */
+#define VXG_ST_FINISHED 0x2u /* the robot has run the step budget set with vxg_set_step_budget      */
+
+/* Per-robot reductions of the voxel state (what CVX_Sim::UpdateStats / the fitness probes read,
+ * VX_Sim.cpp:1511-1690, :2415-2441, :2584-2712).  Filled by vxg_reduce_stats. */
+typedef struct vxg_robot_stats {
+    double com[3];        /* mass-weighted centre of mass  GetCM() VX_Sim.cpp:2415-2441              */
+    double ini_com[3];    /* COM latched at the InitCmTime step   VX_Sim.cpp:1064-1075 (zeros before) */
+    double max_vel;       /* max |Vel|  (SS.MaxVoxVel)                                               */
+    double min_pos[3];    /* min over voxels of Pos                                                  */
+    double max_pos[3];    /* max over voxels of Pos                                                  */
+    double time;          /* CurTime                                                                 */
+    int64_t steps;        /* CurStepCount                                                            */
+    int32_t n_touching_floor; /* count of 0.5 Scale - z > 0     VX_Sim.cpp:2584                      */
+    int32_t ini_com_latched;
+} vxg_robot_stats;
+
+typedef struct vxg_batch vxg_batch; /* opaque; owns all device memory */
+
+/* Library / device discovery.  vxg_device_count returns 0 (not an error) when no GPU is visible so
+ * host-only tools can still link the library; every compute entry point then fails with
+ * VXG_ERR_NO_DEVICE. */
+int vxg_abi_version(void);
+int vxg_device_count(void);
+const char* vxg_last_error(void);
+
+/* Replaces: construction of CVX_Sim::VoxArray / BondArrayInternal storage (VX_Sim.cpp:488-717). */
+int vxg_create(vxg_batch** out, int device, int n_robots, const vxg_limits* lim);
+void vxg_destroy(vxg_batch* b);
+
+/* Replaces: CVX_Sim::Import's array fill + ResetSimulation (VX_Sim.cpp:530-641, :839-1007): copies the
+ * descriptor of one robot into slot `robot` and resets its dynamic state (Pos = NominalPosition,
+ * Angle = identity, momenta 0, Scale = NominalSize, CurTime = 0, dt = 0 for the first bond pass). */
+int vxg_upload(vxg_batch* b, int robot, const vxg_robot_desc* desc);
+
+/* Steps each robot stops after (CurStepCount limit; the host derives it from StopConditionMet,
+ * VX_Sim.cpp:1398-1422, by replaying the fp64 `CurTime += dt` accumulation).  latch_step[r] is the
+ * CurStepCount at whose TimeStep() entry IniCM is latched (VX_Sim.cpp:1064-1075); -1 = never.
+ * Either pointer may be NULL (no limit / no latch). */
+int vxg_set_step_budget(vxg_batch* b, const int64_t* total_steps, const int64_t* latch_step);
+
+/* Replaces: n_steps calls of CVX_Sim::Integrate() (VX_Sim.cpp:1763-1933) on every robot of the batch
+ * that is neither diverged nor finished.  Asynchronous on the batch's stream. */
+int vxg_step(vxg_batch* b, int n_steps);
+
+/* Waits for the stream; status_per_robot (may be NULL) receives VXG_ST_* bits.  Maps to TimeStep()'s
+ * `false` + "Simulation Diverged..." (VX_Sim.cpp:1147-1150) for bit 0. */
+int vxg_sync(vxg_batch* b, uint32_t* status_per_robot);
+
+/* Device time of the launches issued by the last vxg_step call (CUDA events on the batch stream);
+ * valid after vxg_sync. */
+int vxg_last_step_ms(vxg_batch* b, float* ms);
+/* Number of kernels this library launched on the batch so far. */
+int64_t vxg_launch_count(vxg_batch* b);
+
+/* Replaces: the per-voxel / per-bond getters the GUI and CVX_MeshUtil read after a step
+ * (VXS_Voxel.h:46-59, VXS_Bond.h:31-43). */
+int vxg_download_state(vxg_batch* b, int robot, vxg_robot_state* out);
+int vxg_upload_state(vxg_batch* b, int robot, const vxg_robot_state* in, double cur_time, int64_t cur_step);
+
+/* Replaces: CVX_Sim::UpdateStats / GetCM (VX_Sim.cpp:1511-1690, :2415-2441) for the quantities the
+ * result writer needs; out is [n_robots]. Synchronous. */
+int vxg_reduce_stats(vxg_batch* b, vxg_robot_stats* out);
+
+/* Replaces: the contact-bond list CVX_Sim::CalcL1Bonds builds (VX_Sim.cpp:2357-2413): n_pairs voxel
+ * index pairs (v1, v2) and the composite axial stiffness a1 of each (VXS_BondCollision.cpp:41-59). */
+int vxg_set_collision_pairs(vxg_batch* b, int robot, int n_pairs, const int32_t* v1, const int32_t* v2,
+                            const double* a1);
+
+/* Host-buffer convenience used by the end-to-end benchmark: upload all descriptors, run n_steps,
+ * download positions of every robot into pos_out ([n_robots][max_vox][3] doubles). */
+int vxg_run_batch_host(vxg_batch* b, const vxg_robot_desc* descs, int n_descs, int n_steps, double* pos_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VXGPU_H */

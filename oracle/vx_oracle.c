@@ -1,0 +1,497 @@
+/* vx_oracle.c -- plain-C fp64 restatement of the reference Voxelyze timestep.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Restates, operation for operation (so that -ffp-contract=off builds are bit-comparable with the
+ * unmodified reference built under oracle/_ref):
+ *   CVX_Sim::Integrate                 evosoro/_voxcad/Voxelyze/VX_Sim.cpp:1763-1933
+ *   CVXS_BondInternal::CalcLinForce    evosoro/_voxcad/Voxelyze/VXS_BondInternal.cpp:56-187
+ *   CVXS_BondInternal::UpdateBondStrain                                            :189-307
+ *   CVXS_BondInternal::AddDampForces                                               :310-346
+ *   CVXS_BondCollision::CalcContactForce  evosoro/_voxcad/Voxelyze/VXS_BondCollision.cpp:41-59
+ *   CVXS_Voxel::EulerStep              evosoro/_voxcad/Voxelyze/VXS_Voxel.cpp:169-427
+ *   CVXS_Voxel::CalcTotalForce / CalcTotalMoment / CalcFloorEffect                 :482-758
+ *   CQuat / Vec3D helpers              evosoro/_voxcad/Voxelyze/Utils/Vec3D.h:185-314
+ * within the feature set SURVEY.md Appendix A lists (linear materials, no volume effects, no
+ * plasticity, no max-velocity clamp, no equilibrium mode).  The land/water fork's scale law
+ * (evosoro/_voxcad_land_water/Voxelyze/VXS_Voxel.cpp:211-235) is selected by VXG_F_LW_SCALE.
+ *
+ * Not part of the product: nothing under evosoro_b200/ or include/ references this file.
+ */
+#include "vx_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define PI_REF 3.14159265358979                 /* Vec3D.h:21 */
+#define HYST 1.1                                /* VEC3D_HYSTERESIS_FACTOR Vec3D.h:22 */
+#define DISCARD_ANGLE_RAD 1e-7                  /* Vec3D.h:48 */
+#define SMALL_ANGLE_RAD 1.732e-2                /* Vec3D.h:49 */
+#define W_THRESH_ACOS2SQRT 0.9988               /* Vec3D.h:50 */
+#define SA_BOND_BEND_RAD 0.05                   /* VXS_BondInternal.h:23 */
+#define SA_BOND_EXT_PERC 1.30                   /* VXS_BondInternal.h:26 */
+
+typedef struct { double x, y, z; } v3;
+typedef struct { double w, x, y, z; } q4;
+
+struct vxo_sim {
+    int n_vox, n_bond, n_col;
+    vxg_sim_params sim;
+    vxg_vox_class* vc;  int n_vc;
+    vxg_bond_class* bc; int n_bc;
+    int *vcls, *bv1, *bv2, *bax, *bcls;
+    int (*link)[6];            /* InternalBondIndices[6] in BD_PX,NX,PY,NY,PZ,NZ order; -1 none */
+    v3* nom;
+    /* voxel state */
+    v3 *pos, *linmom, *angmom;
+    q4* ang;
+    double *scale, *last_scale;
+    int* sfric;
+    /* bond state + outputs */
+    int* small;
+    v3 *lp2, *la1, *la2;
+    v3 *f1, *f2, *m1, *m2;
+    double* strain;
+    /* contact bonds */
+    int *cv1, *cv2; double* ca1; v3 *cf1, *cf2;
+    double cur_time, dt;
+    int64_t step;
+    int diverged;
+    double small_w, smallish_w, slthresh;
+};
+
+static v3 V(double x, double y, double z) { v3 r = {x, y, z}; return r; }
+static v3 vscale(v3 a, double f) { return V(f * a.x, f * a.y, f * a.z); }          /* Vec3D::operator*(T)  Vec3D.h:83 */
+static v3 vadd(v3 a, v3 b) { return V(a.x + b.x, a.y + b.y, a.z + b.z); }
+static v3 vsub(v3 a, v3 b) { return V(a.x - b.x, a.y - b.y, a.z - b.z); }
+static v3 vneg(v3 a) { return V(-a.x, -a.y, -a.z); }
+static v3 vdiv(v3 a, double f) { double inv = 1.0 / f; return V(inv * a.x, inv * a.y, inv * a.z); } /* Vec3D.h:85 */
+
+/* CQuat::operator*  Vec3D.h:193 */
+static q4 qmul(q4 a, q4 f) {
+    q4 r;
+    r.w = a.w * f.w - a.x * f.x - a.y * f.y - a.z * f.z;
+    r.x = a.w * f.x + a.x * f.w + a.y * f.z - a.z * f.y;
+    r.y = a.w * f.y - a.x * f.z + a.y * f.w + a.z * f.x;
+    r.z = a.w * f.z + a.x * f.y - a.y * f.x + a.z * f.w;
+    return r;
+}
+static q4 qconj(q4 a) { q4 r = {a.w, -a.x, -a.y, -a.z}; return r; }
+
+/* CQuat::RotateVec3DInv  Vec3D.h:300-314 */
+static v3 qrot_inv(q4 q, v3 f) {
+    double tw = q.x * f.x + q.y * f.y + q.z * f.z;
+    double tx = q.w * f.x - q.y * f.z + q.z * f.y;
+    double ty = q.w * f.y + q.x * f.z - q.z * f.x;
+    double tz = q.w * f.z - q.x * f.y + q.y * f.x;
+    return V(tw * q.x + tx * q.w + ty * q.z - tz * q.y, tw * q.y - tx * q.z + ty * q.w + tz * q.x,
+             tw * q.z + tx * q.y - ty * q.x + tz * q.w);
+}
+
+/* CQuat::ToRotationVector  Vec3D.h:270-285 */
+static v3 q_to_rotvec(const vxo_sim* s, q4 q) {
+    double sl = 1.0 - q.w * q.w;
+    if (sl <= 0) return V(0, 0, 0);
+    else if (sl < s->slthresh) {
+        double f = sqrt((2 - 2 * (q.w > 1 ? 1 : q.w)) / sl);
+        return vscale(vscale(V(q.x, q.y, q.z), 2.0), f);
+    } else {
+        double ac = acos(q.w > 1 ? 1 : q.w);
+        return vdiv(vscale(vscale(V(q.x, q.y, q.z), 2.0), ac), sqrt(sl));
+    }
+}
+
+/* CQuat::FromAngleToPosX  Vec3D.h:208-237 (quaternion starts as identity, Vec3D.h:161,175) */
+static q4 q_from_angle_to_posx(v3 from) {
+    q4 q = {1, 0, 0, 0};
+    if (from.x == 0 && from.y == 0 && from.z == 0) return q;
+    double yox = from.y / from.x, zox = from.z / from.x;
+    if (yox < SMALL_ANGLE_RAD && yox > -SMALL_ANGLE_RAD && zox < SMALL_ANGLE_RAD && zox > -SMALL_ANGLE_RAD) {
+        q.x = 0; q.y = 0.5 * zox; q.z = -0.5 * yox;
+        q.w = 1 + 0.5 * (-q.y * q.y - q.z * q.z);
+        return q;
+    }
+    v3 n = from;
+    { /* Vec3D::NormalizeFast Vec3D.h:110 */
+        double l = sqrt(n.x * n.x + n.y * n.y + n.z * n.z);
+        if (l > 0) { double li = 1.0 / l; n.x *= li; n.y *= li; n.z *= li; }
+    }
+    double theta = acos(n.x);
+    if (theta > PI_REF - DISCARD_ANGLE_RAD) { q.w = 0; q.x = 0; q.y = 1; q.z = 0; return q; }
+    double ami = 1.0 / sqrt(n.z * n.z + n.y * n.y);
+    double a = 0.5 * theta;
+    double sn = sin(a);
+    q.w = cos(a); q.x = 0; q.y = n.z * ami * sn; q.z = -n.y * ami * sn;
+    return q;
+}
+
+/* CVX_Bond::ToXDirBond / ToOrigDirBond  VX_Bond.h:45-48 */
+static v3 to_xdir(int ax, v3 v) {
+    if (ax == 1) { double t = v.x; v.x = v.y; v.y = -t; }
+    else if (ax == 2) { double t = v.x; v.x = v.z; v.z = -t; }
+    return v;
+}
+static q4 to_xdir_q(int ax, q4 q) {
+    if (ax == 1) { double t = q.x; q.x = q.y; q.y = -t; }
+    else if (ax == 2) { double t = q.x; q.x = q.z; q.z = -t; }
+    return q;
+}
+static v3 to_origdir(int ax, v3 v) {
+    if (ax == 1) { double t = v.y; v.y = v.x; v.x = -t; }
+    else if (ax == 2) { double t = v.z; v.z = v.x; v.x = -t; }
+    return v;
+}
+
+vxo_sim* vxo_create(const vxg_robot_desc* d) {
+    vxo_sim* s = (vxo_sim*)calloc(1, sizeof(vxo_sim));
+    int nv = d->n_vox, nb = d->n_bond;
+    s->n_vox = nv; s->n_bond = nb; s->sim = d->sim;
+    s->n_vc = d->n_vclass; s->n_bc = d->n_bclass;
+    s->vc = (vxg_vox_class*)malloc(sizeof(vxg_vox_class) * (size_t)(d->n_vclass > 0 ? d->n_vclass : 1));
+    s->bc = (vxg_bond_class*)malloc(sizeof(vxg_bond_class) * (size_t)(d->n_bclass > 0 ? d->n_bclass : 1));
+    memcpy(s->vc, d->vclasses, sizeof(vxg_vox_class) * (size_t)d->n_vclass);
+    if (d->n_bclass) memcpy(s->bc, d->bclasses, sizeof(vxg_bond_class) * (size_t)d->n_bclass);
+#define AL(T, n) (T*)calloc((size_t)((n) > 0 ? (n) : 1), sizeof(T))
+    s->vcls = AL(int, nv); s->bv1 = AL(int, nb); s->bv2 = AL(int, nb); s->bax = AL(int, nb); s->bcls = AL(int, nb);
+    s->link = (int(*)[6])calloc((size_t)(nv > 0 ? nv : 1), sizeof(int[6]));
+    s->nom = AL(v3, nv); s->pos = AL(v3, nv); s->linmom = AL(v3, nv); s->angmom = AL(v3, nv); s->ang = AL(q4, nv);
+    s->scale = AL(double, nv); s->last_scale = AL(double, nv); s->sfric = AL(int, nv);
+    s->small = AL(int, nb); s->lp2 = AL(v3, nb); s->la1 = AL(v3, nb); s->la2 = AL(v3, nb);
+    s->f1 = AL(v3, nb); s->f2 = AL(v3, nb); s->m1 = AL(v3, nb); s->m2 = AL(v3, nb); s->strain = AL(double, nb);
+    for (int i = 0; i < nv; i++) {
+        s->vcls[i] = d->vox_class[i];
+        s->nom[i] = V(d->nom_pos[3 * i], d->nom_pos[3 * i + 1], d->nom_pos[3 * i + 2]);
+        for (int k = 0; k < 6; k++) s->link[i][k] = -1;
+        /* CVXS_Voxel::ResetVoxel  VXS_Voxel.cpp:95-135 */
+        s->pos[i] = s->nom[i];
+        s->ang[i].w = 1.0;
+        s->scale[i] = s->last_scale[i] = s->vc[s->vcls[i]].nom_size;
+    }
+    for (int j = 0; j < nb; j++) {
+        s->bv1[j] = d->bond_v1[j]; s->bv2[j] = d->bond_v2[j]; s->bax[j] = d->bond_axis[j]; s->bcls[j] = d->bond_class[j];
+        /* CreatePermBond VX_Sim.cpp:738-748: negative-side voxel gets BD_P*, positive-side BD_N* */
+        s->link[s->bv1[j]][2 * s->bax[j]] = j;
+        s->link[s->bv2[j]][2 * s->bax[j] + 1] = j;
+        s->small[j] = 1; /* ResetBond VXS_BondInternal.cpp:43 */
+    }
+    /* Vec3D.h:57-60 */
+    s->small_w = cos(SMALL_ANGLE_RAD * 0.5);
+    s->smallish_w = cos(HYST * SMALL_ANGLE_RAD * 0.5);
+    s->slthresh = 1.0 - W_THRESH_ACOS2SQRT * W_THRESH_ACOS2SQRT;
+    s->cur_time = 0; s->dt = 0; s->step = 0; /* ClearAll VX_Sim.cpp:373, ResetSimulation :853-854 */
+    return s;
+}
+
+void vxo_destroy(vxo_sim* s) {
+    if (!s) return;
+    free(s->vc); free(s->bc); free(s->vcls); free(s->bv1); free(s->bv2); free(s->bax); free(s->bcls); free(s->link);
+    free(s->nom); free(s->pos); free(s->linmom); free(s->angmom); free(s->ang); free(s->scale); free(s->last_scale);
+    free(s->sfric); free(s->small); free(s->lp2); free(s->la1); free(s->la2); free(s->f1); free(s->f2); free(s->m1);
+    free(s->m2); free(s->strain); free(s->cv1); free(s->cv2); free(s->ca1); free(s->cf1); free(s->cf2);
+    free(s);
+}
+
+void vxo_set_collision_pairs(vxo_sim* s, int n, const int32_t* v1, const int32_t* v2, const double* a1) {
+    free(s->cv1); free(s->cv2); free(s->ca1); free(s->cf1); free(s->cf2);
+    s->n_col = n;
+    s->cv1 = AL(int, n); s->cv2 = AL(int, n); s->ca1 = AL(double, n); s->cf1 = AL(v3, n); s->cf2 = AL(v3, n);
+    for (int i = 0; i < n; i++) { s->cv1[i] = v1[i]; s->cv2[i] = v2[i]; s->ca1[i] = a1[i]; }
+}
+
+/* CVXS_BondInternal::CalcLinForce (+UpdateBondStrain, AddDampForces) */
+static void bond_update(vxo_sim* s, int j) {
+    const vxg_bond_class* c = &s->bc[s->bcls[j]];
+    int ax = s->bax[j], i1 = s->bv1[j], i2 = s->bv2[j];
+    v3 rel = to_xdir(ax, vsub(s->pos[i2], s->pos[i1]));                 /* :58, :61 */
+    q4 a1 = to_xdir_q(ax, s->ang[i1]), a2 = to_xdir_q(ax, s->ang[i2]);  /* :59-63 */
+    v3 r = qrot_inv(a1, rel);                                           /* :65 */
+    q4 na2 = qmul(qconj(a1), a2);                                       /* :66 */
+    double nom = (s->scale[i1] + s->scale[i2]) * 0.5;                   /* :71 */
+
+    int changed = 0;                                                    /* :74-78 */
+    double small_turn = (fabs(r.z) + fabs(r.y)) / r.x;
+    double ext = r.x / nom;
+    if (!s->small[j] && na2.w > s->small_w && small_turn < SA_BOND_BEND_RAD && ext < SA_BOND_EXT_PERC) { s->small[j] = 1; changed = 1; }
+    else if (s->small[j] && (!(na2.w > s->smallish_w) || small_turn > HYST * SA_BOND_BEND_RAD || ext > HYST * SA_BOND_EXT_PERC)) { s->small[j] = 0; changed = 1; }
+
+    q4 tot; v3 p2, an1, an2;
+    if (s->small[j]) {                                                  /* :87-95 */
+        an1 = V(0, 0, 0);
+        an2 = q_to_rotvec(s, na2);
+        r.x -= nom;
+        p2 = r;
+        tot = qconj(a1);
+    } else {                                                            /* :101-118 */
+        q4 pa = q_from_angle_to_posx(r);
+        tot = qmul(pa, qconj(a1));
+        double len = sqrt(rel.x * rel.x + rel.y * rel.y + rel.z * rel.z);
+        p2 = V(len - nom, 0, 0);
+        an1 = q_to_rotvec(s, pa);
+        an2 = q_to_rotvec(s, qmul(tot, a2));
+    }
+
+    /* UpdateBondStrain(_Pos2.x/L.x)  :120, :189-307 with MDL_LINEAR stress (VX_Object.cpp:1472-1482) */
+    double strain = p2.x / c->len, stress;
+    s->strain[j] = strain;
+    if (c->homogeneous) stress = c->e1 * strain;                        /* :206 */
+    else {                                                              /* :226-258 */
+        double sv1 = strain, sv2 = strain;
+        double st1 = c->e1 * sv1, st2 = c->e2 * sv2;
+        int count = 0;
+        double diff = (st1 >= st2) ? st1 - st2 : st2 - st1;
+        double sum = st1 + st2; if (sum < 0) sum = -sum;
+        while (diff > sum * .0005 && count < 3) {
+            sv1 = 2 * st2 / (st1 + st2) * sv1;
+            sv2 = 2 * st1 / (st1 + st2) * sv2;
+            st1 = c->e1 * sv1; st2 = c->e2 * sv2;
+            diff = (st1 >= st2) ? st1 - st2 : st2 - st1;
+            sum = st1 + st2; if (sum < 0) sum = -sum;
+            count++;
+        }
+        stress = (st1 + st2) / 2;
+    }
+
+    /* beam equations :127-128, :153-154  (CSArea1 == CSArea2 == s^2: VXS_Voxel.cpp:625-631, VXS_Bond.cpp:72) */
+    v3 F1 = V(stress * (c->area + c->area) / 2, c->b1 * p2.y - c->b2 * (an1.z + an2.z), c->b1 * p2.z + c->b2 * (an1.y + an2.y));
+    v3 F2 = vneg(F1);
+    v3 M1 = V(c->a2 * (an1.x - an2.x), c->b2 * p2.z + c->b3 * (2 * an1.y + an2.y), -c->b2 * p2.y + c->b3 * (2 * an1.z + an2.z));
+    v3 M2 = V(c->a2 * (an2.x - an1.x), c->b2 * p2.z + c->b3 * (an1.y + 2 * an2.y), -c->b2 * p2.y + c->b3 * (an1.z + 2 * an2.z));
+
+    if (!changed) {                                                     /* :157, AddDampForces :310-346 */
+        if (s->dt != 0) {
+            double bz = 0.5 * s->sim.bond_damp_z;
+            double dti = 1.0 / s->dt;
+            v3 rv2 = vscale(vsub(p2, s->lp2[j]), dti);
+            v3 ra1 = vscale(vsub(an1, s->la1[j]), dti);
+            v3 ra2 = vscale(vsub(an2, s->la2[j]), dti);
+            F1 = vadd(F1, vscale(V(c->c_a1m1 * rv2.x, c->c_b1m1 * rv2.y - c->c_b2fm1 * (ra1.z + ra2.z),
+                                   c->c_b1m1 * rv2.z + c->c_b2fm1 * (ra1.y + ra2.y)), bz));
+            if (!c->homogeneous)
+                F2 = vadd(F2, vscale(V(-c->c_a1m2 * rv2.x, -c->c_b1m2 * rv2.y + c->c_b2fm2 * (ra1.z + ra2.z),
+                                       -c->c_b1m2 * rv2.z - c->c_b2fm2 * (ra1.y + ra2.y)), bz));
+            M1 = vadd(M1, vscale(V(-c->c_a2i1 * (ra2.x - ra1.x), c->c_b2fm1 * rv2.z + c->c_b3i1 * (2 * ra1.y + ra2.y),
+                                   -c->c_b2fm1 * rv2.y + c->c_b3i1 * (2 * ra1.z + ra2.z)), 0.5 * bz));
+            M2 = vadd(M2, vscale(V(c->c_a2i2 * (ra2.x - ra1.x), c->c_b2fm2 * rv2.z + c->c_b3i2 * (ra1.y + 2 * ra2.y),
+                                   -c->c_b2fm2 * rv2.y + c->c_b3i2 * (ra1.z + 2 * ra2.z)), 0.5 * bz));
+        }
+        s->lp2[j] = p2; s->la1[j] = an1; s->la2[j] = an2;
+    }
+
+    /* back to world frame :161-170 */
+    F1 = qrot_inv(tot, F1);
+    if (!c->homogeneous) F2 = qrot_inv(tot, F2);
+    M1 = qrot_inv(tot, M1);
+    M2 = qrot_inv(tot, M2);
+    F1 = to_origdir(ax, F1);
+    if (c->homogeneous) F2 = vneg(F1); else F2 = to_origdir(ax, F2);
+    M1 = to_origdir(ax, M1);
+    M2 = to_origdir(ax, M2);
+    s->f1[j] = F1; s->f2[j] = F2; s->m1[j] = M1; s->m2[j] = M2;
+}
+
+/* CVXS_BondCollision::CalcContactForce  VXS_BondCollision.cpp:41-59 */
+static void col_update(vxo_sim* s, int k) {
+    v3 p2 = vsub(s->pos[s->cv2[k]], s->pos[s->cv1[k]]);
+    double nomd = (s->scale[s->cv1[k]] + s->scale[s->cv2[k]]) * 0.75;
+    double len = sqrt(p2.x * p2.x + p2.y * p2.y + p2.z * p2.z);
+    double rel = nomd - len;
+    if (rel > 0) {
+        s->cf2[k] = vscale(vscale(vdiv(p2, len), s->ca1[k]), rel);
+        s->cf1[k] = vneg(s->cf2[k]);
+    } else { s->cf2[k] = V(0, 0, 0); s->cf1[k] = V(0, 0, 0); }
+}
+
+/* CVXS_Voxel::EulerStep  VXS_Voxel.cpp:169-427 */
+static void voxel_step(vxo_sim* s, int i) {
+    const vxg_vox_class* c = &s->vc[s->vcls[i]];
+    const vxg_sim_params* P = &s->sim;
+    double dt = s->dt;
+    int dof = c->dof_fixed;
+    if ((dof & VXG_DOF_ALL) == VXG_DOF_ALL) {                           /* :174-179 */
+        s->linmom[i] = V(0, 0, 0);
+        s->pos[i] = vadd(s->nom[i], V(c->ext_disp[0], c->ext_disp[1], c->ext_disp[2]));
+        s->angmom[i] = V(0, 0, 0);
+        { /* FromRotationVector Vec3D.h:203-207 */
+            v3 axv = V(c->ext_tdisp[0], c->ext_tdisp[1], c->ext_tdisp[2]);
+            double l = sqrt(axv.x * axv.x + axv.y * axv.y + axv.z * axv.z);
+            if (l > 0) { axv.x /= l; axv.y /= l; axv.z /= l; }
+            double a = l * 0.5, sn = sin(a), cs = cos(a);
+            s->ang[i].w = cs; s->ang[i].x = axv.x * sn; s->ang[i].y = axv.y * sn; s->ang[i].z = axv.z * sn;
+        }
+    } else {
+        /* CalcTotalForce :482-651 */
+        v3 vel = vscale(s->linmom[i], c->mass_inv);                     /* Vel of the previous step, :415 */
+        v3 F = V(0, 0, 0);
+        F = vadd(F, vscale(vscale(vel, -P->slow_damp_z), c->damp_lin)); /* :487 */
+        for (int k = 0; k < 6; k++) {                                   /* :496-501 */
+            int j = s->link[i][k];
+            if (j < 0) continue;
+            F = vadd(F, (k % 2) ? s->f2[j] : s->f1[j]);
+        }
+        if (P->flags & VXG_F_COLLISIONS)                                 /* :516-528 */
+            for (int k = 0; k < s->n_col; k++) {
+                if (s->cv2[k] == i) F = vadd(F, s->cf2[k]);
+                else if (s->cv1[k] == i) F = vadd(F, s->cf1[k]);
+            }
+        F = vsub(F, V(0, 0, 0));                                        /* InputForce :531 */
+        if (!(P->flags & VXG_F_FLUID)) F.z += c->mass * P->grav_acc;    /* :536 (grav_acc == 0 when disabled) */
+        F = vadd(F, V(c->ext_force[0], c->ext_force[1], c->ext_force[2])); /* :540 */
+        if ((P->flags & VXG_F_FLOOR) && !(P->flags & VXG_F_FLUID)) {    /* :635-639, CalcFloorEffect :708-758 */
+            v3 FF = V(0, 0, 0);
+            s->sfric[i] = 0;
+            double pen = 0.5 * s->scale[i] - s->pos[i].z;               /* :698 */
+            pen = pen <= 0 ? 0 : pen;
+            if (pen > 0) {
+                double normal = c->k_floor * pen;
+                FF.z += normal;
+                FF.z -= P->col_damp_z * c->damp_lin * vel.z;
+                double sv = sqrt(vel.x * vel.x + vel.y * vel.y);
+                double sva = atan2(vel.y, vel.x);
+                double sf = sqrt(F.x * F.x + F.y * F.y);
+                double dfr = c->mu_dynamic * normal;
+                v3 fric = vneg(V(cos(sva) * dfr, sin(sva) * dfr, 0));
+                if (P->flags & VXG_F_STICKY_FLOOR) { vel.x = 0; vel.y = 0; s->linmom[i].x = 0; s->linmom[i].y = 0; s->sfric[i] = 1; }
+                if (vel.x == 0 && vel.y == 0) {
+                    if (sf < c->mu_static * normal) s->sfric[i] = 1;
+                } else {
+                    if (dfr * dt < c->mass * sv) FF = vadd(FF, fric);
+                    else { s->sfric[i] = 1; s->linmom[i].x = 0; s->linmom[i].y = 0; }
+                }
+            }
+            F = vadd(F, FF);
+            if (s->sfric[i]) { F.x = 0; F.y = 0; }
+        }
+        /* :184-197 */
+        s->linmom[i] = vadd(s->linmom[i], vscale(F, dt));
+        v3 disp = vscale(s->linmom[i], dt * c->mass_inv);
+        s->pos[i] = vadd(s->pos[i], disp);
+        if (dof & VXG_DOF_X) { s->pos[i].x = s->nom[i].x + c->ext_disp[0]; s->linmom[i].x = 0; }
+        if (dof & VXG_DOF_Y) { s->pos[i].y = s->nom[i].y + c->ext_disp[1]; s->linmom[i].y = 0; }
+        if (dof & VXG_DOF_Z) { s->pos[i].z = s->nom[i].z + c->ext_disp[2]; s->linmom[i].z = 0; }
+        /* CalcTotalMoment :653-675 */
+        v3 M = V(0, 0, 0);
+        for (int k = 0; k < 6; k++) {
+            int j = s->link[i][k];
+            if (j < 0) continue;
+            M = vsub(M, (k % 2) ? s->m2[j] : s->m1[j]);
+        }
+        M = vadd(M, V(c->ext_torque[0], c->ext_torque[1], c->ext_torque[2]));
+        if (dof & VXG_DOF_TX) M.x = 0;
+        if (dof & VXG_DOF_TY) M.y = 0;
+        if (dof & VXG_DOF_TZ) M.z = 0;
+        s->angmom[i] = vadd(s->angmom[i], vscale(M, dt));               /* :202 */
+        {
+            double fact = (1 - 10 * P->slow_damp_z * c->inertia_inv * c->damp_ang * dt); /* :206 */
+            s->angmom[i].x *= fact; s->angmom[i].y *= fact; s->angmom[i].z *= fact;
+        }
+        v3 w = vscale(s->angmom[i], c->inertia_inv);                    /* :211 */
+        q4 hq = {0 * 0.5, w.x * 0.5, w.y * 0.5, w.z * 0.5};           /* 0.5 * CQuat(0,w): operator*(T f, CQuat v) Vec3D.h:191 */
+        q4 spin = qmul(hq, s->ang[i]);                                  /* ... * Angle :212 */
+        q4* A = &s->ang[i];
+        A->w += spin.w * dt; A->x += spin.x * dt; A->y += spin.y * dt; A->z += spin.z * dt; /* :214 */
+        {   /* NormalizeFast Vec3D.h:243-246 */
+            double l = sqrt(A->x * A->x + A->y * A->y + A->z * A->z + A->w * A->w);
+            if (l != 0) { double li = 1.0 / l; A->w *= li; A->x *= li; A->y *= li; A->z *= li; }
+            if (A->w >= 1.0) { A->w = 1.0; A->x = 0; A->y = 0; A->z = 0; }
+        }
+        if ((dof & VXG_DOF_TX) && (dof & VXG_DOF_TY) && (dof & VXG_DOF_TZ)) { /* :218-221 */
+            v3 axv = V(c->ext_tdisp[0], c->ext_tdisp[1], c->ext_tdisp[2]);
+            double l = sqrt(axv.x * axv.x + axv.y * axv.y + axv.z * axv.z);
+            if (l > 0) { axv.x /= l; axv.y /= l; axv.z /= l; }
+            double a = l * 0.5, sn = sin(a), cs = cos(a);
+            A->w = cs; A->x = axv.x * sn; A->y = axv.y * sn; A->z = axv.z * sn;
+            s->angmom[i] = V(0, 0, 0);
+        }
+    }
+    /* SCALE */
+    if (P->flags & VXG_F_LW_SCALE) {                                    /* LW/VXS_Voxel.cpp:211-235 */
+        double tf = 1.0;
+        if ((P->flags & VXG_F_TEMPERATURE) && s->cur_time >= P->init_cm_time)
+            tf = (1 + (P->temp_amplitude * sin(2 * 3.1415926f * (s->cur_time / P->temp_period + c->phase_offset))) * c->cte);
+        if (tf < P->min_scale_fact) tf = P->min_scale_fact;
+        s->scale[i] = tf * c->nom_size;
+    } else {                                                            /* VXS_Voxel.cpp:224-336, in-scope subset */
+        double max_scale = P->max_scale_fact * c->nom_size;
+        double min_scale = P->min_scale_fact * c->nom_size;
+        double ctrl = 0;
+        if ((P->flags & VXG_F_TEMPERATURE) && s->cur_time >= P->init_cm_time)
+            ctrl = c->temp_amp_damp * (P->temp_amplitude * sin(2 * 3.1415926f * (s->cur_time / P->temp_period + c->phase_offset))) * c->cte * 1;
+        /* prenatal ramp :237-238 (initialVoxelSize is a float member, so the ratio is not exactly 1) */
+        double cc = (s->cur_time >= 0.5 * P->init_cm_time) ? 1.0 : 2 * s->cur_time / P->init_cm_time;
+        double prenatal = cc * ((c->init_size / c->nom_size) - 1);
+        double cur = ctrl * c->nom_size + (1 + prenatal) * (1 + 0.0) * c->nom_size;  /* :321 */
+        if (cur < s->last_scale[i] && cur < min_scale) cur = s->last_scale[i];
+        if (cur > s->last_scale[i] && cur > max_scale) cur = s->last_scale[i];
+        s->scale[i] = cur;
+        s->last_scale[i] = cur;
+    }
+}
+
+int64_t vxo_step(vxo_sim* s, int64_t n) {
+    int64_t k;
+    for (k = 0; k < n; k++) {
+        if (s->diverged) break;
+        int div = 0;
+        for (int j = 0; j < s->n_bond; j++) {                           /* VX_Sim.cpp:1773-1776 */
+            bond_update(s, j);
+            if (s->strain[j] > 100) div = 1;
+        }
+        if (div) { s->diverged = 1; break; }
+        if (s->sim.flags & VXG_F_COLLISIONS) for (int c = 0; c < s->n_col; c++) col_update(s, c); /* :1786-1788 */
+        s->dt = s->sim.dt;                                              /* :1793 */
+        for (int i = 0; i < s->n_vox; i++) voxel_step(s, i);           /* :1913 */
+        s->cur_time += s->dt;                                           /* :1929 */
+        s->step++;
+    }
+    return k;
+}
+
+int vxo_diverged(const vxo_sim* s) { return s->diverged; }
+double vxo_time(const vxo_sim* s) { return s->cur_time; }
+int64_t vxo_step_count(const vxo_sim* s) { return s->step; }
+
+void vxo_get_state(const vxo_sim* s, vxg_robot_state* o) {
+    for (int i = 0; i < s->n_vox; i++) {
+        if (o->pos) { o->pos[3 * i] = s->pos[i].x; o->pos[3 * i + 1] = s->pos[i].y; o->pos[3 * i + 2] = s->pos[i].z; }
+        if (o->quat) { o->quat[4 * i] = s->ang[i].w; o->quat[4 * i + 1] = s->ang[i].x; o->quat[4 * i + 2] = s->ang[i].y; o->quat[4 * i + 3] = s->ang[i].z; }
+        if (o->lin_mom) { o->lin_mom[3 * i] = s->linmom[i].x; o->lin_mom[3 * i + 1] = s->linmom[i].y; o->lin_mom[3 * i + 2] = s->linmom[i].z; }
+        if (o->ang_mom) { o->ang_mom[3 * i] = s->angmom[i].x; o->ang_mom[3 * i + 1] = s->angmom[i].y; o->ang_mom[3 * i + 2] = s->angmom[i].z; }
+        if (o->scale) o->scale[i] = s->scale[i];
+        if (o->static_fric) o->static_fric[i] = s->sfric[i];
+    }
+    for (int j = 0; j < s->n_bond; j++) {
+        if (o->bond_force1) { o->bond_force1[3 * j] = s->f1[j].x; o->bond_force1[3 * j + 1] = s->f1[j].y; o->bond_force1[3 * j + 2] = s->f1[j].z; }
+        if (o->bond_force2) { o->bond_force2[3 * j] = s->f2[j].x; o->bond_force2[3 * j + 1] = s->f2[j].y; o->bond_force2[3 * j + 2] = s->f2[j].z; }
+        if (o->bond_moment1) { o->bond_moment1[3 * j] = s->m1[j].x; o->bond_moment1[3 * j + 1] = s->m1[j].y; o->bond_moment1[3 * j + 2] = s->m1[j].z; }
+        if (o->bond_moment2) { o->bond_moment2[3 * j] = s->m2[j].x; o->bond_moment2[3 * j + 1] = s->m2[j].y; o->bond_moment2[3 * j + 2] = s->m2[j].z; }
+        if (o->bond_strain) o->bond_strain[j] = s->strain[j];
+        if (o->bond_small_angle) o->bond_small_angle[j] = s->small[j];
+    }
+}
+
+/* CVX_Sim::GetCM  VX_Sim.cpp:2415-2430 */
+void vxo_get_com(const vxo_sim* s, double* com) {
+    double tm = 0; v3 sum = V(0, 0, 0);
+    for (int i = 0; i < s->n_vox; i++) {
+        double m = s->vc[s->vcls[i]].mass;
+        sum = vadd(sum, vscale(s->pos[i], m));
+        tm += m;
+    }
+    sum = vdiv(sum, tm);
+    com[0] = sum.x; com[1] = sum.y; com[2] = sum.z;
+}
+
+/* CVX_Sim::GetNumTouchingFloor  VX_Sim.cpp:2432-2441 */
+int vxo_num_touching_floor(const vxo_sim* s) {
+    int n = 0;
+    for (int i = 0; i < s->n_vox; i++) if (0.5 * s->scale[i] - s->pos[i].z > 0) n++;
+    return n;
+}
+
+double vxo_max_vel(const vxo_sim* s) {
+    double mx = 0;
+    for (int i = 0; i < s->n_vox; i++) {
+        v3 v = vscale(s->linmom[i], s->vc[s->vcls[i]].mass_inv);
+        double l = sqrt(v.x * v.x + v.y * v.y + v.z * v.z);
+        if (l > mx) mx = l;
+    }
+    return mx;
+}
