@@ -1,0 +1,421 @@
+// vx_math.cuh -- per-bond and per-voxel arithmetic of the Voxelyze step, templated on the working
+// precision `Real` (float = production, double = logic-parity mode).  Positions and time are always
+// fp64.  Compiles as CUDA device code (nvcc) and as plain host C++ (tests/_build CPU emulation harness
+// uses it to exercise exactly the arithmetic the kernels run -- the harness is test infrastructure,
+// the product library contains the device instantiation only).
+//
+// What is computed follows the reference (file:line cited per function); HOW it is computed does
+// not: every quantity that is a small difference of O(lattice) numbers (bond extension, shear offsets,
+// relative rotation) is formed from small numbers directly ("delta formulation") so that fp32 keeps
+// ~1e-7 RELATIVE accuracy on strains instead of 1e-7 of the lattice pitch:
+//   * bond vector      = (pos2 - pos1) in fp64, minus the nominal pitch, then narrowed to Real;
+//   * inverse rotation = v + 2(u x (u x v) - w (u x v)) so only the O(angle) correction is rounded;
+//   * |dp| - pitch     = (|dp|^2 - pitch^2) / (|dp| + pitch) expanded in the small offsets;
+//   * rotation vectors = v * 2 sqrt(2/(1+w))  [== 2 sqrt((2-2w)/(1-w^2)), Vec3D.h:279, without the
+//                        cancellation], acos branch via atan2(|v|, w).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#if defined(__CUDACC__)
+#define VX_HD __host__ __device__ __forceinline__
+#else
+#define VX_HD inline
+#endif
+
+namespace vx {
+
+// thresholds of the reference (PREC_MED branch)
+#define VX_SMALL_ANGLE_RAD 1.732e-2      /* Vec3D.h:49 */
+#define VX_DISCARD_ANGLE_RAD 1e-7        /* Vec3D.h:48 */
+#define VX_W_THRESH_ACOS2SQRT 0.9988     /* Vec3D.h:50 */
+#define VX_HYST 1.1                      /* Vec3D.h:22 */
+#define VX_SA_BOND_BEND_RAD 0.05         /* VXS_BondInternal.h:23 */
+#define VX_SA_BOND_EXT_PERC 1.30         /* VXS_BondInternal.h:26 */
+#define VX_PI 3.14159265358979           /* Vec3D.h:21 */
+// sin^2 of the half small-angle thresholds: w > cos(a/2)  <=>  |v|^2 < sin^2(a/2) for unit q, w > 0
+#define VX_SIN2_SMALL 7.4993725238740121e-05      /* sin^2(0.5 * 1.732e-2)            (IsSmallAngle,  Vec3D.h:290) */
+#define VX_SIN2_SMALLISH 9.0741931167803269e-05   /* sin^2(0.5 * 1.1 * 1.732e-2)      (IsSmallishAngle Vec3D.h:291) */
+#define VX_SLTHRESH_ACOS2SQRT 0.0023985599999999385 /* 1 - 0.9988^2                      (Vec3D.h:60) */
+
+template <typename T> struct V3 { T x, y, z; };
+template <typename T> struct Q4 { T w, x, y, z; };
+
+template <typename T> VX_HD V3<T> mk3(T x, T y, T z) { V3<T> r; r.x = x; r.y = y; r.z = z; return r; }
+template <typename T> VX_HD V3<T> operator+(V3<T> a, V3<T> b) { return mk3<T>(a.x + b.x, a.y + b.y, a.z + b.z); }
+template <typename T> VX_HD V3<T> operator-(V3<T> a, V3<T> b) { return mk3<T>(a.x - b.x, a.y - b.y, a.z - b.z); }
+template <typename T> VX_HD V3<T> operator-(V3<T> a) { return mk3<T>(-a.x, -a.y, -a.z); }
+template <typename T> VX_HD V3<T> operator*(V3<T> a, T f) { return mk3<T>(a.x * f, a.y * f, a.z * f); }
+template <typename T> VX_HD V3<T> cross(V3<T> a, V3<T> b) { return mk3<T>(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+template <typename T> VX_HD T dot(V3<T> a, V3<T> b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+VX_HD float vx_sqrt(float x) { return sqrtf(x); }
+VX_HD double vx_sqrt(double x) { return sqrt(x); }
+VX_HD float vx_abs(float x) { return fabsf(x); }
+VX_HD double vx_abs(double x) { return fabs(x); }
+VX_HD float vx_atan2(float y, float x) { return atan2f(y, x); }
+VX_HD double vx_atan2(double y, double x) { return atan2(y, x); }
+VX_HD void vx_sincos(float a, float* s, float* c) {
+#if defined(__CUDA_ARCH__)
+    sincosf(a, s, c);
+#else
+    *s = sinf(a); *c = cosf(a);
+#endif
+}
+VX_HD void vx_sincos(double a, double* s, double* c) {
+#if defined(__CUDA_ARCH__)
+    sincos(a, s, c);
+#else
+    *s = sin(a); *c = cos(a);
+#endif
+}
+VX_HD float vx_rsqrt(float x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrtf(x);
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+VX_HD double vx_rsqrt(double x) { return 1.0 / sqrt(x); }
+
+// bond axis permutation: the bond is evaluated as if it pointed along +X (VX_Bond.h:45-48)
+template <typename T> VX_HD V3<T> to_xdir(int ax, V3<T> v) {
+    if (ax == 1) return mk3<T>(v.y, -v.x, v.z);
+    if (ax == 2) return mk3<T>(v.z, v.y, -v.x);
+    return v;
+}
+template <typename T> VX_HD V3<T> to_origdir(int ax, V3<T> v) {
+    if (ax == 1) return mk3<T>(-v.y, v.x, v.z);
+    if (ax == 2) return mk3<T>(-v.z, v.y, v.x);
+    return v;
+}
+
+// rotate v by unit quaternion (w,u): v + 2 (u x (u x v) + w (u x v))      (CQuat::RotateVec3D Vec3D.h:293-299)
+template <typename T> VX_HD V3<T> rot_delta(T w, V3<T> u, V3<T> v) {
+    V3<T> c = cross(u, v);
+    V3<T> d = cross(u, c) + c * w;
+    return d * (T)2;
+}
+template <typename T> VX_HD V3<T> rotate(T w, V3<T> u, V3<T> v) { return v + rot_delta(w, u, v); }
+
+// quaternion product (CQuat::operator* Vec3D.h:193)
+template <typename T> VX_HD Q4<T> qmul(Q4<T> a, Q4<T> f) {
+    Q4<T> r;
+    r.w = a.w * f.w - a.x * f.x - a.y * f.y - a.z * f.z;
+    r.x = a.w * f.x + a.x * f.w + a.y * f.z - a.z * f.y;
+    r.y = a.w * f.y - a.x * f.z + a.y * f.w + a.z * f.x;
+    r.z = a.w * f.z + a.x * f.y - a.y * f.x + a.z * f.w;
+    return r;
+}
+
+// CQuat::ToRotationVector (Vec3D.h:270-285) in cancellation-free form: the vector part scaled by
+// 2 sqrt(2/(1+w)) (sqrt branch) or 2 atan2(|v|, w)/|v| (acos branch); zero when the vector part is zero.
+template <typename T> VX_HD V3<T> rotvec(Q4<T> q) {
+    T vv = q.x * q.x + q.y * q.y + q.z * q.z;
+    T f;
+    if (!(vv > (T)0)) f = (T)0;
+    else if (vv < (T)VX_SLTHRESH_ACOS2SQRT) { T w = q.w > (T)1 ? (T)1 : q.w; f = (T)2 * vx_sqrt((T)2 / ((T)1 + w)); }
+    else { T l = vx_sqrt(vv); f = (T)2 * vx_atan2(l, q.w) / l; }
+    return mk3<T>(q.x * f, q.y * f, q.z * f);
+}
+
+// CQuat::FromAngleToPosX (Vec3D.h:208-237): quaternion turning `from` onto +X (x component is 0)
+template <typename T> VX_HD Q4<T> from_angle_to_posx(V3<T> from) {
+    Q4<T> q; q.w = (T)1; q.x = (T)0; q.y = (T)0; q.z = (T)0;
+    if (from.x == (T)0 && from.y == (T)0 && from.z == (T)0) return q;
+    T inv = (T)1 / from.x;
+    T yox = from.y * inv, zox = from.z * inv;
+    const T sa = (T)VX_SMALL_ANGLE_RAD;
+    if (yox < sa && yox > -sa && zox < sa && zox > -sa) {
+        q.y = (T)0.5 * zox; q.z = (T)-0.5 * yox;
+        q.w = (T)1 + (T)0.5 * (-q.y * q.y - q.z * q.z);
+        return q;
+    }
+    T rr = from.y * from.y + from.z * from.z;
+    T li = vx_rsqrt(from.x * from.x + rr);
+    T nx = from.x * li;
+    T rad = vx_sqrt(rr);                 // |from| sin(theta)
+    T theta = vx_atan2(rad * li, nx);    // == acos(n.x), well conditioned
+    if (theta > (T)(VX_PI - VX_DISCARD_ANGLE_RAD)) { q.w = 0; q.x = 0; q.y = 1; q.z = 0; return q; }
+    T s, c;
+    vx_sincos((T)0.5 * theta, &s, &c);
+    T k = s / rad;                       // n.{y,z} * AxisMagInv = from.{y,z} / rad
+    q.w = c; q.y = from.z * k; q.z = -from.y * k;
+    return q;
+}
+
+// ---- constants narrowed to the working precision -------------------------------------------------
+template <typename T> struct BondK {   // from vxg_bond_class
+    T a2, b1, b2, b3;
+    T inv_len, area_e1, area_e2;       // 1/L.x ; s^2 * E (stress -> axial force)
+    T e1, e2, area;
+    T nom_dist;                        // pitch along the axis (as Real)
+    T len_minus_dist;                  // L.x - pitch (0 on regular lattices)
+    T c_a1m1, c_a1m2, c_a2i1, c_a2i2, c_b1m1, c_b1m2, c_b2fm1, c_b2fm2, c_b3i1, c_b3i2;
+    int homogeneous;
+};
+
+template <typename T> struct VoxK {    // from vxg_vox_class (+ sim constants folded in)
+    T mass, mass_inv, inertia_inv;
+    T slow_lin;        // SlowDampZ * _2xSqMxExS
+    T floor_damp;      // ColDampZ  * _2xSqMxExS
+    T ang_fact;        // 1 - 10 SlowDampZ I^-1 _2xSqIxExSxSxS dt
+    T k_floor, mu_s, mu_d;
+    T weight_z;        // m g  (0 when gravity is off / fluid)
+    T ext_f[3], ext_t[3];
+    int dof;
+    int has_bc;        // any fixed DOF or external load
+};
+
+template <typename T> struct BondOut {
+    V3<T> f1, f2, m1, m2;   // world frame: force/moment on voxel 1 (negative side) and voxel 2
+    T strain;
+};
+
+template <typename T> struct BondHist {  // _LastPos2, _LastAngle1, _LastAngle2 (VXS_Bond.h:57)
+    V3<T> p2, a1, a2;
+};
+
+// One internal bond.  CVXS_BondInternal::CalcLinForce (VXS_BondInternal.cpp:56-187) with
+// UpdateBondStrain (:189-307, linear materials) and AddDampForces (:310-346).
+//   e        : permuted (pos2 - pos1) minus (pitch,0,0), formed in fp64 by the caller, narrowed to Real
+//   q1, q2   : voxel orientations (already permuted into the bond frame)
+//   dnom     : 0.5 (Scale1 + Scale2) - L.x   (deviation of the rest length from nominal)
+//   small    : in/out SmallAngle flag;  hist: in/out damping history
+//   dt_inv   : 1/dt of the PREVIOUS step (0 on the very first step: no damping, history still stored)
+template <typename T>
+VX_HD void bond_force(const BondK<T>& k, int ax, V3<T> e, Q4<T> q1, Q4<T> q2, T dnom, T half_bond_z, T dt_inv,
+                      bool& small, BondHist<T>& hist, BondOut<T>& out) {
+    const T D = k.nom_dist;
+    V3<T> u1 = mk3<T>(q1.x, q1.y, q1.z);
+    V3<T> dp = mk3<T>(D + e.x, e.y, e.z);
+    // Ang1AlignedRelPos - (pitch,0,0)  (:65): inverse rotation = rotation by (w, -u)
+    V3<T> rr = e + rot_delta<T>(q1.w, -u1, dp);
+    T rx = D + rr.x;
+    // NewAng2 = conj(q1) * q2  (:66)
+    Q4<T> c1; c1.w = q1.w; c1.x = -q1.x; c1.y = -q1.y; c1.z = -q1.z;
+    Q4<T> q12 = qmul(c1, q2);
+    T vv12 = q12.x * q12.x + q12.y * q12.y + q12.z * q12.z;
+    T nomrel = dnom + k.len_minus_dist;      // NomDistance - pitch  (:71)
+    T nom = D + nomrel;
+
+    // small/large angle hysteresis (:74-78)
+    bool changed = false;
+    T inv_rx = (T)1 / rx;
+    T small_turn = (vx_abs(rr.z) + vx_abs(rr.y)) * inv_rx;
+    T ext = rx / nom;
+    bool is_small_w = (q12.w > (T)0) && (vv12 < (T)VX_SIN2_SMALL);
+    bool is_smallish_w = (q12.w > (T)0) && (vv12 < (T)VX_SIN2_SMALLISH);
+    if (!small && is_small_w && small_turn < (T)VX_SA_BOND_BEND_RAD && ext < (T)VX_SA_BOND_EXT_PERC) { small = true; changed = true; }
+    else if (small && (!is_smallish_w || small_turn > (T)(VX_HYST * VX_SA_BOND_BEND_RAD) || ext > (T)(VX_HYST * VX_SA_BOND_EXT_PERC))) { small = false; changed = true; }
+
+    V3<T> p2, an1, an2;
+    Q4<T> back;                               // conj(TotalRot): local -> world rotation
+    if (small) {                              // :87-95
+        an1 = mk3<T>(0, 0, 0);
+        an2 = rotvec(q12);
+        p2 = mk3<T>(rr.x - nomrel, rr.y, rr.z);
+        back = q1;
+    } else {                                  // :101-118
+        Q4<T> pa = from_angle_to_posx(mk3<T>(rx, rr.y, rr.z));
+        // |dp| - pitch without cancellation
+        T d2 = (T)2 * D * e.x + (e.x * e.x + e.y * e.y + e.z * e.z);
+        T len = vx_sqrt(D * D + d2);
+        p2 = mk3<T>(d2 / (len + D) - nomrel, 0, 0);
+        an1 = rotvec(pa);
+        an2 = rotvec(qmul(pa, q12));          // (pa * conj(q1)) * q2
+        Q4<T> cpa; cpa.w = pa.w; cpa.x = -pa.x; cpa.y = -pa.y; cpa.z = -pa.z;
+        back = qmul(q1, cpa);                 // conj(pa * conj(q1))
+    }
+
+    // axial stress (:120, :189-307; MDL_LINEAR: VX_Object.cpp:1472-1482)
+    T strain = p2.x * k.inv_len;
+    out.strain = strain;
+    T fx;
+    if (k.homogeneous) fx = k.area_e1 * strain;
+    else {
+        T sv1 = strain, sv2 = strain;
+        T st1 = k.e1 * sv1, st2 = k.e2 * sv2;
+        int count = 0;
+        T diff = vx_abs(st1 - st2), sum = vx_abs(st1 + st2);
+        while (diff > sum * (T).0005 && count < 3) {
+            T inv = (T)1 / (st1 + st2);
+            sv1 = (T)2 * st2 * inv * sv1;
+            sv2 = (T)2 * st1 * inv * sv2;
+            st1 = k.e1 * sv1; st2 = k.e2 * sv2;
+            diff = vx_abs(st1 - st2); sum = vx_abs(st1 + st2);
+            count++;
+        }
+        fx = (st1 + st2) * (T)0.5 * k.area;
+    }
+
+    // beam equations (:127-128, :153-154)
+    V3<T> F1 = mk3<T>(fx, k.b1 * p2.y - k.b2 * (an1.z + an2.z), k.b1 * p2.z + k.b2 * (an1.y + an2.y));
+    V3<T> F2 = -F1;
+    V3<T> M1 = mk3<T>(k.a2 * (an1.x - an2.x), k.b2 * p2.z + k.b3 * ((T)2 * an1.y + an2.y), -k.b2 * p2.y + k.b3 * ((T)2 * an1.z + an2.z));
+    V3<T> M2 = mk3<T>(k.a2 * (an2.x - an1.x), k.b2 * p2.z + k.b3 * (an1.y + (T)2 * an2.y), -k.b2 * p2.y + k.b3 * (an1.z + (T)2 * an2.z));
+
+    if (!changed) {                           // :157, :310-346
+        if (dt_inv != (T)0) {
+            T bz = half_bond_z;               // 0.5 * BondDampingZ
+            V3<T> rv = (p2 - hist.p2) * dt_inv;
+            V3<T> w1 = (an1 - hist.a1) * dt_inv;
+            V3<T> w2 = (an2 - hist.a2) * dt_inv;
+            F1 = F1 + mk3<T>(k.c_a1m1 * rv.x, k.c_b1m1 * rv.y - k.c_b2fm1 * (w1.z + w2.z), k.c_b1m1 * rv.z + k.c_b2fm1 * (w1.y + w2.y)) * bz;
+            if (!k.homogeneous)
+                F2 = F2 + mk3<T>(-k.c_a1m2 * rv.x, -k.c_b1m2 * rv.y + k.c_b2fm2 * (w1.z + w2.z), -k.c_b1m2 * rv.z - k.c_b2fm2 * (w1.y + w2.y)) * bz;
+            T hz = (T)0.5 * bz;
+            M1 = M1 + mk3<T>(-k.c_a2i1 * (w2.x - w1.x), k.c_b2fm1 * rv.z + k.c_b3i1 * ((T)2 * w1.y + w2.y), -k.c_b2fm1 * rv.y + k.c_b3i1 * ((T)2 * w1.z + w2.z)) * hz;
+            M2 = M2 + mk3<T>(k.c_a2i2 * (w2.x - w1.x), k.c_b2fm2 * rv.z + k.c_b3i2 * (w1.y + (T)2 * w2.y), -k.c_b2fm2 * rv.y + k.c_b3i2 * (w1.z + (T)2 * w2.z)) * hz;
+        }
+        hist.p2 = p2; hist.a1 = an1; hist.a2 = an2;
+    }
+
+    // back to the world frame (:161-170)
+    V3<T> ub = mk3<T>(back.x, back.y, back.z);
+    F1 = to_origdir(ax, rotate<T>(back.w, ub, F1));
+    if (k.homogeneous) F2 = -F1; else F2 = to_origdir(ax, rotate<T>(back.w, ub, F2));
+    M1 = to_origdir(ax, rotate<T>(back.w, ub, M1));
+    M2 = to_origdir(ax, rotate<T>(back.w, ub, M2));
+    out.f1 = F1; out.f2 = F2; out.m1 = M1; out.m2 = M2;
+}
+
+// CVXS_BondCollision::CalcContactForce (VXS_BondCollision.cpp:41-59): force on voxel 2; voxel 1 gets the negative
+template <typename T>
+VX_HD V3<T> contact_force(V3<T> dp, T scale1, T scale2, T a1) {
+    T nomd = (scale1 + scale2) * (T)0.75;
+    T len = vx_sqrt(dot(dp, dp));
+    T rel = nomd - len;
+    if (rel > (T)0) return dp * (a1 * rel / len);
+    return mk3<T>(0, 0, 0);
+}
+
+// Tail of CQuat::NormalizeFast (Vec3D.h:246): `if (w >= 1) q = identity`.  In fp64 that only fires
+// when the vector part is below ~1e-8 (w rounds to 1); fp32 rounds w to 1 already at |v| < 2.4e-4,
+// where the vector part still carries the whole rotation -- so the fp32 instantiation applies the
+// reference's effective threshold (|v|^2 <= 2^-53) to the vector part and merely clamps w otherwise.
+VX_HD void clamp_unit_w(Q4<double>& a) {
+    if (a.w >= 1.0) { a.w = 1; a.x = 0; a.y = 0; a.z = 0; }
+}
+VX_HD void clamp_unit_w(Q4<float>& a) {
+    if (a.w >= 1.0f) {
+        a.w = 1.0f;
+        if (a.x * a.x + a.y * a.y + a.z * a.z <= 1.1102230e-16f) { a.x = 0; a.y = 0; a.z = 0; }
+    }
+}
+
+template <typename T> struct VoxState {
+    double px, py, pz;      // Pos (fp64 always)
+    Q4<T> q;                // Angle
+    V3<T> lm, am;           // LinMom, AngMom
+};
+
+// One voxel.  CVXS_Voxel::EulerStep (VXS_Voxel.cpp:169-221) with CalcTotalForce (:482-651),
+// CalcFloorEffect (:708-758) and CalcTotalMoment (:653-675).
+//   F, M       : sums over the voxel's bonds (F: + Force{1|2}; M: + Moment{1|2}, negated here as :664-665)
+//   half_scale : 0.5 * Scale of the PREVIOUS step in fp64 (floor penetration :698)
+//   nom        : NominalPosition (only read for fixed DOFs)
+//   returns StaticFricFlag
+template <typename T>
+VX_HD bool voxel_integrate(const VoxK<T>& k, V3<T> F, V3<T> M, double half_scale, bool floor_on, bool sticky,
+                           T dt, const double* nom, const T* ext_disp, const T* ext_tdisp, VoxState<T>& s) {
+    bool sfric = false;
+    if (k.has_bc && (k.dof & 0x3F) == 0x3F) {          // :174-179 fully fixed
+        s.lm = mk3<T>(0, 0, 0); s.am = mk3<T>(0, 0, 0);
+        s.px = nom[0] + (double)ext_disp[0]; s.py = nom[1] + (double)ext_disp[1]; s.pz = nom[2] + (double)ext_disp[2];
+        T l = vx_sqrt(ext_tdisp[0] * ext_tdisp[0] + ext_tdisp[1] * ext_tdisp[1] + ext_tdisp[2] * ext_tdisp[2]);
+        T sn, cs; vx_sincos((T)0.5 * l, &sn, &cs);
+        T il = l > (T)0 ? (T)1 / l : (T)0;
+        s.q.w = cs; s.q.x = ext_tdisp[0] * il * sn; s.q.y = ext_tdisp[1] * il * sn; s.q.z = ext_tdisp[2] * il * sn;
+        return false;
+    }
+    V3<T> vel = s.lm * k.mass_inv;                      // Vel of the previous step (:415)
+    F = F - vel * k.slow_lin;                           // :487
+    F.z += k.weight_z;                                  // :536
+    if (k.has_bc) { F.x += k.ext_f[0]; F.y += k.ext_f[1]; F.z += k.ext_f[2]; }   // :540
+    if (floor_on) {                                     // :635-639, :708-758
+        T pen = (T)(half_scale - s.pz);
+        if (pen > (T)0) {
+            T normal = k.k_floor * pen;
+            T fz_floor = normal - k.floor_damp * vel.z;
+            T sv2 = vel.x * vel.x + vel.y * vel.y;
+            T sf2 = F.x * F.x + F.y * F.y;
+            T dfr = k.mu_d * normal;
+            if (sticky) { vel.x = 0; vel.y = 0; s.lm.x = 0; s.lm.y = 0; sfric = true; }
+            if (vel.x == (T)0 && vel.y == (T)0) {
+                T lim = k.mu_s * normal;
+                if (sf2 < lim * lim) sfric = true;
+            } else {
+                T sv = vx_sqrt(sv2);
+                if (dfr * dt < k.mass * sv) {           // -mu_d N (cos, sin)(atan2(vy, vx)) == -mu_d N v/|v|
+                    T g = dfr / sv;
+                    F.x -= g * vel.x; F.y -= g * vel.y;
+                } else { sfric = true; s.lm.x = 0; s.lm.y = 0; }
+            }
+            F.z += fz_floor;
+        }
+        if (sfric) { F.x = 0; F.y = 0; }
+    }
+    s.lm = s.lm + F * dt;                               // :184
+    T dtm = dt * k.mass_inv;
+    s.px += (double)(s.lm.x * dtm); s.py += (double)(s.lm.y * dtm); s.pz += (double)(s.lm.z * dtm);   // :185,:193
+    M = -M;                                             // :664-665
+    if (k.has_bc) {
+        if (k.dof & 0x01) { s.px = nom[0] + (double)ext_disp[0]; s.lm.x = 0; }   // :195-197
+        if (k.dof & 0x02) { s.py = nom[1] + (double)ext_disp[1]; s.lm.y = 0; }
+        if (k.dof & 0x04) { s.pz = nom[2] + (double)ext_disp[2]; s.lm.z = 0; }
+        M.x += k.ext_t[0]; M.y += k.ext_t[1]; M.z += k.ext_t[2];                 // :669
+        if (k.dof & 0x08) M.x = 0;
+        if (k.dof & 0x10) M.y = 0;
+        if (k.dof & 0x20) M.z = 0;
+    }
+    s.am = (s.am + M * dt) * k.ang_fact;                // :202-207
+    V3<T> hw = s.am * (k.inertia_inv * (T)0.5);         // :211-212  Spin = 0.5 (0,w) * Angle
+    Q4<T> a = s.q;
+    T sw = -hw.x * a.x - hw.y * a.y - hw.z * a.z;
+    T sx = hw.x * a.w + hw.y * a.z - hw.z * a.y;
+    T sy = -hw.x * a.z + hw.y * a.w + hw.z * a.x;
+    T sz = hw.x * a.y - hw.y * a.x + hw.z * a.w;
+    a.w += sw * dt; a.x += sx * dt; a.y += sy * dt; a.z += sz * dt;              // :214
+    T l2 = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;                        // NormalizeFast Vec3D.h:243-246
+    if (l2 != (T)0) { T li = vx_rsqrt(l2); a.w *= li; a.x *= li; a.y *= li; a.z *= li; }
+    clamp_unit_w(a);
+    s.q = a;
+    if (k.has_bc && (k.dof & 0x38) == 0x38) {           // :218-221
+        T l = vx_sqrt(ext_tdisp[0] * ext_tdisp[0] + ext_tdisp[1] * ext_tdisp[1] + ext_tdisp[2] * ext_tdisp[2]);
+        T sn, cs; vx_sincos((T)0.5 * l, &sn, &cs);
+        T il = l > (T)0 ? (T)1 / l : (T)0;
+        s.q.w = cs; s.q.x = ext_tdisp[0] * il * sn; s.q.y = ext_tdisp[1] * il * sn; s.q.z = ext_tdisp[2] * il * sn;
+        s.am = mk3<T>(0, 0, 0);
+    }
+    return sfric;
+}
+
+// Scale law, evaluated once per voxel CLASS per step in fp64 (every voxel of a class has the same
+// Scale history).  _voxcad: VXS_Voxel.cpp:224-336 restricted to the in-scope features (no growth
+// windows); land/water fork: LW/VXS_Voxel.cpp:211-235.  `t` is CurTime BEFORE the increment.
+struct ScaleK {
+    double nom_size, init_size, cte, temp_amp_damp, phase_offset;
+};
+VX_HD double scale_law(const ScaleK& c, double last_scale, double t, double init_cm_time, double temp_period,
+                       double temp_amplitude, double min_fact, double max_fact, bool temp_on, bool lw) {
+    const double two_pi_f = (double)(2 * 3.1415926f);          // the reference's float literal (VXS_Voxel.cpp:302)
+    if (lw) {
+        double tf = 1.0;
+        if (temp_on && t >= init_cm_time) tf = 1 + (temp_amplitude * sin(two_pi_f * (t / temp_period + c.phase_offset))) * c.cte;
+        if (tf < min_fact) tf = min_fact;
+        return tf * c.nom_size;
+    }
+    double ctrl = 0;
+    if (temp_on && t >= init_cm_time)
+        ctrl = c.temp_amp_damp * (temp_amplitude * sin(two_pi_f * (t / temp_period + c.phase_offset))) * c.cte;
+    double cc = (t >= 0.5 * init_cm_time) ? 1.0 : 2 * t / init_cm_time;
+    double prenatal = cc * ((c.init_size / c.nom_size) - 1);
+    double cur = ctrl * c.nom_size + (1 + prenatal) * c.nom_size;
+    if (cur < last_scale && cur < min_fact * c.nom_size) cur = last_scale;
+    if (cur > last_scale && cur > max_fact * c.nom_size) cur = last_scale;
+    return cur;
+}
+
+}  // namespace vx

@@ -1,0 +1,82 @@
+// vx_pack.h -- host-side flattening of a vxg_robot_desc (include/vxgpu.h) into the device layout:
+// class tables narrowed to the working precision and the initial state blob
+// (CVX_Sim::ResetSimulation, VX_Sim.cpp:839-1007; CVXS_Voxel::ResetVoxel, VXS_Voxel.cpp:95-135;
+// CVXS_BondInternal::ResetBond, VXS_BondInternal.cpp:40-54).  Pure host C++ (no CUDA calls).
+#pragma once
+#include <cstring>
+#include "../../include/vxgpu.h"
+#include "vx_robot.cuh"
+
+namespace vx {
+
+template <typename Real>
+inline void pack_classes(const vxg_robot_desc* d, BondK<Real>* bk, double* bk_dist, VoxK<Real>* vk, ScaleK* sk,
+                         double* scale_c, Real* ext_disp, Real* ext_tdisp) {
+    const vxg_sim_params& P = d->sim;
+    for (int i = 0; i < d->n_bclass; i++) {
+        const vxg_bond_class& c = d->bclasses[i];
+        BondK<Real>& k = bk[i];
+        k.a2 = (Real)c.a2; k.b1 = (Real)c.b1; k.b2 = (Real)c.b2; k.b3 = (Real)c.b3;
+        k.inv_len = (Real)(1.0 / c.len); k.area_e1 = (Real)(c.area * c.e1); k.area_e2 = (Real)(c.area * c.e2);
+        k.e1 = (Real)c.e1; k.e2 = (Real)c.e2; k.area = (Real)c.area;
+        k.nom_dist = (Real)c.nom_dist; k.len_minus_dist = (Real)(c.len - c.nom_dist);
+        k.c_a1m1 = (Real)c.c_a1m1; k.c_a1m2 = (Real)c.c_a1m2; k.c_a2i1 = (Real)c.c_a2i1; k.c_a2i2 = (Real)c.c_a2i2;
+        k.c_b1m1 = (Real)c.c_b1m1; k.c_b1m2 = (Real)c.c_b1m2; k.c_b2fm1 = (Real)c.c_b2fm1; k.c_b2fm2 = (Real)c.c_b2fm2;
+        k.c_b3i1 = (Real)c.c_b3i1; k.c_b3i2 = (Real)c.c_b3i2;
+        k.homogeneous = c.homogeneous;
+        bk_dist[i] = c.nom_dist;
+    }
+    const bool fluid = (P.flags & VXG_F_FLUID) != 0;
+    for (int i = 0; i < d->n_vclass; i++) {
+        const vxg_vox_class& c = d->vclasses[i];
+        VoxK<Real>& k = vk[i];
+        k.mass = (Real)c.mass; k.mass_inv = (Real)c.mass_inv; k.inertia_inv = (Real)c.inertia_inv;
+        k.slow_lin = (Real)(P.slow_damp_z * c.damp_lin);                                   // VXS_Voxel.cpp:487
+        k.floor_damp = (Real)(P.col_damp_z * c.damp_lin);                                  // VXS_Voxel.cpp:725
+        k.ang_fact = (Real)(1 - 10 * P.slow_damp_z * c.inertia_inv * c.damp_ang * P.dt);   // VXS_Voxel.cpp:206
+        k.k_floor = (Real)c.k_floor; k.mu_s = (Real)c.mu_static; k.mu_d = (Real)c.mu_dynamic;
+        k.weight_z = fluid ? (Real)0 : (Real)(c.mass * P.grav_acc);                        // VXS_Voxel.cpp:536, LW :357
+        bool bc = c.dof_fixed != 0;
+        for (int a = 0; a < 3; a++) {
+            k.ext_f[a] = (Real)c.ext_force[a]; k.ext_t[a] = (Real)c.ext_torque[a];
+            ext_disp[3 * i + a] = (Real)c.ext_disp[a]; ext_tdisp[3 * i + a] = (Real)c.ext_tdisp[a];
+            if (c.ext_force[a] != 0 || c.ext_torque[a] != 0) bc = true;
+        }
+        k.dof = c.dof_fixed; k.has_bc = bc ? 1 : 0;
+        ScaleK& s = sk[i];
+        s.nom_size = c.nom_size; s.init_size = c.init_size; s.cte = c.cte; s.temp_amp_damp = c.temp_amp_damp; s.phase_offset = c.phase_offset;
+        scale_c[i] = c.nom_size;   // ResetVoxel: Scale = NominalSize (VXS_Voxel.cpp:110)
+    }
+}
+
+template <typename Real>
+inline void pack_blob(const vxg_robot_desc* d, const BlobLayout& L, unsigned char* blob, double* nom) {
+    memset(blob, 0, L.total_bytes);
+    RobotView<Real> R = make_view<Real>(blob, L, d->n_vox);
+    const int nv = R.nv;
+    int16_t* nbr = (int16_t*)R.nbr; uint16_t* bcls = (uint16_t*)R.bcls; uint16_t* vcls = (uint16_t*)R.vcls;
+    for (int i = 0; i < 3 * nv; i++) nbr[i] = -1;
+    for (int i = 0; i < d->n_vox; i++) {
+        for (int a = 0; a < 3; a++) { R.pos[a * nv + i] = d->nom_pos[3 * i + a]; nom[a * nv + i] = d->nom_pos[3 * i + a]; }
+        R.quat[i] = (Real)1;            // Angle = identity (VXS_Voxel.cpp:98)
+        R.flags[i] = VX_FL_SMALL_ALL;   // SmallAngle = true (VXS_BondInternal.cpp:43)
+        vcls[i] = (uint16_t)d->vox_class[i];
+    }
+    for (int j = 0; j < d->n_bond; j++) {   // voxel bond_v1 (negative side) owns the bond
+        int a = d->bond_axis[j], v1 = d->bond_v1[j];
+        nbr[a * nv + v1] = (int16_t)d->bond_v2[j];
+        bcls[a * nv + v1] = (uint16_t)d->bond_class[j];
+    }
+}
+
+inline void init_ctl(const vxg_robot_desc* d, RobotCtl& c) {
+    const vxg_sim_params& P = d->sim;
+    memset(&c, 0, sizeof c);
+    c.cur_time = 0; c.dt = P.dt; c.init_cm_time = P.init_cm_time; c.temp_period = P.temp_period; c.temp_amplitude = P.temp_amplitude;
+    c.min_fact = P.min_scale_fact; c.max_fact = P.max_scale_fact;
+    c.step = 0; c.total_steps = 0x7fffffffffffffffLL; c.latch_step = -1; c.status = 0; c.flags = P.flags;
+    c.n_vox = d->n_vox; c.n_vclass = d->n_vclass; c.n_bclass = d->n_bclass; c.ini_latched = 0;
+    c.half_bond_z = 0.5 * P.bond_damp_z;
+}
+
+}  // namespace vx

@@ -1,0 +1,478 @@
+// vxg_engine.cu -- C-ABI of libvxgpu.so (include/vxgpu.h): batch management, descriptor flattening
+// into the device blob layout, kernel dispatch, state download.  No CPU compute path exists here:
+// every compute entry point fails with VXG_ERR_NO_DEVICE when no CUDA device is present.
+#include <cuda_runtime.h>
+#include <climits>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/vxgpu.h"
+#include "vxg_kernels.cuh"
+#include "vx_pack.h"
+
+using namespace vx;
+
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(VXG_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+static_assert(sizeof(StatsDev) == sizeof(vxg_robot_stats), "StatsDev must mirror vxg_robot_stats");
+
+struct vxg_batch {
+    int device = 0, n_robots = 0, prec = 0;
+    vxg_limits lim{};
+    BlobLayout L{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    // device
+    unsigned char* d_blobs = nullptr;
+    RobotCtl* d_ctl = nullptr;
+    void* d_bk = nullptr; double* d_bk_dist = nullptr; void* d_vk = nullptr; ScaleK* d_sk = nullptr;
+    double* d_scale_c = nullptr; void* d_ext_disp = nullptr; void* d_ext_tdisp = nullptr; double* d_nom = nullptr;
+    void* d_bond_rec = nullptr; StatsDev* d_stats = nullptr;
+    // pinned host mirrors (whole batch, uploaded in one go before the first step after a change)
+    unsigned char* h_blobs = nullptr;
+    RobotCtl* h_ctl = nullptr;
+    unsigned char* h_bk = nullptr; double* h_bk_dist = nullptr; unsigned char* h_vk = nullptr; ScaleK* h_sk = nullptr;
+    double* h_scale_c = nullptr; unsigned char* h_ext_disp = nullptr; unsigned char* h_ext_tdisp = nullptr; double* h_nom = nullptr;
+    StatsDev* h_stats = nullptr;
+    bool dirty = false;          // host mirrors newer than device
+    bool ctl_dirty = false;      // only h_ctl newer (step budget)
+    std::vector<char> uploaded;
+    std::vector<std::vector<int32_t>> bond_v1, bond_v2, bond_axis;   // for download mapping
+    int64_t launches = 0;
+    int vpt = 1, threads = 32;
+    bool smem_mode = true;
+    size_t smem_bytes = 0;
+    size_t rs() const { return prec == VXG_PREC_F64 ? 8 : 4; }
+    size_t bk_sz() const { return prec == VXG_PREC_F64 ? sizeof(BondK<double>) : sizeof(BondK<float>); }
+    size_t vk_sz() const { return prec == VXG_PREC_F64 ? sizeof(VoxK<double>) : sizeof(VoxK<float>); }
+};
+
+extern "C" int vxg_abi_version(void) { return VXG_ABI_VERSION; }
+extern "C" const char* vxg_last_error(void) { return g_err.c_str(); }
+extern "C" int vxg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+// sizes of the ABI structs as compiled, for the ctypes mirror's self-check
+extern "C" int vxg_struct_sizes(int* out, int n) {
+    int v[] = {(int)sizeof(vxg_vox_class), (int)sizeof(vxg_bond_class), (int)sizeof(vxg_sim_params), (int)sizeof(vxg_robot_desc),
+               (int)sizeof(vxg_robot_state), (int)sizeof(vxg_limits), (int)sizeof(vxg_robot_stats)};
+    int m = (int)(sizeof v / sizeof v[0]);
+    for (int i = 0; i < n && i < m; i++) out[i] = v[i];
+    return m;
+}
+
+template <typename Real> static BatchDev<Real> dev_view(const vxg_batch* b) {
+    BatchDev<Real> B;
+    B.blobs = b->d_blobs; B.L = b->L; B.ctl = b->d_ctl;
+    B.bk = (BondK<Real>*)b->d_bk; B.bk_dist = b->d_bk_dist; B.vk = (VoxK<Real>*)b->d_vk; B.sk = b->d_sk;
+    B.scale_c = b->d_scale_c; B.ext_disp = (Real*)b->d_ext_disp; B.ext_tdisp = (Real*)b->d_ext_tdisp; B.nom = b->d_nom;
+    B.bond_rec = (Real*)b->d_bond_rec;
+    B.max_vclass = b->lim.max_vclass; B.max_bclass = b->lim.max_bclass; B.n_robots = b->n_robots;
+    return B;
+}
+
+template <typename Real, int VPT, bool SMEM>
+static cudaError_t launch_step(vxg_batch* b, int n_steps, int record) {
+    auto kern = vx_step_kernel<Real, VPT, SMEM>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes);
+    if (e != cudaSuccess) return e;
+    kern<<<b->n_robots, b->threads, b->smem_bytes, b->stream>>>(dev_view<Real>(b), n_steps, record);
+    return cudaGetLastError();
+}
+
+template <typename Real> static cudaError_t launch_step_p(vxg_batch* b, int n_steps, int record) {
+    if (b->smem_mode) {
+        switch (b->vpt) {
+            case 1: return launch_step<Real, 1, true>(b, n_steps, record);
+            case 2: return launch_step<Real, 2, true>(b, n_steps, record);
+            default: return launch_step<Real, 4, true>(b, n_steps, record);
+        }
+    }
+    switch (b->vpt) {
+        case 1: return launch_step<Real, 1, false>(b, n_steps, record);
+        case 2: return launch_step<Real, 2, false>(b, n_steps, record);
+        default: return launch_step<Real, 4, false>(b, n_steps, record);
+    }
+}
+
+static void free_all(vxg_batch* b) {
+    cudaFree(b->d_blobs); cudaFree(b->d_ctl); cudaFree(b->d_bk); cudaFree(b->d_bk_dist); cudaFree(b->d_vk); cudaFree(b->d_sk);
+    cudaFree(b->d_scale_c); cudaFree(b->d_ext_disp); cudaFree(b->d_ext_tdisp); cudaFree(b->d_nom); cudaFree(b->d_bond_rec);
+    cudaFree(b->d_stats);
+    cudaFreeHost(b->h_blobs); cudaFreeHost(b->h_ctl); cudaFreeHost(b->h_bk); cudaFreeHost(b->h_bk_dist); cudaFreeHost(b->h_vk);
+    cudaFreeHost(b->h_sk); cudaFreeHost(b->h_scale_c); cudaFreeHost(b->h_ext_disp); cudaFreeHost(b->h_ext_tdisp); cudaFreeHost(b->h_nom);
+    cudaFreeHost(b->h_stats);
+    if (b->ev0) cudaEventDestroy(b->ev0);
+    if (b->ev1) cudaEventDestroy(b->ev1);
+    if (b->stream) cudaStreamDestroy(b->stream);
+}
+
+extern "C" int vxg_create(vxg_batch** out, int device, int n_robots, const vxg_limits* lim) {
+    if (!out || !lim || n_robots <= 0) return fail(VXG_ERR_ARG, "vxg_create: bad argument");
+    *out = nullptr;
+    if (lim->max_vox <= 0 || lim->max_vclass <= 0 || lim->max_bclass <= 0) return fail(VXG_ERR_ARG, "vxg_create: limits must be positive");
+    if (lim->precision != VXG_PREC_F32 && lim->precision != VXG_PREC_F64) return fail(VXG_ERR_ARG, "vxg_create: unknown precision");
+    if (lim->max_vox > 32767) return fail(VXG_UNSUPPORTED_SIZE, "vxg_create: more than 32767 voxels per robot");
+    if (lim->max_vclass > 65535 || lim->max_bclass > 65535) return fail(VXG_UNSUPPORTED_SIZE, "vxg_create: too many classes");
+    int ndev = vxg_device_count();
+    if (ndev <= 0) return fail(VXG_ERR_NO_DEVICE, "no CUDA device visible: the engine has no CPU path");
+    if (device < 0 || device >= ndev) return fail(VXG_ERR_ARG, "vxg_create: device %d out of range (%d devices)", device, ndev);
+    CK(cudaSetDevice(device));
+    vxg_batch* b = new vxg_batch;
+    b->device = device; b->n_robots = n_robots; b->lim = *lim; b->prec = lim->precision;
+    b->L = make_layout(lim->max_vox, (int)b->rs());
+    // thread mapping: smallest VPT with <= 512 threads
+    int vpt = 1;
+    while (vpt < 4 && (lim->max_vox + vpt - 1) / vpt > 512) vpt *= 2;
+    if ((lim->max_vox + vpt - 1) / vpt > 512) { delete b; return fail(VXG_UNSUPPORTED_SIZE, "vxg_create: more than 2048 voxels per robot is not supported yet"); }
+    b->vpt = vpt;
+    b->threads = (((lim->max_vox + vpt - 1) / vpt) + 31) & ~31;
+    size_t tb = b->prec == VXG_PREC_F64 ? tables_bytes<double>(lim->max_vclass, lim->max_bclass) : tables_bytes<float>(lim->max_vclass, lim->max_bclass);
+    int max_smem = 0;
+    CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    if (tb > (size_t)max_smem) { delete b; return fail(VXG_UNSUPPORTED_SIZE, "vxg_create: class tables (%zu B) exceed shared memory", tb); }
+    b->smem_mode = b->L.total_bytes + tb <= (size_t)max_smem;
+    b->smem_bytes = b->smem_mode ? b->L.total_bytes + tb : tb;
+
+    size_t nr = (size_t)n_robots, mv = (size_t)lim->max_vclass, mb = (size_t)lim->max_bclass, nv = (size_t)b->L.nv;
+    cudaError_t e = cudaSuccess;
+#define DA(ptr, bytes) if (e == cudaSuccess) { e = cudaMalloc((void**)&(ptr), (bytes)); if (e == cudaSuccess) e = cudaMemset((ptr), 0, (bytes)); }
+#define HA(ptr, bytes) if (e == cudaSuccess) { e = cudaMallocHost((void**)&(ptr), (bytes)); if (e == cudaSuccess) memset((ptr), 0, (bytes)); }
+    DA(b->d_blobs, nr * b->L.total_bytes); DA(b->d_ctl, nr * sizeof(RobotCtl));
+    DA(b->d_bk, nr * mb * b->bk_sz()); DA(b->d_bk_dist, nr * mb * sizeof(double)); DA(b->d_vk, nr * mv * b->vk_sz());
+    DA(b->d_sk, nr * mv * sizeof(ScaleK)); DA(b->d_scale_c, nr * mv * sizeof(double));
+    DA(b->d_ext_disp, nr * mv * 3 * b->rs()); DA(b->d_ext_tdisp, nr * mv * 3 * b->rs()); DA(b->d_nom, nr * 3 * nv * sizeof(double));
+    DA(b->d_stats, nr * sizeof(StatsDev));
+    HA(b->h_blobs, nr * b->L.total_bytes); HA(b->h_ctl, nr * sizeof(RobotCtl));
+    HA(b->h_bk, nr * mb * b->bk_sz()); HA(b->h_bk_dist, nr * mb * sizeof(double)); HA(b->h_vk, nr * mv * b->vk_sz());
+    HA(b->h_sk, nr * mv * sizeof(ScaleK)); HA(b->h_scale_c, nr * mv * sizeof(double));
+    HA(b->h_ext_disp, nr * mv * 3 * b->rs()); HA(b->h_ext_tdisp, nr * mv * 3 * b->rs()); HA(b->h_nom, nr * 3 * nv * sizeof(double));
+    HA(b->h_stats, nr * sizeof(StatsDev));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&b->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&b->ev1);
+    if (e != cudaSuccess) {
+        free_all(b); delete b; cudaGetLastError();
+        return fail(e == cudaErrorMemoryAllocation ? VXG_ERR_NOMEM : VXG_ERR_CUDA, "vxg_create: %s", cudaGetErrorString(e));
+    }
+    b->uploaded.assign(nr, 0);
+    b->bond_v1.resize(nr); b->bond_v2.resize(nr); b->bond_axis.resize(nr);
+    for (size_t r = 0; r < nr; r++) { b->h_ctl[r].status = VXG_ST_FINISHED; b->h_ctl[r].total_steps = 0; }  // empty slots never run
+    b->dirty = true;
+    *out = b;
+    return VXG_OK;
+}
+
+extern "C" void vxg_destroy(vxg_batch* b) {
+    if (!b) return;
+    cudaSetDevice(b->device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    free_all(b);
+    delete b;
+}
+
+template <typename Real> static void fill_classes(vxg_batch* b, int robot, const vxg_robot_desc* d) {
+    size_t mb = (size_t)b->lim.max_bclass, mv = (size_t)b->lim.max_vclass, r = (size_t)robot;
+    pack_classes<Real>(d, (BondK<Real>*)(b->h_bk) + r * mb, b->h_bk_dist + r * mb, (VoxK<Real>*)(b->h_vk) + r * mv,
+                       b->h_sk + r * mv, b->h_scale_c + r * mv, (Real*)(b->h_ext_disp) + r * mv * 3, (Real*)(b->h_ext_tdisp) + r * mv * 3);
+}
+
+template <typename Real> static void reset_blob(vxg_batch* b, int robot, const vxg_robot_desc* d) {
+    pack_blob<Real>(d, b->L, b->h_blobs + (size_t)robot * b->L.total_bytes, b->h_nom + (size_t)robot * 3 * b->L.nv);
+}
+
+extern "C" int vxg_upload(vxg_batch* b, int robot, const vxg_robot_desc* d) {
+    if (!b || !d) return fail(VXG_ERR_ARG, "vxg_upload: null argument");
+    if (robot < 0 || robot >= b->n_robots) return fail(VXG_ERR_ARG, "vxg_upload: robot %d out of range", robot);
+    if (d->n_vox <= 0) return fail(VXG_ERR_ARG, "vxg_upload: robot has no voxels");
+    if (d->n_vox > b->lim.max_vox) return fail(VXG_UNSUPPORTED_SIZE, "vxg_upload: %d voxels > max_vox %d", d->n_vox, b->lim.max_vox);
+    if (d->n_vclass > b->lim.max_vclass || d->n_vclass <= 0) return fail(VXG_UNSUPPORTED_SIZE, "vxg_upload: %d voxel classes (max %d)", d->n_vclass, b->lim.max_vclass);
+    if (d->n_bclass > b->lim.max_bclass) return fail(VXG_UNSUPPORTED_SIZE, "vxg_upload: %d bond classes (max %d)", d->n_bclass, b->lim.max_bclass);
+    if (d->n_bond < 0 || (d->n_bond > 0 && (!d->bond_v1 || !d->bond_v2 || !d->bond_axis || !d->bond_class || !d->bclasses)))
+        return fail(VXG_ERR_ARG, "vxg_upload: bond arrays missing");
+    if (!d->nom_pos || !d->vox_class || !d->vclasses) return fail(VXG_ERR_ARG, "vxg_upload: voxel arrays missing");
+    const vxg_sim_params& P = d->sim;
+    if (P.flags & VXG_F_COLLISIONS) return fail(VXG_UNSUPPORTED_FEATURE, "self-collision contact bonds are not implemented on the device yet");
+    if (P.flags & VXG_F_FLUID) return fail(VXG_UNSUPPORTED_FEATURE, "land/water fluid drag is not implemented on the device yet");
+    if (!(P.dt > 0) || !std::isfinite(P.dt)) return fail(VXG_ERR_ARG, "vxg_upload: dt must be positive");
+    for (int i = 0; i < d->n_vox; i++)
+        if (d->vox_class[i] < 0 || d->vox_class[i] >= d->n_vclass) return fail(VXG_ERR_ARG, "vxg_upload: voxel %d has class %d", i, d->vox_class[i]);
+    {
+        std::vector<char> used((size_t)d->n_vox * 6, 0);
+        for (int j = 0; j < d->n_bond; j++) {
+            int a = d->bond_axis[j], v1 = d->bond_v1[j], v2 = d->bond_v2[j];
+            if (a < 0 || a > 2 || v1 < 0 || v2 < 0 || v1 >= d->n_vox || v2 >= d->n_vox || v1 == v2) return fail(VXG_ERR_ARG, "vxg_upload: bond %d malformed", j);
+            if (d->bond_class[j] < 0 || d->bond_class[j] >= d->n_bclass) return fail(VXG_ERR_ARG, "vxg_upload: bond %d has class %d", j, d->bond_class[j]);
+            if (used[(size_t)v1 * 6 + 2 * a] || used[(size_t)v2 * 6 + 2 * a + 1]) return fail(VXG_ERR_ARG, "vxg_upload: bond %d duplicates a voxel face", j);
+            used[(size_t)v1 * 6 + 2 * a] = 1; used[(size_t)v2 * 6 + 2 * a + 1] = 1;
+        }
+    }
+    for (int i = 0; i < d->n_vclass; i++) {
+        const vxg_vox_class& c = d->vclasses[i];
+        if (!(c.mass > 0) || !(c.inertia > 0) || !(c.nom_size > 0)) return fail(VXG_ERR_ARG, "vxg_upload: voxel class %d has non-positive mass/inertia/size", i);
+    }
+    if (b->prec == VXG_PREC_F64) { fill_classes<double>(b, robot, d); reset_blob<double>(b, robot, d); }
+    else { fill_classes<float>(b, robot, d); reset_blob<float>(b, robot, d); }
+    init_ctl(d, b->h_ctl[robot]);
+    b->bond_v1[robot].assign(d->bond_v1, d->bond_v1 + d->n_bond);
+    b->bond_v2[robot].assign(d->bond_v2, d->bond_v2 + d->n_bond);
+    b->bond_axis[robot].assign(d->bond_axis, d->bond_axis + d->n_bond);
+    b->uploaded[robot] = 1;
+    b->dirty = true;
+    return VXG_OK;
+}
+
+// make the device copy current (host mirrors -> device) on the batch stream
+static int flush(vxg_batch* b) {
+    CK(cudaSetDevice(b->device));
+    size_t nr = (size_t)b->n_robots, mv = (size_t)b->lim.max_vclass, mb = (size_t)b->lim.max_bclass, nv = (size_t)b->L.nv;
+    if (b->dirty) {
+        CK(cudaMemcpyAsync(b->d_blobs, b->h_blobs, nr * b->L.total_bytes, cudaMemcpyHostToDevice, b->stream));
+        CK(cudaMemcpyAsync(b->d_bk, b->h_bk, nr * mb * b->bk_sz(), cudaMemcpyHostToDevice, b->stream));
+        CK(cudaMemcpyAsync(b->d_bk_dist, b->h_bk_dist, nr * mb * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+        CK(cudaMemcpyAsync(b->d_vk, b->h_vk, nr * mv * b->vk_sz(), cudaMemcpyHostToDevice, b->stream));
+        CK(cudaMemcpyAsync(b->d_sk, b->h_sk, nr * mv * sizeof(ScaleK), cudaMemcpyHostToDevice, b->stream));
+        CK(cudaMemcpyAsync(b->d_scale_c, b->h_scale_c, nr * mv * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+        CK(cudaMemcpyAsync(b->d_ext_disp, b->h_ext_disp, nr * mv * 3 * b->rs(), cudaMemcpyHostToDevice, b->stream));
+        CK(cudaMemcpyAsync(b->d_ext_tdisp, b->h_ext_tdisp, nr * mv * 3 * b->rs(), cudaMemcpyHostToDevice, b->stream));
+        CK(cudaMemcpyAsync(b->d_nom, b->h_nom, nr * 3 * nv * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+    }
+    if (b->dirty || b->ctl_dirty) CK(cudaMemcpyAsync(b->d_ctl, b->h_ctl, nr * sizeof(RobotCtl), cudaMemcpyHostToDevice, b->stream));
+    b->dirty = false; b->ctl_dirty = false;
+    return VXG_OK;
+}
+
+// device -> host mirrors (control blocks always; blobs/scales on request); synchronises the stream
+static int pull(vxg_batch* b, bool blobs, int robot) {
+    CK(cudaSetDevice(b->device));
+    size_t nr = (size_t)b->n_robots, mv = (size_t)b->lim.max_vclass;
+    if (!b->dirty) {
+        CK(cudaMemcpyAsync(b->h_ctl, b->d_ctl, nr * sizeof(RobotCtl), cudaMemcpyDeviceToHost, b->stream));
+        if (blobs) {
+            size_t r0 = robot < 0 ? 0 : (size_t)robot, cnt = robot < 0 ? nr : 1;
+            CK(cudaMemcpyAsync(b->h_blobs + r0 * b->L.total_bytes, b->d_blobs + r0 * b->L.total_bytes, cnt * b->L.total_bytes, cudaMemcpyDeviceToHost, b->stream));
+            CK(cudaMemcpyAsync(b->h_scale_c + r0 * mv, b->d_scale_c + r0 * mv, cnt * mv * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+        }
+    }
+    CK(cudaStreamSynchronize(b->stream));
+    return VXG_OK;
+}
+
+extern "C" int vxg_set_step_budget(vxg_batch* b, const int64_t* total_steps, const int64_t* latch_step) {
+    if (!b) return fail(VXG_ERR_ARG, "vxg_set_step_budget: null batch");
+    int rc = pull(b, false, -1);   // keep the device's time/step/status
+    if (rc) return rc;
+    for (int r = 0; r < b->n_robots; r++) {
+        if (!b->uploaded[r]) continue;
+        RobotCtl& c = b->h_ctl[r];
+        if (total_steps) {
+            c.total_steps = total_steps[r] < 0 ? LLONG_MAX : total_steps[r];
+            if (c.step >= c.total_steps) c.status |= VXG_ST_FINISHED; else c.status &= ~VXG_ST_FINISHED;
+        }
+        if (latch_step) c.latch_step = latch_step[r];
+    }
+    b->ctl_dirty = true;
+    return VXG_OK;
+}
+
+extern "C" int vxg_enable_bond_record(vxg_batch* b, int on) {
+    if (!b) return fail(VXG_ERR_ARG, "vxg_enable_bond_record: null batch");
+    CK(cudaSetDevice(b->device));
+    if (on && !b->d_bond_rec) {
+        size_t bytes = (size_t)b->n_robots * 39 * b->L.nv * b->rs();
+        CK(cudaMalloc(&b->d_bond_rec, bytes));
+        CK(cudaMemset(b->d_bond_rec, 0, bytes));
+    } else if (!on && b->d_bond_rec) {
+        CK(cudaStreamSynchronize(b->stream));
+        cudaFree(b->d_bond_rec); b->d_bond_rec = nullptr;
+    }
+    return VXG_OK;
+}
+
+extern "C" int vxg_step(vxg_batch* b, int n_steps) {
+    if (!b) return fail(VXG_ERR_ARG, "vxg_step: null batch");
+    if (n_steps < 0) return fail(VXG_ERR_ARG, "vxg_step: negative step count");
+    for (int r = 0; r < b->n_robots; r++)
+        if (!b->uploaded[r]) return fail(VXG_ERR_STATE, "vxg_step: robot slot %d was never uploaded", r);
+    int rc = flush(b);
+    if (rc) return rc;
+    CK(cudaEventRecord(b->ev0, b->stream));
+    const int chunk = 4096;   // steps per launch: bounds single-kernel run time, state stays resident inside a chunk
+    int left = n_steps;
+    while (left > 0) {
+        int n = left < chunk ? left : chunk;
+        int record = (b->d_bond_rec && n == left) ? 1 : 0;
+        cudaError_t e = b->prec == VXG_PREC_F64 ? launch_step_p<double>(b, n, record) : launch_step_p<float>(b, n, record);
+        if (e != cudaSuccess) return fail(VXG_ERR_CUDA, "vx_step_kernel launch: %s", cudaGetErrorString(e));
+        b->launches++;
+        left -= n;
+    }
+    CK(cudaEventRecord(b->ev1, b->stream));
+    b->timed = true;
+    return VXG_OK;
+}
+
+extern "C" int vxg_sync(vxg_batch* b, uint32_t* status) {
+    if (!b) return fail(VXG_ERR_ARG, "vxg_sync: null batch");
+    int rc = pull(b, false, -1);
+    if (rc) return rc;
+    if (status) for (int r = 0; r < b->n_robots; r++) status[r] = b->h_ctl[r].status;
+    return VXG_OK;
+}
+
+extern "C" int vxg_last_step_ms(vxg_batch* b, float* ms) {
+    if (!b || !ms) return fail(VXG_ERR_ARG, "vxg_last_step_ms: null argument");
+    if (!b->timed) return fail(VXG_ERR_STATE, "vxg_last_step_ms: no step has been issued");
+    CK(cudaSetDevice(b->device));
+    CK(cudaEventSynchronize(b->ev1));
+    CK(cudaEventElapsedTime(ms, b->ev0, b->ev1));
+    return VXG_OK;
+}
+
+extern "C" int64_t vxg_launch_count(vxg_batch* b) { return b ? b->launches : 0; }
+
+extern "C" int vxg_kernel_config(vxg_batch* b, int* threads, int* vpt, int* smem_mode, int64_t* smem_bytes, int64_t* blob_bytes, int64_t* dyn_bytes) {
+    if (!b) return fail(VXG_ERR_ARG, "vxg_kernel_config: null batch");
+    if (threads) *threads = b->threads;
+    if (vpt) *vpt = b->vpt;
+    if (smem_mode) *smem_mode = b->smem_mode ? 1 : 0;
+    if (smem_bytes) *smem_bytes = (int64_t)b->smem_bytes;
+    if (blob_bytes) *blob_bytes = (int64_t)b->L.total_bytes;
+    if (dyn_bytes) *dyn_bytes = (int64_t)b->L.dyn_bytes;
+    return VXG_OK;
+}
+
+template <typename Real> static void unpack_state(vxg_batch* b, int robot, vxg_robot_state* o) {
+    const RobotCtl& c = b->h_ctl[robot];
+    RobotView<Real> R = make_view<Real>(b->h_blobs + (size_t)robot * b->L.total_bytes, b->L, c.n_vox);
+    const int nv = R.nv;
+    const double* sc = b->h_scale_c + (size_t)robot * b->lim.max_vclass;
+    for (int i = 0; i < c.n_vox; i++) {
+        if (o->pos) for (int a = 0; a < 3; a++) o->pos[3 * i + a] = R.pos[a * nv + i];
+        if (o->quat) for (int a = 0; a < 4; a++) o->quat[4 * i + a] = (double)R.quat[a * nv + i];
+        if (o->lin_mom) for (int a = 0; a < 3; a++) o->lin_mom[3 * i + a] = (double)R.lm[a * nv + i];
+        if (o->ang_mom) for (int a = 0; a < 3; a++) o->ang_mom[3 * i + a] = (double)R.am[a * nv + i];
+        if (o->scale) o->scale[i] = sc[R.vcls[i]];
+        if (o->static_fric) o->static_fric[i] = (R.flags[i] & VX_FL_STATIC_FRIC) ? 1 : 0;
+    }
+}
+
+extern "C" int vxg_download_state(vxg_batch* b, int robot, vxg_robot_state* o) {
+    if (!b || !o) return fail(VXG_ERR_ARG, "vxg_download_state: null argument");
+    if (robot < 0 || robot >= b->n_robots || !b->uploaded[robot]) return fail(VXG_ERR_ARG, "vxg_download_state: robot %d not present", robot);
+    int rc = pull(b, true, robot);
+    if (rc) return rc;
+    if (b->prec == VXG_PREC_F64) unpack_state<double>(b, robot, o); else unpack_state<float>(b, robot, o);
+    const int nb = (int)b->bond_v1[robot].size();
+    const bool want_rec = o->bond_force1 || o->bond_force2 || o->bond_moment1 || o->bond_moment2 || o->bond_strain;
+    if (want_rec && nb > 0) {
+        if (!b->d_bond_rec || b->dirty) return fail(VXG_ERR_STATE, "vxg_download_state: bond outputs need vxg_enable_bond_record before the step");
+        const int nv = b->L.nv;
+        size_t bytes = (size_t)39 * nv * b->rs();
+        std::vector<unsigned char> tmp(bytes);
+        CK(cudaMemcpy(tmp.data(), (unsigned char*)b->d_bond_rec + (size_t)robot * bytes, bytes, cudaMemcpyDeviceToHost));
+        for (int j = 0; j < nb; j++) {
+            int a = b->bond_axis[robot][j], v = b->bond_v1[robot][j];
+            double r[13];
+            for (int cidx = 0; cidx < 13; cidx++) {
+                size_t idx = (size_t)(a * 13 + cidx) * nv + v;
+                r[cidx] = b->prec == VXG_PREC_F64 ? ((double*)tmp.data())[idx] : (double)((float*)tmp.data())[idx];
+            }
+            for (int x = 0; x < 3; x++) {
+                if (o->bond_force1) o->bond_force1[3 * j + x] = r[x];
+                if (o->bond_force2) o->bond_force2[3 * j + x] = r[3 + x];
+                if (o->bond_moment1) o->bond_moment1[3 * j + x] = r[6 + x];
+                if (o->bond_moment2) o->bond_moment2[3 * j + x] = r[9 + x];
+            }
+            if (o->bond_strain) o->bond_strain[j] = r[12];
+        }
+    }
+    if (o->bond_small_angle) {
+        const unsigned char* blob = b->h_blobs + (size_t)robot * b->L.total_bytes;
+        const uint32_t* fl = (const uint32_t*)(blob + b->L.off_flags);
+        for (int j = 0; j < nb; j++) o->bond_small_angle[j] = (fl[b->bond_v1[robot][j]] >> b->bond_axis[robot][j]) & 1u;
+    }
+    return VXG_OK;
+}
+
+template <typename Real> static void pack_state(vxg_batch* b, int robot, const vxg_robot_state* in) {
+    const RobotCtl& c = b->h_ctl[robot];
+    RobotView<Real> R = make_view<Real>(b->h_blobs + (size_t)robot * b->L.total_bytes, b->L, c.n_vox);
+    const int nv = R.nv;
+    for (int i = 0; i < c.n_vox; i++) {
+        if (in->pos) for (int a = 0; a < 3; a++) R.pos[a * nv + i] = in->pos[3 * i + a];
+        if (in->quat) for (int a = 0; a < 4; a++) R.quat[a * nv + i] = (Real)in->quat[4 * i + a];
+        if (in->lin_mom) for (int a = 0; a < 3; a++) R.lm[a * nv + i] = (Real)in->lin_mom[3 * i + a];
+        if (in->ang_mom) for (int a = 0; a < 3; a++) R.am[a * nv + i] = (Real)in->ang_mom[3 * i + a];
+    }
+}
+
+extern "C" int vxg_upload_state(vxg_batch* b, int robot, const vxg_robot_state* in, double cur_time, int64_t cur_step) {
+    if (!b || !in) return fail(VXG_ERR_ARG, "vxg_upload_state: null argument");
+    if (robot < 0 || robot >= b->n_robots || !b->uploaded[robot]) return fail(VXG_ERR_ARG, "vxg_upload_state: robot %d not present", robot);
+    int rc = pull(b, true, -1);   // whole batch: the next flush re-uploads every blob
+    if (rc) return rc;
+    if (b->prec == VXG_PREC_F64) pack_state<double>(b, robot, in); else pack_state<float>(b, robot, in);
+    b->h_ctl[robot].cur_time = cur_time;
+    b->h_ctl[robot].step = cur_step;
+    b->dirty = true;
+    return VXG_OK;
+}
+
+extern "C" int vxg_reduce_stats(vxg_batch* b, vxg_robot_stats* out) {
+    if (!b || !out) return fail(VXG_ERR_ARG, "vxg_reduce_stats: null argument");
+    int rc = flush(b);
+    if (rc) return rc;
+    if (b->prec == VXG_PREC_F64) vx_stats_kernel<double><<<b->n_robots, 256, 0, b->stream>>>(dev_view<double>(b), b->d_stats);
+    else vx_stats_kernel<float><<<b->n_robots, 256, 0, b->stream>>>(dev_view<float>(b), b->d_stats);
+    CK(cudaGetLastError());
+    b->launches++;
+    CK(cudaMemcpyAsync(b->h_stats, b->d_stats, (size_t)b->n_robots * sizeof(StatsDev), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    memcpy(out, b->h_stats, (size_t)b->n_robots * sizeof(StatsDev));
+    return VXG_OK;
+}
+
+extern "C" int vxg_set_collision_pairs(vxg_batch* b, int robot, int n_pairs, const int32_t* v1, const int32_t* v2, const double* a1) {
+    (void)b; (void)robot; (void)n_pairs; (void)v1; (void)v2; (void)a1;
+    return fail(VXG_UNSUPPORTED_FEATURE, "self-collision contact bonds are not implemented on the device yet");
+}
+
+extern "C" int vxg_run_batch_host(vxg_batch* b, const vxg_robot_desc* descs, int n_descs, int n_steps, double* pos_out) {
+    if (!b || !descs || n_descs != b->n_robots) return fail(VXG_ERR_ARG, "vxg_run_batch_host: need one descriptor per robot slot");
+    for (int r = 0; r < n_descs; r++) { int rc = vxg_upload(b, r, &descs[r]); if (rc) return rc; }
+    int rc = vxg_step(b, n_steps);
+    if (rc) return rc;
+    if (pos_out) {
+        // positions only: first 3*nv doubles of every blob (strided device -> host copy)
+        size_t w = (size_t)3 * b->L.nv * sizeof(double);
+        CK(cudaMemcpy2DAsync(b->h_blobs, b->L.total_bytes, b->d_blobs, b->L.total_bytes, w, (size_t)b->n_robots, cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaStreamSynchronize(b->stream));
+        const int nv = b->L.nv, mv = b->lim.max_vox;
+        for (int r = 0; r < b->n_robots; r++) {
+            const double* p = (const double*)(b->h_blobs + (size_t)r * b->L.total_bytes);
+            double* o = pos_out + (size_t)r * mv * 3;
+            int n = b->h_ctl[r].n_vox;
+            for (int i = 0; i < n; i++) { o[3 * i] = p[i]; o[3 * i + 1] = p[nv + i]; o[3 * i + 2] = p[2 * nv + i]; }
+        }
+    } else CK(cudaStreamSynchronize(b->stream));
+    return VXG_OK;
+}

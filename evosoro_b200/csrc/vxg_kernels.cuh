@@ -1,0 +1,298 @@
+// vxg_kernels.cuh -- sm_100a kernels of the Voxelyze timestep engine.
+//
+//   vx_step_kernel<Real, VPT, SMEM>  one CTA per robot; advances the robot `n_steps` timesteps.
+//       SMEM = true : the robot blob is staged into shared memory once, all steps run on chip, the
+//                     dynamic section is written back at the end (HBM traffic = blob in + blob out per
+//                     LAUNCH, not per step).
+//       SMEM = false: same code against the blob in global memory (robots larger than ~227 KB of
+//                     state, e.g. the fp64 mode at 10^3); the working set of the 148 resident robots
+//                     lives in L2.
+//       VPT          : voxels per thread (thread t owns voxels t, t+T, ...), so a 10^3 robot runs with
+//                     512 threads x 2 voxels and <=128 registers per thread.
+//   vx_stats_kernel<Real>            one CTA per robot; reductions for the result writer.
+//
+// Replaces CVX_Sim::Integrate (VX_Sim.cpp:1763-1933); see vx_robot.cuh / vx_math.cuh for the
+// per-bond and per-voxel arithmetic and the reference lines they restate.
+#pragma once
+#include <cuda_runtime.h>
+#include "vx_robot.cuh"
+
+namespace vx {
+
+#define VXG_ST_DIVERGED_ 0x1u
+#define VXG_ST_FINISHED_ 0x2u
+#define VXG_F_FLOOR_ 0x0001u
+#define VXG_F_TEMPERATURE_ 0x0002u
+#define VXG_F_LW_SCALE_ 0x0004u
+#define VXG_F_STICKY_FLOOR_ 0x0008u
+#define VXG_F_FLUID_ 0x0010u
+
+template <typename Real> struct BatchDev {
+    unsigned char* blobs;       // [n_robots][L.total_bytes]
+    BlobLayout L;
+    RobotCtl* ctl;              // [n_robots]
+    BondK<Real>* bk;            // [n_robots][max_bclass]
+    double* bk_dist;            // [n_robots][max_bclass]
+    VoxK<Real>* vk;             // [n_robots][max_vclass]
+    ScaleK* sk;                 // [n_robots][max_vclass]
+    double* scale_c;            // [n_robots][max_vclass]  Scale per class as left by the last step
+    Real* ext_disp;             // [n_robots][max_vclass][3]
+    Real* ext_tdisp;            // [n_robots][max_vclass][3]
+    double* nom;                // [n_robots][3][nv]
+    Real* bond_rec;             // [n_robots][39][nv] or nullptr
+    int max_vclass, max_bclass, n_robots;
+};
+
+// shared-memory carve-up after the blob
+template <typename Real> struct SmemTables {
+    BondK<Real>* bk; double* bk_dist; VoxK<Real>* vk; ScaleK* sk;
+    double* scale_c;  // [2][max_vclass]
+    Real* dsc_c;      // [2][max_vclass]
+    Real* ext_disp; Real* ext_tdisp;
+    double* red;      // [4][32] reduction scratch
+};
+
+template <typename Real>
+__host__ __device__ inline size_t tables_bytes(int max_vclass, int max_bclass) {
+    size_t o = 0;
+    o = vx_align16(o + sizeof(BondK<Real>) * max_bclass);
+    o = vx_align16(o + sizeof(double) * max_bclass);
+    o = vx_align16(o + sizeof(VoxK<Real>) * max_vclass);
+    o = vx_align16(o + sizeof(ScaleK) * max_vclass);
+    o = vx_align16(o + sizeof(double) * 2 * max_vclass);
+    o = vx_align16(o + sizeof(Real) * 2 * max_vclass);
+    o = vx_align16(o + sizeof(Real) * 3 * max_vclass);
+    o = vx_align16(o + sizeof(Real) * 3 * max_vclass);
+    o = vx_align16(o + sizeof(double) * 4 * 32);
+    return o;
+}
+
+template <typename Real>
+__device__ inline SmemTables<Real> carve_tables(unsigned char* p, int max_vclass, int max_bclass) {
+    SmemTables<Real> t; size_t o = 0;
+    t.bk = (BondK<Real>*)(p + o);   o = vx_align16(o + sizeof(BondK<Real>) * max_bclass);
+    t.bk_dist = (double*)(p + o);   o = vx_align16(o + sizeof(double) * max_bclass);
+    t.vk = (VoxK<Real>*)(p + o);    o = vx_align16(o + sizeof(VoxK<Real>) * max_vclass);
+    t.sk = (ScaleK*)(p + o);        o = vx_align16(o + sizeof(ScaleK) * max_vclass);
+    t.scale_c = (double*)(p + o);   o = vx_align16(o + sizeof(double) * 2 * max_vclass);
+    t.dsc_c = (Real*)(p + o);       o = vx_align16(o + sizeof(Real) * 2 * max_vclass);
+    t.ext_disp = (Real*)(p + o);    o = vx_align16(o + sizeof(Real) * 3 * max_vclass);
+    t.ext_tdisp = (Real*)(p + o);   o = vx_align16(o + sizeof(Real) * 3 * max_vclass);
+    t.red = (double*)(p + o);
+    return t;
+}
+
+__device__ inline void copy16(void* dst, const void* src, size_t bytes, int tid, int nthreads) {
+    const uint4* s = (const uint4*)src; uint4* d = (uint4*)dst;
+    size_t n = bytes >> 4;
+    for (size_t i = tid; i < n; i += nthreads) d[i] = s[i];
+}
+__device__ inline void copy4(void* dst, const void* src, size_t bytes, int tid, int nthreads) {
+    const uint32_t* s = (const uint32_t*)src; uint32_t* d = (uint32_t*)dst;
+    size_t n = bytes >> 2;
+    for (size_t i = tid; i < n; i += nthreads) d[i] = s[i];
+}
+
+__device__ inline double warp_sum(double x) {
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+
+// block-wide sum of 4 doubles; result valid in every thread. `red` = [4][32] shared doubles.
+__device__ inline void block_sum4(double& a, double& b, double& c, double& d, double* red) {
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c); d = warp_sum(d);
+    __syncthreads();
+    if (lane == 0) { red[wid] = a; red[32 + wid] = b; red[64 + wid] = c; red[96 + wid] = d; }
+    __syncthreads();
+    a = b = c = d = 0;
+    for (int i = 0; i < nw; i++) { a += red[i]; b += red[32 + i]; c += red[64 + i]; d += red[96 + i]; }
+}
+
+template <typename Real, int VPT, bool SMEM>
+__global__ void __launch_bounds__(512, 1) vx_step_kernel(BatchDev<Real> B, int n_steps, int record_bonds) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int robot = blockIdx.x;
+    const int tid = threadIdx.x, T = blockDim.x;
+    RobotCtl* ctlp = B.ctl + robot;
+    const unsigned int status0 = ctlp->status;
+    if (status0 & (VXG_ST_DIVERGED_ | VXG_ST_FINISHED_)) return;
+    const long long step0 = ctlp->step, total = ctlp->total_steps, latch = ctlp->latch_step;
+    long long remaining = total - step0;
+    int nsteps = remaining < (long long)n_steps ? (int)remaining : n_steps;
+    if (nsteps <= 0) { if (tid == 0) ctlp->status = status0 | VXG_ST_FINISHED_; return; }
+
+    const BlobLayout L = B.L;
+    unsigned char* gblob = B.blobs + (size_t)robot * L.total_bytes;
+    unsigned char* base = SMEM ? smem : gblob;
+    unsigned char* tab = SMEM ? smem + L.total_bytes : smem;
+    SmemTables<Real> S = carve_tables<Real>(tab, B.max_vclass, B.max_bclass);
+    const int n_vox = ctlp->n_vox, n_vc = ctlp->n_vclass, n_bc = ctlp->n_bclass;
+    const unsigned int flags = ctlp->flags;
+
+    // ---- stage in ---------------------------------------------------------------------------
+    if (SMEM) {
+        copy16(smem, gblob, L.stat_bytes, tid, T);
+        // zero the accumulators
+        uint4 z = make_uint4(0, 0, 0, 0);
+        uint4* a = (uint4*)(smem + L.off_accb);
+        for (size_t i = tid; i < ((L.total_bytes - L.off_accb) >> 4); i += T) a[i] = z;
+    }
+    copy4(S.bk, B.bk + (size_t)robot * B.max_bclass, sizeof(BondK<Real>) * n_bc, tid, T);
+    copy4(S.vk, B.vk + (size_t)robot * B.max_vclass, sizeof(VoxK<Real>) * n_vc, tid, T);
+    copy4(S.sk, B.sk + (size_t)robot * B.max_vclass, sizeof(ScaleK) * n_vc, tid, T);
+    for (int i = tid; i < n_bc; i += T) S.bk_dist[i] = B.bk_dist[(size_t)robot * B.max_bclass + i];
+    for (int i = tid; i < n_vc; i += T) {
+        S.scale_c[i] = B.scale_c[(size_t)robot * B.max_vclass + i];
+    }
+    for (int i = tid; i < 3 * n_vc; i += T) {
+        S.ext_disp[i] = B.ext_disp[(size_t)robot * B.max_vclass * 3 + i];
+        S.ext_tdisp[i] = B.ext_tdisp[(size_t)robot * B.max_vclass * 3 + i];
+    }
+    __syncthreads();
+    for (int i = tid; i < n_vc; i += T) S.dsc_c[i] = (Real)(S.scale_c[i] - S.sk[i].nom_size);
+    __syncthreads();
+
+    RobotView<Real> R = make_view<Real>(base, L, n_vox);
+    RobotConsts<Real> C;
+    C.bk = S.bk; C.bk_dist = S.bk_dist; C.vk = S.vk;
+    C.nom = B.nom + (size_t)robot * 3 * L.nv;
+    C.ext_disp = S.ext_disp; C.ext_tdisp = S.ext_tdisp;
+    C.half_bond_z = (Real)ctlp->half_bond_z;
+    const double dt = ctlp->dt;
+    C.dt = (Real)dt;
+    const bool fluid = (flags & VXG_F_FLUID_) != 0;
+    C.floor_on = (flags & VXG_F_FLOOR_) && !fluid;
+    C.sticky = (flags & VXG_F_STICKY_FLOOR_) != 0;
+    const bool temp_on = (flags & VXG_F_TEMPERATURE_) != 0, lw = (flags & VXG_F_LW_SCALE_) != 0;
+    const double init_cm = ctlp->init_cm_time, tper = ctlp->temp_period, tamp = ctlp->temp_amplitude;
+    const double minf = ctlp->min_fact, maxf = ctlp->max_fact;
+    const Real dt_inv_run = (Real)(1.0 / dt);
+    Real* rec_base = (record_bonds && B.bond_rec) ? B.bond_rec + (size_t)robot * 39 * L.nv : nullptr;
+
+    double t = ctlp->cur_time;
+    int cur = 0;
+    int done = 0;
+    bool diverged = false;
+    for (int k = 0; k < nsteps; ++k) {
+        const long long s = step0 + k;
+        if (s == latch) {   // IniCM = SS.CurCM at TimeStep entry (VX_Sim.cpp:1064-1075): COM after the previous step
+            double mx = 0, my = 0, mz = 0, mm = 0;
+            for (int v = tid; v < n_vox; v += T) {
+                double m = (double)S.vk[R.vcls[v]].mass;
+                mx += R.pos[v] * m; my += R.pos[R.nv + v] * m; mz += R.pos[2 * R.nv + v] * m; mm += m;
+            }
+            block_sum4(mx, my, mz, mm, S.red);
+            if (tid == 0) { ctlp->ini_com[0] = mx / mm; ctlp->ini_com[1] = my / mm; ctlp->ini_com[2] = mz / mm; ctlp->ini_latched = 1; }
+        }
+        C.scale_c = S.scale_c + cur * B.max_vclass;
+        C.dsc_c = S.dsc_c + cur * B.max_vclass;
+        const Real dt_inv = (s == 0) ? (Real)0 : dt_inv_run;   // dt == 0 during the very first bond pass (VX_Sim.cpp:373)
+        Real* rec = (k == nsteps - 1) ? rec_base : nullptr;
+
+        V3<Real> F[VPT], M[VPT];
+#pragma unroll
+        for (int j = 0; j < VPT; j++) { F[j] = mk3<Real>(0, 0, 0); M[j] = mk3<Real>(0, 0, 0); }
+        int div = 0;
+#pragma unroll 1
+        for (int ax = 0; ax < 3; ax++) {
+#pragma unroll
+            for (int j = 0; j < VPT; j++) {
+                int v = tid + j * T;
+                if (v < n_vox) div |= bond_task<Real>(R, C, v, ax, dt_inv, F[j], M[j], rec) ? 1 : 0;
+            }
+            if (ax < 2) __syncthreads();
+        }
+        if (__syncthreads_or(div)) { diverged = true; break; }   // Integrate() returns before the voxel loop (VX_Sim.cpp:1777)
+
+#pragma unroll
+        for (int j = 0; j < VPT; j++) {
+            int v = tid + j * T;
+            if (v < n_vox) voxel_task<Real>(R, C, v, F[j], M[j]);
+        }
+        // Scale of every class for the next step, from CurTime before the increment (VXS_Voxel.cpp:224-336)
+        for (int i = tid; i < n_vc; i += T) {
+            double last = S.scale_c[cur * B.max_vclass + i];
+            double ns = scale_law(S.sk[i], last, t, init_cm, tper, tamp, minf, maxf, temp_on, lw);
+            S.scale_c[(cur ^ 1) * B.max_vclass + i] = ns;
+            S.dsc_c[(cur ^ 1) * B.max_vclass + i] = (Real)(ns - S.sk[i].nom_size);
+        }
+        __syncthreads();
+        cur ^= 1;
+        t += dt;                                                 // CurTime += dt (VX_Sim.cpp:1929)
+        done = k + 1;
+    }
+
+    // ---- stage out --------------------------------------------------------------------------
+    __syncthreads();
+    if (SMEM) copy16(gblob, smem, L.dyn_bytes, tid, T);
+    for (int i = tid; i < n_vc; i += T) B.scale_c[(size_t)robot * B.max_vclass + i] = S.scale_c[cur * B.max_vclass + i];
+    if (tid == 0) {
+        ctlp->cur_time = t;
+        ctlp->step = step0 + done;
+        unsigned int st = status0;
+        if (diverged) st |= VXG_ST_DIVERGED_;
+        if (step0 + done >= total) st |= VXG_ST_FINISHED_;
+        ctlp->status = st;
+    }
+}
+
+struct StatsDev {   // mirrors vxg_robot_stats
+    double com[3], ini_com[3], max_vel, min_pos[3], max_pos[3], time;
+    long long steps;
+    int n_touching_floor, ini_com_latched;
+};
+
+__device__ inline double warp_max(double x) {
+    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
+    return x;
+}
+
+// CVX_Sim::GetCM (VX_Sim.cpp:2415-2430), GetNumTouchingFloor (:2432-2441), SS.MaxVoxVel (:1511-1690)
+template <typename Real>
+__global__ void __launch_bounds__(256) vx_stats_kernel(BatchDev<Real> B, StatsDev* out) {
+    __shared__ double red[4 * 32];
+    __shared__ double redm[7 * 8];
+    __shared__ int redi[8];
+    const int robot = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    const RobotCtl* ctl = B.ctl + robot;
+    const BlobLayout L = B.L;
+    RobotView<Real> R = make_view<Real>(B.blobs + (size_t)robot * L.total_bytes, L, ctl->n_vox);
+    const VoxK<Real>* vk = B.vk + (size_t)robot * B.max_vclass;
+    const double* scale_c = B.scale_c + (size_t)robot * B.max_vclass;
+    const int nv = R.nv;
+    double mx = 0, my = 0, mz = 0, mm = 0, vmax = 0;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    int touching = 0;
+    for (int v = tid; v < R.n_vox; v += T) {
+        int vc = R.vcls[v];
+        double m = (double)vk[vc].mass;
+        double px = R.pos[v], py = R.pos[nv + v], pz = R.pos[2 * nv + v];
+        mx += px * m; my += py * m; mz += pz * m; mm += m;
+        double vx_ = (double)R.lm[v] * (double)vk[vc].mass_inv, vy_ = (double)R.lm[nv + v] * (double)vk[vc].mass_inv,
+               vz_ = (double)R.lm[2 * nv + v] * (double)vk[vc].mass_inv;
+        vmax = fmax(vmax, sqrt(vx_ * vx_ + vy_ * vy_ + vz_ * vz_));
+        lo[0] = fmin(lo[0], px); lo[1] = fmin(lo[1], py); lo[2] = fmin(lo[2], pz);
+        hi[0] = fmax(hi[0], px); hi[1] = fmax(hi[1], py); hi[2] = fmax(hi[2], pz);
+        if (0.5 * scale_c[vc] - pz > 0) touching++;
+    }
+    block_sum4(mx, my, mz, mm, red);
+    double m7[7] = {vmax, -lo[0], -lo[1], -lo[2], hi[0], hi[1], hi[2]};
+    int lane = tid & 31, wid = tid >> 5, nw = (T + 31) >> 5;
+    for (int i = 0; i < 7; i++) m7[i] = warp_max(m7[i]);
+    for (int o = 16; o > 0; o >>= 1) touching += __shfl_xor_sync(0xffffffffu, touching, o);
+    if (lane == 0) { for (int i = 0; i < 7; i++) redm[i * 8 + wid] = m7[i]; redi[wid] = touching; }
+    __syncthreads();
+    if (tid == 0) {
+        StatsDev s;
+        for (int i = 0; i < 7; i++) { double x = redm[i * 8]; for (int w = 1; w < nw; w++) x = fmax(x, redm[i * 8 + w]); m7[i] = x; }
+        int tc = 0; for (int w = 0; w < nw; w++) tc += redi[w];
+        s.com[0] = mx / mm; s.com[1] = my / mm; s.com[2] = mz / mm;
+        for (int i = 0; i < 3; i++) { s.ini_com[i] = ctl->ini_com[i]; s.min_pos[i] = -m7[1 + i]; s.max_pos[i] = m7[4 + i]; }
+        s.max_vel = m7[0]; s.time = ctl->cur_time; s.steps = ctl->step;
+        s.n_touching_floor = tc; s.ini_com_latched = ctl->ini_latched;
+        out[robot] = s;
+    }
+}
+
+}  // namespace vx

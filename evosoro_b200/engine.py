@@ -1,0 +1,180 @@
+"""ctypes binding of ``libvxgpu.so`` (``include/vxgpu.h``) -- the Python host side of the engine.
+
+Thin by design: every call maps 1:1 onto a C-ABI entry point.  There is no CPU compute path: if the
+CUDA library is missing or no GPU is visible the calls raise ``EngineError`` (loudly) rather than
+falling back to anything.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libvxgpu.so")
+CSRC = os.path.join(_HERE, "csrc")
+_LIB = None
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"vxgpu error {code}: {msg}")
+        self.code = code
+
+
+def build(force: bool = False) -> str:
+    """Compile libvxgpu.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(os.path.dirname(_HERE), "include", "vxgpu.h")]
+    stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if force or stale:
+        subprocess.run(["make", "-C", CSRC] + (["-B"] if force else []), check=True)
+    return LIB_PATH
+
+
+def lib():
+    """Load the CUDA library; raises if it has not been built (no fallback)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise EngineError(-100, f"{LIB_PATH} is missing: run evosoro_b200.engine.build() / __graft_entry__.build(); "
+                                    "the engine has no CPU path")
+        L = C.CDLL(LIB_PATH)
+        vp = C.c_void_p
+        L.vxg_abi_version.restype = C.c_int
+        L.vxg_device_count.restype = C.c_int
+        L.vxg_last_error.restype = C.c_char_p
+        L.vxg_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.POINTER(abi.Limits)]
+        L.vxg_destroy.argtypes = [vp]
+        L.vxg_destroy.restype = None
+        L.vxg_upload.argtypes = [vp, C.c_int, C.POINTER(abi.RobotDesc)]
+        L.vxg_set_step_budget.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.vxg_step.argtypes = [vp, C.c_int]
+        L.vxg_sync.argtypes = [vp, C.POINTER(C.c_uint32)]
+        L.vxg_last_step_ms.argtypes = [vp, C.POINTER(C.c_float)]
+        L.vxg_launch_count.argtypes = [vp]
+        L.vxg_launch_count.restype = C.c_int64
+        L.vxg_download_state.argtypes = [vp, C.c_int, C.POINTER(abi.RobotState)]
+        L.vxg_upload_state.argtypes = [vp, C.c_int, C.POINTER(abi.RobotState), C.c_double, C.c_int64]
+        L.vxg_reduce_stats.argtypes = [vp, C.POINTER(abi.RobotStats)]
+        L.vxg_enable_bond_record.argtypes = [vp, C.c_int]
+        L.vxg_kernel_config.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                        C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.vxg_struct_sizes.argtypes = [C.POINTER(C.c_int), C.c_int]
+        L.vxg_set_collision_pairs.argtypes = [vp, C.c_int, C.c_int, abi.c_int32_p, abi.c_int32_p, abi.c_double_p]
+        L.vxg_run_batch_host.argtypes = [vp, C.POINTER(abi.RobotDesc), C.c_int, C.c_int, abi.c_double_p]
+        _LIB = L
+    return _LIB
+
+
+def _ck(rc: int):
+    if rc != 0:
+        raise EngineError(rc, lib().vxg_last_error().decode(errors="replace"))
+
+
+def device_count() -> int:
+    return lib().vxg_device_count()
+
+
+class Batch:
+    """A population of robots resident on one GPU (``vxg_batch``)."""
+
+    def __init__(self, robots: Sequence[abi.HostRobot], device: int = 0, precision: int = abi.VXG_PREC_F32,
+                 max_vox: Optional[int] = None, max_vclass: Optional[int] = None, max_bclass: Optional[int] = None,
+                 upload: bool = True):
+        self.robots: List[abi.HostRobot] = list(robots)
+        if not self.robots:
+            raise ValueError("empty batch")
+        lim = abi.Limits()
+        lim.max_vox = max_vox or max(r.n_vox for r in self.robots)
+        lim.max_vclass = max_vclass or max(len(r.vclasses) for r in self.robots)
+        lim.max_bclass = max_bclass or max(1, max(len(r.bclasses) for r in self.robots))
+        lim.precision = precision
+        self.limits = lim
+        self.h = C.c_void_p()
+        _ck(lib().vxg_create(C.byref(self.h), device, len(self.robots), C.byref(lim)))
+        self._descs = (abi.RobotDesc * len(self.robots))(*[r.desc() for r in self.robots])
+        if upload:
+            for i in range(len(self.robots)):
+                _ck(lib().vxg_upload(self.h, i, C.byref(self._descs[i])))
+
+    @property
+    def n_robots(self) -> int:
+        return len(self.robots)
+
+    def set_step_budget(self, total_steps=None, latch_step=None):
+        def arr(x):
+            if x is None:
+                return None, None
+            a = np.ascontiguousarray(x, dtype=np.int64)
+            assert a.shape == (self.n_robots,)
+            return a, a.ctypes.data_as(C.POINTER(C.c_int64))
+        ta, tp = arr(total_steps)
+        la, lp = arr(latch_step)
+        _ck(lib().vxg_set_step_budget(self.h, tp, lp))
+
+    def step(self, n: int):
+        _ck(lib().vxg_step(self.h, int(n)))
+
+    def sync(self) -> np.ndarray:
+        st = np.zeros(self.n_robots, dtype=np.uint32)
+        _ck(lib().vxg_sync(self.h, st.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return st
+
+    def last_step_ms(self) -> float:
+        ms = C.c_float()
+        _ck(lib().vxg_last_step_ms(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    def launch_count(self) -> int:
+        return int(lib().vxg_launch_count(self.h))
+
+    def enable_bond_record(self, on: bool = True):
+        _ck(lib().vxg_enable_bond_record(self.h, 1 if on else 0))
+
+    def kernel_config(self) -> dict:
+        t, v, s = C.c_int(), C.c_int(), C.c_int()
+        sb, bb, db = C.c_int64(), C.c_int64(), C.c_int64()
+        _ck(lib().vxg_kernel_config(self.h, C.byref(t), C.byref(v), C.byref(s), C.byref(sb), C.byref(bb), C.byref(db)))
+        return {"threads": t.value, "voxels_per_thread": v.value, "smem_resident": bool(s.value),
+                "smem_bytes": sb.value, "blob_bytes": bb.value, "dyn_bytes": db.value}
+
+    def download(self, robot: int, bonds: bool = False) -> abi.StateBuffers:
+        r = self.robots[robot]
+        buf = abi.StateBuffers(r.n_vox, r.n_bond)
+        v = buf.view()
+        if not bonds:
+            v.bond_force1 = v.bond_force2 = v.bond_moment1 = v.bond_moment2 = v.bond_strain = None
+        _ck(lib().vxg_download_state(self.h, robot, C.byref(v)))
+        return buf
+
+    def upload_state(self, robot: int, buf: abi.StateBuffers, cur_time: float, cur_step: int):
+        v = buf.view()
+        _ck(lib().vxg_upload_state(self.h, robot, C.byref(v), float(cur_time), int(cur_step)))
+
+    def stats(self):
+        out = (abi.RobotStats * self.n_robots)()
+        _ck(lib().vxg_reduce_stats(self.h, out))
+        return out
+
+    def run_batch_host(self, n_steps: int, pos_out: Optional[np.ndarray] = None) -> np.ndarray:
+        """End-to-end call with host buffers: upload every descriptor, step, bring positions back."""
+        if pos_out is None:
+            pos_out = np.zeros((self.n_robots, self.limits.max_vox, 3))
+        _ck(lib().vxg_run_batch_host(self.h, self._descs, self.n_robots, int(n_steps), pos_out.ctypes.data_as(abi.c_double_p)))
+        return pos_out
+
+    def close(self):
+        if self.h:
+            lib().vxg_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -237,6 +237,17 @@ int64_t vxg_launch_count(vxg_batch* b);
 int vxg_download_state(vxg_batch* b, int robot, vxg_robot_state* out);
 int vxg_upload_state(vxg_batch* b, int robot, const vxg_robot_state* in, double cur_time, int64_t cur_step);
 
+/* Bond outputs (Force1/2, Moment1/2, strain) are only kept when recording is on: the last step of
+ * every vxg_step call then also stores them for vxg_download_state. Off by default (costs HBM writes). */
+int vxg_enable_bond_record(vxg_batch* b, int on);
+
+/* Introspection for benchmarks/tests: launch geometry and per-robot byte counts of the state blob. */
+int vxg_kernel_config(vxg_batch* b, int* threads, int* voxels_per_thread, int* smem_resident,
+                      int64_t* smem_bytes, int64_t* blob_bytes, int64_t* dyn_bytes);
+/* sizeof() of the ABI structs in the order vox_class, bond_class, sim_params, robot_desc, robot_state,
+ * limits, robot_stats; returns how many there are. Lets a foreign-language mirror check its layout. */
+int vxg_struct_sizes(int* out, int n);
+
 /* Replaces: CVX_Sim::UpdateStats / GetCM (VX_Sim.cpp:1511-1690, :2415-2441) for the quantities the
  * result writer needs; out is [n_robots]. Synchronous. */
 int vxg_reduce_stats(vxg_batch* b, vxg_robot_stats* out);

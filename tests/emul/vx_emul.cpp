@@ -1,0 +1,127 @@
+// vx_emul.cpp -- CPU emulation harness for the device arithmetic.  TEST INFRASTRUCTURE ONLY.
+//
+// Compiles evosoro_b200/csrc/vx_math.cuh + vx_robot.cuh + vx_pack.h as plain host C++ and runs the
+// kernel's per-voxel tasks serially in the kernel's phase order (3 bond sub-phases, voxel phase,
+// class-scale update), so the fp32/fp64 "delta formulation" can be checked against the oracle on a
+// machine without a GPU.  It is never linked into libvxgpu.so and nothing in the product calls it.
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../../evosoro_b200/csrc/vx_pack.h"
+
+using namespace vx;
+
+struct EmulBase {
+    virtual ~EmulBase() {}
+    virtual int64_t step(int64_t n) = 0;
+    virtual void get_state(vxg_robot_state* o) = 0;
+    virtual double time() = 0;
+    virtual int diverged() = 0;
+};
+
+template <typename Real> struct Emul : EmulBase {
+    BlobLayout L;
+    std::vector<unsigned char> blob;
+    std::vector<double> nom, bk_dist, scale_c[2];
+    std::vector<BondK<Real>> bk;
+    std::vector<VoxK<Real>> vk;
+    std::vector<ScaleK> sk;
+    std::vector<Real> dsc_c[2], ext_disp, ext_tdisp, rec;
+    std::vector<int32_t> bv1, bax;
+    RobotCtl ctl;
+    int cur = 0;
+    int div = 0;
+
+    Emul(const vxg_robot_desc* d) {
+        L = make_layout(d->n_vox, (int)sizeof(Real));
+        blob.resize(L.total_bytes);
+        nom.resize(3 * (size_t)L.nv);
+        int nvc = d->n_vclass, nbc = d->n_bclass > 0 ? d->n_bclass : 1;
+        bk.resize(nbc); bk_dist.resize(nbc); vk.resize(nvc); sk.resize(nvc);
+        scale_c[0].resize(nvc); scale_c[1].resize(nvc); dsc_c[0].resize(nvc); dsc_c[1].resize(nvc);
+        ext_disp.resize(3 * nvc); ext_tdisp.resize(3 * nvc);
+        pack_classes<Real>(d, bk.data(), bk_dist.data(), vk.data(), sk.data(), scale_c[0].data(), ext_disp.data(), ext_tdisp.data());
+        pack_blob<Real>(d, L, blob.data(), nom.data());
+        init_ctl(d, ctl);
+        for (int i = 0; i < nvc; i++) dsc_c[0][i] = (Real)(scale_c[0][i] - sk[i].nom_size);
+        rec.assign((size_t)39 * L.nv, (Real)0);
+        bv1.assign(d->bond_v1, d->bond_v1 + d->n_bond);
+        bax.assign(d->bond_axis, d->bond_axis + d->n_bond);
+    }
+
+    int64_t step(int64_t n) override {
+        RobotView<Real> R = make_view<Real>(blob.data(), L, ctl.n_vox);
+        RobotConsts<Real> C;
+        C.bk = bk.data(); C.bk_dist = bk_dist.data(); C.vk = vk.data(); C.nom = nom.data();
+        C.ext_disp = ext_disp.data(); C.ext_tdisp = ext_tdisp.data();
+        C.half_bond_z = (Real)ctl.half_bond_z; C.dt = (Real)ctl.dt;
+        const bool fluid = (ctl.flags & VXG_F_FLUID) != 0;
+        C.floor_on = (ctl.flags & VXG_F_FLOOR) && !fluid;
+        C.sticky = (ctl.flags & VXG_F_STICKY_FLOOR) != 0;
+        const bool temp_on = (ctl.flags & VXG_F_TEMPERATURE) != 0, lw = (ctl.flags & VXG_F_LW_SCALE) != 0;
+        const Real dt_inv_run = (Real)(1.0 / ctl.dt);
+        std::vector<V3<Real>> F(ctl.n_vox), M(ctl.n_vox);
+        int64_t k;
+        for (k = 0; k < n; k++) {
+            if (div) break;
+            C.scale_c = scale_c[cur].data(); C.dsc_c = dsc_c[cur].data();
+            const Real dt_inv = ctl.step == 0 ? (Real)0 : dt_inv_run;
+            for (int v = 0; v < ctl.n_vox; v++) { F[v] = mk3<Real>(0, 0, 0); M[v] = mk3<Real>(0, 0, 0); }
+            bool d = false;
+            for (int ax = 0; ax < 3; ax++)
+                for (int v = 0; v < ctl.n_vox; v++) d |= bond_task<Real>(R, C, v, ax, dt_inv, F[v], M[v], rec.data());
+            if (d) { div = 1; break; }
+            for (int v = 0; v < ctl.n_vox; v++) voxel_task<Real>(R, C, v, F[v], M[v]);
+            for (int i = 0; i < ctl.n_vclass; i++) {
+                double ns = scale_law(sk[i], scale_c[cur][i], ctl.cur_time, ctl.init_cm_time, ctl.temp_period, ctl.temp_amplitude,
+                                      ctl.min_fact, ctl.max_fact, temp_on, lw);
+                scale_c[cur ^ 1][i] = ns;
+                dsc_c[cur ^ 1][i] = (Real)(ns - sk[i].nom_size);
+            }
+            cur ^= 1;
+            ctl.cur_time += ctl.dt;
+            ctl.step++;
+        }
+        return k;
+    }
+
+    void get_state(vxg_robot_state* o) override {
+        RobotView<Real> R = make_view<Real>(blob.data(), L, ctl.n_vox);
+        const int nv = R.nv;
+        for (int i = 0; i < ctl.n_vox; i++) {
+            if (o->pos) for (int a = 0; a < 3; a++) o->pos[3 * i + a] = R.pos[a * nv + i];
+            if (o->quat) for (int a = 0; a < 4; a++) o->quat[4 * i + a] = (double)R.quat[a * nv + i];
+            if (o->lin_mom) for (int a = 0; a < 3; a++) o->lin_mom[3 * i + a] = (double)R.lm[a * nv + i];
+            if (o->ang_mom) for (int a = 0; a < 3; a++) o->ang_mom[3 * i + a] = (double)R.am[a * nv + i];
+            if (o->scale) o->scale[i] = scale_c[cur][R.vcls[i]];
+            if (o->static_fric) o->static_fric[i] = (R.flags[i] & VX_FL_STATIC_FRIC) ? 1 : 0;
+        }
+        for (size_t j = 0; j < bv1.size(); j++) {
+            int a = bax[j], v = bv1[j];
+            const Real* r = rec.data() + (size_t)(a * 13) * nv + v;
+            for (int x = 0; x < 3; x++) {
+                if (o->bond_force1) o->bond_force1[3 * j + x] = (double)r[(size_t)x * nv];
+                if (o->bond_force2) o->bond_force2[3 * j + x] = (double)r[(size_t)(3 + x) * nv];
+                if (o->bond_moment1) o->bond_moment1[3 * j + x] = (double)r[(size_t)(6 + x) * nv];
+                if (o->bond_moment2) o->bond_moment2[3 * j + x] = (double)r[(size_t)(9 + x) * nv];
+            }
+            if (o->bond_strain) o->bond_strain[j] = (double)r[(size_t)12 * nv];
+            if (o->bond_small_angle) o->bond_small_angle[j] = (R.flags[v] >> a) & 1u;
+        }
+    }
+    double time() override { return ctl.cur_time; }
+    int diverged() override { return div; }
+};
+
+extern "C" {
+void* vxe_create(const vxg_robot_desc* d, int prec) {
+    if (prec == VXG_PREC_F64) return new Emul<double>(d);
+    return new Emul<float>(d);
+}
+void vxe_destroy(void* h) { delete (EmulBase*)h; }
+int64_t vxe_step(void* h, int64_t n) { return ((EmulBase*)h)->step(n); }
+void vxe_get_state(void* h, vxg_robot_state* o) { ((EmulBase*)h)->get_state(o); }
+double vxe_time(void* h) { return ((EmulBase*)h)->time(); }
+int vxe_diverged(void* h) { return ((EmulBase*)h)->diverged(); }
+}
