@@ -95,6 +95,19 @@ class RobotStats(C.Structure):
     ]
 
 
+class VxaInfo(C.Structure):
+    """vxh_info (include/vxhost.h)"""
+    _fields_ = [
+        ("n_vox", C.c_int32), ("n_bond", C.c_int32),
+        ("x_voxels", C.c_int32), ("y_voxels", C.c_int32), ("z_voxels", C.c_int32),
+        ("stop_condition_type", C.c_int32), ("self_col_enabled", C.c_int32), ("write_fitness_file", C.c_int32),
+        ("stop_condition_value", C.c_double), ("init_cm_time", C.c_double), ("afterlife_time", C.c_double),
+        ("dt_frac", C.c_double), ("optimal_dt", C.c_double), ("lattice_dim", C.c_double),
+        ("col_horizon", C.c_double),
+        ("fitness_file_name", C.c_char * 512),
+    ]
+
+
 def _dp(a: np.ndarray):
     return a.ctypes.data_as(c_double_p)
 

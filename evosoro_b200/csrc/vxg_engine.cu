@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/vxgpu.h"
@@ -37,6 +38,8 @@ struct vxg_batch {
     BlobLayout L{};
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t marks[VXG_N_MARKS] = {};
+    bool mark_set[VXG_N_MARKS] = {};
     bool timed = false;
     // device
     unsigned char* d_blobs = nullptr;
@@ -122,6 +125,7 @@ static void free_all(vxg_batch* b) {
     cudaFreeHost(b->h_stats);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
+    for (int i = 0; i < VXG_N_MARKS; i++) if (b->marks[i]) cudaEventDestroy(b->marks[i]);
     if (b->stream) cudaStreamDestroy(b->stream);
 }
 
@@ -169,6 +173,7 @@ extern "C" int vxg_create(vxg_batch** out, int device, int n_robots, const vxg_l
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev1);
+    for (int i = 0; i < VXG_N_MARKS; i++) if (e == cudaSuccess) e = cudaEventCreate(&b->marks[i]);
     if (e != cudaSuccess) {
         free_all(b); delete b; cudaGetLastError();
         return fail(e == cudaErrorMemoryAllocation ? VXG_ERR_NOMEM : VXG_ERR_CUDA, "vxg_create: %s", cudaGetErrorString(e));
@@ -349,6 +354,23 @@ extern "C" int vxg_last_step_ms(vxg_batch* b, float* ms) {
 
 extern "C" int64_t vxg_launch_count(vxg_batch* b) { return b ? b->launches : 0; }
 
+extern "C" int vxg_mark(vxg_batch* b, int slot) {
+    if (!b || slot < 0 || slot >= VXG_N_MARKS) return fail(VXG_ERR_ARG, "vxg_mark: bad argument");
+    CK(cudaSetDevice(b->device));
+    CK(cudaEventRecord(b->marks[slot], b->stream));
+    b->mark_set[slot] = true;
+    return VXG_OK;
+}
+
+extern "C" int vxg_mark_elapsed_ms(vxg_batch* b, int s0, int s1, float* ms) {
+    if (!b || !ms || s0 < 0 || s1 < 0 || s0 >= VXG_N_MARKS || s1 >= VXG_N_MARKS) return fail(VXG_ERR_ARG, "vxg_mark_elapsed_ms: bad argument");
+    if (!b->mark_set[s0] || !b->mark_set[s1]) return fail(VXG_ERR_STATE, "vxg_mark_elapsed_ms: marker not recorded");
+    CK(cudaSetDevice(b->device));
+    CK(cudaEventSynchronize(b->marks[s1]));
+    CK(cudaEventElapsedTime(ms, b->marks[s0], b->marks[s1]));
+    return VXG_OK;
+}
+
 extern "C" int vxg_kernel_config(vxg_batch* b, int* threads, int* vpt, int* smem_mode, int64_t* smem_bytes, int64_t* blob_bytes, int64_t* dyn_bytes) {
     if (!b) return fail(VXG_ERR_ARG, "vxg_kernel_config: null batch");
     if (threads) *threads = b->threads;
@@ -456,18 +478,47 @@ extern "C" int vxg_set_collision_pairs(vxg_batch* b, int robot, int n_pairs, con
     return fail(VXG_UNSUPPORTED_FEATURE, "self-collision contact bonds are not implemented on the device yet");
 }
 
+// bytes one full population upload moves host -> device (what flush() copies when everything is dirty)
+extern "C" int64_t vxg_upload_bytes(vxg_batch* b) {
+    if (!b) return 0;
+    size_t nr = (size_t)b->n_robots, mv = (size_t)b->lim.max_vclass, mb = (size_t)b->lim.max_bclass, nv = (size_t)b->L.nv;
+    size_t per = b->L.total_bytes + mb * b->bk_sz() + mb * sizeof(double) + mv * b->vk_sz() + mv * sizeof(ScaleK) + mv * sizeof(double) +
+                 2 * mv * 3 * b->rs() + 3 * nv * sizeof(double) + sizeof(RobotCtl);
+    return (int64_t)(nr * per);
+}
+
 extern "C" int vxg_run_batch_host(vxg_batch* b, const vxg_robot_desc* descs, int n_descs, int n_steps, double* pos_out) {
     if (!b || !descs || n_descs != b->n_robots) return fail(VXG_ERR_ARG, "vxg_run_batch_host: need one descriptor per robot slot");
-    for (int r = 0; r < n_descs; r++) { int rc = vxg_upload(b, r, &descs[r]); if (rc) return rc; }
+    // flatten the descriptors into the pinned mirrors on all host cores (slots are independent)
+    {
+        int nt = (int)std::thread::hardware_concurrency();
+        if (nt < 1) nt = 1;
+        if (nt > 32) nt = 32;
+        if (nt > n_descs) nt = n_descs;
+        std::vector<int> rcs((size_t)nt, 0);
+        std::vector<std::string> msgs((size_t)nt);
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++)
+            th.emplace_back([&, t]() {
+                for (int r = t; r < n_descs; r += nt) {
+                    int rc = vxg_upload(b, r, &descs[r]);
+                    if (rc) { rcs[t] = rc; msgs[t] = g_err; return; }
+                }
+            });
+        for (auto& x : th) x.join();
+        for (int t = 0; t < nt; t++) if (rcs[t]) { g_err = msgs[t]; return rcs[t]; }
+    }
     int rc = vxg_step(b, n_steps);
     if (rc) return rc;
     if (pos_out) {
         // positions only: first 3*nv doubles of every blob (strided device -> host copy)
         size_t w = (size_t)3 * b->L.nv * sizeof(double);
         CK(cudaMemcpy2DAsync(b->h_blobs, b->L.total_bytes, b->d_blobs, b->L.total_bytes, w, (size_t)b->n_robots, cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaMemcpyAsync(b->h_ctl, b->d_ctl, (size_t)b->n_robots * sizeof(RobotCtl), cudaMemcpyDeviceToHost, b->stream));
         CK(cudaStreamSynchronize(b->stream));
         const int nv = b->L.nv, mv = b->lim.max_vox;
         for (int r = 0; r < b->n_robots; r++) {
+            if (b->h_ctl[r].status & VXG_ST_DIVERGED) return fail(VXG_ERR_STATE, "vxg_run_batch_host: robot %d diverged (strain > 100)", r);
             const double* p = (const double*)(b->h_blobs + (size_t)r * b->L.total_bytes);
             double* o = pos_out + (size_t)r * mv * 3;
             int n = b->h_ctl[r].n_vox;

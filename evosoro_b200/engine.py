@@ -67,6 +67,21 @@ def lib():
         L.vxg_struct_sizes.argtypes = [C.POINTER(C.c_int), C.c_int]
         L.vxg_set_collision_pairs.argtypes = [vp, C.c_int, C.c_int, abi.c_int32_p, abi.c_int32_p, abi.c_double_p]
         L.vxg_run_batch_host.argtypes = [vp, C.POINTER(abi.RobotDesc), C.c_int, C.c_int, abi.c_double_p]
+        L.vxg_upload_bytes.argtypes = [vp]
+        L.vxg_upload_bytes.restype = C.c_int64
+        L.vxg_mark.argtypes = [vp, C.c_int]
+        L.vxg_mark_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
+        # host side (include/vxhost.h)
+        L.vxh_last_error.restype = C.c_char_p
+        L.vxh_load_vxa_file.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(vp)]
+        L.vxh_load_vxa_string.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(vp)]
+        L.vxh_free.argtypes = [vp]
+        L.vxh_free.restype = None
+        L.vxh_desc.argtypes = [vp]
+        L.vxh_desc.restype = C.POINTER(abi.RobotDesc)
+        L.vxh_get_info.argtypes = [vp, C.POINTER(abi.VxaInfo)]
+        L.vxh_cell_index.argtypes = [vp, abi.c_int32_p]
+        L.vxh_step_plan.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double)]
         _LIB = L
     return _LIB
 
@@ -78,6 +93,55 @@ def _ck(rc: int):
 
 def device_count() -> int:
     return lib().vxg_device_count()
+
+
+VARIANT_VOXCAD = 0
+VARIANT_LAND_WATER = 1
+
+
+class Model:
+    """An imported ``.vxa`` (``vxh_model``): the flat descriptor plus the CLI's step plan.
+
+    Mirrors ``CVX_Sim::LoadVXAFile`` + ``Import`` (VX_Sim.cpp:159-165, :488-717); raises ``EngineError``
+    with a positive code when the file enables a feature the kernels do not implement."""
+
+    def __init__(self, path: Optional[str] = None, text: Optional[str] = None, variant: int = VARIANT_VOXCAD,
+                 ignore_collisions: bool = False):
+        self.h = C.c_void_p()
+        L = lib()
+        if text is not None:
+            rc = L.vxh_load_vxa_string(text.encode("latin-1"), variant, int(ignore_collisions), C.byref(self.h))
+        else:
+            rc = L.vxh_load_vxa_file(os.fsencode(path), variant, int(ignore_collisions), C.byref(self.h))
+        if rc != 0:
+            raise EngineError(rc, L.vxh_last_error().decode(errors="replace"))
+        self.info = abi.VxaInfo()
+        L.vxh_get_info(self.h, C.byref(self.info))
+        self.robot = abi.HostRobot.from_desc(L.vxh_desc(self.h).contents)
+
+    def step_plan(self):
+        """(total_steps, latch_step, final_time) of the reference CLI loop for this file."""
+        t, l, ft = C.c_int64(), C.c_int64(), C.c_double()
+        rc = lib().vxh_step_plan(self.h, C.byref(t), C.byref(l), C.byref(ft))
+        if rc != 0:
+            raise EngineError(rc, lib().vxh_last_error().decode(errors="replace"))
+        return t.value, l.value, ft.value
+
+    def cell_index(self) -> np.ndarray:
+        out = np.zeros(self.info.n_vox, dtype=np.int32)
+        lib().vxh_cell_index(self.h, out.ctypes.data_as(abi.c_int32_p))
+        return out
+
+    def close(self):
+        if self.h:
+            lib().vxh_free(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Batch:
@@ -133,6 +197,14 @@ class Batch:
     def launch_count(self) -> int:
         return int(lib().vxg_launch_count(self.h))
 
+    def mark(self, slot: int):
+        _ck(lib().vxg_mark(self.h, slot))
+
+    def mark_elapsed_ms(self, slot0: int, slot1: int) -> float:
+        ms = C.c_float()
+        _ck(lib().vxg_mark_elapsed_ms(self.h, slot0, slot1, C.byref(ms)))
+        return float(ms.value)
+
     def enable_bond_record(self, on: bool = True):
         _ck(lib().vxg_enable_bond_record(self.h, 1 if on else 0))
 
@@ -167,6 +239,9 @@ class Batch:
             pos_out = np.zeros((self.n_robots, self.limits.max_vox, 3))
         _ck(lib().vxg_run_batch_host(self.h, self._descs, self.n_robots, int(n_steps), pos_out.ctypes.data_as(abi.c_double_p)))
         return pos_out
+
+    def h2d_bytes_per_upload(self) -> int:
+        return int(lib().vxg_upload_bytes(self.h))
 
     def close(self):
         if self.h:

@@ -231,6 +231,11 @@ int vxg_sync(vxg_batch* b, uint32_t* status_per_robot);
 int vxg_last_step_ms(vxg_batch* b, float* ms);
 /* Number of kernels this library launched on the batch so far. */
 int64_t vxg_launch_count(vxg_batch* b);
+/* Benchmark markers: record CUDA event `slot` (0..VXG_N_MARKS-1) on the batch stream -- the stream the
+ * kernels are launched on -- and read the device time between two recorded slots (waits for `slot1`). */
+#define VXG_N_MARKS 8
+int vxg_mark(vxg_batch* b, int slot);
+int vxg_mark_elapsed_ms(vxg_batch* b, int slot0, int slot1, float* ms);
 
 /* Replaces: the per-voxel / per-bond getters the GUI and CVX_MeshUtil read after a step
  * (VXS_Voxel.h:46-59, VXS_Bond.h:31-43). */
@@ -260,6 +265,8 @@ int vxg_set_collision_pairs(vxg_batch* b, int robot, int n_pairs, const int32_t*
 /* Host-buffer convenience used by the end-to-end benchmark: upload all descriptors, run n_steps,
  * download positions of every robot into pos_out ([n_robots][max_vox][3] doubles). */
 int vxg_run_batch_host(vxg_batch* b, const vxg_robot_desc* descs, int n_descs, int n_steps, double* pos_out);
+/* Bytes one full population upload copies host -> device (for the benchmark's h2d accounting). */
+int64_t vxg_upload_bytes(vxg_batch* b);
 
 #ifdef __cplusplus
 }

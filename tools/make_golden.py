@@ -1,0 +1,67 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz from the UNMODIFIED reference engine (oracle/_ref/ref_dump, built from
+/root/reference by oracle/Makefile).  Run in the build container (needs oracle/_ref); the fixtures are
+committed so that the CPU and GPU test-suites can pin the oracle / the kernels without the reference.
+
+    python tools/make_golden.py
+
+Each fixture holds the .vxa text, the reference's imported arrays (dump header) and sampled frames of
+per-voxel state + per-bond outputs -- all fp64, exactly as the reference's public getters return them.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import refdump  # noqa: E402
+from evosoro_b200 import vxa  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+TMP = "/tmp/vx_golden"
+
+
+def case(name, structure, n_steps, every, sim=None, env=None, palette=None, phase=None, lw=False, full=False):
+    os.makedirs(TMP, exist_ok=True)
+    text = vxa.vxa_text(structure, palette=palette, sim=sim, env=env, phase_offset=phase)
+    path = os.path.join(TMP, name + ".vxa")
+    with open(path, "w") as f:
+        f.write(text)
+    d = refdump.run_ref_dump(path, path + ".bin", n_steps, every, nocol=True, lw=lw)
+    out = dict(vxa=np.frombuffer(text.encode("latin-1"), dtype=np.uint8), lw=np.int32(lw), n_steps=np.int64(n_steps), every=np.int64(every),
+               sim=d.sim, vox=d.vox, bond=d.bond, frame_hdr=d.frame_hdr, vstate=d.vstate, bstate=d.bstate)
+    if full:
+        f = refdump.run_ref_full(path, path + ".full.bin", nocol=True, lw=lw)
+        out.update(full_hdr=f.frame_hdr, full_vstate=f.vstate[-1], full_tail=f.tail)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, "voxels", d.n_vox, "bonds", d.n_bond, "frames", d.vstate.shape[0], os.path.getsize(os.path.join(OUT, name + ".npz")) // 1024, "KiB")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    S = vxa.SimParams
+    # settling + actuation onset inside the window (InitCmTime 0.02 s = 312 steps)
+    case("dense3_s5", vxa.dense_lattice(3, 5), 1500, 50, sim=S(init_cm_time=0.02, stop_condition_value=0.2))
+    case("dense4_s7", vxa.dense_lattice(4, 7), 1200, 100, sim=S(init_cm_time=0.02, stop_condition_value=0.2))
+    # every step of the first 40 (dt = 0 first pass, damping history, mode flags)
+    case("dense3_s2_first40", vxa.dense_lattice(3, 2), 40, 1, sim=S(init_cm_time=0.001, stop_condition_value=0.2))
+    # ragged morphology (CPPN-like blob), soft-only palette -> 10x larger dt
+    case("sparse5_s3", vxa.sparse_lattice(5, 3, fill=0.5), 1000, 100, sim=S(init_cm_time=0.02, stop_condition_value=0.2))
+    # per-voxel phase offsets
+    rng = np.random.RandomState(4)
+    case("dense3_phase", vxa.dense_lattice(3, 9), 1000, 100, sim=S(init_cm_time=0.01, stop_condition_value=0.2), phase=rng.uniform(-0.5, 0.5, (3, 3, 3)))
+    # whole CLI run to StopConditionMet: step count, IniCM latch, fitness block
+    case("dense3_full", vxa.dense_lattice(3, 11, materials=(1, 3, 4)), 200, 100, sim=S(init_cm_time=0.05, stop_condition_value=0.25), full=True)
+    # BASELINE config 1/2 shape: dense 6^3, whole 5 s CLI run (78 054 steps): final COM / fitness only
+    case("dense6_s1_full", vxa.dense_lattice(6, 1), 0, 1, full=True)
+    # single voxel / no bonds (edge case: empty bond list)
+    one = np.zeros((2, 2, 2), dtype=np.int32); one[0, 0, 0] = 1
+    case("single_voxel", one, 300, 100, sim=S(init_cm_time=0.01, stop_condition_value=0.1))
+    # land/water fork scale law, no fluid
+    case("lw_dense3_s6", vxa.dense_lattice(3, 6), 1000, 100, sim=S(init_cm_time=0.01, stop_condition_value=0.2), lw=True)
+
+
+if __name__ == "__main__":
+    main()
