@@ -70,14 +70,42 @@ VX_HD void vx_sincos(double a, double* s, double* c) {
     *s = sin(a); *c = cos(a);
 #endif
 }
+// Single-instruction SFU forms on the device for the fp32 instantiation (MUFU.RSQ / MUFU.RCP / MUFU.SQRT,
+// <= 2 ulp): the IEEE-rounded sqrtf / division expand to ~10 instructions plus a slow-path branch each,
+// and their last-ulp difference is far below the fp32 parity tolerance.  fp64 stays IEEE.
 VX_HD float vx_rsqrt(float x) {
 #if defined(__CUDA_ARCH__)
-    return rsqrtf(x);
+    float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
 #else
     return 1.0f / sqrtf(x);
 #endif
 }
 VX_HD double vx_rsqrt(double x) { return 1.0 / sqrt(x); }
+VX_HD float vx_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+    float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+    return 1.0f / x;
+#endif
+}
+VX_HD double vx_rcp(double x) { return 1.0 / x; }
+VX_HD float vx_fsqrt(float x) {   // fast sqrt (vx_sqrt is the IEEE one)
+#if defined(__CUDA_ARCH__)
+    float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+    return sqrtf(x);
+#endif
+}
+VX_HD double vx_fsqrt(double x) { return sqrt(x); }
+#if defined(__CUDACC__)
+#define VX_NOINLINE __host__ __device__ __noinline__
+#else
+#define VX_NOINLINE
+#endif
+// num/den < c and num/den > c without the division, with the IEEE outcome for den <= 0 (negative ratio,
+// +-inf, NaN) that the reference's `(abs(z)+abs(y))/x` and `x/NomDistance` tests would have.
+template <typename T> VX_HD bool ratio_lt(T num, T den, T c) { return den > (T)0 ? num < c * den : (den < (T)0 ? num > c * den : num < (T)0); }
+template <typename T> VX_HD bool ratio_gt(T num, T den, T c) { return den > (T)0 ? num > c * den : (den < (T)0 ? num < c * den : num > (T)0); }
 
 // bond axis permutation: the bond is evaluated as if it pointed along +X (VX_Bond.h:45-48)
 template <typename T> VX_HD V3<T> to_xdir(int ax, V3<T> v) {
@@ -110,46 +138,53 @@ template <typename T> VX_HD Q4<T> qmul(Q4<T> a, Q4<T> f) {
 }
 
 // CQuat::ToRotationVector (Vec3D.h:270-285) in cancellation-free form: the vector part scaled by
-// 2 sqrt(2/(1+w)) (sqrt branch) or 2 atan2(|v|, w)/|v| (acos branch); zero when the vector part is zero.
+// 2 sqrt(2/(1+w)) (sqrt branch) or 2 atan2(|v|, w)/|v| (acos branch); zero when the vector part is zero or
+// |w| >= 1.  The acos branch (relative rotation above ~5.6 degrees) is rare and kept out of line.
+template <typename T> VX_NOINLINE T rotvec_scale_large(T vv, T w) {
+    T l = vx_sqrt(vv);
+    return (T)2 * vx_atan2(l, w) / l;
+}
 template <typename T> VX_HD V3<T> rotvec(Q4<T> q) {
     T vv = q.x * q.x + q.y * q.y + q.z * q.z;
     T f;
-    if (!(vv > (T)0)) f = (T)0;
-    else if (vv < (T)VX_SLTHRESH_ACOS2SQRT) { T w = q.w > (T)1 ? (T)1 : q.w; f = (T)2 * vx_sqrt((T)2 / ((T)1 + w)); }
-    else { T l = vx_sqrt(vv); f = (T)2 * vx_atan2(l, q.w) / l; }
+    if (vv < (T)VX_SLTHRESH_ACOS2SQRT) {
+        T w = q.w > (T)1 ? (T)1 : q.w;
+        f = (T)2.8284271247461903 * vx_rsqrt((T)1 + w);          // 2 sqrt(2/(1+w))
+        if (!(vv > (T)0) || !(w > (T)-1)) f = (T)0;
+    } else f = rotvec_scale_large<T>(vv, q.w);
     return mk3<T>(q.x * f, q.y * f, q.z * f);
 }
 
-// CQuat::FromAngleToPosX (Vec3D.h:208-237): quaternion turning `from` onto +X (x component is 0)
+// CQuat::FromAngleToPosX (Vec3D.h:208-237): quaternion turning `from` onto +X (x component is 0).
+// Large-angle branch without trigonometry: with n = from/|from|, cos(theta) = n.x, so
+// cos(theta/2) = sqrt((1 + n.x)/2) and sin(theta/2)/(|from| sin(theta)) = 1/(2 |from| cos(theta/2));
+// theta > pi - 1e-7 (Vec3D.h:224)  <=>  cos^2(theta/2) < sin^2(0.5e-7) = 2.5e-15.
 template <typename T> VX_HD Q4<T> from_angle_to_posx(V3<T> from) {
     Q4<T> q; q.w = (T)1; q.x = (T)0; q.y = (T)0; q.z = (T)0;
     if (from.x == (T)0 && from.y == (T)0 && from.z == (T)0) return q;
-    T inv = (T)1 / from.x;
-    T yox = from.y * inv, zox = from.z * inv;
     const T sa = (T)VX_SMALL_ANGLE_RAD;
-    if (yox < sa && yox > -sa && zox < sa && zox > -sa) {
-        q.y = (T)0.5 * zox; q.z = (T)-0.5 * yox;
+    T ax = vx_abs(from.x);
+    if (from.x != (T)0 && vx_abs(from.y) < sa * ax && vx_abs(from.z) < sa * ax) {
+        T inv = vx_rcp(from.x);
+        q.y = (T)0.5 * from.z * inv; q.z = (T)-0.5 * from.y * inv;
         q.w = (T)1 + (T)0.5 * (-q.y * q.y - q.z * q.z);
         return q;
     }
     T rr = from.y * from.y + from.z * from.z;
     T li = vx_rsqrt(from.x * from.x + rr);
-    T nx = from.x * li;
-    T rad = vx_sqrt(rr);                 // |from| sin(theta)
-    T theta = vx_atan2(rad * li, nx);    // == acos(n.x), well conditioned
-    if (theta > (T)(VX_PI - VX_DISCARD_ANGLE_RAD)) { q.w = 0; q.x = 0; q.y = 1; q.z = 0; return q; }
-    T s, c;
-    vx_sincos((T)0.5 * theta, &s, &c);
-    T k = s / rad;                       // n.{y,z} * AxisMagInv = from.{y,z} / rad
-    q.w = c; q.y = from.z * k; q.z = -from.y * k;
+    T c2 = (T)0.5 * ((T)1 + from.x * li);
+    if (c2 < (T)2.5e-15) { q.w = 0; q.x = 0; q.y = 1; q.z = 0; return q; }
+    T ic = vx_rsqrt(c2);                 // 1 / cos(theta/2)
+    T k = (T)0.5 * li * ic;
+    q.w = c2 * ic; q.y = from.z * k; q.z = -from.y * k;
     return q;
 }
 
 // ---- constants narrowed to the working precision -------------------------------------------------
 template <typename T> struct BondK {   // from vxg_bond_class
     T a2, b1, b2, b3;
-    T inv_len, area_e1, area_e2;       // 1/L.x ; s^2 * E (stress -> axial force)
-    T e1, e2, area;
+    T inv_len;                         // 1/L.x
+    T k_axial;                         // area * E_eff / L.x : axial force per unit of _Pos2.x (see pack_classes)
     T nom_dist;                        // pitch along the axis (as Real)
     T len_minus_dist;                  // L.x - pitch (0 on regular lattices)
     T c_a1m1, c_a1m2, c_a2i1, c_a2i2, c_b1m1, c_b1m2, c_b2fm1, c_b2fm2, c_b3i1, c_b3i2;
@@ -200,15 +235,14 @@ VX_HD void bond_force(const BondK<T>& k, int ax, V3<T> e, Q4<T> q1, Q4<T> q2, T 
     T nomrel = dnom + k.len_minus_dist;      // NomDistance - pitch  (:71)
     T nom = D + nomrel;
 
-    // small/large angle hysteresis (:74-78)
+    // small/large angle hysteresis (:74-78); SmallTurn = (|z|+|y|)/x and ExtendPerc = x/NomDistance compared
+    // without forming the quotients
     bool changed = false;
-    T inv_rx = (T)1 / rx;
-    T small_turn = (vx_abs(rr.z) + vx_abs(rr.y)) * inv_rx;
-    T ext = rx / nom;
+    T turn_num = vx_abs(rr.z) + vx_abs(rr.y);
     bool is_small_w = (q12.w > (T)0) && (vv12 < (T)VX_SIN2_SMALL);
     bool is_smallish_w = (q12.w > (T)0) && (vv12 < (T)VX_SIN2_SMALLISH);
-    if (!small && is_small_w && small_turn < (T)VX_SA_BOND_BEND_RAD && ext < (T)VX_SA_BOND_EXT_PERC) { small = true; changed = true; }
-    else if (small && (!is_smallish_w || small_turn > (T)(VX_HYST * VX_SA_BOND_BEND_RAD) || ext > (T)(VX_HYST * VX_SA_BOND_EXT_PERC))) { small = false; changed = true; }
+    if (!small && is_small_w && ratio_lt<T>(turn_num, rx, (T)VX_SA_BOND_BEND_RAD) && ratio_lt<T>(rx, nom, (T)VX_SA_BOND_EXT_PERC)) { small = true; changed = true; }
+    else if (small && (!is_smallish_w || ratio_gt<T>(turn_num, rx, (T)(VX_HYST * VX_SA_BOND_BEND_RAD)) || ratio_gt<T>(rx, nom, (T)(VX_HYST * VX_SA_BOND_EXT_PERC)))) { small = false; changed = true; }
 
     V3<T> p2, an1, an2;
     Q4<T> back;                               // conj(TotalRot): local -> world rotation
@@ -221,34 +255,19 @@ VX_HD void bond_force(const BondK<T>& k, int ax, V3<T> e, Q4<T> q1, Q4<T> q2, T 
         Q4<T> pa = from_angle_to_posx(mk3<T>(rx, rr.y, rr.z));
         // |dp| - pitch without cancellation
         T d2 = (T)2 * D * e.x + (e.x * e.x + e.y * e.y + e.z * e.z);
-        T len = vx_sqrt(D * D + d2);
-        p2 = mk3<T>(d2 / (len + D) - nomrel, 0, 0);
+        T len = vx_fsqrt(D * D + d2);
+        p2 = mk3<T>(d2 * vx_rcp(len + D) - nomrel, 0, 0);
         an1 = rotvec(pa);
         an2 = rotvec(qmul(pa, q12));          // (pa * conj(q1)) * q2
         Q4<T> cpa; cpa.w = pa.w; cpa.x = -pa.x; cpa.y = -pa.y; cpa.z = -pa.z;
         back = qmul(q1, cpa);                 // conj(pa * conj(q1))
     }
 
-    // axial stress (:120, :189-307; MDL_LINEAR: VX_Object.cpp:1472-1482)
-    T strain = p2.x * k.inv_len;
-    out.strain = strain;
-    T fx;
-    if (k.homogeneous) fx = k.area_e1 * strain;
-    else {
-        T sv1 = strain, sv2 = strain;
-        T st1 = k.e1 * sv1, st2 = k.e2 * sv2;
-        int count = 0;
-        T diff = vx_abs(st1 - st2), sum = vx_abs(st1 + st2);
-        while (diff > sum * (T).0005 && count < 3) {
-            T inv = (T)1 / (st1 + st2);
-            sv1 = (T)2 * st2 * inv * sv1;
-            sv2 = (T)2 * st1 * inv * sv2;
-            st1 = k.e1 * sv1; st2 = k.e2 * sv2;
-            diff = vx_abs(st1 - st2); sum = vx_abs(st1 + st2);
-            count++;
-        }
-        fx = (st1 + st2) * (T)0.5 * k.area;
-    }
+    // axial stress (:120, :189-307; MDL_LINEAR: VX_Object.cpp:1472-1482).  For linear materials the
+    // heterogeneous fixed-point iteration (:226-258) converges in one pass to sigma = 2 E1 E2/(E1+E2) eps
+    // (eps1 <- 2 s2/(s1+s2) eps gives s1 = s2 exactly), so the force is a constant times _Pos2.x.
+    out.strain = p2.x * k.inv_len;
+    T fx = k.k_axial * p2.x;
 
     // beam equations (:127-128, :153-154)
     V3<T> F1 = mk3<T>(fx, k.b1 * p2.y - k.b2 * (an1.z + an2.z), k.b1 * p2.z + k.b2 * (an1.y + an2.y));

@@ -17,8 +17,15 @@ inline void pack_classes(const vxg_robot_desc* d, BondK<Real>* bk, double* bk_di
         const vxg_bond_class& c = d->bclasses[i];
         BondK<Real>& k = bk[i];
         k.a2 = (Real)c.a2; k.b1 = (Real)c.b1; k.b2 = (Real)c.b2; k.b3 = (Real)c.b3;
-        k.inv_len = (Real)(1.0 / c.len); k.area_e1 = (Real)(c.area * c.e1); k.area_e2 = (Real)(c.area * c.e2);
-        k.e1 = (Real)c.e1; k.e2 = (Real)c.e2; k.area = (Real)c.area;
+        k.inv_len = (Real)(1.0 / c.len);
+        {   // VXS_BondInternal.cpp:206 (homogeneous: E_mat eps) / :226-258 (heterogeneous: one pass of the stress-balancing iteration)
+            double e_eff = c.e1;
+            if (!c.homogeneous) {
+                double diff = c.e1 >= c.e2 ? c.e1 - c.e2 : c.e2 - c.e1, sum = c.e1 + c.e2;
+                e_eff = diff > sum * .0005 ? 2.0 * c.e1 * c.e2 / sum : 0.5 * sum;   // loop entered (one pass converges) / not entered
+            }
+            k.k_axial = (Real)(c.area * e_eff / c.len);
+        }
         k.nom_dist = (Real)c.nom_dist; k.len_minus_dist = (Real)(c.len - c.nom_dist);
         k.c_a1m1 = (Real)c.c_a1m1; k.c_a1m2 = (Real)c.c_a1m2; k.c_a2i1 = (Real)c.c_a2i1; k.c_a2i2 = (Real)c.c_a2i2;
         k.c_b1m1 = (Real)c.c_b1m1; k.c_b1m2 = (Real)c.c_b1m2; k.c_b2fm1 = (Real)c.c_b2fm1; k.c_b2fm2 = (Real)c.c_b2fm2;
