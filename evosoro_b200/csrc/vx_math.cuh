@@ -119,6 +119,35 @@ template <typename T> VX_HD V3<T> to_origdir(int ax, V3<T> v) {
     return v;
 }
 
+// the same permutations with the axis known at compile time (free register renaming in the kernels)
+template <int AX, typename T> VX_HD V3<T> to_xdir_c(V3<T> v) {
+    if (AX == 1) return mk3<T>(v.y, -v.x, v.z);
+    if (AX == 2) return mk3<T>(v.z, v.y, -v.x);
+    return v;
+}
+template <int AX, typename T> VX_HD V3<T> to_origdir_c(V3<T> v) {
+    if (AX == 1) return mk3<T>(-v.y, v.x, v.z);
+    if (AX == 2) return mk3<T>(-v.z, v.y, v.x);
+    return v;
+}
+
+// rotation matrix of a unit quaternion, for applying one rotation to several vectors:
+// v + 2 (u x (u x v) + w (u x v))  ==  M v  with  M = (1 - 2|u|^2) I + 2 u u^T + 2 w [u]x
+template <typename T> struct M33 { T xx, xy, xz, yx, yy, yz, zx, zy, zz; };
+template <typename T> VX_HD M33<T> rot_matrix(Q4<T> q) {
+    T tx = q.x + q.x, ty = q.y + q.y, tz = q.z + q.z;
+    T wx = q.w * tx, wy = q.w * ty, wz = q.w * tz;
+    T xx = q.x * tx, xy = q.x * ty, xz = q.x * tz, yy = q.y * ty, yz = q.y * tz, zz = q.z * tz;
+    M33<T> m;
+    m.xx = (T)1 - (yy + zz); m.xy = xy - wz;          m.xz = xz + wy;
+    m.yx = xy + wz;          m.yy = (T)1 - (xx + zz); m.yz = yz - wx;
+    m.zx = xz - wy;          m.zy = yz + wx;          m.zz = (T)1 - (xx + yy);
+    return m;
+}
+template <typename T> VX_HD V3<T> mat_apply(const M33<T>& m, V3<T> v) {
+    return mk3<T>(m.xx * v.x + m.xy * v.y + m.xz * v.z, m.yx * v.x + m.yy * v.y + m.yz * v.z, m.zx * v.x + m.zy * v.y + m.zz * v.z);
+}
+
 // rotate v by unit quaternion (w,u): v + 2 (u x (u x v) + w (u x v))      (CQuat::RotateVec3D Vec3D.h:293-299)
 template <typename T> VX_HD V3<T> rot_delta(T w, V3<T> u, V3<T> v) {
     V3<T> c = cross(u, v);
@@ -146,12 +175,10 @@ template <typename T> VX_NOINLINE T rotvec_scale_large(T vv, T w) {
 }
 template <typename T> VX_HD V3<T> rotvec(Q4<T> q) {
     T vv = q.x * q.x + q.y * q.y + q.z * q.z;
-    T f;
-    if (vv < (T)VX_SLTHRESH_ACOS2SQRT) {
-        T w = q.w > (T)1 ? (T)1 : q.w;
-        f = (T)2.8284271247461903 * vx_rsqrt((T)1 + w);          // 2 sqrt(2/(1+w))
-        if (!(vv > (T)0) || !(w > (T)-1)) f = (T)0;
-    } else f = rotvec_scale_large<T>(vv, q.w);
+    T w = q.w > (T)1 ? (T)1 : q.w;
+    T f = (T)2.8284271247461903 * vx_rsqrt((T)1 + w);              // 2 sqrt(2/(1+w))
+    f = (vv > (T)0) & (w > (T)-1) ? f : (T)0;
+    if (vv >= (T)VX_SLTHRESH_ACOS2SQRT) f = rotvec_scale_large<T>(vv, q.w);
     return mk3<T>(q.x * f, q.y * f, q.z * f);
 }
 
@@ -181,17 +208,21 @@ template <typename T> VX_HD Q4<T> from_angle_to_posx(V3<T> from) {
 }
 
 // ---- constants narrowed to the working precision -------------------------------------------------
-template <typename T> struct BondK {   // from vxg_bond_class
+// Both tables are read with 128-bit loads (one class per thread), hence the alignment and padding.
+template <typename T> struct alignas(16) BondK {   // from vxg_bond_class
     T a2, b1, b2, b3;
     T inv_len;                         // 1/L.x
     T k_axial;                         // area * E_eff / L.x : axial force per unit of _Pos2.x (see pack_classes)
     T nom_dist;                        // pitch along the axis (as Real)
     T len_minus_dist;                  // L.x - pitch (0 on regular lattices)
-    T c_a1m1, c_a1m2, c_a2i1, c_a2i2, c_b1m1, c_b1m2, c_b2fm1, c_b2fm2, c_b3i1, c_b3i2;
+    T c_a1m1, c_a1m2, c_a2i1, c_a2i2;
+    T c_b1m1, c_b1m2, c_b2fm1, c_b2fm2;
+    T c_b3i1, c_b3i2;
     int homogeneous;
+    int pad_[sizeof(T) == 4 ? 1 : 2];
 };
 
-template <typename T> struct VoxK {    // from vxg_vox_class (+ sim constants folded in)
+template <typename T> struct alignas(16) VoxK {    // from vxg_vox_class (+ sim constants folded in)
     T mass, mass_inv, inertia_inv;
     T slow_lin;        // SlowDampZ * _2xSqMxExS
     T floor_damp;      // ColDampZ  * _2xSqMxExS
@@ -201,11 +232,13 @@ template <typename T> struct VoxK {    // from vxg_vox_class (+ sim constants fo
     T ext_f[3], ext_t[3];
     int dof;
     int has_bc;        // any fixed DOF or external load
+    int pad_[sizeof(T) == 4 ? 2 : 2];
 };
 
 template <typename T> struct BondOut {
     V3<T> f1, f2, m1, m2;   // world frame: force/moment on voxel 1 (negative side) and voxel 2
     T strain;
+    bool changed;           // the small/large-angle mode flipped this step: the caller keeps the old history (:157)
 };
 
 template <typename T> struct BondHist {  // _LastPos2, _LastAngle1, _LastAngle2 (VXS_Bond.h:57)
@@ -214,16 +247,23 @@ template <typename T> struct BondHist {  // _LastPos2, _LastAngle1, _LastAngle2 
 
 // One internal bond.  CVXS_BondInternal::CalcLinForce (VXS_BondInternal.cpp:56-187) with
 // UpdateBondStrain (:189-307, linear materials) and AddDampForces (:310-346).
-//   e        : permuted (pos2 - pos1) minus (pitch,0,0), formed in fp64 by the caller, narrowed to Real
-//   q1, q2   : voxel orientations (already permuted into the bond frame)
+//   AX       : bond axis (0/1/2); e, q1, q2 are given in the world frame and permuted here (VX_Bond.h:45-48)
+//   e        : (pos2 - pos1) minus the pitch along AX, formed in fp64 by the caller, narrowed to Real
 //   dnom     : 0.5 (Scale1 + Scale2) - L.x   (deviation of the rest length from nominal)
-//   small    : in/out SmallAngle flag;  hist: in/out damping history
+//   small    : in/out SmallAngle flag;  hist: in = damping history, out = this step's values (the caller
+//              stores them unless out.changed)
 //   dt_inv   : 1/dt of the PREVIOUS step (0 on the very first step: no damping, history still stored)
-template <typename T>
-VX_HD void bond_force(const BondK<T>& k, int ax, V3<T> e, Q4<T> q1, Q4<T> q2, T dnom, T half_bond_z, T dt_inv,
+// Only the small/large-angle split is a real branch; everything cheap is evaluated unconditionally so
+// the common path is one long basic block the scheduler can interleave across the voxels of a thread.
+template <int AX, typename T>
+VX_HD void bond_force(const BondK<T>& k, V3<T> e_w, Q4<T> q1w, Q4<T> q2w, T dnom, T half_bond_z, T dt_inv,
                       bool& small, BondHist<T>& hist, BondOut<T>& out) {
     const T D = k.nom_dist;
-    V3<T> u1 = mk3<T>(q1.x, q1.y, q1.z);
+    V3<T> e = to_xdir_c<AX>(e_w);
+    V3<T> u1 = to_xdir_c<AX>(mk3<T>(q1w.x, q1w.y, q1w.z));
+    V3<T> u2 = to_xdir_c<AX>(mk3<T>(q2w.x, q2w.y, q2w.z));
+    Q4<T> q1; q1.w = q1w.w; q1.x = u1.x; q1.y = u1.y; q1.z = u1.z;
+    Q4<T> q2; q2.w = q2w.w; q2.x = u2.x; q2.y = u2.y; q2.z = u2.z;
     V3<T> dp = mk3<T>(D + e.x, e.y, e.z);
     // Ang1AlignedRelPos - (pitch,0,0)  (:65): inverse rotation = rotation by (w, -u)
     V3<T> rr = e + rot_delta<T>(q1.w, -u1, dp);
@@ -236,13 +276,14 @@ VX_HD void bond_force(const BondK<T>& k, int ax, V3<T> e, Q4<T> q1, Q4<T> q2, T 
     T nom = D + nomrel;
 
     // small/large angle hysteresis (:74-78); SmallTurn = (|z|+|y|)/x and ExtendPerc = x/NomDistance compared
-    // without forming the quotients
-    bool changed = false;
+    // without forming the quotients; non-short-circuit on purpose (no branches)
     T turn_num = vx_abs(rr.z) + vx_abs(rr.y);
-    bool is_small_w = (q12.w > (T)0) && (vv12 < (T)VX_SIN2_SMALL);
-    bool is_smallish_w = (q12.w > (T)0) && (vv12 < (T)VX_SIN2_SMALLISH);
-    if (!small && is_small_w && ratio_lt<T>(turn_num, rx, (T)VX_SA_BOND_BEND_RAD) && ratio_lt<T>(rx, nom, (T)VX_SA_BOND_EXT_PERC)) { small = true; changed = true; }
-    else if (small && (!is_smallish_w || ratio_gt<T>(turn_num, rx, (T)(VX_HYST * VX_SA_BOND_BEND_RAD)) || ratio_gt<T>(rx, nom, (T)(VX_HYST * VX_SA_BOND_EXT_PERC)))) { small = false; changed = true; }
+    bool is_small_w = (q12.w > (T)0) & (vv12 < (T)VX_SIN2_SMALL);
+    bool is_smallish_w = (q12.w > (T)0) & (vv12 < (T)VX_SIN2_SMALLISH);
+    bool to_small = !small & is_small_w & ratio_lt<T>(turn_num, rx, (T)VX_SA_BOND_BEND_RAD) & ratio_lt<T>(rx, nom, (T)VX_SA_BOND_EXT_PERC);
+    bool to_large = small & (!is_smallish_w | ratio_gt<T>(turn_num, rx, (T)(VX_HYST * VX_SA_BOND_BEND_RAD)) | ratio_gt<T>(rx, nom, (T)(VX_HYST * VX_SA_BOND_EXT_PERC)));
+    const bool changed = to_small | to_large;
+    small = (small | to_small) & !to_large;
 
     V3<T> p2, an1, an2;
     Q4<T> back;                               // conj(TotalRot): local -> world rotation
@@ -267,37 +308,38 @@ VX_HD void bond_force(const BondK<T>& k, int ax, V3<T> e, Q4<T> q1, Q4<T> q2, T 
     // heterogeneous fixed-point iteration (:226-258) converges in one pass to sigma = 2 E1 E2/(E1+E2) eps
     // (eps1 <- 2 s2/(s1+s2) eps gives s1 = s2 exactly), so the force is a constant times _Pos2.x.
     out.strain = p2.x * k.inv_len;
+    out.changed = changed;
     T fx = k.k_axial * p2.x;
 
-    // beam equations (:127-128, :153-154)
-    V3<T> F1 = mk3<T>(fx, k.b1 * p2.y - k.b2 * (an1.z + an2.z), k.b1 * p2.z + k.b2 * (an1.y + an2.y));
-    V3<T> F2 = -F1;
-    V3<T> M1 = mk3<T>(k.a2 * (an1.x - an2.x), k.b2 * p2.z + k.b3 * ((T)2 * an1.y + an2.y), -k.b2 * p2.y + k.b3 * ((T)2 * an1.z + an2.z));
-    V3<T> M2 = mk3<T>(k.a2 * (an2.x - an1.x), k.b2 * p2.z + k.b3 * (an1.y + (T)2 * an2.y), -k.b2 * p2.y + k.b3 * (an1.z + (T)2 * an2.z));
+    // beam equations (:127-128, :153-154) + damping (:157, :310-346).  The damping terms vanish by
+    // themselves when the rates are zero, which is what dt == 0 (first step) and a mode flip ask for.
+    const T dti = changed ? (T)0 : dt_inv;
+    V3<T> rv = (p2 - hist.p2) * dti;
+    V3<T> w1 = (an1 - hist.a1) * dti;
+    V3<T> w2 = (an2 - hist.a2) * dti;
+    const T bz = half_bond_z, hz = (T)0.5 * half_bond_z;          // 0.5 BondDampingZ, and half of it for the moments
+    T ey = k.b1 * p2.y - k.b2 * (an1.z + an2.z), ez = k.b1 * p2.z + k.b2 * (an1.y + an2.y);
+    T swz = w1.z + w2.z, swy = w1.y + w2.y;
+    V3<T> F1 = mk3<T>(fx + bz * (k.c_a1m1 * rv.x), ey + bz * (k.c_b1m1 * rv.y - k.c_b2fm1 * swz), ez + bz * (k.c_b1m1 * rv.z + k.c_b2fm1 * swy));
+    // Force2 = -Force1 for a homogeneous bond (:128, :166); with the voxel-2 damping constants the general
+    // expression reduces to exactly that when both voxels have the same mass, so no branch is needed
+    V3<T> F2 = mk3<T>(-fx - bz * (k.c_a1m2 * rv.x), -ey - bz * (k.c_b1m2 * rv.y - k.c_b2fm2 * swz), -ez - bz * (k.c_b1m2 * rv.z + k.c_b2fm2 * swy));
+    T tw = w2.x - w1.x;
+    T my = k.b2 * p2.z, mz = -k.b2 * p2.y;
+    V3<T> M1 = mk3<T>(k.a2 * (an1.x - an2.x) - hz * (k.c_a2i1 * tw),
+                      my + k.b3 * ((T)2 * an1.y + an2.y) + hz * (k.c_b2fm1 * rv.z + k.c_b3i1 * ((T)2 * w1.y + w2.y)),
+                      mz + k.b3 * ((T)2 * an1.z + an2.z) + hz * (-k.c_b2fm1 * rv.y + k.c_b3i1 * ((T)2 * w1.z + w2.z)));
+    V3<T> M2 = mk3<T>(k.a2 * (an2.x - an1.x) + hz * (k.c_a2i2 * tw),
+                      my + k.b3 * (an1.y + (T)2 * an2.y) + hz * (k.c_b2fm2 * rv.z + k.c_b3i2 * (w1.y + (T)2 * w2.y)),
+                      mz + k.b3 * (an1.z + (T)2 * an2.z) + hz * (-k.c_b2fm2 * rv.y + k.c_b3i2 * (w1.z + (T)2 * w2.z)));
+    hist.p2 = p2; hist.a1 = an1; hist.a2 = an2;
 
-    if (!changed) {                           // :157, :310-346
-        if (dt_inv != (T)0) {
-            T bz = half_bond_z;               // 0.5 * BondDampingZ
-            V3<T> rv = (p2 - hist.p2) * dt_inv;
-            V3<T> w1 = (an1 - hist.a1) * dt_inv;
-            V3<T> w2 = (an2 - hist.a2) * dt_inv;
-            F1 = F1 + mk3<T>(k.c_a1m1 * rv.x, k.c_b1m1 * rv.y - k.c_b2fm1 * (w1.z + w2.z), k.c_b1m1 * rv.z + k.c_b2fm1 * (w1.y + w2.y)) * bz;
-            if (!k.homogeneous)
-                F2 = F2 + mk3<T>(-k.c_a1m2 * rv.x, -k.c_b1m2 * rv.y + k.c_b2fm2 * (w1.z + w2.z), -k.c_b1m2 * rv.z - k.c_b2fm2 * (w1.y + w2.y)) * bz;
-            T hz = (T)0.5 * bz;
-            M1 = M1 + mk3<T>(-k.c_a2i1 * (w2.x - w1.x), k.c_b2fm1 * rv.z + k.c_b3i1 * ((T)2 * w1.y + w2.y), -k.c_b2fm1 * rv.y + k.c_b3i1 * ((T)2 * w1.z + w2.z)) * hz;
-            M2 = M2 + mk3<T>(k.c_a2i2 * (w2.x - w1.x), k.c_b2fm2 * rv.z + k.c_b3i2 * (w1.y + (T)2 * w2.y), -k.c_b2fm2 * rv.y + k.c_b3i2 * (w1.z + (T)2 * w2.z)) * hz;
-        }
-        hist.p2 = p2; hist.a1 = an1; hist.a2 = an2;
-    }
-
-    // back to the world frame (:161-170)
-    V3<T> ub = mk3<T>(back.x, back.y, back.z);
-    F1 = to_origdir(ax, rotate<T>(back.w, ub, F1));
-    if (k.homogeneous) F2 = -F1; else F2 = to_origdir(ax, rotate<T>(back.w, ub, F2));
-    M1 = to_origdir(ax, rotate<T>(back.w, ub, M1));
-    M2 = to_origdir(ax, rotate<T>(back.w, ub, M2));
-    out.f1 = F1; out.f2 = F2; out.m1 = M1; out.m2 = M2;
+    // back to the world frame (:161-170): one rotation matrix for the four vectors
+    const M33<T> Rm = rot_matrix(back);
+    out.f1 = to_origdir_c<AX>(mat_apply(Rm, F1));
+    out.f2 = to_origdir_c<AX>(mat_apply(Rm, F2));
+    out.m1 = to_origdir_c<AX>(mat_apply(Rm, M1));
+    out.m2 = to_origdir_c<AX>(mat_apply(Rm, M2));
 }
 
 // CVXS_BondCollision::CalcContactForce (VXS_BondCollision.cpp:41-59): force on voxel 2; voxel 1 gets the negative

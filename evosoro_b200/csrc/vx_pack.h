@@ -61,18 +61,17 @@ inline void pack_blob(const vxg_robot_desc* d, const BlobLayout& L, unsigned cha
     memset(blob, 0, L.total_bytes);
     RobotView<Real> R = make_view<Real>(blob, L, d->n_vox);
     const int nv = R.nv;
-    int16_t* nbr = (int16_t*)R.nbr; uint16_t* bcls = (uint16_t*)R.bcls; uint16_t* vcls = (uint16_t*)R.vcls;
-    for (int i = 0; i < 3 * nv; i++) nbr[i] = -1;
+    for (int i = 0; i < nv; i++) { R.stat[i].nbr[0] = R.stat[i].nbr[1] = R.stat[i].nbr[2] = -1; }
     for (int i = 0; i < d->n_vox; i++) {
         for (int a = 0; a < 3; a++) { R.pos[a * nv + i] = d->nom_pos[3 * i + a]; nom[a * nv + i] = d->nom_pos[3 * i + a]; }
-        R.quat[i] = (Real)1;            // Angle = identity (VXS_Voxel.cpp:98)
+        R.quat[i].x = (Real)1;          // Angle = identity (VXS_Voxel.cpp:98); stored (w,x,y,z)
         R.flags[i] = VX_FL_SMALL_ALL;   // SmallAngle = true (VXS_BondInternal.cpp:43)
-        vcls[i] = (uint16_t)d->vox_class[i];
+        R.stat[i].vcls = (uint16_t)d->vox_class[i];
     }
     for (int j = 0; j < d->n_bond; j++) {   // voxel bond_v1 (negative side) owns the bond
         int a = d->bond_axis[j], v1 = d->bond_v1[j];
-        nbr[a * nv + v1] = (int16_t)d->bond_v2[j];
-        bcls[a * nv + v1] = (uint16_t)d->bond_class[j];
+        R.stat[v1].nbr[a] = (int16_t)d->bond_v2[j];
+        R.stat[v1].bcls[a] = (uint16_t)d->bond_class[j];
     }
 }
 

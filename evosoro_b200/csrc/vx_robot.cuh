@@ -1,8 +1,13 @@
 // vx_robot.cuh -- per-robot state layout ("blob") and the per-voxel tasks of one timestep.
 //
-// One robot slot = one contiguous, SoA, fixed-stride blob in HBM so that a CTA can bulk-copy it into
-// shared memory, advance it K steps there and bulk-copy it back (DESIGN.md "Data layout").  The same
-// task functions run against a view of global memory when the robot does not fit on chip.
+// One robot slot = one contiguous, fixed-stride blob in HBM so that a CTA can bulk-copy it into shared
+// memory, advance it K steps there and bulk-copy it back (DESIGN.md "Data layout").  The same task
+// functions run against a view of global memory when the robot does not fit on chip.
+//
+// Inside the blob every array has stride `nv` (a power of two >= 64 chosen at vxg_create, a compile-time
+// constant in the kernels) and the words a thread needs together are grouped into 128-bit / 64-bit
+// vectors, so one LDS.128 / LDG.128 replaces four scalar loads and consecutive threads touch consecutive
+// vectors (bank-conflict free, fully coalesced).
 //
 // Task decomposition (replaces the serial bond loop + voxel loop of CVX_Sim::Integrate,
 // VX_Sim.cpp:1773-1776 and :1913): voxel v OWNS its +X, +Y, +Z bonds.  In the bond phase the owner
@@ -22,40 +27,65 @@ namespace vx {
 #define VX_FL_SMALL_ALL 0x7u
 #define VX_FL_STATIC_FRIC 0x8u // StaticFricFlag of the last step (VXS_Voxel.h:129)
 
-// number of Real planes in the dynamic section after the fp64 positions
-#define VX_N_HIST 27           // 3 owned bonds x (_LastPos2, _LastAngle1, _LastAngle2)
-#define VX_N_ACC 6
+template <typename T> struct alignas(4 * sizeof(T)) R4 { T x, y, z, w; };
+template <typename T> struct alignas(2 * sizeof(T)) R2 { T x, y; };
 
-struct BlobLayout {            // byte offsets inside one robot blob; all multiples of 16
-    int nv;                    // voxel stride (max_vox rounded up to 8)
+// static description of one voxel: one 128-bit word
+struct alignas(16) VoxStat {
+    int16_t nbr[3];    // index of the +X/+Y/+Z neighbour, -1 = no bond
+    uint16_t vcls;     // voxel class
+    uint16_t bcls[3];  // class of the owned +axis bond
+    uint16_t pad;
+};
+
+struct BlobLayout {            // byte offsets inside one robot blob; all multiples of 32
+    int nv;                    // voxel stride
     int real_size;
-    size_t off_pos, off_quat, off_lm, off_am, off_hist, off_flags;   // dynamic: copied in and out
+    // dynamic: copied in and out
+    size_t off_pos;            // double [3][nv]
+    size_t off_quat;           // R4 [nv]                     Angle (w,x,y,z) stored as (x=w, y=x, z=y, w=z)
+    size_t off_momA;           // R4 [nv]  LinMom.xyz, AngMom.x
+    size_t off_momB;           // R2 [nv]  AngMom.y, AngMom.z
+    size_t off_hist;           // per axis: R4 A[nv] (p2.xyz, a1.x), R4 B[nv] (a1.y, a1.z, a2.x, a2.y), Real C[nv] (a2.z)
+    size_t hist_axis_bytes;
+    size_t off_flags;          // uint32 [nv]
     size_t dyn_bytes;
-    size_t off_nbr, off_bcls, off_vcls;                               // static: copied in
+    // static: copied in
+    size_t off_stat;           // VoxStat [nv]
     size_t stat_bytes;         // dynamic + static
-    size_t off_accb;           // scratch: zero-initialised on chip, never written back
+    // scratch: zero-initialised on chip, never written back
+    size_t off_accA;           // R4 [nv]  Force.xyz, Moment.x received from the -axis neighbours
+    size_t off_accB;           // R2 [nv]  Moment.y, Moment.z
     size_t total_bytes;
 };
 
-VX_HD size_t vx_align16(size_t x) { return (x + 15) & ~(size_t)15; }
+VX_HD constexpr size_t vx_align16(size_t x) { return (x + 15) & ~(size_t)15; }
+VX_HD constexpr size_t vx_align32(size_t x) { return (x + 31) & ~(size_t)31; }
 
-inline BlobLayout make_layout(int max_vox, int real_size) {
-    BlobLayout L;
-    L.nv = (max_vox + 7) & ~7;
+// voxel stride used for a robot of up to max_vox voxels: the kernels are instantiated for these strides
+inline int stride_for(int max_vox) {
+    int nv = 64;
+    while (nv < max_vox) nv *= 2;
+    return nv;
+}
+
+VX_HD constexpr BlobLayout make_layout(int nv_in, int real_size) {
+    BlobLayout L{};
+    L.nv = nv_in;
     L.real_size = real_size;
-    size_t nv = (size_t)L.nv, rs = (size_t)real_size, o = 0;
-    L.off_pos = o;   o = vx_align16(o + 3 * nv * sizeof(double));
-    L.off_quat = o;  o = vx_align16(o + 4 * nv * rs);
-    L.off_lm = o;    o = vx_align16(o + 3 * nv * rs);
-    L.off_am = o;    o = vx_align16(o + 3 * nv * rs);
-    L.off_hist = o;  o = vx_align16(o + VX_N_HIST * nv * rs);
-    L.off_flags = o; o = vx_align16(o + nv * sizeof(uint32_t));
+    size_t nv = (size_t)nv_in, rs = (size_t)real_size, o = 0;
+    L.off_pos = o;   o = vx_align32(o + 3 * nv * sizeof(double));
+    L.off_quat = o;  o = vx_align32(o + 4 * nv * rs);
+    L.off_momA = o;  o = vx_align32(o + 4 * nv * rs);
+    L.off_momB = o;  o = vx_align32(o + 2 * nv * rs);
+    L.hist_axis_bytes = vx_align32(9 * nv * rs);
+    L.off_hist = o;  o = o + 3 * L.hist_axis_bytes;
+    L.off_flags = o; o = vx_align32(o + nv * sizeof(uint32_t));
     L.dyn_bytes = o;
-    L.off_nbr = o;   o = vx_align16(o + 3 * nv * sizeof(int16_t));
-    L.off_bcls = o;  o = vx_align16(o + 3 * nv * sizeof(uint16_t));
-    L.off_vcls = o;  o = vx_align16(o + nv * sizeof(uint16_t));
+    L.off_stat = o;  o = vx_align32(o + nv * sizeof(VoxStat));
     L.stat_bytes = o;
-    L.off_accb = o;  o = vx_align16(o + VX_N_ACC * nv * rs);
+    L.off_accA = o;  o = vx_align32(o + 4 * nv * rs);
+    L.off_accB = o;  o = vx_align32(o + 2 * nv * rs);
     L.total_bytes = o;
     return L;
 }
@@ -63,15 +93,18 @@ inline BlobLayout make_layout(int max_vox, int real_size) {
 template <typename Real> struct RobotView {
     int n_vox, nv;
     double* pos;          // [3][nv]
-    Real* quat;           // [4][nv] w,x,y,z planes
-    Real* lm;             // [3][nv]
-    Real* am;             // [3][nv]
-    Real* hist;           // [27][nv] plane = axis*9 + {p2.xyz, a1.xyz, a2.xyz}
+    R4<Real>* quat;       // [nv]
+    R4<Real>* momA;       // [nv]
+    R2<Real>* momB;       // [nv]
+    unsigned char* hist;  // 3 axis blocks
+    size_t hist_axis_bytes;
     uint32_t* flags;      // [nv]
-    const int16_t* nbr;   // [3][nv] index of the +axis neighbour, -1 = no bond
-    const uint16_t* bcls; // [3][nv] class of the owned +axis bond
-    const uint16_t* vcls; // [nv]
-    Real* accb;           // [6][nv] Force2/Moment2 received from the -axis neighbours
+    VoxStat* stat;        // [nv]
+    R4<Real>* accA;       // [nv]
+    R2<Real>* accB;       // [nv]
+    VX_HD R4<Real>* histA(int ax) const { return (R4<Real>*)(hist + (size_t)ax * hist_axis_bytes); }
+    VX_HD R4<Real>* histB(int ax) const { return (R4<Real>*)(hist + (size_t)ax * hist_axis_bytes) + nv; }
+    VX_HD Real* histC(int ax) const { return (Real*)((R4<Real>*)(hist + (size_t)ax * hist_axis_bytes) + 2 * (size_t)nv); }
 };
 
 template <typename Real>
@@ -79,15 +112,15 @@ VX_HD RobotView<Real> make_view(unsigned char* base, const BlobLayout& L, int n_
     RobotView<Real> v;
     v.n_vox = n_vox; v.nv = L.nv;
     v.pos = (double*)(base + L.off_pos);
-    v.quat = (Real*)(base + L.off_quat);
-    v.lm = (Real*)(base + L.off_lm);
-    v.am = (Real*)(base + L.off_am);
-    v.hist = (Real*)(base + L.off_hist);
+    v.quat = (R4<Real>*)(base + L.off_quat);
+    v.momA = (R4<Real>*)(base + L.off_momA);
+    v.momB = (R2<Real>*)(base + L.off_momB);
+    v.hist = base + L.off_hist;
+    v.hist_axis_bytes = L.hist_axis_bytes;
     v.flags = (uint32_t*)(base + L.off_flags);
-    v.nbr = (const int16_t*)(base + L.off_nbr);
-    v.bcls = (const uint16_t*)(base + L.off_bcls);
-    v.vcls = (const uint16_t*)(base + L.off_vcls);
-    v.accb = (Real*)(base + L.off_accb);
+    v.stat = (VoxStat*)(base + L.off_stat);
+    v.accA = (R4<Real>*)(base + L.off_accA);
+    v.accB = (R2<Real>*)(base + L.off_accB);
     return v;
 }
 
@@ -106,49 +139,61 @@ template <typename Real> struct RobotConsts {
     bool floor_on, sticky;
 };
 
-// optional per-bond outputs of the last step (vxg_download_state): [13][3][nv] planes
-template <typename Real> struct BondRecord { Real* out; };   // out == nullptr: do not record
+// The owner's own position and orientation, loaded once per step and reused by its three bonds.
+template <typename Real> struct OwnState { double px, py, pz; R4<Real> q; };
+template <typename Real> VX_HD OwnState<Real> load_own(const RobotView<Real>& R, int v) {
+    OwnState<Real> o;
+    o.px = R.pos[v]; o.py = R.pos[R.nv + v]; o.pz = R.pos[2 * R.nv + v]; o.q = R.quat[v];
+    return o;
+}
+// The neighbour's share of one bond, waiting to be added to the neighbour's accumulator.
+template <typename Real> struct BondPush { int w; V3<Real> f2, m2; };   // w < 0: nothing to push
 
-// Bond (v, axis): evaluate, push the neighbour's share, return the owner's share in (F, M) +=.
-// Returns true when the bond diverged (strain > 100, VX_Sim.cpp:1775).
-template <typename Real>
-VX_HD bool bond_task(const RobotView<Real>& R, const RobotConsts<Real>& C, int v, int ax, Real dt_inv,
-                     V3<Real>& F, V3<Real>& M, Real* rec) {
+// Bond (v, AX): evaluate; the owner's share goes into (F, M) +=, the neighbour's share into `p`.
+// `st` is the owner's static word, `fl` its flags word, `own` its position/orientation (all kept in
+// registers across the three axes by the caller).  rec != nullptr: also store the bond outputs
+// ([39][nv] planes, vxg_download_state).  Touches no accumulator, so it needs no ordering against the
+// other voxels' pushes.  Returns true when the bond diverged (strain > 100, VX_Sim.cpp:1775).
+template <typename Real, int AX>
+VX_HD bool bond_eval(const RobotView<Real>& R, const RobotConsts<Real>& C, int v, const VoxStat& st, const OwnState<Real>& own,
+                     uint32_t& fl, Real dt_inv, V3<Real>& F, V3<Real>& M, Real* rec, BondPush<Real>& p) {
     const int nv = R.nv;
-    int w = R.nbr[ax * nv + v];
+    const int w = st.nbr[AX];
+    p.w = w;
     if (w < 0) return false;
-    int bc = R.bcls[ax * nv + v];
-    const BondK<Real>& k = C.bk[bc];
+    const int bc = st.bcls[AX];
+    const BondK<Real> k = C.bk[bc];
     // bond vector in fp64, pitch removed before narrowing (VXS_BondInternal.cpp:58)
-    V3<double> dp = mk3<double>(R.pos[w] - R.pos[v], R.pos[nv + w] - R.pos[nv + v], R.pos[2 * nv + w] - R.pos[2 * nv + v]);
-    dp = to_xdir(ax, dp);
-    V3<Real> e = mk3<Real>((Real)(dp.x - C.bk_dist[bc]), (Real)dp.y, (Real)dp.z);
+    double dpa[3] = {R.pos[w] - own.px, R.pos[nv + w] - own.py, R.pos[2 * nv + w] - own.pz};
+    dpa[AX] -= C.bk_dist[bc];
+    V3<Real> e = mk3<Real>((Real)dpa[0], (Real)dpa[1], (Real)dpa[2]);
+    const R4<Real> qa = own.q, qb = R.quat[w];
     Q4<Real> q1, q2;
-    {
-        V3<Real> u1 = to_xdir(ax, mk3<Real>(R.quat[nv + v], R.quat[2 * nv + v], R.quat[3 * nv + v]));
-        V3<Real> u2 = to_xdir(ax, mk3<Real>(R.quat[nv + w], R.quat[2 * nv + w], R.quat[3 * nv + w]));
-        q1.w = R.quat[v]; q1.x = u1.x; q1.y = u1.y; q1.z = u1.z;
-        q2.w = R.quat[w]; q2.x = u2.x; q2.y = u2.y; q2.z = u2.z;
-    }
-    Real dnom = (Real)0.5 * (C.dsc_c[R.vcls[v]] + C.dsc_c[R.vcls[w]]);
-    uint32_t fl = R.flags[v];
-    bool small = (fl >> ax) & 1u;
+    q1.w = qa.x; q1.x = qa.y; q1.y = qa.z; q1.z = qa.w;
+    q2.w = qb.x; q2.x = qb.y; q2.y = qb.z; q2.z = qb.w;
+    Real dnom = (Real)0.5 * (C.dsc_c[st.vcls] + C.dsc_c[R.stat[w].vcls]);
+    bool small = (fl >> AX) & 1u;
+    R4<Real>* hA = R.histA(AX) + v; R4<Real>* hB = R.histB(AX) + v; Real* hC = R.histC(AX) + v;
     BondHist<Real> h;
-    Real* hp = R.hist + (size_t)(ax * 9) * nv + v;
-    h.p2 = mk3<Real>(hp[0], hp[nv], hp[2 * nv]);
-    h.a1 = mk3<Real>(hp[3 * nv], hp[4 * nv], hp[5 * nv]);
-    h.a2 = mk3<Real>(hp[6 * nv], hp[7 * nv], hp[8 * nv]);
+    {
+        const R4<Real> a = *hA, b = *hB; const Real c = *hC;
+        h.p2 = mk3<Real>(a.x, a.y, a.z);
+        h.a1 = mk3<Real>(a.w, b.x, b.y);
+        h.a2 = mk3<Real>(b.z, b.w, c);
+    }
     BondOut<Real> o;
-    bond_force<Real>(k, ax, e, q1, q2, dnom, C.half_bond_z, dt_inv, small, h, o);
-    hp[0] = h.p2.x; hp[nv] = h.p2.y; hp[2 * nv] = h.p2.z;
-    hp[3 * nv] = h.a1.x; hp[4 * nv] = h.a1.y; hp[5 * nv] = h.a1.z;
-    hp[6 * nv] = h.a2.x; hp[7 * nv] = h.a2.y; hp[8 * nv] = h.a2.z;
-    R.flags[v] = (fl & ~(1u << ax)) | ((small ? 1u : 0u) << ax);
+    bond_force<AX, Real>(k, e, q1, q2, dnom, C.half_bond_z, dt_inv, small, h, o);
+    if (!o.changed) {   // _LastPos2/_LastAngle* keep their values on a mode-flip step (VXS_BondInternal.cpp:157)
+        R4<Real> a, b;
+        a.x = h.p2.x; a.y = h.p2.y; a.z = h.p2.z; a.w = h.a1.x;
+        b.x = h.a1.y; b.y = h.a1.z; b.z = h.a2.x; b.w = h.a2.y;
+        *hA = a; *hB = b; *hC = h.a2.z;
+    }
+    fl = (fl & ~(1u << AX)) | ((small ? 1u : 0u) << AX);
     F = F + o.f1; M = M + o.m1;
-    R.accb[w] += o.f2.x; R.accb[nv + w] += o.f2.y; R.accb[2 * nv + w] += o.f2.z;
-    R.accb[3 * nv + w] += o.m2.x; R.accb[4 * nv + w] += o.m2.y; R.accb[5 * nv + w] += o.m2.z;
+    p.f2 = o.f2; p.m2 = o.m2;
     if (rec) {
-        Real* r = rec + (size_t)(ax * 13) * nv + v;
+        Real* r = rec + (size_t)(AX * 13) * nv + v;
         r[0] = o.f1.x; r[nv] = o.f1.y; r[2 * nv] = o.f1.z; r[3 * nv] = o.f2.x; r[4 * nv] = o.f2.y; r[5 * nv] = o.f2.z;
         r[6 * nv] = o.m1.x; r[7 * nv] = o.m1.y; r[8 * nv] = o.m1.z; r[9 * nv] = o.m2.x; r[10 * nv] = o.m2.y; r[11 * nv] = o.m2.z;
         r[12 * nv] = o.strain;
@@ -156,29 +201,60 @@ VX_HD bool bond_task(const RobotView<Real>& R, const RobotConsts<Real>& C, int v
     return o.strain > (Real)100;
 }
 
+// Add the neighbour's share to its accumulator.  Within one axis sub-phase every accumulator has exactly
+// one writer; sub-phases of different axes must be ordered (barrier) by the caller.
+template <typename Real>
+VX_HD void bond_push(const RobotView<Real>& R, const BondPush<Real>& p) {
+    if (p.w < 0) return;
+    R4<Real> a = R.accA[p.w]; R2<Real> b = R.accB[p.w];
+    a.x += p.f2.x; a.y += p.f2.y; a.z += p.f2.z; a.w += p.m2.x;
+    b.x += p.m2.y; b.y += p.m2.z;
+    R.accA[p.w] = a; R.accB[p.w] = b;
+}
+
+template <typename Real, int AX>
+VX_HD bool bond_task(const RobotView<Real>& R, const RobotConsts<Real>& C, int v, const VoxStat& st, uint32_t& fl,
+                     Real dt_inv, V3<Real>& F, V3<Real>& M, Real* rec) {
+    BondPush<Real> p;
+    bool d = bond_eval<Real, AX>(R, C, v, st, load_own<Real>(R, v), fl, dt_inv, F, M, rec, p);
+    bond_push<Real>(R, p);
+    return d;
+}
+
 // Voxel v: total force/moment = own share + received share; integrate (EulerStep).
 template <typename Real>
-VX_HD void voxel_task(const RobotView<Real>& R, const RobotConsts<Real>& C, int v, V3<Real> F, V3<Real> M) {
+VX_HD void voxel_task(const RobotView<Real>& R, const RobotConsts<Real>& C, int v, const VoxStat& st, const OwnState<Real>& own,
+                      uint32_t fl, V3<Real> F, V3<Real> M) {
     const int nv = R.nv;
-    F = F + mk3<Real>(R.accb[v], R.accb[nv + v], R.accb[2 * nv + v]);
-    M = M + mk3<Real>(R.accb[3 * nv + v], R.accb[4 * nv + v], R.accb[5 * nv + v]);
-    R.accb[v] = 0; R.accb[nv + v] = 0; R.accb[2 * nv + v] = 0; R.accb[3 * nv + v] = 0; R.accb[4 * nv + v] = 0; R.accb[5 * nv + v] = 0;
-    int vc = R.vcls[v];
-    const VoxK<Real>& k = C.vk[vc];
+    {
+        const R4<Real> a = R.accA[v]; const R2<Real> b = R.accB[v];
+        F = F + mk3<Real>(a.x, a.y, a.z);
+        M = M + mk3<Real>(a.w, b.x, b.y);
+        R4<Real> za; za.x = za.y = za.z = za.w = (Real)0; R2<Real> zb; zb.x = zb.y = (Real)0;
+        R.accA[v] = za; R.accB[v] = zb;
+    }
+    const int vc = st.vcls;
+    const VoxK<Real> k = C.vk[vc];
     VoxState<Real> s;
-    s.px = R.pos[v]; s.py = R.pos[nv + v]; s.pz = R.pos[2 * nv + v];
-    s.q.w = R.quat[v]; s.q.x = R.quat[nv + v]; s.q.y = R.quat[2 * nv + v]; s.q.z = R.quat[3 * nv + v];
-    s.lm = mk3<Real>(R.lm[v], R.lm[nv + v], R.lm[2 * nv + v]);
-    s.am = mk3<Real>(R.am[v], R.am[nv + v], R.am[2 * nv + v]);
+    s.px = own.px; s.py = own.py; s.pz = own.pz;
+    {
+        const R4<Real> q = own.q, a = R.momA[v]; const R2<Real> b = R.momB[v];
+        s.q.w = q.x; s.q.x = q.y; s.q.y = q.z; s.q.z = q.w;
+        s.lm = mk3<Real>(a.x, a.y, a.z);
+        s.am = mk3<Real>(a.w, b.x, b.y);
+    }
     double nom[3] = {0, 0, 0};
     if (k.has_bc) { nom[0] = C.nom[v]; nom[1] = C.nom[nv + v]; nom[2] = C.nom[2 * nv + v]; }
     bool sf = voxel_integrate<Real>(k, F, M, 0.5 * C.scale_c[vc], C.floor_on, C.sticky, C.dt, nom,
                                     C.ext_disp + 3 * vc, C.ext_tdisp + 3 * vc, s);
     R.pos[v] = s.px; R.pos[nv + v] = s.py; R.pos[2 * nv + v] = s.pz;
-    R.quat[v] = s.q.w; R.quat[nv + v] = s.q.x; R.quat[2 * nv + v] = s.q.y; R.quat[3 * nv + v] = s.q.z;
-    R.lm[v] = s.lm.x; R.lm[nv + v] = s.lm.y; R.lm[2 * nv + v] = s.lm.z;
-    R.am[v] = s.am.x; R.am[nv + v] = s.am.y; R.am[2 * nv + v] = s.am.z;
-    uint32_t fl = R.flags[v];
+    {
+        R4<Real> q, a; R2<Real> b;
+        q.x = s.q.w; q.y = s.q.x; q.z = s.q.y; q.w = s.q.z;
+        a.x = s.lm.x; a.y = s.lm.y; a.z = s.lm.z; a.w = s.am.x;
+        b.x = s.am.y; b.y = s.am.z;
+        R.quat[v] = q; R.momA[v] = a; R.momB[v] = b;
+    }
     R.flags[v] = sf ? (fl | VX_FL_STATIC_FRIC) : (fl & ~VX_FL_STATIC_FRIC);
 }
 

@@ -92,28 +92,29 @@ template <typename Real> static BatchDev<Real> dev_view(const vxg_batch* b) {
     return B;
 }
 
-template <typename Real, int VPT, bool SMEM>
+template <typename Real, int NV, int VPT, bool SMEM>
 static cudaError_t launch_step(vxg_batch* b, int n_steps, int record) {
-    auto kern = vx_step_kernel<Real, VPT, SMEM>;
+    auto kern = vx_step_kernel<Real, NV, VPT, SMEM>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes);
     if (e != cudaSuccess) return e;
-    kern<<<b->n_robots, b->threads, b->smem_bytes, b->stream>>>(dev_view<Real>(b), n_steps, record);
+    kern<<<b->n_robots, NV / VPT, b->smem_bytes, b->stream>>>(dev_view<Real>(b), n_steps, record);
     return cudaGetLastError();
 }
 
+template <typename Real, bool SMEM> static cudaError_t launch_step_s(vxg_batch* b, int n_steps, int record) {
+    switch (b->L.nv) {   // strides the kernels are instantiated for (stride_for); <= 512 threads per CTA
+        case 64: return launch_step<Real, 64, 1, SMEM>(b, n_steps, record);
+        case 128: return launch_step<Real, 128, 1, SMEM>(b, n_steps, record);
+        case 256: return launch_step<Real, 256, 1, SMEM>(b, n_steps, record);
+        case 512: return launch_step<Real, 512, 1, SMEM>(b, n_steps, record);
+        case 1024: return launch_step<Real, 1024, 2, SMEM>(b, n_steps, record);
+        case 2048: return launch_step<Real, 2048, 4, SMEM>(b, n_steps, record);
+    }
+    return cudaErrorInvalidValue;
+}
+
 template <typename Real> static cudaError_t launch_step_p(vxg_batch* b, int n_steps, int record) {
-    if (b->smem_mode) {
-        switch (b->vpt) {
-            case 1: return launch_step<Real, 1, true>(b, n_steps, record);
-            case 2: return launch_step<Real, 2, true>(b, n_steps, record);
-            default: return launch_step<Real, 4, true>(b, n_steps, record);
-        }
-    }
-    switch (b->vpt) {
-        case 1: return launch_step<Real, 1, false>(b, n_steps, record);
-        case 2: return launch_step<Real, 2, false>(b, n_steps, record);
-        default: return launch_step<Real, 4, false>(b, n_steps, record);
-    }
+    return b->smem_mode ? launch_step_s<Real, true>(b, n_steps, record) : launch_step_s<Real, false>(b, n_steps, record);
 }
 
 static void free_all(vxg_batch* b) {
@@ -142,13 +143,11 @@ extern "C" int vxg_create(vxg_batch** out, int device, int n_robots, const vxg_l
     CK(cudaSetDevice(device));
     vxg_batch* b = new vxg_batch;
     b->device = device; b->n_robots = n_robots; b->lim = *lim; b->prec = lim->precision;
-    b->L = make_layout(lim->max_vox, (int)b->rs());
-    // thread mapping: smallest VPT with <= 512 threads
-    int vpt = 1;
-    while (vpt < 4 && (lim->max_vox + vpt - 1) / vpt > 512) vpt *= 2;
-    if ((lim->max_vox + vpt - 1) / vpt > 512) { delete b; return fail(VXG_UNSUPPORTED_SIZE, "vxg_create: more than 2048 voxels per robot is not supported yet"); }
-    b->vpt = vpt;
-    b->threads = (((lim->max_vox + vpt - 1) / vpt) + 31) & ~31;
+    if (lim->max_vox > 2048) { delete b; return fail(VXG_UNSUPPORTED_SIZE, "vxg_create: more than 2048 voxels per robot is not supported yet"); }
+    b->L = make_layout(stride_for(lim->max_vox), (int)b->rs());
+    // thread mapping: <= 512 threads per CTA, VPT voxels per thread
+    b->vpt = b->L.nv <= 512 ? 1 : b->L.nv / 512;
+    b->threads = b->L.nv / b->vpt;
     size_t tb = b->prec == VXG_PREC_F64 ? tables_bytes<double>(lim->max_vclass, lim->max_bclass) : tables_bytes<float>(lim->max_vclass, lim->max_bclass);
     int max_smem = 0;
     CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
@@ -388,11 +387,12 @@ template <typename Real> static void unpack_state(vxg_batch* b, int robot, vxg_r
     const int nv = R.nv;
     const double* sc = b->h_scale_c + (size_t)robot * b->lim.max_vclass;
     for (int i = 0; i < c.n_vox; i++) {
+        const R4<Real> q = R.quat[i], ma = R.momA[i]; const R2<Real> mb = R.momB[i];
         if (o->pos) for (int a = 0; a < 3; a++) o->pos[3 * i + a] = R.pos[a * nv + i];
-        if (o->quat) for (int a = 0; a < 4; a++) o->quat[4 * i + a] = (double)R.quat[a * nv + i];
-        if (o->lin_mom) for (int a = 0; a < 3; a++) o->lin_mom[3 * i + a] = (double)R.lm[a * nv + i];
-        if (o->ang_mom) for (int a = 0; a < 3; a++) o->ang_mom[3 * i + a] = (double)R.am[a * nv + i];
-        if (o->scale) o->scale[i] = sc[R.vcls[i]];
+        if (o->quat) { o->quat[4 * i] = (double)q.x; o->quat[4 * i + 1] = (double)q.y; o->quat[4 * i + 2] = (double)q.z; o->quat[4 * i + 3] = (double)q.w; }
+        if (o->lin_mom) { o->lin_mom[3 * i] = (double)ma.x; o->lin_mom[3 * i + 1] = (double)ma.y; o->lin_mom[3 * i + 2] = (double)ma.z; }
+        if (o->ang_mom) { o->ang_mom[3 * i] = (double)ma.w; o->ang_mom[3 * i + 1] = (double)mb.x; o->ang_mom[3 * i + 2] = (double)mb.y; }
+        if (o->scale) o->scale[i] = sc[R.stat[i].vcls];
         if (o->static_fric) o->static_fric[i] = (R.flags[i] & VX_FL_STATIC_FRIC) ? 1 : 0;
     }
 }
@@ -429,7 +429,7 @@ extern "C" int vxg_download_state(vxg_batch* b, int robot, vxg_robot_state* o) {
     }
     if (o->bond_small_angle) {
         const unsigned char* blob = b->h_blobs + (size_t)robot * b->L.total_bytes;
-        const uint32_t* fl = (const uint32_t*)(blob + b->L.off_flags);
+        const uint32_t* fl = (const uint32_t*)(blob + b->L.off_flags);   // flags plane is precision-independent
         for (int j = 0; j < nb; j++) o->bond_small_angle[j] = (fl[b->bond_v1[robot][j]] >> b->bond_axis[robot][j]) & 1u;
     }
     return VXG_OK;
@@ -441,9 +441,9 @@ template <typename Real> static void pack_state(vxg_batch* b, int robot, const v
     const int nv = R.nv;
     for (int i = 0; i < c.n_vox; i++) {
         if (in->pos) for (int a = 0; a < 3; a++) R.pos[a * nv + i] = in->pos[3 * i + a];
-        if (in->quat) for (int a = 0; a < 4; a++) R.quat[a * nv + i] = (Real)in->quat[4 * i + a];
-        if (in->lin_mom) for (int a = 0; a < 3; a++) R.lm[a * nv + i] = (Real)in->lin_mom[3 * i + a];
-        if (in->ang_mom) for (int a = 0; a < 3; a++) R.am[a * nv + i] = (Real)in->ang_mom[3 * i + a];
+        if (in->quat) { R.quat[i].x = (Real)in->quat[4 * i]; R.quat[i].y = (Real)in->quat[4 * i + 1]; R.quat[i].z = (Real)in->quat[4 * i + 2]; R.quat[i].w = (Real)in->quat[4 * i + 3]; }
+        if (in->lin_mom) { R.momA[i].x = (Real)in->lin_mom[3 * i]; R.momA[i].y = (Real)in->lin_mom[3 * i + 1]; R.momA[i].z = (Real)in->lin_mom[3 * i + 2]; }
+        if (in->ang_mom) { R.momA[i].w = (Real)in->ang_mom[3 * i]; R.momB[i].x = (Real)in->ang_mom[3 * i + 1]; R.momB[i].y = (Real)in->ang_mom[3 * i + 2]; }
     }
 }
 

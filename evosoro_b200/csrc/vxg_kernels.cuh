@@ -1,14 +1,16 @@
 // vxg_kernels.cuh -- sm_100a kernels of the Voxelyze timestep engine.
 //
-//   vx_step_kernel<Real, VPT, SMEM>  one CTA per robot; advances the robot `n_steps` timesteps.
+//   vx_step_kernel<Real, NV, VPT, SMEM>  one CTA per robot; advances the robot `n_steps` timesteps.
+//       NV           : voxel stride of the blob (compile-time: every array offset is an immediate);
+//                     the CTA has NV / VPT threads.
 //       SMEM = true : the robot blob is staged into shared memory once, all steps run on chip, the
 //                     dynamic section is written back at the end (HBM traffic = blob in + blob out per
 //                     LAUNCH, not per step).
 //       SMEM = false: same code against the blob in global memory (robots larger than ~227 KB of
 //                     state, e.g. the fp64 mode at 10^3); the working set of the 148 resident robots
 //                     lives in L2.
-//       VPT          : voxels per thread (thread t owns voxels t, t+T, ...), so a 10^3 robot runs with
-//                     512 threads x 2 voxels and <=128 registers per thread.
+//       VPT          : voxels per thread (thread t owns voxels t, t+T, ...), so a 10^3 robot (NV = 1024) runs
+//                     with 512 threads x 2 voxels and <=128 registers per thread.
 //   vx_stats_kernel<Real>            one CTA per robot; reductions for the result writer.
 //
 // Replaces CVX_Sim::Integrate (VX_Sim.cpp:1763-1933); see vx_robot.cuh / vx_math.cuh for the
@@ -50,6 +52,7 @@ template <typename Real> struct SmemTables {
     Real* dsc_c;      // [2][max_vclass]
     Real* ext_disp; Real* ext_tdisp;
     double* red;      // [4][32] reduction scratch
+    unsigned long long* mbar;   // split-phase barrier between the axis sub-phases
 };
 
 template <typename Real>
@@ -64,6 +67,7 @@ __host__ __device__ inline size_t tables_bytes(int max_vclass, int max_bclass) {
     o = vx_align16(o + sizeof(Real) * 3 * max_vclass);
     o = vx_align16(o + sizeof(Real) * 3 * max_vclass);
     o = vx_align16(o + sizeof(double) * 4 * 32);
+    o = vx_align16(o + sizeof(unsigned long long));
     return o;
 }
 
@@ -78,7 +82,8 @@ __device__ inline SmemTables<Real> carve_tables(unsigned char* p, int max_vclass
     t.dsc_c = (Real*)(p + o);       o = vx_align16(o + sizeof(Real) * 2 * max_vclass);
     t.ext_disp = (Real*)(p + o);    o = vx_align16(o + sizeof(Real) * 3 * max_vclass);
     t.ext_tdisp = (Real*)(p + o);   o = vx_align16(o + sizeof(Real) * 3 * max_vclass);
-    t.red = (double*)(p + o);
+    t.red = (double*)(p + o);       o = vx_align16(o + sizeof(double) * 4 * 32);
+    t.mbar = (unsigned long long*)(p + o);
     return t;
 }
 
@@ -91,6 +96,29 @@ __device__ inline void copy4(void* dst, const void* src, size_t bytes, int tid, 
     const uint32_t* s = (const uint32_t*)src; uint32_t* d = (uint32_t*)dst;
     size_t n = bytes >> 2;
     for (size_t i = tid; i < n; i += nthreads) d[i] = s[i];
+}
+
+// Split-phase CTA barrier (mbarrier): a warp ARRIVES once its accumulator pushes of one axis are done and
+// only WAITS right before its pushes of the next axis, so the whole bond evaluation in between hides the
+// barrier latency.  One arrival per warp (after __syncwarp, which orders the other lanes' stores).
+__device__ inline unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ inline void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ inline void mbar_arrive_warp(unsigned long long* bar) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ inline void mbar_wait(unsigned long long* bar, unsigned int parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "VX_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra VX_MBAR_DONE;\n"
+        "bra VX_MBAR_WAIT;\n"
+        "VX_MBAR_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
 __device__ inline double warp_sum(double x) {
@@ -109,11 +137,13 @@ __device__ inline void block_sum4(double& a, double& b, double& c, double& d, do
     for (int i = 0; i < nw; i++) { a += red[i]; b += red[32 + i]; c += red[64 + i]; d += red[96 + i]; }
 }
 
-template <typename Real, int VPT, bool SMEM>
-__global__ void __launch_bounds__(512, 1) vx_step_kernel(BatchDev<Real> B, int n_steps, int record_bonds) {
-    extern __shared__ __align__(16) unsigned char smem[];
+template <typename Real, int NV, int VPT, bool SMEM>
+__global__ void __launch_bounds__(NV / VPT, 1) vx_step_kernel(BatchDev<Real> B, int n_steps, int record_bonds) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int T = NV / VPT;
+    constexpr BlobLayout L = make_layout(NV, (int)sizeof(Real));
     const int robot = blockIdx.x;
-    const int tid = threadIdx.x, T = blockDim.x;
+    const int tid = threadIdx.x;
     RobotCtl* ctlp = B.ctl + robot;
     const unsigned int status0 = ctlp->status;
     if (status0 & (VXG_ST_DIVERGED_ | VXG_ST_FINISHED_)) return;
@@ -122,7 +152,6 @@ __global__ void __launch_bounds__(512, 1) vx_step_kernel(BatchDev<Real> B, int n
     int nsteps = remaining < (long long)n_steps ? (int)remaining : n_steps;
     if (nsteps <= 0) { if (tid == 0) ctlp->status = status0 | VXG_ST_FINISHED_; return; }
 
-    const BlobLayout L = B.L;
     unsigned char* gblob = B.blobs + (size_t)robot * L.total_bytes;
     unsigned char* base = SMEM ? smem : gblob;
     unsigned char* tab = SMEM ? smem + L.total_bytes : smem;
@@ -135,8 +164,8 @@ __global__ void __launch_bounds__(512, 1) vx_step_kernel(BatchDev<Real> B, int n
         copy16(smem, gblob, L.stat_bytes, tid, T);
         // zero the accumulators
         uint4 z = make_uint4(0, 0, 0, 0);
-        uint4* a = (uint4*)(smem + L.off_accb);
-        for (size_t i = tid; i < ((L.total_bytes - L.off_accb) >> 4); i += T) a[i] = z;
+        uint4* a = (uint4*)(smem + L.off_accA);
+        for (size_t i = tid; i < ((L.total_bytes - L.off_accA) >> 4); i += T) a[i] = z;
     }
     copy4(S.bk, B.bk + (size_t)robot * B.max_bclass, sizeof(BondK<Real>) * n_bc, tid, T);
     copy4(S.vk, B.vk + (size_t)robot * B.max_vclass, sizeof(VoxK<Real>) * n_vc, tid, T);
@@ -149,14 +178,16 @@ __global__ void __launch_bounds__(512, 1) vx_step_kernel(BatchDev<Real> B, int n
         S.ext_disp[i] = B.ext_disp[(size_t)robot * B.max_vclass * 3 + i];
         S.ext_tdisp[i] = B.ext_tdisp[(size_t)robot * B.max_vclass * 3 + i];
     }
+    if (tid == 0) mbar_init(S.mbar, T / 32);
     __syncthreads();
     for (int i = tid; i < n_vc; i += T) S.dsc_c[i] = (Real)(S.scale_c[i] - S.sk[i].nom_size);
     __syncthreads();
+    unsigned int mpar = 0;
 
     RobotView<Real> R = make_view<Real>(base, L, n_vox);
     RobotConsts<Real> C;
     C.bk = S.bk; C.bk_dist = S.bk_dist; C.vk = S.vk;
-    C.nom = B.nom + (size_t)robot * 3 * L.nv;
+    C.nom = B.nom + (size_t)robot * 3 * NV;
     C.ext_disp = S.ext_disp; C.ext_tdisp = S.ext_tdisp;
     C.half_bond_z = (Real)ctlp->half_bond_z;
     const double dt = ctlp->dt;
@@ -168,7 +199,7 @@ __global__ void __launch_bounds__(512, 1) vx_step_kernel(BatchDev<Real> B, int n
     const double init_cm = ctlp->init_cm_time, tper = ctlp->temp_period, tamp = ctlp->temp_amplitude;
     const double minf = ctlp->min_fact, maxf = ctlp->max_fact;
     const Real dt_inv_run = (Real)(1.0 / dt);
-    Real* rec_base = (record_bonds && B.bond_rec) ? B.bond_rec + (size_t)robot * 39 * L.nv : nullptr;
+    Real* rec_base = (record_bonds && B.bond_rec) ? B.bond_rec + (size_t)robot * 39 * NV : nullptr;
 
     double t = ctlp->cur_time;
     int cur = 0;
@@ -179,8 +210,8 @@ __global__ void __launch_bounds__(512, 1) vx_step_kernel(BatchDev<Real> B, int n
         if (s == latch) {   // IniCM = SS.CurCM at TimeStep entry (VX_Sim.cpp:1064-1075): COM after the previous step
             double mx = 0, my = 0, mz = 0, mm = 0;
             for (int v = tid; v < n_vox; v += T) {
-                double m = (double)S.vk[R.vcls[v]].mass;
-                mx += R.pos[v] * m; my += R.pos[R.nv + v] * m; mz += R.pos[2 * R.nv + v] * m; mm += m;
+                double m = (double)S.vk[R.stat[v].vcls].mass;
+                mx += R.pos[v] * m; my += R.pos[NV + v] * m; mz += R.pos[2 * NV + v] * m; mm += m;
             }
             block_sum4(mx, my, mz, mm, S.red);
             if (tid == 0) { ctlp->ini_com[0] = mx / mm; ctlp->ini_com[1] = my / mm; ctlp->ini_com[2] = mz / mm; ctlp->ini_latched = 1; }
@@ -191,31 +222,53 @@ __global__ void __launch_bounds__(512, 1) vx_step_kernel(BatchDev<Real> B, int n
         Real* rec = (k == nsteps - 1) ? rec_base : nullptr;
 
         V3<Real> F[VPT], M[VPT];
+        VoxStat st[VPT];
+        OwnState<Real> own[VPT];
+        BondPush<Real> P[VPT];
+        uint32_t fl[VPT];
 #pragma unroll
-        for (int j = 0; j < VPT; j++) { F[j] = mk3<Real>(0, 0, 0); M[j] = mk3<Real>(0, 0, 0); }
-        int div = 0;
-#pragma unroll 1
-        for (int ax = 0; ax < 3; ax++) {
-#pragma unroll
-            for (int j = 0; j < VPT; j++) {
-                int v = tid + j * T;
-                if (v < n_vox) div |= bond_task<Real>(R, C, v, ax, dt_inv, F[j], M[j], rec) ? 1 : 0;
-            }
-            if (ax < 2) __syncthreads();
+        for (int j = 0; j < VPT; j++) {
+            F[j] = mk3<Real>(0, 0, 0); M[j] = mk3<Real>(0, 0, 0);
+            st[j] = R.stat[tid + j * T];
+            fl[j] = R.flags[tid + j * T];
+            own[j] = load_own<Real>(R, tid + j * T);
         }
+        // Scale of every class for the NEXT step, from CurTime before the increment (VXS_Voxel.cpp:224-336).
+        // It depends on time only, so it is evaluated here, off the critical path, by the highest threads
+        // of the CTA (the last warp owns the fewest voxels); it lands in the other half of the double buffer,
+        // which nobody reads before the end-of-step barrier.
+        for (int i = T - 1 - tid; i < n_vc; i += T) {
+            double last = S.scale_c[cur * B.max_vclass + i];
+            double ns = scale_law(S.sk[i], last, t, init_cm, tper, tamp, minf, maxf, temp_on, lw);
+            S.scale_c[(cur ^ 1) * B.max_vclass + i] = ns;
+            S.dsc_c[(cur ^ 1) * B.max_vclass + i] = (Real)(ns - S.sk[i].nom_size);
+        }
+        // Bond phase.  Evaluations read only state of the previous step; the pushes of one axis must be
+        // complete before the pushes of the next axis start (same accumulator, different writer), which
+        // the split-phase barrier orders without stalling the evaluations.
+        int div = 0;
+#pragma unroll
+        for (int j = 0; j < VPT; j++) { P[j].w = -1; if (tid + j * T < n_vox) div |= bond_eval<Real, 0>(R, C, tid + j * T, st[j], own[j], fl[j], dt_inv, F[j], M[j], rec, P[j]) ? 1 : 0; }
+#pragma unroll
+        for (int j = 0; j < VPT; j++) bond_push<Real>(R, P[j]);
+        mbar_arrive_warp(S.mbar);
+#pragma unroll
+        for (int j = 0; j < VPT; j++) { P[j].w = -1; if (tid + j * T < n_vox) div |= bond_eval<Real, 1>(R, C, tid + j * T, st[j], own[j], fl[j], dt_inv, F[j], M[j], rec, P[j]) ? 1 : 0; }
+        mbar_wait(S.mbar, mpar); mpar ^= 1u;
+#pragma unroll
+        for (int j = 0; j < VPT; j++) bond_push<Real>(R, P[j]);
+        mbar_arrive_warp(S.mbar);
+#pragma unroll
+        for (int j = 0; j < VPT; j++) { P[j].w = -1; if (tid + j * T < n_vox) div |= bond_eval<Real, 2>(R, C, tid + j * T, st[j], own[j], fl[j], dt_inv, F[j], M[j], rec, P[j]) ? 1 : 0; }
+        mbar_wait(S.mbar, mpar); mpar ^= 1u;
+#pragma unroll
+        for (int j = 0; j < VPT; j++) bond_push<Real>(R, P[j]);
         if (__syncthreads_or(div)) { diverged = true; break; }   // Integrate() returns before the voxel loop (VX_Sim.cpp:1777)
 
 #pragma unroll
         for (int j = 0; j < VPT; j++) {
             int v = tid + j * T;
-            if (v < n_vox) voxel_task<Real>(R, C, v, F[j], M[j]);
-        }
-        // Scale of every class for the next step, from CurTime before the increment (VXS_Voxel.cpp:224-336)
-        for (int i = tid; i < n_vc; i += T) {
-            double last = S.scale_c[cur * B.max_vclass + i];
-            double ns = scale_law(S.sk[i], last, t, init_cm, tper, tamp, minf, maxf, temp_on, lw);
-            S.scale_c[(cur ^ 1) * B.max_vclass + i] = ns;
-            S.dsc_c[(cur ^ 1) * B.max_vclass + i] = (Real)(ns - S.sk[i].nom_size);
+            if (v < n_vox) voxel_task<Real>(R, C, v, st[j], own[j], fl[j], F[j], M[j]);
         }
         __syncthreads();
         cur ^= 1;
@@ -230,10 +283,10 @@ __global__ void __launch_bounds__(512, 1) vx_step_kernel(BatchDev<Real> B, int n
     if (tid == 0) {
         ctlp->cur_time = t;
         ctlp->step = step0 + done;
-        unsigned int st = status0;
-        if (diverged) st |= VXG_ST_DIVERGED_;
-        if (step0 + done >= total) st |= VXG_ST_FINISHED_;
-        ctlp->status = st;
+        unsigned int st2 = status0;
+        if (diverged) st2 |= VXG_ST_DIVERGED_;
+        if (step0 + done >= total) st2 |= VXG_ST_FINISHED_;
+        ctlp->status = st2;
     }
 }
 
@@ -265,12 +318,13 @@ __global__ void __launch_bounds__(256) vx_stats_kernel(BatchDev<Real> B, StatsDe
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
     int touching = 0;
     for (int v = tid; v < R.n_vox; v += T) {
-        int vc = R.vcls[v];
+        int vc = R.stat[v].vcls;
         double m = (double)vk[vc].mass;
         double px = R.pos[v], py = R.pos[nv + v], pz = R.pos[2 * nv + v];
         mx += px * m; my += py * m; mz += pz * m; mm += m;
-        double vx_ = (double)R.lm[v] * (double)vk[vc].mass_inv, vy_ = (double)R.lm[nv + v] * (double)vk[vc].mass_inv,
-               vz_ = (double)R.lm[2 * nv + v] * (double)vk[vc].mass_inv;
+        const R4<Real> lm = R.momA[v];
+        double vx_ = (double)lm.x * (double)vk[vc].mass_inv, vy_ = (double)lm.y * (double)vk[vc].mass_inv,
+               vz_ = (double)lm.z * (double)vk[vc].mass_inv;
         vmax = fmax(vmax, sqrt(vx_ * vx_ + vy_ * vy_ + vz_ * vz_));
         lo[0] = fmin(lo[0], px); lo[1] = fmin(lo[1], py); lo[2] = fmin(lo[2], pz);
         hi[0] = fmax(hi[0], px); hi[1] = fmax(hi[1], py); hi[2] = fmax(hi[2], pz);

@@ -34,7 +34,7 @@ template <typename Real> struct Emul : EmulBase {
     int div = 0;
 
     Emul(const vxg_robot_desc* d) {
-        L = make_layout(d->n_vox, (int)sizeof(Real));
+        L = make_layout(stride_for(d->n_vox), (int)sizeof(Real));
         blob.resize(L.total_bytes);
         nom.resize(3 * (size_t)L.nv);
         int nvc = d->n_vclass, nbc = d->n_bclass > 0 ? d->n_bclass : 1;
@@ -69,10 +69,13 @@ template <typename Real> struct Emul : EmulBase {
             const Real dt_inv = ctl.step == 0 ? (Real)0 : dt_inv_run;
             for (int v = 0; v < ctl.n_vox; v++) { F[v] = mk3<Real>(0, 0, 0); M[v] = mk3<Real>(0, 0, 0); }
             bool d = false;
-            for (int ax = 0; ax < 3; ax++)
-                for (int v = 0; v < ctl.n_vox; v++) d |= bond_task<Real>(R, C, v, ax, dt_inv, F[v], M[v], rec.data());
+            std::vector<uint32_t> fl(ctl.n_vox);
+            for (int v = 0; v < ctl.n_vox; v++) fl[v] = R.flags[v];
+            for (int v = 0; v < ctl.n_vox; v++) d |= bond_task<Real, 0>(R, C, v, R.stat[v], fl[v], dt_inv, F[v], M[v], rec.data());
+            for (int v = 0; v < ctl.n_vox; v++) d |= bond_task<Real, 1>(R, C, v, R.stat[v], fl[v], dt_inv, F[v], M[v], rec.data());
+            for (int v = 0; v < ctl.n_vox; v++) d |= bond_task<Real, 2>(R, C, v, R.stat[v], fl[v], dt_inv, F[v], M[v], rec.data());
             if (d) { div = 1; break; }
-            for (int v = 0; v < ctl.n_vox; v++) voxel_task<Real>(R, C, v, F[v], M[v]);
+            for (int v = 0; v < ctl.n_vox; v++) voxel_task<Real>(R, C, v, R.stat[v], load_own<Real>(R, v), fl[v], F[v], M[v]);
             for (int i = 0; i < ctl.n_vclass; i++) {
                 double ns = scale_law(sk[i], scale_c[cur][i], ctl.cur_time, ctl.init_cm_time, ctl.temp_period, ctl.temp_amplitude,
                                       ctl.min_fact, ctl.max_fact, temp_on, lw);
@@ -90,11 +93,12 @@ template <typename Real> struct Emul : EmulBase {
         RobotView<Real> R = make_view<Real>(blob.data(), L, ctl.n_vox);
         const int nv = R.nv;
         for (int i = 0; i < ctl.n_vox; i++) {
+            const R4<Real> q = R.quat[i], ma = R.momA[i]; const R2<Real> mb = R.momB[i];
             if (o->pos) for (int a = 0; a < 3; a++) o->pos[3 * i + a] = R.pos[a * nv + i];
-            if (o->quat) for (int a = 0; a < 4; a++) o->quat[4 * i + a] = (double)R.quat[a * nv + i];
-            if (o->lin_mom) for (int a = 0; a < 3; a++) o->lin_mom[3 * i + a] = (double)R.lm[a * nv + i];
-            if (o->ang_mom) for (int a = 0; a < 3; a++) o->ang_mom[3 * i + a] = (double)R.am[a * nv + i];
-            if (o->scale) o->scale[i] = scale_c[cur][R.vcls[i]];
+            if (o->quat) { o->quat[4 * i] = (double)q.x; o->quat[4 * i + 1] = (double)q.y; o->quat[4 * i + 2] = (double)q.z; o->quat[4 * i + 3] = (double)q.w; }
+            if (o->lin_mom) { o->lin_mom[3 * i] = (double)ma.x; o->lin_mom[3 * i + 1] = (double)ma.y; o->lin_mom[3 * i + 2] = (double)ma.z; }
+            if (o->ang_mom) { o->ang_mom[3 * i] = (double)ma.w; o->ang_mom[3 * i + 1] = (double)mb.x; o->ang_mom[3 * i + 2] = (double)mb.y; }
+            if (o->scale) o->scale[i] = scale_c[cur][R.stat[i].vcls];
             if (o->static_fric) o->static_fric[i] = (R.flags[i] & VX_FL_STATIC_FRIC) ? 1 : 0;
         }
         for (size_t j = 0; j < bv1.size(); j++) {
