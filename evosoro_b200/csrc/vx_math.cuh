@@ -104,8 +104,17 @@ VX_HD double vx_fsqrt(double x) { return sqrt(x); }
 #endif
 // num/den < c and num/den > c without the division, with the IEEE outcome for den <= 0 (negative ratio,
 // +-inf, NaN) that the reference's `(abs(z)+abs(y))/x` and `x/NomDistance` tests would have.
-template <typename T> VX_HD bool ratio_lt(T num, T den, T c) { return den > (T)0 ? num < c * den : (den < (T)0 ? num > c * den : num < (T)0); }
-template <typename T> VX_HD bool ratio_gt(T num, T den, T c) { return den > (T)0 ? num > c * den : (den < (T)0 ? num < c * den : num > (T)0); }
+// Written with non-short-circuit predicate logic so that they compile to compare + predicate ops, no branches.
+template <typename T> VX_HD bool ratio_lt(T num, T den, T c) {
+    const T cd = c * den;
+    const bool pos = den > (T)0, neg = den < (T)0;
+    return (pos & (num < cd)) | (neg & (num > cd)) | (!(pos | neg) & (num < (T)0));
+}
+template <typename T> VX_HD bool ratio_gt(T num, T den, T c) {
+    const T cd = c * den;
+    const bool pos = den > (T)0, neg = den < (T)0;
+    return (pos & (num > cd)) | (neg & (num < cd)) | (!(pos | neg) & (num > (T)0));
+}
 
 // bond axis permutation: the bond is evaluated as if it pointed along +X (VX_Bond.h:45-48)
 template <typename T> VX_HD V3<T> to_xdir(int ax, V3<T> v) {
@@ -175,9 +184,11 @@ template <typename T> VX_NOINLINE T rotvec_scale_large(T vv, T w) {
 }
 template <typename T> VX_HD V3<T> rotvec(Q4<T> q) {
     T vv = q.x * q.x + q.y * q.y + q.z * q.z;
-    T w = q.w > (T)1 ? (T)1 : q.w;
-    T f = (T)2.8284271247461903 * vx_rsqrt((T)1 + w);              // 2 sqrt(2/(1+w))
-    f = (vv > (T)0) & (w > (T)-1) ? f : (T)0;
+    // 2 sqrt(2/(1+w)); w is clamped into (-1, 1] so the factor stays finite: for |w| >= 1 the reference returns
+    // the zero vector, and there the vector part itself is (numerically) zero
+    T d = (T)1 + (q.w > (T)1 ? (T)1 : q.w);
+    d = d > (T)1e-12 ? d : (T)1e-12;
+    T f = (T)2.8284271247461903 * vx_rsqrt(d);
     if (vv >= (T)VX_SLTHRESH_ACOS2SQRT) f = rotvec_scale_large<T>(vv, q.w);
     return mk3<T>(q.x * f, q.y * f, q.z * f);
 }
@@ -222,6 +233,35 @@ template <typename T> struct alignas(16) BondK {   // from vxg_bond_class
     int pad_[sizeof(T) == 4 ? 1 : 2];
 };
 
+// Compact form of a bond class for lattices of equal cubic voxels, where every beam constant of
+// CVX_Bond::UpdateConstants (VX_Bond.cpp:125-170, A = L^2, Iy = Iz = L^4/12, J = L^4/6, inertia = m L^2/6,
+// first moment = m L/2) is a power of L times one of four class numbers:
+//   b1 = a1 = E L   b2 = E L^2/2   b3 = E L^3/6   a2 = b3 / (2(1+nu))
+//   2 sqrt(a1 m) = 2 sqrt(b1 m) = s   2 sqrt(b2 FM) = s L/2   2 sqrt(b3 I) = s L^2/6   2 sqrt(a2 I) = s L^2/6 / sqrt(2(1+nu))
+// Two 128-bit loads per bond instead of five; the host verifies the relations per class at upload
+// (pack_classes) and the batch falls back to the wide table if any class deviates.
+template <typename T> struct alignas(16) BondKc {
+    T ec, k_axial, s1, s2;                      // composite E; axial force per unit _Pos2.x; 2 sqrt(E L m1), 2 sqrt(E L m2)
+    T tnu_half, sq_tnu, nom_dist, len_minus_dist;   // 1/(2(1+nu)) and its square root; pitch; L.x - pitch
+};
+template <typename T> struct BondGeo { T L, L2h, L3s, Lh, L2s, inv_len; };   // L, L^2/2, L^3/6, L/2, L^2/6, 1/L
+template <typename T> VX_HD BondGeo<T> make_geo(double L) {
+    BondGeo<T> g;
+    g.L = (T)L; g.L2h = (T)(L * L / 2); g.L3s = (T)(L * L * L / 6); g.Lh = (T)(L / 2); g.L2s = (T)(L * L / 6); g.inv_len = (T)(1.0 / L);
+    return g;
+}
+template <typename T> VX_HD BondK<T> expand_bond(const BondKc<T>& c, const BondGeo<T>& g) {
+    BondK<T> k;
+    k.b1 = c.ec * g.L; k.b2 = c.ec * g.L2h; k.b3 = c.ec * g.L3s; k.a2 = k.b3 * c.tnu_half;
+    k.inv_len = g.inv_len; k.k_axial = c.k_axial; k.nom_dist = c.nom_dist; k.len_minus_dist = c.len_minus_dist;
+    k.c_a1m1 = c.s1; k.c_a1m2 = c.s2; k.c_b1m1 = c.s1; k.c_b1m2 = c.s2;
+    k.c_b2fm1 = c.s1 * g.Lh; k.c_b2fm2 = c.s2 * g.Lh;
+    k.c_b3i1 = c.s1 * g.L2s; k.c_b3i2 = c.s2 * g.L2s;
+    k.c_a2i1 = k.c_b3i1 * c.sq_tnu; k.c_a2i2 = k.c_b3i2 * c.sq_tnu;
+    k.homogeneous = 0;
+    return k;
+}
+
 template <typename T> struct alignas(16) VoxK {    // from vxg_vox_class (+ sim constants folded in)
     T mass, mass_inv, inertia_inv;
     T slow_lin;        // SlowDampZ * _2xSqMxExS
@@ -255,8 +295,10 @@ template <typename T> struct BondHist {  // _LastPos2, _LastAngle1, _LastAngle2 
 //   dt_inv   : 1/dt of the PREVIOUS step (0 on the very first step: no damping, history still stored)
 // Only the small/large-angle split is a real branch; everything cheap is evaluated unconditionally so
 // the common path is one long basic block the scheduler can interleave across the voxels of a thread.
+//   sym_mass : every bond of the robot joins voxels of equal mass/inertia (uniform density, as in all evosoro
+//              palettes): Force2 == -Force1 exactly, so its evaluation and rotation are skipped (robot-uniform flag)
 template <int AX, typename T>
-VX_HD void bond_force(const BondK<T>& k, V3<T> e_w, Q4<T> q1w, Q4<T> q2w, T dnom, T half_bond_z, T dt_inv,
+VX_HD void bond_force(const BondK<T>& k, V3<T> e_w, Q4<T> q1w, Q4<T> q2w, T dnom, T half_bond_z, T dt_inv, bool sym_mass,
                       bool& small, BondHist<T>& hist, BondOut<T>& out) {
     const T D = k.nom_dist;
     V3<T> e = to_xdir_c<AX>(e_w);
@@ -323,7 +365,8 @@ VX_HD void bond_force(const BondK<T>& k, V3<T> e_w, Q4<T> q1w, Q4<T> q2w, T dnom
     V3<T> F1 = mk3<T>(fx + bz * (k.c_a1m1 * rv.x), ey + bz * (k.c_b1m1 * rv.y - k.c_b2fm1 * swz), ez + bz * (k.c_b1m1 * rv.z + k.c_b2fm1 * swy));
     // Force2 = -Force1 for a homogeneous bond (:128, :166); with the voxel-2 damping constants the general
     // expression reduces to exactly that when both voxels have the same mass, so no branch is needed
-    V3<T> F2 = mk3<T>(-fx - bz * (k.c_a1m2 * rv.x), -ey - bz * (k.c_b1m2 * rv.y - k.c_b2fm2 * swz), -ez - bz * (k.c_b1m2 * rv.z + k.c_b2fm2 * swy));
+    V3<T> F2 = mk3<T>(0, 0, 0);
+    if (!sym_mass) F2 = mk3<T>(-fx - bz * (k.c_a1m2 * rv.x), -ey - bz * (k.c_b1m2 * rv.y - k.c_b2fm2 * swz), -ez - bz * (k.c_b1m2 * rv.z + k.c_b2fm2 * swy));
     T tw = w2.x - w1.x;
     T my = k.b2 * p2.z, mz = -k.b2 * p2.y;
     V3<T> M1 = mk3<T>(k.a2 * (an1.x - an2.x) - hz * (k.c_a2i1 * tw),
@@ -337,7 +380,7 @@ VX_HD void bond_force(const BondK<T>& k, V3<T> e_w, Q4<T> q1w, Q4<T> q2w, T dnom
     // back to the world frame (:161-170): one rotation matrix for the four vectors
     const M33<T> Rm = rot_matrix(back);
     out.f1 = to_origdir_c<AX>(mat_apply(Rm, F1));
-    out.f2 = to_origdir_c<AX>(mat_apply(Rm, F2));
+    out.f2 = sym_mass ? -out.f1 : to_origdir_c<AX>(mat_apply(Rm, F2));
     out.m1 = to_origdir_c<AX>(mat_apply(Rm, M1));
     out.m2 = to_origdir_c<AX>(mat_apply(Rm, M2));
 }
@@ -440,7 +483,7 @@ VX_HD bool voxel_integrate(const VoxK<T>& k, V3<T> F, V3<T> M, double half_scale
     T sz = hw.x * a.y - hw.y * a.x + hw.z * a.w;
     a.w += sw * dt; a.x += sx * dt; a.y += sy * dt; a.z += sz * dt;              // :214
     T l2 = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;                        // NormalizeFast Vec3D.h:243-246
-    if (l2 != (T)0) { T li = vx_rsqrt(l2); a.w *= li; a.x *= li; a.y *= li; a.z *= li; }
+    { T li = vx_rsqrt(l2 > (T)1e-30 ? l2 : (T)1e-30); a.w *= li; a.x *= li; a.y *= li; a.z *= li; }   // `if (l)`: never zero for a unit quaternion
     clamp_unit_w(a);
     s.q = a;
     if (k.has_bc && (k.dof & 0x38) == 0x38) {           // :218-221

@@ -3,11 +3,41 @@
 // (CVX_Sim::ResetSimulation, VX_Sim.cpp:839-1007; CVXS_Voxel::ResetVoxel, VXS_Voxel.cpp:95-135;
 // CVXS_BondInternal::ResetBond, VXS_BondInternal.cpp:40-54).  Pure host C++ (no CUDA calls).
 #pragma once
+#include <cmath>
 #include <cstring>
 #include "../../include/vxgpu.h"
 #include "vx_robot.cuh"
 
 namespace vx {
+
+// Compact bond classes (BondKc): returns false when some class is not of the equal-cubic-voxel beam form
+// (relative deviation above 1e-9) or the classes do not share one bond length; *len_out = that length.
+template <typename Real>
+inline bool pack_compact(const vxg_robot_desc* d, BondKc<Real>* bkc, double* len_out) {
+    auto near = [](double a, double b) { double m = fabs(a) > fabs(b) ? fabs(a) : fabs(b); return fabs(a - b) <= 1e-9 * m; };
+    double L = d->n_bclass > 0 ? d->bclasses[0].len : 1.0;
+    *len_out = L;
+    bool ok = true;
+    for (int i = 0; i < d->n_bclass; i++) {
+        const vxg_bond_class& c = d->bclasses[i];
+        if (!(c.len > 0) || !near(c.len, L) || !(c.b1 > 0) || !(c.b3 > 0) || !(c.a2 > 0)) { ok = false; continue; }
+        const double ec = c.b1 / L, th = c.a2 / c.b3, sq = sqrt(th), s1 = c.c_a1m1, s2 = c.c_a1m2;
+        ok = ok && near(c.b2, ec * L * L / 2) && near(c.b3, ec * L * L * L / 6);
+        ok = ok && near(c.c_b1m1, s1) && near(c.c_b1m2, s2) && near(c.c_b2fm1, s1 * L / 2) && near(c.c_b2fm2, s2 * L / 2);
+        ok = ok && near(c.c_b3i1, s1 * L * L / 6) && near(c.c_b3i2, s2 * L * L / 6);
+        ok = ok && near(c.c_a2i1, s1 * L * L / 6 * sq) && near(c.c_a2i2, s2 * L * L / 6 * sq);
+        BondKc<Real>& k = bkc[i];
+        k.ec = (Real)ec; k.s1 = (Real)s1; k.s2 = (Real)s2; k.tnu_half = (Real)th; k.sq_tnu = (Real)sq;
+        k.nom_dist = (Real)c.nom_dist; k.len_minus_dist = (Real)(c.len - c.nom_dist);
+        double e_eff = c.e1;
+        if (!c.homogeneous) {
+            double diff = c.e1 >= c.e2 ? c.e1 - c.e2 : c.e2 - c.e1, sum = c.e1 + c.e2;
+            e_eff = diff > sum * .0005 ? 2.0 * c.e1 * c.e2 / sum : 0.5 * sum;
+        }
+        k.k_axial = (Real)(c.area * e_eff / c.len);
+    }
+    return ok;
+}
 
 template <typename Real>
 inline void pack_classes(const vxg_robot_desc* d, BondK<Real>* bk, double* bk_dist, VoxK<Real>* vk, ScaleK* sk,
@@ -83,6 +113,11 @@ inline void init_ctl(const vxg_robot_desc* d, RobotCtl& c) {
     c.step = 0; c.total_steps = 0x7fffffffffffffffLL; c.latch_step = -1; c.status = 0; c.flags = P.flags;
     c.n_vox = d->n_vox; c.n_vclass = d->n_vclass; c.n_bclass = d->n_bclass; c.ini_latched = 0;
     c.half_bond_z = 0.5 * P.bond_damp_z;
+    c.sym_mass = 1;
+    for (int i = 0; i < d->n_bclass; i++) {
+        const vxg_bond_class& b = d->bclasses[i];
+        if (b.c_a1m1 != b.c_a1m2 || b.c_a2i1 != b.c_a2i2 || b.c_b1m1 != b.c_b1m2 || b.c_b2fm1 != b.c_b2fm2 || b.c_b3i1 != b.c_b3i2) c.sym_mass = 0;
+    }
 }
 
 }  // namespace vx

@@ -126,7 +126,9 @@ VX_HD RobotView<Real> make_view(unsigned char* base, const BlobLayout& L, int n_
 
 // Per-robot constants the tasks read (class tables live in shared memory in the kernel).
 template <typename Real> struct RobotConsts {
-    const BondK<Real>* bk;      // [n_bclass]
+    const BondK<Real>* bk;      // [n_bclass] wide bond classes (nullptr in compact mode)
+    const BondKc<Real>* bkc;    // [n_bclass] compact bond classes + the shared geometry
+    BondGeo<Real> geo;
     const double* bk_dist;      // [n_bclass] pitch along the bond axis, fp64
     const VoxK<Real>* vk;       // [n_vclass]
     const double* scale_c;      // [n_vclass] Scale of each class as left by the previous step
@@ -137,6 +139,7 @@ template <typename Real> struct RobotConsts {
     Real half_bond_z;           // 0.5 BondDampingZ
     Real dt;
     bool floor_on, sticky;
+    bool sym_mass;              // every bond class has equal end-voxel masses: Force2 = -Force1
 };
 
 // The owner's own position and orientation, loaded once per step and reused by its three bonds.
@@ -154,7 +157,7 @@ template <typename Real> struct BondPush { int w; V3<Real> f2, m2; };   // w < 0
 // registers across the three axes by the caller).  rec != nullptr: also store the bond outputs
 // ([39][nv] planes, vxg_download_state).  Touches no accumulator, so it needs no ordering against the
 // other voxels' pushes.  Returns true when the bond diverged (strain > 100, VX_Sim.cpp:1775).
-template <typename Real, int AX>
+template <typename Real, int AX, bool COMPACT = false>
 VX_HD bool bond_eval(const RobotView<Real>& R, const RobotConsts<Real>& C, int v, const VoxStat& st, const OwnState<Real>& own,
                      uint32_t& fl, Real dt_inv, V3<Real>& F, V3<Real>& M, Real* rec, BondPush<Real>& p) {
     const int nv = R.nv;
@@ -162,7 +165,9 @@ VX_HD bool bond_eval(const RobotView<Real>& R, const RobotConsts<Real>& C, int v
     p.w = w;
     if (w < 0) return false;
     const int bc = st.bcls[AX];
-    const BondK<Real> k = C.bk[bc];
+    BondK<Real> k;
+    if (COMPACT) { const BondKc<Real> kc = C.bkc[bc]; k = expand_bond<Real>(kc, C.geo); }
+    else k = C.bk[bc];
     // bond vector in fp64, pitch removed before narrowing (VXS_BondInternal.cpp:58)
     double dpa[3] = {R.pos[w] - own.px, R.pos[nv + w] - own.py, R.pos[2 * nv + w] - own.pz};
     dpa[AX] -= C.bk_dist[bc];
@@ -182,7 +187,7 @@ VX_HD bool bond_eval(const RobotView<Real>& R, const RobotConsts<Real>& C, int v
         h.a2 = mk3<Real>(b.z, b.w, c);
     }
     BondOut<Real> o;
-    bond_force<AX, Real>(k, e, q1, q2, dnom, C.half_bond_z, dt_inv, small, h, o);
+    bond_force<AX, Real>(k, e, q1, q2, dnom, C.half_bond_z, dt_inv, C.sym_mass, small, h, o);
     if (!o.changed) {   // _LastPos2/_LastAngle* keep their values on a mode-flip step (VXS_BondInternal.cpp:157)
         R4<Real> a, b;
         a.x = h.p2.x; a.y = h.p2.y; a.z = h.p2.z; a.w = h.a1.x;
@@ -212,11 +217,11 @@ VX_HD void bond_push(const RobotView<Real>& R, const BondPush<Real>& p) {
     R.accA[p.w] = a; R.accB[p.w] = b;
 }
 
-template <typename Real, int AX>
+template <typename Real, int AX, bool COMPACT = false>
 VX_HD bool bond_task(const RobotView<Real>& R, const RobotConsts<Real>& C, int v, const VoxStat& st, uint32_t& fl,
                      Real dt_inv, V3<Real>& F, V3<Real>& M, Real* rec) {
     BondPush<Real> p;
-    bool d = bond_eval<Real, AX>(R, C, v, st, load_own<Real>(R, v), fl, dt_inv, F, M, rec, p);
+    bool d = bond_eval<Real, AX, COMPACT>(R, C, v, st, load_own<Real>(R, v), fl, dt_inv, F, M, rec, p);
     bond_push<Real>(R, p);
     return d;
 }
@@ -270,9 +275,10 @@ struct RobotCtl {
     unsigned int status;    // VXG_ST_*
     unsigned int flags;     // VXG_F_*
     int n_vox, n_vclass, n_bclass, ini_latched;
-    float half_bond_z_pad;  // unused
-    int pad;
+    int compact_ok;         // this robot's bond classes have the compact form (pack_compact)
+    int sym_mass;           // every bond class has identical voxel-1 / voxel-2 damping constants
     double half_bond_z;     // 0.5 BondDampingZ
+    double bond_len;        // the common bond length L of the compact form
 };
 
 }  // namespace vx

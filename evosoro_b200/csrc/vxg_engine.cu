@@ -50,6 +50,8 @@ struct vxg_batch {
     // pinned host mirrors (whole batch, uploaded in one go before the first step after a change)
     unsigned char* h_blobs = nullptr;
     RobotCtl* h_ctl = nullptr;
+    unsigned char* h_bkc = nullptr;   // compact bond classes of every robot (BondKc), used when the whole batch qualifies
+    bool compact = false;             // mode of the tables currently on the device
     unsigned char* h_bk = nullptr; double* h_bk_dist = nullptr; unsigned char* h_vk = nullptr; ScaleK* h_sk = nullptr;
     double* h_scale_c = nullptr; unsigned char* h_ext_disp = nullptr; unsigned char* h_ext_tdisp = nullptr; double* h_nom = nullptr;
     StatsDev* h_stats = nullptr;
@@ -61,8 +63,12 @@ struct vxg_batch {
     int vpt = 1, threads = 32;
     bool smem_mode = true;
     size_t smem_bytes = 0;
+    size_t tb_wide = 0, tb_compact = 0;          // shared-memory table bytes with the wide / compact bond classes
+    bool smem_wide_fits = false;                 // blob + wide tables fit in shared memory
+    bool smem_mode_wide_or_compact = false;      // blob + compact tables fit
     size_t rs() const { return prec == VXG_PREC_F64 ? 8 : 4; }
     size_t bk_sz() const { return prec == VXG_PREC_F64 ? sizeof(BondK<double>) : sizeof(BondK<float>); }
+    size_t bkc_sz() const { return prec == VXG_PREC_F64 ? sizeof(BondKc<double>) : sizeof(BondKc<float>); }
     size_t vk_sz() const { return prec == VXG_PREC_F64 ? sizeof(VoxK<double>) : sizeof(VoxK<float>); }
 };
 
@@ -85,42 +91,47 @@ extern "C" int vxg_struct_sizes(int* out, int n) {
 template <typename Real> static BatchDev<Real> dev_view(const vxg_batch* b) {
     BatchDev<Real> B;
     B.blobs = b->d_blobs; B.L = b->L; B.ctl = b->d_ctl;
-    B.bk = (BondK<Real>*)b->d_bk; B.bk_dist = b->d_bk_dist; B.vk = (VoxK<Real>*)b->d_vk; B.sk = b->d_sk;
+    B.bk = (unsigned char*)b->d_bk; B.bk_dist = b->d_bk_dist; B.vk = (VoxK<Real>*)b->d_vk; B.sk = b->d_sk;
     B.scale_c = b->d_scale_c; B.ext_disp = (Real*)b->d_ext_disp; B.ext_tdisp = (Real*)b->d_ext_tdisp; B.nom = b->d_nom;
     B.bond_rec = (Real*)b->d_bond_rec;
     B.max_vclass = b->lim.max_vclass; B.max_bclass = b->lim.max_bclass; B.n_robots = b->n_robots;
     return B;
 }
 
-template <typename Real, int NV, int VPT, bool SMEM>
+template <typename Real, int NV, int VPT, bool SMEM, bool COMPACT>
 static cudaError_t launch_step(vxg_batch* b, int n_steps, int record) {
-    auto kern = vx_step_kernel<Real, NV, VPT, SMEM>;
+    auto kern = vx_step_kernel<Real, NV, VPT, SMEM, COMPACT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes);
     if (e != cudaSuccess) return e;
     kern<<<b->n_robots, NV / VPT, b->smem_bytes, b->stream>>>(dev_view<Real>(b), n_steps, record);
     return cudaGetLastError();
 }
 
-template <typename Real, bool SMEM> static cudaError_t launch_step_s(vxg_batch* b, int n_steps, int record) {
+template <typename Real, bool SMEM, bool COMPACT> static cudaError_t launch_step_s(vxg_batch* b, int n_steps, int record) {
     switch (b->L.nv) {   // strides the kernels are instantiated for (stride_for); <= 512 threads per CTA
-        case 64: return launch_step<Real, 64, 1, SMEM>(b, n_steps, record);
-        case 128: return launch_step<Real, 128, 1, SMEM>(b, n_steps, record);
-        case 256: return launch_step<Real, 256, 1, SMEM>(b, n_steps, record);
-        case 512: return launch_step<Real, 512, 1, SMEM>(b, n_steps, record);
-        case 1024: return launch_step<Real, 1024, 2, SMEM>(b, n_steps, record);
-        case 2048: return launch_step<Real, 2048, 4, SMEM>(b, n_steps, record);
+        case 64: return launch_step<Real, 64, 1, SMEM, COMPACT>(b, n_steps, record);
+        case 128: return launch_step<Real, 128, 1, SMEM, COMPACT>(b, n_steps, record);
+        case 256: return launch_step<Real, 256, 1, SMEM, COMPACT>(b, n_steps, record);
+        case 512: return launch_step<Real, 512, 1, SMEM, COMPACT>(b, n_steps, record);
+        case 1024: return launch_step<Real, 1024, 2, SMEM, COMPACT>(b, n_steps, record);
+        case 2048: return launch_step<Real, 2048, 4, SMEM, COMPACT>(b, n_steps, record);
     }
     return cudaErrorInvalidValue;
 }
 
-template <typename Real> static cudaError_t launch_step_p(vxg_batch* b, int n_steps, int record) {
-    return b->smem_mode ? launch_step_s<Real, true>(b, n_steps, record) : launch_step_s<Real, false>(b, n_steps, record);
+// The compact bond table exists for the production path only (fp32, shared-memory resident).
+static cudaError_t launch_step_p(vxg_batch* b, int n_steps, int record) {
+    if (b->prec == VXG_PREC_F64)
+        return b->smem_mode ? launch_step_s<double, true, false>(b, n_steps, record) : launch_step_s<double, false, false>(b, n_steps, record);
+    if (!b->smem_mode) return launch_step_s<float, false, false>(b, n_steps, record);
+    return b->compact ? launch_step_s<float, true, true>(b, n_steps, record) : launch_step_s<float, true, false>(b, n_steps, record);
 }
 
 static void free_all(vxg_batch* b) {
     cudaFree(b->d_blobs); cudaFree(b->d_ctl); cudaFree(b->d_bk); cudaFree(b->d_bk_dist); cudaFree(b->d_vk); cudaFree(b->d_sk);
     cudaFree(b->d_scale_c); cudaFree(b->d_ext_disp); cudaFree(b->d_ext_tdisp); cudaFree(b->d_nom); cudaFree(b->d_bond_rec);
     cudaFree(b->d_stats);
+    cudaFreeHost(b->h_bkc);
     cudaFreeHost(b->h_blobs); cudaFreeHost(b->h_ctl); cudaFreeHost(b->h_bk); cudaFreeHost(b->h_bk_dist); cudaFreeHost(b->h_vk);
     cudaFreeHost(b->h_sk); cudaFreeHost(b->h_scale_c); cudaFreeHost(b->h_ext_disp); cudaFreeHost(b->h_ext_tdisp); cudaFreeHost(b->h_nom);
     cudaFreeHost(b->h_stats);
@@ -152,7 +163,11 @@ extern "C" int vxg_create(vxg_batch** out, int device, int n_robots, const vxg_l
     int max_smem = 0;
     CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     if (tb > (size_t)max_smem) { delete b; return fail(VXG_UNSUPPORTED_SIZE, "vxg_create: class tables (%zu B) exceed shared memory", tb); }
-    b->smem_mode = b->L.total_bytes + tb <= (size_t)max_smem;
+    b->tb_wide = tb;
+    b->tb_compact = tables_bytes<float>(lim->max_vclass, lim->max_bclass, true);
+    b->smem_wide_fits = b->L.total_bytes + tb <= (size_t)max_smem;
+    b->smem_mode_wide_or_compact = b->prec == VXG_PREC_F32 && b->L.total_bytes + b->tb_compact <= (size_t)max_smem;
+    b->smem_mode = b->smem_wide_fits || b->smem_mode_wide_or_compact;   // final choice is made at flush, when the classes are known
     b->smem_bytes = b->smem_mode ? b->L.total_bytes + tb : tb;
 
     size_t nr = (size_t)n_robots, mv = (size_t)lim->max_vclass, mb = (size_t)lim->max_bclass, nv = (size_t)b->L.nv;
@@ -165,6 +180,7 @@ extern "C" int vxg_create(vxg_batch** out, int device, int n_robots, const vxg_l
     DA(b->d_ext_disp, nr * mv * 3 * b->rs()); DA(b->d_ext_tdisp, nr * mv * 3 * b->rs()); DA(b->d_nom, nr * 3 * nv * sizeof(double));
     DA(b->d_stats, nr * sizeof(StatsDev));
     HA(b->h_blobs, nr * b->L.total_bytes); HA(b->h_ctl, nr * sizeof(RobotCtl));
+    HA(b->h_bkc, nr * mb * b->bkc_sz());
     HA(b->h_bk, nr * mb * b->bk_sz()); HA(b->h_bk_dist, nr * mb * sizeof(double)); HA(b->h_vk, nr * mv * b->vk_sz());
     HA(b->h_sk, nr * mv * sizeof(ScaleK)); HA(b->h_scale_c, nr * mv * sizeof(double));
     HA(b->h_ext_disp, nr * mv * 3 * b->rs()); HA(b->h_ext_tdisp, nr * mv * 3 * b->rs()); HA(b->h_nom, nr * 3 * nv * sizeof(double));
@@ -197,6 +213,10 @@ template <typename Real> static void fill_classes(vxg_batch* b, int robot, const
     size_t mb = (size_t)b->lim.max_bclass, mv = (size_t)b->lim.max_vclass, r = (size_t)robot;
     pack_classes<Real>(d, (BondK<Real>*)(b->h_bk) + r * mb, b->h_bk_dist + r * mb, (VoxK<Real>*)(b->h_vk) + r * mv,
                        b->h_sk + r * mv, b->h_scale_c + r * mv, (Real*)(b->h_ext_disp) + r * mv * 3, (Real*)(b->h_ext_tdisp) + r * mv * 3);
+}
+
+template <typename Real> static bool fill_compact(vxg_batch* b, int robot, const vxg_robot_desc* d, double* len) {
+    return pack_compact<Real>(d, (BondKc<Real>*)(b->h_bkc) + (size_t)robot * b->lim.max_bclass, len);
 }
 
 template <typename Real> static void reset_blob(vxg_batch* b, int robot, const vxg_robot_desc* d) {
@@ -236,6 +256,12 @@ extern "C" int vxg_upload(vxg_batch* b, int robot, const vxg_robot_desc* d) {
     if (b->prec == VXG_PREC_F64) { fill_classes<double>(b, robot, d); reset_blob<double>(b, robot, d); }
     else { fill_classes<float>(b, robot, d); reset_blob<float>(b, robot, d); }
     init_ctl(d, b->h_ctl[robot]);
+    {
+        double len = 1.0;
+        bool ok = b->prec == VXG_PREC_F64 ? fill_compact<double>(b, robot, d, &len) : fill_compact<float>(b, robot, d, &len);
+        b->h_ctl[robot].compact_ok = ok ? 1 : 0;
+        b->h_ctl[robot].bond_len = len;
+    }
     b->bond_v1[robot].assign(d->bond_v1, d->bond_v1 + d->n_bond);
     b->bond_v2[robot].assign(d->bond_v2, d->bond_v2 + d->n_bond);
     b->bond_axis[robot].assign(d->bond_axis, d->bond_axis + d->n_bond);
@@ -249,8 +275,15 @@ static int flush(vxg_batch* b) {
     CK(cudaSetDevice(b->device));
     size_t nr = (size_t)b->n_robots, mv = (size_t)b->lim.max_vclass, mb = (size_t)b->lim.max_bclass, nv = (size_t)b->L.nv;
     if (b->dirty) {
+        // compact bond tables only if the production kernel runs and every robot of the batch qualifies
+        bool compact = b->prec == VXG_PREC_F32 && b->smem_mode_wide_or_compact;
+        for (size_t r = 0; r < nr && compact; r++) if (b->uploaded[r] && !b->h_ctl[r].compact_ok) compact = false;
+        b->compact = compact;
+        if (compact) { b->smem_mode = true; b->smem_bytes = b->L.total_bytes + b->tb_compact; }
+        else { b->smem_mode = b->smem_wide_fits; b->smem_bytes = b->smem_wide_fits ? b->L.total_bytes + b->tb_wide : b->tb_wide; }
         CK(cudaMemcpyAsync(b->d_blobs, b->h_blobs, nr * b->L.total_bytes, cudaMemcpyHostToDevice, b->stream));
-        CK(cudaMemcpyAsync(b->d_bk, b->h_bk, nr * mb * b->bk_sz(), cudaMemcpyHostToDevice, b->stream));
+        if (compact) CK(cudaMemcpyAsync(b->d_bk, b->h_bkc, nr * mb * b->bkc_sz(), cudaMemcpyHostToDevice, b->stream));
+        else CK(cudaMemcpyAsync(b->d_bk, b->h_bk, nr * mb * b->bk_sz(), cudaMemcpyHostToDevice, b->stream));
         CK(cudaMemcpyAsync(b->d_bk_dist, b->h_bk_dist, nr * mb * sizeof(double), cudaMemcpyHostToDevice, b->stream));
         CK(cudaMemcpyAsync(b->d_vk, b->h_vk, nr * mv * b->vk_sz(), cudaMemcpyHostToDevice, b->stream));
         CK(cudaMemcpyAsync(b->d_sk, b->h_sk, nr * mv * sizeof(ScaleK), cudaMemcpyHostToDevice, b->stream));
@@ -324,7 +357,7 @@ extern "C" int vxg_step(vxg_batch* b, int n_steps) {
     while (left > 0) {
         int n = left < chunk ? left : chunk;
         int record = (b->d_bond_rec && n == left) ? 1 : 0;
-        cudaError_t e = b->prec == VXG_PREC_F64 ? launch_step_p<double>(b, n, record) : launch_step_p<float>(b, n, record);
+        cudaError_t e = launch_step_p(b, n, record);
         if (e != cudaSuccess) return fail(VXG_ERR_CUDA, "vx_step_kernel launch: %s", cudaGetErrorString(e));
         b->launches++;
         left -= n;
@@ -372,6 +405,11 @@ extern "C" int vxg_mark_elapsed_ms(vxg_batch* b, int s0, int s1, float* ms) {
 
 extern "C" int vxg_kernel_config(vxg_batch* b, int* threads, int* vpt, int* smem_mode, int64_t* smem_bytes, int64_t* blob_bytes, int64_t* dyn_bytes) {
     if (!b) return fail(VXG_ERR_ARG, "vxg_kernel_config: null batch");
+    {   // the table form (wide / compact) and with it the shared-memory size is decided when the classes are flushed
+        bool all = true;
+        for (int r = 0; r < b->n_robots; r++) all = all && b->uploaded[r];
+        if (all) { int rc = flush(b); if (rc) return rc; }
+    }
     if (threads) *threads = b->threads;
     if (vpt) *vpt = b->vpt;
     if (smem_mode) *smem_mode = b->smem_mode ? 1 : 0;

@@ -1,6 +1,6 @@
 // vxg_kernels.cuh -- sm_100a kernels of the Voxelyze timestep engine.
 //
-//   vx_step_kernel<Real, NV, VPT, SMEM>  one CTA per robot; advances the robot `n_steps` timesteps.
+//   vx_step_kernel<Real, NV, VPT, SMEM, COMPACT>  one CTA per robot; advances the robot `n_steps` timesteps.
 //       NV           : voxel stride of the blob (compile-time: every array offset is an immediate);
 //                     the CTA has NV / VPT threads.
 //       SMEM = true : the robot blob is staged into shared memory once, all steps run on chip, the
@@ -9,6 +9,7 @@
 //       SMEM = false: same code against the blob in global memory (robots larger than ~227 KB of
 //                     state, e.g. the fp64 mode at 10^3); the working set of the 148 resident robots
 //                     lives in L2.
+//       COMPACT      : bond classes in the two-vector compact form (BondKc, vx_math.cuh) instead of the wide table.
 //       VPT          : voxels per thread (thread t owns voxels t, t+T, ...), so a 10^3 robot (NV = 1024) runs
 //                     with 512 threads x 2 voxels and <=128 registers per thread.
 //   vx_stats_kernel<Real>            one CTA per robot; reductions for the result writer.
@@ -33,7 +34,7 @@ template <typename Real> struct BatchDev {
     unsigned char* blobs;       // [n_robots][L.total_bytes]
     BlobLayout L;
     RobotCtl* ctl;              // [n_robots]
-    BondK<Real>* bk;            // [n_robots][max_bclass]
+    unsigned char* bk;          // [n_robots][max_bclass] BondK<Real> (wide) or BondKc<Real> (compact) records
     double* bk_dist;            // [n_robots][max_bclass]
     VoxK<Real>* vk;             // [n_robots][max_vclass]
     ScaleK* sk;                 // [n_robots][max_vclass]
@@ -47,7 +48,8 @@ template <typename Real> struct BatchDev {
 
 // shared-memory carve-up after the blob
 template <typename Real> struct SmemTables {
-    BondK<Real>* bk; double* bk_dist; VoxK<Real>* vk; ScaleK* sk;
+    unsigned char* bk;   // BondK<Real> or BondKc<Real> records
+    double* bk_dist; VoxK<Real>* vk; ScaleK* sk;
     double* scale_c;  // [2][max_vclass]
     Real* dsc_c;      // [2][max_vclass]
     Real* ext_disp; Real* ext_tdisp;
@@ -56,9 +58,9 @@ template <typename Real> struct SmemTables {
 };
 
 template <typename Real>
-__host__ __device__ inline size_t tables_bytes(int max_vclass, int max_bclass) {
+__host__ __device__ inline size_t tables_bytes(int max_vclass, int max_bclass, bool compact = false) {
     size_t o = 0;
-    o = vx_align16(o + sizeof(BondK<Real>) * max_bclass);
+    o = vx_align16(o + (compact ? sizeof(BondKc<Real>) : sizeof(BondK<Real>)) * max_bclass);
     o = vx_align16(o + sizeof(double) * max_bclass);
     o = vx_align16(o + sizeof(VoxK<Real>) * max_vclass);
     o = vx_align16(o + sizeof(ScaleK) * max_vclass);
@@ -72,9 +74,9 @@ __host__ __device__ inline size_t tables_bytes(int max_vclass, int max_bclass) {
 }
 
 template <typename Real>
-__device__ inline SmemTables<Real> carve_tables(unsigned char* p, int max_vclass, int max_bclass) {
+__device__ inline SmemTables<Real> carve_tables(unsigned char* p, int max_vclass, int max_bclass, bool compact) {
     SmemTables<Real> t; size_t o = 0;
-    t.bk = (BondK<Real>*)(p + o);   o = vx_align16(o + sizeof(BondK<Real>) * max_bclass);
+    t.bk = p + o;                   o = vx_align16(o + (compact ? sizeof(BondKc<Real>) : sizeof(BondK<Real>)) * max_bclass);
     t.bk_dist = (double*)(p + o);   o = vx_align16(o + sizeof(double) * max_bclass);
     t.vk = (VoxK<Real>*)(p + o);    o = vx_align16(o + sizeof(VoxK<Real>) * max_vclass);
     t.sk = (ScaleK*)(p + o);        o = vx_align16(o + sizeof(ScaleK) * max_vclass);
@@ -137,7 +139,7 @@ __device__ inline void block_sum4(double& a, double& b, double& c, double& d, do
     for (int i = 0; i < nw; i++) { a += red[i]; b += red[32 + i]; c += red[64 + i]; d += red[96 + i]; }
 }
 
-template <typename Real, int NV, int VPT, bool SMEM>
+template <typename Real, int NV, int VPT, bool SMEM, bool COMPACT>
 __global__ void __launch_bounds__(NV / VPT, 1) vx_step_kernel(BatchDev<Real> B, int n_steps, int record_bonds) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int T = NV / VPT;
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(NV / VPT, 1) vx_step_kernel(BatchDev<Real> B, 
     unsigned char* gblob = B.blobs + (size_t)robot * L.total_bytes;
     unsigned char* base = SMEM ? smem : gblob;
     unsigned char* tab = SMEM ? smem + L.total_bytes : smem;
-    SmemTables<Real> S = carve_tables<Real>(tab, B.max_vclass, B.max_bclass);
+    SmemTables<Real> S = carve_tables<Real>(tab, B.max_vclass, B.max_bclass, COMPACT);
     const int n_vox = ctlp->n_vox, n_vc = ctlp->n_vclass, n_bc = ctlp->n_bclass;
     const unsigned int flags = ctlp->flags;
 
@@ -167,7 +169,8 @@ __global__ void __launch_bounds__(NV / VPT, 1) vx_step_kernel(BatchDev<Real> B, 
         uint4* a = (uint4*)(smem + L.off_accA);
         for (size_t i = tid; i < ((L.total_bytes - L.off_accA) >> 4); i += T) a[i] = z;
     }
-    copy4(S.bk, B.bk + (size_t)robot * B.max_bclass, sizeof(BondK<Real>) * n_bc, tid, T);
+    constexpr size_t BREC = COMPACT ? sizeof(BondKc<Real>) : sizeof(BondK<Real>);
+    copy4(S.bk, B.bk + (size_t)robot * B.max_bclass * BREC, BREC * n_bc, tid, T);
     copy4(S.vk, B.vk + (size_t)robot * B.max_vclass, sizeof(VoxK<Real>) * n_vc, tid, T);
     copy4(S.sk, B.sk + (size_t)robot * B.max_vclass, sizeof(ScaleK) * n_vc, tid, T);
     for (int i = tid; i < n_bc; i += T) S.bk_dist[i] = B.bk_dist[(size_t)robot * B.max_bclass + i];
@@ -186,7 +189,10 @@ __global__ void __launch_bounds__(NV / VPT, 1) vx_step_kernel(BatchDev<Real> B, 
 
     RobotView<Real> R = make_view<Real>(base, L, n_vox);
     RobotConsts<Real> C;
-    C.bk = S.bk; C.bk_dist = S.bk_dist; C.vk = S.vk;
+    C.bk = COMPACT ? nullptr : (const BondK<Real>*)S.bk;
+    C.bkc = COMPACT ? (const BondKc<Real>*)S.bk : nullptr;
+    C.geo = make_geo<Real>(ctlp->bond_len);
+    C.bk_dist = S.bk_dist; C.vk = S.vk;
     C.nom = B.nom + (size_t)robot * 3 * NV;
     C.ext_disp = S.ext_disp; C.ext_tdisp = S.ext_tdisp;
     C.half_bond_z = (Real)ctlp->half_bond_z;
@@ -195,6 +201,7 @@ __global__ void __launch_bounds__(NV / VPT, 1) vx_step_kernel(BatchDev<Real> B, 
     const bool fluid = (flags & VXG_F_FLUID_) != 0;
     C.floor_on = (flags & VXG_F_FLOOR_) && !fluid;
     C.sticky = (flags & VXG_F_STICKY_FLOOR_) != 0;
+    C.sym_mass = ctlp->sym_mass != 0;
     const bool temp_on = (flags & VXG_F_TEMPERATURE_) != 0, lw = (flags & VXG_F_LW_SCALE_) != 0;
     const double init_cm = ctlp->init_cm_time, tper = ctlp->temp_period, tamp = ctlp->temp_amplitude;
     const double minf = ctlp->min_fact, maxf = ctlp->max_fact;
@@ -248,18 +255,18 @@ __global__ void __launch_bounds__(NV / VPT, 1) vx_step_kernel(BatchDev<Real> B, 
         // the split-phase barrier orders without stalling the evaluations.
         int div = 0;
 #pragma unroll
-        for (int j = 0; j < VPT; j++) { P[j].w = -1; if (tid + j * T < n_vox) div |= bond_eval<Real, 0>(R, C, tid + j * T, st[j], own[j], fl[j], dt_inv, F[j], M[j], rec, P[j]) ? 1 : 0; }
+        for (int j = 0; j < VPT; j++) { P[j].w = -1; if (tid + j * T < n_vox) div |= bond_eval<Real, 0, COMPACT>(R, C, tid + j * T, st[j], own[j], fl[j], dt_inv, F[j], M[j], rec, P[j]) ? 1 : 0; }
 #pragma unroll
         for (int j = 0; j < VPT; j++) bond_push<Real>(R, P[j]);
         mbar_arrive_warp(S.mbar);
 #pragma unroll
-        for (int j = 0; j < VPT; j++) { P[j].w = -1; if (tid + j * T < n_vox) div |= bond_eval<Real, 1>(R, C, tid + j * T, st[j], own[j], fl[j], dt_inv, F[j], M[j], rec, P[j]) ? 1 : 0; }
+        for (int j = 0; j < VPT; j++) { P[j].w = -1; if (tid + j * T < n_vox) div |= bond_eval<Real, 1, COMPACT>(R, C, tid + j * T, st[j], own[j], fl[j], dt_inv, F[j], M[j], rec, P[j]) ? 1 : 0; }
         mbar_wait(S.mbar, mpar); mpar ^= 1u;
 #pragma unroll
         for (int j = 0; j < VPT; j++) bond_push<Real>(R, P[j]);
         mbar_arrive_warp(S.mbar);
 #pragma unroll
-        for (int j = 0; j < VPT; j++) { P[j].w = -1; if (tid + j * T < n_vox) div |= bond_eval<Real, 2>(R, C, tid + j * T, st[j], own[j], fl[j], dt_inv, F[j], M[j], rec, P[j]) ? 1 : 0; }
+        for (int j = 0; j < VPT; j++) { P[j].w = -1; if (tid + j * T < n_vox) div |= bond_eval<Real, 2, COMPACT>(R, C, tid + j * T, st[j], own[j], fl[j], dt_inv, F[j], M[j], rec, P[j]) ? 1 : 0; }
         mbar_wait(S.mbar, mpar); mpar ^= 1u;
 #pragma unroll
         for (int j = 0; j < VPT; j++) bond_push<Real>(R, P[j]);

@@ -20,11 +20,14 @@ struct EmulBase {
     virtual int diverged() = 0;
 };
 
-template <typename Real> struct Emul : EmulBase {
+template <typename Real, bool COMPACT = false> struct Emul : EmulBase {
     BlobLayout L;
     std::vector<unsigned char> blob;
     std::vector<double> nom, bk_dist, scale_c[2];
     std::vector<BondK<Real>> bk;
+    std::vector<BondKc<Real>> bkc;
+    double bond_len = 1.0;
+    bool compact_ok = false;
     std::vector<VoxK<Real>> vk;
     std::vector<ScaleK> sk;
     std::vector<Real> dsc_c[2], ext_disp, ext_tdisp, rec;
@@ -43,6 +46,8 @@ template <typename Real> struct Emul : EmulBase {
         ext_disp.resize(3 * nvc); ext_tdisp.resize(3 * nvc);
         pack_classes<Real>(d, bk.data(), bk_dist.data(), vk.data(), sk.data(), scale_c[0].data(), ext_disp.data(), ext_tdisp.data());
         pack_blob<Real>(d, L, blob.data(), nom.data());
+        bkc.resize(nbc);
+        compact_ok = pack_compact<Real>(d, bkc.data(), &bond_len);
         init_ctl(d, ctl);
         for (int i = 0; i < nvc; i++) dsc_c[0][i] = (Real)(scale_c[0][i] - sk[i].nom_size);
         rec.assign((size_t)39 * L.nv, (Real)0);
@@ -53,12 +58,13 @@ template <typename Real> struct Emul : EmulBase {
     int64_t step(int64_t n) override {
         RobotView<Real> R = make_view<Real>(blob.data(), L, ctl.n_vox);
         RobotConsts<Real> C;
-        C.bk = bk.data(); C.bk_dist = bk_dist.data(); C.vk = vk.data(); C.nom = nom.data();
+        C.bk = bk.data(); C.bkc = bkc.data(); C.geo = make_geo<Real>(bond_len); C.bk_dist = bk_dist.data(); C.vk = vk.data(); C.nom = nom.data();
         C.ext_disp = ext_disp.data(); C.ext_tdisp = ext_tdisp.data();
         C.half_bond_z = (Real)ctl.half_bond_z; C.dt = (Real)ctl.dt;
         const bool fluid = (ctl.flags & VXG_F_FLUID) != 0;
         C.floor_on = (ctl.flags & VXG_F_FLOOR) && !fluid;
         C.sticky = (ctl.flags & VXG_F_STICKY_FLOOR) != 0;
+        C.sym_mass = ctl.sym_mass != 0;
         const bool temp_on = (ctl.flags & VXG_F_TEMPERATURE) != 0, lw = (ctl.flags & VXG_F_LW_SCALE) != 0;
         const Real dt_inv_run = (Real)(1.0 / ctl.dt);
         std::vector<V3<Real>> F(ctl.n_vox), M(ctl.n_vox);
@@ -71,9 +77,9 @@ template <typename Real> struct Emul : EmulBase {
             bool d = false;
             std::vector<uint32_t> fl(ctl.n_vox);
             for (int v = 0; v < ctl.n_vox; v++) fl[v] = R.flags[v];
-            for (int v = 0; v < ctl.n_vox; v++) d |= bond_task<Real, 0>(R, C, v, R.stat[v], fl[v], dt_inv, F[v], M[v], rec.data());
-            for (int v = 0; v < ctl.n_vox; v++) d |= bond_task<Real, 1>(R, C, v, R.stat[v], fl[v], dt_inv, F[v], M[v], rec.data());
-            for (int v = 0; v < ctl.n_vox; v++) d |= bond_task<Real, 2>(R, C, v, R.stat[v], fl[v], dt_inv, F[v], M[v], rec.data());
+            for (int v = 0; v < ctl.n_vox; v++) d |= bond_task<Real, 0, COMPACT>(R, C, v, R.stat[v], fl[v], dt_inv, F[v], M[v], rec.data());
+            for (int v = 0; v < ctl.n_vox; v++) d |= bond_task<Real, 1, COMPACT>(R, C, v, R.stat[v], fl[v], dt_inv, F[v], M[v], rec.data());
+            for (int v = 0; v < ctl.n_vox; v++) d |= bond_task<Real, 2, COMPACT>(R, C, v, R.stat[v], fl[v], dt_inv, F[v], M[v], rec.data());
             if (d) { div = 1; break; }
             for (int v = 0; v < ctl.n_vox; v++) voxel_task<Real>(R, C, v, R.stat[v], load_own<Real>(R, v), fl[v], F[v], M[v]);
             for (int i = 0; i < ctl.n_vclass; i++) {
@@ -121,6 +127,11 @@ template <typename Real> struct Emul : EmulBase {
 extern "C" {
 void* vxe_create(const vxg_robot_desc* d, int prec) {
     if (prec == VXG_PREC_F64) return new Emul<double>(d);
+    if (prec == 2) {   // fp32 with the compact bond table (what the production kernel uses when every class qualifies)
+        Emul<float, true>* e = new Emul<float, true>(d);
+        if (!e->compact_ok) { delete e; return nullptr; }
+        return e;
+    }
     return new Emul<float>(d);
 }
 void vxe_destroy(void* h) { delete (EmulBase*)h; }

@@ -40,11 +40,15 @@ def test_emulated_f64_kernel_arithmetic(name):
             assert np.abs(s.bond_force2 - d.bstate[f, :, 3:6]).max() <= ftol * fmax
 
 
+@pytest.mark.parametrize("prec", [abi.VXG_PREC_F32, 2], ids=["wide", "compact"])
 @pytest.mark.parametrize("name", CASES)
-def test_emulated_f32_kernel_arithmetic(name):
+def test_emulated_f32_kernel_arithmetic(name, prec):
+    """prec 2 = fp32 with the compact bond-class table (BondKc): every class of the reference's importer
+    must qualify for it, and it must meet the same tolerance as the wide table."""
     g = golden_lib.Golden(name)
     d = g.dump
-    e = emul_lib.EmulSim(g.robot(), abi.VXG_PREC_F32)
+    e = emul_lib.EmulSim(g.robot(), prec)
+    assert e.h, "bond classes did not qualify for the compact form"
     for f in range(1, d.vstate.shape[0]):
         assert e.step(g.every) == g.every
         s = e.state()
