@@ -92,6 +92,9 @@ class RobotStats(C.Structure):
         ("com", C.c_double * 3), ("ini_com", C.c_double * 3), ("max_vel", C.c_double),
         ("min_pos", C.c_double * 3), ("max_pos", C.c_double * 3), ("time", C.c_double),
         ("steps", C.c_int64), ("n_touching_floor", C.c_int32), ("ini_com_latched", C.c_int32),
+        ("anterior_dist", C.c_double), ("posterior_dist", C.c_double), ("anterior_y", C.c_double),
+        ("posterior_y", C.c_double), ("eol_posterior_y", C.c_double),
+        ("n_nonfeet_touching_floor", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

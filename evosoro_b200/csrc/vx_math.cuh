@@ -501,6 +501,7 @@ VX_HD bool voxel_integrate(const VoxK<T>& k, V3<T> F, V3<T> M, double half_scale
 // windows); land/water fork: LW/VXS_Voxel.cpp:211-235.  `t` is CurTime BEFORE the increment.
 struct ScaleK {
     double nom_size, init_size, cte, temp_amp_damp, phase_offset;
+    long long mat_index;   // palette index of the class (fitness probes key on 5 / 6, VX_Sim.cpp:2626-2705)
 };
 VX_HD double scale_law(const ScaleK& c, double last_scale, double t, double init_cm_time, double temp_period,
                        double temp_amplitude, double min_fact, double max_fact, bool temp_on, bool lw) {

@@ -81,6 +81,7 @@ inline void pack_classes(const vxg_robot_desc* d, BondK<Real>* bk, double* bk_di
         }
         k.dof = c.dof_fixed; k.has_bc = bc ? 1 : 0;
         ScaleK& s = sk[i];
+        s.mat_index = c.mat_index;
         s.nom_size = c.nom_size; s.init_size = c.init_size; s.cte = c.cte; s.temp_amp_damp = c.temp_amp_damp; s.phase_offset = c.phase_offset;
         scale_c[i] = c.nom_size;   // ResetVoxel: Scale = NominalSize (VXS_Voxel.cpp:110)
     }
@@ -110,7 +111,7 @@ inline void init_ctl(const vxg_robot_desc* d, RobotCtl& c) {
     memset(&c, 0, sizeof c);
     c.cur_time = 0; c.dt = P.dt; c.init_cm_time = P.init_cm_time; c.temp_period = P.temp_period; c.temp_amplitude = P.temp_amplitude;
     c.min_fact = P.min_scale_fact; c.max_fact = P.max_scale_fact;
-    c.step = 0; c.total_steps = 0x7fffffffffffffffLL; c.latch_step = -1; c.status = 0; c.flags = P.flags;
+    c.step = 0; c.total_steps = 0x7fffffffffffffffLL; c.latch_step = -1; c.eol_step = -1; c.eol_post_y = 0; c.status = 0; c.flags = P.flags;
     c.n_vox = d->n_vox; c.n_vclass = d->n_vclass; c.n_bclass = d->n_bclass; c.ini_latched = 0;
     c.half_bond_z = 0.5 * P.bond_damp_z;
     c.sym_mass = 1;

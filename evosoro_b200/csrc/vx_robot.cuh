@@ -279,6 +279,8 @@ struct RobotCtl {
     int sym_mass;           // every bond class has identical voxel-1 / voxel-2 damping constants
     double half_bond_z;     // 0.5 BondDampingZ
     double bond_len;        // the common bond length L of the compact form
+    long long eol_step;     // CurStepCount at which EndOfLifetimePosteriorY is latched (-1 never)
+    double eol_post_y;      // min Pos.y over material != 5 at that step (metres); 0 = not latched
 };
 
 }  // namespace vx

@@ -330,6 +330,15 @@ extern "C" int vxg_set_step_budget(vxg_batch* b, const int64_t* total_steps, con
     return VXG_OK;
 }
 
+extern "C" int vxg_set_eol_step(vxg_batch* b, const int64_t* eol_step) {
+    if (!b || !eol_step) return fail(VXG_ERR_ARG, "vxg_set_eol_step: null argument");
+    int rc = pull(b, false, -1);
+    if (rc) return rc;
+    for (int r = 0; r < b->n_robots; r++) if (b->uploaded[r]) b->h_ctl[r].eol_step = eol_step[r];
+    b->ctl_dirty = true;
+    return VXG_OK;
+}
+
 extern "C" int vxg_enable_bond_record(vxg_batch* b, int on) {
     if (!b) return fail(VXG_ERR_ARG, "vxg_enable_bond_record: null batch");
     CK(cudaSetDevice(b->device));

@@ -123,6 +123,10 @@ __device__ inline void mbar_wait(unsigned long long* bar, unsigned int parity) {
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+__device__ inline double warp_max(double x) {
+    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
+    return x;
+}
 __device__ inline double warp_sum(double x) {
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
     return x;
@@ -149,7 +153,7 @@ __global__ void __launch_bounds__(NV / VPT, 1) vx_step_kernel(BatchDev<Real> B, 
     RobotCtl* ctlp = B.ctl + robot;
     const unsigned int status0 = ctlp->status;
     if (status0 & (VXG_ST_DIVERGED_ | VXG_ST_FINISHED_)) return;
-    const long long step0 = ctlp->step, total = ctlp->total_steps, latch = ctlp->latch_step;
+    const long long step0 = ctlp->step, total = ctlp->total_steps, latch = ctlp->latch_step, eol = ctlp->eol_step;
     long long remaining = total - step0;
     int nsteps = remaining < (long long)n_steps ? (int)remaining : n_steps;
     if (nsteps <= 0) { if (tid == 0) ctlp->status = status0 | VXG_ST_FINISHED_; return; }
@@ -222,6 +226,15 @@ __global__ void __launch_bounds__(NV / VPT, 1) vx_step_kernel(BatchDev<Real> B, 
             }
             block_sum4(mx, my, mz, mm, S.red);
             if (tid == 0) { ctlp->ini_com[0] = mx / mm; ctlp->ini_com[1] = my / mm; ctlp->ini_com[2] = mz / mm; ctlp->ini_latched = 1; }
+        }
+        if (s == eol) {     // SS.EndOfLifetimePosteriorY = getPosteriorY() at TimeStep entry (VX_Sim.cpp:1078-1082)
+            double lo = 1e300;
+            for (int v = tid; v < n_vox; v += T) if (S.sk[R.stat[v].vcls].mat_index != 5) lo = fmin(lo, R.pos[NV + v]);
+            lo = -warp_max(-lo);
+            __syncthreads();
+            if ((tid & 31) == 0) S.red[tid >> 5] = lo;
+            __syncthreads();
+            if (tid == 0) { for (int i = 1; i < T / 32; i++) lo = fmin(lo, S.red[i]); ctlp->eol_post_y = lo; }
         }
         C.scale_c = S.scale_c + cur * B.max_vclass;
         C.dsc_c = S.dsc_c + cur * B.max_vclass;
@@ -301,29 +314,30 @@ struct StatsDev {   // mirrors vxg_robot_stats
     double com[3], ini_com[3], max_vel, min_pos[3], max_pos[3], time;
     long long steps;
     int n_touching_floor, ini_com_latched;
+    double anterior_dist, posterior_dist, anterior_y, posterior_y, eol_posterior_y;
+    int n_nonfeet_touching_floor, reserved;
 };
 
-__device__ inline double warp_max(double x) {
-    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
-    return x;
-}
 
 // CVX_Sim::GetCM (VX_Sim.cpp:2415-2430), GetNumTouchingFloor (:2432-2441), SS.MaxVoxVel (:1511-1690)
 template <typename Real>
 __global__ void __launch_bounds__(256) vx_stats_kernel(BatchDev<Real> B, StatsDev* out) {
     __shared__ double red[4 * 32];
-    __shared__ double redm[7 * 8];
-    __shared__ int redi[8];
+    __shared__ double redm[11 * 8];
+    __shared__ int redi[2 * 8];
     const int robot = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
     const RobotCtl* ctl = B.ctl + robot;
     const BlobLayout L = B.L;
     RobotView<Real> R = make_view<Real>(B.blobs + (size_t)robot * L.total_bytes, L, ctl->n_vox);
     const VoxK<Real>* vk = B.vk + (size_t)robot * B.max_vclass;
+    const ScaleK* sk = B.sk + (size_t)robot * B.max_vclass;
     const double* scale_c = B.scale_c + (size_t)robot * B.max_vclass;
     const int nv = R.nv;
+    const double icx = ctl->ini_com[0], icy = ctl->ini_com[1];
     double mx = 0, my = 0, mz = 0, mm = 0, vmax = 0;
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-    int touching = 0;
+    double dmax = 0, dmin = 1e300, ymax = -1e300, ymin = 1e300;
+    int touching = 0, feet = 0;
     for (int v = tid; v < R.n_vox; v += T) {
         int vc = R.stat[v].vcls;
         double m = (double)vk[vc].mass;
@@ -335,23 +349,31 @@ __global__ void __launch_bounds__(256) vx_stats_kernel(BatchDev<Real> B, StatsDe
         vmax = fmax(vmax, sqrt(vx_ * vx_ + vy_ * vy_ + vz_ * vz_));
         lo[0] = fmin(lo[0], px); lo[1] = fmin(lo[1], py); lo[2] = fmin(lo[2], pz);
         hi[0] = fmax(hi[0], px); hi[1] = fmax(hi[1], py); hi[2] = fmax(hi[2], pz);
-        if (0.5 * scale_c[vc] - pz > 0) touching++;
+        const bool touch = 0.5 * scale_c[vc] - pz > 0;
+        if (touch) touching++;
+        const long long mat = sk[vc].mat_index;
+        if (touch && mat == 6) feet++;                                   // GetNumNonFeetTouchingFloor (VX_Sim.cpp:2690-2704)
+        double dd = sqrt((px - icx) * (px - icx) + (py - icy) * (py - icy));   // getAnteriorDist / getPosteriorDist
+        dmax = fmax(dmax, dd); dmin = fmin(dmin, dd);
+        if (mat != 5) { ymax = fmax(ymax, py); ymin = fmin(ymin, py); }  // getAnteriorY / getPosteriorY
     }
     block_sum4(mx, my, mz, mm, red);
-    double m7[7] = {vmax, -lo[0], -lo[1], -lo[2], hi[0], hi[1], hi[2]};
+    double m11[11] = {vmax, -lo[0], -lo[1], -lo[2], hi[0], hi[1], hi[2], dmax, -dmin, ymax, -ymin};
     int lane = tid & 31, wid = tid >> 5, nw = (T + 31) >> 5;
-    for (int i = 0; i < 7; i++) m7[i] = warp_max(m7[i]);
-    for (int o = 16; o > 0; o >>= 1) touching += __shfl_xor_sync(0xffffffffu, touching, o);
-    if (lane == 0) { for (int i = 0; i < 7; i++) redm[i * 8 + wid] = m7[i]; redi[wid] = touching; }
+    for (int i = 0; i < 11; i++) m11[i] = warp_max(m11[i]);
+    for (int o = 16; o > 0; o >>= 1) { touching += __shfl_xor_sync(0xffffffffu, touching, o); feet += __shfl_xor_sync(0xffffffffu, feet, o); }
+    if (lane == 0) { for (int i = 0; i < 11; i++) redm[i * 8 + wid] = m11[i]; redi[wid] = touching; redi[8 + wid] = feet; }
     __syncthreads();
     if (tid == 0) {
         StatsDev s;
-        for (int i = 0; i < 7; i++) { double x = redm[i * 8]; for (int w = 1; w < nw; w++) x = fmax(x, redm[i * 8 + w]); m7[i] = x; }
-        int tc = 0; for (int w = 0; w < nw; w++) tc += redi[w];
+        for (int i = 0; i < 11; i++) { double x = redm[i * 8]; for (int w = 1; w < nw; w++) x = fmax(x, redm[i * 8 + w]); m11[i] = x; }
+        int tc = 0, fc = 0; for (int w = 0; w < nw; w++) { tc += redi[w]; fc += redi[8 + w]; }
         s.com[0] = mx / mm; s.com[1] = my / mm; s.com[2] = mz / mm;
-        for (int i = 0; i < 3; i++) { s.ini_com[i] = ctl->ini_com[i]; s.min_pos[i] = -m7[1 + i]; s.max_pos[i] = m7[4 + i]; }
-        s.max_vel = m7[0]; s.time = ctl->cur_time; s.steps = ctl->step;
+        for (int i = 0; i < 3; i++) { s.ini_com[i] = ctl->ini_com[i]; s.min_pos[i] = -m11[1 + i]; s.max_pos[i] = m11[4 + i]; }
+        s.max_vel = m11[0]; s.time = ctl->cur_time; s.steps = ctl->step;
         s.n_touching_floor = tc; s.ini_com_latched = ctl->ini_latched;
+        s.anterior_dist = m11[7]; s.posterior_dist = -m11[8]; s.anterior_y = m11[9]; s.posterior_y = -m11[10];
+        s.eol_posterior_y = ctl->eol_post_y; s.n_nonfeet_touching_floor = fc; s.reserved = 0;
         out[robot] = s;
     }
 }

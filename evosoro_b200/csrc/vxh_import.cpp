@@ -12,6 +12,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <sstream>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -185,7 +186,7 @@ struct Parsed {
     // <Environment>  (VX_Environment.cpp:123-293)
     int n_bcs = 0;
     bool grav_on = false, floor_on = false, temp_on = false, vary_temp = false, sticky = false, falling_prohibited = false;
-    bool limited_floor = false, sources = false, fluid = false;
+    bool limited_floor = false, sources = false, fluid = false, needle = false, norm_by_vol = false, save_traces = false;
     double grav_acc = -9.81, temp_base = 25, temp_amplitude = 0, temp_period = 0.1, growth_amp = 0, drag = 0;
     // <VXC>  (VX_Object.cpp:435-490, :1064-1074, :1733-1930, :2495-2513)
     double lat = 0.001, adj[3] = {1, 1, 1}, line_off[2] = {0, 0}, layer_off[2] = {0, 0};
@@ -275,6 +276,7 @@ int parse_vxa(const XNode* root, int variant, Parsed& P) {
             if (!load(E, "GrowthAmplitude", &P.growth_amp)) P.growth_amp = 0;
             load(E, "StickyFloor", &P.sticky);
             load(E, "FallingProhibited", &P.falling_prohibited);
+            load(E, "NeedleInHaystack", &P.needle); load(E, "NormDistByVol", &P.norm_by_vol); load(E, "SaveTraces", &P.save_traces);
             double fr; P.limited_floor = load(E, "FloorRadius", &fr);
             if (const XNode* s = E->child("Sources")) P.sources = s->child("Source") != nullptr;
         } else {
@@ -353,6 +355,9 @@ int check_supported(const Parsed& P, int ignore_collisions) {
     if (P.limited_floor) return hfail(VXG_UNSUPPORTED_FEATURE, "FloorRadius (limited floor) is not supported");
     if (P.sources) return hfail(VXG_UNSUPPORTED_FEATURE, "environmental <Sources> are not supported");
     if (P.falling_prohibited) return hfail(VXG_UNSUPPORTED_FEATURE, "FallingProhibited is not supported");
+    if (P.needle) return hfail(VXG_UNSUPPORTED_FEATURE, "NeedleInHaystack is not supported");
+    if (P.norm_by_vol) return hfail(VXG_UNSUPPORTED_FEATURE, "NormDistByVol (volume traces) is not supported");
+    if (P.save_traces) return hfail(VXG_UNSUPPORTED_FEATURE, "SaveTraces (CM traces in the result file) is not supported");
     for (size_t i = 1; i < P.palette.size(); i++)
         if (P.palette[i].mat_model != 0 && P.palette[i].mat_model != 1) {   // MDL_LINEAR, MDL_LINEAR_FAIL
             bool used = false;
@@ -555,8 +560,9 @@ extern "C" int vxh_cell_index(const vxh_model* m, int32_t* out) {
 }
 
 // The CLI loop `while (!StopConditionMet()) TimeStep()` (voxelyzeMain/main.cpp:89-110) replayed on the
-// fp64 clock alone: StopConditionMet VX_Sim.cpp:1398-1425, IniCM latch VX_Sim.cpp:1064, CurTime += dt :1929.
-extern "C" int vxh_step_plan(const vxh_model* m, int64_t* total_steps, int64_t* latch_step, double* final_time) {
+// fp64 clock alone: StopConditionMet VX_Sim.cpp:1398-1425, IniCM latch VX_Sim.cpp:1064, EndOfLifetimePosteriorY
+// latch :1078-1082, CurTime += dt :1929.
+extern "C" int vxh_step_plan_ex(const vxh_model* m, int64_t* total_steps, int64_t* latch_step, int64_t* eol_step, double* final_time) {
     if (!m) return hfail(VXG_ERR_ARG, "null model");
     const vxh_info& I = m->info;
     const double dt = m->desc.sim.dt;
@@ -566,20 +572,82 @@ extern "C" int vxh_step_plan(const vxh_model* m, int64_t* total_steps, int64_t* 
         return hfail(VXG_UNSUPPORTED_FEATURE, "stop condition type %d depends on simulation state; only MAX_TIME_STEPS / MAX_SIM_TIME / TEMP_CYCLES are supported", type);
     double limit = type == 2 ? I.stop_condition_value + I.afterlife_time : (type == 3 ? m->temp_period * I.stop_condition_value : 0);
     if (type != 1 && !(limit / dt < 4e9)) return hfail(VXG_ERR_ARG, "stop condition needs more than 4e9 steps");
-    double t = 0; int64_t step = 0, latch = -1;
+    const bool lw = m->variant == VXH_VARIANT_LAND_WATER;
+    double t = 0; int64_t step = 0, latch = -1, eol = -1;
     for (;;) {
         bool met = false;
-        if (t > I.init_cm_time) {
+        if (lw || t > I.init_cm_time) {   // the land/water fork has no InitCmTime guard (LW/VX_Sim.cpp StopConditionMet)
             if (type == 1) met = step > (int64_t)(int)(I.stop_condition_value + 0.5);
             else met = t > limit;
         }
         if (met) break;
         if (latch < 0 && t > I.init_cm_time) latch = step;
+        if (!lw && eol < 0 && t >= I.stop_condition_value) eol = step;
         t += dt; step++;
         if (step > 4000000000LL) return hfail(VXG_ERR_ARG, "stop condition never met");
     }
     if (total_steps) *total_steps = step;
     if (latch_step) *latch_step = latch;
+    if (eol_step) *eol_step = eol;
     if (final_time) *final_time = t;
     return 0;
+}
+
+extern "C" int vxh_step_plan(const vxh_model* m, int64_t* total_steps, int64_t* latch_step, double* final_time) {
+    return vxh_step_plan_ex(m, total_steps, latch_step, nullptr, final_time);
+}
+
+// CVX_SimGA::WriteResultFile (VX_SimGA.cpp:33-168; LW/VX_SimGA.cpp:33-75).  Numbers go through an
+// ostringstream exactly like CXML_Rip::Element (Utils/XML_Rip.h:57-59), the layout is tinyxml's SaveFile.
+extern "C" int vxh_format_result(const vxh_model* m, const vxg_robot_stats* st, char* buf, int cap, const char* path) {
+    if (!m || !st) return hfail(VXG_ERR_ARG, "null argument");
+    const double lat = m->info.lattice_dim;
+    std::ostringstream o;
+    auto el = [&o](const char* tag, double v) { std::ostringstream t; t << v; o << "        <" << tag << ">" << t.str() << "</" << tag << ">\n"; };
+    auto elf = [&o](const char* tag, float v) { std::ostringstream t; t << v; o << "        <" << tag << ">" << t.str() << "</" << tag << ">\n"; };
+    auto eli = [&o](const char* tag, long long v) { o << "        <" << tag << ">" << v << "</" << tag << ">\n"; };
+    o << "<?xml version=\"1.0\" ?>\n<Voxelyze_Sim_Result Version=\"1.0\">\n    <Fitness>\n";
+    const double dx = st->com[0] - st->ini_com[0], dy = st->com[1] - st->ini_com[1], dz = st->com[2] - st->ini_com[2];
+    if (m->variant == VXH_VARIANT_LAND_WATER) {
+        const double nx = dx / lat, ny = dy / lat, nz = dz / lat;
+        eli("VoxelNumber", m->info.n_vox);
+        elf("normAbsoluteDisplacement", (float)sqrt(nx * nx + ny * ny + nz * nz));
+        elf("normDistX", (float)nx); elf("normDistY", (float)ny); elf("normDistZ", (float)nz);
+        // shape descriptors are only computed with --computeShapeDescriptors (needs qhull); the stock run leaves -1
+        // RobotVolumeStart: the closed surface mesh of the undeformed robot encloses exactly its voxels
+        el("RobotVolumeStart", m->info.n_vox * lat * lat * lat); el("ConvexHullVolumeStart", -1); el("RobotVolumeEnd", -1); el("ConvexHullVolumeEnd", -1);
+        el("ShapeComplexityStart", -1); el("ShapeComplexityEnd", -1);
+    } else {
+        const double final_dist = pow(pow(dx, 2) + pow(dy, 2), 0.5) / lat;
+        const double post_dist = st->posterior_dist / lat, ant_dist = st->anterior_dist / lat;
+        double ant_y = st->anterior_y / lat; if (!(ant_y > 0.0)) ant_y = 0.0;            // getAnteriorY starts from 0
+        double post_y = st->posterior_y / lat; if (!(post_y < 100000.0)) post_y = 100000.0;   // getPosteriorY starts from 1e5
+        const double eol = st->eol_posterior_y / lat;
+        el("NormFinalDist", final_dist);                 // normFinalDist - normFrozenDist, no volume normalisation in scope
+        el("NormRegimeDist", post_dist - eol);
+        el("NormFrozenDist", 0);
+        el("FinalDist", final_dist);
+        el("finalDistY", dy / lat);
+        el("AnteriorDist", ant_dist);
+        el("PosteriorDist", post_dist);
+        el("AnteriorY", ant_y);
+        el("PosteriorY", post_y);
+        el("EndOfLifePosteriorY", eol);
+        el("FallAdjPostY", eol);
+        eli("NumNonFeetTouchingFloor", st->n_nonfeet_touching_floor);
+        eli("NumTouchingFloor", st->n_touching_floor);
+        el("Lifetime", st->time - m->info.afterlife_time);
+        eli("FoundNeedleInHaystack", 0);
+        el("PushDist", 0);
+    }
+    o << "    </Fitness>\n</Voxelyze_Sim_Result>\n";
+    const std::string text = o.str();
+    if (buf && cap > 0) { snprintf(buf, (size_t)cap, "%s", text.c_str()); }
+    if (path && *path) {
+        FILE* f = fopen(path, "wb");
+        if (!f) return hfail(VXG_ERR_ARG, "cannot write %s", path);
+        fwrite(text.data(), 1, text.size(), f);
+        fclose(f);
+    }
+    return (int)text.size();
 }

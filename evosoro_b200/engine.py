@@ -82,6 +82,9 @@ def lib():
         L.vxh_get_info.argtypes = [vp, C.POINTER(abi.VxaInfo)]
         L.vxh_cell_index.argtypes = [vp, abi.c_int32_p]
         L.vxh_step_plan.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+        L.vxh_step_plan_ex.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+        L.vxh_format_result.argtypes = [vp, C.POINTER(abi.RobotStats), C.c_char_p, C.c_int, C.c_char_p]
+        L.vxg_set_eol_step.argtypes = [vp, C.POINTER(C.c_int64)]
         _LIB = L
     return _LIB
 
@@ -126,6 +129,22 @@ class Model:
         if rc != 0:
             raise EngineError(rc, lib().vxh_last_error().decode(errors="replace"))
         return t.value, l.value, ft.value
+
+    def step_plan_ex(self):
+        """(total_steps, latch_step, eol_step, final_time)"""
+        t, l, e, ft = C.c_int64(), C.c_int64(), C.c_int64(), C.c_double()
+        rc = lib().vxh_step_plan_ex(self.h, C.byref(t), C.byref(l), C.byref(e), C.byref(ft))
+        if rc != 0:
+            raise EngineError(rc, lib().vxh_last_error().decode(errors="replace"))
+        return t.value, l.value, e.value, ft.value
+
+    def format_result(self, stats: "abi.RobotStats", path: Optional[str] = None) -> str:
+        """The result XML of CVX_SimGA::WriteResultFile for this robot's reductions."""
+        buf = C.create_string_buffer(4096)
+        n = lib().vxh_format_result(self.h, C.byref(stats), buf, 4096, os.fsencode(path) if path else None)
+        if n < 0:
+            raise EngineError(n, lib().vxh_last_error().decode(errors="replace"))
+        return buf.value.decode()
 
     def cell_index(self) -> np.ndarray:
         out = np.zeros(self.info.n_vox, dtype=np.int32)
@@ -180,6 +199,11 @@ class Batch:
         ta, tp = arr(total_steps)
         la, lp = arr(latch_step)
         _ck(lib().vxg_set_step_budget(self.h, tp, lp))
+
+    def set_eol_step(self, eol_step):
+        a = np.ascontiguousarray(eol_step, dtype=np.int64)
+        assert a.shape == (self.n_robots,)
+        _ck(lib().vxg_set_eol_step(self.h, a.ctypes.data_as(C.POINTER(C.c_int64))))
 
     def step(self, n: int):
         _ck(lib().vxg_step(self.h, int(n)))

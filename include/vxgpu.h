@@ -190,8 +190,16 @@ typedef struct vxg_robot_stats {
     double max_pos[3];    /* max over voxels of Pos                                                  */
     double time;          /* CurTime                                                                 */
     int64_t steps;        /* CurStepCount                                                            */
-    int32_t n_touching_floor; /* count of 0.5 Scale - z > 0     VX_Sim.cpp:2584                      */
+    int32_t n_touching_floor; /* count of 0.5 Scale - z > 0     VX_Sim.cpp:2432-2441                 */
     int32_t ini_com_latched;
+    /* fitness probes of the result writer (VX_Sim.cpp:2584-2712), in metres (the writer divides by the lattice pitch) */
+    double anterior_dist;     /* max over voxels of the horizontal distance to IniCM   getAnteriorDist  */
+    double posterior_dist;    /* min ...                                               getPosteriorDist */
+    double anterior_y;        /* max Pos.y over voxels whose material index != 5, floor 0  getAnteriorY  */
+    double posterior_y;       /* min Pos.y over voxels whose material index != 5, cap 1e5 lattice pitches  getPosteriorY */
+    double eol_posterior_y;   /* posterior_y latched at the TimeStep() entry where CurTime >= StopConditionValue (VX_Sim.cpp:1078-1082); 0 = never */
+    int32_t n_nonfeet_touching_floor; /* touching-floor count restricted to material index 6  GetNumNonFeetTouchingFloor */
+    int32_t reserved;
 } vxg_robot_stats;
 
 typedef struct vxg_batch vxg_batch; /* opaque; owns all device memory */
@@ -217,6 +225,9 @@ int vxg_upload(vxg_batch* b, int robot, const vxg_robot_desc* desc);
  * CurStepCount at whose TimeStep() entry IniCM is latched (VX_Sim.cpp:1064-1075); -1 = never.
  * Either pointer may be NULL (no limit / no latch). */
 int vxg_set_step_budget(vxg_batch* b, const int64_t* total_steps, const int64_t* latch_step);
+/* eol_step[r] = CurStepCount at whose TimeStep() entry EndOfLifetimePosteriorY is latched (CurTime >=
+ * StopConditionValue, VX_Sim.cpp:1078-1082); -1 = never (the usual case without an afterlife). */
+int vxg_set_eol_step(vxg_batch* b, const int64_t* eol_step);
 
 /* Replaces: n_steps calls of CVX_Sim::Integrate() (VX_Sim.cpp:1763-1933) on every robot of the batch
  * that is neither diverged nor finished.  Asynchronous on the batch's stream. */

@@ -56,6 +56,15 @@ int vxh_cell_index(const vxh_model* m, int32_t* out);
  * SC_TEMP_CYCLES are time-driven; others return VXG_UNSUPPORTED_FEATURE. */
 int vxh_step_plan(const vxh_model* m, int64_t* total_steps, int64_t* latch_step, double* final_time);
 
+/* Same, plus the CurStepCount at whose TimeStep() entry EndOfLifetimePosteriorY is latched (VX_Sim.cpp:1078-1082; -1 = never). */
+int vxh_step_plan_ex(const vxh_model* m, int64_t* total_steps, int64_t* latch_step, int64_t* eol_step, double* final_time);
+
+/* Replaces CVX_SimGA::WriteResultFile / SaveResultFile (VX_SimGA.cpp:25-168; land/water fork: LW/VX_SimGA.cpp:36-75):
+ * formats the <Voxelyze_Sim_Result><Fitness> block from the device reductions with the reference's tag set and
+ * number formatting.  buf/cap receive the text (may be NULL/0); path (may be NULL) is written if given.
+ * Returns the text length, or a negative error. */
+int vxh_format_result(const vxh_model* m, const vxg_robot_stats* st, char* buf, int cap, const char* path);
+
 /* thread-local message of the last failing vxh_* call */
 const char* vxh_last_error(void);
 

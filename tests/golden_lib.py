@@ -23,10 +23,19 @@ class Golden:
         self.full_hdr = z["full_hdr"] if "full_hdr" in z else None
         self.full_vstate = z["full_vstate"] if "full_vstate" in z else None
         self.full_tail = z["full_tail"] if "full_tail" in z else None
+        self.result_xml = bytes(z["result_xml"]).decode("latin-1") if "result_xml" in z else None
+        self.fitness_file = bytes(z["fitness_file"]).decode() if "fitness_file" in z else None
 
     def robot(self):
         """Descriptor derived from the reference's own imported arrays (independent of the product importer)."""
         return refdump.desc_from_dump(self.dump, lw=self.lw)
+
+
+def parse_result(xml: str) -> dict:
+    """tag -> float of a <Voxelyze_Sim_Result>, read the way evosoro does (line-wise <tag>value</tag>,
+    read_write_voxelyze.py:27-35)."""
+    import re
+    return {m.group(1): float(m.group(2)) for m in re.finditer(r"<(\w+)>([^<]+)</\1>", xml)}
 
 
 def names():

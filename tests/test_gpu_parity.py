@@ -3,6 +3,9 @@
   (b) the reference itself run on this box (oracle/_ref/ref_dump, when it travelled with the snapshot),
   (c) the C oracle (oracle/vx_oracle.c) on seeded inputs, up to BASELINE.json's full sizes.
 Tolerances are stated per test: positions in units of the lattice pitch."""
+import os
+import subprocess
+
 import numpy as np
 import pytest
 
@@ -249,3 +252,58 @@ def test_host_buffer_entry_point_matches_resident_path():
     for r in range(6):
         assert np.array_equal(pos[r, : robots[r].n_vox], b.download(r).pos)
     e.close(); b.close()
+
+
+# ---- P5: the CLI contract (seam B1) ----------------------------------------------------------------
+FULL_XML = [n for n in golden_lib.names() if n.endswith("_full") and golden_lib.Golden(n).result_xml]
+CLI = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "evosoro_b200", "lib", "voxelyze")
+
+
+def _check_result(ours_xml, g):
+    ours, ref = golden_lib.parse_result(ours_xml), golden_lib.parse_result(g.result_xml)
+    assert list(ours.keys()) == list(ref.keys())
+    for k, v in ref.items():
+        if g.lw and k == "RobotVolumeEnd":
+            continue
+        if k in ("NumTouchingFloor", "NumNonFeetTouchingFloor", "VoxelNumber", "FoundNeedleInHaystack"):
+            assert ours[k] == v, k
+        else:   # distances are in voxel lengths: P3 tolerance 1e-2, relative 1e-3 for the O(1) ones
+            assert ours[k] == pytest.approx(v, rel=1e-3, abs=1e-2), k
+
+
+@pytest.mark.parametrize("name", FULL_XML)
+def test_cli_drop_in_writes_reference_result_file(name, tmp_path):
+    """`voxelyze -f file.vxa`: exit code 1, result XML at <FitnessFileName> with the reference's tags/values."""
+    g = golden_lib.Golden(name)
+    out = tmp_path / "fit.xml"
+    vxa_path = tmp_path / (name + ".vxa")
+    vxa_path.write_text(g.vxa_text.replace(g.fitness_file, str(out)))
+    cmd = [CLI, "-f", str(vxa_path)] + (["--lw"] if g.lw else [])
+    rc = subprocess.run(cmd).returncode
+    assert rc == 1
+    _check_result(out.read_text(), g)
+
+
+def test_cli_batch_mode_many_files(tmp_path):
+    """The batched form: several -f files in one process = one GPU batch; every robot gets its own result file,
+    identical to running it alone."""
+    names = ["dense3_full", "dense3_afterlife_full"]
+    outs, args = [], []
+    for n in names * 2:
+        g = golden_lib.Golden(n)
+        out = tmp_path / f"fit_{len(outs)}.xml"
+        p = tmp_path / f"r_{len(outs)}.vxa"
+        p.write_text(g.vxa_text.replace(g.fitness_file, str(out)))
+        outs.append((out, g)); args += ["-f", str(p)]
+    assert subprocess.run([CLI] + args).returncode == 1
+    for out, g in outs:
+        _check_result(out.read_text(), g)
+    assert outs[0][0].read_text() == outs[2][0].read_text()     # same robot in two slots: identical file
+
+
+def test_cli_rejects_unsupported_instead_of_falling_back(tmp_path):
+    p = tmp_path / "eq.vxa"
+    p.write_text(vxa.vxa_text(vxa.dense_lattice(2, 1), sim=vxa.SimParams(equilibrium_mode=1, fitness_file=str(tmp_path / "f.xml"))))
+    r = subprocess.run([CLI, "-f", str(p)], capture_output=True, text=True)
+    assert r.returncode == 0 and "not supported" in r.stderr
+    assert not (tmp_path / "f.xml").exists()

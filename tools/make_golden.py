@@ -25,6 +25,9 @@ TMP = "/tmp/vx_golden"
 
 def case(name, structure, n_steps, every, sim=None, env=None, palette=None, phase=None, lw=False, full=False):
     os.makedirs(TMP, exist_ok=True)
+    if full:   # the stock CLI writes its result file where <FitnessFileName> says
+        sim = sim or vxa.SimParams()
+        sim.fitness_file = os.path.join(TMP, name + "_result.xml")
     text = vxa.vxa_text(structure, palette=palette, sim=sim, env=env, phase_offset=phase)
     path = os.path.join(TMP, name + ".vxa")
     with open(path, "w") as f:
@@ -35,6 +38,14 @@ def case(name, structure, n_steps, every, sim=None, env=None, palette=None, phas
     if full:
         f = refdump.run_ref_full(path, path + ".full.bin", nocol=True, lw=lw)
         out.update(full_hdr=f.frame_hdr, full_vstate=f.vstate[-1], full_tail=f.tail)
+        # the unmodified reference CLI (voxelyzeMain/main.cpp) on the same file: its result XML is the P5 pin
+        import subprocess
+        exe = os.path.join(ROOT, "oracle", "_ref", "voxelyze_ref_lw" if lw else "voxelyze_ref")
+        if os.path.exists(sim.fitness_file):
+            os.remove(sim.fitness_file)
+        rc = subprocess.run([exe, "-f", path]).returncode
+        assert rc == 1, rc
+        out.update(result_xml=np.frombuffer(open(sim.fitness_file, "rb").read(), dtype=np.uint8), fitness_file=np.frombuffer(sim.fitness_file.encode(), dtype=np.uint8))
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
     print(name, "voxels", d.n_vox, "bonds", d.n_bond, "frames", d.vstate.shape[0], os.path.getsize(os.path.join(OUT, name + ".npz")) // 1024, "KiB")
 
@@ -54,6 +65,11 @@ def main():
     case("dense3_phase", vxa.dense_lattice(3, 9), 1000, 100, sim=S(init_cm_time=0.01, stop_condition_value=0.2), phase=rng.uniform(-0.5, 0.5, (3, 3, 3)))
     # whole CLI run to StopConditionMet: step count, IniCM latch, fitness block
     case("dense3_full", vxa.dense_lattice(3, 11, materials=(1, 3, 4)), 200, 100, sim=S(init_cm_time=0.05, stop_condition_value=0.25), full=True)
+    # afterlife: EndOfLifetimePosteriorY is latched at StopConditionValue, the run ends AfterlifeTime later
+    case("dense3_afterlife_full", vxa.dense_lattice(3, 12, materials=(1, 3, 4)), 0, 1,
+         sim=S(init_cm_time=0.05, stop_condition_value=0.2, afterlife_time=0.05), full=True)
+    # land/water fork, whole run, its own result tags
+    case("lw_dense3_full", vxa.dense_lattice(3, 13, materials=(1, 3, 4)), 0, 1, sim=S(init_cm_time=0.05, stop_condition_value=0.25), lw=True, full=True)
     # BASELINE config 1/2 shape: dense 6^3, whole 5 s CLI run (78 054 steps): final COM / fitness only
     case("dense6_s1_full", vxa.dense_lattice(6, 1), 0, 1, full=True)
     # single voxel / no bonds (edge case: empty bond list)
