@@ -83,7 +83,7 @@ class RobotState(C.Structure):
 class Limits(C.Structure):
     _fields_ = [
         ("max_vox", C.c_int32), ("max_vclass", C.c_int32), ("max_bclass", C.c_int32), ("precision", C.c_int32),
-        ("max_col_pairs", C.c_int32), ("reserved", C.c_int32 * 3),
+        ("max_col_pairs", C.c_int32), ("max_mesh_verts", C.c_int32), ("reserved", C.c_int32 * 2),
     ]
 
 

@@ -61,6 +61,7 @@ int main(int argc, char** argv) {
         lim.max_vox = std::max(lim.max_vox, descs[r].n_vox);
         lim.max_vclass = std::max(lim.max_vclass, descs[r].n_vclass);
         lim.max_bclass = std::max(lim.max_bclass, descs[r].n_bclass);
+        if (descs[r].sim.flags & VXG_F_FLUID) lim.max_mesh_verts = std::max(lim.max_mesh_verts, vxg_mesh_vertex_count(&descs[r]));
         max_total = std::max(max_total, total[r]);
         if (print_scrn) printf("Imported %s: %d voxels, %d bonds, %lld steps\n", files[r].c_str(), descs[r].n_vox, descs[r].n_bond, (long long)total[r]);
     }

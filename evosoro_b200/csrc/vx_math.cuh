@@ -229,9 +229,9 @@ template <typename T> struct alignas(16) BondK {   // from vxg_bond_class
     T c_a1m1, c_a1m2, c_a2i1, c_a2i2;
     T c_b1m1, c_b1m2, c_b2fm1, c_b2fm2;
     T c_b3i1, c_b3i2;
+    T sf1, sf2;                        // per-voxel share of the axial strain (UpdateBondStrain: CurStrainV1/V2 = sf * strain)
     int homogeneous;
-    int pad_[sizeof(T) == 4 ? 1 : 2];
-};
+};   // alignas(16) rounds the size up to whole 128-bit words
 
 // Compact form of a bond class for lattices of equal cubic voxels, where every beam constant of
 // CVX_Bond::UpdateConstants (VX_Bond.cpp:125-170, A = L^2, Iy = Iz = L^4/12, J = L^4/6, inertia = m L^2/6,
@@ -258,6 +258,7 @@ template <typename T> VX_HD BondK<T> expand_bond(const BondKc<T>& c, const BondG
     k.c_b2fm1 = c.s1 * g.Lh; k.c_b2fm2 = c.s2 * g.Lh;
     k.c_b3i1 = c.s1 * g.L2s; k.c_b3i2 = c.s2 * g.L2s;
     k.c_a2i1 = k.c_b3i1 * c.sq_tnu; k.c_a2i2 = k.c_b3i2 * c.sq_tnu;
+    k.sf1 = (T)1; k.sf2 = (T)1;   // the compact form is not used by the fluid kernels (they need the real factors)
     k.homogeneous = 0;
     return k;
 }
@@ -272,12 +273,13 @@ template <typename T> struct alignas(16) VoxK {    // from vxg_vox_class (+ sim 
     T ext_f[3], ext_t[3];
     int dof;
     int has_bc;        // any fixed DOF or external load
-    int pad_[sizeof(T) == 4 ? 2 : 2];
+    T half_nom;        // NominalSize / 2 (corner extents of the surface mesh, LW/VXS_Voxel.cpp:474-475)
 };
 
 template <typename T> struct BondOut {
     V3<T> f1, f2, m1, m2;   // world frame: force/moment on voxel 1 (negative side) and voxel 2
     T strain;
+    T strain1, strain2;     // CurStrainV1 / CurStrainV2: what SetStrainDir hands to the two voxels (VXS_BondInternal.cpp:300-304)
     bool changed;           // the small/large-angle mode flipped this step: the caller keeps the old history (:157)
 };
 
@@ -350,6 +352,7 @@ VX_HD void bond_force(const BondK<T>& k, V3<T> e_w, Q4<T> q1w, Q4<T> q2w, T dnom
     // heterogeneous fixed-point iteration (:226-258) converges in one pass to sigma = 2 E1 E2/(E1+E2) eps
     // (eps1 <- 2 s2/(s1+s2) eps gives s1 = s2 exactly), so the force is a constant times _Pos2.x.
     out.strain = p2.x * k.inv_len;
+    out.strain1 = out.strain * k.sf1; out.strain2 = out.strain * k.sf2;
     out.changed = changed;
     T fx = k.k_axial * p2.x;
 

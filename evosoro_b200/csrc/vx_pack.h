@@ -5,6 +5,9 @@
 #pragma once
 #include <cmath>
 #include <cstring>
+#include <map>
+#include <tuple>
+#include <vector>
 #include "../../include/vxgpu.h"
 #include "vx_robot.cuh"
 
@@ -55,6 +58,10 @@ inline void pack_classes(const vxg_robot_desc* d, BondK<Real>* bk, double* bk_di
                 e_eff = diff > sum * .0005 ? 2.0 * c.e1 * c.e2 / sum : 0.5 * sum;   // loop entered (one pass converges) / not entered
             }
             k.k_axial = (Real)(c.area * e_eff / c.len);
+            // strains the two voxels see (-> SetStrainDir, VXS_BondInternal.cpp:300-304): equal unless the iteration ran
+            double diff = c.e1 >= c.e2 ? c.e1 - c.e2 : c.e2 - c.e1, sum = c.e1 + c.e2;
+            bool iter = !c.homogeneous && diff > sum * .0005;
+            k.sf1 = (Real)(iter ? 2.0 * c.e2 / sum : 1.0); k.sf2 = (Real)(iter ? 2.0 * c.e1 / sum : 1.0);
         }
         k.nom_dist = (Real)c.nom_dist; k.len_minus_dist = (Real)(c.len - c.nom_dist);
         k.c_a1m1 = (Real)c.c_a1m1; k.c_a1m2 = (Real)c.c_a1m2; k.c_a2i1 = (Real)c.c_a2i1; k.c_a2i2 = (Real)c.c_a2i2;
@@ -80,6 +87,7 @@ inline void pack_classes(const vxg_robot_desc* d, BondK<Real>* bk, double* bk_di
             if (c.ext_force[a] != 0 || c.ext_torque[a] != 0) bc = true;
         }
         k.dof = c.dof_fixed; k.has_bc = bc ? 1 : 0;
+        k.half_nom = (Real)(0.5 * c.nom_size);
         ScaleK& s = sk[i];
         s.mat_index = c.mat_index;
         s.nom_size = c.nom_size; s.init_size = c.init_size; s.cte = c.cte; s.temp_amp_damp = c.temp_amp_damp; s.phase_offset = c.phase_offset;
@@ -106,6 +114,64 @@ inline void pack_blob(const vxg_robot_desc* d, const BlobLayout& L, unsigned cha
     }
 }
 
+// Integer lattice coordinates of every voxel, recovered from the nominal positions (cell centres at
+// (i + 0.5) * pitch, VX_Object.cpp:543); pitch per axis = the bond pitch along it, else the voxel size.
+inline void lattice_coords(const vxg_robot_desc* d, std::vector<int>& ijk) {
+    double pitch[3] = {0, 0, 0};
+    for (int j = 0; j < d->n_bond; j++) { int a = d->bond_axis[j]; double p = d->bclasses[d->bond_class[j]].nom_dist; if (p > 0 && (pitch[a] == 0 || p < pitch[a])) pitch[a] = p; }
+    for (int a = 0; a < 3; a++) if (!(pitch[a] > 0)) pitch[a] = d->vclasses[d->vox_class[0]].nom_size;
+    ijk.resize((size_t)3 * d->n_vox);
+    for (int i = 0; i < d->n_vox; i++) for (int a = 0; a < 3; a++) ijk[3 * i + a] = (int)llround(d->nom_pos[3 * i + a] / pitch[a] - 0.5);
+}
+
+// Number of surface-mesh vertices of a robot: lattice points touched by 1..7 voxels (LW/VX_MeshUtil.cpp:249-262).
+inline int mesh_vertex_count(const vxg_robot_desc* d) {
+    std::vector<int> ijk; lattice_coords(d, ijk);
+    std::map<std::tuple<int, int, int>, int> cnt;
+    for (int i = 0; i < d->n_vox; i++) for (int c = 0; c < 8; c++) cnt[std::make_tuple(ijk[3 * i] + ((c >> 2) & 1), ijk[3 * i + 1] + ((c >> 1) & 1), ijk[3 * i + 2] + (c & 1))]++;
+    int n = 0;
+    for (auto& kv : cnt) if (kv.second != 8) n++;
+    return n;
+}
+
+// Surface-mesh tables of CVX_MeshUtil::LinkSimVoxels (LW/VX_MeshUtil.cpp:110-276): exposed-face mask per voxel,
+// voxel -> corner vertices, vertex -> voxels.  Vertices are numbered in lattice order (x fastest), interior ones
+// (8 voxels) skipped, exactly like the reference's Map[].  Returns the vertex count, or -1 if it exceeds the capacity.
+template <typename Real>
+inline int pack_mesh(const vxg_robot_desc* d, const BlobLayout& L, unsigned char* blob) {
+    RobotView<Real> R = make_view<Real>(blob, L, d->n_vox);
+    std::vector<int> ijk; lattice_coords(d, ijk);
+    std::map<std::tuple<int, int, int>, int> occ;
+    for (int i = 0; i < d->n_vox; i++) occ[std::make_tuple(ijk[3 * i + 2], ijk[3 * i + 1], ijk[3 * i])] = i;   // (z, y, x): lattice order
+    static const int dir[6][3] = {{1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
+    std::map<std::tuple<int, int, int>, Corner8> verts;   // keyed (z, y, x) so that iteration is the reference's vertex order
+    for (int i = 0; i < d->n_vox; i++) {
+        unsigned faces = 0;
+        for (int f = 0; f < 6; f++)
+            if (!occ.count(std::make_tuple(ijk[3 * i + 2] + dir[f][2], ijk[3 * i + 1] + dir[f][1], ijk[3 * i] + dir[f][0]))) faces |= 1u << f;
+        R.stat[i].faces = (uint16_t)faces;
+        for (int c = 0; c < 8; c++) {
+            auto key = std::make_tuple(ijk[3 * i + 2] + (c & 1), ijk[3 * i + 1] + ((c >> 1) & 1), ijk[3 * i] + ((c >> 2) & 1));
+            auto it = verts.find(key);
+            if (it == verts.end()) { Corner8 e; for (int k = 0; k < 8; k++) e.i[k] = -1; it = verts.emplace(key, e).first; }
+            it->second.i[c] = (int16_t)i;
+        }
+    }
+    int n_vert = 0;
+    std::map<std::tuple<int, int, int>, int> id;
+    for (auto& kv : verts) {
+        int cnt = 0; for (int k = 0; k < 8; k++) cnt += kv.second.i[k] >= 0;
+        if (cnt == 8) { id[kv.first] = -1; continue; }
+        if (n_vert >= L.nvert_cap) return -1;
+        R.vcon[n_vert] = kv.second;
+        id[kv.first] = n_vert++;
+    }
+    for (int i = 0; i < d->n_vox; i++)
+        for (int c = 0; c < 8; c++)
+            R.cvert[i].i[c] = (int16_t)id[std::make_tuple(ijk[3 * i + 2] + (c & 1), ijk[3 * i + 1] + ((c >> 1) & 1), ijk[3 * i] + ((c >> 2) & 1))];
+    return n_vert;
+}
+
 inline void init_ctl(const vxg_robot_desc* d, RobotCtl& c) {
     const vxg_sim_params& P = d->sim;
     memset(&c, 0, sizeof c);
@@ -114,6 +180,7 @@ inline void init_ctl(const vxg_robot_desc* d, RobotCtl& c) {
     c.step = 0; c.total_steps = 0x7fffffffffffffffLL; c.latch_step = -1; c.eol_step = -1; c.eol_post_y = 0; c.status = 0; c.flags = P.flags;
     c.n_vox = d->n_vox; c.n_vclass = d->n_vclass; c.n_bclass = d->n_bclass; c.ini_latched = 0;
     c.half_bond_z = 0.5 * P.bond_damp_z;
+    c.drag_coeff = P.drag_coeff; c.n_vert = 0;
     c.sym_mass = 1;
     for (int i = 0; i < d->n_bclass; i++) {
         const vxg_bond_class& b = d->bclasses[i];

@@ -35,8 +35,11 @@ struct alignas(16) VoxStat {
     int16_t nbr[3];    // index of the +X/+Y/+Z neighbour, -1 = no bond
     uint16_t vcls;     // voxel class
     uint16_t bcls[3];  // class of the owned +axis bond
-    uint16_t pad;
+    uint16_t faces;    // bit d set: no voxel at the lattice neighbour in direction d (+X,-X,+Y,-Y,+Z,-Z): an exposed face
 };
+// surface-mesh tables of the land/water fork (LW/VX_MeshUtil.cpp:110-276)
+struct alignas(16) Corner8 { int16_t i[8]; };   // per voxel: mesh vertex at each corner (code = 4*X+ + 2*Y+ + Z+), -1 interior;
+                                                // per vertex: the voxel that has this vertex as its corner `code`, -1 none
 
 struct BlobLayout {            // byte offsets inside one robot blob; all multiples of 32
     int nv;                    // voxel stride
@@ -49,14 +52,19 @@ struct BlobLayout {            // byte offsets inside one robot blob; all multip
     size_t off_hist;           // per axis: R4 A[nv] (p2.xyz, a1.x), R4 B[nv] (a1.y, a1.z, a2.x, a2.y), Real C[nv] (a2.z)
     size_t hist_axis_bytes;
     size_t off_flags;          // uint32 [nv]
+    size_t off_strain;         // fluid only: Real [6][nv]  StrainPosDirsCur.xyz, StrainNegDirsCur.xyz of the last bond pass
     size_t dyn_bytes;
     // static: copied in
     size_t off_stat;           // VoxStat [nv]
+    size_t off_cvert;          // fluid only: Corner8 [nv]          voxel -> its 8 mesh vertices
+    size_t off_vcon;           // fluid only: Corner8 [nvert_cap]   mesh vertex -> its <= 8 voxels
     size_t stat_bytes;         // dynamic + static
     // scratch: zero-initialised on chip, never written back
     size_t off_accA;           // R4 [nv]  Force.xyz, Moment.x received from the -axis neighbours
     size_t off_accB;           // R2 [nv]  Moment.y, Moment.z
+    size_t off_vpos;           // fluid only: double [3][nvert_cap]  deformed mesh vertex positions of this step
     size_t total_bytes;
+    int nvert_cap;             // mesh vertex capacity (0 = no fluid-drag support in this batch)
 };
 
 VX_HD constexpr size_t vx_align16(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -69,10 +77,12 @@ inline int stride_for(int max_vox) {
     return nv;
 }
 
-VX_HD constexpr BlobLayout make_layout(int nv_in, int real_size) {
+VX_HD constexpr BlobLayout make_layout(int nv_in, int real_size, int nvert_cap = 0) {
     BlobLayout L{};
     L.nv = nv_in;
     L.real_size = real_size;
+    L.nvert_cap = nvert_cap;
+    const size_t nvc = (size_t)nvert_cap;
     size_t nv = (size_t)nv_in, rs = (size_t)real_size, o = 0;
     L.off_pos = o;   o = vx_align32(o + 3 * nv * sizeof(double));
     L.off_quat = o;  o = vx_align32(o + 4 * nv * rs);
@@ -81,11 +91,15 @@ VX_HD constexpr BlobLayout make_layout(int nv_in, int real_size) {
     L.hist_axis_bytes = vx_align32(9 * nv * rs);
     L.off_hist = o;  o = o + 3 * L.hist_axis_bytes;
     L.off_flags = o; o = vx_align32(o + nv * sizeof(uint32_t));
+    L.off_strain = o; if (nvc) o = vx_align32(o + 6 * nv * rs);
     L.dyn_bytes = o;
     L.off_stat = o;  o = vx_align32(o + nv * sizeof(VoxStat));
+    L.off_cvert = o; if (nvc) o = vx_align32(o + nv * sizeof(Corner8));
+    L.off_vcon = o;  if (nvc) o = vx_align32(o + nvc * sizeof(Corner8));
     L.stat_bytes = o;
     L.off_accA = o;  o = vx_align32(o + 4 * nv * rs);
     L.off_accB = o;  o = vx_align32(o + 2 * nv * rs);
+    L.off_vpos = o;  if (nvc) o = vx_align32(o + 3 * nvc * sizeof(double));
     L.total_bytes = o;
     return L;
 }
@@ -102,6 +116,11 @@ template <typename Real> struct RobotView {
     VoxStat* stat;        // [nv]
     R4<Real>* accA;       // [nv]
     R2<Real>* accB;       // [nv]
+    Real* strain;         // [6][nv]          (fluid layouts only)
+    Corner8* cvert;       // [nv]
+    Corner8* vcon;        // [nvert_cap]
+    double* vpos;         // [3][nvert_cap]
+    int nvert_cap;
     VX_HD R4<Real>* histA(int ax) const { return (R4<Real>*)(hist + (size_t)ax * hist_axis_bytes); }
     VX_HD R4<Real>* histB(int ax) const { return (R4<Real>*)(hist + (size_t)ax * hist_axis_bytes) + nv; }
     VX_HD Real* histC(int ax) const { return (Real*)((R4<Real>*)(hist + (size_t)ax * hist_axis_bytes) + 2 * (size_t)nv); }
@@ -121,6 +140,11 @@ VX_HD RobotView<Real> make_view(unsigned char* base, const BlobLayout& L, int n_
     v.stat = (VoxStat*)(base + L.off_stat);
     v.accA = (R4<Real>*)(base + L.off_accA);
     v.accB = (R2<Real>*)(base + L.off_accB);
+    v.strain = (Real*)(base + L.off_strain);
+    v.cvert = (Corner8*)(base + L.off_cvert);
+    v.vcon = (Corner8*)(base + L.off_vcon);
+    v.vpos = (double*)(base + L.off_vpos);
+    v.nvert_cap = L.nvert_cap;
     return v;
 }
 
@@ -140,6 +164,9 @@ template <typename Real> struct RobotConsts {
     Real dt;
     bool floor_on, sticky;
     bool sym_mass;              // every bond class has equal end-voxel masses: Force2 = -Force1
+    bool fluid;                 // land/water fluid environment: surface drag, no gravity / floor (LW/VX_Sim.cpp:1516-1597)
+    Real drag_coeff;            // AggregateDragCoefficient
+    int n_vert;                 // mesh vertices of this robot
 };
 
 // The owner's own position and orientation, loaded once per step and reused by its three bonds.
@@ -157,7 +184,7 @@ template <typename Real> struct BondPush { int w; V3<Real> f2, m2; };   // w < 0
 // registers across the three axes by the caller).  rec != nullptr: also store the bond outputs
 // ([39][nv] planes, vxg_download_state).  Touches no accumulator, so it needs no ordering against the
 // other voxels' pushes.  Returns true when the bond diverged (strain > 100, VX_Sim.cpp:1775).
-template <typename Real, int AX, bool COMPACT = false>
+template <typename Real, int AX, bool COMPACT = false, bool FLUID = false>
 VX_HD bool bond_eval(const RobotView<Real>& R, const RobotConsts<Real>& C, int v, const VoxStat& st, const OwnState<Real>& own,
                      uint32_t& fl, Real dt_inv, V3<Real>& F, V3<Real>& M, Real* rec, BondPush<Real>& p) {
     const int nv = R.nv;
@@ -197,6 +224,10 @@ VX_HD bool bond_eval(const RobotView<Real>& R, const RobotConsts<Real>& C, int v
     fl = (fl & ~(1u << AX)) | ((small ? 1u : 0u) << AX);
     F = F + o.f1; M = M + o.m1;
     p.f2 = o.f2; p.m2 = o.m2;
+    if (FLUID) {   // SetStrainDir(BD_P<axis>, CurStrainV1) on voxel 1, (BD_N<axis>, CurStrainV2) on voxel 2: one writer per slot
+        R.strain[AX * nv + v] = o.strain1;
+        R.strain[(3 + AX) * nv + w] = o.strain2;
+    }
     if (rec) {
         Real* r = rec + (size_t)(AX * 13) * nv + v;
         r[0] = o.f1.x; r[nv] = o.f1.y; r[2 * nv] = o.f1.z; r[3 * nv] = o.f2.x; r[4 * nv] = o.f2.y; r[5 * nv] = o.f2.z;
@@ -217,12 +248,80 @@ VX_HD void bond_push(const RobotView<Real>& R, const BondPush<Real>& p) {
     R.accA[p.w] = a; R.accB[p.w] = b;
 }
 
-template <typename Real, int AX, bool COMPACT = false>
+template <typename Real, int AX, bool COMPACT = false, bool FLUID = false>
 VX_HD bool bond_task(const RobotView<Real>& R, const RobotConsts<Real>& C, int v, const VoxStat& st, uint32_t& fl,
                      Real dt_inv, V3<Real>& F, V3<Real>& M, Real* rec) {
     BondPush<Real> p;
-    bool d = bond_eval<Real, AX, COMPACT>(R, C, v, st, load_own<Real>(R, v), fl, dt_inv, F, M, rec, p);
+    bool d = bond_eval<Real, AX, COMPACT, FLUID>(R, C, v, st, load_own<Real>(R, v), fl, dt_inv, F, M, rec, p);
     bond_push<Real>(R, p);
+    return d;
+}
+
+// ---- land/water fluid drag (LW/VX_Sim.cpp:1516-1597) ------------------------------------------------
+// Deformed position of mesh vertex u: mean over the voxels that share it of Pos + Angle * corner offset,
+// corner extents (1 + strain of the bond in that direction) * NominalSize / 2 from the PREVIOUS bond pass
+// (CVX_MeshUtil::GetCurVLoc LW/VX_MeshUtil.cpp:388-428, LW/VXS_Voxel.cpp:474-475).
+template <typename Real>
+VX_HD void mesh_vertex(const RobotView<Real>& R, const RobotConsts<Real>& C, int u) {
+    const int nv = R.nv;
+    const Corner8 con = R.vcon[u];
+    double sx = 0, sy = 0, sz = 0; int cnt = 0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        const int vv = con.i[c];
+        if (vv < 0) continue;
+        const Real h = C.vk[R.stat[vv].vcls].half_nom;
+        const Real ox = (c & 4) ? ((Real)1 + R.strain[vv]) * h : -((Real)1 + R.strain[3 * nv + vv]) * h;
+        const Real oy = (c & 2) ? ((Real)1 + R.strain[nv + vv]) * h : -((Real)1 + R.strain[4 * nv + vv]) * h;
+        const Real oz = (c & 1) ? ((Real)1 + R.strain[2 * nv + vv]) * h : -((Real)1 + R.strain[5 * nv + vv]) * h;
+        const R4<Real> q = R.quat[vv];
+        const V3<Real> r = rotate<Real>(q.x, mk3<Real>(q.y, q.z, q.w), mk3<Real>(ox, oy, oz));
+        sx += R.pos[vv] + (double)r.x; sy += R.pos[nv + vv] + (double)r.y; sz += R.pos[2 * nv + vv] + (double)r.z;
+        cnt++;
+    }
+    const double inv = 1.0 / (double)cnt;
+    R.vpos[u] = sx * inv; R.vpos[R.nvert_cap + u] = sy * inv; R.vpos[2 * R.nvert_cap + u] = sz * inv;
+}
+
+// drag of one triangular facet (A, B, C) on its voxel moving with `vel`: -C_d * area * (v.n)^2 n when the facet
+// faces the flow (acos(v^.n^) < pi/2, LW/VX_Sim.cpp:1559-1577), n = (B-A)x(C-A) normalised (CMesh::CalcFaceNormals)
+template <typename Real>
+VX_HD V3<Real> facet_drag(const RobotView<Real>& R, int a, int b, int c, V3<Real> vel, Real cd) {
+    const int nc = R.nvert_cap;
+    const double ax = R.vpos[a], ay = R.vpos[nc + a], az = R.vpos[2 * nc + a];
+    const V3<Real> ab = mk3<Real>((Real)(R.vpos[b] - ax), (Real)(R.vpos[nc + b] - ay), (Real)(R.vpos[2 * nc + b] - az));
+    const V3<Real> ac = mk3<Real>((Real)(R.vpos[c] - ax), (Real)(R.vpos[nc + c] - ay), (Real)(R.vpos[2 * nc + c] - az));
+    const V3<Real> cr = cross(ab, ac);
+    const Real l2 = dot(cr, cr);
+    if (!(l2 > (Real)0)) return mk3<Real>(0, 0, 0);
+    const Real il = vx_rsqrt(l2);
+    const V3<Real> n = cr * il;
+    const Real vn = dot(vel, n);
+    if (!(vn > (Real)0)) return mk3<Real>(0, 0, 0);
+    const Real area = (Real)0.5 * l2 * il;
+    return n * (-cd * area * vn * vn);
+}
+
+// DragForce of voxel v: sum over the two facets of each exposed face (facet vertex order as in LinkSimVoxels,
+// LW/VX_MeshUtil.cpp:161-190; FacetToSIndex = the voxel the face belongs to)
+template <typename Real>
+VX_HD V3<Real> voxel_drag(const RobotView<Real>& R, const RobotConsts<Real>& C, int v, const VoxStat& st) {
+    V3<Real> d = mk3<Real>(0, 0, 0);
+    const unsigned faces = st.faces & 63u;
+    if (!faces) return d;
+    const Corner8 cv = R.cvert[v];
+    const R4<Real> lm = R.momA[v];
+    const Real mi = C.vk[st.vcls].mass_inv;
+    const V3<Real> vel = mk3<Real>(lm.x * mi, lm.y * mi, lm.z * mi);
+    // corner codes of (tri1, tri2) per direction +X,-X,+Y,-Y,+Z,-Z
+    const int T1[6][3] = {{4, 6, 7}, {0, 3, 2}, {2, 3, 7}, {0, 5, 1}, {1, 5, 7}, {0, 6, 4}};
+    const int T2[6][3] = {{4, 7, 5}, {0, 1, 3}, {2, 7, 6}, {0, 4, 5}, {1, 7, 3}, {0, 2, 6}};
+#pragma unroll
+    for (int f = 0; f < 6; f++) {
+        if (!((faces >> f) & 1u)) continue;
+        d = d + facet_drag<Real>(R, cv.i[T1[f][0]], cv.i[T1[f][1]], cv.i[T1[f][2]], vel, C.drag_coeff);
+        d = d + facet_drag<Real>(R, cv.i[T2[f][0]], cv.i[T2[f][1]], cv.i[T2[f][2]], vel, C.drag_coeff);
+    }
     return d;
 }
 
@@ -279,6 +378,8 @@ struct RobotCtl {
     int sym_mass;           // every bond class has identical voxel-1 / voxel-2 damping constants
     double half_bond_z;     // 0.5 BondDampingZ
     double bond_len;        // the common bond length L of the compact form
+    double drag_coeff;      // AggregateDragCoefficient (fluid)
+    int n_vert, pad2;       // mesh vertices (fluid)
     long long eol_step;     // CurStepCount at which EndOfLifetimePosteriorY is latched (-1 never)
     double eol_post_y;      // min Pos.y over material != 5 at that step (metres); 0 = not latched
 };

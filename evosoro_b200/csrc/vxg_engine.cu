@@ -98,9 +98,9 @@ template <typename Real> static BatchDev<Real> dev_view(const vxg_batch* b) {
     return B;
 }
 
-template <typename Real, int NV, int VPT, bool SMEM, bool COMPACT>
+template <typename Real, int NV, int VPT, bool SMEM, bool COMPACT, bool FLUID = false>
 static cudaError_t launch_step(vxg_batch* b, int n_steps, int record) {
-    auto kern = vx_step_kernel<Real, NV, VPT, SMEM, COMPACT>;
+    auto kern = vx_step_kernel<Real, NV, VPT, SMEM, COMPACT, FLUID>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes);
     if (e != cudaSuccess) return e;
     kern<<<b->n_robots, NV / VPT, b->smem_bytes, b->stream>>>(dev_view<Real>(b), n_steps, record);
@@ -119,8 +119,22 @@ template <typename Real, bool SMEM, bool COMPACT> static cudaError_t launch_step
     return cudaErrorInvalidValue;
 }
 
+// land/water layouts (surface-mesh arrays): fp32, shared-memory resident, wide bond table
+static cudaError_t launch_step_fluid(vxg_batch* b, int n_steps, int record) {
+    switch (b->L.nv) {
+        case 64: return launch_step<float, 64, 1, true, false, true>(b, n_steps, record);
+        case 128: return launch_step<float, 128, 1, true, false, true>(b, n_steps, record);
+        case 256: return launch_step<float, 256, 1, true, false, true>(b, n_steps, record);
+        case 512: return launch_step<float, 512, 1, true, false, true>(b, n_steps, record);
+        case 1024: return launch_step<float, 1024, 2, true, false, true>(b, n_steps, record);
+        case 2048: return launch_step<float, 2048, 4, true, false, true>(b, n_steps, record);
+    }
+    return cudaErrorInvalidValue;
+}
+
 // The compact bond table exists for the production path only (fp32, shared-memory resident).
 static cudaError_t launch_step_p(vxg_batch* b, int n_steps, int record) {
+    if (b->L.nvert_cap > 0) return launch_step_fluid(b, n_steps, record);
     if (b->prec == VXG_PREC_F64)
         return b->smem_mode ? launch_step_s<double, true, false>(b, n_steps, record) : launch_step_s<double, false, false>(b, n_steps, record);
     if (!b->smem_mode) return launch_step_s<float, false, false>(b, n_steps, record);
@@ -155,7 +169,9 @@ extern "C" int vxg_create(vxg_batch** out, int device, int n_robots, const vxg_l
     vxg_batch* b = new vxg_batch;
     b->device = device; b->n_robots = n_robots; b->lim = *lim; b->prec = lim->precision;
     if (lim->max_vox > 2048) { delete b; return fail(VXG_UNSUPPORTED_SIZE, "vxg_create: more than 2048 voxels per robot is not supported yet"); }
-    b->L = make_layout(stride_for(lim->max_vox), (int)b->rs());
+    if (lim->max_mesh_verts < 0 || lim->max_mesh_verts > 32767) { delete b; return fail(VXG_ERR_ARG, "vxg_create: max_mesh_verts out of range"); }
+    if (lim->max_mesh_verts > 0 && lim->precision != VXG_PREC_F32) { delete b; return fail(VXG_UNSUPPORTED_FEATURE, "vxg_create: the fluid-drag kernels exist in fp32 only"); }
+    b->L = make_layout(stride_for(lim->max_vox), (int)b->rs(), (lim->max_mesh_verts + 31) & ~31);
     // thread mapping: <= 512 threads per CTA, VPT voxels per thread
     b->vpt = b->L.nv <= 512 ? 1 : b->L.nv / 512;
     b->threads = b->L.nv / b->vpt;
@@ -167,6 +183,10 @@ extern "C" int vxg_create(vxg_batch** out, int device, int n_robots, const vxg_l
     b->tb_compact = tables_bytes<float>(lim->max_vclass, lim->max_bclass, true);
     b->smem_wide_fits = b->L.total_bytes + tb <= (size_t)max_smem;
     b->smem_mode_wide_or_compact = b->prec == VXG_PREC_F32 && b->L.total_bytes + b->tb_compact <= (size_t)max_smem;
+    if (b->L.nvert_cap > 0) {   // fluid layouts run shared-memory resident with the wide table only
+        b->smem_mode_wide_or_compact = false;
+        if (!b->smem_wide_fits) { delete b; return fail(VXG_UNSUPPORTED_SIZE, "vxg_create: robot blob with surface mesh (%zu B) exceeds shared memory", b->L.total_bytes + tb); }
+    }
     b->smem_mode = b->smem_wide_fits || b->smem_mode_wide_or_compact;   // final choice is made at flush, when the classes are known
     b->smem_bytes = b->smem_mode ? b->L.total_bytes + tb : tb;
 
@@ -235,7 +255,8 @@ extern "C" int vxg_upload(vxg_batch* b, int robot, const vxg_robot_desc* d) {
     if (!d->nom_pos || !d->vox_class || !d->vclasses) return fail(VXG_ERR_ARG, "vxg_upload: voxel arrays missing");
     const vxg_sim_params& P = d->sim;
     if (P.flags & VXG_F_COLLISIONS) return fail(VXG_UNSUPPORTED_FEATURE, "self-collision contact bonds are not implemented on the device yet");
-    if (P.flags & VXG_F_FLUID) return fail(VXG_UNSUPPORTED_FEATURE, "land/water fluid drag is not implemented on the device yet");
+    if ((P.flags & VXG_F_FLUID) && b->L.nvert_cap <= 0)
+        return fail(VXG_UNSUPPORTED_SIZE, "vxg_upload: a fluid-environment robot needs a batch created with limits.max_mesh_verts > 0");
     if (!(P.dt > 0) || !std::isfinite(P.dt)) return fail(VXG_ERR_ARG, "vxg_upload: dt must be positive");
     for (int i = 0; i < d->n_vox; i++)
         if (d->vox_class[i] < 0 || d->vox_class[i] >= d->n_vclass) return fail(VXG_ERR_ARG, "vxg_upload: voxel %d has class %d", i, d->vox_class[i]);
@@ -256,6 +277,11 @@ extern "C" int vxg_upload(vxg_batch* b, int robot, const vxg_robot_desc* d) {
     if (b->prec == VXG_PREC_F64) { fill_classes<double>(b, robot, d); reset_blob<double>(b, robot, d); }
     else { fill_classes<float>(b, robot, d); reset_blob<float>(b, robot, d); }
     init_ctl(d, b->h_ctl[robot]);
+    if (b->L.nvert_cap > 0) {   // surface-mesh tables (also for non-fluid robots of a fluid batch: cheap, keeps one code path)
+        int nvx = pack_mesh<float>(d, b->L, b->h_blobs + (size_t)robot * b->L.total_bytes);
+        if (nvx < 0) return fail(VXG_UNSUPPORTED_SIZE, "vxg_upload: robot %d has more than max_mesh_verts = %d surface-mesh vertices", robot, b->lim.max_mesh_verts);
+        b->h_ctl[robot].n_vert = nvx;
+    }
     {
         double len = 1.0;
         bool ok = b->prec == VXG_PREC_F64 ? fill_compact<double>(b, robot, d, &len) : fill_compact<float>(b, robot, d, &len);
@@ -523,6 +549,11 @@ extern "C" int vxg_reduce_stats(vxg_batch* b, vxg_robot_stats* out) {
 extern "C" int vxg_set_collision_pairs(vxg_batch* b, int robot, int n_pairs, const int32_t* v1, const int32_t* v2, const double* a1) {
     (void)b; (void)robot; (void)n_pairs; (void)v1; (void)v2; (void)a1;
     return fail(VXG_UNSUPPORTED_FEATURE, "self-collision contact bonds are not implemented on the device yet");
+}
+
+extern "C" int vxg_mesh_vertex_count(const vxg_robot_desc* d) {
+    if (!d || d->n_vox <= 0 || !d->nom_pos || !d->vox_class || !d->vclasses) return fail(VXG_ERR_ARG, "vxg_mesh_vertex_count: bad descriptor");
+    return mesh_vertex_count(d);
 }
 
 // bytes one full population upload moves host -> device (what flush() copies when everything is dirty)

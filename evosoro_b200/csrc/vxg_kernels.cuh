@@ -143,11 +143,13 @@ __device__ inline void block_sum4(double& a, double& b, double& c, double& d, do
     for (int i = 0; i < nw; i++) { a += red[i]; b += red[32 + i]; c += red[64 + i]; d += red[96 + i]; }
 }
 
-template <typename Real, int NV, int VPT, bool SMEM, bool COMPACT>
+//       FLUID        : blob layout with the land/water surface-mesh arrays; robots with VXG_F_FLUID get the drag phase.
+template <typename Real, int NV, int VPT, bool SMEM, bool COMPACT, bool FLUID = false>
 __global__ void __launch_bounds__(NV / VPT, 1) vx_step_kernel(BatchDev<Real> B, int n_steps, int record_bonds) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int T = NV / VPT;
-    constexpr BlobLayout L = make_layout(NV, (int)sizeof(Real));
+    constexpr BlobLayout LC = make_layout(NV, (int)sizeof(Real));
+    const BlobLayout L = FLUID ? B.L : LC;   // with the mesh arrays the capacity is a run-time size
     const int robot = blockIdx.x;
     const int tid = threadIdx.x;
     RobotCtl* ctlp = B.ctl + robot;
@@ -203,6 +205,7 @@ __global__ void __launch_bounds__(NV / VPT, 1) vx_step_kernel(BatchDev<Real> B, 
     const double dt = ctlp->dt;
     C.dt = (Real)dt;
     const bool fluid = (flags & VXG_F_FLUID_) != 0;
+    C.fluid = FLUID && fluid; C.drag_coeff = (Real)ctlp->drag_coeff; C.n_vert = ctlp->n_vert;
     C.floor_on = (flags & VXG_F_FLOOR_) && !fluid;
     C.sticky = (flags & VXG_F_STICKY_FLOOR_) != 0;
     C.sym_mass = ctlp->sym_mass != 0;
@@ -253,6 +256,12 @@ __global__ void __launch_bounds__(NV / VPT, 1) vx_step_kernel(BatchDev<Real> B, 
             fl[j] = R.flags[tid + j * T];
             own[j] = load_own<Real>(R, tid + j * T);
         }
+        if (FLUID && C.fluid) {   // DragForce of this step from the state and bond strains of the previous one
+            for (int u = tid; u < C.n_vert; u += T) mesh_vertex<Real>(R, C, u);
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < VPT; j++) if (tid + j * T < n_vox) F[j] = voxel_drag<Real>(R, C, tid + j * T, st[j]);
+        }
         // Scale of every class for the NEXT step, from CurTime before the increment (VXS_Voxel.cpp:224-336).
         // It depends on time only, so it is evaluated here, off the critical path, by the highest threads
         // of the CTA (the last warp owns the fewest voxels); it lands in the other half of the double buffer,
@@ -268,18 +277,18 @@ __global__ void __launch_bounds__(NV / VPT, 1) vx_step_kernel(BatchDev<Real> B, 
         // the split-phase barrier orders without stalling the evaluations.
         int div = 0;
 #pragma unroll
-        for (int j = 0; j < VPT; j++) { P[j].w = -1; if (tid + j * T < n_vox) div |= bond_eval<Real, 0, COMPACT>(R, C, tid + j * T, st[j], own[j], fl[j], dt_inv, F[j], M[j], rec, P[j]) ? 1 : 0; }
+        for (int j = 0; j < VPT; j++) { P[j].w = -1; if (tid + j * T < n_vox) div |= bond_eval<Real, 0, COMPACT, FLUID>(R, C, tid + j * T, st[j], own[j], fl[j], dt_inv, F[j], M[j], rec, P[j]) ? 1 : 0; }
 #pragma unroll
         for (int j = 0; j < VPT; j++) bond_push<Real>(R, P[j]);
         mbar_arrive_warp(S.mbar);
 #pragma unroll
-        for (int j = 0; j < VPT; j++) { P[j].w = -1; if (tid + j * T < n_vox) div |= bond_eval<Real, 1, COMPACT>(R, C, tid + j * T, st[j], own[j], fl[j], dt_inv, F[j], M[j], rec, P[j]) ? 1 : 0; }
+        for (int j = 0; j < VPT; j++) { P[j].w = -1; if (tid + j * T < n_vox) div |= bond_eval<Real, 1, COMPACT, FLUID>(R, C, tid + j * T, st[j], own[j], fl[j], dt_inv, F[j], M[j], rec, P[j]) ? 1 : 0; }
         mbar_wait(S.mbar, mpar); mpar ^= 1u;
 #pragma unroll
         for (int j = 0; j < VPT; j++) bond_push<Real>(R, P[j]);
         mbar_arrive_warp(S.mbar);
 #pragma unroll
-        for (int j = 0; j < VPT; j++) { P[j].w = -1; if (tid + j * T < n_vox) div |= bond_eval<Real, 2, COMPACT>(R, C, tid + j * T, st[j], own[j], fl[j], dt_inv, F[j], M[j], rec, P[j]) ? 1 : 0; }
+        for (int j = 0; j < VPT; j++) { P[j].w = -1; if (tid + j * T < n_vox) div |= bond_eval<Real, 2, COMPACT, FLUID>(R, C, tid + j * T, st[j], own[j], fl[j], dt_inv, F[j], M[j], rec, P[j]) ? 1 : 0; }
         mbar_wait(S.mbar, mpar); mpar ^= 1u;
 #pragma unroll
         for (int j = 0; j < VPT; j++) bond_push<Real>(R, P[j]);

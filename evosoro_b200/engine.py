@@ -67,6 +67,7 @@ def lib():
         L.vxg_struct_sizes.argtypes = [C.POINTER(C.c_int), C.c_int]
         L.vxg_set_collision_pairs.argtypes = [vp, C.c_int, C.c_int, abi.c_int32_p, abi.c_int32_p, abi.c_double_p]
         L.vxg_run_batch_host.argtypes = [vp, C.POINTER(abi.RobotDesc), C.c_int, C.c_int, abi.c_double_p]
+        L.vxg_mesh_vertex_count.argtypes = [C.POINTER(abi.RobotDesc)]
         L.vxg_upload_bytes.argtypes = [vp]
         L.vxg_upload_bytes.restype = C.c_int64
         L.vxg_mark.argtypes = [vp, C.c_int]
@@ -177,6 +178,9 @@ class Batch:
         lim.max_vclass = max_vclass or max(len(r.vclasses) for r in self.robots)
         lim.max_bclass = max_bclass or max(1, max(len(r.bclasses) for r in self.robots))
         lim.precision = precision
+        # land/water fluid drag needs the surface-mesh arrays: size them for the largest mesh of the batch
+        if any(r.sim.flags & abi.VXG_F_FLUID for r in self.robots):
+            lim.max_mesh_verts = max(lib().vxg_mesh_vertex_count(C.byref(r.desc())) for r in self.robots)
         self.limits = lim
         self.h = C.c_void_p()
         _ck(lib().vxg_create(C.byref(self.h), device, len(self.robots), C.byref(lim)))

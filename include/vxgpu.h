@@ -43,7 +43,7 @@ enum {
 #define VXG_F_TEMPERATURE  0x0002u /* VXSFEAT_TEMPERATURE  VXS_Voxel.cpp:292-305 (thermal actuation)   */
 #define VXG_F_LW_SCALE     0x0004u /* _voxcad_land_water scale law, LW/VXS_Voxel.cpp:211-235           */
 #define VXG_F_STICKY_FLOOR 0x0008u /* getUsingStickyFloor() VXS_Voxel.cpp:736-739                      */
-#define VXG_F_FLUID        0x0010u /* LW fluid environment: gravity and floor inert, LW/VXS_Voxel.cpp:357,467 */
+#define VXG_F_FLUID        0x0010u /* LW fluid environment: surface drag (LW/VX_Sim.cpp:1516-1597), gravity and floor inert (LW/VXS_Voxel.cpp:357,467) */
 #define VXG_F_COLLISIONS   0x0020u /* VXSFEAT_COLLISIONS: contact bonds given through vxg_set_collision_pairs */
 
 /* degrees of freedom, same bit values as the reference (VX_FRegion.h DOF_*) */
@@ -173,7 +173,9 @@ typedef struct vxg_limits {
     int32_t max_bclass;   /* >= n_bclass                                                             */
     int32_t precision;    /* VXG_PREC_F32 / VXG_PREC_F64                                             */
     int32_t max_col_pairs;/* capacity for contact bonds per robot (0 = self-collision unused)        */
-    int32_t reserved[3];
+    int32_t max_mesh_verts;/* capacity for surface-mesh vertices per robot: needed (>= vxg_mesh_vertex_count of every
+                              robot) to upload VXG_F_FLUID robots; 0 = no fluid-drag support in this batch      */
+    int32_t reserved[2];
 } vxg_limits;
 
 /* status bits written by vxg_sync */
@@ -276,6 +278,9 @@ int vxg_set_collision_pairs(vxg_batch* b, int robot, int n_pairs, const int32_t*
 /* Host-buffer convenience used by the end-to-end benchmark: upload all descriptors, run n_steps,
  * download positions of every robot into pos_out ([n_robots][max_vox][3] doubles). */
 int vxg_run_batch_host(vxg_batch* b, const vxg_robot_desc* descs, int n_descs, int n_steps, double* pos_out);
+/* Surface-mesh vertices of a robot (lattice points shared by 1..7 voxels, LW/VX_MeshUtil.cpp:249-262): what
+ * limits.max_mesh_verts must cover for the land/water fluid drag. */
+int vxg_mesh_vertex_count(const vxg_robot_desc* desc);
 /* Bytes one full population upload copies host -> device (for the benchmark's h2d accounting). */
 int64_t vxg_upload_bytes(vxg_batch* b);
 

@@ -20,7 +20,7 @@ struct EmulBase {
     virtual int diverged() = 0;
 };
 
-template <typename Real, bool COMPACT = false> struct Emul : EmulBase {
+template <typename Real, bool COMPACT = false, bool FLUID = false> struct Emul : EmulBase {
     BlobLayout L;
     std::vector<unsigned char> blob;
     std::vector<double> nom, bk_dist, scale_c[2];
@@ -37,7 +37,7 @@ template <typename Real, bool COMPACT = false> struct Emul : EmulBase {
     int div = 0;
 
     Emul(const vxg_robot_desc* d) {
-        L = make_layout(stride_for(d->n_vox), (int)sizeof(Real));
+        L = make_layout(stride_for(d->n_vox), (int)sizeof(Real), FLUID ? ((mesh_vertex_count(d) + 31) & ~31) : 0);
         blob.resize(L.total_bytes);
         nom.resize(3 * (size_t)L.nv);
         int nvc = d->n_vclass, nbc = d->n_bclass > 0 ? d->n_bclass : 1;
@@ -49,6 +49,7 @@ template <typename Real, bool COMPACT = false> struct Emul : EmulBase {
         bkc.resize(nbc);
         compact_ok = pack_compact<Real>(d, bkc.data(), &bond_len);
         init_ctl(d, ctl);
+        if (FLUID) ctl.n_vert = pack_mesh<Real>(d, L, blob.data());
         for (int i = 0; i < nvc; i++) dsc_c[0][i] = (Real)(scale_c[0][i] - sk[i].nom_size);
         rec.assign((size_t)39 * L.nv, (Real)0);
         bv1.assign(d->bond_v1, d->bond_v1 + d->n_bond);
@@ -65,6 +66,7 @@ template <typename Real, bool COMPACT = false> struct Emul : EmulBase {
         C.floor_on = (ctl.flags & VXG_F_FLOOR) && !fluid;
         C.sticky = (ctl.flags & VXG_F_STICKY_FLOOR) != 0;
         C.sym_mass = ctl.sym_mass != 0;
+        C.fluid = FLUID && fluid; C.drag_coeff = (Real)ctl.drag_coeff; C.n_vert = ctl.n_vert;
         const bool temp_on = (ctl.flags & VXG_F_TEMPERATURE) != 0, lw = (ctl.flags & VXG_F_LW_SCALE) != 0;
         const Real dt_inv_run = (Real)(1.0 / ctl.dt);
         std::vector<V3<Real>> F(ctl.n_vox), M(ctl.n_vox);
@@ -74,12 +76,16 @@ template <typename Real, bool COMPACT = false> struct Emul : EmulBase {
             C.scale_c = scale_c[cur].data(); C.dsc_c = dsc_c[cur].data();
             const Real dt_inv = ctl.step == 0 ? (Real)0 : dt_inv_run;
             for (int v = 0; v < ctl.n_vox; v++) { F[v] = mk3<Real>(0, 0, 0); M[v] = mk3<Real>(0, 0, 0); }
+            if (C.fluid) {
+                for (int u = 0; u < C.n_vert; u++) mesh_vertex<Real>(R, C, u);
+                for (int v = 0; v < ctl.n_vox; v++) F[v] = voxel_drag<Real>(R, C, v, R.stat[v]);
+            }
             bool d = false;
             std::vector<uint32_t> fl(ctl.n_vox);
             for (int v = 0; v < ctl.n_vox; v++) fl[v] = R.flags[v];
-            for (int v = 0; v < ctl.n_vox; v++) d |= bond_task<Real, 0, COMPACT>(R, C, v, R.stat[v], fl[v], dt_inv, F[v], M[v], rec.data());
-            for (int v = 0; v < ctl.n_vox; v++) d |= bond_task<Real, 1, COMPACT>(R, C, v, R.stat[v], fl[v], dt_inv, F[v], M[v], rec.data());
-            for (int v = 0; v < ctl.n_vox; v++) d |= bond_task<Real, 2, COMPACT>(R, C, v, R.stat[v], fl[v], dt_inv, F[v], M[v], rec.data());
+            for (int v = 0; v < ctl.n_vox; v++) d |= bond_task<Real, 0, COMPACT, FLUID>(R, C, v, R.stat[v], fl[v], dt_inv, F[v], M[v], rec.data());
+            for (int v = 0; v < ctl.n_vox; v++) d |= bond_task<Real, 1, COMPACT, FLUID>(R, C, v, R.stat[v], fl[v], dt_inv, F[v], M[v], rec.data());
+            for (int v = 0; v < ctl.n_vox; v++) d |= bond_task<Real, 2, COMPACT, FLUID>(R, C, v, R.stat[v], fl[v], dt_inv, F[v], M[v], rec.data());
             if (d) { div = 1; break; }
             for (int v = 0; v < ctl.n_vox; v++) voxel_task<Real>(R, C, v, R.stat[v], load_own<Real>(R, v), fl[v], F[v], M[v]);
             for (int i = 0; i < ctl.n_vclass; i++) {
@@ -127,6 +133,8 @@ template <typename Real, bool COMPACT = false> struct Emul : EmulBase {
 extern "C" {
 void* vxe_create(const vxg_robot_desc* d, int prec) {
     if (prec == VXG_PREC_F64) return new Emul<double>(d);
+    if (prec == 3) return new Emul<float, false, true>(d);    // fp32, land/water layout with the fluid-drag phase
+    if (prec == 4) return new Emul<double, false, true>(d);   // fp64, same (logic parity of the drag phase on the CPU)
     if (prec == 2) {   // fp32 with the compact bond table (what the production kernel uses when every class qualifies)
         Emul<float, true>* e = new Emul<float, true>(d);
         if (!e->compact_ok) { delete e; return nullptr; }

@@ -17,14 +17,17 @@ import golden_lib
 from evosoro_b200 import abi
 
 LAT = 0.01
-CASES = [n for n in golden_lib.names() if n != "dense3_full"]
+CASES = [n for n in golden_lib.names() if not n.endswith("_full")]
+FLUID = lambda n: n.startswith("lw_fluid")
 
 
 @pytest.mark.parametrize("name", CASES)
 def test_emulated_f64_kernel_arithmetic(name):
+    """For the lw_fluid_* fixtures this is the logic-parity pin of the fluid-drag phase (mesh vertices, facet
+    normals/areas, drag law): the kernels' own mesh_vertex / voxel_drag functions in fp64 vs the reference."""
     g = golden_lib.Golden(name)
     d = g.dump
-    e = emul_lib.EmulSim(g.robot(), abi.VXG_PREC_F64)
+    e = emul_lib.EmulSim(g.robot(), 4 if FLUID(name) else abi.VXG_PREC_F64)   # 4 = fp64 with the land/water drag phase
     for f in range(1, d.vstate.shape[0]):
         assert e.step(g.every) == g.every
         s = e.state()
@@ -36,6 +39,8 @@ def test_emulated_f64_kernel_arithmetic(name):
             assert np.array_equal(s.bond_small_angle, d.bstate[f, :, 13].astype(np.int32))
             fmax = max(1e-9, np.abs(d.bstate[f, :, 0:3]).max())
             ftol = 2e-3 if g.every * f <= 100 else 1e-6   # see the module docstring
+            if FLUID(name):
+                ftol = 2e-3   # neutrally buoyant, nothing settles the lattice: rotations stay in the noise regime longer
             assert np.abs(s.bond_force1 - d.bstate[f, :, 0:3]).max() <= ftol * fmax
             assert np.abs(s.bond_force2 - d.bstate[f, :, 3:6]).max() <= ftol * fmax
 
@@ -47,6 +52,10 @@ def test_emulated_f32_kernel_arithmetic(name, prec):
     must qualify for it, and it must meet the same tolerance as the wide table."""
     g = golden_lib.Golden(name)
     d = g.dump
+    if FLUID(name):
+        if prec == 2:
+            pytest.skip("the fluid kernels use the wide bond table")
+        prec = 3   # fp32 with the land/water drag phase
     e = emul_lib.EmulSim(g.robot(), prec)
     assert e.h, "bond classes did not qualify for the compact form"
     for f in range(1, d.vstate.shape[0]):

@@ -79,5 +79,19 @@ def main():
     case("lw_dense3_s6", vxa.dense_lattice(3, 6), 1000, 100, sim=S(init_cm_time=0.01, stop_condition_value=0.2), lw=True)
 
 
+def fluid_cases():
+    """land/water fork in a fluid environment (config 5 of BASELINE.json: surface drag, gravity and floor inert)"""
+    S, E = vxa.SimParams, vxa.EnvParams
+    env = lambda: E(fluid_environment=1, aggregate_drag_coefficient=750.0)
+    case("lw_fluid_dense3", vxa.dense_lattice(3, 21, materials=(1, 3, 4)), 1200, 100, sim=S(init_cm_time=0.01, stop_condition_value=0.2), env=env(), lw=True)
+    case("lw_fluid_sparse4", vxa.sparse_lattice(4, 22, fill=0.5, materials=(1, 3, 4)), 1000, 100, sim=S(init_cm_time=0.01, stop_condition_value=0.2), env=env(), lw=True)
+    case("lw_fluid_first30", vxa.dense_lattice(2, 23, materials=(3, 4)), 30, 1, sim=S(init_cm_time=0.0005, stop_condition_value=0.2), env=env(), lw=True)
+    case("lw_fluid_dense3_full", vxa.dense_lattice(3, 24, materials=(1, 3, 4)), 0, 1, sim=S(init_cm_time=0.02, stop_condition_value=0.3), env=env(), lw=True, full=True)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "fluid":
+        fluid_cases()
+    else:
+        main()
+        fluid_cases()
