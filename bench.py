@@ -49,13 +49,22 @@ def algorithmic_bytes_per_voxel_step(n_vox: int, n_bond: int) -> float:
     return 115.0 + 72.0 * n_bond / n_vox
 
 
+WATER = False   # --workload water: BASELINE.json config 5 (land/water fork, fluid drag) instead of the headline config
+
+
 def synthetic_vxa(n: int, seed: int) -> str:
     from evosoro_b200 import vxa
     sim = vxa.SimParams(init_cm_time=INIT_CM_TIME, stop_condition_value=5.0)
+    if WATER:   # evosoro/examples/swimming_basic.py:68-70,137-138
+        env = vxa.EnvParams(fluid_environment=1, aggregate_drag_coefficient=750.0)
+        return vxa.vxa_text(vxa.dense_lattice(n, seed), sim=sim, env=env)
     return vxa.vxa_text(vxa.dense_lattice(n, seed), sim=sim)
 
 
 def workload_name(n: int, robots: int) -> str:
+    if WATER:
+        return (f"land/water fork: dense{n}^3 x {robots} robots per GPU ({n ** 3} voxels / {3 * n * n * (n - 1)} bonds each), 4 materials, "
+                "fluid environment (surface drag, C_d 750), thermal actuation")
     return (f"dense{n}^3 x {robots} robots per GPU ({n ** 3} voxels / {3 * n * n * (n - 1)} bonds each), 4 materials, "
             "gravity+floor+thermal actuation, SelfCol 0")
 
@@ -96,7 +105,8 @@ def run_reference_cpu(lattice: int, warm_ts: int, timed_ts: int, procs: int, tmp
             with open(p, "w") as f:
                 f.write(synthetic_vxa(lattice, seed0 + i))
             paths.append(p)
-        ps = [subprocess.Popen([REF_DUMP, "time", p, str(warm_ts), str(timed_ts), "nocol"], stdout=subprocess.PIPE, text=True) for p in paths]
+        exe = REF_DUMP + "_lw" if WATER else REF_DUMP
+        ps = [subprocess.Popen([exe, "time", p, str(warm_ts), str(timed_ts), "nocol"], stdout=subprocess.PIPE, text=True) for p in paths]
         outs = [p.communicate()[0] for p in ps]
         vox_steps, worst = 0.0, 0.0
         for o in outs:
@@ -221,7 +231,7 @@ def gpu_arm(args):
     # ---- inputs: R distinct robots per GPU, imported from .vxa text by the product importer ------
     robots = []
     for r in range(R):
-        m = engine.Model(text=synthetic_vxa(n, rank * R + r))
+        m = engine.Model(text=synthetic_vxa(n, rank * R + r), variant=engine.VARIANT_LAND_WATER if WATER else engine.VARIANT_VOXCAD)
         robots.append(m.robot)
         m.close()
     n_vox, n_bond = robots[0].n_vox, robots[0].n_bond
@@ -348,7 +358,10 @@ def main():
     ap.add_argument("--cpu-timesteps", type=int, default=10000, help="timed timesteps of the cpu_baseline sample")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="land", choices=["land", "water"], help="water = BASELINE config 5 (use --lattice 8 --robots 2048)")
     args = ap.parse_args()
+    global WATER
+    WATER = args.workload == "water"
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":

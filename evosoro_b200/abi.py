@@ -23,6 +23,7 @@ VXG_PREC_F64 = 1
 
 VXG_ST_DIVERGED = 0x1
 VXG_ST_FINISHED = 0x2
+VXG_ST_COL_OVERFLOW = 0x4
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
@@ -56,7 +57,7 @@ class SimParams(C.Structure):
         ("dt", C.c_double), ("bond_damp_z", C.c_double), ("col_damp_z", C.c_double), ("slow_damp_z", C.c_double),
         ("grav_acc", C.c_double), ("init_cm_time", C.c_double), ("temp_period", C.c_double),
         ("temp_amplitude", C.c_double), ("min_scale_fact", C.c_double), ("max_scale_fact", C.c_double),
-        ("lattice_dim", C.c_double), ("drag_coeff", C.c_double),
+        ("lattice_dim", C.c_double), ("drag_coeff", C.c_double), ("col_horizon", C.c_double),
         ("flags", C.c_uint32), ("reserved", C.c_uint32),
     ]
 

@@ -61,6 +61,7 @@ int main(int argc, char** argv) {
         lim.max_vox = std::max(lim.max_vox, descs[r].n_vox);
         lim.max_vclass = std::max(lim.max_vclass, descs[r].n_vclass);
         lim.max_bclass = std::max(lim.max_bclass, descs[r].n_bclass);
+        if (descs[r].sim.flags & VXG_F_COLLISIONS) lim.max_col_pairs = 512;   // contact-bond list capacity (overflow is reported, never truncated)
         if (descs[r].sim.flags & VXG_F_FLUID) lim.max_mesh_verts = std::max(lim.max_mesh_verts, vxg_mesh_vertex_count(&descs[r]));
         max_total = std::max(max_total, total[r]);
         if (print_scrn) printf("Imported %s: %d voxels, %d bonds, %lld steps\n", files[r].c_str(), descs[r].n_vox, descs[r].n_bond, (long long)total[r]);
@@ -83,7 +84,8 @@ int main(int argc, char** argv) {
     int ok = 1;
     for (int r = 0; r < n; r++) {
         vxh_info info; vxh_get_info(models[r], &info);
-        if (status[r] & VXG_ST_DIVERGED) { fprintf(stderr, "%s: Simulation Diverged. Please reduce forces or accelerations.\n", files[r].c_str()); }
+        if (status[r] & VXG_ST_COL_OVERFLOW) { fprintf(stderr, "%s: more than %d self-collision contact bonds\n", files[r].c_str(), lim.max_col_pairs); ok = 0; }
+        else if (status[r] & VXG_ST_DIVERGED) { fprintf(stderr, "%s: Simulation Diverged. Please reduce forces or accelerations.\n", files[r].c_str()); }
         if (print_scrn) printf("Ended at: %g\n", stats[r].time);
         if (info.fitness_file_name[0]) {   // SaveResultFile(FitnessFileName), main.cpp:130
             if (vxh_format_result(models[r], &stats[r], nullptr, 0, info.fitness_file_name) < 0) { fprintf(stderr, "voxelyze: %s\n", vxh_last_error()); ok = 0; }

@@ -274,6 +274,7 @@ template <typename T> struct alignas(16) VoxK {    // from vxg_vox_class (+ sim 
     int dof;
     int has_bc;        // any fixed DOF or external load
     T half_nom;        // NominalSize / 2 (corner extents of the surface mesh, LW/VXS_Voxel.cpp:474-475)
+    T e_mod;           // Vox_E: composite stiffness of contact bonds (CVX_Bond::LinkVoxels VX_Bond.cpp:84-102)
 };
 
 template <typename T> struct BondOut {

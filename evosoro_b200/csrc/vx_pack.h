@@ -87,7 +87,7 @@ inline void pack_classes(const vxg_robot_desc* d, BondK<Real>* bk, double* bk_di
             if (c.ext_force[a] != 0 || c.ext_torque[a] != 0) bc = true;
         }
         k.dof = c.dof_fixed; k.has_bc = bc ? 1 : 0;
-        k.half_nom = (Real)(0.5 * c.nom_size);
+        k.half_nom = (Real)(0.5 * c.nom_size); k.e_mod = (Real)c.e_mod;
         ScaleK& s = sk[i];
         s.mat_index = c.mat_index;
         s.nom_size = c.nom_size; s.init_size = c.init_size; s.cte = c.cte; s.temp_amp_damp = c.temp_amp_damp; s.phase_offset = c.phase_offset;
@@ -172,6 +172,45 @@ inline int pack_mesh(const vxg_robot_desc* d, const BlobLayout& L, unsigned char
     return n_vert;
 }
 
+// Static tables of the self-collision broad phase (CVX_Sim::Import VX_Sim.cpp:675-686, CVX_Voxel::CalcNearby
+// VX_Voxel.cpp:171-209): the surface voxels (any of the 6 faces without a bond), every voxel's lattice
+// coordinates, and per voxel a 64-bit mask over the lattice offsets with |dx|+|dy|+|dz| <= 3 telling which of
+// those voxels are within `hops` bond hops (NearbyVoxInds).  Returns false if hops > 3.
+inline int near_code_host(int dx, int dy, int dz) {
+    int code = 0;
+    for (int z = -3; z <= 3; z++) for (int y = -3; y <= 3; y++) for (int x = -3; x <= 3; x++) {
+        if (abs(x) + abs(y) + abs(z) > 3) continue;
+        if (x == dx && y == dy && z == dz) return code;
+        code++;
+    }
+    return -1;
+}
+inline bool pack_collision_tables(const vxg_robot_desc* d, int hops, std::vector<int16_t>& surf, std::vector<int8_t>& lat4, std::vector<unsigned long long>& near) {
+    if (hops > 3) return false;
+    std::vector<int> ijk; lattice_coords(d, ijk);
+    int lo[3] = {1 << 30, 1 << 30, 1 << 30};
+    for (int i = 0; i < d->n_vox; i++) for (int a = 0; a < 3; a++) if (ijk[3 * i + a] < lo[a]) lo[a] = ijk[3 * i + a];
+    std::vector<std::vector<int>> adj(d->n_vox);
+    std::vector<int> nb(d->n_vox, 0);
+    for (int j = 0; j < d->n_bond; j++) { adj[d->bond_v1[j]].push_back(d->bond_v2[j]); adj[d->bond_v2[j]].push_back(d->bond_v1[j]); nb[d->bond_v1[j]]++; nb[d->bond_v2[j]]++; }
+    surf.clear(); lat4.assign((size_t)4 * d->n_vox, 0); near.assign(d->n_vox, 0ULL);
+    for (int i = 0; i < d->n_vox; i++) {
+        if (nb[i] < 6) surf.push_back((int16_t)i);   // IsSurfaceVoxel (VX_Voxel.h:80)
+        for (int a = 0; a < 3; a++) { int c = ijk[3 * i + a] - lo[a]; if (c > 120) return false; lat4[4 * i + a] = (int8_t)c; }
+        std::vector<int> cur(1, i), seen(1, i);   // breadth-first over the permanent bonds
+        for (int h = 0; h < hops; h++) {
+            std::vector<int> nxt;
+            for (int u : cur) for (int w : adj[u]) { bool s = false; for (int x : seen) if (x == w) { s = true; break; } if (!s) { seen.push_back(w); nxt.push_back(w); } }
+            cur.swap(nxt);
+        }
+        for (int w : seen) {
+            int code = near_code_host(ijk[3 * w] - ijk[3 * i], ijk[3 * w + 1] - ijk[3 * i + 1], ijk[3 * w + 2] - ijk[3 * i + 2]);
+            if (code >= 0) near[i] |= 1ULL << code;   // a voxel h hops away is at most h lattice steps away, so it always has a code
+        }
+    }
+    return true;
+}
+
 inline void init_ctl(const vxg_robot_desc* d, RobotCtl& c) {
     const vxg_sim_params& P = d->sim;
     memset(&c, 0, sizeof c);
@@ -181,6 +220,8 @@ inline void init_ctl(const vxg_robot_desc* d, RobotCtl& c) {
     c.n_vox = d->n_vox; c.n_vclass = d->n_vclass; c.n_bclass = d->n_bclass; c.ini_latched = 0;
     c.half_bond_z = 0.5 * P.bond_damp_z;
     c.drag_coeff = P.drag_coeff; c.n_vert = 0;
+    c.col_horizon = P.col_horizon; c.lattice_dim = P.lattice_dim; c.col_acc = 0; c.max_vel = 0;
+    c.n_col = 0; c.col_first = 1; c.col_host = 0; c.n_surf = 0; c.col_hops = (int)(P.col_horizon * 1.5);
     c.sym_mass = 1;
     for (int i = 0; i < d->n_bclass; i++) {
         const vxg_bond_class& b = d->bclasses[i];

@@ -325,9 +325,67 @@ VX_HD V3<Real> voxel_drag(const RobotView<Real>& R, const RobotConsts<Real>& C, 
     return d;
 }
 
-// Voxel v: total force/moment = own share + received share; integrate (EulerStep).
+// ---- self-collision (VX_Sim.cpp:1729-1755, :2357-2413; VXS_BondCollision.cpp:41-59) ------------------
+struct ColPair { int16_t v1, v2; };
+struct ColTables {              // per-robot static tables in global memory, read by the list rebuild only
+    const int16_t* surf;        // [n_surf] surface voxels, ascending
+    const int8_t* lat4;         // [nv][4] lattice coordinates
+    const unsigned long long* near;   // [nv] mask over lattice offsets: within col_hops bond hops (CalcNearby)
+    int n_surf, hops;
+};
+VX_HD int near_code(int dx, int dy, int dz) {   // rank of (dx,dy,dz) among the offsets with |dx|+|dy|+|dz| <= 3, z slowest
+    int code = 0;
+    for (int z = -3; z <= 3; z++) for (int y = -3; y <= 3; y++) for (int x = -3; x <= 3; x++) {
+        int l1 = (x < 0 ? -x : x) + (y < 0 ? -y : y) + (z < 0 ? -z : z);
+        if (l1 > 3) continue;
+        if (x == dx && y == dy && z == dz) return code;
+        code++;
+    }
+    return -1;
+}
+// CalcL1Bonds' pair test (VX_Sim.cpp:2376-2386): inside the filter radius, not a lattice-near neighbour, and
+// closer than CollisionHorizon * Scale_1 (the reference uses voxel 1's scale twice)
 template <typename Real>
-VX_HD void voxel_task(const RobotView<Real>& R, const RobotConsts<Real>& C, int v, const VoxStat& st, const OwnState<Real>& own,
+VX_HD bool col_pair_hit(const RobotView<Real>& R, const RobotConsts<Real>& C, const ColTables& ct, int vi, int vj, Real horizon, Real filt2) {
+    const int nv = R.nv;
+    const Real dx = (Real)(R.pos[vi] - R.pos[vj]), dy = (Real)(R.pos[nv + vi] - R.pos[nv + vj]), dz = (Real)(R.pos[2 * nv + vi] - R.pos[2 * nv + vj]);
+    const Real d2 = dx * dx + dy * dy + dz * dz;
+    if (!(d2 < filt2)) return false;
+    const int ox = ct.lat4[4 * vj] - ct.lat4[4 * vi], oy = ct.lat4[4 * vj + 1] - ct.lat4[4 * vi + 1], oz = ct.lat4[4 * vj + 2] - ct.lat4[4 * vi + 2];
+    const int l1 = (ox < 0 ? -ox : ox) + (oy < 0 ? -oy : oy) + (oz < 0 ? -oz : oz);
+    if (l1 <= 3 && ((ct.near[vi] >> near_code(ox, oy, oz)) & 1ULL)) return false;   // IsNearbyVox
+    const Real act = horizon * (Real)C.scale_c[R.stat[vi].vcls];
+    return d2 < act * act;
+}
+// CVXS_BondCollision::CalcContactForce, the share of voxel v: both ends of a pair are pushed apart along the line
+// of centres with a1 * overlap, a1 = composite E * mean size (CVX_Bond::LinkVoxels / UpdateConstants)
+template <typename Real>
+VX_HD V3<Real> col_force_on(const RobotView<Real>& R, const RobotConsts<Real>& C, int v, const VoxStat& st, const OwnState<Real>& own,
+                            const ColPair* pairs, int n_col) {
+    V3<Real> f = mk3<Real>(0, 0, 0);
+    const int nv = R.nv;
+    for (int k = 0; k < n_col; k++) {
+        const ColPair p = pairs[k];
+        if (p.v1 != v && p.v2 != v) continue;
+        const int o = p.v1 == v ? p.v2 : p.v1;
+        const Real dx = (Real)(R.pos[o] - own.px), dy = (Real)(R.pos[nv + o] - own.py), dz = (Real)(R.pos[2 * nv + o] - own.pz);
+        const int vco = R.stat[o].vcls;
+        const Real nomd = (Real)((C.scale_c[st.vcls] + C.scale_c[vco]) * 0.75);
+        const Real len = vx_sqrt(dx * dx + dy * dy + dz * dz);
+        const Real rel = nomd - len;
+        if (rel > (Real)0) {
+            const VoxK<Real>& k1 = C.vk[st.vcls]; const VoxK<Real>& k2 = C.vk[vco];
+            const Real a1 = ((k1.e_mod * k2.e_mod / (k1.e_mod + k2.e_mod)) * (Real)2) * (k1.half_nom + k2.half_nom);
+            const Real g = a1 * rel / len;
+            f.x -= dx * g; f.y -= dy * g; f.z -= dz * g;
+        }
+    }
+    return f;
+}
+
+// Voxel v: total force/moment = own share + received share; integrate (EulerStep).  Returns |Vel|^2 after the step.
+template <typename Real>
+VX_HD Real voxel_task(const RobotView<Real>& R, const RobotConsts<Real>& C, int v, const VoxStat& st, const OwnState<Real>& own,
                       uint32_t fl, V3<Real> F, V3<Real> M) {
     const int nv = R.nv;
     {
@@ -360,6 +418,8 @@ VX_HD void voxel_task(const RobotView<Real>& R, const RobotConsts<Real>& C, int 
         R.quat[v] = q; R.momA[v] = a; R.momB[v] = b;
     }
     R.flags[v] = sf ? (fl | VX_FL_STATIC_FRIC) : (fl & ~VX_FL_STATIC_FRIC);
+    const V3<Real> vel = s.lm * k.mass_inv;
+    return dot(vel, vel);
 }
 
 // Per-robot control block (global memory)
@@ -380,6 +440,14 @@ struct RobotCtl {
     double bond_len;        // the common bond length L of the compact form
     double drag_coeff;      // AggregateDragCoefficient (fluid)
     int n_vert, pad2;       // mesh vertices (fluid)
+    // self-collision (VXG_F_COLLISIONS): CVX_Sim::UpdateCollisions state, VX_Sim.cpp:1729-1755
+    double col_horizon, lattice_dim;
+    double col_acc;         // MaxDispSinceLastBondUpdate
+    double max_vel;         // SS.MaxVoxVel of the last step
+    int n_col;              // contact bonds in the list
+    int col_first;          // ColEnableChanged: rebuild at the next step
+    int col_host;           // the host manages the list (vxg_set_collision_pairs): no device rebuild
+    int n_surf, col_hops, pad3;
     long long eol_step;     // CurStepCount at which EndOfLifetimePosteriorY is latched (-1 never)
     double eol_post_y;      // min Pos.y over material != 5 at that step (metres); 0 = not latched
 };

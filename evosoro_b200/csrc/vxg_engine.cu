@@ -47,6 +47,9 @@ struct vxg_batch {
     void* d_bk = nullptr; double* d_bk_dist = nullptr; void* d_vk = nullptr; ScaleK* d_sk = nullptr;
     double* d_scale_c = nullptr; void* d_ext_disp = nullptr; void* d_ext_tdisp = nullptr; double* d_nom = nullptr;
     void* d_bond_rec = nullptr; StatsDev* d_stats = nullptr;
+    // self-collision (allocated when limits.max_col_pairs > 0)
+    ColPair* d_col_pairs = nullptr; int16_t* d_col_surf = nullptr; int8_t* d_col_lat4 = nullptr; unsigned long long* d_col_near = nullptr;
+    ColPair* h_col_pairs = nullptr; int16_t* h_col_surf = nullptr; int8_t* h_col_lat4 = nullptr; unsigned long long* h_col_near = nullptr;
     // pinned host mirrors (whole batch, uploaded in one go before the first step after a change)
     unsigned char* h_blobs = nullptr;
     RobotCtl* h_ctl = nullptr;
@@ -95,12 +98,14 @@ template <typename Real> static BatchDev<Real> dev_view(const vxg_batch* b) {
     B.scale_c = b->d_scale_c; B.ext_disp = (Real*)b->d_ext_disp; B.ext_tdisp = (Real*)b->d_ext_tdisp; B.nom = b->d_nom;
     B.bond_rec = (Real*)b->d_bond_rec;
     B.max_vclass = b->lim.max_vclass; B.max_bclass = b->lim.max_bclass; B.n_robots = b->n_robots;
+    B.col_pairs = b->d_col_pairs; B.col_surf = b->d_col_surf; B.col_lat4 = b->d_col_lat4; B.col_near = b->d_col_near;
+    B.max_col = b->lim.max_col_pairs;
     return B;
 }
 
-template <typename Real, int NV, int VPT, bool SMEM, bool COMPACT, bool FLUID = false>
+template <typename Real, int NV, int VPT, bool SMEM, bool COMPACT, bool FLUID = false, bool COLLIDE = false>
 static cudaError_t launch_step(vxg_batch* b, int n_steps, int record) {
-    auto kern = vx_step_kernel<Real, NV, VPT, SMEM, COMPACT, FLUID>;
+    auto kern = vx_step_kernel<Real, NV, VPT, SMEM, COMPACT, FLUID, COLLIDE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes);
     if (e != cudaSuccess) return e;
     kern<<<b->n_robots, NV / VPT, b->smem_bytes, b->stream>>>(dev_view<Real>(b), n_steps, record);
@@ -132,9 +137,23 @@ static cudaError_t launch_step_fluid(vxg_batch* b, int n_steps, int record) {
     return cudaErrorInvalidValue;
 }
 
+// batches with self-collision (limits.max_col_pairs > 0): fp32, shared-memory resident, wide bond table
+static cudaError_t launch_step_collide(vxg_batch* b, int n_steps, int record) {
+    switch (b->L.nv) {
+        case 64: return launch_step<float, 64, 1, true, false, false, true>(b, n_steps, record);
+        case 128: return launch_step<float, 128, 1, true, false, false, true>(b, n_steps, record);
+        case 256: return launch_step<float, 256, 1, true, false, false, true>(b, n_steps, record);
+        case 512: return launch_step<float, 512, 1, true, false, false, true>(b, n_steps, record);
+        case 1024: return launch_step<float, 1024, 2, true, false, false, true>(b, n_steps, record);
+        case 2048: return launch_step<float, 2048, 4, true, false, false, true>(b, n_steps, record);
+    }
+    return cudaErrorInvalidValue;
+}
+
 // The compact bond table exists for the production path only (fp32, shared-memory resident).
 static cudaError_t launch_step_p(vxg_batch* b, int n_steps, int record) {
     if (b->L.nvert_cap > 0) return launch_step_fluid(b, n_steps, record);
+    if (b->lim.max_col_pairs > 0) return launch_step_collide(b, n_steps, record);
     if (b->prec == VXG_PREC_F64)
         return b->smem_mode ? launch_step_s<double, true, false>(b, n_steps, record) : launch_step_s<double, false, false>(b, n_steps, record);
     if (!b->smem_mode) return launch_step_s<float, false, false>(b, n_steps, record);
@@ -145,6 +164,8 @@ static void free_all(vxg_batch* b) {
     cudaFree(b->d_blobs); cudaFree(b->d_ctl); cudaFree(b->d_bk); cudaFree(b->d_bk_dist); cudaFree(b->d_vk); cudaFree(b->d_sk);
     cudaFree(b->d_scale_c); cudaFree(b->d_ext_disp); cudaFree(b->d_ext_tdisp); cudaFree(b->d_nom); cudaFree(b->d_bond_rec);
     cudaFree(b->d_stats);
+    cudaFree(b->d_col_pairs); cudaFree(b->d_col_surf); cudaFree(b->d_col_lat4); cudaFree(b->d_col_near);
+    cudaFreeHost(b->h_col_pairs); cudaFreeHost(b->h_col_surf); cudaFreeHost(b->h_col_lat4); cudaFreeHost(b->h_col_near);
     cudaFreeHost(b->h_bkc);
     cudaFreeHost(b->h_blobs); cudaFreeHost(b->h_ctl); cudaFreeHost(b->h_bk); cudaFreeHost(b->h_bk_dist); cudaFreeHost(b->h_vk);
     cudaFreeHost(b->h_sk); cudaFreeHost(b->h_scale_c); cudaFreeHost(b->h_ext_disp); cudaFreeHost(b->h_ext_tdisp); cudaFreeHost(b->h_nom);
@@ -175,17 +196,22 @@ extern "C" int vxg_create(vxg_batch** out, int device, int n_robots, const vxg_l
     // thread mapping: <= 512 threads per CTA, VPT voxels per thread
     b->vpt = b->L.nv <= 512 ? 1 : b->L.nv / 512;
     b->threads = b->L.nv / b->vpt;
-    size_t tb = b->prec == VXG_PREC_F64 ? tables_bytes<double>(lim->max_vclass, lim->max_bclass) : tables_bytes<float>(lim->max_vclass, lim->max_bclass);
+    if (lim->max_col_pairs < 0 || lim->max_col_pairs > 16384) { delete b; return fail(VXG_ERR_ARG, "vxg_create: max_col_pairs out of range"); }
+    const int mc = lim->max_col_pairs;
+    size_t tb = b->prec == VXG_PREC_F64 ? tables_bytes<double>(lim->max_vclass, lim->max_bclass, false, mc) : tables_bytes<float>(lim->max_vclass, lim->max_bclass, false, mc);
     int max_smem = 0;
     CK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     if (tb > (size_t)max_smem) { delete b; return fail(VXG_UNSUPPORTED_SIZE, "vxg_create: class tables (%zu B) exceed shared memory", tb); }
     b->tb_wide = tb;
-    b->tb_compact = tables_bytes<float>(lim->max_vclass, lim->max_bclass, true);
+    b->tb_compact = tables_bytes<float>(lim->max_vclass, lim->max_bclass, true, mc);
     b->smem_wide_fits = b->L.total_bytes + tb <= (size_t)max_smem;
     b->smem_mode_wide_or_compact = b->prec == VXG_PREC_F32 && b->L.total_bytes + b->tb_compact <= (size_t)max_smem;
-    if (b->L.nvert_cap > 0) {   // fluid layouts run shared-memory resident with the wide table only
+    if (mc > 0 && (lim->precision != VXG_PREC_F32 || lim->max_mesh_verts > 0)) {
+        delete b; return fail(VXG_UNSUPPORTED_FEATURE, "vxg_create: the self-collision kernels exist in fp32 without fluid drag only");
+    }
+    if (mc > 0 || b->L.nvert_cap > 0) {   // these layouts run shared-memory resident with the wide table only
         b->smem_mode_wide_or_compact = false;
-        if (!b->smem_wide_fits) { delete b; return fail(VXG_UNSUPPORTED_SIZE, "vxg_create: robot blob with surface mesh (%zu B) exceeds shared memory", b->L.total_bytes + tb); }
+        if (!b->smem_wide_fits) { delete b; return fail(VXG_UNSUPPORTED_SIZE, "vxg_create: robot blob with collision list / surface mesh (%zu B) exceeds shared memory", b->L.total_bytes + tb); }
     }
     b->smem_mode = b->smem_wide_fits || b->smem_mode_wide_or_compact;   // final choice is made at flush, when the classes are known
     b->smem_bytes = b->smem_mode ? b->L.total_bytes + tb : tb;
@@ -199,12 +225,20 @@ extern "C" int vxg_create(vxg_batch** out, int device, int n_robots, const vxg_l
     DA(b->d_sk, nr * mv * sizeof(ScaleK)); DA(b->d_scale_c, nr * mv * sizeof(double));
     DA(b->d_ext_disp, nr * mv * 3 * b->rs()); DA(b->d_ext_tdisp, nr * mv * 3 * b->rs()); DA(b->d_nom, nr * 3 * nv * sizeof(double));
     DA(b->d_stats, nr * sizeof(StatsDev));
+    if (mc > 0) {
+        DA(b->d_col_pairs, nr * (size_t)mc * sizeof(ColPair)); DA(b->d_col_surf, nr * nv * sizeof(int16_t));
+        DA(b->d_col_lat4, nr * nv * 4); DA(b->d_col_near, nr * nv * sizeof(unsigned long long));
+    }
     HA(b->h_blobs, nr * b->L.total_bytes); HA(b->h_ctl, nr * sizeof(RobotCtl));
     HA(b->h_bkc, nr * mb * b->bkc_sz());
     HA(b->h_bk, nr * mb * b->bk_sz()); HA(b->h_bk_dist, nr * mb * sizeof(double)); HA(b->h_vk, nr * mv * b->vk_sz());
     HA(b->h_sk, nr * mv * sizeof(ScaleK)); HA(b->h_scale_c, nr * mv * sizeof(double));
     HA(b->h_ext_disp, nr * mv * 3 * b->rs()); HA(b->h_ext_tdisp, nr * mv * 3 * b->rs()); HA(b->h_nom, nr * 3 * nv * sizeof(double));
     HA(b->h_stats, nr * sizeof(StatsDev));
+    if (mc > 0) {
+        HA(b->h_col_pairs, nr * (size_t)mc * sizeof(ColPair)); HA(b->h_col_surf, nr * nv * sizeof(int16_t));
+        HA(b->h_col_lat4, nr * nv * 4); HA(b->h_col_near, nr * nv * sizeof(unsigned long long));
+    }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev1);
@@ -254,7 +288,8 @@ extern "C" int vxg_upload(vxg_batch* b, int robot, const vxg_robot_desc* d) {
         return fail(VXG_ERR_ARG, "vxg_upload: bond arrays missing");
     if (!d->nom_pos || !d->vox_class || !d->vclasses) return fail(VXG_ERR_ARG, "vxg_upload: voxel arrays missing");
     const vxg_sim_params& P = d->sim;
-    if (P.flags & VXG_F_COLLISIONS) return fail(VXG_UNSUPPORTED_FEATURE, "self-collision contact bonds are not implemented on the device yet");
+    if ((P.flags & VXG_F_COLLISIONS) && b->lim.max_col_pairs <= 0)
+        return fail(VXG_UNSUPPORTED_SIZE, "vxg_upload: a robot with self-collision needs a batch created with limits.max_col_pairs > 0");
     if ((P.flags & VXG_F_FLUID) && b->L.nvert_cap <= 0)
         return fail(VXG_UNSUPPORTED_SIZE, "vxg_upload: a fluid-environment robot needs a batch created with limits.max_mesh_verts > 0");
     if (!(P.dt > 0) || !std::isfinite(P.dt)) return fail(VXG_ERR_ARG, "vxg_upload: dt must be positive");
@@ -277,6 +312,19 @@ extern "C" int vxg_upload(vxg_batch* b, int robot, const vxg_robot_desc* d) {
     if (b->prec == VXG_PREC_F64) { fill_classes<double>(b, robot, d); reset_blob<double>(b, robot, d); }
     else { fill_classes<float>(b, robot, d); reset_blob<float>(b, robot, d); }
     init_ctl(d, b->h_ctl[robot]);
+    if (b->lim.max_col_pairs > 0) {   // broad-phase tables of the self-collision list (CalcNearby, surface voxels)
+        std::vector<int16_t> surf; std::vector<int8_t> lat4; std::vector<unsigned long long> near;
+        const int hops = (int)(P.col_horizon * 1.5);
+        if ((P.flags & VXG_F_COLLISIONS) && (!(P.col_horizon > 0) || !pack_collision_tables(d, hops, surf, lat4, near)))
+            return fail(VXG_UNSUPPORTED_FEATURE, "vxg_upload: CollisionHorizon %g needs more than 3 bond hops (or the lattice is wider than 120 cells)", P.col_horizon);
+        if (P.flags & VXG_F_COLLISIONS) {
+            const size_t nv = (size_t)b->L.nv, r = (size_t)robot;
+            memcpy(b->h_col_surf + r * nv, surf.data(), surf.size() * sizeof(int16_t));
+            memcpy(b->h_col_lat4 + r * nv * 4, lat4.data(), lat4.size());
+            memcpy(b->h_col_near + r * nv, near.data(), near.size() * sizeof(unsigned long long));
+            b->h_ctl[robot].n_surf = (int)surf.size();
+        }
+    }
     if (b->L.nvert_cap > 0) {   // surface-mesh tables (also for non-fluid robots of a fluid batch: cheap, keeps one code path)
         int nvx = pack_mesh<float>(d, b->L, b->h_blobs + (size_t)robot * b->L.total_bytes);
         if (nvx < 0) return fail(VXG_UNSUPPORTED_SIZE, "vxg_upload: robot %d has more than max_mesh_verts = %d surface-mesh vertices", robot, b->lim.max_mesh_verts);
@@ -317,6 +365,12 @@ static int flush(vxg_batch* b) {
         CK(cudaMemcpyAsync(b->d_ext_disp, b->h_ext_disp, nr * mv * 3 * b->rs(), cudaMemcpyHostToDevice, b->stream));
         CK(cudaMemcpyAsync(b->d_ext_tdisp, b->h_ext_tdisp, nr * mv * 3 * b->rs(), cudaMemcpyHostToDevice, b->stream));
         CK(cudaMemcpyAsync(b->d_nom, b->h_nom, nr * 3 * nv * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+        if (b->lim.max_col_pairs > 0) {
+            CK(cudaMemcpyAsync(b->d_col_pairs, b->h_col_pairs, nr * (size_t)b->lim.max_col_pairs * sizeof(ColPair), cudaMemcpyHostToDevice, b->stream));
+            CK(cudaMemcpyAsync(b->d_col_surf, b->h_col_surf, nr * nv * sizeof(int16_t), cudaMemcpyHostToDevice, b->stream));
+            CK(cudaMemcpyAsync(b->d_col_lat4, b->h_col_lat4, nr * nv * 4, cudaMemcpyHostToDevice, b->stream));
+            CK(cudaMemcpyAsync(b->d_col_near, b->h_col_near, nr * nv * sizeof(unsigned long long), cudaMemcpyHostToDevice, b->stream));
+        }
     }
     if (b->dirty || b->ctl_dirty) CK(cudaMemcpyAsync(b->d_ctl, b->h_ctl, nr * sizeof(RobotCtl), cudaMemcpyHostToDevice, b->stream));
     b->dirty = false; b->ctl_dirty = false;
@@ -547,8 +601,27 @@ extern "C" int vxg_reduce_stats(vxg_batch* b, vxg_robot_stats* out) {
 }
 
 extern "C" int vxg_set_collision_pairs(vxg_batch* b, int robot, int n_pairs, const int32_t* v1, const int32_t* v2, const double* a1) {
-    (void)b; (void)robot; (void)n_pairs; (void)v1; (void)v2; (void)a1;
-    return fail(VXG_UNSUPPORTED_FEATURE, "self-collision contact bonds are not implemented on the device yet");
+    (void)a1;
+    if (!b) return fail(VXG_ERR_ARG, "vxg_set_collision_pairs: null batch");
+    if (robot < 0 || robot >= b->n_robots || !b->uploaded[robot]) return fail(VXG_ERR_ARG, "vxg_set_collision_pairs: robot %d not present", robot);
+    if (b->lim.max_col_pairs <= 0) return fail(VXG_UNSUPPORTED_SIZE, "vxg_set_collision_pairs: the batch was created with limits.max_col_pairs = 0");
+    if (n_pairs > b->lim.max_col_pairs) return fail(VXG_UNSUPPORTED_SIZE, "vxg_set_collision_pairs: %d pairs > max_col_pairs %d", n_pairs, b->lim.max_col_pairs);
+    if (n_pairs > 0 && (!v1 || !v2)) return fail(VXG_ERR_ARG, "vxg_set_collision_pairs: null pair arrays");
+    int rc = pull(b, true, -1);   // keep the device state; the whole batch is re-uploaded by the next flush
+    if (rc) return rc;
+    if (!b->dirty) CK(cudaMemcpy(b->h_col_pairs, b->d_col_pairs, (size_t)b->n_robots * b->lim.max_col_pairs * sizeof(ColPair), cudaMemcpyDeviceToHost));
+    RobotCtl& c = b->h_ctl[robot];
+    if (n_pairs < 0) { c.col_host = 0; c.col_first = 1; c.n_col = 0; }
+    else {
+        ColPair* p = b->h_col_pairs + (size_t)robot * b->lim.max_col_pairs;
+        for (int i = 0; i < n_pairs; i++) {
+            if (v1[i] < 0 || v2[i] < 0 || v1[i] >= c.n_vox || v2[i] >= c.n_vox || v1[i] == v2[i]) return fail(VXG_ERR_ARG, "vxg_set_collision_pairs: pair %d malformed", i);
+            p[i].v1 = (int16_t)v1[i]; p[i].v2 = (int16_t)v2[i];
+        }
+        c.col_host = 1; c.n_col = n_pairs; c.flags |= VXG_F_COLLISIONS;
+    }
+    b->dirty = true;
+    return VXG_OK;
 }
 
 extern "C" int vxg_mesh_vertex_count(const vxg_robot_desc* d) {

@@ -29,6 +29,8 @@ namespace vx {
 #define VXG_F_LW_SCALE_ 0x0004u
 #define VXG_F_STICKY_FLOOR_ 0x0008u
 #define VXG_F_FLUID_ 0x0010u
+#define VXG_F_COLLISIONS_ 0x0020u
+#define VXG_ST_COL_OVERFLOW_ 0x4u
 
 template <typename Real> struct BatchDev {
     unsigned char* blobs;       // [n_robots][L.total_bytes]
@@ -44,6 +46,12 @@ template <typename Real> struct BatchDev {
     double* nom;                // [n_robots][3][nv]
     Real* bond_rec;             // [n_robots][39][nv] or nullptr
     int max_vclass, max_bclass, n_robots;
+    // self-collision: contact-bond list (persists between launches) and the static broad-phase tables
+    ColPair* col_pairs;         // [n_robots][max_col]
+    int16_t* col_surf;          // [n_robots][nv]
+    int8_t* col_lat4;           // [n_robots][nv][4]
+    unsigned long long* col_near;   // [n_robots][nv]
+    int max_col;
 };
 
 // shared-memory carve-up after the blob
@@ -55,10 +63,12 @@ template <typename Real> struct SmemTables {
     Real* ext_disp; Real* ext_tdisp;
     double* red;      // [4][32] reduction scratch
     unsigned long long* mbar;   // split-phase barrier between the axis sub-phases
+    unsigned int* maxvel;       // [2] max |Vel|^2 of a step as float bits (double-buffered by step parity)
+    ColPair* pairs;             // [max_col] contact bonds
 };
 
 template <typename Real>
-__host__ __device__ inline size_t tables_bytes(int max_vclass, int max_bclass, bool compact = false) {
+__host__ __device__ inline size_t tables_bytes(int max_vclass, int max_bclass, bool compact = false, int max_col = 0) {
     size_t o = 0;
     o = vx_align16(o + (compact ? sizeof(BondKc<Real>) : sizeof(BondK<Real>)) * max_bclass);
     o = vx_align16(o + sizeof(double) * max_bclass);
@@ -69,12 +79,13 @@ __host__ __device__ inline size_t tables_bytes(int max_vclass, int max_bclass, b
     o = vx_align16(o + sizeof(Real) * 3 * max_vclass);
     o = vx_align16(o + sizeof(Real) * 3 * max_vclass);
     o = vx_align16(o + sizeof(double) * 4 * 32);
-    o = vx_align16(o + sizeof(unsigned long long));
+    o = vx_align16(o + sizeof(unsigned long long) + 2 * sizeof(unsigned int));
+    o = vx_align16(o + sizeof(ColPair) * max_col);
     return o;
 }
 
 template <typename Real>
-__device__ inline SmemTables<Real> carve_tables(unsigned char* p, int max_vclass, int max_bclass, bool compact) {
+__device__ inline SmemTables<Real> carve_tables(unsigned char* p, int max_vclass, int max_bclass, bool compact, int max_col) {
     SmemTables<Real> t; size_t o = 0;
     t.bk = p + o;                   o = vx_align16(o + (compact ? sizeof(BondKc<Real>) : sizeof(BondK<Real>)) * max_bclass);
     t.bk_dist = (double*)(p + o);   o = vx_align16(o + sizeof(double) * max_bclass);
@@ -86,6 +97,9 @@ __device__ inline SmemTables<Real> carve_tables(unsigned char* p, int max_vclass
     t.ext_tdisp = (Real*)(p + o);   o = vx_align16(o + sizeof(Real) * 3 * max_vclass);
     t.red = (double*)(p + o);       o = vx_align16(o + sizeof(double) * 4 * 32);
     t.mbar = (unsigned long long*)(p + o);
+    t.maxvel = (unsigned int*)(p + o + sizeof(unsigned long long));
+    o = vx_align16(o + sizeof(unsigned long long) + 2 * sizeof(unsigned int));
+    t.pairs = (ColPair*)(p + o);
     return t;
 }
 
@@ -143,8 +157,44 @@ __device__ inline void block_sum4(double& a, double& b, double& c, double& d, do
     for (int i = 0; i < nw; i++) { a += red[i]; b += red[32 + i]; c += red[64 + i]; d += red[96 + i]; }
 }
 
+// CVX_Sim::CalcL1Bonds (VX_Sim.cpp:2357-2413): rebuild the contact-bond list from the current positions.
+// Every thread owns a contiguous block of rows i of the surface-voxel pair triangle (i < j); two passes
+// (count, block-wide exclusive scan, write) keep the list in the reference's creation order (i, then j).
+// Returns the number of contact bonds found (the caller treats > cap as an overflow error).
+template <typename Real>
+__device__ __noinline__ int col_rebuild(const RobotView<Real>& R, const RobotConsts<Real>& C, const ColTables& ct, Real horizon, Real lattice,
+                                        ColPair* pairs, int cap, int* scratch /* [33] ints of shared memory */) {
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = T >> 5;
+    const Real filt = horizon * (Real)1.5 * lattice;
+    const Real filt2 = filt * filt;
+    const int S = ct.n_surf;
+    const int rpt = (S + T - 1) / T;
+    const int r0 = tid * rpt, r1 = (r0 + rpt < S) ? r0 + rpt : S;
+    int cnt = 0;
+    for (int i = r0; i < r1; i++) { const int vi = ct.surf[i]; for (int j = i + 1; j < S; j++) cnt += col_pair_hit<Real>(R, C, ct, vi, ct.surf[j], horizon, filt2) ? 1 : 0; }
+    int inc = cnt;   // inclusive scan across the block, in thread (= row) order
+    for (int o = 1; o < 32; o <<= 1) { int x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
+    __syncthreads();
+    if (lane == 31) scratch[wid] = inc;
+    __syncthreads();
+    int base = 0, total = 0;
+    for (int w = 0; w < nw; w++) { int x = scratch[w]; if (w < wid) base += x; total += x; }
+    int off = base + inc - cnt;
+    for (int i = r0; i < r1; i++) {
+        const int vi = ct.surf[i];
+        for (int j = i + 1; j < S; j++) {
+            const int vj = ct.surf[j];
+            if (col_pair_hit<Real>(R, C, ct, vi, vj, horizon, filt2)) { if (off < cap) { ColPair p; p.v1 = (int16_t)vi; p.v2 = (int16_t)vj; pairs[off] = p; } off++; }
+        }
+    }
+    __syncthreads();
+    return total;
+}
+
 //       FLUID        : blob layout with the land/water surface-mesh arrays; robots with VXG_F_FLUID get the drag phase.
-template <typename Real, int NV, int VPT, bool SMEM, bool COMPACT, bool FLUID = false>
+//       COLLIDE      : self-collision support compiled in (contact-bond list, rebuild, max-velocity reduction); kept out
+//                     of the other instantiations so that they do not pay its registers.
+template <typename Real, int NV, int VPT, bool SMEM, bool COMPACT, bool FLUID = false, bool COLLIDE = false>
 __global__ void __launch_bounds__(NV / VPT, 1) vx_step_kernel(BatchDev<Real> B, int n_steps, int record_bonds) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int T = NV / VPT;
@@ -163,7 +213,7 @@ __global__ void __launch_bounds__(NV / VPT, 1) vx_step_kernel(BatchDev<Real> B, 
     unsigned char* gblob = B.blobs + (size_t)robot * L.total_bytes;
     unsigned char* base = SMEM ? smem : gblob;
     unsigned char* tab = SMEM ? smem + L.total_bytes : smem;
-    SmemTables<Real> S = carve_tables<Real>(tab, B.max_vclass, B.max_bclass, COMPACT);
+    SmemTables<Real> S = carve_tables<Real>(tab, B.max_vclass, B.max_bclass, COMPACT, B.max_col);
     const int n_vox = ctlp->n_vox, n_vc = ctlp->n_vclass, n_bc = ctlp->n_bclass;
     const unsigned int flags = ctlp->flags;
 
@@ -215,6 +265,23 @@ __global__ void __launch_bounds__(NV / VPT, 1) vx_step_kernel(BatchDev<Real> B, 
     const Real dt_inv_run = (Real)(1.0 / dt);
     Real* rec_base = (record_bonds && B.bond_rec) ? B.bond_rec + (size_t)robot * 39 * NV : nullptr;
 
+    // self-collision state (CVX_Sim::UpdateCollisions): the list lives in shared memory during the launch
+    const bool col_on = COLLIDE && (flags & VXG_F_COLLISIONS_) != 0 && B.max_col > 0;
+    ColTables CT;
+    CT.surf = B.col_surf + (size_t)robot * NV; CT.lat4 = B.col_lat4 + (size_t)robot * NV * 4; CT.near = B.col_near + (size_t)robot * NV;
+    CT.n_surf = ctlp->n_surf; CT.hops = ctlp->col_hops;
+    int n_col = col_on ? ctlp->n_col : 0;
+    bool col_first = ctlp->col_first != 0;
+    const bool col_host = ctlp->col_host != 0;
+    double col_acc = ctlp->col_acc, max_vel = ctlp->max_vel;
+    const double col_h = ctlp->col_horizon, lat_dim = ctlp->lattice_dim;
+    bool col_overflow = false;
+    if (COLLIDE && col_on) {
+        for (int i = tid; i < n_col; i += T) S.pairs[i] = B.col_pairs[(size_t)robot * B.max_col + i];
+        if (tid == 0) { S.maxvel[0] = 0u; S.maxvel[1] = 0u; }
+        __syncthreads();
+    }
+
     double t = ctlp->cur_time;
     int cur = 0;
     int done = 0;
@@ -244,6 +311,19 @@ __global__ void __launch_bounds__(NV / VPT, 1) vx_step_kernel(BatchDev<Real> B, 
         const Real dt_inv = (s == 0) ? (Real)0 : dt_inv_run;   // dt == 0 during the very first bond pass (VX_Sim.cpp:373)
         Real* rec = (k == nsteps - 1) ? rec_base : nullptr;
 
+        if (COLLIDE && col_on) {   // UpdateCollisions (VX_Sim.cpp:1729-1755): dt is still 0 in the very first step
+            const unsigned int mvb = S.maxvel[(k + 1) & 1];            // written by the previous step's voxel phase
+            if (k > 0) max_vel = sqrt((double)__uint_as_float(mvb));
+            if (tid == 0) S.maxvel[k & 1] = 0u;                        // this step's slot; next read after two barriers
+            col_acc += fabs(max_vel * (s == 0 ? 0.0 : dt) / lat_dim);
+            if (!col_host && (col_acc > (col_h - 1.0) / 2 || col_first)) {
+                col_first = false;
+                C.scale_c = S.scale_c + cur * B.max_vclass;
+                n_col = col_rebuild<Real>(R, C, CT, (Real)col_h, (Real)lat_dim, S.pairs, B.max_col, (int*)S.red);
+                col_acc = 0.0;
+                if (n_col > B.max_col) { col_overflow = true; break; }
+            }
+        }
         V3<Real> F[VPT], M[VPT];
         VoxStat st[VPT];
         OwnState<Real> own[VPT];
@@ -292,12 +372,22 @@ __global__ void __launch_bounds__(NV / VPT, 1) vx_step_kernel(BatchDev<Real> B, 
         mbar_wait(S.mbar, mpar); mpar ^= 1u;
 #pragma unroll
         for (int j = 0; j < VPT; j++) bond_push<Real>(R, P[j]);
+        if (COLLIDE && col_on && n_col > 0) {   // contact bonds: positions are still those of the previous step here
+#pragma unroll
+            for (int j = 0; j < VPT; j++) if (tid + j * T < n_vox) F[j] = F[j] + col_force_on<Real>(R, C, tid + j * T, st[j], own[j], S.pairs, n_col);
+        }
         if (__syncthreads_or(div)) { diverged = true; break; }   // Integrate() returns before the voxel loop (VX_Sim.cpp:1777)
 
+        Real sp2 = (Real)0;
 #pragma unroll
         for (int j = 0; j < VPT; j++) {
             int v = tid + j * T;
-            if (v < n_vox) voxel_task<Real>(R, C, v, st[j], own[j], fl[j], F[j], M[j]);
+            if (v < n_vox) { Real x = voxel_task<Real>(R, C, v, st[j], own[j], fl[j], F[j], M[j]); sp2 = x > sp2 ? x : sp2; }
+        }
+        if (COLLIDE && col_on) {   // SS.MaxVoxVel for the next UpdateCollisions (VX_Sim.cpp:1626-1649)
+            float m = (float)sp2;
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if ((tid & 31) == 0) atomicMax(&S.maxvel[k & 1], __float_as_uint(m));
         }
         __syncthreads();
         cur ^= 1;
@@ -309,10 +399,17 @@ __global__ void __launch_bounds__(NV / VPT, 1) vx_step_kernel(BatchDev<Real> B, 
     __syncthreads();
     if (SMEM) copy16(gblob, smem, L.dyn_bytes, tid, T);
     for (int i = tid; i < n_vc; i += T) B.scale_c[(size_t)robot * B.max_vclass + i] = S.scale_c[cur * B.max_vclass + i];
+    if (COLLIDE && col_on) {
+        const int nc = n_col < B.max_col ? n_col : B.max_col;
+        for (int i = tid; i < nc; i += T) B.col_pairs[(size_t)robot * B.max_col + i] = S.pairs[i];
+        if (done > 0) max_vel = sqrt((double)__uint_as_float(S.maxvel[(done - 1) & 1]));
+    }
     if (tid == 0) {
         ctlp->cur_time = t;
         ctlp->step = step0 + done;
+        if (COLLIDE && col_on) { ctlp->n_col = n_col < B.max_col ? n_col : B.max_col; ctlp->col_first = col_first ? 1 : 0; ctlp->col_acc = col_acc; ctlp->max_vel = max_vel; }
         unsigned int st2 = status0;
+        if (col_overflow) st2 |= VXG_ST_COL_OVERFLOW_ | VXG_ST_DIVERGED_;
         if (diverged) st2 |= VXG_ST_DIVERGED_;
         if (step0 + done >= total) st2 |= VXG_ST_FINISHED_;
         ctlp->status = st2;

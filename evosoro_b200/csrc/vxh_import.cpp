@@ -345,7 +345,6 @@ int parse_vxa(const XNode* root, int variant, Parsed& P) {
 }
 
 int check_supported(const Parsed& P, int ignore_collisions) {
-    if (P.self_col && !ignore_collisions) return hfail(VXG_UNSUPPORTED_FEATURE, "SelfColEnabled=1: self-collision is not implemented on the device yet");
     if (P.max_vel) return hfail(VXG_UNSUPPORTED_FEATURE, "MaxVelLimitEnabled is not supported");
     if (P.blending) return hfail(VXG_UNSUPPORTED_FEATURE, "BlendingEnabled is not supported");
     if (P.volume_fx) return hfail(VXG_UNSUPPORTED_FEATURE, "VolumeEffectsEnabled is not supported");
@@ -425,7 +424,7 @@ int flatten(const Parsed& P, int variant, int ignore_collisions, vxh_model& M) {
 
     // bonds: for each voxel look +X, +Y, +Z (VX_Sim.cpp:621-641)
     M.bond_v1.clear(); M.bond_v2.clear(); M.bond_axis.clear(); M.bond_class.clear(); M.bclasses.clear();
-    typedef std::tuple<int, int, long long> BKey;   // voxel class 1, voxel class 2, pitch in 1e-9 voxel sizes (may differ per axis)
+    typedef std::tuple<int, int, long long> BKey;   // material 1, material 2, pitch in 1e-9 voxel sizes (may differ per axis)
     std::map<BKey, int> bkeys;
     double max_freq2 = 0;
     for (int v1 = 0; v1 < n_vox; v1++) {
@@ -443,7 +442,7 @@ int flatten(const Parsed& P, int variant, int ignore_collisions, vxh_model& M) {
             if (E1 == 0 || E2 == 0) continue;                           // LinkVoxels fails: no bond (VX_Bond.cpp:87)
             if (u1 < 0 || u1 > 0.5 || u2 < 0 || u2 > 0.5) continue;     // (VX_Bond.cpp:88)
             const double pitch = M.nom_pos[3 * v2 + ax] - M.nom_pos[3 * v1 + ax];
-            BKey key(M.vox_class[v1], M.vox_class[v2], llround(pitch / s * 1e9));
+            BKey key(c1.mat_index, c2.mat_index, llround(pitch / s * 1e9));   // bond constants depend on the materials only (not on per-voxel phase)
             auto it = bkeys.find(key);
             if (it == bkeys.end()) {
                 vxg_bond_class b; memset(&b, 0, sizeof b);
@@ -487,7 +486,7 @@ int flatten(const Parsed& P, int variant, int ignore_collisions, vxh_model& M) {
     sp.temp_amplitude = (double)(float)P.temp_amplitude;
     sp.min_scale_fact = P.min_temp_fact;
     sp.max_scale_fact = 1.0 + P.growth_amp;
-    sp.lattice_dim = P.lat; sp.drag_coeff = P.drag;
+    sp.lattice_dim = P.lat; sp.drag_coeff = P.drag; sp.col_horizon = P.col_horizon;
     uint32_t fl = 0;
     if (P.floor_on) fl |= VXG_F_FLOOR;
     if (P.temp_on) fl |= VXG_F_TEMPERATURE;

@@ -169,7 +169,7 @@ class Batch:
 
     def __init__(self, robots: Sequence[abi.HostRobot], device: int = 0, precision: int = abi.VXG_PREC_F32,
                  max_vox: Optional[int] = None, max_vclass: Optional[int] = None, max_bclass: Optional[int] = None,
-                 upload: bool = True):
+                 upload: bool = True, max_col_pairs: Optional[int] = None):
         self.robots: List[abi.HostRobot] = list(robots)
         if not self.robots:
             raise ValueError("empty batch")
@@ -181,6 +181,11 @@ class Batch:
         # land/water fluid drag needs the surface-mesh arrays: size them for the largest mesh of the batch
         if any(r.sim.flags & abi.VXG_F_FLUID for r in self.robots):
             lim.max_mesh_verts = max(lib().vxg_mesh_vertex_count(C.byref(r.desc())) for r in self.robots)
+        # self-collision: room for the contact-bond list (a handful in practice; 4 bytes each in shared memory)
+        if max_col_pairs is not None:
+            lim.max_col_pairs = max_col_pairs
+        elif any(r.sim.flags & abi.VXG_F_COLLISIONS for r in self.robots):
+            lim.max_col_pairs = 512
         self.limits = lim
         self.h = C.c_void_p()
         _ck(lib().vxg_create(C.byref(self.h), device, len(self.robots), C.byref(lim)))

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define VXG_ABI_VERSION 1
+#define VXG_ABI_VERSION 2
 
 /* ---- return codes ------------------------------------------------------------------------------ */
 enum {
@@ -44,7 +44,9 @@ enum {
 #define VXG_F_LW_SCALE     0x0004u /* _voxcad_land_water scale law, LW/VXS_Voxel.cpp:211-235           */
 #define VXG_F_STICKY_FLOOR 0x0008u /* getUsingStickyFloor() VXS_Voxel.cpp:736-739                      */
 #define VXG_F_FLUID        0x0010u /* LW fluid environment: surface drag (LW/VX_Sim.cpp:1516-1597), gravity and floor inert (LW/VXS_Voxel.cpp:357,467) */
-#define VXG_F_COLLISIONS   0x0020u /* VXSFEAT_COLLISIONS: contact bonds given through vxg_set_collision_pairs */
+#define VXG_F_COLLISIONS   0x0020u /* VXSFEAT_COLLISIONS: self-collision contact bonds; the list is rebuilt on the device
+                                      (UpdateCollisions / CalcL1Bonds, VX_Sim.cpp:1729-1755, :2357-2413) unless the host
+                                      supplies it with vxg_set_collision_pairs; needs limits.max_col_pairs > 0          */
 
 /* degrees of freedom, same bit values as the reference (VX_FRegion.h DOF_*) */
 #define VXG_DOF_X  0x01
@@ -125,6 +127,7 @@ typedef struct vxg_sim_params {
     double max_scale_fact;  /* 1 + getGrowthAmplitude()  VXS_Voxel.cpp:225                           */
     double lattice_dim;     /* LocalVXC.GetLatticeDim()                                              */
     double drag_coeff;      /* LW AggregateDragCoefficient (VXG_F_FLUID)                             */
+    double col_horizon;     /* CollisionHorizon (VXG_F_COLLISIONS), in lattice pitches  VX_Sim.cpp:1741, :2357-2385 */
     uint32_t flags;         /* VXG_F_*                                                               */
     uint32_t reserved;
 } vxg_sim_params;
@@ -181,6 +184,7 @@ typedef struct vxg_limits {
 /* status bits written by vxg_sync */
 #define VXG_ST_DIVERGED 0x1u /* a bond strain exceeded 100: Integrate() returned false, VX_Sim.cpp:1775-1777 */
 #define VXG_ST_FINISHED 0x2u /* the robot has run the step budget set with vxg_set_step_budget      */
+#define VXG_ST_COL_OVERFLOW 0x4u /* more contact bonds than limits.max_col_pairs: the robot stopped (never truncated silently) */
 
 /* Per-robot reductions of the voxel state (what CVX_Sim::UpdateStats / the fitness probes read,
  * VX_Sim.cpp:1511-1690, :2415-2441, :2584-2712).  Filled by vxg_reduce_stats. */
@@ -270,8 +274,11 @@ int vxg_struct_sizes(int* out, int n);
  * result writer needs; out is [n_robots]. Synchronous. */
 int vxg_reduce_stats(vxg_batch* b, vxg_robot_stats* out);
 
-/* Replaces: the contact-bond list CVX_Sim::CalcL1Bonds builds (VX_Sim.cpp:2357-2413): n_pairs voxel
- * index pairs (v1, v2) and the composite axial stiffness a1 of each (VXS_BondCollision.cpp:41-59). */
+/* Host-managed contact bonds (seam B2, where CVX_Sim::UpdateCollisions stays on the host): replaces the list
+ * CVX_Sim::CalcL1Bonds builds (VX_Sim.cpp:2357-2413) with n_pairs voxel index pairs (v1, v2) and switches the
+ * device-side rebuild off for this robot.  The contact stiffness is derived from the voxels' classes
+ * (CVX_Bond::LinkVoxels VX_Bond.cpp:90-102: a1 = composite E * mean size); `a1` is accepted for symmetry with
+ * CVXS_BondCollision and may be NULL.  n_pairs < 0 hands the list back to the device. */
 int vxg_set_collision_pairs(vxg_batch* b, int robot, int n_pairs, const int32_t* v1, const int32_t* v2,
                             const double* a1);
 

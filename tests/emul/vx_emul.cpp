@@ -20,7 +20,7 @@ struct EmulBase {
     virtual int diverged() = 0;
 };
 
-template <typename Real, bool COMPACT = false, bool FLUID = false> struct Emul : EmulBase {
+template <typename Real, bool COMPACT = false, bool FLUID = false, bool COLLIDE = false> struct Emul : EmulBase {
     BlobLayout L;
     std::vector<unsigned char> blob;
     std::vector<double> nom, bk_dist, scale_c[2];
@@ -35,6 +35,11 @@ template <typename Real, bool COMPACT = false, bool FLUID = false> struct Emul :
     RobotCtl ctl;
     int cur = 0;
     int div = 0;
+    // self-collision (mirrors the COLLIDE kernel: UpdateCollisions state + CalcL1Bonds tables)
+    std::vector<int16_t> surf; std::vector<int8_t> lat4; std::vector<unsigned long long> near;
+    std::vector<ColPair> pairs;
+    double col_acc = 0, max_vel = 0; bool col_first = true;
+    int n_rebuilds = 0;
 
     Emul(const vxg_robot_desc* d) {
         L = make_layout(stride_for(d->n_vox), (int)sizeof(Real), FLUID ? ((mesh_vertex_count(d) + 31) & ~31) : 0);
@@ -50,6 +55,7 @@ template <typename Real, bool COMPACT = false, bool FLUID = false> struct Emul :
         compact_ok = pack_compact<Real>(d, bkc.data(), &bond_len);
         init_ctl(d, ctl);
         if (FLUID) ctl.n_vert = pack_mesh<Real>(d, L, blob.data());
+        if (COLLIDE && (ctl.flags & VXG_F_COLLISIONS)) pack_collision_tables(d, ctl.col_hops, surf, lat4, near);
         for (int i = 0; i < nvc; i++) dsc_c[0][i] = (Real)(scale_c[0][i] - sk[i].nom_size);
         rec.assign((size_t)39 * L.nv, (Real)0);
         bv1.assign(d->bond_v1, d->bond_v1 + d->n_bond);
@@ -75,6 +81,18 @@ template <typename Real, bool COMPACT = false, bool FLUID = false> struct Emul :
             if (div) break;
             C.scale_c = scale_c[cur].data(); C.dsc_c = dsc_c[cur].data();
             const Real dt_inv = ctl.step == 0 ? (Real)0 : dt_inv_run;
+            const bool col_on = COLLIDE && (ctl.flags & VXG_F_COLLISIONS);
+            if (col_on) {   // UpdateCollisions (VX_Sim.cpp:1729-1755), same order of operations as the kernel
+                col_acc += fabs(max_vel * (ctl.step == 0 ? 0.0 : ctl.dt) / ctl.lattice_dim);
+                if (col_acc > (ctl.col_horizon - 1.0) / 2 || col_first) {
+                    col_first = false; col_acc = 0; n_rebuilds++;
+                    ColTables ct; ct.surf = surf.data(); ct.lat4 = lat4.data(); ct.near = near.data(); ct.n_surf = (int)surf.size(); ct.hops = ctl.col_hops;
+                    const Real hz = (Real)ctl.col_horizon, filt = hz * (Real)1.5 * (Real)ctl.lattice_dim;
+                    pairs.clear();
+                    for (int i = 0; i < ct.n_surf; i++) for (int j = i + 1; j < ct.n_surf; j++)
+                        if (col_pair_hit<Real>(R, C, ct, surf[i], surf[j], hz, filt * filt)) { ColPair p; p.v1 = surf[i]; p.v2 = surf[j]; pairs.push_back(p); }
+                }
+            }
             for (int v = 0; v < ctl.n_vox; v++) { F[v] = mk3<Real>(0, 0, 0); M[v] = mk3<Real>(0, 0, 0); }
             if (C.fluid) {
                 for (int u = 0; u < C.n_vert; u++) mesh_vertex<Real>(R, C, u);
@@ -86,8 +104,12 @@ template <typename Real, bool COMPACT = false, bool FLUID = false> struct Emul :
             for (int v = 0; v < ctl.n_vox; v++) d |= bond_task<Real, 0, COMPACT, FLUID>(R, C, v, R.stat[v], fl[v], dt_inv, F[v], M[v], rec.data());
             for (int v = 0; v < ctl.n_vox; v++) d |= bond_task<Real, 1, COMPACT, FLUID>(R, C, v, R.stat[v], fl[v], dt_inv, F[v], M[v], rec.data());
             for (int v = 0; v < ctl.n_vox; v++) d |= bond_task<Real, 2, COMPACT, FLUID>(R, C, v, R.stat[v], fl[v], dt_inv, F[v], M[v], rec.data());
+            if (col_on && !pairs.empty())
+                for (int v = 0; v < ctl.n_vox; v++) F[v] = F[v] + col_force_on<Real>(R, C, v, R.stat[v], load_own<Real>(R, v), pairs.data(), (int)pairs.size());
             if (d) { div = 1; break; }
-            for (int v = 0; v < ctl.n_vox; v++) voxel_task<Real>(R, C, v, R.stat[v], load_own<Real>(R, v), fl[v], F[v], M[v]);
+            Real sp2 = 0;
+            for (int v = 0; v < ctl.n_vox; v++) { Real x = voxel_task<Real>(R, C, v, R.stat[v], load_own<Real>(R, v), fl[v], F[v], M[v]); if (x > sp2) sp2 = x; }
+            max_vel = sizeof(Real) == 8 ? sqrt((double)sp2) : sqrt((double)(float)sp2);
             for (int i = 0; i < ctl.n_vclass; i++) {
                 double ns = scale_law(sk[i], scale_c[cur][i], ctl.cur_time, ctl.init_cm_time, ctl.temp_period, ctl.temp_amplitude,
                                       ctl.min_fact, ctl.max_fact, temp_on, lw);
@@ -133,6 +155,8 @@ template <typename Real, bool COMPACT = false, bool FLUID = false> struct Emul :
 extern "C" {
 void* vxe_create(const vxg_robot_desc* d, int prec) {
     if (prec == VXG_PREC_F64) return new Emul<double>(d);
+    if (prec == 5) return new Emul<double, false, false, true>(d);   // fp64 with self-collision
+    if (prec == 6) return new Emul<float, false, false, true>(d);    // fp32 with self-collision
     if (prec == 3) return new Emul<float, false, true>(d);    // fp32, land/water layout with the fluid-drag phase
     if (prec == 4) return new Emul<double, false, true>(d);   // fp64, same (logic parity of the drag phase on the CPU)
     if (prec == 2) {   // fp32 with the compact bond table (what the production kernel uses when every class qualifies)

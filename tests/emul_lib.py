@@ -19,7 +19,8 @@ def lib():
     if _LIB is None:
         so = os.path.join(HERE, "_build", "libvxemul.so")
         srcs = [os.path.join(HERE, "emul", "vx_emul.cpp")] + [
-            os.path.join(ROOT, "evosoro_b200", "csrc", f) for f in ("vx_math.cuh", "vx_robot.cuh", "vx_pack.h")]
+            os.path.join(ROOT, "evosoro_b200", "csrc", f) for f in ("vx_math.cuh", "vx_robot.cuh", "vx_pack.h")] + [
+            os.path.join(ROOT, "include", "vxgpu.h")]
         if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(s) for s in srcs):
             os.makedirs(os.path.dirname(so), exist_ok=True)
             subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", so, srcs[0]], check=True)

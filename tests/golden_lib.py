@@ -28,7 +28,13 @@ class Golden:
 
     def robot(self):
         """Descriptor derived from the reference's own imported arrays (independent of the product importer)."""
-        return refdump.desc_from_dump(self.dump, lw=self.lw)
+        import re
+        m = re.search(r"<CollisionHorizon>([^<]+)<", self.vxa_text)
+        return refdump.desc_from_dump(self.dump, lw=self.lw, col_horizon=float(m.group(1)) if m else 2.0)
+
+    @property
+    def collide(self):
+        return bool(self.dump.sim[15])
 
 
 def parse_result(xml: str) -> dict:

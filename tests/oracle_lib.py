@@ -18,8 +18,8 @@ def lib():
     global _LIB
     if _LIB is None:
         so = os.path.join(ORACLE_DIR, "libvxoracle.so")
-        src = os.path.join(ORACLE_DIR, "vx_oracle.c")
-        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        srcs = [os.path.join(ORACLE_DIR, "vx_oracle.c"), os.path.join(ORACLE_DIR, "vx_oracle.h"), os.path.join(ROOT, "include", "vxgpu.h")]
+        if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(s) for s in srcs):
             subprocess.run(["make", "-C", ORACLE_DIR, "oracle"], check=True, stdout=subprocess.DEVNULL)
         L = C.CDLL(so)
         L.vxo_create.restype = C.c_void_p

@@ -97,7 +97,7 @@ def f32(x: float) -> float:
     return float(np.float32(x))
 
 
-def desc_from_dump(d: RefDump, lw: bool = False) -> abi.HostRobot:
+def desc_from_dump(d: RefDump, lw: bool = False, col_horizon: float = 2.0) -> abi.HostRobot:
     """Flat model from the reference's own imported arrays (dump header), constants by closed form:
     CVX_Voxel::SetMaterial VX_Voxel.cpp:109-125, CVX_Bond::LinkVoxels/UpdateConstants VX_Bond.cpp:65-173."""
     S = d.sim
@@ -111,7 +111,9 @@ def desc_from_dump(d: RefDump, lw: bool = False) -> abi.HostRobot:
     sp.min_scale_fact = S[19]
     sp.max_scale_fact = 1.0 + S[20]
     sp.lattice_dim = S[14]
+    sp.col_horizon = col_horizon   # CollisionHorizon is not reachable through the reference's public API: the caller reads it from the .vxa
     flags = 0
+    if S[15]: flags |= abi.VXG_F_COLLISIONS
     if S[7]: flags |= abi.VXG_F_FLOOR
     if S[8]: flags |= abi.VXG_F_TEMPERATURE
     if lw:

@@ -41,7 +41,7 @@ def _run_gpu(rob, prec, frames, every, bonds=True):
 
 
 # ---- (a) golden fixtures, imported by the product importer ---------------------------------------
-@pytest.mark.parametrize("name", [n for n in TRAJ if not n.startswith("lw_fluid")])
+@pytest.mark.parametrize("name", [n for n in TRAJ if not n.startswith("lw_fluid") and not n.startswith("col_")])
 def test_golden_f64_logic_parity(name):
     """P1: fp64 instantiation vs the reference, per-frame state: positions <= 1e-9 pitch."""
     g = golden_lib.Golden(name)
@@ -351,3 +351,56 @@ def test_fluid_robot_needs_mesh_capacity():
     rc = engine.lib().vxg_upload(lim_batch.h, 0, C.byref(d))
     assert rc == 2 and b"max_mesh_verts" in engine.lib().vxg_last_error()
     lim_batch.close()
+
+
+# ---- self-collision: the device-side list rebuild and contact forces -------------------
+def test_collision_list_overflow_is_an_error_not_a_truncation():
+    g = golden_lib.Golden("col_pincer")
+    rob = engine.Model(text=g.vxa_text).robot
+    b = engine.Batch([rob], max_col_pairs=4)      # the pincer needs up to 22 contact bonds
+    b.step(800)
+    st = b.sync()
+    assert st[0] & abi.VXG_ST_COL_OVERFLOW and st[0] & abi.VXG_ST_DIVERGED
+    assert b.stats()[0].steps < 800
+    b.close()
+
+
+def test_collision_state_survives_launch_boundaries():
+    """The contact-bond list, MaxDispSinceLastBondUpdate and MaxVoxVel persist between launches: 800 single-step
+    launches == one 800-step launch, bit for bit, through the contact episode."""
+    g = golden_lib.Golden("col_pincer")
+    rob = engine.Model(text=g.vxa_text).robot
+    b1 = engine.Batch([rob]); b2 = engine.Batch([rob])
+    b1.step(800)
+    for _ in range(16):
+        b2.step(50)
+    b1.sync(); b2.sync()
+    s1, s2 = b1.download(0), b2.download(0)
+    assert np.array_equal(s1.pos, s2.pos) and np.array_equal(s1.quat, s2.quat)
+    assert common.max_abs(s1.pos, g.dump.pos[-1]) <= 2e-5 * LAT
+    b1.close(); b2.close()
+
+
+@needs_ref
+def test_large_folding_robot_with_real_contacts_vs_reference_run(tmp_path):
+    """A 660-voxel robot whose limbs press against each other (over a hundred contact bonds, trajectories with and
+    without collisions differ by ~1 pitch): fp32 kernel with the device-side list vs the unmodified reference
+    with SelfColEnabled=1, 2000 steps.  The input is built here, not copied: two actuated slabs on a
+    passive base plate that fold onto each other."""
+    st = np.zeros((9, 10, 8), dtype=np.int32)
+    st[:, :, 0:2] = 1                       # passive base plate
+    st[0:2, :, 2:] = 3; st[2:4, :, 2:] = 4  # left slab bends right
+    st[5:7, :, 2:] = 4; st[7:9, :, 2:] = 3  # right slab bends left, one empty column between them
+    sim = vxa.SimParams(init_cm_time=0.005, stop_condition_value=0.5, self_col_enabled=1)
+    p = tmp_path / "fold.vxa"
+    p.write_text(vxa.vxa_text(st, sim=sim))
+    d = refdump.run_ref_dump(str(p), str(p) + ".bin", 1000, 250, nocol=False)
+    dn = refdump.run_ref_dump(str(p), str(p) + ".n.bin", 1000, 1000, nocol=True)
+    assert d.frame_hdr[:, 9].max() > 10                                  # contact bonds exist ...
+    assert common.max_abs(d.pos[-1], dn.pos[-1]) > 1e-2 * LAT            # ... and matter
+    rob = engine.Model(path=str(p)).robot
+    b = engine.Batch([rob] * 4)
+    for f in range(1, 5):
+        b.step(250); assert not b.sync().any()
+        assert common.max_abs(b.download(2).pos, d.pos[f]) <= 5e-5 * LAT, f
+    b.close()

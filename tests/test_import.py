@@ -61,7 +61,6 @@ def test_class_deduplication_is_compact():
 
 
 @pytest.mark.parametrize("edit,code", [
-    (lambda t: t.replace("<SelfColEnabled>0", "<SelfColEnabled>1"), 1),
     (lambda t: t.replace("<EquilibriumModeEnabled>0", "<EquilibriumModeEnabled>1"), 1),
     (lambda t: t.replace("<FluidDampEnabled>0</FluidDampEnabled>", "<VolumeEffectsEnabled>1</VolumeEffectsEnabled>"), 1),
     (lambda t: t.replace("<MatModel>0", "<MatModel>2"), 1),
@@ -82,6 +81,8 @@ def test_selfcol_can_be_switched_off_like_enablefeature():
     text = vxa.vxa_text(vxa.dense_lattice(3, 1), sim=vxa.SimParams(self_col_enabled=1))
     m = engine.Model(text=text, ignore_collisions=True)
     assert m.info.self_col_enabled == 1 and not (m.robot.sim.flags & abi.VXG_F_COLLISIONS)
+    m = engine.Model(text=text)
+    assert (m.robot.sim.flags & abi.VXG_F_COLLISIONS) and m.robot.sim.col_horizon == 2.0
 
 
 def test_empty_structure_is_an_error():

@@ -23,7 +23,7 @@ OUT = os.path.join(ROOT, "tests", "golden")
 TMP = "/tmp/vx_golden"
 
 
-def case(name, structure, n_steps, every, sim=None, env=None, palette=None, phase=None, lw=False, full=False):
+def case(name, structure, n_steps, every, sim=None, env=None, palette=None, phase=None, lw=False, full=False, col=False):
     os.makedirs(TMP, exist_ok=True)
     if full:   # the stock CLI writes its result file where <FitnessFileName> says
         sim = sim or vxa.SimParams()
@@ -32,11 +32,11 @@ def case(name, structure, n_steps, every, sim=None, env=None, palette=None, phas
     path = os.path.join(TMP, name + ".vxa")
     with open(path, "w") as f:
         f.write(text)
-    d = refdump.run_ref_dump(path, path + ".bin", n_steps, every, nocol=True, lw=lw)
+    d = refdump.run_ref_dump(path, path + ".bin", n_steps, every, nocol=not col, lw=lw)
     out = dict(vxa=np.frombuffer(text.encode("latin-1"), dtype=np.uint8), lw=np.int32(lw), n_steps=np.int64(n_steps), every=np.int64(every),
                sim=d.sim, vox=d.vox, bond=d.bond, frame_hdr=d.frame_hdr, vstate=d.vstate, bstate=d.bstate)
     if full:
-        f = refdump.run_ref_full(path, path + ".full.bin", nocol=True, lw=lw)
+        f = refdump.run_ref_full(path, path + ".full.bin", nocol=not col, lw=lw)
         out.update(full_hdr=f.frame_hdr, full_vstate=f.vstate[-1], full_tail=f.tail)
         # the unmodified reference CLI (voxelyzeMain/main.cpp) on the same file: its result XML is the P5 pin
         import subprocess
@@ -79,6 +79,23 @@ def main():
     case("lw_dense3_s6", vxa.dense_lattice(3, 6), 1000, 100, sim=S(init_cm_time=0.01, stop_condition_value=0.2), lw=True)
 
 
+def pincer(h=5):
+    """Two actuated pillars on a passive base that bend towards each other: sustained self-contact between voxels
+    that are far apart in the lattice graph (contact bonds, VX_Sim.cpp:2357-2413)."""
+    st = np.zeros((6, 2, h + 1), dtype=np.int32)
+    st[:, :, 0] = 1
+    st[0, :, 1:] = 3; st[1, :, 1:] = 4; st[4, :, 1:] = 4; st[5, :, 1:] = 3
+    return st
+
+
+def collision_cases():
+    S = vxa.SimParams
+    case("col_pincer", pincer(), 800, 50, sim=S(init_cm_time=0.005, stop_condition_value=0.5, self_col_enabled=1), col=True)
+    case("col_pincer_full", pincer(4), 0, 1, sim=S(init_cm_time=0.05, stop_condition_value=0.6, self_col_enabled=1), col=True, full=True)
+    # SelfColEnabled=1 but nothing ever touches: list rebuilds only
+    case("col_dense3", vxa.dense_lattice(3, 31), 600, 100, sim=S(init_cm_time=0.02, stop_condition_value=0.2, self_col_enabled=1), col=True)
+
+
 def fluid_cases():
     """land/water fork in a fluid environment (config 5 of BASELINE.json: surface drag, gravity and floor inert)"""
     S, E = vxa.SimParams, vxa.EnvParams
@@ -92,6 +109,9 @@ def fluid_cases():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "fluid":
         fluid_cases()
+    elif len(sys.argv) > 1 and sys.argv[1] == "col":
+        collision_cases()
     else:
         main()
         fluid_cases()
+        collision_cases()
