@@ -1,0 +1,114 @@
+"""Batched replacement for evosoro's ``evaluate_all`` (evosoro/tools/evaluation.py:18-219).
+
+The reference fires one ``./voxelyze -f <id>.vxa`` subprocess per individual and polls ``fitnessFiles/`` until
+every result file has appeared.  Here the whole population goes to the GPU engine as ONE batch per device
+(``evosoro_b200/lib/voxelyze -f a.vxa -f b.vxa ...``, the drop-in CLI of ``csrc/voxelyze_main.cpp``), which
+writes exactly the per-individual result files the reference's ``read_voxlyze_results`` parses.  Everything
+else -- writing the .vxa files, the md5 cache of already evaluated phenotypes, invalid individuals, objective
+assignment, file bookkeeping -- follows the reference step for step, so ``Optimizer(evaluation_func=...)``
+(evosoro/tools/algorithms.py:15) can take this function unchanged.
+
+Written to run under evosoro's own interpreter as well (Python 2.7 syntax subset, no third-party imports); the
+two evosoro I/O functions are imported lazily from the caller's environment or injected for tests.
+"""
+from __future__ import print_function
+
+import os
+import shutil
+import subprocess as sub
+import time
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+VOXELYZE = os.path.join(_HERE, "lib", "voxelyze")
+
+
+def run_batch(vxa_paths, devices=(0,), voxelyze=VOXELYZE, extra_args=()):
+    """Simulate every .vxa in ``vxa_paths`` (each writes its own <FitnessFileName>): contiguous shards, one CLI
+    process per device, all running concurrently.  Returns the list of exit codes (1 = completed, the
+    reference's convention)."""
+    vxa_paths = list(vxa_paths)
+    if not vxa_paths:
+        return []
+    devices = list(devices) or [0]
+    per = (len(vxa_paths) + len(devices) - 1) // len(devices)
+    procs = []
+    for k, dev in enumerate(devices):
+        shard = vxa_paths[k * per:(k + 1) * per]
+        if not shard:
+            continue
+        cmd = [voxelyze, "--device", str(dev)] + list(extra_args)
+        for p in shard:
+            cmd += ["-f", p]
+        procs.append(sub.Popen(cmd))
+    return [p.wait() for p in procs]
+
+
+def evaluate_all(sim, env, pop, print_log, save_vxa_every, run_directory, run_name, max_eval_time=60,
+                 time_to_try_again=10, save_lineages=False, devices=(0,), io=None):
+    """Same signature and side effects as evosoro.tools.evaluation.evaluate_all (the two timing arguments are
+    accepted and unused: there is nothing to poll for).  ``io`` may carry ``write_voxelyze_file`` and
+    ``read_voxlyze_results``; by default they come from evosoro's own ``read_write_voxelyze`` module."""
+    if io is None:
+        import read_write_voxelyze as io   # evosoro/tools/read_write_voxelyze.py, on the GA's import path
+    start_time = time.time()
+    to_run = []
+
+    for ind in pop:
+        ind.md5 = io.write_voxelyze_file(sim, env, ind, run_directory, run_name)
+        vxa = run_directory + "/voxelyzeFiles/" + run_name + "--id_%05i.vxa" % ind.id
+
+        if not ind.phenotype.is_valid():                                   # evaluation.py:63-68
+            for rank, goal in pop.objective_dict.items():
+                if goal["name"] != "age":
+                    setattr(ind, goal["name"], goal["worst_value"])
+            print_log.message("Skipping invalid individual")
+
+        elif env.actuation_variance == 0 and ind.md5 in pop.already_evaluated:   # evaluation.py:70-80
+            for rank, goal in pop.objective_dict.items():
+                if goal["tag"] is not None:
+                    setattr(ind, goal["name"], pop.already_evaluated[ind.md5][rank])
+            if save_vxa_every > 0 and pop.gen % save_vxa_every == 0:
+                shutil.copy(vxa, run_directory + "/Gen_%04i/" % pop.gen + run_name +
+                            "--Gen_%04i--fit_%.08f--id_%05i.vxa" % (pop.gen, ind.fitness, ind.id))
+        else:                                                              # evaluation.py:82-90
+            pop.total_evaluations += 1
+            to_run.append(ind)
+
+    print_log.message("Launched one batched voxelyze call for {0} out of {1} individuals".format(len(to_run), len(pop)))
+    codes = run_batch([run_directory + "/voxelyzeFiles/" + run_name + "--id_%05i.vxa" % ind.id for ind in to_run], devices)
+    if any(c != 1 for c in codes):
+        print_log.message("WARNING: a voxelyze batch did not complete (exit codes {0}); "
+                          "the min fitness stays assigned for its individuals".format(codes))
+
+    for ind in to_run:                                                     # evaluation.py:128-207
+        result = run_directory + "/fitnessFiles/softbotsOutput--id_%05i.xml" % ind.id
+        vxa = run_directory + "/voxelyzeFiles/" + run_name + "--id_%05i.vxa" % ind.id
+        if not os.path.exists(result):
+            continue
+        objective_values_dict = io.read_voxlyze_results(pop, print_log, result)
+        print_log.message("softbotsOutput--id_%05i.xml fit = %s" % (ind.id, objective_values_dict[0]))
+        os.remove(result)
+        for rank, details in pop.objective_dict.items():
+            if objective_values_dict[rank] is not None:
+                setattr(ind, details["name"], objective_values_dict[rank])
+            else:
+                for name, details_phenotype in ind.genotype.to_phenotype_mapping.items():
+                    if name == details["output_node_name"]:
+                        setattr(ind, details["name"], details["node_func"](details_phenotype["state"]))
+        pop.already_evaluated[ind.md5] = [getattr(ind, details["name"]) for rank, details in pop.objective_dict.items()]
+        pop.all_evaluated_individuals_ids += [ind.id]
+        if ind.fitness > pop.best_fit_so_far:
+            pop.best_fit_so_far = ind.fitness
+            shutil.copy(vxa, run_directory + "/bestSoFar/fitOnly/" + run_name +
+                        "--Gen_%04i--fit_%.08f--id_%05i.vxa" % (pop.gen, ind.fitness, ind.id))
+        if save_lineages:
+            shutil.copy(vxa, run_directory + "/ancestors/")
+        if save_vxa_every > 0 and pop.gen % save_vxa_every == 0:
+            shutil.move(vxa, run_directory + "/Gen_%04i/" % pop.gen + run_name +
+                        "--Gen_%04i--fit_%.08f--id_%05i.vxa" % (pop.gen, ind.fitness, ind.id))
+        else:
+            os.remove(vxa)
+
+    print_log.message("\nAll Voxelyze evals finished in {} seconds".format(time.time() - start_time))
+    print_log.message("num_evaluated_this_gen: {0}".format(len(to_run)))
+    print_log.message("total_evaluations: {}".format(pop.total_evaluations))

@@ -1,0 +1,97 @@
+"""The batched evaluate_all hook (evosoro_b200/evaluation.py) driven the way evosoro's Optimizer drives the
+reference's (evosoro/tools/algorithms.py:15, evaluation.py:18-219), with stand-ins for the GA objects and for
+evosoro's two I/O functions (the package itself is Python 2 and cannot be imported here).  The stand-in reader
+is a line-for-line restatement of read_voxlyze_results (read_write_voxelyze.py:7-37)."""
+import hashlib
+import os
+import types
+
+import numpy as np
+import pytest
+
+import golden_lib
+from evosoro_b200 import evaluation, vxa
+
+
+class Log:
+    def __init__(self): self.lines = []
+    def message(self, s): self.lines.append(s)
+
+
+class Phenotype:
+    def __init__(self, st): self.st = st
+    def is_valid(self): return bool((self.st > 0).any())
+
+
+class Ind:
+    def __init__(self, idx, st):
+        self.id, self.phenotype, self.fitness, self.md5 = idx, Phenotype(st), -1e9, None
+        self.genotype = types.SimpleNamespace(to_phenotype_mapping={})
+
+
+class Pop(list):
+    objective_dict = {0: {"name": "fitness", "tag": "<NormFinalDist>", "worst_value": -1e9, "output_node_name": None, "node_func": None},
+                      1: {"name": "touching", "tag": "<NumTouchingFloor>", "worst_value": 0, "output_node_name": None, "node_func": None}}
+    gen, pop_size, total_evaluations, best_fit_so_far = 0, 0, 0, -1e9
+
+    def __init__(self, inds):
+        super().__init__(inds)
+        self.already_evaluated, self.all_evaluated_individuals_ids = {}, []
+        self.pop_size = len(inds)
+
+
+def make_io(sim_params):
+    def write_voxelyze_file(sim, env, ind, run_directory, run_name):
+        s = vxa.SimParams(**{**sim_params, "fitness_file": run_directory + "/fitnessFiles/softbotsOutput--id_%05i.xml" % ind.id})
+        text = vxa.vxa_text(ind.phenotype.st if ind.phenotype.is_valid() else np.ones((1, 1, 1), dtype=np.int32), sim=s)
+        with open(run_directory + "/voxelyzeFiles/" + run_name + "--id_%05i.vxa" % ind.id, "w") as f:
+            f.write(text)
+        return hashlib.md5(ind.phenotype.st.tobytes()).hexdigest()
+
+    def read_voxlyze_results(population, print_log, filename):
+        results = {rank: None for rank in range(len(population.objective_dict))}
+        for rank, details in population.objective_dict.items():
+            tag = details["tag"]
+            if tag is not None:
+                for line in open(filename):
+                    if tag in line:
+                        results[rank] = float(line[line.find(tag) + len(tag):line.find("</" + tag[1:])])
+        return results
+    return types.SimpleNamespace(write_voxelyze_file=write_voxelyze_file, read_voxlyze_results=read_voxlyze_results)
+
+
+def test_run_batch_with_nothing_to_do():
+    assert evaluation.run_batch([]) == []
+
+
+@pytest.mark.gpu
+def test_evaluate_all_hook_end_to_end(tmp_path):
+    run = str(tmp_path)
+    for d in ("voxelyzeFiles", "fitnessFiles", "bestSoFar/fitOnly", "Gen_0000", "ancestors"):
+        os.makedirs(os.path.join(run, d))
+    g = golden_lib.Golden("dense3_full")
+    import re
+    st = np.zeros((3, 3, 3), dtype=np.int32)
+    layers = re.findall(r"CDATA\[(\d+)\]", g.vxa_text)
+    for z, row in enumerate(layers):
+        for k, ch in enumerate(row):
+            st[k % 3, k // 3, z] = int(ch)
+    inds = [Ind(0, st), Ind(1, vxa.dense_lattice(3, 5)), Ind(2, st.copy()), Ind(3, np.zeros((3, 3, 3), dtype=np.int32))]
+    pop = Pop(inds)
+    env = types.SimpleNamespace(actuation_variance=0)
+    log = Log()
+    io = make_io(dict(init_cm_time=0.05, stop_condition_value=0.25))
+    evaluation.evaluate_all(None, env, pop, log, 0, run, "t", io=io)
+    ref = golden_lib.parse_result(g.result_xml)
+    assert inds[0].fitness == pytest.approx(ref["NormFinalDist"], abs=1e-2)      # same robot as the golden CLI run
+    assert inds[0].touching == ref["NumTouchingFloor"]
+    assert inds[2].fitness == inds[0].fitness                                    # identical phenotype evaluated in the same batch
+    assert inds[3].fitness == -1e9 and "Skipping invalid individual" in log.lines
+    assert inds[1].fitness > -1e9 and pop.total_evaluations == 3
+    assert not os.listdir(os.path.join(run, "fitnessFiles"))                     # result files consumed like the reference does
+    assert len(os.listdir(os.path.join(run, "bestSoFar/fitOnly"))) >= 1
+    # second generation: cached phenotypes are not re-simulated
+    pop2 = Pop([Ind(10, st)])
+    pop2.already_evaluated = pop.already_evaluated
+    evaluation.evaluate_all(None, env, pop2, log, 0, run, "t", io=io)
+    assert pop2[0].fitness == inds[0].fitness and pop2.total_evaluations == 0
