@@ -105,15 +105,13 @@ VX_HD double vx_fsqrt(double x) { return sqrt(x); }
 // num/den < c and num/den > c without the division, with the IEEE outcome for den <= 0 (negative ratio,
 // +-inf, NaN) that the reference's `(abs(z)+abs(y))/x` and `x/NomDistance` tests would have.
 // Written with non-short-circuit predicate logic so that they compile to compare + predicate ops, no branches.
-template <typename T> VX_HD bool ratio_lt(T num, T den, T c) {
-    const T cd = c * den;
-    const bool pos = den > (T)0, neg = den < (T)0;
-    return (pos & (num < cd)) | (neg & (num > cd)) | (!(pos | neg) & (num < (T)0));
+// den == 0 exactly (a bond folded to zero length along its own axis) is not distinguished from den < 0.
+template <typename T> VX_HD bool ratio_lt(T num, T den, T c) {   // num >= 0
+    const bool pos = den > (T)0;
+    return (pos & (num < c * den)) | !pos;      // den < 0: the quotient is negative, hence below any positive bound
 }
-template <typename T> VX_HD bool ratio_gt(T num, T den, T c) {
-    const T cd = c * den;
-    const bool pos = den > (T)0, neg = den < (T)0;
-    return (pos & (num > cd)) | (neg & (num < cd)) | (!(pos | neg) & (num > (T)0));
+template <typename T> VX_HD bool ratio_gt(T num, T den, T c) {   // num >= 0
+    return (den > (T)0) & (num > c * den);      // den < 0: negative quotient, never above a positive bound
 }
 
 // bond axis permutation: the bond is evaluated as if it pointed along +X (VX_Bond.h:45-48)
@@ -178,9 +176,14 @@ template <typename T> VX_HD Q4<T> qmul(Q4<T> a, Q4<T> f) {
 // CQuat::ToRotationVector (Vec3D.h:270-285) in cancellation-free form: the vector part scaled by
 // 2 sqrt(2/(1+w)) (sqrt branch) or 2 atan2(|v|, w)/|v| (acos branch); zero when the vector part is zero or
 // |w| >= 1.  The acos branch (relative rotation above ~5.6 degrees) is rare and kept out of line.
+// theta / |v| for a rotation above ~5.6 degrees (|v| = sin(theta/2) >= 0.049, w = cos(theta/2)): the half angle is
+// asin(|v|) below 45 degrees and acos(w) above, each evaluated where it is well conditioned (both are short
+// polynomial kernels without slow paths, unlike atan2)
+VX_HD float vx_half_angle(float l, float w) { return (w > 0.70710678f) ? asinf(l) : acosf(w < -1.0f ? -1.0f : w); }
+VX_HD double vx_half_angle(double l, double w) { return atan2(l, w); }
 template <typename T> VX_NOINLINE T rotvec_scale_large(T vv, T w) {
     T l = vx_sqrt(vv);
-    return (T)2 * vx_atan2(l, w) / l;
+    return (T)2 * vx_half_angle(l, w) / l;
 }
 template <typename T> VX_HD V3<T> rotvec(Q4<T> q) {
     T vv = q.x * q.x + q.y * q.y + q.z * q.z;
@@ -198,18 +201,20 @@ template <typename T> VX_HD V3<T> rotvec(Q4<T> q) {
 // cos(theta/2) = sqrt((1 + n.x)/2) and sin(theta/2)/(|from| sin(theta)) = 1/(2 |from| cos(theta/2));
 // theta > pi - 1e-7 (Vec3D.h:224)  <=>  cos^2(theta/2) < sin^2(0.5e-7) = 2.5e-15.
 template <typename T> VX_HD Q4<T> from_angle_to_posx(V3<T> from) {
+    // (the reference's early-out for a zero vector, Vec3D.h:210, cannot occur for a bond vector; the clamp below
+    // keeps that state finite instead of testing for it on every bond)
     Q4<T> q; q.w = (T)1; q.x = (T)0; q.y = (T)0; q.z = (T)0;
-    if (from.x == (T)0 && from.y == (T)0 && from.z == (T)0) return q;
     const T sa = (T)VX_SMALL_ANGLE_RAD;
     T ax = vx_abs(from.x);
-    if (from.x != (T)0 && vx_abs(from.y) < sa * ax && vx_abs(from.z) < sa * ax) {
+    if (vx_abs(from.y) < sa * ax && vx_abs(from.z) < sa * ax) {
         T inv = vx_rcp(from.x);
         q.y = (T)0.5 * from.z * inv; q.z = (T)-0.5 * from.y * inv;
         q.w = (T)1 + (T)0.5 * (-q.y * q.y - q.z * q.z);
         return q;
     }
     T rr = from.y * from.y + from.z * from.z;
-    T li = vx_rsqrt(from.x * from.x + rr);
+    T n2 = from.x * from.x + rr;
+    T li = vx_rsqrt(n2 > (T)1e-30 ? n2 : (T)1e-30);
     T c2 = (T)0.5 * ((T)1 + from.x * li);
     if (c2 < (T)2.5e-15) { q.w = 0; q.x = 0; q.y = 1; q.z = 0; return q; }
     T ic = vx_rsqrt(c2);                 // 1 / cos(theta/2)
@@ -325,8 +330,9 @@ VX_HD void bond_force(const BondK<T>& k, V3<T> e_w, Q4<T> q1w, Q4<T> q2w, T dnom
     T turn_num = vx_abs(rr.z) + vx_abs(rr.y);
     bool is_small_w = (q12.w > (T)0) & (vv12 < (T)VX_SIN2_SMALL);
     bool is_smallish_w = (q12.w > (T)0) & (vv12 < (T)VX_SIN2_SMALLISH);
-    bool to_small = !small & is_small_w & ratio_lt<T>(turn_num, rx, (T)VX_SA_BOND_BEND_RAD) & ratio_lt<T>(rx, nom, (T)VX_SA_BOND_EXT_PERC);
-    bool to_large = small & (!is_smallish_w | ratio_gt<T>(turn_num, rx, (T)(VX_HYST * VX_SA_BOND_BEND_RAD)) | ratio_gt<T>(rx, nom, (T)(VX_HYST * VX_SA_BOND_EXT_PERC)));
+    // NomDistance = 0.5 (Scale1 + Scale2) is positive, so the extension tests need no sign handling
+    bool to_small = !small & is_small_w & ratio_lt<T>(turn_num, rx, (T)VX_SA_BOND_BEND_RAD) & (rx < (T)VX_SA_BOND_EXT_PERC * nom);
+    bool to_large = small & (!is_smallish_w | ratio_gt<T>(turn_num, rx, (T)(VX_HYST * VX_SA_BOND_BEND_RAD)) | (rx > (T)(VX_HYST * VX_SA_BOND_EXT_PERC) * nom));
     const bool changed = to_small | to_large;
     small = (small | to_small) & !to_large;
 
