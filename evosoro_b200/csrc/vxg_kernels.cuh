@@ -121,9 +121,9 @@ __device__ inline unsigned int smem_u32(const void* p) { return (unsigned int)__
 __device__ inline void mbar_init(unsigned long long* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ inline void mbar_arrive_warp(unsigned long long* bar) {
+__device__ inline void mbar_arrive_warp(unsigned long long* bar, bool lane0) {
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+    if (lane0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ inline void mbar_wait(unsigned long long* bar, unsigned int parity) {
     asm volatile(
@@ -201,7 +201,8 @@ __global__ void __launch_bounds__(NV / VPT, 1) vx_step_kernel(BatchDev<Real> B, 
     constexpr BlobLayout LC = make_layout(NV, (int)sizeof(Real));
     const BlobLayout L = FLUID ? B.L : LC;   // with the mesh arrays the capacity is a run-time size
     const int robot = blockIdx.x;
-    const int tid = threadIdx.x;
+    int tid;   // read once: an asm the compiler cannot re-materialise (it otherwise re-reads %tid.x ~9x per voxel-step)
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
     RobotCtl* ctlp = B.ctl + robot;
     const unsigned int status0 = ctlp->status;
     if (status0 & (VXG_ST_DIVERGED_ | VXG_ST_FINISHED_)) return;
@@ -360,13 +361,13 @@ __global__ void __launch_bounds__(NV / VPT, 1) vx_step_kernel(BatchDev<Real> B, 
         for (int j = 0; j < VPT; j++) { P[j].w = -1; if (tid + j * T < n_vox) div |= bond_eval<Real, 0, COMPACT, FLUID>(R, C, tid + j * T, st[j], own[j], fl[j], dt_inv, F[j], M[j], rec, P[j]) ? 1 : 0; }
 #pragma unroll
         for (int j = 0; j < VPT; j++) bond_push<Real>(R, P[j]);
-        mbar_arrive_warp(S.mbar);
+        mbar_arrive_warp(S.mbar, (tid & 31) == 0);
 #pragma unroll
         for (int j = 0; j < VPT; j++) { P[j].w = -1; if (tid + j * T < n_vox) div |= bond_eval<Real, 1, COMPACT, FLUID>(R, C, tid + j * T, st[j], own[j], fl[j], dt_inv, F[j], M[j], rec, P[j]) ? 1 : 0; }
         mbar_wait(S.mbar, mpar); mpar ^= 1u;
 #pragma unroll
         for (int j = 0; j < VPT; j++) bond_push<Real>(R, P[j]);
-        mbar_arrive_warp(S.mbar);
+        mbar_arrive_warp(S.mbar, (tid & 31) == 0);
 #pragma unroll
         for (int j = 0; j < VPT; j++) { P[j].w = -1; if (tid + j * T < n_vox) div |= bond_eval<Real, 2, COMPACT, FLUID>(R, C, tid + j * T, st[j], own[j], fl[j], dt_inv, F[j], M[j], rec, P[j]) ? 1 : 0; }
         mbar_wait(S.mbar, mpar); mpar ^= 1u;
