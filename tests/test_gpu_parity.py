@@ -404,3 +404,34 @@ def test_large_folding_robot_with_real_contacts_vs_reference_run(tmp_path):
         b.step(250); assert not b.sync().any()
         assert common.max_abs(b.download(2).pos, d.pos[f]) <= 5e-5 * LAT, f
     b.close()
+
+
+# ---- randomized robots: mixed densities / Poisson ratios / friction, ragged shapes ---------------------
+def _random_robot_text(seed):
+    rng = np.random.RandomState(seed)
+    n = int(rng.randint(3, 7))
+    st = vxa.sparse_lattice(n, seed, fill=float(rng.uniform(0.4, 0.95)))
+    pal = [vxa.Material("m%d" % i, elastic_mod=float(10 ** rng.uniform(6.3, 7.7)), cte=float(rng.choice([0, 0.01, -0.01, 0.02])),
+                        density=float(10 ** rng.uniform(5.7, 6.3)), poisson=float(rng.uniform(0.0, 0.45)),
+                        u_static=float(rng.uniform(0.3, 1.5)), u_dynamic=float(rng.uniform(0.1, 0.8))) for i in range(4)]
+    sim = vxa.SimParams(init_cm_time=0.01, stop_condition_value=0.3, dt_frac=float(rng.uniform(0.5, 0.95)),
+                        bond_damping_z=float(rng.uniform(0.5, 1.0)), slow_damping_z=float(rng.uniform(0.0, 0.05)))
+    env = vxa.EnvParams(temp_period=float(rng.uniform(0.05, 0.3)), growth_amplitude=float(rng.choice([0.0, 0.2])))
+    return vxa.vxa_text(st, palette=pal, sim=sim, env=env)
+
+
+def test_randomized_population_vs_c_oracle():
+    """48 random robots in ONE ragged batch (3^3..6^3 sparse shapes, 4 random materials each with different
+    densities -- so Force2 != -Force1 --, Poisson ratios, friction, damping, dt fractions, actuation periods):
+    every robot within 2e-5 pitch of the fp64 C oracle after 1500 steps."""
+    robots = [engine.Model(text=_random_robot_text(1000 + s)).robot for s in range(48)]
+    b = engine.Batch(robots)
+    b.step(1500)
+    assert not b.sync().any()
+    worst = 0.0
+    for r, rob in enumerate(robots):
+        o = oracle_lib.OracleSim(rob)
+        o.step(1500)
+        worst = max(worst, common.max_abs(b.download(r).pos, o.state().pos) / LAT)
+    assert worst <= 2e-5, worst
+    b.close()
