@@ -14,6 +14,11 @@
  * plasticity, no max-velocity clamp, no equilibrium mode).  The land/water fork's scale law
  * (evosoro/_voxcad_land_water/Voxelyze/VXS_Voxel.cpp:211-235) is selected by VXG_F_LW_SCALE.
  *
+ * Also restated (fp64, reference order of operations):
+ *   CVX_Sim::UpdateCollisions / CalcL1Bonds, CVX_Voxel::CalcNearby   VX_Sim.cpp:1729-1755, :2357-2413; VX_Voxel.cpp:171-209
+ *   land/water fluid drag: CVX_MeshUtil::LinkSimVoxels / GetCurVLoc, CMesh::CalcFaceNormals, the facet loop
+ *       evosoro/_voxcad_land_water/Voxelyze/VX_MeshUtil.cpp:110-276, :388-428; Utils/Mesh.cpp:659-665; VX_Sim.cpp:1516-1597
+ *
  * Not part of the product: nothing under evosoro_b200/ or include/ references this file.
  */
 #include "vx_oracle.h"
@@ -55,6 +60,21 @@ struct vxo_sim {
     double cur_time, dt;
     int64_t step;
     int diverged;
+    /* self-collision (UpdateCollisions state) */
+    int col_auto;               /* the list is rebuilt here (no vxo_set_collision_pairs call) */
+    int col_first;              /* ColEnableChanged */
+    double col_acc, max_vel;    /* MaxDispSinceLastBondUpdate, SS.MaxVoxVel */
+    int* ijk;                   /* lattice coordinates [n_vox][3] */
+    int *near_off, *near_idx;   /* CalcNearby lists (CSR) */
+    int* surf; int n_surf;      /* SurfVoxels */
+    /* land/water fluid drag */
+    v3 *sp, *sn;                /* StrainPosDirsCur / StrainNegDirsCur */
+    v3 *cpos, *cneg;            /* CornerPosCur / CornerNegCur */
+    v3* drag;                   /* DragForce */
+    int n_vert, n_facet;
+    int* vert_off; int* vert_vox; int* vert_corner;   /* CalcVerts[].ConVoxels (voxel, corner code) */
+    int* facet_v; int* facet_owner;                   /* DefMesh.Facets[].vi[3], FacetToSIndex */
+    v3* vpos;
     double small_w, smallish_w, slthresh;
 };
 
@@ -140,6 +160,9 @@ static v3 to_origdir(int ax, v3 v) {
     return v;
 }
 
+#define AL(T, n) (T*)calloc((size_t)((n) > 0 ? (n) : 1), sizeof(T))
+static void build_topology(vxo_sim* s);
+
 vxo_sim* vxo_create(const vxg_robot_desc* d) {
     vxo_sim* s = (vxo_sim*)calloc(1, sizeof(vxo_sim));
     int nv = d->n_vox, nb = d->n_bond;
@@ -149,7 +172,6 @@ vxo_sim* vxo_create(const vxg_robot_desc* d) {
     s->bc = (vxg_bond_class*)malloc(sizeof(vxg_bond_class) * (size_t)(d->n_bclass > 0 ? d->n_bclass : 1));
     memcpy(s->vc, d->vclasses, sizeof(vxg_vox_class) * (size_t)d->n_vclass);
     if (d->n_bclass) memcpy(s->bc, d->bclasses, sizeof(vxg_bond_class) * (size_t)d->n_bclass);
-#define AL(T, n) (T*)calloc((size_t)((n) > 0 ? (n) : 1), sizeof(T))
     s->vcls = AL(int, nv); s->bv1 = AL(int, nb); s->bv2 = AL(int, nb); s->bax = AL(int, nb); s->bcls = AL(int, nb);
     s->link = (int(*)[6])calloc((size_t)(nv > 0 ? nv : 1), sizeof(int[6]));
     s->nom = AL(v3, nv); s->pos = AL(v3, nv); s->linmom = AL(v3, nv); s->angmom = AL(v3, nv); s->ang = AL(q4, nv);
@@ -177,7 +199,187 @@ vxo_sim* vxo_create(const vxg_robot_desc* d) {
     s->smallish_w = cos(HYST * SMALL_ANGLE_RAD * 0.5);
     s->slthresh = 1.0 - W_THRESH_ACOS2SQRT * W_THRESH_ACOS2SQRT;
     s->cur_time = 0; s->dt = 0; s->step = 0; /* ClearAll VX_Sim.cpp:373, ResetSimulation :853-854 */
+    s->col_auto = 1; s->col_first = 1;         /* ColEnableChanged = true  VX_Sim.cpp:50 */
+    build_topology(s);
     return s;
+}
+
+
+/* ---- lattice topology: CalcNearby lists, surface voxels, the land/water surface mesh ------------------ */
+static int find_vox(const vxo_sim* s, int x, int y, int z) {
+    for (int i = 0; i < s->n_vox; i++) if (s->ijk[3 * i] == x && s->ijk[3 * i + 1] == y && s->ijk[3 * i + 2] == z) return i;
+    return -1;
+}
+static void build_topology(vxo_sim* s) {
+    int nv = s->n_vox;
+    /* lattice coordinates from the nominal positions (cell centres at (i + 0.5) * pitch, VX_Object.cpp:543) */
+    double pitch[3] = {0, 0, 0};
+    for (int j = 0; j < s->n_bond; j++) { double p = s->bc[s->bcls[j]].nom_dist; int a = s->bax[j]; if (p > 0 && (pitch[a] == 0 || p < pitch[a])) pitch[a] = p; }
+    for (int a = 0; a < 3; a++) if (!(pitch[a] > 0)) pitch[a] = s->vc[s->vcls[0]].nom_size;
+    s->ijk = AL(int, 3 * nv);
+    for (int i = 0; i < nv; i++) {
+        s->ijk[3 * i] = (int)floor(s->nom[i].x / pitch[0]); s->ijk[3 * i + 1] = (int)floor(s->nom[i].y / pitch[1]); s->ijk[3 * i + 2] = (int)floor(s->nom[i].z / pitch[2]);
+    }
+    /* SurfVoxels (VX_Sim.cpp:675-680, IsSurfaceVoxel VX_Voxel.h:80) and CalcNearby(NumHops = (int)(CollisionHorizon*1.5)) */
+    s->surf = AL(int, nv); s->n_surf = 0;
+    for (int i = 0; i < nv; i++) { int n = 0; for (int k = 0; k < 6; k++) n += s->link[i][k] >= 0; if (n < 6) s->surf[s->n_surf++] = i; }
+    int hops = (int)(s->sim.col_horizon * 1.5);
+    s->near_off = AL(int, nv + 1);
+    int cap = 64, used = 0;
+    s->near_idx = AL(int, cap);
+    int* list = AL(int, nv);
+    for (int i = 0; i < nv; i++) {                                       /* VX_Voxel.cpp:171-209 */
+        int n = 0, start = 0, stop = 1;
+        list[n++] = i;
+        for (int h = 0; h < hops; h++) {
+            for (int j = start; j < stop; j++) {
+                int v = list[j];
+                for (int k = 0; k < 6; k++) {
+                    int b = s->link[v][k];
+                    if (b < 0) continue;
+                    int o = (k % 2) ? s->bv1[b] : s->bv2[b];
+                    int seen = 0; for (int q = 0; q < n; q++) if (list[q] == o) { seen = 1; break; }
+                    if (!seen) list[n++] = o;
+                }
+            }
+            start = stop; stop = n;
+        }
+        while (used + n > cap) { cap *= 2; s->near_idx = (int*)realloc(s->near_idx, sizeof(int) * (size_t)cap); }
+        s->near_off[i] = used;
+        memcpy(s->near_idx + used, list, sizeof(int) * (size_t)n);
+        used += n;
+    }
+    s->near_off[nv] = used;
+    free(list);
+    /* fluid state */
+    s->sp = AL(v3, nv); s->sn = AL(v3, nv); s->cpos = AL(v3, nv); s->cneg = AL(v3, nv); s->drag = AL(v3, nv);
+    for (int i = 0; i < nv; i++) { double h = s->scale[i] / 2; s->cpos[i] = V(h, h, h); s->cneg[i] = V(-h, -h, -h); }   /* LW ResetVoxel :106-107 */
+    if (!(s->sim.flags & VXG_F_FLUID)) return;
+    /* CVX_MeshUtil::LinkSimVoxels (LW/VX_MeshUtil.cpp:110-276) */
+    int lo[3] = {1 << 30, 1 << 30, 1 << 30}, hi[3] = {-(1 << 30), -(1 << 30), -(1 << 30)};
+    for (int i = 0; i < nv; i++) for (int a = 0; a < 3; a++) { int c = s->ijk[3 * i + a]; if (c < lo[a]) lo[a] = c; if (c > hi[a]) hi[a] = c; }
+    int tx = hi[0] - lo[0] + 2, ty = hi[1] - lo[1] + 2, tz = hi[2] - lo[2] + 2;
+    int ngrid = tx * ty * tz;
+    int* cnt = AL(int, ngrid);
+    for (int i = 0; i < nv; i++) for (int c = 0; c < 8; c++) {
+        int gx = s->ijk[3 * i] - lo[0] + ((c >> 2) & 1), gy = s->ijk[3 * i + 1] - lo[1] + ((c >> 1) & 1), gz = s->ijk[3 * i + 2] - lo[2] + (c & 1);
+        cnt[(gz * ty + gy) * tx + gx]++;
+    }
+    int* map = AL(int, ngrid);
+    s->n_vert = 0;
+    for (int g = 0; g < ngrid; g++) map[g] = (cnt[g] != 0 && cnt[g] != 8) ? s->n_vert++ : -1;   /* :249-262 */
+    s->vert_off = AL(int, s->n_vert + 1);
+    int tot = 0;
+    for (int g = 0; g < ngrid; g++) if (map[g] >= 0) { s->vert_off[map[g]] = tot; tot += cnt[g]; }
+    s->vert_off[s->n_vert] = tot;
+    s->vert_vox = AL(int, tot); s->vert_corner = AL(int, tot);
+    int* fill = AL(int, s->n_vert);
+    for (int i = 0; i < nv; i++) for (int c = 0; c < 8; c++) {             /* ConVoxels in simulation-index order :131-144 */
+        int gx = s->ijk[3 * i] - lo[0] + ((c >> 2) & 1), gy = s->ijk[3 * i + 1] - lo[1] + ((c >> 1) & 1), gz = s->ijk[3 * i + 2] - lo[2] + (c & 1);
+        int u = map[(gz * ty + gy) * tx + gx];
+        if (u < 0) continue;
+        int at = s->vert_off[u] + fill[u]++;
+        s->vert_vox[at] = i; s->vert_corner[at] = c;
+    }
+    /* facets: per voxel, open faces +X,-X,+Y,-Y,+Z,-Z, two triangles each, vertex order of :161-190 */
+    static const int T1[6][3] = {{4, 6, 7}, {0, 3, 2}, {2, 3, 7}, {0, 5, 1}, {1, 5, 7}, {0, 6, 4}};
+    static const int T2[6][3] = {{4, 7, 5}, {0, 1, 3}, {2, 7, 6}, {0, 4, 5}, {1, 7, 3}, {0, 2, 6}};
+    static const int D[6][3] = {{1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
+    s->facet_v = AL(int, 3 * 12 * nv); s->facet_owner = AL(int, 12 * nv); s->n_facet = 0;
+    for (int i = 0; i < nv; i++) for (int f = 0; f < 6; f++) {
+        if (find_vox(s, s->ijk[3 * i] + D[f][0], s->ijk[3 * i + 1] + D[f][1], s->ijk[3 * i + 2] + D[f][2]) >= 0) continue;
+        for (int t = 0; t < 2; t++) {
+            const int* tri = t ? T2[f] : T1[f];
+            for (int k = 0; k < 3; k++) {
+                int c = tri[k];
+                int gx = s->ijk[3 * i] - lo[0] + ((c >> 2) & 1), gy = s->ijk[3 * i + 1] - lo[1] + ((c >> 1) & 1), gz = s->ijk[3 * i + 2] - lo[2] + (c & 1);
+                s->facet_v[3 * s->n_facet + k] = map[(gz * ty + gy) * tx + gx];
+            }
+            s->facet_owner[s->n_facet++] = i;
+        }
+    }
+    s->vpos = AL(v3, s->n_vert);
+    free(cnt); free(map); free(fill);
+}
+
+/* CQuat::RotateVec3D  Vec3D.h:293-299 */
+static v3 qrot(q4 q, v3 f) {
+    double fx = f.x, fy = f.y, fz = f.z;
+    double tw = fx * q.x + fy * q.y + fz * q.z;
+    double tx = fx * q.w - fy * q.z + fz * q.y;
+    double ty = fx * q.z + fy * q.w - fz * q.x;
+    double tz = -fx * q.y + fy * q.x + fz * q.w;
+    return V(q.w * tx + q.x * tw + q.y * tz - q.z * ty, q.w * ty - q.x * tz + q.y * tw + q.z * tx, q.w * tz + q.x * ty - q.y * tx + q.z * tw);
+}
+
+/* the fluid block of LW CVX_Sim::Integrate (LW/VX_Sim.cpp:1516-1597) */
+static void fluid_drag(vxo_sim* s) {
+    for (int i = 0; i < s->n_vox; i++) s->drag[i] = V(0, 0, 0);
+    for (int u = 0; u < s->n_vert; u++) {                                  /* UpdateMeshPhysicsOnlyNoColors -> GetCurVLoc :388-428 */
+        v3 avg = V(0, 0, 0); double totw = 0;
+        for (int k = s->vert_off[u]; k < s->vert_off[u + 1]; k++) {
+            int i = s->vert_vox[k], c = s->vert_corner[k];
+            v3 off = V((c & 4) ? s->cpos[i].x : s->cneg[i].x, (c & 2) ? s->cpos[i].y : s->cneg[i].y, (c & 1) ? s->cpos[i].z : s->cneg[i].z);
+            v3 p = vadd(s->pos[i], qrot(s->ang[i], off));
+            avg = vadd(avg, vscale(p, 1.0)); totw += 1.0;
+        }
+        s->vpos[u] = vdiv(avg, totw);
+    }
+    for (int f = 0; f < s->n_facet; f++) {
+        v3 A = s->vpos[s->facet_v[3 * f]], B = s->vpos[s->facet_v[3 * f + 1]], C = s->vpos[s->facet_v[3 * f + 2]];
+        v3 AB = vsub(B, A), AC = vsub(C, A);
+        v3 cr = V(AB.y * AC.z - AB.z * AC.y, AB.z * AC.x - AB.x * AC.z, AB.x * AC.y - AB.y * AC.x);
+        double crl = sqrt(cr.x * cr.x + cr.y * cr.y + cr.z * cr.z);
+        double area = fabs(crl / 2.0);
+        v3 n = crl > 0 ? vdiv(cr, crl) : cr;                               /* CalcFaceNormals: Normalized() */
+        int i = s->facet_owner[f];
+        v3 vel = vscale(s->linmom[i], s->vc[s->vcls[i]].mass_inv);         /* GetCurVel() */
+        double vl = sqrt(vel.x * vel.x + vel.y * vel.y + vel.z * vel.z);
+        v3 vn = vl > 0 ? vdiv(vel, vl) : vel;
+        double nl = sqrt(n.x * n.x + n.y * n.y + n.z * n.z);
+        v3 nn = nl > 0 ? vdiv(n, nl) : n;
+        float ang = (float)acos(vn.x * nn.x + vn.y * nn.y + vn.z * nn.z);  /* `float speedNormalAngle` :1563 */
+        v3 proj = V(0, 0, 0);
+        if (fabs(ang) < PI_REF / 2) proj = vscale(nn, vel.x * n.x + vel.y * n.y + vel.z * n.z);   /* ProjectOnTo Vec3D.h:142 */
+        double pl2 = proj.x * proj.x + proj.y * proj.y + proj.z * proj.z, pl = sqrt(pl2);
+        v3 pn = pl > 0 ? vdiv(proj, pl) : proj;
+        v3 d = vscale(pn, -(double)(float)s->sim.drag_coeff * area * pl2);  /* `float aggregateDragCoefficient` */
+        s->drag[i] = vadd(s->drag[i], d);
+    }
+}
+
+/* CVX_Sim::UpdateCollisions + CalcL1Bonds (VX_Sim.cpp:1729-1755, :2357-2413) */
+static void update_collisions(vxo_sim* s) {
+    double H = s->sim.col_horizon, lat = s->sim.lattice_dim;
+    s->col_acc += fabs(s->max_vel * s->dt / lat);
+    if (!(s->col_acc > (H - 1.0) / 2 || s->col_first)) return;
+    s->col_first = 0; s->col_acc = 0.0;
+    double filt = H * 1.5 * lat, filt2 = filt * filt;
+    int cap = 64, n = 0;
+    int* v1 = AL(int, cap); int* v2 = AL(int, cap); double* a1 = AL(double, cap);
+    for (int i = 0; i < s->n_surf; i++) {
+        int s1 = s->surf[i];
+        for (int j = i + 1; j < s->n_surf; j++) {
+            int s2 = s->surf[j];
+            v3 d = vsub(s->pos[s1], s->pos[s2]);
+            double d2 = d.x * d.x + d.y * d.y + d.z * d.z;
+            if (!(d2 < filt2)) continue;
+            int nearby = 0;
+            for (int q = s->near_off[s1]; q < s->near_off[s1 + 1]; q++) if (s->near_idx[q] == s2) { nearby = 1; break; }
+            if (nearby) continue;
+            double act = H * (s->scale[s1] + s->scale[s1]) * 0.5;          /* voxel 1's scale twice :2382 */
+            if (!(d2 < act * act)) continue;
+            /* CreateColBond -> CVX_Bond::LinkVoxels / UpdateConstants: a1 = E A / L */
+            const vxg_vox_class* c1 = &s->vc[s->vcls[s1]]; const vxg_vox_class* c2 = &s->vc[s->vcls[s2]];
+            double E1 = c1->e_mod, E2 = c2->e_mod;
+            if (E1 == 0 || E2 == 0) continue;
+            double E = (E1 * E2 / (E1 + E2)) * 2, L = (c1->nom_size + c2->nom_size) * 0.5;
+            if (n == cap) { cap *= 2; v1 = (int*)realloc(v1, sizeof(int) * (size_t)cap); v2 = (int*)realloc(v2, sizeof(int) * (size_t)cap); a1 = (double*)realloc(a1, sizeof(double) * (size_t)cap); }
+            v1[n] = s1; v2[n] = s2; a1[n] = E * (L * L) / L; n++;
+        }
+    }
+    free(s->cv1); free(s->cv2); free(s->ca1); free(s->cf1); free(s->cf2);
+    s->n_col = n; s->cv1 = v1; s->cv2 = v2; s->ca1 = a1; s->cf1 = AL(v3, n); s->cf2 = AL(v3, n);
 }
 
 void vxo_destroy(vxo_sim* s) {
@@ -186,12 +388,14 @@ void vxo_destroy(vxo_sim* s) {
     free(s->nom); free(s->pos); free(s->linmom); free(s->angmom); free(s->ang); free(s->scale); free(s->last_scale);
     free(s->sfric); free(s->small); free(s->lp2); free(s->la1); free(s->la2); free(s->f1); free(s->f2); free(s->m1);
     free(s->m2); free(s->strain); free(s->cv1); free(s->cv2); free(s->ca1); free(s->cf1); free(s->cf2);
+    free(s->ijk); free(s->near_off); free(s->near_idx); free(s->surf); free(s->sp); free(s->sn); free(s->cpos); free(s->cneg);
+    free(s->drag); free(s->vert_off); free(s->vert_vox); free(s->vert_corner); free(s->facet_v); free(s->facet_owner); free(s->vpos);
     free(s);
 }
 
 void vxo_set_collision_pairs(vxo_sim* s, int n, const int32_t* v1, const int32_t* v2, const double* a1) {
     free(s->cv1); free(s->cv2); free(s->ca1); free(s->cf1); free(s->cf2);
-    s->n_col = n;
+    s->n_col = n; s->col_auto = 0;   /* host-managed list: no rebuild here */
     s->cv1 = AL(int, n); s->cv2 = AL(int, n); s->ca1 = AL(double, n); s->cf1 = AL(v3, n); s->cf2 = AL(v3, n);
     for (int i = 0; i < n; i++) { s->cv1[i] = v1[i]; s->cv2[i] = v2[i]; s->ca1[i] = a1[i]; }
 }
@@ -231,9 +435,9 @@ static void bond_update(vxo_sim* s, int j) {
     /* UpdateBondStrain(_Pos2.x/L.x)  :120, :189-307 with MDL_LINEAR stress (VX_Object.cpp:1472-1482) */
     double strain = p2.x / c->len, stress;
     s->strain[j] = strain;
+    double sv1 = strain, sv2 = strain;                                  /* CurStrainV1 = CurStrainV2 = CurStrainIn :208 */
     if (c->homogeneous) stress = c->e1 * strain;                        /* :206 */
     else {                                                              /* :226-258 */
-        double sv1 = strain, sv2 = strain;
         double st1 = c->e1 * sv1, st2 = c->e2 * sv2;
         int count = 0;
         double diff = (st1 >= st2) ? st1 - st2 : st2 - st1;
@@ -247,6 +451,10 @@ static void bond_update(vxo_sim* s, int j) {
             count++;
         }
         stress = (st1 + st2) / 2;
+    }
+    {   /* SetStrainDir(BD_P<axis>, CurStrainV1) / (BD_N<axis>, CurStrainV2)  :300-304 */
+        int v1 = s->bv1[j], v2 = s->bv2[j], a = s->bax[j];
+        if (a == 0) { s->sp[v1].x = sv1; s->sn[v2].x = sv2; } else if (a == 1) { s->sp[v1].y = sv1; s->sn[v2].y = sv2; } else { s->sp[v1].z = sv1; s->sn[v2].z = sv2; }
     }
 
     /* beam equations :127-128, :153-154  (CSArea1 == CSArea2 == s^2: VXS_Voxel.cpp:625-631, VXS_Bond.cpp:72) */
@@ -334,6 +542,7 @@ static void voxel_step(vxo_sim* s, int i) {
         F = vsub(F, V(0, 0, 0));                                        /* InputForce :531 */
         if (!(P->flags & VXG_F_FLUID)) F.z += c->mass * P->grav_acc;    /* :536 (grav_acc == 0 when disabled) */
         F = vadd(F, V(c->ext_force[0], c->ext_force[1], c->ext_force[2])); /* :540 */
+        if (P->flags & VXG_F_FLUID) F = vadd(F, s->drag[i]);            /* LW/VXS_Voxel.cpp:370-371 */
         if ((P->flags & VXG_F_FLOOR) && !(P->flags & VXG_F_FLUID)) {    /* :635-639, CalcFloorEffect :708-758 */
             v3 FF = V(0, 0, 0);
             s->sfric[i] = 0;
@@ -358,6 +567,12 @@ static void voxel_step(vxo_sim* s, int i) {
             }
             F = vadd(F, FF);
             if (s->sfric[i]) { F.x = 0; F.y = 0; }
+        }
+        {   /* corner extents for the surface mesh, LW/VXS_Voxel.cpp:474-475 */
+            double hs = c->nom_size / 2;
+            s->cpos[i] = V((1 + s->sp[i].x) * c->nom_size / 2, (1 + s->sp[i].y) * c->nom_size / 2, (1 + s->sp[i].z) * c->nom_size / 2);
+            s->cneg[i] = V(-(1 + s->sn[i].x) * c->nom_size / 2, -(1 + s->sn[i].y) * c->nom_size / 2, -(1 + s->sn[i].z) * c->nom_size / 2);
+            (void)hs;
         }
         /* :184-197 */
         s->linmom[i] = vadd(s->linmom[i], vscale(F, dt));
@@ -429,6 +644,7 @@ int64_t vxo_step(vxo_sim* s, int64_t n) {
     int64_t k;
     for (k = 0; k < n; k++) {
         if (s->diverged) break;
+        if ((s->sim.flags & VXG_F_COLLISIONS) && s->col_auto) update_collisions(s);   /* TimeStep: VX_Sim.cpp:1131-1134 */
         int div = 0;
         for (int j = 0; j < s->n_bond; j++) {                           /* VX_Sim.cpp:1773-1776 */
             bond_update(s, j);
@@ -437,7 +653,13 @@ int64_t vxo_step(vxo_sim* s, int64_t n) {
         if (div) { s->diverged = 1; break; }
         if (s->sim.flags & VXG_F_COLLISIONS) for (int c = 0; c < s->n_col; c++) col_update(s, c); /* :1786-1788 */
         s->dt = s->sim.dt;                                              /* :1793 */
+        if (s->sim.flags & VXG_F_FLUID) fluid_drag(s);                  /* LW/VX_Sim.cpp:1516-1597 */
         for (int i = 0; i < s->n_vox; i++) voxel_step(s, i);           /* :1913 */
+        {   /* SS.MaxVoxVel (UpdateStats VX_Sim.cpp:1626-1649) */
+            double m2 = 0;
+            for (int i = 0; i < s->n_vox; i++) { v3 v = vscale(s->linmom[i], s->vc[s->vcls[i]].mass_inv); double l2 = v.x * v.x + v.y * v.y + v.z * v.z; if (l2 > m2) m2 = l2; }
+            s->max_vel = sqrt(m2);
+        }
         s->cur_time += s->dt;                                           /* :1929 */
         s->step++;
     }
