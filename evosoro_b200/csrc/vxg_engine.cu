@@ -124,15 +124,15 @@ template <typename Real, bool SMEM, bool COMPACT> static cudaError_t launch_step
     return cudaErrorInvalidValue;
 }
 
-// land/water layouts (surface-mesh arrays): fp32, shared-memory resident, wide bond table
-static cudaError_t launch_step_fluid(vxg_batch* b, int n_steps, int record) {
+// land/water layouts (surface-mesh arrays): fp32, shared-memory resident, wide bond table; with or without self-collision
+template <bool COLLIDE> static cudaError_t launch_step_fluid(vxg_batch* b, int n_steps, int record) {
     switch (b->L.nv) {
-        case 64: return launch_step<float, 64, 1, true, false, true>(b, n_steps, record);
-        case 128: return launch_step<float, 128, 1, true, false, true>(b, n_steps, record);
-        case 256: return launch_step<float, 256, 1, true, false, true>(b, n_steps, record);
-        case 512: return launch_step<float, 512, 1, true, false, true>(b, n_steps, record);
-        case 1024: return launch_step<float, 1024, 2, true, false, true>(b, n_steps, record);
-        case 2048: return launch_step<float, 2048, 4, true, false, true>(b, n_steps, record);
+        case 64: return launch_step<float, 64, 1, true, false, true, COLLIDE>(b, n_steps, record);
+        case 128: return launch_step<float, 128, 1, true, false, true, COLLIDE>(b, n_steps, record);
+        case 256: return launch_step<float, 256, 1, true, false, true, COLLIDE>(b, n_steps, record);
+        case 512: return launch_step<float, 512, 1, true, false, true, COLLIDE>(b, n_steps, record);
+        case 1024: return launch_step<float, 1024, 2, true, false, true, COLLIDE>(b, n_steps, record);
+        case 2048: return launch_step<float, 2048, 4, true, false, true, COLLIDE>(b, n_steps, record);
     }
     return cudaErrorInvalidValue;
 }
@@ -152,7 +152,7 @@ static cudaError_t launch_step_collide(vxg_batch* b, int n_steps, int record) {
 
 // The compact bond table exists for the production path only (fp32, shared-memory resident).
 static cudaError_t launch_step_p(vxg_batch* b, int n_steps, int record) {
-    if (b->L.nvert_cap > 0) return launch_step_fluid(b, n_steps, record);
+    if (b->L.nvert_cap > 0) return b->lim.max_col_pairs > 0 ? launch_step_fluid<true>(b, n_steps, record) : launch_step_fluid<false>(b, n_steps, record);
     if (b->lim.max_col_pairs > 0) return launch_step_collide(b, n_steps, record);
     if (b->prec == VXG_PREC_F64)
         return b->smem_mode ? launch_step_s<double, true, false>(b, n_steps, record) : launch_step_s<double, false, false>(b, n_steps, record);
@@ -206,9 +206,7 @@ extern "C" int vxg_create(vxg_batch** out, int device, int n_robots, const vxg_l
     b->tb_compact = tables_bytes<float>(lim->max_vclass, lim->max_bclass, true, mc);
     b->smem_wide_fits = b->L.total_bytes + tb <= (size_t)max_smem;
     b->smem_mode_wide_or_compact = b->prec == VXG_PREC_F32 && b->L.total_bytes + b->tb_compact <= (size_t)max_smem;
-    if (mc > 0 && (lim->precision != VXG_PREC_F32 || lim->max_mesh_verts > 0)) {
-        delete b; return fail(VXG_UNSUPPORTED_FEATURE, "vxg_create: the self-collision kernels exist in fp32 without fluid drag only");
-    }
+    if (mc > 0 && lim->precision != VXG_PREC_F32) { delete b; return fail(VXG_UNSUPPORTED_FEATURE, "vxg_create: the self-collision kernels exist in fp32 only"); }
     if (mc > 0 || b->L.nvert_cap > 0) {   // these layouts run shared-memory resident with the wide table only
         b->smem_mode_wide_or_compact = false;
         if (!b->smem_wide_fits) { delete b; return fail(VXG_UNSUPPORTED_SIZE, "vxg_create: robot blob with collision list / surface mesh (%zu B) exceeds shared memory", b->L.total_bytes + tb); }

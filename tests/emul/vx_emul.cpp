@@ -155,6 +155,8 @@ template <typename Real, bool COMPACT = false, bool FLUID = false, bool COLLIDE 
 extern "C" {
 void* vxe_create(const vxg_robot_desc* d, int prec) {
     if (prec == VXG_PREC_F64) return new Emul<double>(d);
+    if (prec == 7) return new Emul<double, false, true, true>(d);    // fp64, land/water drag + self-collision
+    if (prec == 8) return new Emul<float, false, true, true>(d);     // fp32, same
     if (prec == 5) return new Emul<double, false, false, true>(d);   // fp64 with self-collision
     if (prec == 6) return new Emul<float, false, false, true>(d);    // fp32 with self-collision
     if (prec == 3) return new Emul<float, false, true>(d);    // fp32, land/water layout with the fluid-drag phase

@@ -19,7 +19,7 @@ from evosoro_b200 import abi
 LAT = 0.01
 CASES = [n for n in golden_lib.names() if not n.endswith("_full")]
 FLUID = lambda n: n.startswith("lw_fluid")
-COLLIDE = lambda n: n.startswith("col_")
+COLLIDE = lambda n: "col_" in n
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -29,7 +29,7 @@ def test_emulated_f64_kernel_arithmetic(name):
     g = golden_lib.Golden(name)
     d = g.dump
     # 4 = fp64 with the land/water drag phase, 5 = fp64 with the self-collision list
-    e = emul_lib.EmulSim(g.robot(), 4 if FLUID(name) else (5 if COLLIDE(name) else abi.VXG_PREC_F64))
+    e = emul_lib.EmulSim(g.robot(), (7 if COLLIDE(name) else 4) if FLUID(name) else (5 if COLLIDE(name) else abi.VXG_PREC_F64))   # 7 = both
     ptol = 1e-7 if COLLIDE(name) else 1e-9   # contact (overlap * stiffness) amplifies rounding differences
     for f in range(1, d.vstate.shape[0]):
         assert e.step(g.every) == g.every
@@ -58,8 +58,8 @@ def test_emulated_f32_kernel_arithmetic(name, prec):
     if FLUID(name):
         if prec == 2:
             pytest.skip("the fluid kernels use the wide bond table")
-        prec = 3   # fp32 with the land/water drag phase
-    if COLLIDE(name):
+        prec = 8 if COLLIDE(name) else 3   # fp32 with the land/water drag phase (8: and the self-collision list)
+    elif COLLIDE(name):
         if prec == 2:
             pytest.skip("the self-collision kernels use the wide bond table")
         prec = 6   # fp32 with the self-collision list

@@ -41,7 +41,7 @@ def _run_gpu(rob, prec, frames, every, bonds=True):
 
 
 # ---- (a) golden fixtures, imported by the product importer ---------------------------------------
-@pytest.mark.parametrize("name", [n for n in TRAJ if not n.startswith("lw_fluid") and not n.startswith("col_")])
+@pytest.mark.parametrize("name", [n for n in TRAJ if not n.startswith("lw_fluid") and "col_" not in n])
 def test_golden_f64_logic_parity(name):
     """P1: fp64 instantiation vs the reference, per-frame state: positions <= 1e-9 pitch."""
     g = golden_lib.Golden(name)

@@ -103,6 +103,8 @@ def fluid_cases():
     case("lw_fluid_dense3", vxa.dense_lattice(3, 21, materials=(1, 3, 4)), 1200, 100, sim=S(init_cm_time=0.01, stop_condition_value=0.2), env=env(), lw=True)
     case("lw_fluid_sparse4", vxa.sparse_lattice(4, 22, fill=0.5, materials=(1, 3, 4)), 1000, 100, sim=S(init_cm_time=0.01, stop_condition_value=0.2), env=env(), lw=True)
     case("lw_fluid_first30", vxa.dense_lattice(2, 23, materials=(3, 4)), 30, 1, sim=S(init_cm_time=0.0005, stop_condition_value=0.2), env=env(), lw=True)
+    # the evosoro default for swimmers: fluid AND SelfColEnabled=1 (evosoro/base.py:24); the pincer makes real contacts
+    case("lw_fluid_col_pincer", pincer(), 800, 50, sim=S(init_cm_time=0.005, stop_condition_value=0.5, self_col_enabled=1), env=env(), lw=True, col=True)
     case("lw_fluid_dense3_full", vxa.dense_lattice(3, 24, materials=(1, 3, 4)), 0, 1, sim=S(init_cm_time=0.02, stop_condition_value=0.3), env=env(), lw=True, full=True)
 
 
