@@ -12,7 +12,7 @@
 #include <vector>
 
 #include "../../include/vxgpu.h"
-#include "vxg_kernels.cuh"
+#include "vxg_launch.cuh"
 #include "vx_pack.h"
 
 using namespace vx;
@@ -103,61 +103,16 @@ template <typename Real> static BatchDev<Real> dev_view(const vxg_batch* b) {
     return B;
 }
 
-template <typename Real, int NV, int VPT, bool SMEM, bool COMPACT, bool FLUID = false, bool COLLIDE = false>
-static cudaError_t launch_step(vxg_batch* b, int n_steps, int record) {
-    auto kern = vx_step_kernel<Real, NV, VPT, SMEM, COMPACT, FLUID, COLLIDE>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes);
-    if (e != cudaSuccess) return e;
-    kern<<<b->n_robots, NV / VPT, b->smem_bytes, b->stream>>>(dev_view<Real>(b), n_steps, record);
-    return cudaGetLastError();
-}
-
-template <typename Real, bool SMEM, bool COMPACT> static cudaError_t launch_step_s(vxg_batch* b, int n_steps, int record) {
-    switch (b->L.nv) {   // strides the kernels are instantiated for (stride_for); <= 512 threads per CTA
-        case 64: return launch_step<Real, 64, 1, SMEM, COMPACT>(b, n_steps, record);
-        case 128: return launch_step<Real, 128, 1, SMEM, COMPACT>(b, n_steps, record);
-        case 256: return launch_step<Real, 256, 1, SMEM, COMPACT>(b, n_steps, record);
-        case 512: return launch_step<Real, 512, 1, SMEM, COMPACT>(b, n_steps, record);
-        case 1024: return launch_step<Real, 1024, 2, SMEM, COMPACT>(b, n_steps, record);
-        case 2048: return launch_step<Real, 2048, 4, SMEM, COMPACT>(b, n_steps, record);
-    }
-    return cudaErrorInvalidValue;
-}
-
-// land/water layouts (surface-mesh arrays): fp32, shared-memory resident, wide bond table; with or without self-collision
-template <bool COLLIDE> static cudaError_t launch_step_fluid(vxg_batch* b, int n_steps, int record) {
-    switch (b->L.nv) {
-        case 64: return launch_step<float, 64, 1, true, false, true, COLLIDE>(b, n_steps, record);
-        case 128: return launch_step<float, 128, 1, true, false, true, COLLIDE>(b, n_steps, record);
-        case 256: return launch_step<float, 256, 1, true, false, true, COLLIDE>(b, n_steps, record);
-        case 512: return launch_step<float, 512, 1, true, false, true, COLLIDE>(b, n_steps, record);
-        case 1024: return launch_step<float, 1024, 2, true, false, true, COLLIDE>(b, n_steps, record);
-        case 2048: return launch_step<float, 2048, 4, true, false, true, COLLIDE>(b, n_steps, record);
-    }
-    return cudaErrorInvalidValue;
-}
-
-// batches with self-collision (limits.max_col_pairs > 0): fp32, shared-memory resident, wide bond table
-static cudaError_t launch_step_collide(vxg_batch* b, int n_steps, int record) {
-    switch (b->L.nv) {
-        case 64: return launch_step<float, 64, 1, true, false, false, true>(b, n_steps, record);
-        case 128: return launch_step<float, 128, 1, true, false, false, true>(b, n_steps, record);
-        case 256: return launch_step<float, 256, 1, true, false, false, true>(b, n_steps, record);
-        case 512: return launch_step<float, 512, 1, true, false, false, true>(b, n_steps, record);
-        case 1024: return launch_step<float, 1024, 2, true, false, false, true>(b, n_steps, record);
-        case 2048: return launch_step<float, 2048, 4, true, false, false, true>(b, n_steps, record);
-    }
-    return cudaErrorInvalidValue;
-}
-
+// Picks the kernel family for the batch (each family lives in its own translation unit, vxg_k_*.cu).
 // The compact bond table exists for the production path only (fp32, shared-memory resident).
 static cudaError_t launch_step_p(vxg_batch* b, int n_steps, int record) {
-    if (b->L.nvert_cap > 0) return b->lim.max_col_pairs > 0 ? launch_step_fluid<true>(b, n_steps, record) : launch_step_fluid<false>(b, n_steps, record);
-    if (b->lim.max_col_pairs > 0) return launch_step_collide(b, n_steps, record);
-    if (b->prec == VXG_PREC_F64)
-        return b->smem_mode ? launch_step_s<double, true, false>(b, n_steps, record) : launch_step_s<double, false, false>(b, n_steps, record);
-    if (!b->smem_mode) return launch_step_s<float, false, false>(b, n_steps, record);
-    return b->compact ? launch_step_s<float, true, true>(b, n_steps, record) : launch_step_s<float, true, false>(b, n_steps, record);
+    LaunchCfg c; c.n_robots = b->n_robots; c.nv = b->L.nv; c.smem_bytes = b->smem_bytes; c.stream = b->stream; c.n_steps = n_steps; c.record = record;
+    if (b->prec == VXG_PREC_F64) return launch_f64(dev_view<double>(b), c, b->smem_mode);
+    const BatchDev<float> B = dev_view<float>(b);
+    if (b->L.nvert_cap > 0) return launch_f32_fluid(B, c, b->lim.max_col_pairs > 0);
+    if (b->lim.max_col_pairs > 0) return launch_f32_collide(B, c);
+    if (!b->smem_mode) return launch_f32_wide(B, c, false);
+    return b->compact ? launch_f32_compact(B, c) : launch_f32_wide(B, c, true);
 }
 
 static void free_all(vxg_batch* b) {
@@ -588,8 +543,8 @@ extern "C" int vxg_reduce_stats(vxg_batch* b, vxg_robot_stats* out) {
     if (!b || !out) return fail(VXG_ERR_ARG, "vxg_reduce_stats: null argument");
     int rc = flush(b);
     if (rc) return rc;
-    if (b->prec == VXG_PREC_F64) vx_stats_kernel<double><<<b->n_robots, 256, 0, b->stream>>>(dev_view<double>(b), b->d_stats);
-    else vx_stats_kernel<float><<<b->n_robots, 256, 0, b->stream>>>(dev_view<float>(b), b->d_stats);
+    if (b->prec == VXG_PREC_F64) launch_stats_f64(dev_view<double>(b), b->d_stats, b->n_robots, b->stream);
+    else launch_stats_f32(dev_view<float>(b), b->d_stats, b->n_robots, b->stream);
     CK(cudaGetLastError());
     b->launches++;
     CK(cudaMemcpyAsync(b->h_stats, b->d_stats, (size_t)b->n_robots * sizeof(StatsDev), cudaMemcpyDeviceToHost, b->stream));

@@ -1,0 +1,49 @@
+// vxg_launch.cuh -- launch plumbing shared by the kernel translation units.  Each vxg_k_*.cu instantiates one
+// family of vx_step_kernel (so the families compile in parallel) and exports one plain function that picks
+// the instantiation for the batch's voxel stride.
+#pragma once
+#include <cuda_runtime.h>
+#include "vxg_kernels.cuh"
+
+namespace vx {
+
+struct LaunchCfg {
+    int n_robots, nv;
+    size_t smem_bytes;
+    cudaStream_t stream;
+    int n_steps, record;
+};
+
+template <typename Real, int NV, int VPT, bool SMEM, bool COMPACT, bool FLUID, bool COLLIDE>
+inline cudaError_t launch_one(const BatchDev<Real>& B, const LaunchCfg& c) {
+    auto kern = vx_step_kernel<Real, NV, VPT, SMEM, COMPACT, FLUID, COLLIDE>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem_bytes);
+    if (e != cudaSuccess) return e;
+    kern<<<c.n_robots, NV / VPT, c.smem_bytes, c.stream>>>(B, c.n_steps, c.record);
+    return cudaGetLastError();
+}
+
+// strides the kernels are instantiated for (stride_for); <= 512 threads per CTA
+template <typename Real, bool SMEM, bool COMPACT, bool FLUID, bool COLLIDE>
+inline cudaError_t launch_by_stride(const BatchDev<Real>& B, const LaunchCfg& c) {
+    switch (c.nv) {
+        case 64: return launch_one<Real, 64, 1, SMEM, COMPACT, FLUID, COLLIDE>(B, c);
+        case 128: return launch_one<Real, 128, 1, SMEM, COMPACT, FLUID, COLLIDE>(B, c);
+        case 256: return launch_one<Real, 256, 1, SMEM, COMPACT, FLUID, COLLIDE>(B, c);
+        case 512: return launch_one<Real, 512, 1, SMEM, COMPACT, FLUID, COLLIDE>(B, c);
+        case 1024: return launch_one<Real, 1024, 2, SMEM, COMPACT, FLUID, COLLIDE>(B, c);
+        case 2048: return launch_one<Real, 2048, 4, SMEM, COMPACT, FLUID, COLLIDE>(B, c);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// one per translation unit
+cudaError_t launch_f32_compact(const BatchDev<float>& B, const LaunchCfg& c);                 // production: fp32, smem, compact table
+cudaError_t launch_f32_wide(const BatchDev<float>& B, const LaunchCfg& c, bool smem);         // fp32, wide table, smem or global blob
+cudaError_t launch_f64(const BatchDev<double>& B, const LaunchCfg& c, bool smem);             // logic-parity mode
+cudaError_t launch_f32_collide(const BatchDev<float>& B, const LaunchCfg& c);                 // + self-collision
+cudaError_t launch_f32_fluid(const BatchDev<float>& B, const LaunchCfg& c, bool collide);     // land/water layouts (+ self-collision)
+void launch_stats_f32(const BatchDev<float>& B, StatsDev* out, int n_robots, cudaStream_t s);
+void launch_stats_f64(const BatchDev<double>& B, StatsDev* out, int n_robots, cudaStream_t s);
+
+}  // namespace vx

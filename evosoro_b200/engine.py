@@ -32,7 +32,7 @@ def build(force: bool = False) -> str:
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(os.path.dirname(_HERE), "include", "vxgpu.h")]
     stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if force or stale:
-        subprocess.run(["make", "-C", CSRC] + (["-B"] if force else []), check=True)
+        subprocess.run(["make", "-C", CSRC, "-j8"] + (["-B"] if force else []), check=True)
     return LIB_PATH
 
 
