@@ -2,6 +2,7 @@
 // into the device blob layout, kernel dispatch, state download.  No CPU compute path exists here:
 // every compute entry point fails with VXG_ERR_NO_DEVICE when no CUDA device is present.
 #include <cuda_runtime.h>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstdarg>
@@ -591,8 +592,12 @@ extern "C" int64_t vxg_upload_bytes(vxg_batch* b) {
     return (int64_t)(nr * per);
 }
 
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 extern "C" int vxg_run_batch_host(vxg_batch* b, const vxg_robot_desc* descs, int n_descs, int n_steps, double* pos_out) {
     if (!b || !descs || n_descs != b->n_robots) return fail(VXG_ERR_ARG, "vxg_run_batch_host: need one descriptor per robot slot");
+    const bool timing = getenv("VXG_TIMING") != nullptr;
+    const double t0 = now_ms();
     // flatten the descriptors into the pinned mirrors on all host cores (slots are independent)
     {
         int nt = (int)std::thread::hardware_concurrency();
@@ -612,8 +617,11 @@ extern "C" int vxg_run_batch_host(vxg_batch* b, const vxg_robot_desc* descs, int
         for (auto& x : th) x.join();
         for (int t = 0; t < nt; t++) if (rcs[t]) { g_err = msgs[t]; return rcs[t]; }
     }
+    const double t1 = now_ms();
     int rc = vxg_step(b, n_steps);
     if (rc) return rc;
+    if (timing) { cudaStreamSynchronize(b->stream); }
+    const double t2 = now_ms();
     if (pos_out) {
         // positions only: first 3*nv doubles of every blob (strided device -> host copy)
         size_t w = (size_t)3 * b->L.nv * sizeof(double);
@@ -629,5 +637,6 @@ extern "C" int vxg_run_batch_host(vxg_batch* b, const vxg_robot_desc* descs, int
             for (int i = 0; i < n; i++) { o[3 * i] = p[i]; o[3 * i + 1] = p[nv + i]; o[3 * i + 2] = p[2 * nv + i]; }
         }
     } else CK(cudaStreamSynchronize(b->stream));
+    if (timing) fprintf(stderr, "vxg_run_batch_host: flatten %.2f ms, upload+step %.2f ms, download+unpack %.2f ms\n", t1 - t0, t2 - t1, now_ms() - t2);
     return VXG_OK;
 }
