@@ -176,6 +176,13 @@ struct vxh_model {
 
 namespace {
 
+struct Region {     // CVX_FRegion (VX_FRegion.cpp:165-221): one primitive + what it imposes on the voxels it touches
+    int prim = -1;                       // PRIM_BOX 0, PRIM_CYLINDER 1, PRIM_SPHERE 2, PRIM_MESH 3 (Utils/... VX_FRegion.h)
+    double x = 0, y = 0, z = 0, dx = 0, dy = 0, dz = 0, radius = 0;   // in fractions of the workspace
+    int dof = 0;
+    double force[3] = {0, 0, 0}, torque[3] = {0, 0, 0}, disp[3] = {0, 0, 0}, adisp[3] = {0, 0, 0};
+};
+
 struct Parsed {
     // <Simulator>  (VX_Sim.cpp:263-356, VX_SimGA.cpp:205-220)
     double dt_frac = 0.9, bond_damp = 0.1, col_damp = 1.0, slow_damp = 1.0, col_horizon = 2.0;
@@ -184,7 +191,7 @@ struct Parsed {
     double min_temp_fact = 0.1;
     std::string fitness_file; bool write_fitness = true;
     // <Environment>  (VX_Environment.cpp:123-293)
-    int n_bcs = 0;
+    std::vector<Region> bcs;
     bool grav_on = false, floor_on = false, temp_on = false, vary_temp = false, sticky = false, falling_prohibited = false;
     bool limited_floor = false, sources = false, fluid = false, needle = false, norm_by_vol = false, save_traces = false;
     double grav_acc = -9.81, temp_base = 25, temp_amplitude = 0, temp_period = 0.1, growth_amp = 0, drag = 0;
@@ -217,6 +224,54 @@ int parse_per_voxel(const XNode* st, const char* tag, const Parsed& P, std::vect
         }
     }
     return 0;
+}
+
+// CVX_FRegion::ReadXML (VX_FRegion.cpp:165-221) for the `count_tag` regions of one container element
+int parse_regions(const XNode* box, const char* count_tag, std::vector<Region>& out) {
+    int n = 0;
+    if (!load(box, count_tag, &n)) n = 0;
+    auto regs = box->children("FRegion");
+    if (n > (int)regs.size()) return hfail(VXG_ERR_ARG, "<%s> is %d but only %d <FRegion> elements follow", count_tag, n, (int)regs.size());
+    for (int i = 0; i < n; i++) {
+        const XNode* r = regs[i];
+        Region g;
+        if (!load(r, "PrimType", &g.prim)) return hfail(VXG_ERR_ARG, "<FRegion> without <PrimType>");
+        if (g.prim == 3) return hfail(VXG_UNSUPPORTED_FEATURE, "mesh-shaped boundary-condition regions are not supported");
+        if (g.prim < 0 || g.prim > 3) return hfail(VXG_ERR_ARG, "unknown <PrimType> %d", g.prim);
+        load(r, "X", &g.x); load(r, "Y", &g.y); load(r, "Z", &g.z);
+        load(r, "dX", &g.dx); load(r, "dY", &g.dy); load(r, "dZ", &g.dz); load(r, "Radius", &g.radius);
+        int dof;
+        if (load(r, "DofFixed", &dof)) g.dof = (int)(signed char)dof & 0x3F;
+        else { bool fixed = false; g.dof = (load(r, "Fixed", &fixed) && fixed) ? 0x3F : 0; }   // pre-DofFixed files
+        load(r, "ForceX", &g.force[0]); load(r, "ForceY", &g.force[1]); load(r, "ForceZ", &g.force[2]);
+        load(r, "TorqueX", &g.torque[0]); load(r, "TorqueY", &g.torque[1]); load(r, "TorqueZ", &g.torque[2]);
+        load(r, "DisplaceX", &g.disp[0]); load(r, "DisplaceY", &g.disp[1]); load(r, "DisplaceZ", &g.disp[2]);
+        load(r, "AngDisplaceX", &g.adisp[0]); load(r, "AngDisplaceY", &g.adisp[1]); load(r, "AngDisplaceZ", &g.adisp[2]);
+        out.push_back(g);
+    }
+    return 0;
+}
+
+// CPrimitive::IsTouching(P, Dist, Envelope) (VX_FRegion.cpp:420-429 box, :531-534 cylinder = IsIn :495-524,
+// :601-605 sphere): does the voxel centred at p (half extents h) touch the region, envelope = the workspace
+bool region_touches(const Region& g, const double p[3], const double h[3], const double ws[3]) {
+    if (g.prim == 0) {
+        const double px = p[0] / ws[0], py = p[1] / ws[1], pz = p[2] / ws[2];
+        const double hx = h[0] / ws[0], hy = h[1] / ws[1], hz = h[2] / ws[2];
+        return px + hx > g.x && px - hx < g.x + g.dx && py + hy > g.y && py - hy < g.y + g.dy && pz + hz > g.z && pz - hz < g.z + g.dz;
+    }
+    const double cx = g.x * ws[0], cy = g.y * ws[1], cz = g.z * ws[2];
+    const double sx = g.dx * ws[0], sy = g.dy * ws[1], sz = g.dz * ws[2];
+    const double wmax = ws[0] > ws[1] ? (ws[0] > ws[2] ? ws[0] : ws[2]) : (ws[1] > ws[2] ? ws[1] : ws[2]);
+    const double rad = g.radius * wmax;
+    if (g.prim == 1) {
+        if (g.dx != 0) return p[0] > cx && p[0] < cx + sx && sqrt((p[1] - cy) * (p[1] - cy) + (p[2] - cz) * (p[2] - cz)) < rad;
+        if (g.dy != 0) return p[1] > cy && p[1] < cy + sy && sqrt((p[0] - cx) * (p[0] - cx) + (p[2] - cz) * (p[2] - cz)) < rad;
+        if (g.dz != 0) return p[2] > cz && p[2] < cz + sz && sqrt((p[0] - cx) * (p[0] - cx) + (p[1] - cy) * (p[1] - cy)) < rad;
+        return false;
+    }
+    const double dist = sqrt(h[0] * h[0] + h[1] * h[1] + h[2] * h[2]);   // Dist->Length()
+    return sqrt((p[0] - cx) * (p[0] - cx) + (p[1] - cy) * (p[1] - cy) + (p[2] - cz) * (p[2] - cz)) < rad + dist;
 }
 
 int parse_vxa(const XNode* root, int variant, Parsed& P) {
@@ -252,10 +307,11 @@ int parse_vxa(const XNode* root, int variant, Parsed& P) {
         if (lw || !load(S, "MinTempFact", &P.min_temp_fact)) P.min_temp_fact = 0.1;   // LW: MIN_TEMP_FACTOR constant, LW/VX_Sim.h:31
     }
     if (const XNode* E = root->child("Environment")) {
-        if (const XNode* n = E->child("Boundary_Conditions")) { int k = 0; load(n, "NumBCs", &k); P.n_bcs += k; }
-        else {
-            if (const XNode* f = E->child("Fixed_Regions")) { int k = 0; load(f, "NumFixed", &k); P.n_bcs += k; }
-            if (const XNode* f = E->child("Forced_Regions")) { int k = 0; load(f, "NumForced", &k); P.n_bcs += k; }
+        int rc;
+        if (const XNode* n = E->child("Boundary_Conditions")) { if ((rc = parse_regions(n, "NumBCs", P.bcs))) return rc; }
+        else {   // legacy layout (VX_Environment.cpp:140-169): fixed regions first, then forced ones
+            if (const XNode* f = E->child("Fixed_Regions")) { if ((rc = parse_regions(f, "NumFixed", P.bcs))) return rc; }
+            if (const XNode* f = E->child("Forced_Regions")) { if ((rc = parse_regions(f, "NumForced", P.bcs))) return rc; }
         }
         if (const XNode* n = E->child("Gravity")) {
             if (!load(n, "GravEnabled", &P.grav_on)) P.grav_on = false;
@@ -350,7 +406,8 @@ int check_supported(const Parsed& P, int ignore_collisions) {
     if (P.volume_fx) return hfail(VXG_UNSUPPORTED_FEATURE, "VolumeEffectsEnabled is not supported");
     if (P.equilibrium) return hfail(VXG_UNSUPPORTED_FEATURE, "EquilibriumModeEnabled is not supported");
     if (P.midlife_freeze > 0) return hfail(VXG_UNSUPPORTED_FEATURE, "MidLifeFreezeTime > 0 (development) is not supported");
-    if (P.n_bcs > 0) return hfail(VXG_UNSUPPORTED_FEATURE, "fixed / forced regions in the .vxa are not supported by the importer yet (the C-ABI accepts them)");
+    if (!P.bcs.empty() && (P.line_off[0] != 0 || P.line_off[1] != 0 || P.layer_off[0] != 0 || P.layer_off[1] != 0))
+        return hfail(VXG_UNSUPPORTED_FEATURE, "boundary-condition regions on a lattice with line / layer offsets are not supported");
     if (P.limited_floor) return hfail(VXG_UNSUPPORTED_FEATURE, "FloorRadius (limited floor) is not supported");
     if (P.sources) return hfail(VXG_UNSUPPORTED_FEATURE, "environmental <Sources> are not supported");
     if (P.falling_prohibited) return hfail(VXG_UNSUPPORTED_FEATURE, "FallingProhibited is not supported");
@@ -385,8 +442,56 @@ int flatten(const Parsed& P, int variant, int ignore_collisions, vxh_model& M) {
     const double s = ld[0];
 
     M.nom_pos.resize((size_t)n_vox * 3); M.vox_class.resize(n_vox); M.cell_index.resize(n_vox);
-    typedef std::tuple<int, float, double> VKey;   // material, phaseOffset (a float upstream), TempAmpDamp
+    typedef std::tuple<int, float, double, int> VKey;   // material, phaseOffset (a float upstream), TempAmpDamp, boundary-condition record
     std::map<VKey, int> vkeys;
+
+    // Boundary conditions (VX_Sim.cpp:517-582): a region's force / torque is shared equally by the voxels it touches
+    // (GetNumTouching, VX_Environment.cpp:330-347); fixed DOFs accumulate, prescribed displacements overwrite per axis.
+    struct VoxBC { int dof = 0; double f[3] = {0, 0, 0}, t[3] = {0, 0, 0}, d[3] = {0, 0, 0}, a[3] = {0, 0, 0}; };
+    std::vector<VoxBC> bc_recs(1);                   // record 0 = unconstrained
+    std::map<std::vector<double>, int> bc_ids;
+    std::vector<int> vox_bc(n_vox, 0);
+    if (!P.bcs.empty()) {
+        const double ws[3] = {ld[0] * nx, ld[1] * ny, ld[2] * nz};   // GetWorkSpace (VX_Object.cpp:492-497), no offsets
+        const double half[3] = {ld[0] / 2.0, ld[1] / 2.0, ld[2] / 2.0};
+        auto cell_pos = [&](size_t i, double p[3]) {
+            int iz = (int)(i / ((size_t)nx * ny)), iy = (int)((i - (size_t)iz * nx * ny) / nx), ix = (int)(i - (size_t)iz * nx * ny - (size_t)iy * nx);
+            p[0] = ld[0] * (ix + 0.5); p[1] = ld[1] * (iy + 0.5); p[2] = ld[2] * (iz + 0.5);
+        };
+        // GetNumTouching tests GetXYZ(i) WITH offsets (VX_Object.cpp:513-545): on an offset-free lattice that is the nominal
+        // position shifted by the reference's Eps = 1e-6 pitches in x and y, so a region edge that coincides with a voxel face
+        // can count a voxel the import loop (nominal position) does not constrain -- restated as is.
+        auto count_pos = [&](size_t i, double p[3]) {
+            int iz = (int)(i / ((size_t)nx * ny)), iy = (int)((i - (size_t)iz * nx * ny) / nx), ix = (int)(i - (size_t)iz * nx * ny - (size_t)iy * nx);
+            const double eps = 0.000001;
+            double ox = eps - (int)(eps / P.adj[0]) * P.adj[0], oy = eps - (int)(eps / P.adj[1]) * P.adj[1];
+            p[0] = P.lat * (P.adj[0] * (0.5 + ix) + ox); p[1] = P.lat * (P.adj[1] * (0.5 + iy) + oy); p[2] = P.lat * P.adj[2] * (0.5 + iz);
+        };
+        std::vector<int> sizes(P.bcs.size(), 0);
+        for (size_t j = 0; j < P.bcs.size(); j++)
+            for (size_t i = 0; i < ncell; i++) { if (x2s[i] < 0) continue; double p[3]; count_pos(i, p); if (region_touches(P.bcs[j], p, half, ws)) sizes[j]++; }
+        for (size_t i = 0; i < ncell; i++) {
+            if (x2s[i] < 0) continue;
+            double p[3]; cell_pos(i, p);
+            VoxBC b; bool any = false;
+            for (size_t j = 0; j < P.bcs.size(); j++) {
+                const Region& g = P.bcs[j];
+                if (!region_touches(g, p, half, ws)) continue;
+                any = true;
+                b.dof |= g.dof;
+                for (int a = 0; a < 3; a++) {
+                    b.f[a] += g.force[a] / sizes[j]; b.t[a] += g.torque[a] / sizes[j];
+                    if (g.dof & (1 << a)) b.d[a] = g.disp[a];
+                    if (g.dof & (8 << a)) b.a[a] = g.adisp[a];
+                }
+            }
+            if (!any) continue;
+            std::vector<double> key = {(double)b.dof, b.f[0], b.f[1], b.f[2], b.t[0], b.t[1], b.t[2], b.d[0], b.d[1], b.d[2], b.a[0], b.a[1], b.a[2]};
+            auto it = bc_ids.find(key);
+            if (it == bc_ids.end()) { it = bc_ids.emplace(key, (int)bc_recs.size()).first; bc_recs.push_back(b); }
+            vox_bc[x2s[i]] = it->second;
+        }
+    }
     M.vclasses.clear();
     for (size_t i = 0; i < ncell; i++) {
         int sidx = x2s[i];
@@ -399,7 +504,7 @@ int flatten(const Parsed& P, int variant, int ignore_collisions, vxh_model& M) {
         int mat = P.cells[i];
         float phase = P.has_phase ? (float)P.phase[sidx] : 0.0f;   // VXS_Voxel.h: `float phaseOffset`
         double tad = P.has_tad ? P.tad[sidx] : 1.0;
-        VKey key(mat, phase, tad);
+        VKey key(mat, phase, tad, vox_bc[sidx]);
         auto it = vkeys.find(key);
         if (it == vkeys.end()) {
             const Material& pm = P.palette[mat];
@@ -415,7 +520,9 @@ int flatten(const Parsed& P, int variant, int ignore_collisions, vxh_model& M) {
             c.mu_static = pm.u_static; c.mu_dynamic = pm.u_dynamic;
             c.nom_size = s; c.cte = pm.cte; c.temp_amp_damp = tad; c.phase_offset = (double)phase; c.e_mod = pm.e;
             c.init_size = lw ? s : (double)(float)s;   // `float initialVoxelSize` (VXS_Voxel.h:100, VX_Sim.cpp:905)
-            c.dof_fixed = 0; c.mat_index = mat;
+            const VoxBC& bc = bc_recs[vox_bc[sidx]];
+            c.dof_fixed = bc.dof; c.mat_index = mat;
+            for (int a = 0; a < 3; a++) { c.ext_force[a] = bc.f[a]; c.ext_torque[a] = bc.t[a]; c.ext_disp[a] = bc.d[a]; c.ext_tdisp[a] = bc.a[a]; }
             it = vkeys.emplace(key, (int)M.vclasses.size()).first;
             M.vclasses.push_back(c);
         }
@@ -437,6 +544,7 @@ int flatten(const Parsed& P, int variant, int ignore_collisions, vxh_model& M) {
             int v2 = x2s[j];
             if (v2 < 0) continue;
             const vxg_vox_class& c1 = M.vclasses[M.vox_class[v1]]; const vxg_vox_class& c2 = M.vclasses[M.vox_class[v2]];
+            if ((c1.dof_fixed & 0x3F) == 0x3F && (c2.dof_fixed & 0x3F) == 0x3F) continue;   // CreatePermBond: no bond between two fully fixed voxels (VX_Sim.cpp:728)
             const Material& m1 = P.palette[c1.mat_index]; const Material& m2 = P.palette[c2.mat_index];
             double E1 = m1.e, E2 = m2.e, u1 = m1.poisson, u2 = m2.poisson;
             if (E1 == 0 || E2 == 0) continue;                           // LinkVoxels fails: no bond (VX_Bond.cpp:87)

@@ -89,6 +89,21 @@ class EnvParams:
     extra_tags: dict = field(default_factory=dict)
 
 
+@dataclass
+class Region:
+    """One ``<FRegion>`` boundary condition (reference: VX_FRegion.cpp:122-163).  Position / size are fractions
+    of the workspace; ``dof_fixed`` is the bit mask X=1 Y=2 Z=4 TX=8 TY=16 TZ=32 (VX_FRegion.h:30-37)."""
+    prim_type: int = 0                      # 0 box, 1 cylinder, 2 sphere
+    pos: Sequence[float] = (0.0, 0.0, 0.0)
+    size: Sequence[float] = (0.0, 0.0, 0.0)
+    radius: float = 0.0
+    dof_fixed: int = 0
+    force: Sequence[float] = (0.0, 0.0, 0.0)
+    torque: Sequence[float] = (0.0, 0.0, 0.0)
+    displace: Sequence[float] = (0.0, 0.0, 0.0)
+    ang_displace: Sequence[float] = (0.0, 0.0, 0.0)
+
+
 def _fmt(v) -> str:
     if isinstance(v, (bool, np.bool_)):
         return str(int(v))
@@ -98,12 +113,15 @@ def _fmt(v) -> str:
 
 
 def vxa_text(structure: np.ndarray, palette: Sequence[Material] = None, sim: SimParams = None,
-             env: EnvParams = None, phase_offset: Optional[np.ndarray] = None) -> str:
+             env: EnvParams = None, phase_offset: Optional[np.ndarray] = None,
+             boundary_conditions: Optional[Sequence[Region]] = None) -> str:
     """Return the ``.vxa`` text for one robot.
 
     ``structure`` is an integer array indexed ``[x, y, z]`` of material IDs (0 = empty), the same
     orientation evosoro's phenotype arrays use (read_write_voxelyze.py:380-386).
     ``phase_offset`` (same shape, floats) is written as a ``<PhaseOffset>`` block when given.
+    ``boundary_conditions`` (fixed / forced regions) are written as a ``<Boundary_Conditions>`` block; evosoro
+    itself always writes the empty legacy ``<Fixed_Regions>`` / ``<Forced_Regions>`` pair.
     """
     palette = list(palette) if palette is not None else four_material_palette()
     sim = sim or SimParams()
@@ -160,12 +178,31 @@ def vxa_text(structure: np.ndarray, palette: Sequence[Material] = None, sim: Sim
         w(f"<FluidEnvironment>{int(env.fluid_environment)}</FluidEnvironment>")
     if env.aggregate_drag_coefficient is not None:
         w(f"<AggregateDragCoefficient>{_fmt(env.aggregate_drag_coefficient)}</AggregateDragCoefficient>")
-    w("<Fixed_Regions>")
-    w("<NumFixed>0</NumFixed>")
-    w("</Fixed_Regions>")
-    w("<Forced_Regions>")
-    w("<NumForced>0</NumForced>")
-    w("</Forced_Regions>")
+    if boundary_conditions:
+        w("<Boundary_Conditions>")
+        w(f"<NumBCs>{len(boundary_conditions)}</NumBCs>")
+        for g in boundary_conditions:
+            w("<FRegion>")
+            w(f"<PrimType>{int(g.prim_type)}</PrimType>")
+            for t, v in zip(("X", "Y", "Z"), g.pos):
+                w(f"<{t}>{_fmt(float(v))}</{t}>")
+            for t, v in zip(("dX", "dY", "dZ"), g.size):
+                w(f"<{t}>{_fmt(float(v))}</{t}>")
+            w(f"<Radius>{_fmt(float(g.radius))}</Radius>")
+            w("<R>0.4</R><G>0.6</G><B>0.4</B><alpha>1</alpha>")
+            w(f"<DofFixed>{int(g.dof_fixed)}</DofFixed>")
+            for pre, vec in (("Force", g.force), ("Torque", g.torque), ("Displace", g.displace), ("AngDisplace", g.ang_displace)):
+                for t, v in zip("XYZ", vec):
+                    w(f"<{pre}{t}>{_fmt(float(v))}</{pre}{t}>")
+            w("</FRegion>")
+        w("</Boundary_Conditions>")
+    else:
+        w("<Fixed_Regions>")
+        w("<NumFixed>0</NumFixed>")
+        w("</Fixed_Regions>")
+        w("<Forced_Regions>")
+        w("<NumForced>0</NumForced>")
+        w("</Forced_Regions>")
     w("<Gravity>")
     w(f"<GravEnabled>{int(env.grav_enabled)}</GravEnabled>")
     w(f"<GravAcc>{_fmt(env.grav_acc)}</GravAcc>")

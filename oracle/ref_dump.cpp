@@ -57,10 +57,17 @@ struct Ref {
 };
 
 #define N_SIM 24
-#define N_VD 24
+#define N_VD 36
 #define N_BD 4
 #define N_VS 15
 #define N_BS 14
+
+// The prescribed displacements of fixed DOFs have no public getter (VX_Voxel.h:121-123, protected): read them
+// through pointers-to-member re-exported by a derived type (no reference source is changed).
+struct VoxBcAccess : CVX_Voxel {
+    using CVX_Voxel::ExternalDisp;
+    using CVX_Voxel::ExternalTDisp;
+};
 
 static void dump_header(FILE* f, Ref& r, long long nframes) {
     CVX_SimGA& S = r.Sim;
@@ -112,6 +119,10 @@ static void dump_header(FILE* f, Ref& r, long long nframes) {
         d[21] = 1.0; d[22] = v.GetNominalSize();
 #endif
         d[23] = v.GetLinearStiffness();
+        Vec3D<> ef = v.GetExternalForce(), et = v.GetExternalTorque();
+        Vec3D<> ed = v.*(&VoxBcAccess::ExternalDisp), ea = v.*(&VoxBcAccess::ExternalTDisp);
+        d[24] = ef.x; d[25] = ef.y; d[26] = ef.z; d[27] = et.x; d[28] = et.y; d[29] = et.z;
+        d[30] = ed.x; d[31] = ed.y; d[32] = ed.z; d[33] = ea.x; d[34] = ea.y; d[35] = ea.z;
         wr(f, d, sizeof d);
     }
     for (int j = 0; j < S.NumBond(); j++) {

@@ -129,7 +129,8 @@ def desc_from_dump(d: RefDump, lw: bool = False, col_horizon: float = 2.0) -> ab
     for i in range(d.n_vox):
         v = d.vox[i]
         s, mat, E, nu, cte, mass, inertia, fm = v[3], int(v[4]), v[5], v[6], v[7], v[8], v[9], v[10]
-        key = (s, mat, E, nu, cte, mass, v[11], v[12], v[16], v[21], int(v[19]), v[14], v[22])
+        bc = tuple(v[24:36]) if len(v) >= 36 else (0.0,) * 12   # boundary-condition columns (dumps written before them: none)
+        key = (s, mat, E, nu, cte, mass, v[11], v[12], v[16], v[21], int(v[19]), v[14], v[22]) + bc
         if key not in vkeys:
             c = abi.VoxClass()
             c.mass = mass; c.mass_inv = 1 / mass
@@ -145,6 +146,8 @@ def desc_from_dump(d: RefDump, lw: bool = False, col_horizon: float = 2.0) -> ab
             c.e_mod = E
             c.init_size = v[22]
             c.dof_fixed = int(v[19])
+            for a in range(3):
+                c.ext_force[a], c.ext_torque[a], c.ext_disp[a], c.ext_tdisp[a] = bc[a], bc[3 + a], bc[6 + a], bc[9 + a]
             c.mat_index = mat
             vkeys[key] = len(vclasses)
             vclasses.append(c)

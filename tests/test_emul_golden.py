@@ -28,6 +28,7 @@ def test_emulated_f64_kernel_arithmetic(name):
     normals/areas, drag law): the kernels' own mesh_vertex / voxel_drag functions in fp64 vs the reference."""
     g = golden_lib.Golden(name)
     d = g.dump
+    LAT = float(d.sim[14])   # the fixture's own lattice pitch
     # 4 = fp64 with the land/water drag phase, 5 = fp64 with the self-collision list
     e = emul_lib.EmulSim(g.robot(), (7 if COLLIDE(name) else 4) if FLUID(name) else (5 if COLLIDE(name) else abi.VXG_PREC_F64))   # 7 = both
     ptol = 1e-7 if COLLIDE(name) else 1e-9   # contact (overlap * stiffness) amplifies rounding differences
@@ -55,6 +56,7 @@ def test_emulated_f32_kernel_arithmetic(name, prec):
     must qualify for it, and it must meet the same tolerance as the wide table."""
     g = golden_lib.Golden(name)
     d = g.dump
+    LAT = float(d.sim[14])   # the fixture's own lattice pitch
     if FLUID(name):
         if prec == 2:
             pytest.skip("the fluid kernels use the wide bond table")

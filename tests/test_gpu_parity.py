@@ -46,6 +46,7 @@ def test_golden_f64_logic_parity(name):
     """P1: fp64 instantiation vs the reference, per-frame state: positions <= 1e-9 pitch."""
     g = golden_lib.Golden(name)
     d = g.dump
+    LAT = float(d.sim[14])   # the fixture's own lattice pitch
     rob = engine.Model(text=g.vxa_text, variant=_variant(g)).robot
     got = _run_gpu(rob, abi.VXG_PREC_F64, d.vstate.shape[0] - 1, g.every)
     for f, s in enumerate(got, start=1):
@@ -67,12 +68,31 @@ def test_golden_f32_short_horizon(name):
     max |dpos| <= 2e-5 pitch, quaternions <= 1e-5."""
     g = golden_lib.Golden(name)
     d = g.dump
+    LAT = float(d.sim[14])   # the fixture's own lattice pitch
     rob = engine.Model(text=g.vxa_text, variant=_variant(g)).robot
     got = _run_gpu(rob, abi.VXG_PREC_F32, d.vstate.shape[0] - 1, g.every, bonds=False)
     for f, s in enumerate(got, start=1):
         assert common.max_abs(s.pos, d.pos[f]) <= 2e-5 * LAT, (name, f, common.max_abs(s.pos, d.pos[f]) / LAT)
         assert common.max_abs(s.quat, d.quat[f]) <= 1e-5
         assert common.max_abs(s.scale, d.scale[f]) <= 1e-15
+
+
+@pytest.mark.parametrize("prec,tol", [(abi.VXG_PREC_F32, 1e-5), (abi.VXG_PREC_F64, 1e-9)])
+def test_cantilever_rests_at_beam_theory_deflection(prec, tol):
+    """P4: 20x1x1 cantilever (VX_Benchmark.cpp:36-79), clamped at x = 0, transverse tip load, 80 000 steps to rest:
+    tip deflection within `tol` pitch of the reference's and within 0.3 % of 4 P (n-1)^3 / (E s)."""
+    g = golden_lib.Golden("bc_cantilever20")
+    d = g.dump
+    n, P, E, s = 20, 3e-5, 1e6, 1e-3
+    b = engine.Batch([engine.Model(text=g.vxa_text).robot], precision=prec)
+    b.step(g.n_steps)
+    assert b.sync()[0] == 0
+    st = b.download(0)
+    b.close()
+    tip, ref_tip = d.vox[-1, 2] - st.pos[-1, 2], d.vox[-1, 2] - d.pos[-1, -1, 2]
+    assert abs(tip - ref_tip) <= tol * s
+    assert abs(tip / (4 * P * (n - 1) ** 3 / (E * s)) - 1) < 3e-3
+    assert np.array_equal(st.pos[0], d.vox[0, 0:3])   # the clamped voxel never moves
 
 
 @pytest.mark.parametrize("name,prec,tol", [("dense3_full", abi.VXG_PREC_F32, 1e-2), ("dense3_full", abi.VXG_PREC_F64, 1e-6),

@@ -64,7 +64,8 @@ def test_class_deduplication_is_compact():
     (lambda t: t.replace("<EquilibriumModeEnabled>0", "<EquilibriumModeEnabled>1"), 1),
     (lambda t: t.replace("<FluidDampEnabled>0</FluidDampEnabled>", "<VolumeEffectsEnabled>1</VolumeEffectsEnabled>"), 1),
     (lambda t: t.replace("<MatModel>0", "<MatModel>2"), 1),
-    (lambda t: t.replace("<NumFixed>0", "<NumFixed>1"), 1),
+    (lambda t: t.replace("<NumFixed>0", "<NumFixed>1"), -1),                                   # count without its <FRegion>
+    (lambda t: t.replace("<NumFixed>0</NumFixed>", "<NumFixed>1</NumFixed><FRegion><PrimType>3</PrimType></FRegion>"), 1),   # mesh region
     (lambda t: t.replace('Compression="ASCII_READABLE"', 'Compression="ZLIB"'), 1),
     (lambda t: t.replace("</VXA>", ""), -1),
     (lambda t: t.replace("<X_Voxels>3", "<X_Voxels>4"), -1),
@@ -96,3 +97,22 @@ def test_file_and_string_entry_points_agree(tmp_path):
     p.write_text(text)
     a, b = engine.Model(path=str(p)).robot, engine.Model(text=text).robot
     assert np.array_equal(a.nom_pos, b.nom_pos) and np.array_equal(a.bond_class, b.bond_class)
+
+
+def test_boundary_conditions_legacy_and_current_layouts_agree():
+    """<Fixed_Regions>/<Forced_Regions> (legacy, VX_Environment.cpp:140-169) and <Boundary_Conditions> give the same model;
+    a pre-DofFixed <Fixed>1</Fixed> means all six DOFs."""
+    st = vxa.dense_lattice(3, 2)
+    cur = vxa.vxa_text(st, boundary_conditions=[vxa.Region(0, (0, 0, 0), (0.3, 1, 1), dof_fixed=0x3F),
+                                                vxa.Region(0, (0.7, 0, 0), (0.3, 1, 1), force=(0, 0, -1.0))])
+    reg = lambda body: f"<FRegion><PrimType>0</PrimType>{body}</FRegion>"
+    fixed = reg("<X>0</X><Y>0</Y><Z>0</Z><dX>0.3</dX><dY>1</dY><dZ>1</dZ><Fixed>1</Fixed>")
+    forced = reg("<X>0.7</X><Y>0</Y><Z>0</Z><dX>0.3</dX><dY>1</dY><dZ>1</dZ><ForceZ>-1.0</ForceZ>")
+    old = vxa.vxa_text(st).replace("<NumFixed>0</NumFixed>", "<NumFixed>1</NumFixed>" + fixed).replace("<NumForced>0</NumForced>", "<NumForced>1</NumForced>" + forced)
+    a, b = engine.Model(text=cur).robot, engine.Model(text=old).robot
+    assert [c.dof_fixed for c in _expand_v(a)] == [c.dof_fixed for c in _expand_v(b)]
+    assert [list(c.ext_force) for c in _expand_v(a)] == [list(c.ext_force) for c in _expand_v(b)]
+    dof = np.array([c.dof_fixed for c in _expand_v(a)])
+    assert (dof == 0x3F).sum() == 9 and a.n_bond == 54 - 12      # the 12 bonds inside the clamped face are not created
+    fz = np.array([c.ext_force[2] for c in _expand_v(a)])
+    assert (fz != 0).sum() == 9 and abs(fz.sum() + 1.0) < 1e-15   # the region's force is shared by the voxels it touches

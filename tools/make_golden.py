@@ -23,12 +23,12 @@ OUT = os.path.join(ROOT, "tests", "golden")
 TMP = "/tmp/vx_golden"
 
 
-def case(name, structure, n_steps, every, sim=None, env=None, palette=None, phase=None, lw=False, full=False, col=False):
+def case(name, structure, n_steps, every, sim=None, env=None, palette=None, phase=None, lw=False, full=False, col=False, bcs=None):
     os.makedirs(TMP, exist_ok=True)
     if full:   # the stock CLI writes its result file where <FitnessFileName> says
         sim = sim or vxa.SimParams()
         sim.fitness_file = os.path.join(TMP, name + "_result.xml")
-    text = vxa.vxa_text(structure, palette=palette, sim=sim, env=env, phase_offset=phase)
+    text = vxa.vxa_text(structure, palette=palette, sim=sim, env=env, phase_offset=phase, boundary_conditions=bcs)
     path = os.path.join(TMP, name + ".vxa")
     with open(path, "w") as f:
         f.write(text)
@@ -108,8 +108,34 @@ def fluid_cases():
     case("lw_fluid_dense3_full", vxa.dense_lattice(3, 24, materials=(1, 3, 4)), 0, 1, sim=S(init_cm_time=0.02, stop_condition_value=0.3), env=env(), lw=True, full=True)
 
 
+def bc_cases():
+    """fixed / forced regions (VX_Sim.cpp:517-582, VXS_Voxel.cpp:174-221, :540, :668-672)"""
+    S, E, R = vxa.SimParams, vxa.EnvParams, vxa.Region
+    free = lambda: E(grav_enabled=0, floor_enabled=0, temp_enabled=0, lattice_dim=0.001)
+    soft = [vxa.Material("1MPa", 1e6, density=1.0)]
+    # P4 of SURVEY 8c: 20x1x1 cantilever of VX_Benchmark.cpp:36-79, clamped at x = 0, transverse tip load, run to rest
+    n = 20
+    beam = np.ones((n, 1, 1), dtype=np.int32)
+    bcs = [R(0, (0, 0, 0), (0.5 / n, 1, 1), dof_fixed=0x3F), R(0, ((n - 0.5) / n, 0, 0), (0.5 / n, 1, 1), force=(0, 0, -3e-5))]
+    case("bc_cantilever20", beam, 80000, 4000, sim=S(bond_damping_z=1.0, slow_damping_z=0.001, init_cm_time=0.0, stop_condition_type=1, stop_condition_value=80000),
+         env=free(), palette=soft, bcs=bcs)
+    # mixed constraints on a heterogeneous block under gravity: a clamped corner column with a prescribed displacement and
+    # rotation, a plane on rollers (z only), a sphere-shaped forced region with force + torque, overlapping regions
+    blk = vxa.dense_lattice(4, 41)
+    bcs = [R(0, (0, 0, 0), (0.25, 0.25, 1), dof_fixed=0x3F, displace=(1e-4, 0, 2e-4), ang_displace=(0, 0.05, 0.02)),
+           R(0, (0.75, 0, 0), (0.25, 1, 0.25), dof_fixed=0x04, displace=(0, 0, -1e-4)),
+           R(2, (0.5, 0.5, 1.0), radius=0.3, force=(0.2, -0.1, 0.3), torque=(1e-4, 0, -2e-4)),
+           R(0, (0, 0.75, 0.5), (0.5, 0.25, 0.5), dof_fixed=0x38, ang_displace=(0.01, 0, 0)),
+           R(1, (0.4, 0.4, 0.0), (0, 0, 1.0), radius=0.2, force=(0, 0, 0.5))]
+    case("bc_block4_mixed", blk, 1500, 100, sim=S(init_cm_time=0.01, stop_condition_value=0.2), env=E(floor_enabled=0), bcs=bcs)
+    # the first 30 steps of the same, every step
+    case("bc_block4_first30", blk, 30, 1, sim=S(init_cm_time=0.0005, stop_condition_value=0.2), env=E(floor_enabled=0), bcs=bcs)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "fluid":
+    if len(sys.argv) > 1 and sys.argv[1] == "bc":
+        bc_cases()
+    elif len(sys.argv) > 1 and sys.argv[1] == "fluid":
         fluid_cases()
     elif len(sys.argv) > 1 and sys.argv[1] == "col":
         collision_cases()
@@ -117,3 +143,4 @@ if __name__ == "__main__":
         main()
         fluid_cases()
         collision_cases()
+        bc_cases()
