@@ -71,3 +71,21 @@ def test_product_does_not_reference_the_oracle():
                     if re.search(r"vx_oracle|libvxoracle|oracle_lib|oracle/_ref|ref_dump", t):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_class_api_adapter_has_no_cpu_path(tmp_path):
+    """Seam B2 binary (reference CLI + library, Integrate() swapped): without a CUDA device it must stop with the engine's
+    message and exit code 3 -- never fall through to the reference's CPU loop it is linked with."""
+    import os
+    import subprocess
+    from evosoro_b200 import engine, vxa
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "voxelyze_gpu_adapter")
+    if not os.access(exe, os.X_OK):
+        pytest.skip("oracle/_ref/voxelyze_gpu_adapter not built")
+    if engine.device_count() > 0:
+        pytest.skip("a GPU is visible")
+    p = tmp_path / "r.vxa"
+    p.write_text(vxa.vxa_text(vxa.dense_lattice(2, 1), sim=vxa.SimParams(init_cm_time=0.001, stop_condition_value=0.01, fitness_file=str(tmp_path / "f.xml"))))
+    r = subprocess.run([exe, "-f", str(p)], capture_output=True, text=True)
+    assert r.returncode == 3 and "no CUDA device" in r.stderr
+    assert not (tmp_path / "f.xml").exists()

@@ -329,6 +329,41 @@ def test_cli_rejects_unsupported_instead_of_falling_back(tmp_path):
     assert not (tmp_path / "f.xml").exists()
 
 
+# ---- seam B2: the reference's own CLI + library with CVX_Sim::Integrate() swapped for the engine ------
+ADAPTER = os.path.join(refdump.REF_DIR, "voxelyze_gpu_adapter")
+needs_adapter = pytest.mark.skipif(not os.access(ADAPTER, os.X_OK), reason="oracle/_ref/voxelyze_gpu_adapter did not travel with the snapshot")
+
+
+@needs_adapter
+@pytest.mark.parametrize("name,f64", [("dense3_full", False), ("dense3_full", True), ("dense3_afterlife_full", False), ("col_pincer_full", False)])
+def test_class_api_adapter_reference_cli_on_the_engine(name, f64, tmp_path):
+    """voxelyzeMain/main.cpp, LoadVXAFile/Import, TimeStep's latches, UpdateCollisions (host-side contact list ->
+    vxg_set_collision_pairs), UpdateStats and WriteResultFile are all the UNMODIFIED reference; only Integrate() is
+    evosoro_b200/adapter/vx_integrate_gpu.cpp (one device step + write-back into VoxArray per call).  The result file
+    the reference writes from the written-back state must be the one it writes on its own CPU path."""
+    g = golden_lib.Golden(name)
+    out = tmp_path / "fit.xml"
+    vxa_path = tmp_path / (name + ".vxa")
+    vxa_path.write_text(g.vxa_text.replace(g.fitness_file, str(out)))
+    env = dict(os.environ, **({"VXG_ADAPTER_F64": "1"} if f64 else {}))
+    r = subprocess.run([ADAPTER, "-f", str(vxa_path)], env=env, capture_output=True, text=True)
+    assert r.returncode == 1, r.stderr
+    _check_result(out.read_text(), g)
+    if f64:   # logic parity: the reference's own getters over fp64 device state reproduce its CPU run to the printed digits
+        ours, ref = golden_lib.parse_result(out.read_text()), golden_lib.parse_result(g.result_xml)
+        for k, v in ref.items():
+            assert ours[k] == pytest.approx(v, rel=1e-6, abs=1e-9), k
+
+
+@needs_adapter
+def test_class_api_adapter_rejects_unsupported(tmp_path):
+    p = tmp_path / "eq.vxa"
+    p.write_text(vxa.vxa_text(vxa.dense_lattice(2, 1), sim=vxa.SimParams(equilibrium_mode=1, fitness_file=str(tmp_path / "f.xml"))))
+    r = subprocess.run([ADAPTER, "-f", str(p)], capture_output=True, text=True)
+    assert r.returncode == 3 and "EquilibriumModeEnabled" in r.stderr
+    assert not (tmp_path / "f.xml").exists()
+
+
 # ---- BASELINE config 5: land/water fork, 8^3 swimming robots with fluid drag -------------------------
 def _lw_fluid_text(n, seed):
     env = vxa.EnvParams(fluid_environment=1, aggregate_drag_coefficient=750.0)
