@@ -38,6 +38,9 @@ class VoxClass(C.Structure):
         ("ext_force", C.c_double * 3), ("ext_torque", C.c_double * 3),
         ("ext_disp", C.c_double * 3), ("ext_tdisp", C.c_double * 3),
         ("dof_fixed", C.c_int32), ("mat_index", C.c_int32),
+        ("final_size", C.c_double), ("growth_time", C.c_double), ("start_growth_time", C.c_double),
+        ("final_phase_offset", C.c_double), ("final_temp_amp_damp", C.c_double),
+        ("dev_flags", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -59,6 +62,7 @@ class SimParams(C.Structure):
         ("temp_amplitude", C.c_double), ("min_scale_fact", C.c_double), ("max_scale_fact", C.c_double),
         ("lattice_dim", C.c_double), ("drag_coeff", C.c_double), ("col_horizon", C.c_double),
         ("flags", C.c_uint32), ("reserved", C.c_uint32),
+        ("growth_amplitude", C.c_double), ("midlife_freeze_time", C.c_double), ("stop_condition_value", C.c_double),
     ]
 
 

@@ -79,11 +79,6 @@ void check_supported(CVX_Sim& S) {
     if (E->getFloorRadius() > 0) die("unsupported feature", "FloorRadius (limited floor)");
     if (E->isFallingProhibited()) die("unsupported feature", "FallingProhibited");
     if (E->GetNumTimeStepsInWindow() > 0) die("unsupported feature", "velocity-adjusted development windows");
-    if (S.GetMidLifeFreezeTime() > 0) die("unsupported feature", "MidLifeFreezeTime");
-    CVX_Object* O = E->pObj;
-    if (O->GetUsingFinalVoxelSize() || O->GetUsingGrowthTime() || O->GetUsingStartGrowthTime() || O->GetUsingFinalPhaseOffset() ||
-        O->GetUsingFinalTempAmpDamp() || O->GetUsingStiffnessPlasticity() || O->GetEvolvingStiffness())
-        die("unsupported feature", "per-voxel development / evolved stiffness fields");
 #endif
     for (int i = 0; i < S.NumVox(); i++) {
         int model = S.VoxArray[i].GetpMaterial()->GetMatModel();
@@ -91,9 +86,9 @@ void check_supported(CVX_Sim& S) {
     }
 }
 
-// CVX_Sim -> flat descriptor.  Constants by the closed forms of CVX_Voxel::SetMaterial (VX_Voxel.cpp:109-125) and
-// CVX_Bond::LinkVoxels / UpdateConstants (VX_Bond.cpp:65-173), like csrc/vxh_import.cpp:flatten() -- but starting
-// from the reference's own imported arrays instead of the .vxa text.
+// CVX_Sim -> flat descriptor: the constants are the reference's own cached members (CVX_Voxel::SetMaterial
+// VX_Voxel.cpp:109-125, CVX_Bond::LinkVoxels / UpdateConstants VX_Bond.cpp:65-173), read as they stand after
+// Import + ResetSimulation -- so whatever the reference derived them from (palette or evolved stiffness) carries over.
 void attach(CVX_Sim& S, Attached& A) {
     if (vxg_device_count() <= 0) die("no CUDA device", "the engine has no CPU path");
     check_supported(S);
@@ -107,13 +102,21 @@ void attach(CVX_Sim& S, Attached& A) {
         nom[3 * i] = p.x; nom[3 * i + 1] = p.y; nom[3 * i + 2] = p.z;
         vxg_vox_class c; memset(&c, 0, sizeof c);
         const double s = v.GetNominalSize(), E = v.GetEMod();
-        c.mass = v.GetMass(); c.mass_inv = 1 / c.mass; c.inertia = v.GetInertia(); c.inertia_inv = 1 / c.inertia;
-        c.damp_lin = 2 * sqrt(c.mass * E * s); c.damp_ang = 2 * sqrt(c.inertia * E * s * s * s);
-        c.k_floor = 2 * E * s;
+        c.mass = v.GetMass(); c.mass_inv = v._massInv; c.inertia = v.GetInertia(); c.inertia_inv = v._inertiaInv;
+        c.damp_lin = v._2xSqMxExS; c.damp_ang = v._2xSqIxExSxSxS;
+        c.k_floor = v.GetLinearStiffness();
         c.mu_static = v.GetpMaterial()->GetuStatic(); c.mu_dynamic = v.GetpMaterial()->GetuDynamic();
         c.nom_size = s; c.cte = v.GetCTE(); c.phase_offset = v.phaseOffset; c.e_mod = E;
 #ifndef REF_LW
         c.temp_amp_damp = v.TempAmpDamp; c.init_size = v.initialVoxelSize;
+        c.final_size = v.finalVoxelSize; c.growth_time = v.growthTime; c.start_growth_time = v.startGrowthTime;
+        c.final_phase_offset = v.finalPhaseOffset; c.final_temp_amp_damp = v.finalTempAmpDamp;
+        {
+            CVX_Object* O = S.pEnv->pObj;
+            c.dev_flags = (O->GetUsingFinalVoxelSize() ? VXG_DEV_FINAL_SIZE : 0) | (O->GetUsingFinalPhaseOffset() ? VXG_DEV_FINAL_PHASE : 0) |
+                          (O->GetUsingFinalTempAmpDamp() ? VXG_DEV_FINAL_TAD : 0) |
+                          ((O->GetUsingInitialVoxelSize() || O->GetUsingFinalVoxelSize()) ? VXG_DEV_SIZE_ADJUST : 0);
+        }
 #else
         c.temp_amp_damp = 1.0; c.init_size = s;
 #endif
@@ -130,25 +133,19 @@ void attach(CVX_Sim& S, Attached& A) {
         b1[j] = b.GetVox1SInd(); b2[j] = b.GetVox2SInd(); bax[j] = (int)b.GetBondAxis() - 1;   // AXIS_X = 1 (VX_Enums.h:66-70)
         CVXS_Voxel& v1 = S.VoxArray[b1[j]]; CVXS_Voxel& v2 = S.VoxArray[b2[j]];
         vxg_bond_class k; memset(&k, 0, sizeof k);
-        const double E1 = v1.GetEMod(), E2 = v2.GetEMod(), u1 = v1.GetPoisson(), u2 = v2.GetPoisson();
-        const double E = (E1 * E2 / (E1 + E2)) * 2, u = (u1 == 0 && u2 == 0) ? 0 : (u1 * u2 / (u1 + u2)) * 2;
-        const double L = (v1.GetNominalSize() + v2.GetNominalSize()) * 0.5, G = E / (2 * (1 + u));
-        const double A = L * L, Iy = L * L * L * L / 12, J = L * L * (L * L + L * L) / 12;
-        k.a1 = E * A / L; k.a2 = G * J / L; k.b1 = 12 * E * Iy / (L * L * L); k.b2 = 6 * E * Iy / (L * L); k.b3 = 2 * E * Iy / L;
-        k.len = L; k.area = A;
+        k.a1 = b.a1; k.a2 = b.a2; k.b1 = b.b1y; k.b2 = b.b2y; k.b3 = b.b3y;      // cubic voxels: the y and z constants coincide
+        k.len = b.L.x; k.area = v1.GetNominalSize() * v1.GetNominalSize();       // CSArea reset to s^2 every step (VXS_Voxel.cpp:625-631)
 #ifndef REF_LW   // the stress model's modulus: the palette material's (VX_Object.cpp:1477); the land/water fork passes the voxel's own
         k.e1 = v1.GetpMaterial()->GetElasticMod(); k.e2 = v2.GetpMaterial()->GetElasticMod();
-        k.homogeneous = v1.GetMaterialIndex() == v2.GetMaterialIndex() ? 1 : 0;
-#else
-        k.e1 = E1; k.e2 = E2;
-        k.homogeneous = (v1.GetMaterialIndex() == v2.GetMaterialIndex() && E1 == E2) ? 1 : 0;
+#else            // ... through a `float voxelEmod` parameter (LW/VX_Object.cpp:1472-1474)
+        k.e1 = (double)(float)v1.GetEMod(); k.e2 = (double)(float)v2.GetEMod();
 #endif
+        k.homogeneous = b.HomogenousBond ? 1 : 0;
         const Vec3D<> p1 = v1.GetNominalPosition(), p2 = v2.GetNominalPosition();
         k.nom_dist = bax[j] == 0 ? p2.x - p1.x : (bax[j] == 1 ? p2.y - p1.y : p2.z - p1.z);
-        const double M1 = v1.GetMass(), M2 = v2.GetMass(), I1 = v1.GetInertia(), I2 = v2.GetInertia(), FM1 = v1.GetFirstMoment(), FM2 = v2.GetFirstMoment();
-        k.c_a1m1 = 2 * sqrt(k.a1 * M1); k.c_a1m2 = 2 * sqrt(k.a1 * M2); k.c_a2i1 = 2 * sqrt(k.a2 * I1); k.c_a2i2 = 2 * sqrt(k.a2 * I2);
-        k.c_b1m1 = 2 * sqrt(k.b1 * M1); k.c_b1m2 = 2 * sqrt(k.b1 * M2); k.c_b2fm1 = 2 * sqrt(k.b2 * FM1); k.c_b2fm2 = 2 * sqrt(k.b2 * FM2);
-        k.c_b3i1 = 2 * sqrt(k.b3 * I1); k.c_b3i2 = 2 * sqrt(k.b3 * I2);
+        k.c_a1m1 = b._2xSqA1xM1; k.c_a1m2 = b._2xSqA1xM2; k.c_a2i1 = b._2xSqA2xI1; k.c_a2i2 = b._2xSqA2xI2;
+        k.c_b1m1 = b._2xSqB1YxM1; k.c_b1m2 = b._2xSqB1YxM2; k.c_b2fm1 = b._2xSqB2YxFM1; k.c_b2fm2 = b._2xSqB2YxFM2;
+        k.c_b3i1 = b._2xSqB3YxI1; k.c_b3i2 = b._2xSqB3YxI2;
         bcls[j] = intern(bc, k);
     }
     vxg_robot_desc d; memset(&d, 0, sizeof d);
@@ -169,6 +166,7 @@ void attach(CVX_Sim& S, Attached& A) {
     if (A.collisions) fl |= VXG_F_COLLISIONS;
 #ifndef REF_LW
     sp.min_scale_fact = S.getMinTempFact(); sp.max_scale_fact = 1.0 + S.pEnv->getGrowthAmplitude();
+    sp.growth_amplitude = S.pEnv->getGrowthAmplitude(); sp.midlife_freeze_time = S.GetMidLifeFreezeTime(); sp.stop_condition_value = S.GetStopConditionValue();
     if (S.pEnv->getUsingStickyFloor()) fl |= VXG_F_STICKY_FLOOR;
 #else
     sp.min_scale_fact = MIN_TEMP_FACTOR; sp.max_scale_fact = 1.0;

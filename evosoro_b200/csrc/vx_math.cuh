@@ -507,29 +507,61 @@ VX_HD bool voxel_integrate(const VoxK<T>& k, V3<T> F, V3<T> M, double half_scale
 }
 
 // Scale law, evaluated once per voxel CLASS per step in fp64 (every voxel of a class has the same
-// Scale history).  _voxcad: VXS_Voxel.cpp:224-336 restricted to the in-scope features (no growth
-// windows); land/water fork: LW/VXS_Voxel.cpp:211-235.  `t` is CurTime BEFORE the increment.
+// Scale history).  _voxcad: VXS_Voxel.cpp:224-336 -- prenatal ramp, mid-life freeze, postnatal linear development of
+// size / phase / actuation amplitude, size-adjusted actuation; the velocity-adjusted ("ballistic") development
+// windows (:340-381) depend on simulation state and are rejected at import.  Land/water fork: LW/VXS_Voxel.cpp:211-235.
+// `t` is CurTime BEFORE the increment.  The development members are `float` upstream, so differences / quotients
+// of two of them are float operations there (usual arithmetic conversions) and are restated as such.
 struct ScaleK {
     double nom_size, init_size, cte, temp_amp_damp, phase_offset;
-    long long mat_index;   // palette index of the class (fitness probes key on 5 / 6, VX_Sim.cpp:2626-2705)
+    double final_size, growth_time, start_growth, final_phase, final_tad;
+    int mat_index;         // palette index of the class (fitness probes key on 5 / 6, VX_Sim.cpp:2626-2705)
+    int dev_flags;         // VXG_DEV_*
 };
-VX_HD double scale_law(const ScaleK& c, double last_scale, double t, double init_cm_time, double temp_period,
-                       double temp_amplitude, double min_fact, double max_fact, bool temp_on, bool lw) {
+struct ScaleSim {          // what the law reads from CVX_Sim / CVX_Environment
+    double init_cm_time, temp_period, temp_amplitude, min_fact, max_fact, growth_amp, midlife_freeze, stop_value;
+    bool temp_on, lw;
+};
+VX_HD double scale_law(const ScaleK& c, double last_scale, double t, const ScaleSim& S) {
     const double two_pi_f = (double)(2 * 3.1415926f);          // the reference's float literal (VXS_Voxel.cpp:302)
-    if (lw) {
+    if (S.lw) {
         double tf = 1.0;
-        if (temp_on && t >= init_cm_time) tf = 1 + (temp_amplitude * sin(two_pi_f * (t / temp_period + c.phase_offset))) * c.cte;
-        if (tf < min_fact) tf = min_fact;
+        if (S.temp_on && t >= S.init_cm_time) tf = 1 + (S.temp_amplitude * sin(two_pi_f * (t / S.temp_period + c.phase_offset))) * c.cte;
+        if (tf < S.min_fact) tf = S.min_fact;
         return tf * c.nom_size;
     }
-    double ctrl = 0;
-    if (temp_on && t >= init_cm_time)
-        ctrl = c.temp_amp_damp * (temp_amplitude * sin(two_pi_f * (t / temp_period + c.phase_offset))) * c.cte;
-    double cc = (t >= 0.5 * init_cm_time) ? 1.0 : 2 * t / init_cm_time;
+    double cc = (t >= 0.5 * S.init_cm_time) ? 1.0 : 2 * t / S.init_cm_time;      // :237-238
     double prenatal = cc * ((c.init_size / c.nom_size) - 1);
-    double cur = ctrl * c.nom_size + (1 + prenatal) * c.nom_size;
-    if (cur < last_scale && cur < min_fact * c.nom_size) cur = last_scale;
-    if (cur > last_scale && cur > max_fact * c.nom_size) cur = last_scale;
+    double frozen_adj = 0, freeze_init = 1;
+    if (S.midlife_freeze > 0) {                                                  // :241-259
+        double middle = 0.5 * (S.stop_value - S.init_cm_time);
+        double fs = middle - 0.5 * S.midlife_freeze, fe = middle + 0.5 * S.midlife_freeze;
+        if (t > fs && t < fe) { frozen_adj = t - fs; if (t < fs + S.init_cm_time) freeze_init = 0; }
+        if (t > fe) frozen_adj = S.midlife_freeze;
+    }
+    double dev = 0, dphase = 0, dtad = 0;
+    if (c.dev_flags != 0 && t >= c.start_growth && c.growth_time > 0) {          // :262-291 (without a flag k has no effect)
+        double lim = (double)((float)c.start_growth + (float)c.growth_time) + S.midlife_freeze;
+        double eff = (t <= lim) ? t : lim;
+        eff = eff - frozen_adj;
+        double k = (eff - c.start_growth) / c.growth_time;
+        if (c.dev_flags & 0x1) dev = k * ((double)((float)c.final_size / (float)c.init_size) - 1.0);
+        if (c.dev_flags & 0x2) dphase = k * (double)((float)c.final_phase - (float)c.phase_offset);
+        if (c.dev_flags & 0x4) dtad = k * (double)((float)c.final_tad - (float)c.temp_amp_damp);
+    }
+    double ctrl = 0;
+    if (S.temp_on && t >= S.init_cm_time)                                        // :294-305
+        ctrl = (c.temp_amp_damp + dtad) * (S.temp_amplitude * sin(two_pi_f * (t / S.temp_period + (c.phase_offset + dphase)))) * c.cte * freeze_init;
+    if (c.dev_flags & 0x8) {                                                     // :308-318
+        double cur_size = (1 + prenatal) * (1 + dev) * c.nom_size;
+        double orig = (cur_size / c.nom_size - 1) / S.growth_amp;
+        double pos = (orig + 1) * 0.5;
+        double capped = (pos > 0.5) ? 0.5 : pos;
+        ctrl = ctrl * capped * 2;
+    }
+    double cur = ctrl * c.nom_size + (1 + prenatal) * (1 + dev) * c.nom_size;    // :321
+    if (cur < last_scale && cur < S.min_fact * c.nom_size) cur = last_scale;     // :324-330
+    if (cur > last_scale && cur > S.max_fact * c.nom_size) cur = last_scale;
     return cur;
 }
 

@@ -91,6 +91,8 @@ inline void pack_classes(const vxg_robot_desc* d, BondK<Real>* bk, double* bk_di
         ScaleK& s = sk[i];
         s.mat_index = c.mat_index;
         s.nom_size = c.nom_size; s.init_size = c.init_size; s.cte = c.cte; s.temp_amp_damp = c.temp_amp_damp; s.phase_offset = c.phase_offset;
+        s.final_size = c.final_size; s.growth_time = c.growth_time; s.start_growth = c.start_growth_time;
+        s.final_phase = c.final_phase_offset; s.final_tad = c.final_temp_amp_damp; s.dev_flags = c.dev_flags;
         scale_c[i] = c.nom_size;   // ResetVoxel: Scale = NominalSize (VXS_Voxel.cpp:110)
     }
 }
@@ -216,6 +218,7 @@ inline void init_ctl(const vxg_robot_desc* d, RobotCtl& c) {
     memset(&c, 0, sizeof c);
     c.cur_time = 0; c.dt = P.dt; c.init_cm_time = P.init_cm_time; c.temp_period = P.temp_period; c.temp_amplitude = P.temp_amplitude;
     c.min_fact = P.min_scale_fact; c.max_fact = P.max_scale_fact;
+    c.growth_amp = P.growth_amplitude; c.midlife_freeze = P.midlife_freeze_time; c.stop_value = P.stop_condition_value;
     c.step = 0; c.total_steps = 0x7fffffffffffffffLL; c.latch_step = -1; c.eol_step = -1; c.eol_post_y = 0; c.status = 0; c.flags = P.flags;
     c.n_vox = d->n_vox; c.n_vclass = d->n_vclass; c.n_bclass = d->n_bclass; c.ini_latched = 0;
     c.half_bond_z = 0.5 * P.bond_damp_z;

@@ -450,6 +450,7 @@ struct RobotCtl {
     int n_surf, col_hops, pad3;
     long long eol_step;     // CurStepCount at which EndOfLifetimePosteriorY is latched (-1 never)
     double eol_post_y;      // min Pos.y over material != 5 at that step (metres); 0 = not latched
+    double growth_amp, midlife_freeze, stop_value;   // development terms of the scale law (ScaleSim)
 };
 
 }  // namespace vx

@@ -64,6 +64,7 @@ template <typename Real> struct SmemTables {
     double* red;      // [4][32] reduction scratch
     unsigned long long* mbar;   // split-phase barrier between the axis sub-phases
     unsigned int* maxvel;       // [2] max |Vel|^2 of a step as float bits (double-buffered by step parity)
+    ScaleSim* sl;               // the robot's scale-law constants (read by the few threads that evaluate the law)
     ColPair* pairs;             // [max_col] contact bonds
 };
 
@@ -80,6 +81,7 @@ __host__ __device__ inline size_t tables_bytes(int max_vclass, int max_bclass, b
     o = vx_align16(o + sizeof(Real) * 3 * max_vclass);
     o = vx_align16(o + sizeof(double) * 4 * 32);
     o = vx_align16(o + sizeof(unsigned long long) + 2 * sizeof(unsigned int));
+    o = vx_align16(o + sizeof(ScaleSim));
     o = vx_align16(o + sizeof(ColPair) * max_col);
     return o;
 }
@@ -99,6 +101,7 @@ __device__ inline SmemTables<Real> carve_tables(unsigned char* p, int max_vclass
     t.mbar = (unsigned long long*)(p + o);
     t.maxvel = (unsigned int*)(p + o + sizeof(unsigned long long));
     o = vx_align16(o + sizeof(unsigned long long) + 2 * sizeof(unsigned int));
+    t.sl = (ScaleSim*)(p + o);      o = vx_align16(o + sizeof(ScaleSim));
     t.pairs = (ColPair*)(p + o);
     return t;
 }
@@ -261,8 +264,14 @@ __global__ void __launch_bounds__(NV / VPT, 1) vx_step_kernel(BatchDev<Real> B, 
     C.sticky = (flags & VXG_F_STICKY_FLOOR_) != 0;
     C.sym_mass = ctlp->sym_mass != 0;
     const bool temp_on = (flags & VXG_F_TEMPERATURE_) != 0, lw = (flags & VXG_F_LW_SCALE_) != 0;
-    const double init_cm = ctlp->init_cm_time, tper = ctlp->temp_period, tamp = ctlp->temp_amplitude;
-    const double minf = ctlp->min_fact, maxf = ctlp->max_fact;
+    if (tid == 0) {
+        ScaleSim SL;
+        SL.init_cm_time = ctlp->init_cm_time; SL.temp_period = ctlp->temp_period; SL.temp_amplitude = ctlp->temp_amplitude;
+        SL.min_fact = ctlp->min_fact; SL.max_fact = ctlp->max_fact; SL.growth_amp = ctlp->growth_amp;
+        SL.midlife_freeze = ctlp->midlife_freeze; SL.stop_value = ctlp->stop_value; SL.temp_on = temp_on; SL.lw = lw;
+        *S.sl = SL;
+    }
+    __syncthreads();
     const Real dt_inv_run = (Real)(1.0 / dt);
     Real* rec_base = (record_bonds && B.bond_rec) ? B.bond_rec + (size_t)robot * 39 * NV : nullptr;
 
@@ -349,7 +358,7 @@ __global__ void __launch_bounds__(NV / VPT, 1) vx_step_kernel(BatchDev<Real> B, 
         // which nobody reads before the end-of-step barrier.
         for (int i = T - 1 - tid; i < n_vc; i += T) {
             double last = S.scale_c[cur * B.max_vclass + i];
-            double ns = scale_law(S.sk[i], last, t, init_cm, tper, tamp, minf, maxf, temp_on, lw);
+            double ns = scale_law(S.sk[i], last, t, *S.sl);
             S.scale_c[(cur ^ 1) * B.max_vclass + i] = ns;
             S.dsc_c[(cur ^ 1) * B.max_vclass + i] = (Real)(ns - S.sk[i].nom_size);
         }

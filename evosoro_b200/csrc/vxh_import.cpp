@@ -202,6 +202,13 @@ struct Parsed {
     std::vector<int> cells;          // material index per lattice cell, x fastest
     bool has_phase = false, has_tad = false;
     std::vector<double> phase, tad;  // per occupied-cell rank (VX_Object.cpp:1892-1899)
+    // development / evolved stiffness blocks (VX_Object.cpp:1910-2322), same layout
+    bool has_final_phase = false, has_final_tad = false, has_init_size = false, has_final_size = false, has_growth_time = false,
+         has_start_growth = false, has_stiffness = false;
+    std::vector<double> final_phase, final_tad, init_size, final_size, growth_time, start_growth, stiffness;
+    double min_growth_time = 0, parent_lifetime = 0;
+    bool has_parent_lifetime = false, onset_relative = false, termination_relative = false;
+    int steps_in_window = 0;
 };
 
 int parse_per_voxel(const XNode* st, const char* tag, const Parsed& P, std::vector<double>& out, bool* present) {
@@ -299,6 +306,7 @@ int parse_vxa(const XNode* root, int variant, Parsed& P) {
             if (!lw) { load(n, "AfterlifeTime", &P.afterlife); load(n, "MidLifeFreezeTime", &P.midlife_freeze); }
             load(n, "InitCmTime", &P.init_cm_time);
         }
+        if (!lw) P.has_parent_lifetime = load(S, "ParentLifetime", &P.parent_lifetime);   // VX_Sim.cpp:348
         if (const XNode* n = S->child("EquilibriumMode")) load(n, "EquilibriumModeEnabled", &P.equilibrium);
         if (const XNode* n = S->child("GA")) {
             if (!load(n, "FitnessFileName", &P.fitness_file)) P.fitness_file = "";
@@ -330,6 +338,9 @@ int parse_vxa(const XNode* root, int variant, Parsed& P) {
         }
         if (!lw) {
             if (!load(E, "GrowthAmplitude", &P.growth_amp)) P.growth_amp = 0;
+            if (!load(E, "MinGrowthTime", &P.min_growth_time)) P.min_growth_time = 0;       // VX_Environment.cpp:210
+            load(E, "OnsetRelative", &P.onset_relative); load(E, "TerminationRelative", &P.termination_relative);
+            load(E, "NumTimeStepsInWindow", &P.steps_in_window);
             load(E, "StickyFloor", &P.sticky);
             load(E, "FallingProhibited", &P.falling_prohibited);
             load(E, "NeedleInHaystack", &P.needle); load(E, "NormDistByVol", &P.norm_by_vol); load(E, "SaveTraces", &P.save_traces);
@@ -391,12 +402,21 @@ int parse_vxa(const XNode* root, int variant, Parsed& P) {
     }
     int rc;
     if ((rc = parse_per_voxel(st, "PhaseOffset", P, P.phase, &P.has_phase))) return rc;
-    if (!lw) { if ((rc = parse_per_voxel(st, "TempAmpDamp", P, P.tad, &P.has_tad))) return rc; }
-    static const char* unsupported_blocks[] = {"FinalPhaseOffset", "FinalTempAmpDamp", "InitialVoxelSize", "FinalVoxelSize", "GrowthTime",
-                                               "StartGrowthTime", "StiffnessPlasticityRate", "KP", "KI", "ANTIWINDUP", "Stiffness",
-                                               "SynapseWeights", "Weights"};
+    if ((rc = parse_per_voxel(st, "Stiffness", P, P.stiffness, &P.has_stiffness))) return rc;
+    if (!lw) {   // the land/water fork reads PhaseOffset and Stiffness only (LW/VX_Object.cpp:1879-1970)
+        if ((rc = parse_per_voxel(st, "TempAmpDamp", P, P.tad, &P.has_tad))) return rc;
+        if ((rc = parse_per_voxel(st, "FinalPhaseOffset", P, P.final_phase, &P.has_final_phase))) return rc;
+        if ((rc = parse_per_voxel(st, "FinalTempAmpDamp", P, P.final_tad, &P.has_final_tad))) return rc;
+        if ((rc = parse_per_voxel(st, "InitialVoxelSize", P, P.init_size, &P.has_init_size))) return rc;
+        if ((rc = parse_per_voxel(st, "FinalVoxelSize", P, P.final_size, &P.has_final_size))) return rc;
+        if ((rc = parse_per_voxel(st, "GrowthTime", P, P.growth_time, &P.has_growth_time))) return rc;
+        if ((rc = parse_per_voxel(st, "StartGrowthTime", P, P.start_growth, &P.has_start_growth))) return rc;
+    }
+    // <StiffnessPlasticityRate>, <KP>, <KI>, <ANTIWINDUP> are stored per voxel by the reference (VX_Sim.cpp:977-981) but no
+    // step code reads them: accepted and ignored.  Synapse weights belong to the removed neural-net controller.
+    static const char* unsupported_blocks[] = {"SynapseWeights", "Weights"};
     for (const char* t : unsupported_blocks)
-        if (st->child(t)) return hfail(VXG_UNSUPPORTED_FEATURE, "per-voxel <%s> (development / evolved stiffness) is not implemented on the device", t);
+        if (st->child(t)) return hfail(VXG_UNSUPPORTED_FEATURE, "per-voxel <%s> is not implemented on the device", t);
     return 0;
 }
 
@@ -405,7 +425,7 @@ int check_supported(const Parsed& P, int ignore_collisions) {
     if (P.blending) return hfail(VXG_UNSUPPORTED_FEATURE, "BlendingEnabled is not supported");
     if (P.volume_fx) return hfail(VXG_UNSUPPORTED_FEATURE, "VolumeEffectsEnabled is not supported");
     if (P.equilibrium) return hfail(VXG_UNSUPPORTED_FEATURE, "EquilibriumModeEnabled is not supported");
-    if (P.midlife_freeze > 0) return hfail(VXG_UNSUPPORTED_FEATURE, "MidLifeFreezeTime > 0 (development) is not supported");
+    if (P.steps_in_window > 0) return hfail(VXG_UNSUPPORTED_FEATURE, "NumTimeStepsInWindow > 0 (velocity-adjusted development windows) is not supported");
     if (!P.bcs.empty() && (P.line_off[0] != 0 || P.line_off[1] != 0 || P.layer_off[0] != 0 || P.layer_off[1] != 0))
         return hfail(VXG_UNSUPPORTED_FEATURE, "boundary-condition regions on a lattice with line / layer offsets are not supported");
     if (P.limited_floor) return hfail(VXG_UNSUPPORTED_FEATURE, "FloorRadius (limited floor) is not supported");
@@ -436,13 +456,19 @@ int flatten(const Parsed& P, int variant, int ignore_collisions, vxh_model& M) {
     if (n_vox == 0) return hfail(VXG_ERR_ARG, "No voxels in object");
     if (P.has_phase && (int)P.phase.size() != n_vox) return hfail(VXG_ERR_ARG, "<PhaseOffset> does not cover every voxel");
     if (P.has_tad && (int)P.tad.size() != n_vox) return hfail(VXG_ERR_ARG, "<TempAmpDamp> does not cover every voxel");
+    {
+        const std::pair<bool, const std::vector<double>*> blocks[] = {{P.has_final_phase, &P.final_phase}, {P.has_final_tad, &P.final_tad},
+            {P.has_init_size, &P.init_size}, {P.has_final_size, &P.final_size}, {P.has_growth_time, &P.growth_time},
+            {P.has_start_growth, &P.start_growth}, {P.has_stiffness, &P.stiffness}};
+        for (auto& b : blocks) if (b.first && (int)b.second->size() != n_vox) return hfail(VXG_ERR_ARG, "a per-voxel block does not cover every voxel");
+    }
 
     // GetLatDimEnv() = Lattice_Dim * DimAdj (VX_Object.h:377); voxels are forced cubic with the X pitch (VX_Sim.cpp:527)
     const double ld[3] = {P.lat * P.adj[0], P.lat * P.adj[1], P.lat * P.adj[2]};
     const double s = ld[0];
 
     M.nom_pos.resize((size_t)n_vox * 3); M.vox_class.resize(n_vox); M.cell_index.resize(n_vox);
-    typedef std::tuple<int, float, double, int> VKey;   // material, phaseOffset (a float upstream), TempAmpDamp, boundary-condition record
+    typedef std::vector<double> VKey;   // material, phaseOffset, TempAmpDamp, boundary-condition record, development values, evolved stiffness
     std::map<VKey, int> vkeys;
 
     // Boundary conditions (VX_Sim.cpp:517-582): a region's force / torque is shared equally by the voxels it touches
@@ -503,8 +529,47 @@ int flatten(const Parsed& P, int variant, int ignore_collisions, vxh_model& M) {
         M.cell_index[sidx] = (int32_t)i;
         int mat = P.cells[i];
         float phase = P.has_phase ? (float)P.phase[sidx] : 0.0f;   // VXS_Voxel.h: `float phaseOffset`
-        double tad = P.has_tad ? P.tad[sidx] : 1.0;
-        VKey key(mat, phase, tad, vox_bc[sidx]);
+        double tad = P.has_tad ? (double)(float)P.tad[sidx] : 1.0;   // `float TempAmpDamp` (VXS_Voxel.h:94)
+
+        // Per-voxel development parameters as ResetSimulation derives them (VX_Sim.cpp:878-975); the members are floats.
+        const double stop_v = P.stop_value, icm = P.init_cm_time, midlife = lw ? 0.0 : P.midlife_freeze;
+        const double parent_life = P.has_parent_lifetime ? P.parent_lifetime : stop_v;
+        const float onset_bound = (float)(P.onset_relative ? parent_life : stop_v);
+        const float term_bound = (float)(P.termination_relative ? parent_life : stop_v);
+        float init_size_f = (float)s, final_size_f, start_growth_f, growth_time_f;
+        int dev_flags = 0;
+        if (P.has_init_size) {
+            double f = 1 + (P.growth_amp * P.init_size[sidx]);
+            double eff = (f < P.min_temp_fact) ? P.min_temp_fact : f;
+            init_size_f = (float)(eff * s);
+        }
+        if (P.has_final_size) {
+            double f = 1 + (P.growth_amp * P.final_size[sidx]);
+            double eff = (f < P.min_temp_fact) ? P.min_temp_fact : f;
+            final_size_f = (float)(eff * s);
+            dev_flags |= VXG_DEV_FINAL_SIZE;
+        } else final_size_f = init_size_f;
+        if (P.has_start_growth) {
+            double g = P.start_growth[sidx] * (onset_bound - icm) + icm;
+            if (g >= onset_bound - P.min_growth_time) start_growth_f = (float)(onset_bound - P.min_growth_time);
+            else start_growth_f = (float)g;
+        } else if (P.has_final_size || P.has_growth_time) start_growth_f = (float)icm;
+        else start_growth_f = (float)(stop_v - midlife);
+        if (P.has_growth_time) {
+            double g = P.growth_time[sidx] * (term_bound - start_growth_f - midlife);
+            growth_time_f = (float)((g <= P.min_growth_time) ? P.min_growth_time : g);
+        } else if (P.has_final_size) growth_time_f = (float)(term_bound - start_growth_f - midlife);
+        else growth_time_f = (float)P.min_growth_time;
+        float final_phase_f = P.has_final_phase ? (float)P.final_phase[sidx] : 0.0f;
+        float final_tad_f = P.has_final_tad ? (float)P.final_tad[sidx] : 1.0f;
+        if (P.has_final_phase) dev_flags |= VXG_DEV_FINAL_PHASE;
+        if (P.has_final_tad) dev_flags |= VXG_DEV_FINAL_TAD;
+        if (P.has_init_size || P.has_final_size) dev_flags |= VXG_DEV_SIZE_ADJUST;
+        if (lw) dev_flags = 0;
+        const double stiff = P.has_stiffness ? P.stiffness[sidx] : -1.0;
+
+        VKey key = {(double)mat, (double)phase, tad, (double)vox_bc[sidx], (double)init_size_f, (double)final_size_f, (double)start_growth_f,
+                    (double)growth_time_f, (double)final_phase_f, (double)final_tad_f, (double)dev_flags, stiff};
         auto it = vkeys.find(key);
         if (it == vkeys.end()) {
             const Material& pm = P.palette[mat];
@@ -519,7 +584,20 @@ int flatten(const Parsed& P, int variant, int ignore_collisions, vxh_model& M) {
             c.k_floor = 2 * pm.e * s;
             c.mu_static = pm.u_static; c.mu_dynamic = pm.u_dynamic;
             c.nom_size = s; c.cte = pm.cte; c.temp_amp_damp = tad; c.phase_offset = (double)phase; c.e_mod = pm.e;
-            c.init_size = lw ? s : (double)(float)s;   // `float initialVoxelSize` (VXS_Voxel.h:100, VX_Sim.cpp:905)
+            c.init_size = lw ? s : (double)init_size_f;   // `float initialVoxelSize` (VXS_Voxel.h:100, VX_Sim.cpp:905)
+            if (!lw) {
+                c.final_size = final_size_f; c.growth_time = growth_time_f; c.start_growth_time = start_growth_f;
+                c.final_phase_offset = final_phase_f; c.final_temp_amp_damp = final_tad_f; c.dev_flags = dev_flags;
+            }
+            if (P.has_stiffness) {
+                // _voxcad: SetEMod at reset (VX_Sim.cpp:983-988) changes Vox_E AFTER SetMaterial cached the damping terms and after the
+                // internal bonds were linked -- only what reads Vox_E later follows it: floor contact (GetLinearStiffness, VX_Voxel.h:64)
+                // and contact bonds (LinkVoxels at creation, VX_Bond.cpp:83).  Land/water fork: SetVoxData runs before the bonds are
+                // linked (LW/VX_Sim.cpp:541) and its SetEMod refreshes the damping terms (LW/VX_Voxel.h:61): everything follows it.
+                c.e_mod = stiff;
+                c.k_floor = 2 * stiff * s;
+                if (lw) { c.damp_lin = 2 * sqrt(c.mass * stiff * s); c.damp_ang = 2 * sqrt(c.inertia * stiff * s * s * s); }
+            }
             const VoxBC& bc = bc_recs[vox_bc[sidx]];
             c.dof_fixed = bc.dof; c.mat_index = mat;
             for (int a = 0; a < 3; a++) { c.ext_force[a] = bc.f[a]; c.ext_torque[a] = bc.t[a]; c.ext_disp[a] = bc.d[a]; c.ext_tdisp[a] = bc.a[a]; }
@@ -531,7 +609,7 @@ int flatten(const Parsed& P, int variant, int ignore_collisions, vxh_model& M) {
 
     // bonds: for each voxel look +X, +Y, +Z (VX_Sim.cpp:621-641)
     M.bond_v1.clear(); M.bond_v2.clear(); M.bond_axis.clear(); M.bond_class.clear(); M.bclasses.clear();
-    typedef std::tuple<int, int, long long> BKey;   // material 1, material 2, pitch in 1e-9 voxel sizes (may differ per axis)
+    typedef std::tuple<int, int, long long, double, double> BKey;   // material 1, material 2, pitch in 1e-9 voxel sizes (may differ per axis), linking moduli
     std::map<BKey, int> bkeys;
     double max_freq2 = 0;
     for (int v1 = 0; v1 < n_vox; v1++) {
@@ -546,11 +624,12 @@ int flatten(const Parsed& P, int variant, int ignore_collisions, vxh_model& M) {
             const vxg_vox_class& c1 = M.vclasses[M.vox_class[v1]]; const vxg_vox_class& c2 = M.vclasses[M.vox_class[v2]];
             if ((c1.dof_fixed & 0x3F) == 0x3F && (c2.dof_fixed & 0x3F) == 0x3F) continue;   // CreatePermBond: no bond between two fully fixed voxels (VX_Sim.cpp:728)
             const Material& m1 = P.palette[c1.mat_index]; const Material& m2 = P.palette[c2.mat_index];
-            double E1 = m1.e, E2 = m2.e, u1 = m1.poisson, u2 = m2.poisson;
+            // Vox_E at LinkVoxels time (VX_Bond.cpp:83): the palette modulus, or the evolved one in the land/water fork
+            double E1 = lw ? c1.e_mod : m1.e, E2 = lw ? c2.e_mod : m2.e, u1 = m1.poisson, u2 = m2.poisson;
             if (E1 == 0 || E2 == 0) continue;                           // LinkVoxels fails: no bond (VX_Bond.cpp:87)
             if (u1 < 0 || u1 > 0.5 || u2 < 0 || u2 > 0.5) continue;     // (VX_Bond.cpp:88)
             const double pitch = M.nom_pos[3 * v2 + ax] - M.nom_pos[3 * v1 + ax];
-            BKey key(c1.mat_index, c2.mat_index, llround(pitch / s * 1e9));   // bond constants depend on the materials only (not on per-voxel phase)
+            BKey key(c1.mat_index, c2.mat_index, llround(pitch / s * 1e9), E1, E2);   // bond constants depend on the materials / moduli only (not on per-voxel phase)
             auto it = bkeys.find(key);
             if (it == bkeys.end()) {
                 vxg_bond_class b; memset(&b, 0, sizeof b);
@@ -562,7 +641,7 @@ int flatten(const Parsed& P, int variant, int ignore_collisions, vxh_model& M) {
                 b.a1 = E * A / L; b.a2 = G * J / L;
                 b.b1 = 12 * E * Iy / (L * L * L); b.b2 = 6 * E * Iy / (L * L); b.b3 = 2 * E * Iy / L;
                 b.len = L; b.area = c1.nom_size * c1.nom_size;           // CSArea reset to s^2 by both voxels (VXS_Voxel.cpp:625-631)
-                b.e1 = E1; b.e2 = E2;
+                b.e1 = lw ? (double)(float)E1 : E1; b.e2 = lw ? (double)(float)E2 : E2;   // LW: `float voxelEmod` (LW/VX_Object.cpp:1472-1474)
                 b.nom_dist = pitch;
                 double FM1 = c1.mass * c1.nom_size / 2, FM2 = c2.mass * c2.nom_size / 2;
                 b.c_a1m1 = 2.0 * sqrt(b.a1 * c1.mass); b.c_a1m2 = 2.0 * sqrt(b.a1 * c2.mass);
@@ -594,6 +673,7 @@ int flatten(const Parsed& P, int variant, int ignore_collisions, vxh_model& M) {
     sp.temp_amplitude = (double)(float)P.temp_amplitude;
     sp.min_scale_fact = P.min_temp_fact;
     sp.max_scale_fact = 1.0 + P.growth_amp;
+    sp.growth_amplitude = lw ? 0.0 : P.growth_amp; sp.midlife_freeze_time = lw ? 0.0 : P.midlife_freeze; sp.stop_condition_value = lw ? 0.0 : P.stop_value;   // read by the _voxcad scale law only
     sp.lattice_dim = P.lat; sp.drag_coeff = P.drag; sp.col_horizon = P.col_horizon;
     uint32_t fl = 0;
     if (P.floor_on) fl |= VXG_F_FLOOR;

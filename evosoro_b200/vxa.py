@@ -114,7 +114,7 @@ def _fmt(v) -> str:
 
 def vxa_text(structure: np.ndarray, palette: Sequence[Material] = None, sim: SimParams = None,
              env: EnvParams = None, phase_offset: Optional[np.ndarray] = None,
-             boundary_conditions: Optional[Sequence[Region]] = None) -> str:
+             boundary_conditions: Optional[Sequence[Region]] = None, per_voxel: Optional[dict] = None) -> str:
     """Return the ``.vxa`` text for one robot.
 
     ``structure`` is an integer array indexed ``[x, y, z]`` of material IDs (0 = empty), the same
@@ -122,6 +122,9 @@ def vxa_text(structure: np.ndarray, palette: Sequence[Material] = None, sim: Sim
     ``phase_offset`` (same shape, floats) is written as a ``<PhaseOffset>`` block when given.
     ``boundary_conditions`` (fixed / forced regions) are written as a ``<Boundary_Conditions>`` block; evosoro
     itself always writes the empty legacy ``<Fixed_Regions>`` / ``<Forced_Regions>`` pair.
+    ``per_voxel`` maps further per-voxel block names (``TempAmpDamp``, ``FinalPhaseOffset``, ``InitialVoxelSize``,
+    ``FinalVoxelSize``, ``GrowthTime``, ``StartGrowthTime``, ``Stiffness`` ...; reference: read_write_voxelyze.py:403-520,
+    VX_Object.cpp:1879-2322) to float arrays of the structure's shape, written like ``<PhaseOffset>``.
     """
     palette = list(palette) if palette is not None else four_material_palette()
     sim = sim or SimParams()
@@ -263,13 +266,15 @@ def vxa_text(structure: np.ndarray, palette: Sequence[Material] = None, sim: Sim
         layer = "".join(str(int(st[x, y, z])) for y in range(ny) for x in range(nx))
         w(f"<Layer><![CDATA[{layer}]]></Layer>")
     w("</Data>")
-    if phase_offset is not None:
-        po = np.asarray(phase_offset, dtype=float)
-        w("<PhaseOffset>")
+    blocks = {} if phase_offset is None else {"PhaseOffset": phase_offset}
+    blocks.update(per_voxel or {})
+    for tag, arr in blocks.items():
+        po = np.asarray(arr, dtype=float)
+        w(f"<{tag}>")
         for z in range(nz):
-            layer = "".join(f"{po[x, y, z]!r}, " for y in range(ny) for x in range(nx))
+            layer = "".join(f"{float(po[x, y, z])!r}, " for y in range(ny) for x in range(nx))   # plain decimal text: the engines read it with atof
             w(f"<Layer><![CDATA[{layer}]]></Layer>")
-        w("</PhaseOffset>")
+        w(f"</{tag}>")
     w("</Structure>")
     w("</VXC>")
     w("</VXA>")

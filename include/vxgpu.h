@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define VXG_ABI_VERSION 2
+#define VXG_ABI_VERSION 3
 
 /* ---- return codes ------------------------------------------------------------------------------ */
 enum {
@@ -88,7 +88,23 @@ typedef struct vxg_vox_class {
     double ext_tdisp[3];  /* ExternalTDisp (fixed rot. DOFs)          VX_Sim.cpp:579-581             */
     int32_t dof_fixed;    /* VXG_DOF_* mask                           VX_Voxel.h:90                  */
     int32_t mat_index;    /* palette index (fitness probes key on 5/6/7, VX_Sim.cpp:2626)            */
+    /* development (VX_Sim.cpp:878-975 sets them at reset, VXS_Voxel.cpp:240-318 reads them every step); all of them are
+     * `float` members upstream (VXS_Voxel.h:92-100): the values here are the float-rounded ones.  Zeros + dev_flags 0 =
+     * no development (every file evosoro's stock experiments write). */
+    double final_size;            /* finalVoxelSize                    VX_Sim.cpp:908-924             */
+    double growth_time;           /* growthTime                        VX_Sim.cpp:957-974             */
+    double start_growth_time;     /* startGrowthTime                   VX_Sim.cpp:927-953             */
+    double final_phase_offset;    /* finalPhaseOffset                  VX_Sim.cpp:883                 */
+    double final_temp_amp_damp;   /* finalTempAmpDamp                  VX_Sim.cpp:886                 */
+    int32_t dev_flags;            /* VXG_DEV_*                                                        */
+    int32_t reserved;
 } vxg_vox_class;
+
+#define VXG_DEV_FINAL_SIZE  0x1  /* GetUsingFinalVoxelSize()   VXS_Voxel.cpp:272-275                          */
+#define VXG_DEV_FINAL_PHASE 0x2  /* GetUsingFinalPhaseOffset() VXS_Voxel.cpp:278-284                          */
+#define VXG_DEV_FINAL_TAD   0x4  /* GetUsingFinalTempAmpDamp() VXS_Voxel.cpp:286-289                          */
+#define VXG_DEV_SIZE_ADJUST 0x8  /* GetUsingInitialVoxelSize() || GetUsingFinalVoxelSize(): actuation is scaled by the
+                                    voxel's current size, VXS_Voxel.cpp:308-318                                 */
 
 /* Per-bond constants, de-duplicated into classes (a class = an ordered material pair in
  * evosoro-written files).  VX_Bond.cpp:65-109 (LinkVoxels), :123-173 (UpdateConstants).
@@ -130,6 +146,9 @@ typedef struct vxg_sim_params {
     double col_horizon;     /* CollisionHorizon (VXG_F_COLLISIONS), in lattice pitches  VX_Sim.cpp:1741, :2357-2385 */
     uint32_t flags;         /* VXG_F_*                                                               */
     uint32_t reserved;
+    double growth_amplitude;     /* getGrowthAmplitude()   VXS_Voxel.cpp:313 (size-adjusted actuation)       */
+    double midlife_freeze_time;  /* GetMidLifeFreezeTime() VXS_Voxel.cpp:241-259, :266                       */
+    double stop_condition_value; /* GetStopConditionValue() (the freeze window is centred on the lifetime)   */
 } vxg_sim_params;
 
 /* One imported robot, flat.  Voxel i is the reference's simulation index i (rank among occupied

@@ -57,7 +57,7 @@ struct Ref {
 };
 
 #define N_SIM 24
-#define N_VD 36
+#define N_VD 42
 #define N_BD 4
 #define N_VS 15
 #define N_BS 14
@@ -93,6 +93,7 @@ static void dump_header(FILE* f, Ref& r, long long nframes) {
     sp[19] = S.getMinTempFact();
     sp[20] = S.pEnv->getGrowthAmplitude();
     sp[21] = S.GetAfterlifeTime();
+    sp[22] = S.GetMidLifeFreezeTime();
 #else
     sp[19] = 0.1; /* MIN_TEMP_FACTOR, LW/VX_Sim.h:31 */
     sp[22] = S.pEnv->GetFluidEnvironment() ? 1 : 0;
@@ -123,6 +124,12 @@ static void dump_header(FILE* f, Ref& r, long long nframes) {
         Vec3D<> ed = v.*(&VoxBcAccess::ExternalDisp), ea = v.*(&VoxBcAccess::ExternalTDisp);
         d[24] = ef.x; d[25] = ef.y; d[26] = ef.z; d[27] = et.x; d[28] = et.y; d[29] = et.z;
         d[30] = ed.x; d[31] = ed.y; d[32] = ed.z; d[33] = ea.x; d[34] = ea.y; d[35] = ea.z;
+#ifndef REF_LW   /* development parameters as ResetSimulation left them (VX_Sim.cpp:878-975) */
+        d[36] = v.finalVoxelSize; d[37] = v.growthTime; d[38] = v.startGrowthTime; d[39] = v.finalPhaseOffset; d[40] = v.finalTempAmpDamp;
+        CVX_Object* O = S.pEnv->pObj;
+        d[41] = (O->GetUsingFinalVoxelSize() ? 1 : 0) | (O->GetUsingFinalPhaseOffset() ? 2 : 0) | (O->GetUsingFinalTempAmpDamp() ? 4 : 0) |
+                ((O->GetUsingInitialVoxelSize() || O->GetUsingFinalVoxelSize()) ? 8 : 0);
+#endif
         wr(f, d, sizeof d);
     }
     for (int j = 0; j < S.NumBond(); j++) {

@@ -623,16 +623,46 @@ static void voxel_step(vxo_sim* s, int i) {
             tf = (1 + (P->temp_amplitude * sin(2 * 3.1415926f * (s->cur_time / P->temp_period + c->phase_offset))) * c->cte);
         if (tf < P->min_scale_fact) tf = P->min_scale_fact;
         s->scale[i] = tf * c->nom_size;
-    } else {                                                            /* VXS_Voxel.cpp:224-336, in-scope subset */
-        double max_scale = P->max_scale_fact * c->nom_size;
-        double min_scale = P->min_scale_fact * c->nom_size;
-        double ctrl = 0;
-        if ((P->flags & VXG_F_TEMPERATURE) && s->cur_time >= P->init_cm_time)
-            ctrl = c->temp_amp_damp * (P->temp_amplitude * sin(2 * 3.1415926f * (s->cur_time / P->temp_period + c->phase_offset))) * c->cte * 1;
+    } else {                                                            /* VXS_Voxel.cpp:224-336 (without the velocity-adjusted windows :340-381) */
+        double max_scale = P->max_scale_fact * c->nom_size;             /* :225 */
+        double min_scale = P->min_scale_fact * c->nom_size;             /* :226 */
+        double t = s->cur_time;
+        double ctrl = 0, dev = 0, dphase = 0, dtad = 0, k = 0, frozen_adj = 0, freeze_init = 1;
         /* prenatal ramp :237-238 (initialVoxelSize is a float member, so the ratio is not exactly 1) */
-        double cc = (s->cur_time >= 0.5 * P->init_cm_time) ? 1.0 : 2 * s->cur_time / P->init_cm_time;
+        double cc = (t >= 0.5 * P->init_cm_time) ? 1.0 : 2 * t / P->init_cm_time;
         double prenatal = cc * ((c->init_size / c->nom_size) - 1);
-        double cur = ctrl * c->nom_size + (1 + prenatal) * (1 + 0.0) * c->nom_size;  /* :321 */
+        if (P->midlife_freeze_time > 0) {                               /* :241-259 */
+            double middle = 0.5 * (P->stop_condition_value - P->init_cm_time);
+            double fstart = middle - 0.5 * P->midlife_freeze_time, fend = middle + 0.5 * P->midlife_freeze_time;
+            if (t > fstart && t < fend) {
+                frozen_adj = t - fstart;
+                if (t < fstart + P->init_cm_time) freeze_init = 0;
+            }
+            if (t > fend) frozen_adj = P->midlife_freeze_time;
+        }
+        {   /* postnatal linear development :262-291; the members are floats upstream, so float op float stays float */
+            float start_f = (float)c->start_growth_time, growth_f = (float)c->growth_time;
+            if (t >= start_f && growth_f > 0) {
+                double eff = (t <= start_f + growth_f + P->midlife_freeze_time) ? t : start_f + growth_f + P->midlife_freeze_time;
+                eff = eff - frozen_adj;
+                k = (eff - start_f) / growth_f;
+                if (c->dev_flags & VXG_DEV_FINAL_SIZE) dev = k * (((float)c->final_size / (float)c->init_size) - 1.0);
+                if (c->dev_flags & VXG_DEV_FINAL_PHASE) dphase = k * ((float)c->final_phase_offset - (float)c->phase_offset);
+                if (c->dev_flags & VXG_DEV_FINAL_TAD) dtad = k * ((float)c->final_temp_amp_damp - (float)c->temp_amp_damp);
+            }
+        }
+        if ((P->flags & VXG_F_TEMPERATURE) && t >= P->init_cm_time) {  /* :294-305 */
+            double phase = c->phase_offset + dphase, tad = c->temp_amp_damp + dtad;
+            ctrl = tad * (P->temp_amplitude * sin(2 * 3.1415926f * (t / P->temp_period + phase))) * c->cte * freeze_init;
+        }
+        if (c->dev_flags & VXG_DEV_SIZE_ADJUST) {                       /* :308-318 */
+            double cur_size = (1 + prenatal) * (1 + dev) * c->nom_size;
+            double original = (cur_size / c->nom_size - 1) / P->growth_amplitude;
+            double positive = (original + 1) * 0.5;
+            double capped = (positive > 0.5) ? 0.5 : positive;
+            ctrl = ctrl * capped * 2;
+        }
+        double cur = ctrl * c->nom_size + (1 + prenatal) * (1 + dev) * c->nom_size;  /* :321 */
         if (cur < s->last_scale[i] && cur < min_scale) cur = s->last_scale[i];
         if (cur > s->last_scale[i] && cur > max_scale) cur = s->last_scale[i];
         s->scale[i] = cur;

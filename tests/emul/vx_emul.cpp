@@ -111,8 +111,11 @@ template <typename Real, bool COMPACT = false, bool FLUID = false, bool COLLIDE 
             for (int v = 0; v < ctl.n_vox; v++) { Real x = voxel_task<Real>(R, C, v, R.stat[v], load_own<Real>(R, v), fl[v], F[v], M[v]); if (x > sp2) sp2 = x; }
             max_vel = sizeof(Real) == 8 ? sqrt((double)sp2) : sqrt((double)(float)sp2);
             for (int i = 0; i < ctl.n_vclass; i++) {
-                double ns = scale_law(sk[i], scale_c[cur][i], ctl.cur_time, ctl.init_cm_time, ctl.temp_period, ctl.temp_amplitude,
-                                      ctl.min_fact, ctl.max_fact, temp_on, lw);
+                ScaleSim SL;
+                SL.init_cm_time = ctl.init_cm_time; SL.temp_period = ctl.temp_period; SL.temp_amplitude = ctl.temp_amplitude;
+                SL.min_fact = ctl.min_fact; SL.max_fact = ctl.max_fact; SL.growth_amp = ctl.growth_amp;
+                SL.midlife_freeze = ctl.midlife_freeze; SL.stop_value = ctl.stop_value; SL.temp_on = temp_on; SL.lw = lw;
+                double ns = scale_law(sk[i], scale_c[cur][i], ctl.cur_time, SL);
                 scale_c[cur ^ 1][i] = ns;
                 dsc_c[cur ^ 1][i] = (Real)(ns - sk[i].nom_size);
             }

@@ -111,6 +111,9 @@ def desc_from_dump(d: RefDump, lw: bool = False, col_horizon: float = 2.0) -> ab
     sp.min_scale_fact = S[19]
     sp.max_scale_fact = 1.0 + S[20]
     sp.lattice_dim = S[14]
+    if not lw:
+        sp.growth_amplitude, sp.stop_condition_value = S[20], S[12]
+        sp.midlife_freeze_time = S[22]
     sp.col_horizon = col_horizon   # CollisionHorizon is not reachable through the reference's public API: the caller reads it from the .vxa
     flags = 0
     if S[15]: flags |= abi.VXG_F_COLLISIONS
@@ -130,14 +133,18 @@ def desc_from_dump(d: RefDump, lw: bool = False, col_horizon: float = 2.0) -> ab
         v = d.vox[i]
         s, mat, E, nu, cte, mass, inertia, fm = v[3], int(v[4]), v[5], v[6], v[7], v[8], v[9], v[10]
         bc = tuple(v[24:36]) if len(v) >= 36 else (0.0,) * 12   # boundary-condition columns (dumps written before them: none)
-        key = (s, mat, E, nu, cte, mass, v[11], v[12], v[16], v[21], int(v[19]), v[14], v[22]) + bc
+        dev = tuple(v[36:42]) if (len(v) >= 42 and not lw) else (0.0,) * 6   # development columns
+        key = (s, mat, E, nu, cte, mass, v[11], v[12], v[16], v[21], int(v[19]), v[14], v[22]) + bc + dev
         if key not in vkeys:
             c = abi.VoxClass()
             c.mass = mass; c.mass_inv = 1 / mass
             c.inertia = inertia; c.inertia_inv = 1 / inertia
-            c.damp_lin = 2 * math.sqrt(mass * E * s)
-            c.damp_ang = 2 * math.sqrt(inertia * E * s * s * s)
-            c.k_floor = 2 * E * s
+            # _voxcad: SetMaterial caches the damping terms with the palette modulus (VX_Voxel.cpp:116-125) BEFORE an evolved
+            # <Stiffness> overrides Vox_E (VX_Sim.cpp:983-988); GetLinearStiffness reads Vox_E live
+            Em = v[5] if lw else v[14]   # the land/water fork's SetEMod refreshes the cached terms (LW/VX_Voxel.h:61)
+            c.damp_lin = 2 * math.sqrt(mass * Em * s)
+            c.damp_ang = 2 * math.sqrt(inertia * Em * s * s * s)
+            c.k_floor = v[23]
             c.mu_static, c.mu_dynamic = v[11], v[12]
             c.nom_size = s
             c.cte = cte
@@ -146,6 +153,8 @@ def desc_from_dump(d: RefDump, lw: bool = False, col_horizon: float = 2.0) -> ab
             c.e_mod = E
             c.init_size = v[22]
             c.dof_fixed = int(v[19])
+            c.final_size, c.growth_time, c.start_growth_time, c.final_phase_offset, c.final_temp_amp_damp = dev[0:5]
+            c.dev_flags = int(dev[5])
             for a in range(3):
                 c.ext_force[a], c.ext_torque[a], c.ext_disp[a], c.ext_tdisp[a] = bc[a], bc[3 + a], bc[6 + a], bc[9 + a]
             c.mat_index = mat
@@ -163,11 +172,15 @@ def desc_from_dump(d: RefDump, lw: bool = False, col_horizon: float = 2.0) -> ab
         nomd = v2[ax] - v1[ax]
         # stress model modulus: _voxcad uses the palette material's Elastic_Mod (VX_Object.cpp:1477);
         # the land/water fork passes the voxel's own (possibly evolved) modulus (LW/VX_Object.cpp:1474)
-        e1s, e2s = (v1[5], v2[5]) if lw else (v1[14], v2[14])
+        # (through a `float voxelEmod` parameter, LW/VX_Object.cpp:1472-1474)
+        e1s, e2s = (f32(v1[5]), f32(v2[5])) if lw else (v1[14], v2[14])
         homog = int(v1[4]) == int(v2[4]) and (not lw or v1[5] == v2[5])
         key = (int(v1[4]), int(v2[4]), v1[5], v2[5], v1[6], v2[6], v1[3], v2[3], v1[8], v2[8], round(nomd / v1[3], 9))
         if key not in bkeys:
-            E1, E2, u1, u2 = v1[5], v2[5], v1[6], v2[6]
+            # LinkVoxels reads Vox_E (VX_Bond.cpp:83): in _voxcad the internal bonds are linked during Import, before the reset
+            # that applies an evolved <Stiffness>, so they keep the palette modulus; the land/water fork overrides Vox_E first
+            E1, E2 = (v1[5], v2[5]) if lw else (v1[14], v2[14])
+            u1, u2 = v1[6], v2[6]
             E = (E1 * E2 / (E1 + E2)) * 2
             u = 0.0 if (u1 == 0 and u2 == 0) else (u1 * u2 / (u1 + u2)) * 2
             L = (v1[3] + v2[3]) * 0.5

@@ -23,12 +23,12 @@ OUT = os.path.join(ROOT, "tests", "golden")
 TMP = "/tmp/vx_golden"
 
 
-def case(name, structure, n_steps, every, sim=None, env=None, palette=None, phase=None, lw=False, full=False, col=False, bcs=None):
+def case(name, structure, n_steps, every, sim=None, env=None, palette=None, phase=None, lw=False, full=False, col=False, bcs=None, per_voxel=None):
     os.makedirs(TMP, exist_ok=True)
     if full:   # the stock CLI writes its result file where <FitnessFileName> says
         sim = sim or vxa.SimParams()
         sim.fitness_file = os.path.join(TMP, name + "_result.xml")
-    text = vxa.vxa_text(structure, palette=palette, sim=sim, env=env, phase_offset=phase, boundary_conditions=bcs)
+    text = vxa.vxa_text(structure, palette=palette, sim=sim, env=env, phase_offset=phase, boundary_conditions=bcs, per_voxel=per_voxel)
     path = os.path.join(TMP, name + ".vxa")
     with open(path, "w") as f:
         f.write(text)
@@ -132,8 +132,38 @@ def bc_cases():
     case("bc_block4_first30", blk, 30, 1, sim=S(init_cm_time=0.0005, stop_condition_value=0.2), env=E(floor_enabled=0), bcs=bcs)
 
 
+def dev_cases():
+    """per-voxel development and evolved stiffness (VX_Sim.cpp:878-991, VXS_Voxel.cpp:224-336)"""
+    S, E = vxa.SimParams, vxa.EnvParams
+    rng = np.random.RandomState(8)
+    u = lambda n, lo, hi: rng.uniform(lo, hi, (n, n, n))
+    soft = (1, 3, 4)   # no bone: dt = 6.4e-4 s, so a 0.3 s life is ~470 steps
+    # everything at once: initial / final size, growth window, developing phase and amplitude; MinGrowthTime clamps some windows
+    pv = {"InitialVoxelSize": u(4, -1, 1), "FinalVoxelSize": u(4, -1, 1), "GrowthTime": u(4, 0, 1), "StartGrowthTime": u(4, 0, 1),
+          "FinalPhaseOffset": u(4, -0.5, 0.5), "TempAmpDamp": u(4, 0.2, 1), "FinalTempAmpDamp": u(4, 0.2, 1)}
+    case("dev_growth4", vxa.dense_lattice(4, 51, materials=soft), 480, 40, sim=S(init_cm_time=0.02, stop_condition_value=0.3),
+         env=E(growth_amplitude=0.75, extra_tags={"MinGrowthTime": 0.05}), phase=u(4, -0.5, 0.5), per_voxel=pv)
+    # final size only (growth starts at InitCmTime and lasts the whole life) with a mid-life freeze
+    case("dev_freeze3", vxa.dense_lattice(3, 52, materials=soft), 480, 40, sim=S(init_cm_time=0.02, stop_condition_value=0.3, mid_life_freeze_time=0.06),
+         env=E(growth_amplitude=0.5), per_voxel={"FinalVoxelSize": u(3, -1, 1)})
+    # initial size only: prenatal ramp to a per-voxel size, actuation scaled by size; shrinking below MinTempFact is clamped
+    case("dev_initsize3_first40", vxa.dense_lattice(3, 53, materials=soft), 40, 1, sim=S(init_cm_time=0.01, stop_condition_value=0.3, min_temp_fact=0.6),
+         env=E(growth_amplitude=0.75), per_voxel={"InitialVoxelSize": u(3, -1, 1)})
+    # evolved stiffness: floor contact and contact bonds follow it, the internal bonds keep the palette modulus
+    stiff = lambda n: 10 ** rng.uniform(np.log10(5e6), np.log10(5e8), (n, n, n))
+    # (_voxcad keeps dt at the palette's bond stiffness, so a much stiffer evolved floor contact chatters and amplifies rounding
+    # differences between any two fp64 evaluation orders: the fixture stays within 3x of the palette modulus)
+    case("dev_stiffness3", vxa.dense_lattice(3, 54, materials=soft), 600, 50, sim=S(init_cm_time=0.02, stop_condition_value=0.3),
+         per_voxel={"Stiffness": 10 ** rng.uniform(np.log10(1e6), np.log10(1.5e7), (3, 3, 3))})
+    case("dev_stiffness_col_pincer", pincer(), 600, 50, sim=S(init_cm_time=0.005, stop_condition_value=0.5, self_col_enabled=1), col=True,
+         per_voxel={"Stiffness": 10 ** rng.uniform(np.log10(5e6), np.log10(5e7), pincer().shape)})
+    case("lw_stiffness3", vxa.dense_lattice(3, 55, materials=soft), 600, 50, sim=S(init_cm_time=0.02, stop_condition_value=0.3), lw=True, per_voxel={"Stiffness": stiff(3)})
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "bc":
+    if len(sys.argv) > 1 and sys.argv[1] == "dev":
+        dev_cases()
+    elif len(sys.argv) > 1 and sys.argv[1] == "bc":
         bc_cases()
     elif len(sys.argv) > 1 and sys.argv[1] == "fluid":
         fluid_cases()
@@ -144,3 +174,4 @@ if __name__ == "__main__":
         fluid_cases()
         collision_cases()
         bc_cases()
+        dev_cases()
