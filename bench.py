@@ -299,7 +299,10 @@ def gpu_arm(args):
         e2e_s = float(t[0])
     e2e_value = units_per_step * ke / e2e_s
     h2d = eb.h2d_bytes_per_upload()
-    d2h = R * eb.limits.max_vox * 3 * 8
+    stride = 64
+    while stride < eb.limits.max_vox:
+        stride *= 2
+    d2h = R * stride * 3 * 8   # the position planes of every blob at the device stride (the per-robot control blocks, ~0.3 KB each, not counted)
     if not np.isfinite(pos).all():
         raise SystemExit("bench.py: non-finite positions from the e2e path")
     eb.close()

@@ -512,6 +512,14 @@ VX_HD bool voxel_integrate(const VoxK<T>& k, V3<T> F, V3<T> M, double half_scale
 // windows (:340-381) depend on simulation state and are rejected at import.  Land/water fork: LW/VXS_Voxel.cpp:211-235.
 // `t` is CurTime BEFORE the increment.  The development members are `float` upstream, so differences / quotients
 // of two of them are float operations there (usual arithmetic conversions) and are restated as such.
+// IEEE-rounded float quotient whatever the translation unit's --prec-div setting (the reference divides two float members)
+VX_HD float vx_fdiv_ieee(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fdiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
 struct ScaleK {
     double nom_size, init_size, cte, temp_amp_damp, phase_offset;
     double final_size, growth_time, start_growth, final_phase, final_tad;
@@ -545,7 +553,7 @@ VX_HD double scale_law(const ScaleK& c, double last_scale, double t, const Scale
         double eff = (t <= lim) ? t : lim;
         eff = eff - frozen_adj;
         double k = (eff - c.start_growth) / c.growth_time;
-        if (c.dev_flags & 0x1) dev = k * ((double)((float)c.final_size / (float)c.init_size) - 1.0);
+        if (c.dev_flags & 0x1) dev = k * ((double)vx_fdiv_ieee((float)c.final_size, (float)c.init_size) - 1.0);
         if (c.dev_flags & 0x2) dphase = k * (double)((float)c.final_phase - (float)c.phase_offset);
         if (c.dev_flags & 0x4) dtad = k * (double)((float)c.final_tad - (float)c.temp_amp_damp);
     }

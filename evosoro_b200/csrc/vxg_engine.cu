@@ -62,8 +62,10 @@ struct vxg_batch {
     bool dirty = false;          // host mirrors newer than device
     bool ctl_dirty = false;      // only h_ctl newer (step budget)
     std::vector<char> uploaded;
+    std::vector<char> reset_image;   // the slot's host mirror is the plain reset image vxg_upload packed (nothing pulled or edited since)
     std::vector<std::vector<int32_t>> bond_v1, bond_v2, bond_axis;   // for download mapping
     int64_t launches = 0;
+    size_t last_upload_bytes = 0;    // blob + NominalPosition bytes the last population upload copied host -> device
     int vpt = 1, threads = 32;
     bool smem_mode = true;
     size_t smem_bytes = 0;
@@ -201,7 +203,7 @@ extern "C" int vxg_create(vxg_batch** out, int device, int n_robots, const vxg_l
         free_all(b); delete b; cudaGetLastError();
         return fail(e == cudaErrorMemoryAllocation ? VXG_ERR_NOMEM : VXG_ERR_CUDA, "vxg_create: %s", cudaGetErrorString(e));
     }
-    b->uploaded.assign(nr, 0);
+    b->uploaded.assign(nr, 0); b->reset_image.assign(nr, 0);
     b->bond_v1.resize(nr); b->bond_v2.resize(nr); b->bond_axis.resize(nr);
     for (size_t r = 0; r < nr; r++) { b->h_ctl[r].status = VXG_ST_FINISHED; b->h_ctl[r].total_steps = 0; }  // empty slots never run
     b->dirty = true;
@@ -293,9 +295,31 @@ extern "C" int vxg_upload(vxg_batch* b, int robot, const vxg_robot_desc* d) {
     b->bond_v1[robot].assign(d->bond_v1, d->bond_v1 + d->n_bond);
     b->bond_v2[robot].assign(d->bond_v2, d->bond_v2 + d->n_bond);
     b->bond_axis[robot].assign(d->bond_axis, d->bond_axis + d->n_bond);
-    b->uploaded[robot] = 1;
+    b->uploaded[robot] = 1; b->reset_image[robot] = 1;
     b->dirty = true;
     return VXG_OK;
+}
+
+// Device-side half of ResetSimulation (VX_Sim.cpp:839-877, VXS_Voxel.cpp:92-128, VXS_BondInternal.cpp:40-54) for slots whose
+// host mirror is a plain reset image: only the words that differ per robot travel over PCIe (nominal positions and the
+// static section); Angle = identity, zero momenta / damping history / accumulators, SmallAngle = true and the
+// NominalPosition table are written here.  One CTA per robot slot.
+template <typename Real>
+__global__ void __launch_bounds__(256) vx_reset_kernel(unsigned char* blobs, BlobLayout L, const RobotCtl* ctl, double* nom) {
+    const int robot = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    unsigned char* blob = blobs + (size_t)robot * L.total_bytes;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    uint4* a = (uint4*)(blob + L.off_quat);
+    for (size_t i = tid; i < ((L.dyn_bytes - L.off_quat) >> 4); i += T) a[i] = z;
+    uint4* c = (uint4*)(blob + L.stat_bytes);
+    for (size_t i = tid; i < ((L.total_bytes - L.stat_bytes) >> 4); i += T) c[i] = z;
+    __syncthreads();
+    RobotView<Real> R = make_view<Real>(blob, L, 0);
+    int n_vox = ctl[robot].n_vox;
+    if (n_vox > L.nv) n_vox = L.nv;
+    for (int v = tid; v < n_vox; v += T) { R.quat[v].x = (Real)1; R.flags[v] = VX_FL_SMALL_ALL; }
+    double* nm = nom + (size_t)robot * 3 * L.nv;
+    for (int i = tid; i < 3 * L.nv; i += T) nm[i] = R.pos[i];
 }
 
 // make the device copy current (host mirrors -> device) on the batch stream
@@ -309,7 +333,24 @@ static int flush(vxg_batch* b) {
         b->compact = compact;
         if (compact) { b->smem_mode = true; b->smem_bytes = b->L.total_bytes + b->tb_compact; }
         else { b->smem_mode = b->smem_wide_fits; b->smem_bytes = b->smem_wide_fits ? b->L.total_bytes + b->tb_wide : b->tb_wide; }
-        CK(cudaMemcpyAsync(b->d_blobs, b->h_blobs, nr * b->L.total_bytes, cudaMemcpyHostToDevice, b->stream));
+        bool sparse = true;   // every slot still holds the reset image vxg_upload packed: positions + static section travel, the rest is written on the device
+        for (size_t r = 0; r < nr && sparse; r++) if (b->uploaded[r] && !b->reset_image[r]) sparse = false;
+        b->last_upload_bytes = 0;
+        if (sparse) {
+            const size_t pos_bytes = 3 * nv * sizeof(double), st_bytes = b->L.stat_bytes - b->L.off_stat, tb = b->L.total_bytes;
+            CK(cudaMemcpy2DAsync(b->d_blobs + b->L.off_pos, tb, b->h_blobs + b->L.off_pos, tb, pos_bytes, nr, cudaMemcpyHostToDevice, b->stream));
+            CK(cudaMemcpy2DAsync(b->d_blobs + b->L.off_stat, tb, b->h_blobs + b->L.off_stat, tb, st_bytes, nr, cudaMemcpyHostToDevice, b->stream));
+            CK(cudaMemcpyAsync(b->d_ctl, b->h_ctl, nr * sizeof(RobotCtl), cudaMemcpyHostToDevice, b->stream));
+            if (b->prec == VXG_PREC_F64) vx_reset_kernel<double><<<(unsigned)nr, 256, 0, b->stream>>>(b->d_blobs, b->L, b->d_ctl, b->d_nom);
+            else vx_reset_kernel<float><<<(unsigned)nr, 256, 0, b->stream>>>(b->d_blobs, b->L, b->d_ctl, b->d_nom);
+            CK(cudaGetLastError());
+            b->launches++;
+            b->last_upload_bytes += nr * (pos_bytes + st_bytes);
+        } else {
+            CK(cudaMemcpyAsync(b->d_blobs, b->h_blobs, nr * b->L.total_bytes, cudaMemcpyHostToDevice, b->stream));
+            CK(cudaMemcpyAsync(b->d_nom, b->h_nom, nr * 3 * nv * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+            b->last_upload_bytes += nr * (b->L.total_bytes + 3 * nv * sizeof(double));
+        }
         if (compact) CK(cudaMemcpyAsync(b->d_bk, b->h_bkc, nr * mb * b->bkc_sz(), cudaMemcpyHostToDevice, b->stream));
         else CK(cudaMemcpyAsync(b->d_bk, b->h_bk, nr * mb * b->bk_sz(), cudaMemcpyHostToDevice, b->stream));
         CK(cudaMemcpyAsync(b->d_bk_dist, b->h_bk_dist, nr * mb * sizeof(double), cudaMemcpyHostToDevice, b->stream));
@@ -318,7 +359,6 @@ static int flush(vxg_batch* b) {
         CK(cudaMemcpyAsync(b->d_scale_c, b->h_scale_c, nr * mv * sizeof(double), cudaMemcpyHostToDevice, b->stream));
         CK(cudaMemcpyAsync(b->d_ext_disp, b->h_ext_disp, nr * mv * 3 * b->rs(), cudaMemcpyHostToDevice, b->stream));
         CK(cudaMemcpyAsync(b->d_ext_tdisp, b->h_ext_tdisp, nr * mv * 3 * b->rs(), cudaMemcpyHostToDevice, b->stream));
-        CK(cudaMemcpyAsync(b->d_nom, b->h_nom, nr * 3 * nv * sizeof(double), cudaMemcpyHostToDevice, b->stream));
         if (b->lim.max_col_pairs > 0) {
             CK(cudaMemcpyAsync(b->d_col_pairs, b->h_col_pairs, nr * (size_t)b->lim.max_col_pairs * sizeof(ColPair), cudaMemcpyHostToDevice, b->stream));
             CK(cudaMemcpyAsync(b->d_col_surf, b->h_col_surf, nr * nv * sizeof(int16_t), cudaMemcpyHostToDevice, b->stream));
@@ -340,6 +380,7 @@ static int pull(vxg_batch* b, bool blobs, int robot) {
         if (blobs) {
             size_t r0 = robot < 0 ? 0 : (size_t)robot, cnt = robot < 0 ? nr : 1;
             CK(cudaMemcpyAsync(b->h_blobs + r0 * b->L.total_bytes, b->d_blobs + r0 * b->L.total_bytes, cnt * b->L.total_bytes, cudaMemcpyDeviceToHost, b->stream));
+            for (size_t r = r0; r < r0 + cnt; r++) b->reset_image[r] = 0;
             CK(cudaMemcpyAsync(b->h_scale_c + r0 * mv, b->d_scale_c + r0 * mv, cnt * mv * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
         }
     }
@@ -534,6 +575,7 @@ extern "C" int vxg_upload_state(vxg_batch* b, int robot, const vxg_robot_state* 
     int rc = pull(b, true, -1);   // whole batch: the next flush re-uploads every blob
     if (rc) return rc;
     if (b->prec == VXG_PREC_F64) pack_state<double>(b, robot, in); else pack_state<float>(b, robot, in);
+    b->reset_image[robot] = 0;
     b->h_ctl[robot].cur_time = cur_time;
     b->h_ctl[robot].step = cur_step;
     b->dirty = true;
@@ -587,9 +629,12 @@ extern "C" int vxg_mesh_vertex_count(const vxg_robot_desc* d) {
 extern "C" int64_t vxg_upload_bytes(vxg_batch* b) {
     if (!b) return 0;
     size_t nr = (size_t)b->n_robots, mv = (size_t)b->lim.max_vclass, mb = (size_t)b->lim.max_bclass, nv = (size_t)b->L.nv;
-    size_t per = b->L.total_bytes + mb * b->bk_sz() + mb * sizeof(double) + mv * b->vk_sz() + mv * sizeof(ScaleK) + mv * sizeof(double) +
-                 2 * mv * 3 * b->rs() + 3 * nv * sizeof(double) + sizeof(RobotCtl);
-    return (int64_t)(nr * per);
+    // state part: what the last flush copied (positions + static section when every slot was a fresh reset image, else whole blobs
+    // + NominalPosition); before any flush, the fresh-reset figure
+    size_t state = b->last_upload_bytes ? b->last_upload_bytes : nr * (3 * nv * sizeof(double) + (b->L.stat_bytes - b->L.off_stat));
+    size_t per = mb * (b->compact ? b->bkc_sz() : b->bk_sz()) + mb * sizeof(double) + mv * b->vk_sz() + mv * sizeof(ScaleK) + mv * sizeof(double) +
+                 2 * mv * 3 * b->rs() + sizeof(RobotCtl);
+    return (int64_t)(state + nr * per);
 }
 
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -626,6 +671,7 @@ extern "C" int vxg_run_batch_host(vxg_batch* b, const vxg_robot_desc* descs, int
         // positions only: first 3*nv doubles of every blob (strided device -> host copy)
         size_t w = (size_t)3 * b->L.nv * sizeof(double);
         CK(cudaMemcpy2DAsync(b->h_blobs, b->L.total_bytes, b->d_blobs, b->L.total_bytes, w, (size_t)b->n_robots, cudaMemcpyDeviceToHost, b->stream));
+        std::fill(b->reset_image.begin(), b->reset_image.end(), 0);
         CK(cudaMemcpyAsync(b->h_ctl, b->d_ctl, (size_t)b->n_robots * sizeof(RobotCtl), cudaMemcpyDeviceToHost, b->stream));
         CK(cudaStreamSynchronize(b->stream));
         const int nv = b->L.nv, mv = b->lim.max_vox;
