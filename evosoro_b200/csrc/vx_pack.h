@@ -97,16 +97,22 @@ inline void pack_classes(const vxg_robot_desc* d, BondK<Real>* bk, double* bk_di
     }
 }
 
+// The reset image of one robot.  `partial`: only the words that differ from robot to robot are written -- the position planes
+// and the static section; the rest (identity orientation, zero momenta / history / accumulators, SmallAngle flags) is what
+// vx_reset_kernel writes on the device, or pack_blob_rest on the host when the whole blob has to travel.
 template <typename Real>
-inline void pack_blob(const vxg_robot_desc* d, const BlobLayout& L, unsigned char* blob, double* nom) {
-    memset(blob, 0, L.total_bytes);
+inline void pack_blob(const vxg_robot_desc* d, const BlobLayout& L, unsigned char* blob, double* nom, bool partial = false) {
+    if (partial) { memset(blob + L.off_pos, 0, L.off_quat - L.off_pos); memset(blob + L.off_stat, 0, L.stat_bytes - L.off_stat); }
+    else memset(blob, 0, L.total_bytes);
     RobotView<Real> R = make_view<Real>(blob, L, d->n_vox);
     const int nv = R.nv;
     for (int i = 0; i < nv; i++) { R.stat[i].nbr[0] = R.stat[i].nbr[1] = R.stat[i].nbr[2] = -1; }
     for (int i = 0; i < d->n_vox; i++) {
         for (int a = 0; a < 3; a++) { R.pos[a * nv + i] = d->nom_pos[3 * i + a]; nom[a * nv + i] = d->nom_pos[3 * i + a]; }
-        R.quat[i].x = (Real)1;          // Angle = identity (VXS_Voxel.cpp:98); stored (w,x,y,z)
-        R.flags[i] = VX_FL_SMALL_ALL;   // SmallAngle = true (VXS_BondInternal.cpp:43)
+        if (!partial) {
+            R.quat[i].x = (Real)1;          // Angle = identity (VXS_Voxel.cpp:98); stored (w,x,y,z)
+            R.flags[i] = VX_FL_SMALL_ALL;   // SmallAngle = true (VXS_BondInternal.cpp:43)
+        }
         R.stat[i].vcls = (uint16_t)d->vox_class[i];
     }
     for (int j = 0; j < d->n_bond; j++) {   // voxel bond_v1 (negative side) owns the bond
@@ -114,6 +120,15 @@ inline void pack_blob(const vxg_robot_desc* d, const BlobLayout& L, unsigned cha
         R.stat[v1].nbr[a] = (int16_t)d->bond_v2[j];
         R.stat[v1].bcls[a] = (uint16_t)d->bond_class[j];
     }
+}
+
+// Completes a `partial` reset image on the host (same words vx_reset_kernel writes on the device).
+template <typename Real>
+inline void pack_blob_rest(const BlobLayout& L, unsigned char* blob, int n_vox) {
+    memset(blob + L.off_quat, 0, L.dyn_bytes - L.off_quat);
+    memset(blob + L.stat_bytes, 0, L.total_bytes - L.stat_bytes);
+    RobotView<Real> R = make_view<Real>(blob, L, n_vox);
+    for (int i = 0; i < n_vox; i++) { R.quat[i].x = (Real)1; R.flags[i] = VX_FL_SMALL_ALL; }
 }
 
 // Integer lattice coordinates of every voxel, recovered from the nominal positions (cell centres at

@@ -62,7 +62,9 @@ struct vxg_batch {
     bool dirty = false;          // host mirrors newer than device
     bool ctl_dirty = false;      // only h_ctl newer (step budget)
     std::vector<char> uploaded;
-    std::vector<char> reset_image;   // the slot's host mirror is the plain reset image vxg_upload packed (nothing pulled or edited since)
+    std::vector<char> slot_dirty;    // the slot's host mirror (blob, Scale, control block) is newer than the device copy
+    std::vector<char> reset_image;   // the slot's host mirror is the plain reset image vxg_upload packed (nothing pulled or edited since);
+                                     // 2 = only its position planes and static section are filled in (pack_blob partial)
     std::vector<std::vector<int32_t>> bond_v1, bond_v2, bond_axis;   // for download mapping
     int64_t launches = 0;
     size_t last_upload_bytes = 0;    // blob + NominalPosition bytes the last population upload copied host -> device
@@ -203,7 +205,7 @@ extern "C" int vxg_create(vxg_batch** out, int device, int n_robots, const vxg_l
         free_all(b); delete b; cudaGetLastError();
         return fail(e == cudaErrorMemoryAllocation ? VXG_ERR_NOMEM : VXG_ERR_CUDA, "vxg_create: %s", cudaGetErrorString(e));
     }
-    b->uploaded.assign(nr, 0); b->reset_image.assign(nr, 0);
+    b->uploaded.assign(nr, 0); b->reset_image.assign(nr, 0); b->slot_dirty.assign(nr, 1);
     b->bond_v1.resize(nr); b->bond_v2.resize(nr); b->bond_axis.resize(nr);
     for (size_t r = 0; r < nr; r++) { b->h_ctl[r].status = VXG_ST_FINISHED; b->h_ctl[r].total_steps = 0; }  // empty slots never run
     b->dirty = true;
@@ -230,7 +232,15 @@ template <typename Real> static bool fill_compact(vxg_batch* b, int robot, const
 }
 
 template <typename Real> static void reset_blob(vxg_batch* b, int robot, const vxg_robot_desc* d) {
-    pack_blob<Real>(d, b->L, b->h_blobs + (size_t)robot * b->L.total_bytes, b->h_nom + (size_t)robot * 3 * b->L.nv);
+    // fluid layouts keep dynamic strain planes and mesh tables next to the rest: always packed whole
+    pack_blob<Real>(d, b->L, b->h_blobs + (size_t)robot * b->L.total_bytes, b->h_nom + (size_t)robot * 3 * b->L.nv, b->L.nvert_cap == 0);
+}
+// the host mirror of a slot as a complete reset image (before anything reads or edits it on the host, or uploads it whole)
+static void complete_mirror(vxg_batch* b, size_t r) {
+    if (b->reset_image[r] != 2) return;
+    unsigned char* blob = b->h_blobs + r * b->L.total_bytes;
+    if (b->prec == VXG_PREC_F64) pack_blob_rest<double>(b->L, blob, b->h_ctl[r].n_vox); else pack_blob_rest<float>(b->L, blob, b->h_ctl[r].n_vox);
+    b->reset_image[r] = 1;
 }
 
 extern "C" int vxg_upload(vxg_batch* b, int robot, const vxg_robot_desc* d) {
@@ -295,7 +305,7 @@ extern "C" int vxg_upload(vxg_batch* b, int robot, const vxg_robot_desc* d) {
     b->bond_v1[robot].assign(d->bond_v1, d->bond_v1 + d->n_bond);
     b->bond_v2[robot].assign(d->bond_v2, d->bond_v2 + d->n_bond);
     b->bond_axis[robot].assign(d->bond_axis, d->bond_axis + d->n_bond);
-    b->uploaded[robot] = 1; b->reset_image[robot] = 1;
+    b->uploaded[robot] = 1; b->reset_image[robot] = b->L.nvert_cap == 0 ? 2 : 1; b->slot_dirty[robot] = 1;
     b->dirty = true;
     return VXG_OK;
 }
@@ -333,11 +343,15 @@ static int flush(vxg_batch* b) {
         b->compact = compact;
         if (compact) { b->smem_mode = true; b->smem_bytes = b->L.total_bytes + b->tb_compact; }
         else { b->smem_mode = b->smem_wide_fits; b->smem_bytes = b->smem_wide_fits ? b->L.total_bytes + b->tb_wide : b->tb_wide; }
-        bool sparse = true;   // every slot still holds the reset image vxg_upload packed: positions + static section travel, the rest is written on the device
-        for (size_t r = 0; r < nr && sparse; r++) if (b->uploaded[r] && !b->reset_image[r]) sparse = false;
+        // Dynamic state travels for the slots the host changed since the last flush only (slot_dirty): the others keep what the
+        // device computed.  Whole-population case (every slot a fresh reset image -- the GA's evaluate_all): positions + static
+        // section in two strided copies, the rest of the reset image is written by vx_reset_kernel.
+        size_t n_dirty = 0; bool all_reset = true;
+        for (size_t r = 0; r < nr; r++) if (b->slot_dirty[r]) { n_dirty++; if (b->uploaded[r] && !b->reset_image[r]) all_reset = false; }
         b->last_upload_bytes = 0;
-        if (sparse) {
-            const size_t pos_bytes = 3 * nv * sizeof(double), st_bytes = b->L.stat_bytes - b->L.off_stat, tb = b->L.total_bytes;
+        const size_t tb = b->L.total_bytes;
+        if (n_dirty == nr && all_reset) {
+            const size_t pos_bytes = 3 * nv * sizeof(double), st_bytes = b->L.stat_bytes - b->L.off_stat;
             CK(cudaMemcpy2DAsync(b->d_blobs + b->L.off_pos, tb, b->h_blobs + b->L.off_pos, tb, pos_bytes, nr, cudaMemcpyHostToDevice, b->stream));
             CK(cudaMemcpy2DAsync(b->d_blobs + b->L.off_stat, tb, b->h_blobs + b->L.off_stat, tb, st_bytes, nr, cudaMemcpyHostToDevice, b->stream));
             CK(cudaMemcpyAsync(b->d_ctl, b->h_ctl, nr * sizeof(RobotCtl), cudaMemcpyHostToDevice, b->stream));
@@ -345,18 +359,24 @@ static int flush(vxg_batch* b) {
             else vx_reset_kernel<float><<<(unsigned)nr, 256, 0, b->stream>>>(b->d_blobs, b->L, b->d_ctl, b->d_nom);
             CK(cudaGetLastError());
             b->launches++;
+            CK(cudaMemcpyAsync(b->d_scale_c, b->h_scale_c, nr * mv * sizeof(double), cudaMemcpyHostToDevice, b->stream));
             b->last_upload_bytes += nr * (pos_bytes + st_bytes);
         } else {
-            CK(cudaMemcpyAsync(b->d_blobs, b->h_blobs, nr * b->L.total_bytes, cudaMemcpyHostToDevice, b->stream));
-            CK(cudaMemcpyAsync(b->d_nom, b->h_nom, nr * 3 * nv * sizeof(double), cudaMemcpyHostToDevice, b->stream));
-            b->last_upload_bytes += nr * (b->L.total_bytes + 3 * nv * sizeof(double));
+            for (size_t r = 0; r < nr; r++) {
+                if (!b->slot_dirty[r]) continue;
+                if (b->uploaded[r]) complete_mirror(b, r);
+                CK(cudaMemcpyAsync(b->d_blobs + r * tb, b->h_blobs + r * tb, tb, cudaMemcpyHostToDevice, b->stream));
+                CK(cudaMemcpyAsync(b->d_nom + r * 3 * nv, b->h_nom + r * 3 * nv, 3 * nv * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+                CK(cudaMemcpyAsync(b->d_scale_c + r * mv, b->h_scale_c + r * mv, mv * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+                CK(cudaMemcpyAsync(b->d_ctl + r, b->h_ctl + r, sizeof(RobotCtl), cudaMemcpyHostToDevice, b->stream));
+                b->last_upload_bytes += tb + 3 * nv * sizeof(double);
+            }
         }
         if (compact) CK(cudaMemcpyAsync(b->d_bk, b->h_bkc, nr * mb * b->bkc_sz(), cudaMemcpyHostToDevice, b->stream));
         else CK(cudaMemcpyAsync(b->d_bk, b->h_bk, nr * mb * b->bk_sz(), cudaMemcpyHostToDevice, b->stream));
         CK(cudaMemcpyAsync(b->d_bk_dist, b->h_bk_dist, nr * mb * sizeof(double), cudaMemcpyHostToDevice, b->stream));
         CK(cudaMemcpyAsync(b->d_vk, b->h_vk, nr * mv * b->vk_sz(), cudaMemcpyHostToDevice, b->stream));
         CK(cudaMemcpyAsync(b->d_sk, b->h_sk, nr * mv * sizeof(ScaleK), cudaMemcpyHostToDevice, b->stream));
-        CK(cudaMemcpyAsync(b->d_scale_c, b->h_scale_c, nr * mv * sizeof(double), cudaMemcpyHostToDevice, b->stream));
         CK(cudaMemcpyAsync(b->d_ext_disp, b->h_ext_disp, nr * mv * 3 * b->rs(), cudaMemcpyHostToDevice, b->stream));
         CK(cudaMemcpyAsync(b->d_ext_tdisp, b->h_ext_tdisp, nr * mv * 3 * b->rs(), cudaMemcpyHostToDevice, b->stream));
         if (b->lim.max_col_pairs > 0) {
@@ -366,8 +386,9 @@ static int flush(vxg_batch* b) {
             CK(cudaMemcpyAsync(b->d_col_near, b->h_col_near, nr * nv * sizeof(unsigned long long), cudaMemcpyHostToDevice, b->stream));
         }
     }
-    if (b->dirty || b->ctl_dirty) CK(cudaMemcpyAsync(b->d_ctl, b->h_ctl, nr * sizeof(RobotCtl), cudaMemcpyHostToDevice, b->stream));
+    if (b->ctl_dirty) CK(cudaMemcpyAsync(b->d_ctl, b->h_ctl, nr * sizeof(RobotCtl), cudaMemcpyHostToDevice, b->stream));   // the setters pulled it first
     b->dirty = false; b->ctl_dirty = false;
+    std::fill(b->slot_dirty.begin(), b->slot_dirty.end(), 0);
     return VXG_OK;
 }
 
@@ -383,6 +404,9 @@ static int pull(vxg_batch* b, bool blobs, int robot) {
             for (size_t r = r0; r < r0 + cnt; r++) b->reset_image[r] = 0;
             CK(cudaMemcpyAsync(b->h_scale_c + r0 * mv, b->d_scale_c + r0 * mv, cnt * mv * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
         }
+    } else if (blobs) {   // nothing ran since the host wrote the mirrors: they are the current state, make them whole before they are read
+        size_t r0 = robot < 0 ? 0 : (size_t)robot, cnt = robot < 0 ? nr : 1;
+        for (size_t r = r0; r < r0 + cnt; r++) if (b->uploaded[r]) complete_mirror(b, r);
     }
     CK(cudaStreamSynchronize(b->stream));
     return VXG_OK;
@@ -576,6 +600,7 @@ extern "C" int vxg_upload_state(vxg_batch* b, int robot, const vxg_robot_state* 
     if (rc) return rc;
     if (b->prec == VXG_PREC_F64) pack_state<double>(b, robot, in); else pack_state<float>(b, robot, in);
     b->reset_image[robot] = 0;
+    std::fill(b->slot_dirty.begin(), b->slot_dirty.end(), 1);   // every mirror is current (pulled above) and travels again
     b->h_ctl[robot].cur_time = cur_time;
     b->h_ctl[robot].step = cur_step;
     b->dirty = true;
@@ -616,6 +641,7 @@ extern "C" int vxg_set_collision_pairs(vxg_batch* b, int robot, int n_pairs, con
         }
         c.col_host = 1; c.n_col = n_pairs; c.flags |= VXG_F_COLLISIONS;
     }
+    b->slot_dirty[robot] = 1;   // its mirror was pulled above, so it is current; the pair lists travel whole
     b->dirty = true;
     return VXG_OK;
 }
@@ -675,13 +701,23 @@ extern "C" int vxg_run_batch_host(vxg_batch* b, const vxg_robot_desc* descs, int
         CK(cudaMemcpyAsync(b->h_ctl, b->d_ctl, (size_t)b->n_robots * sizeof(RobotCtl), cudaMemcpyDeviceToHost, b->stream));
         CK(cudaStreamSynchronize(b->stream));
         const int nv = b->L.nv, mv = b->lim.max_vox;
-        for (int r = 0; r < b->n_robots; r++) {
+        for (int r = 0; r < b->n_robots; r++)
             if (b->h_ctl[r].status & VXG_ST_DIVERGED) return fail(VXG_ERR_STATE, "vxg_run_batch_host: robot %d diverged (strain > 100)", r);
-            const double* p = (const double*)(b->h_blobs + (size_t)r * b->L.total_bytes);
-            double* o = pos_out + (size_t)r * mv * 3;
-            int n = b->h_ctl[r].n_vox;
-            for (int i = 0; i < n; i++) { o[3 * i] = p[i]; o[3 * i + 1] = p[nv + i]; o[3 * i + 2] = p[2 * nv + i]; }
-        }
+        int nt = (int)std::thread::hardware_concurrency();   // plane layout -> the caller's [voxel][xyz] rows, on all host cores
+        if (nt < 1) nt = 1;
+        if (nt > 16) nt = 16;
+        if (nt > b->n_robots) nt = b->n_robots;
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++)
+            th.emplace_back([&, t]() {
+                for (int r = t; r < b->n_robots; r += nt) {
+                    const double* p = (const double*)(b->h_blobs + (size_t)r * b->L.total_bytes);
+                    double* o = pos_out + (size_t)r * mv * 3;
+                    int n = b->h_ctl[r].n_vox;
+                    for (int i = 0; i < n; i++) { o[3 * i] = p[i]; o[3 * i + 1] = p[nv + i]; o[3 * i + 2] = p[2 * nv + i]; }
+                }
+            });
+        for (auto& x : th) x.join();
     } else CK(cudaStreamSynchronize(b->stream));
     if (timing) fprintf(stderr, "vxg_run_batch_host: flatten %.2f ms, upload+step %.2f ms, download+unpack %.2f ms\n", t1 - t0, t2 - t1, now_ms() - t2);
     return VXG_OK;

@@ -194,6 +194,14 @@ class Batch:
             for i in range(len(self.robots)):
                 _ck(lib().vxg_upload(self.h, i, C.byref(self._descs[i])))
 
+    def reupload(self, robot: int, desc: Optional[abi.HostRobot] = None):
+        """``vxg_upload`` of one slot: the robot (or a new one of the same limits) restarts from its reset state; the other
+        slots keep the state the device computed."""
+        if desc is not None:
+            self.robots[robot] = desc
+            self._descs[robot] = desc.desc()
+        _ck(lib().vxg_upload(self.h, robot, C.byref(self._descs[robot])))
+
     @property
     def n_robots(self) -> int:
         return len(self.robots)

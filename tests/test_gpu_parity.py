@@ -165,6 +165,25 @@ def test_batch_of_identical_robots_is_uniform():
     b.close()
 
 
+def test_reuploading_one_slot_leaves_the_others_running():
+    """vxg_upload of a single slot after the batch has advanced: that robot restarts from rest, the others keep the state
+    the device computed (the upload path moves the slots the host changed, nothing else)."""
+    sim = vxa.SimParams(init_cm_time=0.005, stop_condition_value=0.2)
+    robots = [engine.Model(text=vxa.vxa_text(vxa.dense_lattice(4, 60 + s), sim=sim)).robot for s in range(3)]
+    a = engine.Batch(robots); a.step(300); assert not a.sync().any()
+    a.reupload(1)
+    a.step(200); assert not a.sync().any()
+    ref = engine.Batch(robots); ref.step(500); ref.sync()
+    fresh = engine.Batch(robots[1:2]); fresh.step(200); fresh.sync()
+    for r in (0, 2):
+        assert np.array_equal(a.download(r).pos, ref.download(r).pos) and np.array_equal(a.download(r).scale, ref.download(r).scale)
+    assert np.array_equal(a.download(1).pos, fresh.download(0).pos)
+    st = a.stats()
+    assert [int(s.steps) for s in st] == [500, 200, 500]
+    for b in (a, ref, fresh):
+        b.close()
+
+
 def test_step_chunking_is_exact():
     """K steps in one launch == K single-step launches (state round-trips through HBM exactly)."""
     rob = engine.Model(text=vxa.vxa_text(vxa.dense_lattice(4, 11))).robot
