@@ -10,6 +10,8 @@
 //                     state, e.g. the fp64 mode at 10^3); the working set of the 148 resident robots
 //                     lives in L2.
 //       COMPACT      : bond classes in the two-vector compact form (BondKc, vx_math.cuh) instead of the wide table.
+//                     Small robots run with fewer threads per CTA; the launch bounds ask for 512 resident threads per SM
+//                     whatever the CTA size (<= 128 registers per thread), so that several small CTAs share an SM.
 //       VPT          : voxels per thread (thread t owns voxels t, t+T, ...), so a 10^3 robot (NV = 1024) runs
 //                     with 512 threads x 2 voxels and <=128 registers per thread.
 //   vx_stats_kernel<Real>            one CTA per robot; reductions for the result writer.
@@ -22,6 +24,9 @@
 
 namespace vx {
 
+#ifndef VX_CTAS_512
+#define VX_CTAS_512 2
+#endif
 #define VXG_ST_DIVERGED_ 0x1u
 #define VXG_ST_FINISHED_ 0x2u
 #define VXG_F_FLOOR_ 0x0001u
@@ -194,11 +199,17 @@ __device__ __noinline__ int col_rebuild(const RobotView<Real>& R, const RobotCon
     return total;
 }
 
+// Resident CTAs per SM the register allocation is sized for.  Stride 1024 and up: one robot fills the SM's shared memory -> 1
+// (128 registers at 512 threads, 64 at 1024).  Stride 512: two robots fit -> 2 x 512 threads, 64 registers (the fluid and
+// self-collision variants need more registers and room: 1).  Smaller robots: 768 resident threads, i.e. 80 registers -- what one voxel per thread needs without spilling.
+__host__ __device__ constexpr int vx_min_ctas(int nv, int threads, bool extras) {   // extras: fluid / self-collision variants (more registers)
+    return nv >= 1024 ? 1 : (nv >= 512 ? (extras ? 1 : VX_CTAS_512) : 768 / threads);
+}
 //       FLUID        : blob layout with the land/water surface-mesh arrays; robots with VXG_F_FLUID get the drag phase.
 //       COLLIDE      : self-collision support compiled in (contact-bond list, rebuild, max-velocity reduction); kept out
 //                     of the other instantiations so that they do not pay its registers.
 template <typename Real, int NV, int VPT, bool SMEM, bool COMPACT, bool FLUID = false, bool COLLIDE = false>
-__global__ void __launch_bounds__(NV / VPT, 1) vx_step_kernel(BatchDev<Real> B, int n_steps, int record_bonds) {
+__global__ void __launch_bounds__(NV / VPT, vx_min_ctas(NV, NV / VPT, FLUID || COLLIDE)) vx_step_kernel(BatchDev<Real> B, int n_steps, int record_bonds) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int T = NV / VPT;
     constexpr BlobLayout LC = make_layout(NV, (int)sizeof(Real));

@@ -12,6 +12,7 @@ struct LaunchCfg {
     size_t smem_bytes;
     cudaStream_t stream;
     int n_steps, record;
+    int vpt;   // voxels per thread the batch runs with (stride 1024 has two instantiations in the production family)
 };
 
 template <typename Real, int NV, int VPT, bool SMEM, bool COMPACT, bool FLUID, bool COLLIDE>
@@ -31,7 +32,9 @@ inline cudaError_t launch_by_stride(const BatchDev<Real>& B, const LaunchCfg& c)
         case 128: return launch_one<Real, 128, 1, SMEM, COMPACT, FLUID, COLLIDE>(B, c);
         case 256: return launch_one<Real, 256, 1, SMEM, COMPACT, FLUID, COLLIDE>(B, c);
         case 512: return launch_one<Real, 512, 1, SMEM, COMPACT, FLUID, COLLIDE>(B, c);
-        case 1024: return launch_one<Real, 1024, 2, SMEM, COMPACT, FLUID, COLLIDE>(B, c);
+        case 1024:
+            if constexpr (COMPACT && SMEM && !FLUID && !COLLIDE && sizeof(Real) == 4) { if (c.vpt == 1) return launch_one<Real, 1024, 1, true, true, false, false>(B, c); }
+            return launch_one<Real, 1024, 2, SMEM, COMPACT, FLUID, COLLIDE>(B, c);
         case 2048: return launch_one<Real, 2048, 4, SMEM, COMPACT, FLUID, COLLIDE>(B, c);
     }
     return cudaErrorInvalidValue;

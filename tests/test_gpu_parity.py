@@ -227,7 +227,7 @@ def test_full_size_population_1024_x_10cubed():
     distinct = [engine.Model(text=vxa.vxa_text(vxa.dense_lattice(10, s), sim=sim)).robot for s in range(512)]
     b = engine.Batch(distinct + distinct)
     cfg = b.kernel_config()
-    assert cfg["smem_resident"] and cfg["threads"] == 512
+    assert cfg["smem_resident"] and cfg["threads"] == 1024 and cfg["voxels_per_thread"] == 1
     b.step(300)
     st = b.sync()
     assert not st.any()
