@@ -141,13 +141,37 @@ inline void lattice_coords(const vxg_robot_desc* d, std::vector<int>& ijk) {
     for (int i = 0; i < d->n_vox; i++) for (int a = 0; a < 3; a++) ijk[3 * i + a] = (int)llround(d->nom_pos[3 * i + a] / pitch[a] - 0.5);
 }
 
+// Dense occupancy grid over the robot's bounding box (cells) and its lattice points (cell corners), z slowest / x fastest
+// like the reference's own arrays.
+struct LatticeGrid {
+    int lo[3], n[3];                 // lowest cell index per axis, cells per axis
+    std::vector<int> cell;           // [nz][ny][nx] voxel index or -1
+    std::vector<int> ijk;
+    explicit LatticeGrid(const vxg_robot_desc* d) {
+        lattice_coords(d, ijk);
+        int hi[3];
+        for (int a = 0; a < 3; a++) { lo[a] = 1 << 30; hi[a] = -(1 << 30); }
+        for (int i = 0; i < d->n_vox; i++) for (int a = 0; a < 3; a++) { int c = ijk[3 * i + a]; if (c < lo[a]) lo[a] = c; if (c > hi[a]) hi[a] = c; }
+        for (int a = 0; a < 3; a++) n[a] = hi[a] - lo[a] + 1;
+        cell.assign((size_t)n[0] * n[1] * n[2], -1);
+        for (int i = 0; i < d->n_vox; i++) cell[cidx(ijk[3 * i] - lo[0], ijk[3 * i + 1] - lo[1], ijk[3 * i + 2] - lo[2])] = i;
+    }
+    size_t cidx(int x, int y, int z) const { return ((size_t)z * n[1] + y) * n[0] + x; }
+    int at(int x, int y, int z) const { return (x < 0 || y < 0 || z < 0 || x >= n[0] || y >= n[1] || z >= n[2]) ? -1 : cell[cidx(x, y, z)]; }
+    size_t n_points() const { return (size_t)(n[0] + 1) * (n[1] + 1) * (n[2] + 1); }
+    size_t pidx(int x, int y, int z) const { return ((size_t)z * (n[1] + 1) + y) * (n[0] + 1) + x; }
+};
+
 // Number of surface-mesh vertices of a robot: lattice points touched by 1..7 voxels (LW/VX_MeshUtil.cpp:249-262).
 inline int mesh_vertex_count(const vxg_robot_desc* d) {
-    std::vector<int> ijk; lattice_coords(d, ijk);
-    std::map<std::tuple<int, int, int>, int> cnt;
-    for (int i = 0; i < d->n_vox; i++) for (int c = 0; c < 8; c++) cnt[std::make_tuple(ijk[3 * i] + ((c >> 2) & 1), ijk[3 * i + 1] + ((c >> 1) & 1), ijk[3 * i + 2] + (c & 1))]++;
+    LatticeGrid G(d);
+    std::vector<unsigned char> cnt(G.n_points(), 0);
+    for (int i = 0; i < d->n_vox; i++) {
+        const int x = G.ijk[3 * i] - G.lo[0], y = G.ijk[3 * i + 1] - G.lo[1], z = G.ijk[3 * i + 2] - G.lo[2];
+        for (int c = 0; c < 8; c++) cnt[G.pidx(x + ((c >> 2) & 1), y + ((c >> 1) & 1), z + (c & 1))]++;
+    }
     int n = 0;
-    for (auto& kv : cnt) if (kv.second != 8) n++;
+    for (unsigned char c : cnt) if (c != 0 && c != 8) n++;
     return n;
 }
 
@@ -157,35 +181,30 @@ inline int mesh_vertex_count(const vxg_robot_desc* d) {
 template <typename Real>
 inline int pack_mesh(const vxg_robot_desc* d, const BlobLayout& L, unsigned char* blob) {
     RobotView<Real> R = make_view<Real>(blob, L, d->n_vox);
-    std::vector<int> ijk; lattice_coords(d, ijk);
-    std::map<std::tuple<int, int, int>, int> occ;
-    for (int i = 0; i < d->n_vox; i++) occ[std::make_tuple(ijk[3 * i + 2], ijk[3 * i + 1], ijk[3 * i])] = i;   // (z, y, x): lattice order
+    LatticeGrid G(d);
     static const int dir[6][3] = {{1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
-    std::map<std::tuple<int, int, int>, Corner8> verts;   // keyed (z, y, x) so that iteration is the reference's vertex order
+    Corner8 none; for (int k = 0; k < 8; k++) none.i[k] = -1;
+    std::vector<Corner8> verts(G.n_points(), none);   // lattice point -> the voxel that has it as corner c
     for (int i = 0; i < d->n_vox; i++) {
+        const int x = G.ijk[3 * i] - G.lo[0], y = G.ijk[3 * i + 1] - G.lo[1], z = G.ijk[3 * i + 2] - G.lo[2];
         unsigned faces = 0;
-        for (int f = 0; f < 6; f++)
-            if (!occ.count(std::make_tuple(ijk[3 * i + 2] + dir[f][2], ijk[3 * i + 1] + dir[f][1], ijk[3 * i] + dir[f][0]))) faces |= 1u << f;
+        for (int f = 0; f < 6; f++) if (G.at(x + dir[f][0], y + dir[f][1], z + dir[f][2]) < 0) faces |= 1u << f;
         R.stat[i].faces = (uint16_t)faces;
-        for (int c = 0; c < 8; c++) {
-            auto key = std::make_tuple(ijk[3 * i + 2] + (c & 1), ijk[3 * i + 1] + ((c >> 1) & 1), ijk[3 * i] + ((c >> 2) & 1));
-            auto it = verts.find(key);
-            if (it == verts.end()) { Corner8 e; for (int k = 0; k < 8; k++) e.i[k] = -1; it = verts.emplace(key, e).first; }
-            it->second.i[c] = (int16_t)i;
-        }
+        for (int c = 0; c < 8; c++) verts[G.pidx(x + ((c >> 2) & 1), y + ((c >> 1) & 1), z + (c & 1))].i[c] = (int16_t)i;
     }
     int n_vert = 0;
-    std::map<std::tuple<int, int, int>, int> id;
-    for (auto& kv : verts) {
-        int cnt = 0; for (int k = 0; k < 8; k++) cnt += kv.second.i[k] >= 0;
-        if (cnt == 8) { id[kv.first] = -1; continue; }
+    std::vector<int> id(G.n_points(), -1);
+    for (size_t p = 0; p < verts.size(); p++) {   // ascending p = (z, y, x) lattice order
+        int cnt = 0; for (int k = 0; k < 8; k++) cnt += verts[p].i[k] >= 0;
+        if (cnt == 0 || cnt == 8) continue;
         if (n_vert >= L.nvert_cap) return -1;
-        R.vcon[n_vert] = kv.second;
-        id[kv.first] = n_vert++;
+        R.vcon[n_vert] = verts[p];
+        id[p] = n_vert++;
     }
-    for (int i = 0; i < d->n_vox; i++)
-        for (int c = 0; c < 8; c++)
-            R.cvert[i].i[c] = (int16_t)id[std::make_tuple(ijk[3 * i + 2] + (c & 1), ijk[3 * i + 1] + ((c >> 1) & 1), ijk[3 * i] + ((c >> 2) & 1))];
+    for (int i = 0; i < d->n_vox; i++) {
+        const int x = G.ijk[3 * i] - G.lo[0], y = G.ijk[3 * i + 1] - G.lo[1], z = G.ijk[3 * i + 2] - G.lo[2];
+        for (int c = 0; c < 8; c++) R.cvert[i].i[c] = (int16_t)id[G.pidx(x + ((c >> 2) & 1), y + ((c >> 1) & 1), z + (c & 1))];
+    }
     return n_vert;
 }
 

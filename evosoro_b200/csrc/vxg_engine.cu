@@ -233,8 +233,8 @@ template <typename Real> static bool fill_compact(vxg_batch* b, int robot, const
 }
 
 template <typename Real> static void reset_blob(vxg_batch* b, int robot, const vxg_robot_desc* d) {
-    // fluid layouts keep dynamic strain planes and mesh tables next to the rest: always packed whole
-    pack_blob<Real>(d, b->L, b->h_blobs + (size_t)robot * b->L.total_bytes, b->h_nom + (size_t)robot * 3 * b->L.nv, b->L.nvert_cap == 0);
+    // partial image: position planes + static section (incl. the fluid layouts' mesh tables, which pack_mesh fills in afterwards)
+    pack_blob<Real>(d, b->L, b->h_blobs + (size_t)robot * b->L.total_bytes, b->h_nom + (size_t)robot * 3 * b->L.nv, true);
 }
 // the host mirror of a slot as a complete reset image (before anything reads or edits it on the host, or uploads it whole)
 static void complete_mirror(vxg_batch* b, size_t r) {
@@ -306,7 +306,7 @@ extern "C" int vxg_upload(vxg_batch* b, int robot, const vxg_robot_desc* d) {
     b->bond_v1[robot].assign(d->bond_v1, d->bond_v1 + d->n_bond);
     b->bond_v2[robot].assign(d->bond_v2, d->bond_v2 + d->n_bond);
     b->bond_axis[robot].assign(d->bond_axis, d->bond_axis + d->n_bond);
-    b->uploaded[robot] = 1; b->reset_image[robot] = b->L.nvert_cap == 0 ? 2 : 1; b->slot_dirty[robot] = 1;
+    b->uploaded[robot] = 1; b->reset_image[robot] = 2; b->slot_dirty[robot] = 1;
     b->dirty = true;
     return VXG_OK;
 }
