@@ -184,6 +184,29 @@ def test_reuploading_one_slot_leaves_the_others_running():
         b.close()
 
 
+def test_large_robot_with_a_class_per_voxel_runs_from_global_memory():
+    """A 10^3 robot whose every voxel has its own phase offset (continuous CPPN output) needs 1000 voxel classes: the class
+    tables take the shared memory the blob would use, so the batch runs the same kernels on the blob in global memory.  Checked
+    against the fp64 C oracle after 150 steps through actuation onset."""
+    rng = np.random.RandomState(5)
+    text = vxa.vxa_text(vxa.dense_lattice(10, 77, materials=(1, 3, 4)), sim=vxa.SimParams(init_cm_time=0.02, stop_condition_value=0.2),
+                        phase_offset=rng.uniform(-0.5, 0.5, (10, 10, 10)))
+    rob = engine.Model(text=text).robot
+    assert len(rob.vclasses) == 1000
+    b = engine.Batch([rob, rob])
+    cfg = b.kernel_config()
+    assert not cfg["smem_resident"]
+    b.step(150)
+    assert not b.sync().any()
+    o = oracle_lib.OracleSim(rob)
+    o.step(150)
+    got, want = b.download(0), o.state()
+    assert common.max_abs(got.pos, want.pos) <= 1e-5 * LAT
+    assert common.max_abs(got.scale, want.scale) <= 1e-12 and np.ptp(want.scale) > 1e-4   # actuation is on, per voxel
+    assert np.array_equal(got.pos, b.download(1).pos)
+    b.close()
+
+
 def test_step_chunking_is_exact():
     """K steps in one launch == K single-step launches (state round-trips through HBM exactly)."""
     rob = engine.Model(text=vxa.vxa_text(vxa.dense_lattice(4, 11))).robot
