@@ -377,7 +377,8 @@ needs_adapter = pytest.mark.skipif(not os.access(ADAPTER, os.X_OK), reason="orac
 
 
 @needs_adapter
-@pytest.mark.parametrize("name,f64", [("dense3_full", False), ("dense3_full", True), ("dense3_afterlife_full", False), ("col_pincer_full", False)])
+@pytest.mark.parametrize("name,f64", [("dense3_full", False), ("dense3_full", True), ("dense3_afterlife_full", False), ("col_pincer_full", False),
+                                      ("dev_growth3_full", False), ("dev_growth3_full", True)])
 def test_class_api_adapter_reference_cli_on_the_engine(name, f64, tmp_path):
     """voxelyzeMain/main.cpp, LoadVXAFile/Import, TimeStep's latches, UpdateCollisions (host-side contact list ->
     vxg_set_collision_pairs), UpdateStats and WriteResultFile are all the UNMODIFIED reference; only Integrate() is

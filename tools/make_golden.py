@@ -157,6 +157,13 @@ def dev_cases():
          per_voxel={"Stiffness": 10 ** rng.uniform(np.log10(1e6), np.log10(1.5e7), (3, 3, 3))})
     case("dev_stiffness_col_pincer", pincer(), 600, 50, sim=S(init_cm_time=0.005, stop_condition_value=0.5, self_col_enabled=1), col=True,
          per_voxel={"Stiffness": 10 ** rng.uniform(np.log10(5e6), np.log10(5e7), pincer().shape)})
+    # whole CLI run of a developing robot with evolved stiffness: the result file both CLI seams have to reproduce
+    rng2 = np.random.RandomState(9)
+    u2 = lambda lo, hi: rng2.uniform(lo, hi, (3, 3, 3))
+    case("dev_growth3_full", vxa.dense_lattice(3, 56, materials=soft), 0, 1, sim=S(init_cm_time=0.05, stop_condition_value=0.4),
+         env=E(growth_amplitude=0.5, extra_tags={"MinGrowthTime": 0.02}), phase=u2(-0.5, 0.5), full=True,
+         per_voxel={"InitialVoxelSize": u2(-1, 1), "FinalVoxelSize": u2(-1, 1), "GrowthTime": u2(0, 1), "StartGrowthTime": u2(0, 1),
+                    "FinalPhaseOffset": u2(-0.5, 0.5), "Stiffness": 10 ** u2(np.log10(2e6), np.log10(1.2e7))})
     case("lw_stiffness3", vxa.dense_lattice(3, 55, materials=soft), 600, 50, sim=S(init_cm_time=0.02, stop_condition_value=0.3), lw=True, per_voxel={"Stiffness": stiff(3)})
 
 
