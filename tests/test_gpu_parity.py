@@ -207,6 +207,26 @@ def test_large_robot_with_a_class_per_voxel_runs_from_global_memory():
     b.close()
 
 
+def test_largest_supported_robot_and_the_size_limit():
+    """Maximum size: a 12^3 robot (1728 voxels, stride 2048) does not fit in shared memory and runs from global memory; it
+    must agree with the fp64 C oracle like the resident path.  One size up (13^3 = 2197 voxels) is refused, not truncated."""
+    sim = vxa.SimParams(init_cm_time=0.01, stop_condition_value=0.2)
+    rob = engine.Model(text=vxa.vxa_text(vxa.dense_lattice(12, 3), sim=sim)).robot
+    assert rob.n_vox == 1728
+    b = engine.Batch([rob])
+    assert not b.kernel_config()["smem_resident"]
+    b.step(200)
+    assert not b.sync().any()
+    o = oracle_lib.OracleSim(rob)
+    o.step(200)
+    assert common.max_abs(b.download(0).pos, o.state().pos) <= 1e-5 * LAT
+    b.close()
+    big = engine.Model(text=vxa.vxa_text(vxa.dense_lattice(13, 3), sim=sim)).robot
+    with pytest.raises(engine.EngineError) as ei:
+        engine.Batch([big])
+    assert ei.value.code > 0   # unsupported size: the caller must abort
+
+
 def test_step_chunking_is_exact():
     """K steps in one launch == K single-step launches (state round-trips through HBM exactly)."""
     rob = engine.Model(text=vxa.vxa_text(vxa.dense_lattice(4, 11))).robot
