@@ -179,7 +179,7 @@ inline int mesh_vertex_count(const vxg_robot_desc* d) {
 // voxel -> corner vertices, vertex -> voxels.  Vertices are numbered in lattice order (x fastest), interior ones
 // (8 voxels) skipped, exactly like the reference's Map[].  Returns the vertex count, or -1 if it exceeds the capacity.
 template <typename Real>
-inline int pack_mesh(const vxg_robot_desc* d, const BlobLayout& L, unsigned char* blob) {
+inline int pack_mesh(const vxg_robot_desc* d, const BlobLayout& L, unsigned char* blob, int* n_facet_out) {
     RobotView<Real> R = make_view<Real>(blob, L, d->n_vox);
     LatticeGrid G(d);
     static const int dir[6][3] = {{1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
@@ -198,13 +198,30 @@ inline int pack_mesh(const vxg_robot_desc* d, const BlobLayout& L, unsigned char
         int cnt = 0; for (int k = 0; k < 8; k++) cnt += verts[p].i[k] >= 0;
         if (cnt == 0 || cnt == 8) continue;
         if (n_vert >= L.nvert_cap) return -1;
-        R.vcon[n_vert] = verts[p];
+        Corner8 e = none; int k = 0;   // compacted (code << 12) | voxel, ascending corner code
+        for (int c = 0; c < 8; c++) if (verts[p].i[c] >= 0) e.i[k++] = (int16_t)((c << 12) | verts[p].i[c]);
+        R.vcon[n_vert] = e;
         id[p] = n_vert++;
     }
+    // facets: for every voxel (ascending) its exposed faces +X,-X,+Y,-Y,+Z,-Z, two triangles each; corner codes of the
+    // triangles as CVX_MeshUtil::LinkSimVoxels lists them (LW/VX_MeshUtil.cpp:161-190)
+    static const int T1[6][3] = {{4, 6, 7}, {0, 3, 2}, {2, 3, 7}, {0, 5, 1}, {1, 5, 7}, {0, 6, 4}};
+    static const int T2[6][3] = {{4, 7, 5}, {0, 1, 3}, {2, 7, 6}, {0, 4, 5}, {1, 7, 3}, {0, 2, 6}};
+    int n_facet = 0;
     for (int i = 0; i < d->n_vox; i++) {
         const int x = G.ijk[3 * i] - G.lo[0], y = G.ijk[3 * i + 1] - G.lo[1], z = G.ijk[3 * i + 2] - G.lo[2];
-        for (int c = 0; c < 8; c++) R.cvert[i].i[c] = (int16_t)id[G.pidx(x + ((c >> 2) & 1), y + ((c >> 1) & 1), z + (c & 1))];
+        int cv[8];
+        for (int c = 0; c < 8; c++) cv[c] = id[G.pidx(x + ((c >> 2) & 1), y + ((c >> 1) & 1), z + (c & 1))];
+        R.fbase[i] = (uint16_t)n_facet;
+        for (int f = 0; f < 6; f++) {
+            if (!((R.stat[i].faces >> f) & 1u)) continue;
+            if (n_facet + 2 > L.nfacet_cap || n_facet + 2 > 65535) return -2;
+            Facet a; a.a = (int16_t)cv[T1[f][0]]; a.b = (int16_t)cv[T1[f][1]]; a.c = (int16_t)cv[T1[f][2]]; a.v = (int16_t)i;
+            Facet b; b.a = (int16_t)cv[T2[f][0]]; b.b = (int16_t)cv[T2[f][1]]; b.c = (int16_t)cv[T2[f][2]]; b.v = (int16_t)i;
+            R.facet[n_facet++] = a; R.facet[n_facet++] = b;
+        }
     }
+    if (n_facet_out) *n_facet_out = n_facet;
     return n_vert;
 }
 

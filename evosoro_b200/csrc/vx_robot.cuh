@@ -38,8 +38,9 @@ struct alignas(16) VoxStat {
     uint16_t faces;    // bit d set: no voxel at the lattice neighbour in direction d (+X,-X,+Y,-Y,+Z,-Z): an exposed face
 };
 // surface-mesh tables of the land/water fork (LW/VX_MeshUtil.cpp:110-276)
-struct alignas(16) Corner8 { int16_t i[8]; };   // per voxel: mesh vertex at each corner (code = 4*X+ + 2*Y+ + Z+), -1 interior;
-                                                // per vertex: the voxel that has this vertex as its corner `code`, -1 none
+struct alignas(16) Corner8 { int16_t i[8]; };   // per mesh vertex: the voxels that share it, compacted: entry = (code << 12) | voxel with
+                                                // code = 4*X+ + 2*Y+ + Z+ of the corner the vertex is for that voxel, ascending code, -1 ends
+struct alignas(8) Facet { int16_t a, b, c, v; };   // one triangle of an exposed face: its three mesh vertices and the voxel it belongs to
 
 struct BlobLayout {            // byte offsets inside one robot blob; all multiples of 32
     int nv;                    // voxel stride
@@ -56,15 +57,18 @@ struct BlobLayout {            // byte offsets inside one robot blob; all multip
     size_t dyn_bytes;
     // static: copied in
     size_t off_stat;           // VoxStat [nv]
-    size_t off_cvert;          // fluid only: Corner8 [nv]          voxel -> its 8 mesh vertices
+    size_t off_fbase;          // fluid only: uint16 [nv]           first facet of each voxel (its facets are consecutive: face ascending, 2 each)
+    size_t off_facet;          // fluid only: Facet [nfacet_cap]    the triangles of all exposed faces, ordered by voxel
     size_t off_vcon;           // fluid only: Corner8 [nvert_cap]   mesh vertex -> its <= 8 voxels
     size_t stat_bytes;         // dynamic + static
     // scratch: zero-initialised on chip, never written back
     size_t off_accA;           // R4 [nv]  Force.xyz, Moment.x received from the -axis neighbours
     size_t off_accB;           // R2 [nv]  Moment.y, Moment.z
     size_t off_vpos;           // fluid only: double [3][nvert_cap]  deformed mesh vertex positions of this step
+    size_t off_fdrag;          // fluid only: Real [3][nfacet_cap]   drag of every facet of this step
     size_t total_bytes;
     int nvert_cap;             // mesh vertex capacity (0 = no fluid-drag support in this batch)
+    int nfacet_cap;            // facet capacity, derived: a closed quad surface has V - 2 + 2g faces, i.e. 2V - 4 + 4g triangles
 };
 
 VX_HD constexpr size_t vx_align16(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -82,7 +86,8 @@ VX_HD constexpr BlobLayout make_layout(int nv_in, int real_size, int nvert_cap =
     L.nv = nv_in;
     L.real_size = real_size;
     L.nvert_cap = nvert_cap;
-    const size_t nvc = (size_t)nvert_cap;
+    L.nfacet_cap = nvert_cap ? ((2 * nvert_cap + 64 + 31) & ~31) : 0;
+    const size_t nvc = (size_t)nvert_cap, nfc = (size_t)L.nfacet_cap;
     size_t nv = (size_t)nv_in, rs = (size_t)real_size, o = 0;
     L.off_pos = o;   o = vx_align32(o + 3 * nv * sizeof(double));
     L.off_quat = o;  o = vx_align32(o + 4 * nv * rs);
@@ -94,12 +99,14 @@ VX_HD constexpr BlobLayout make_layout(int nv_in, int real_size, int nvert_cap =
     L.off_strain = o; if (nvc) o = vx_align32(o + 6 * nv * rs);
     L.dyn_bytes = o;
     L.off_stat = o;  o = vx_align32(o + nv * sizeof(VoxStat));
-    L.off_cvert = o; if (nvc) o = vx_align32(o + nv * sizeof(Corner8));
+    L.off_fbase = o; if (nvc) o = vx_align32(o + nv * sizeof(uint16_t));
+    L.off_facet = o; if (nvc) o = vx_align32(o + nfc * sizeof(Facet));
     L.off_vcon = o;  if (nvc) o = vx_align32(o + nvc * sizeof(Corner8));
     L.stat_bytes = o;
     L.off_accA = o;  o = vx_align32(o + 4 * nv * rs);
     L.off_accB = o;  o = vx_align32(o + 2 * nv * rs);
     L.off_vpos = o;  if (nvc) o = vx_align32(o + 3 * nvc * sizeof(double));
+    L.off_fdrag = o; if (nvc) o = vx_align32(o + 3 * nfc * rs);
     L.total_bytes = o;
     return L;
 }
@@ -117,10 +124,12 @@ template <typename Real> struct RobotView {
     R4<Real>* accA;       // [nv]
     R2<Real>* accB;       // [nv]
     Real* strain;         // [6][nv]          (fluid layouts only)
-    Corner8* cvert;       // [nv]
+    uint16_t* fbase;      // [nv]
+    Facet* facet;         // [nfacet_cap]
     Corner8* vcon;        // [nvert_cap]
     double* vpos;         // [3][nvert_cap]
-    int nvert_cap;
+    Real* fdrag;          // [3][nfacet_cap]
+    int nvert_cap, nfacet_cap;
     VX_HD R4<Real>* histA(int ax) const { return (R4<Real>*)(hist + (size_t)ax * hist_axis_bytes); }
     VX_HD R4<Real>* histB(int ax) const { return (R4<Real>*)(hist + (size_t)ax * hist_axis_bytes) + nv; }
     VX_HD Real* histC(int ax) const { return (Real*)((R4<Real>*)(hist + (size_t)ax * hist_axis_bytes) + 2 * (size_t)nv); }
@@ -141,10 +150,12 @@ VX_HD RobotView<Real> make_view(unsigned char* base, const BlobLayout& L, int n_
     v.accA = (R4<Real>*)(base + L.off_accA);
     v.accB = (R2<Real>*)(base + L.off_accB);
     v.strain = (Real*)(base + L.off_strain);
-    v.cvert = (Corner8*)(base + L.off_cvert);
+    v.fbase = (uint16_t*)(base + L.off_fbase);
+    v.facet = (Facet*)(base + L.off_facet);
     v.vcon = (Corner8*)(base + L.off_vcon);
     v.vpos = (double*)(base + L.off_vpos);
-    v.nvert_cap = L.nvert_cap;
+    v.fdrag = (Real*)(base + L.off_fdrag);
+    v.nvert_cap = L.nvert_cap; v.nfacet_cap = L.nfacet_cap;
     return v;
 }
 
@@ -166,7 +177,7 @@ template <typename Real> struct RobotConsts {
     bool sym_mass;              // every bond class has equal end-voxel masses: Force2 = -Force1
     bool fluid;                 // land/water fluid environment: surface drag, no gravity / floor (LW/VX_Sim.cpp:1516-1597)
     Real drag_coeff;            // AggregateDragCoefficient
-    int n_vert;                 // mesh vertices of this robot
+    int n_vert, n_facet;        // mesh vertices / facets of this robot
 };
 
 // The owner's own position and orientation, loaded once per step and reused by its three bonds.
@@ -267,9 +278,10 @@ VX_HD void mesh_vertex(const RobotView<Real>& R, const RobotConsts<Real>& C, int
     const Corner8 con = R.vcon[u];
     double sx = 0, sy = 0, sz = 0; int cnt = 0;
 #pragma unroll
-    for (int c = 0; c < 8; c++) {
-        const int vv = con.i[c];
-        if (vv < 0) continue;
+    for (int k = 0; k < 8; k++) {   // compacted entries: a warp runs as many rounds as its busiest vertex needs (4 on a flat face)
+        const int e = con.i[k];
+        if (e < 0) break;
+        const int vv = e & 0xFFF, c = (e >> 12) & 7;
         const Real h = C.vk[R.stat[vv].vcls].half_nom;
         const Real ox = (c & 4) ? ((Real)1 + R.strain[vv]) * h : -((Real)1 + R.strain[3 * nv + vv]) * h;
         const Real oy = (c & 2) ? ((Real)1 + R.strain[nv + vv]) * h : -((Real)1 + R.strain[4 * nv + vv]) * h;
@@ -302,26 +314,31 @@ VX_HD V3<Real> facet_drag(const RobotView<Real>& R, int a, int b, int c, V3<Real
     return n * (-cd * area * vn * vn);
 }
 
-// DragForce of voxel v: sum over the two facets of each exposed face (facet vertex order as in LinkSimVoxels,
-// LW/VX_MeshUtil.cpp:161-190; FacetToSIndex = the voxel the face belongs to)
+// Facet i of the robot (one thread per facet, so the lanes of a warp are all busy whatever the robot's shape): its drag on
+// the voxel it belongs to, from that voxel's velocity of the previous step.
 template <typename Real>
-VX_HD V3<Real> voxel_drag(const RobotView<Real>& R, const RobotConsts<Real>& C, int v, const VoxStat& st) {
+VX_HD void facet_task(const RobotView<Real>& R, const RobotConsts<Real>& C, int i) {
+    const Facet f = R.facet[i];
+    const R4<Real> lm = R.momA[f.v];
+    const Real mi = C.vk[R.stat[f.v].vcls].mass_inv;
+    const V3<Real> d = facet_drag<Real>(R, f.a, f.b, f.c, mk3<Real>(lm.x * mi, lm.y * mi, lm.z * mi), C.drag_coeff);
+    R.fdrag[i] = d.x; R.fdrag[R.nfacet_cap + i] = d.y; R.fdrag[2 * R.nfacet_cap + i] = d.z;
+}
+
+// DragForce of voxel v: the sum over its facets in the reference's order (faces +X,-X,+Y,-Y,+Z,-Z, two triangles each,
+// vertex order as in LinkSimVoxels, LW/VX_MeshUtil.cpp:161-190; FacetToSIndex = the voxel the face belongs to)
+template <typename Real>
+VX_HD V3<Real> voxel_drag(const RobotView<Real>& R, int v, const VoxStat& st) {
     V3<Real> d = mk3<Real>(0, 0, 0);
     const unsigned faces = st.faces & 63u;
     if (!faces) return d;
-    const Corner8 cv = R.cvert[v];
-    const R4<Real> lm = R.momA[v];
-    const Real mi = C.vk[st.vcls].mass_inv;
-    const V3<Real> vel = mk3<Real>(lm.x * mi, lm.y * mi, lm.z * mi);
-    // corner codes of (tri1, tri2) per direction +X,-X,+Y,-Y,+Z,-Z
-    const int T1[6][3] = {{4, 6, 7}, {0, 3, 2}, {2, 3, 7}, {0, 5, 1}, {1, 5, 7}, {0, 6, 4}};
-    const int T2[6][3] = {{4, 7, 5}, {0, 1, 3}, {2, 7, 6}, {0, 4, 5}, {1, 7, 3}, {0, 2, 6}};
-#pragma unroll
-    for (int f = 0; f < 6; f++) {
-        if (!((faces >> f) & 1u)) continue;
-        d = d + facet_drag<Real>(R, cv.i[T1[f][0]], cv.i[T1[f][1]], cv.i[T1[f][2]], vel, C.drag_coeff);
-        d = d + facet_drag<Real>(R, cv.i[T2[f][0]], cv.i[T2[f][1]], cv.i[T2[f][2]], vel, C.drag_coeff);
-    }
+#if defined(__CUDA_ARCH__)
+    const int n = 2 * __popc(faces);
+#else
+    const int n = 2 * __builtin_popcount(faces);
+#endif
+    const int f0 = R.fbase[v], nc = R.nfacet_cap;
+    for (int k = 0; k < n; k++) d = d + mk3<Real>(R.fdrag[f0 + k], R.fdrag[nc + f0 + k], R.fdrag[2 * nc + f0 + k]);
     return d;
 }
 
@@ -439,7 +456,7 @@ struct RobotCtl {
     double half_bond_z;     // 0.5 BondDampingZ
     double bond_len;        // the common bond length L of the compact form
     double drag_coeff;      // AggregateDragCoefficient (fluid)
-    int n_vert, pad2;       // mesh vertices (fluid)
+    int n_vert, n_facet;    // mesh vertices / facets (fluid)
     // self-collision (VXG_F_COLLISIONS): CVX_Sim::UpdateCollisions state, VX_Sim.cpp:1729-1755
     double col_horizon, lattice_dim;
     double col_acc;         // MaxDispSinceLastBondUpdate

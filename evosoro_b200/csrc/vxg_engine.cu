@@ -293,7 +293,10 @@ extern "C" int vxg_upload(vxg_batch* b, int robot, const vxg_robot_desc* d) {
         }
     }
     if (b->L.nvert_cap > 0) {   // surface-mesh tables (also for non-fluid robots of a fluid batch: cheap, keeps one code path)
-        int nvx = pack_mesh<float>(d, b->L, b->h_blobs + (size_t)robot * b->L.total_bytes);
+        int nfc = 0;
+        int nvx = pack_mesh<float>(d, b->L, b->h_blobs + (size_t)robot * b->L.total_bytes, &nfc);
+        if (nvx == -2) return fail(VXG_UNSUPPORTED_SIZE, "vxg_upload: robot %d has more surface facets than the batch's mesh capacity holds (raise limits.max_mesh_verts)", robot);
+        b->h_ctl[robot].n_facet = nfc;
         if (nvx < 0) return fail(VXG_UNSUPPORTED_SIZE, "vxg_upload: robot %d has more than max_mesh_verts = %d surface-mesh vertices", robot, b->lim.max_mesh_verts);
         b->h_ctl[robot].n_vert = nvx;
     }

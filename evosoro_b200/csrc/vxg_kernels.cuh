@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(NV / VPT, vx_min_ctas(NV, NV / VPT, FLUID || C
     const double dt = ctlp->dt;
     C.dt = (Real)dt;
     const bool fluid = (flags & VXG_F_FLUID_) != 0;
-    C.fluid = FLUID && fluid; C.drag_coeff = (Real)ctlp->drag_coeff; C.n_vert = ctlp->n_vert;
+    C.fluid = FLUID && fluid; C.drag_coeff = (Real)ctlp->drag_coeff; C.n_vert = ctlp->n_vert; C.n_facet = ctlp->n_facet;
     C.floor_on = (flags & VXG_F_FLOOR_) && !fluid;
     C.sticky = (flags & VXG_F_STICKY_FLOOR_) != 0;
     C.sym_mass = ctlp->sym_mass != 0;
@@ -360,8 +360,10 @@ __global__ void __launch_bounds__(NV / VPT, vx_min_ctas(NV, NV / VPT, FLUID || C
         if (FLUID && C.fluid) {   // DragForce of this step from the state and bond strains of the previous one
             for (int u = tid; u < C.n_vert; u += T) mesh_vertex<Real>(R, C, u);
             __syncthreads();
+            for (int i = tid; i < C.n_facet; i += T) facet_task<Real>(R, C, i);
+            __syncthreads();
 #pragma unroll
-            for (int j = 0; j < VPT; j++) if (tid + j * T < n_vox) F[j] = voxel_drag<Real>(R, C, tid + j * T, st[j]);
+            for (int j = 0; j < VPT; j++) if (tid + j * T < n_vox) F[j] = voxel_drag<Real>(R, tid + j * T, st[j]);
         }
         // Scale of every class for the NEXT step, from CurTime before the increment (VXS_Voxel.cpp:224-336).
         // It depends on time only, so it is evaluated here, off the critical path, by the highest threads

@@ -54,7 +54,7 @@ template <typename Real, bool COMPACT = false, bool FLUID = false, bool COLLIDE 
         bkc.resize(nbc);
         compact_ok = pack_compact<Real>(d, bkc.data(), &bond_len);
         init_ctl(d, ctl);
-        if (FLUID) ctl.n_vert = pack_mesh<Real>(d, L, blob.data());
+        if (FLUID) ctl.n_vert = pack_mesh<Real>(d, L, blob.data(), &ctl.n_facet);
         if (COLLIDE && (ctl.flags & VXG_F_COLLISIONS)) pack_collision_tables(d, ctl.col_hops, surf, lat4, near);
         for (int i = 0; i < nvc; i++) dsc_c[0][i] = (Real)(scale_c[0][i] - sk[i].nom_size);
         rec.assign((size_t)39 * L.nv, (Real)0);
@@ -72,7 +72,7 @@ template <typename Real, bool COMPACT = false, bool FLUID = false, bool COLLIDE 
         C.floor_on = (ctl.flags & VXG_F_FLOOR) && !fluid;
         C.sticky = (ctl.flags & VXG_F_STICKY_FLOOR) != 0;
         C.sym_mass = ctl.sym_mass != 0;
-        C.fluid = FLUID && fluid; C.drag_coeff = (Real)ctl.drag_coeff; C.n_vert = ctl.n_vert;
+        C.fluid = FLUID && fluid; C.drag_coeff = (Real)ctl.drag_coeff; C.n_vert = ctl.n_vert; C.n_facet = ctl.n_facet;
         const bool temp_on = (ctl.flags & VXG_F_TEMPERATURE) != 0, lw = (ctl.flags & VXG_F_LW_SCALE) != 0;
         const Real dt_inv_run = (Real)(1.0 / ctl.dt);
         std::vector<V3<Real>> F(ctl.n_vox), M(ctl.n_vox);
@@ -96,7 +96,8 @@ template <typename Real, bool COMPACT = false, bool FLUID = false, bool COLLIDE 
             for (int v = 0; v < ctl.n_vox; v++) { F[v] = mk3<Real>(0, 0, 0); M[v] = mk3<Real>(0, 0, 0); }
             if (C.fluid) {
                 for (int u = 0; u < C.n_vert; u++) mesh_vertex<Real>(R, C, u);
-                for (int v = 0; v < ctl.n_vox; v++) F[v] = voxel_drag<Real>(R, C, v, R.stat[v]);
+                for (int i = 0; i < C.n_facet; i++) facet_task<Real>(R, C, i);
+                for (int v = 0; v < ctl.n_vox; v++) F[v] = voxel_drag<Real>(R, v, R.stat[v]);
             }
             bool d = false;
             std::vector<uint32_t> fl(ctl.n_vox);
