@@ -96,7 +96,7 @@ def test_cantilever_rests_at_beam_theory_deflection(prec, tol):
 
 
 @pytest.mark.parametrize("name,prec,tol", [("dense3_full", abi.VXG_PREC_F32, 1e-2), ("dense3_full", abi.VXG_PREC_F64, 1e-6),
-                                           ("dense6_s1_full", abi.VXG_PREC_F32, 1e-2)])
+                                           ("dense6_s1_full", abi.VXG_PREC_F32, 1e-2), ("dense10_s3_full", abi.VXG_PREC_F32, 1e-2)])
 def test_full_cli_run_fitness(name, prec, tol):
     """P3: the whole `voxelyze -f` run (step budget and IniCM latch from vxh_step_plan, all on the device):
     NormFinalDist / finalDistY / final COM within `tol` voxel lengths of the reference's result."""

@@ -72,6 +72,8 @@ def main():
     case("lw_dense3_full", vxa.dense_lattice(3, 13, materials=(1, 3, 4)), 0, 1, sim=S(init_cm_time=0.05, stop_condition_value=0.25), lw=True, full=True)
     # BASELINE config 1/2 shape: dense 6^3, whole 5 s CLI run (78 054 steps): final COM / fitness only
     case("dense6_s1_full", vxa.dense_lattice(6, 1), 0, 1, full=True)
+    # the headline shape: dense 10^3, whole 5 s CLI run (78 054 steps x 1000 voxels): final COM / fitness only
+    case("dense10_s3_full", vxa.dense_lattice(10, 3), 0, 1, full=True)
     # single voxel / no bonds (edge case: empty bond list)
     one = np.zeros((2, 2, 2), dtype=np.int32); one[0, 0, 0] = 1
     case("single_voxel", one, 300, 100, sim=S(init_cm_time=0.01, stop_condition_value=0.1))
@@ -168,7 +170,9 @@ def dev_cases():
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "dev":
+    if len(sys.argv) > 1 and sys.argv[1] == "big":
+        case("dense10_s3_full", vxa.dense_lattice(10, 3), 0, 1, full=True)
+    elif len(sys.argv) > 1 and sys.argv[1] == "dev":
         dev_cases()
     elif len(sys.argv) > 1 and sys.argv[1] == "bc":
         bc_cases()
