@@ -100,6 +100,7 @@ class RobotStats(C.Structure):
         ("anterior_dist", C.c_double), ("posterior_dist", C.c_double), ("anterior_y", C.c_double),
         ("posterior_y", C.c_double), ("eol_posterior_y", C.c_double),
         ("n_nonfeet_touching_floor", C.c_int32), ("reserved", C.c_int32),
+        ("mesh_volume", C.c_double),
     ]
 
 

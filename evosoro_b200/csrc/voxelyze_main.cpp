@@ -62,7 +62,9 @@ int main(int argc, char** argv) {
         lim.max_vclass = std::max(lim.max_vclass, descs[r].n_vclass);
         lim.max_bclass = std::max(lim.max_bclass, descs[r].n_bclass);
         if (descs[r].sim.flags & VXG_F_COLLISIONS) lim.max_col_pairs = 512;   // contact-bond list capacity (overflow is reported, never truncated)
-        if (descs[r].sim.flags & VXG_F_FLUID) lim.max_mesh_verts = std::max(lim.max_mesh_verts, vxg_mesh_vertex_count(&descs[r]));
+        // the land/water result file reports the volume of the deformed surface mesh at the end: every robot of that fork needs the
+        // mesh tables, not only those in a fluid environment
+        if (descs[r].sim.flags & (VXG_F_FLUID | VXG_F_LW_SCALE)) lim.max_mesh_verts = std::max(lim.max_mesh_verts, vxg_mesh_vertex_count(&descs[r]));
         max_total = std::max(max_total, total[r]);
         if (print_scrn) printf("Imported %s: %d voxels, %d bonds, %lld steps\n", files[r].c_str(), descs[r].n_vox, descs[r].n_bond, (long long)total[r]);
     }

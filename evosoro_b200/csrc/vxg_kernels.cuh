@@ -445,6 +445,7 @@ struct StatsDev {   // mirrors vxg_robot_stats
     int n_touching_floor, ini_com_latched;
     double anterior_dist, posterior_dist, anterior_y, posterior_y, eol_posterior_y;
     int n_nonfeet_touching_floor, reserved;
+    double mesh_volume;
 };
 
 
@@ -486,6 +487,27 @@ __global__ void __launch_bounds__(256) vx_stats_kernel(BatchDev<Real> B, StatsDe
         dmax = fmax(dmax, dd); dmin = fmin(dmin, dd);
         if (mat != 5) { ymax = fmax(ymax, py); ymin = fmin(ymin, py); }  // getAnteriorY / getPosteriorY
     }
+    // RobotVolumeEnd (land/water result file): rebuild the deformed surface mesh from the final state in the blob's own
+    // vertex scratch (global memory here) and sum the signed tetrahedra of its facets
+    double vol = -1.0;
+    if (L.nvert_cap > 0) {
+        RobotConsts<Real> C;
+        C.vk = vk;
+        for (int u = tid; u < ctl->n_vert; u += T) mesh_vertex<Real>(R, C, u);
+        __syncthreads();
+        const int nc = L.nvert_cap;
+        double v6 = 0, z1 = 0, z2 = 0, z3 = 0;
+        for (int i = tid; i < ctl->n_facet; i += T) {
+            const Facet f = R.facet[i];
+            const double ax = R.vpos[f.a], ay = R.vpos[nc + f.a], az = R.vpos[2 * nc + f.a];
+            const double bx = R.vpos[f.b], by = R.vpos[nc + f.b], bz = R.vpos[2 * nc + f.b];
+            const double cx = R.vpos[f.c], cy = R.vpos[nc + f.c], cz = R.vpos[2 * nc + f.c];
+            v6 += (1.0 / 6.0) * ((ay * bz - az * by) * cx + (az * bx - ax * bz) * cy + (ax * by - ay * bx) * cz);
+        }
+        block_sum4(v6, z1, z2, z3, red);
+        vol = v6;
+        __syncthreads();
+    }
     block_sum4(mx, my, mz, mm, red);
     double m11[11] = {vmax, -lo[0], -lo[1], -lo[2], hi[0], hi[1], hi[2], dmax, -dmin, ymax, -ymin};
     int lane = tid & 31, wid = tid >> 5, nw = (T + 31) >> 5;
@@ -503,6 +525,7 @@ __global__ void __launch_bounds__(256) vx_stats_kernel(BatchDev<Real> B, StatsDe
         s.n_touching_floor = tc; s.ini_com_latched = ctl->ini_latched;
         s.anterior_dist = m11[7]; s.posterior_dist = -m11[8]; s.anterior_y = m11[9]; s.posterior_y = -m11[10];
         s.eol_posterior_y = ctl->eol_post_y; s.n_nonfeet_touching_floor = fc; s.reserved = 0;
+        s.mesh_volume = vol;
         out[robot] = s;
     }
 }

@@ -802,7 +802,9 @@ extern "C" int vxh_format_result(const vxh_model* m, const vxg_robot_stats* st, 
         elf("normDistX", (float)nx); elf("normDistY", (float)ny); elf("normDistZ", (float)nz);
         // shape descriptors are only computed with --computeShapeDescriptors (needs qhull); the stock run leaves -1
         // RobotVolumeStart: the closed surface mesh of the undeformed robot encloses exactly its voxels
-        el("RobotVolumeStart", m->info.n_vox * lat * lat * lat); el("ConvexHullVolumeStart", -1); el("RobotVolumeEnd", -1); el("ConvexHullVolumeEnd", -1);
+        el("RobotVolumeStart", m->info.n_vox * lat * lat * lat); el("ConvexHullVolumeStart", -1);
+        el("RobotVolumeEnd", st->mesh_volume);   // -1 from a batch without mesh capacity, like the reference without its mesh
+        el("ConvexHullVolumeEnd", -1);
         el("ShapeComplexityStart", -1); el("ShapeComplexityEnd", -1);
     } else {
         const double final_dist = pow(pow(dx, 2) + pow(dy, 2), 0.5) / lat;

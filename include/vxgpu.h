@@ -225,6 +225,9 @@ typedef struct vxg_robot_stats {
     double eol_posterior_y;   /* posterior_y latched at the TimeStep() entry where CurTime >= StopConditionValue (VX_Sim.cpp:1078-1082); 0 = never */
     int32_t n_nonfeet_touching_floor; /* touching-floor count restricted to material index 6  GetNumNonFeetTouchingFloor */
     int32_t reserved;
+    double mesh_volume;       /* volume enclosed by the deformed surface mesh, sum over its facets of (V1 x V2) . V3 / 6
+                                 (CVX_MeshUtil::computeCurrentRobotVolume, LW/VX_MeshUtil.cpp:908-953 -> RobotVolumeEnd); -1 when the
+                                 batch was created without mesh capacity (limits.max_mesh_verts = 0)                              */
 } vxg_robot_stats;
 
 typedef struct vxg_batch vxg_batch; /* opaque; owns all device memory */

@@ -345,7 +345,8 @@ def _check_result(ours_xml, g):
     ours, ref = golden_lib.parse_result(ours_xml), golden_lib.parse_result(g.result_xml)
     assert list(ours.keys()) == list(ref.keys())
     for k, v in ref.items():
-        if g.lw and k == "RobotVolumeEnd":
+        if k == "RobotVolumeEnd":   # volume of the deformed surface mesh at the end (m^3): relative, it is ~1e-5
+            assert ours[k] == pytest.approx(v, rel=1e-4), k
             continue
         if k in ("NumTouchingFloor", "NumNonFeetTouchingFloor", "VoxelNumber", "FoundNeedleInHaystack"):
             assert ours[k] == v, k
