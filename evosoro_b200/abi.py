@@ -82,6 +82,7 @@ class RobotState(C.Structure):
         ("scale", c_double_p), ("static_fric", c_int32_p),
         ("bond_force1", c_double_p), ("bond_force2", c_double_p), ("bond_moment1", c_double_p),
         ("bond_moment2", c_double_p), ("bond_strain", c_double_p), ("bond_small_angle", c_int32_p),
+        ("vox_strain", c_double_p),
     ]
 
 

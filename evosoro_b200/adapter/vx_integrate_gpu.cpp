@@ -48,7 +48,7 @@ struct Attached {
     int n_vox = 0, n_bond = 0;
     bool collisions = false;
     std::vector<int32_t> col_v1, col_v2;      // the contact-bond list last handed to the device
-    std::vector<double> pos, quat, lin_mom, ang_mom, scale, f1, f2, m1, m2, strain;
+    std::vector<double> pos, quat, lin_mom, ang_mom, scale, f1, f2, m1, m2, strain, vstrain;
     std::vector<int32_t> sfric, small;
 };
 
@@ -180,7 +180,11 @@ void attach(CVX_Sim& S, Attached& A) {
     lim.max_vox = nv; lim.max_vclass = d.n_vclass; lim.max_bclass = d.n_bclass > 0 ? d.n_bclass : 1;
     lim.precision = getenv("VXG_ADAPTER_F64") ? VXG_PREC_F64 : VXG_PREC_F32;
     lim.max_col_pairs = A.collisions ? 4 * nv + 64 : 0;             // the host's list (UpdateCollisions stays the reference's)
-    lim.max_mesh_verts = (fl & VXG_F_FLUID) ? vxg_mesh_vertex_count(&d) : 0;
+#ifdef REF_LW   // the fork's deformable surface mesh (fluid drag, RobotVolumeEnd) reads per-voxel strains after every step
+    lim.max_mesh_verts = vxg_mesh_vertex_count(&d);
+#else
+    lim.max_mesh_verts = 0;
+#endif
     const char* dev = getenv("VXG_DEVICE");
     if (A.batch) { vxg_destroy(A.batch); A.batch = nullptr; }
     int rc = vxg_create(&A.batch, dev ? atoi(dev) : 0, 1, &lim);
@@ -192,7 +196,7 @@ void attach(CVX_Sim& S, Attached& A) {
     A.pos.resize(3 * (size_t)nv); A.quat.resize(4 * (size_t)nv); A.lin_mom.resize(3 * (size_t)nv); A.ang_mom.resize(3 * (size_t)nv);
     A.scale.resize(nv); A.sfric.resize(nv);
     A.f1.resize(3 * (size_t)nb); A.f2.resize(3 * (size_t)nb); A.m1.resize(3 * (size_t)nb); A.m2.resize(3 * (size_t)nb);
-    A.strain.resize(nb); A.small.resize(nb);
+    A.strain.resize(nb); A.small.resize(nb); A.vstrain.resize(6 * (size_t)nv);
 }
 
 // device state -> VoxArray / BondArrayInternal (what EulerStep / UpdateBond leave behind: VXS_Voxel.cpp:184-215, :414-417;
@@ -203,6 +207,9 @@ void write_back(CVX_Sim& S, Attached& A) {
     st.scale = A.scale.data(); st.static_fric = A.sfric.data();
     if (A.n_bond) { st.bond_force1 = A.f1.data(); st.bond_force2 = A.f2.data(); st.bond_moment1 = A.m1.data(); st.bond_moment2 = A.m2.data();
                     st.bond_strain = A.strain.data(); st.bond_small_angle = A.small.data(); }
+#ifdef REF_LW
+    st.vox_strain = A.vstrain.data();
+#endif
     if (vxg_download_state(A.batch, 0, &st)) die("engine error", vxg_last_error());
     const bool kin = (S.StatToCalc & CALCSTAT_KINE) != 0;
     for (int i = 0; i < A.n_vox; i++) {
@@ -214,6 +221,12 @@ void write_back(CVX_Sim& S, Attached& A) {
         v.Scale = A.scale[i];
 #ifndef REF_LW
         v.lastScale = A.scale[i];
+#endif
+#ifdef REF_LW   // SetStrainDir of every bond + the corner extents CalcTotalForce derives from them (LW/VXS_Voxel.cpp:258-268, :474-475)
+        v.StrainPosDirsCur = Vec3D<>(A.vstrain[6 * i], A.vstrain[6 * i + 1], A.vstrain[6 * i + 2]);
+        v.StrainNegDirsCur = Vec3D<>(A.vstrain[6 * i + 3], A.vstrain[6 * i + 4], A.vstrain[6 * i + 5]);
+        v.CornerPosCur = (Vec3D<>(1, 1, 1) + v.StrainPosDirsCur) * v.NominalSize / 2;
+        v.CornerNegCur = -(Vec3D<>(1, 1, 1) + v.StrainNegDirsCur) * v.NominalSize / 2;
 #endif
         v.StaticFricFlag = A.sfric[i] != 0;
         v.Vel = v.LinMom * v._massInv; v.AngVel = v.AngMom * v._inertiaInv;

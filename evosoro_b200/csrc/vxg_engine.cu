@@ -547,6 +547,7 @@ template <typename Real> static void unpack_state(vxg_batch* b, int robot, vxg_r
         if (o->ang_mom) { o->ang_mom[3 * i] = (double)ma.w; o->ang_mom[3 * i + 1] = (double)mb.x; o->ang_mom[3 * i + 2] = (double)mb.y; }
         if (o->scale) o->scale[i] = sc[R.stat[i].vcls];
         if (o->static_fric) o->static_fric[i] = (R.flags[i] & VX_FL_STATIC_FRIC) ? 1 : 0;
+        if (o->vox_strain) for (int a = 0; a < 6; a++) o->vox_strain[6 * i + a] = b->L.nvert_cap > 0 ? (double)R.strain[a * nv + i] : 0.0;
     }
 }
 

@@ -186,6 +186,9 @@ typedef struct vxg_robot_state {
     double* bond_moment2; /* [n_bond][3]                                                              */
     double* bond_strain;  /* [n_bond]  CurStrainTot                                                   */
     int32_t* bond_small_angle; /* [n_bond] SmallAngle                                                 */
+    double* vox_strain;   /* [n_vox][6] StrainPosDirsCur.xyz, StrainNegDirsCur.xyz of the last bond pass (LW/VXS_Voxel.cpp:258-268;
+                             they set the corner extents of the surface mesh, :474-475); download only, batches with mesh capacity
+                             (zeros otherwise)                                                                                  */
 } vxg_robot_state;
 
 /* Sizing of a batch: every robot slot gets the same stride so a slot is one contiguous blob. */

@@ -419,6 +419,23 @@ def test_class_api_adapter_reference_cli_on_the_engine(name, f64, tmp_path):
             assert ours[k] == pytest.approx(v, rel=1e-6, abs=1e-9), k
 
 
+ADAPTER_LW = os.path.join(refdump.REF_DIR, "voxelyze_gpu_adapter_lw")
+
+
+@pytest.mark.skipif(not os.access(ADAPTER_LW, os.X_OK), reason="oracle/_ref/voxelyze_gpu_adapter_lw did not travel with the snapshot")
+@pytest.mark.parametrize("name", ["lw_dense3_full", "lw_fluid_dense3_full"])
+def test_class_api_adapter_land_water_fork(name, tmp_path):
+    """The same seam under the land/water fork's CLI + library: its Integrate() (bonds, surface-mesh fluid drag, voxels) runs on
+    the device; the per-voxel strains are written back too, so the reference's own deformable mesh yields RobotVolumeEnd."""
+    g = golden_lib.Golden(name)
+    out = tmp_path / "fit.xml"
+    vxa_path = tmp_path / (name + ".vxa")
+    vxa_path.write_text(g.vxa_text.replace(g.fitness_file, str(out)))
+    r = subprocess.run([ADAPTER_LW, "-f", str(vxa_path)], capture_output=True, text=True)
+    assert r.returncode == 1, r.stderr
+    _check_result(out.read_text(), g)
+
+
 @needs_adapter
 def test_class_api_adapter_rejects_unsupported(tmp_path):
     p = tmp_path / "eq.vxa"
