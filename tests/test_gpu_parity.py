@@ -399,7 +399,7 @@ needs_adapter = pytest.mark.skipif(not os.access(ADAPTER, os.X_OK), reason="orac
 
 @needs_adapter
 @pytest.mark.parametrize("name,f64", [("dense3_full", False), ("dense3_full", True), ("dense3_afterlife_full", False), ("col_pincer_full", False),
-                                      ("dev_growth3_full", False), ("dev_growth3_full", True)])
+                                      ("dev_growth3_full", False), ("dev_growth3_full", True), ("evosoro_basic_id1_full", False)])
 def test_class_api_adapter_reference_cli_on_the_engine(name, f64, tmp_path):
     """voxelyzeMain/main.cpp, LoadVXAFile/Import, TimeStep's latches, UpdateCollisions (host-side contact list ->
     vxg_set_collision_pairs), UpdateStats and WriteResultFile are all the UNMODIFIED reference; only Integrate() is

@@ -29,6 +29,13 @@ def case(name, structure, n_steps, every, sim=None, env=None, palette=None, phas
         sim = sim or vxa.SimParams()
         sim.fitness_file = os.path.join(TMP, name + "_result.xml")
     text = vxa.vxa_text(structure, palette=palette, sim=sim, env=env, phase_offset=phase, boundary_conditions=bcs, per_voxel=per_voxel)
+    case_text(name, text, n_steps, every, lw=lw, full=full, col=col, fitness_file=sim.fitness_file if full else None)
+
+
+def case_text(name, text, n_steps, every, lw=False, full=False, col=False, fitness_file=None):
+    class _S: pass
+    sim = _S(); sim.fitness_file = fitness_file
+    os.makedirs(TMP, exist_ok=True)
     path = os.path.join(TMP, name + ".vxa")
     with open(path, "w") as f:
         f.write(text)
@@ -169,8 +176,24 @@ def dev_cases():
     case("lw_stiffness3", vxa.dense_lattice(3, 55, materials=soft), 600, 50, sim=S(init_cm_time=0.02, stop_condition_value=0.3), lw=True, per_voxel={"Stiffness": stiff(3)})
 
 
+def evosoro_cases():
+    """The wire format as evosoro itself writes it: two individuals of the first population of its stock experiment
+    (examples/basic.py: 6^3 workspace, CPPN morphologies, SelfColEnabled=1, 5 s lifetime), written by evosoro's own
+    write_voxelyze_file (tools/make_evosoro_vxa.py), whole CLI runs."""
+    import re
+    import make_evosoro_vxa
+    files = make_evosoro_vxa.main(os.path.join(TMP, "evosoro_basic"), 6)
+    for idx in (1, 2):
+        text = open(files[idx]).read()
+        fit = os.path.join(TMP, "evosoro_basic_id%d_result.xml" % idx)
+        text = re.sub(r"<FitnessFileName>[^<]*</FitnessFileName>", "<FitnessFileName>" + fit + "</FitnessFileName>", text)
+        case_text("evosoro_basic_id%d_full" % idx, text, 0, 1, full=True, col=True, fitness_file=fit)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "big":
+    if len(sys.argv) > 1 and sys.argv[1] == "evosoro":
+        evosoro_cases()
+    elif len(sys.argv) > 1 and sys.argv[1] == "big":
         case("dense10_s3_full", vxa.dense_lattice(10, 3), 0, 1, full=True)
     elif len(sys.argv) > 1 and sys.argv[1] == "dev":
         dev_cases()
@@ -186,3 +209,4 @@ if __name__ == "__main__":
         collision_cases()
         bc_cases()
         dev_cases()
+        evosoro_cases()
