@@ -431,11 +431,11 @@ template <typename T> struct VoxState {
 //   half_scale : 0.5 * Scale of the PREVIOUS step in fp64 (floor penetration :698)
 //   nom        : NominalPosition (only read for fixed DOFs)
 //   returns StaticFricFlag
-template <typename T>
+template <typename T, bool BC = true>
 VX_HD bool voxel_integrate(const VoxK<T>& k, V3<T> F, V3<T> M, double half_scale, bool floor_on, bool sticky,
                            T dt, const double* nom, const T* ext_disp, const T* ext_tdisp, VoxState<T>& s) {
     bool sfric = false;
-    if (k.has_bc && (k.dof & 0x3F) == 0x3F) {          // :174-179 fully fixed
+    if (BC && k.has_bc && (k.dof & 0x3F) == 0x3F) {          // :174-179 fully fixed
         s.lm = mk3<T>(0, 0, 0); s.am = mk3<T>(0, 0, 0);
         s.px = nom[0] + (double)ext_disp[0]; s.py = nom[1] + (double)ext_disp[1]; s.pz = nom[2] + (double)ext_disp[2];
         T l = vx_sqrt(ext_tdisp[0] * ext_tdisp[0] + ext_tdisp[1] * ext_tdisp[1] + ext_tdisp[2] * ext_tdisp[2]);
@@ -447,7 +447,7 @@ VX_HD bool voxel_integrate(const VoxK<T>& k, V3<T> F, V3<T> M, double half_scale
     V3<T> vel = s.lm * k.mass_inv;                      // Vel of the previous step (:415)
     F = F - vel * k.slow_lin;                           // :487
     F.z += k.weight_z;                                  // :536
-    if (k.has_bc) { F.x += k.ext_f[0]; F.y += k.ext_f[1]; F.z += k.ext_f[2]; }   // :540
+    if (BC && k.has_bc) { F.x += k.ext_f[0]; F.y += k.ext_f[1]; F.z += k.ext_f[2]; }   // :540
     if (floor_on) {                                     // :635-639, :708-758
         T pen = (T)(half_scale - s.pz);
         if (pen > (T)0) {
@@ -475,7 +475,7 @@ VX_HD bool voxel_integrate(const VoxK<T>& k, V3<T> F, V3<T> M, double half_scale
     T dtm = dt * k.mass_inv;
     s.px += (double)(s.lm.x * dtm); s.py += (double)(s.lm.y * dtm); s.pz += (double)(s.lm.z * dtm);   // :185,:193
     M = -M;                                             // :664-665
-    if (k.has_bc) {
+    if (BC && k.has_bc) {
         if (k.dof & 0x01) { s.px = nom[0] + (double)ext_disp[0]; s.lm.x = 0; }   // :195-197
         if (k.dof & 0x02) { s.py = nom[1] + (double)ext_disp[1]; s.lm.y = 0; }
         if (k.dof & 0x04) { s.pz = nom[2] + (double)ext_disp[2]; s.lm.z = 0; }
@@ -496,7 +496,7 @@ VX_HD bool voxel_integrate(const VoxK<T>& k, V3<T> F, V3<T> M, double half_scale
     { T li = vx_rsqrt(l2 > (T)1e-30 ? l2 : (T)1e-30); a.w *= li; a.x *= li; a.y *= li; a.z *= li; }   // `if (l)`: never zero for a unit quaternion
     clamp_unit_w(a);
     s.q = a;
-    if (k.has_bc && (k.dof & 0x38) == 0x38) {           // :218-221
+    if (BC && k.has_bc && (k.dof & 0x38) == 0x38) {           // :218-221
         T l = vx_sqrt(ext_tdisp[0] * ext_tdisp[0] + ext_tdisp[1] * ext_tdisp[1] + ext_tdisp[2] * ext_tdisp[2]);
         T sn, cs; vx_sincos((T)0.5 * l, &sn, &cs);
         T il = l > (T)0 ? (T)1 / l : (T)0;

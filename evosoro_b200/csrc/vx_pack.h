@@ -14,13 +14,21 @@
 namespace vx {
 
 // Compact bond classes (BondKc): returns false when some class is not of the equal-cubic-voxel beam form
-// (relative deviation above 1e-9) or the classes do not share one bond length; *len_out = that length.
+// (relative deviation above 1e-9), the classes do not share one bond length, or a voxel class carries boundary conditions;
+// *len_out = the bond length.
 template <typename Real>
 inline bool pack_compact(const vxg_robot_desc* d, BondKc<Real>* bkc, double* len_out) {
     auto near = [](double a, double b) { double m = fabs(a) > fabs(b) ? fabs(a) : fabs(b); return fabs(a - b) <= 1e-9 * m; };
     double L = d->n_bclass > 0 ? d->bclasses[0].len : 1.0;
     *len_out = L;
     bool ok = true;
+    // the production family is compiled without the boundary-condition code (fixed DOFs, external loads): robots that use it
+    // run the wide-table family
+    for (int i = 0; i < d->n_vclass; i++) {
+        const vxg_vox_class& c = d->vclasses[i];
+        if (c.dof_fixed != 0) ok = false;
+        for (int a = 0; a < 3; a++) if (c.ext_force[a] != 0 || c.ext_torque[a] != 0) ok = false;
+    }
     for (int i = 0; i < d->n_bclass; i++) {
         const vxg_bond_class& c = d->bclasses[i];
         if (!(c.len > 0) || !near(c.len, L) || !(c.b1 > 0) || !(c.b3 > 0) || !(c.a2 > 0)) { ok = false; continue; }

@@ -401,7 +401,7 @@ VX_HD V3<Real> col_force_on(const RobotView<Real>& R, const RobotConsts<Real>& C
 }
 
 // Voxel v: total force/moment = own share + received share; integrate (EulerStep).  Returns |Vel|^2 after the step.
-template <typename Real>
+template <typename Real, bool BC = true>
 VX_HD Real voxel_task(const RobotView<Real>& R, const RobotConsts<Real>& C, int v, const VoxStat& st, const OwnState<Real>& own,
                       uint32_t fl, V3<Real> F, V3<Real> M) {
     const int nv = R.nv;
@@ -423,8 +423,8 @@ VX_HD Real voxel_task(const RobotView<Real>& R, const RobotConsts<Real>& C, int 
         s.am = mk3<Real>(a.w, b.x, b.y);
     }
     double nom[3] = {0, 0, 0};
-    if (k.has_bc) { nom[0] = C.nom[v]; nom[1] = C.nom[nv + v]; nom[2] = C.nom[2 * nv + v]; }
-    bool sf = voxel_integrate<Real>(k, F, M, 0.5 * C.scale_c[vc], C.floor_on, C.sticky, C.dt, nom,
+    if (BC && k.has_bc) { nom[0] = C.nom[v]; nom[1] = C.nom[nv + v]; nom[2] = C.nom[2 * nv + v]; }
+    bool sf = voxel_integrate<Real, BC>(k, F, M, 0.5 * C.scale_c[vc], C.floor_on, C.sticky, C.dt, nom,
                                     C.ext_disp + 3 * vc, C.ext_tdisp + 3 * vc, s);
     R.pos[v] = s.px; R.pos[nv + v] = s.py; R.pos[2 * nv + v] = s.pz;
     {

@@ -9,7 +9,8 @@
 //       SMEM = false: same code against the blob in global memory (robots larger than ~227 KB of
 //                     state, e.g. the fp64 mode at 10^3); the working set of the 148 resident robots
 //                     lives in L2.
-//       COMPACT      : bond classes in the two-vector compact form (BondKc, vx_math.cuh) instead of the wide table.
+//       COMPACT      : bond classes in the two-vector compact form (BondKc, vx_math.cuh) instead of the wide table; this
+//                     production family also leaves out the boundary-condition code (pack_compact sends such robots to the wide one).
 //                     Small robots run with fewer threads per CTA; the launch bounds ask for 512 resident threads per SM
 //                     whatever the CTA size (<= 128 registers per thread), so that several small CTAs share an SM.
 //       VPT          : voxels per thread (thread t owns voxels t, t+T, ...), so a 10^3 robot (NV = 1024) runs
@@ -405,7 +406,7 @@ __global__ void __launch_bounds__(NV / VPT, vx_min_ctas(NV, NV / VPT, FLUID || C
 #pragma unroll
         for (int j = 0; j < VPT; j++) {
             int v = tid + j * T;
-            if (v < n_vox) { Real x = voxel_task<Real>(R, C, v, st[j], own[j], fl[j], F[j], M[j]); sp2 = x > sp2 ? x : sp2; }
+            if (v < n_vox) { Real x = voxel_task<Real, !COMPACT>(R, C, v, st[j], own[j], fl[j], F[j], M[j]); sp2 = x > sp2 ? x : sp2; }
         }
         if (COLLIDE && col_on) {   // SS.MaxVoxVel for the next UpdateCollisions (VX_Sim.cpp:1626-1649)
             float m = (float)sp2;
