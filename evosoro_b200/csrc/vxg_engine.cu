@@ -61,6 +61,7 @@ struct vxg_batch {
     StatsDev* h_stats = nullptr;
     bool dirty = false;          // host mirrors newer than device
     bool ctl_dirty = false;      // only h_ctl newer (step budget)
+    bool tables_dirty = false;   // the class tables must travel again in the other form (bond recording switched on / off)
     std::vector<char> uploaded;
     std::vector<char> slot_dirty;    // the slot's host mirror (blob, Scale, control block) is newer than the device copy
     std::vector<char> reset_image;   // the slot's host mirror is the plain reset image vxg_upload packed (nothing pulled or edited since);
@@ -340,9 +341,9 @@ __global__ void __launch_bounds__(256) vx_reset_kernel(unsigned char* blobs, Blo
 static int flush(vxg_batch* b) {
     CK(cudaSetDevice(b->device));
     size_t nr = (size_t)b->n_robots, mv = (size_t)b->lim.max_vclass, mb = (size_t)b->lim.max_bclass, nv = (size_t)b->L.nv;
-    if (b->dirty) {
+    if (b->dirty || b->tables_dirty) {
         // compact bond tables only if the production kernel runs and every robot of the batch qualifies
-        bool compact = b->prec == VXG_PREC_F32 && b->smem_mode_wide_or_compact;
+        bool compact = b->prec == VXG_PREC_F32 && b->smem_mode_wide_or_compact && !b->d_bond_rec;   // recording batches run the wide family
         for (size_t r = 0; r < nr && compact; r++) if (b->uploaded[r] && !b->h_ctl[r].compact_ok) compact = false;
         b->compact = compact;
         // stride 1024 (10^3 robots): the production family runs 1024 threads x 1 voxel (32 warps, 64 registers: measured 3 % faster
@@ -350,6 +351,7 @@ static int flush(vxg_batch* b) {
         if (b->L.nv == 1024) { b->vpt = compact ? 1 : 2; b->threads = b->L.nv / b->vpt; }
         if (compact) { b->smem_mode = true; b->smem_bytes = b->L.total_bytes + b->tb_compact; }
         else { b->smem_mode = b->smem_wide_fits; b->smem_bytes = b->smem_wide_fits ? b->L.total_bytes + b->tb_wide : b->tb_wide; }
+        if (b->dirty) {
         // Dynamic state travels for the slots the host changed since the last flush only (slot_dirty): the others keep what the
         // device computed.  Whole-population case (every slot a fresh reset image -- the GA's evaluate_all): positions + static
         // section in two strided copies, the rest of the reset image is written by vx_reset_kernel.
@@ -379,6 +381,7 @@ static int flush(vxg_batch* b) {
                 b->last_upload_bytes += tb + 3 * nv * sizeof(double);
             }
         }
+        }
         if (compact) CK(cudaMemcpyAsync(b->d_bk, b->h_bkc, nr * mb * b->bkc_sz(), cudaMemcpyHostToDevice, b->stream));
         else CK(cudaMemcpyAsync(b->d_bk, b->h_bk, nr * mb * b->bk_sz(), cudaMemcpyHostToDevice, b->stream));
         CK(cudaMemcpyAsync(b->d_bk_dist, b->h_bk_dist, nr * mb * sizeof(double), cudaMemcpyHostToDevice, b->stream));
@@ -394,8 +397,8 @@ static int flush(vxg_batch* b) {
         }
     }
     if (b->ctl_dirty) CK(cudaMemcpyAsync(b->d_ctl, b->h_ctl, nr * sizeof(RobotCtl), cudaMemcpyHostToDevice, b->stream));   // the setters pulled it first
-    b->dirty = false; b->ctl_dirty = false;
-    std::fill(b->slot_dirty.begin(), b->slot_dirty.end(), 0);
+    if (b->dirty) std::fill(b->slot_dirty.begin(), b->slot_dirty.end(), 0);
+    b->dirty = false; b->ctl_dirty = false; b->tables_dirty = false;
     return VXG_OK;
 }
 
@@ -452,9 +455,11 @@ extern "C" int vxg_enable_bond_record(vxg_batch* b, int on) {
         size_t bytes = (size_t)b->n_robots * 39 * b->L.nv * b->rs();
         CK(cudaMalloc(&b->d_bond_rec, bytes));
         CK(cudaMemset(b->d_bond_rec, 0, bytes));
+        b->tables_dirty = true;   // the production family does not record: the wide tables travel before the next step
     } else if (!on && b->d_bond_rec) {
         CK(cudaStreamSynchronize(b->stream));
         cudaFree(b->d_bond_rec); b->d_bond_rec = nullptr;
+        b->tables_dirty = true;
     }
     return VXG_OK;
 }

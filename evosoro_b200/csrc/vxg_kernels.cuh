@@ -285,7 +285,9 @@ __global__ void __launch_bounds__(NV / VPT, vx_min_ctas(NV, NV / VPT, FLUID || C
     }
     __syncthreads();
     const Real dt_inv_run = (Real)(1.0 / dt);
-    Real* rec_base = (record_bonds && B.bond_rec) ? B.bond_rec + (size_t)robot * 39 * NV : nullptr;
+    // bond outputs are recorded by the wide-table families only (the engine switches a recording batch to them): the production
+    // family carries neither the pointer nor the per-bond test
+    Real* rec_base = (!COMPACT && record_bonds && B.bond_rec) ? B.bond_rec + (size_t)robot * 39 * NV : nullptr;
 
     // self-collision state (CVX_Sim::UpdateCollisions): the list lives in shared memory during the launch
     const bool col_on = COLLIDE && (flags & VXG_F_COLLISIONS_) != 0 && B.max_col > 0;
@@ -331,7 +333,7 @@ __global__ void __launch_bounds__(NV / VPT, vx_min_ctas(NV, NV / VPT, FLUID || C
         C.scale_c = S.scale_c + cur * B.max_vclass;
         C.dsc_c = S.dsc_c + cur * B.max_vclass;
         const Real dt_inv = (s == 0) ? (Real)0 : dt_inv_run;   // dt == 0 during the very first bond pass (VX_Sim.cpp:373)
-        Real* rec = (k == nsteps - 1) ? rec_base : nullptr;
+        Real* rec = (!COMPACT && k == nsteps - 1) ? rec_base : nullptr;
 
         if (COLLIDE && col_on) {   // UpdateCollisions (VX_Sim.cpp:1729-1755): dt is still 0 in the very first step
             const unsigned int mvb = S.maxvel[(k + 1) & 1];            // written by the previous step's voxel phase
