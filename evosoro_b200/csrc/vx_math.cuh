@@ -305,9 +305,13 @@ template <typename T> struct BondHist {  // _LastPos2, _LastAngle1, _LastAngle2 
 // the common path is one long basic block the scheduler can interleave across the voxels of a thread.
 //   sym_mass : every bond of the robot joins voxels of equal mass/inertia (uniform density, as in all evosoro
 //              palettes): Force2 == -Force1 exactly, so its evaluation and rotation are skipped (robot-uniform flag)
-template <int AX, typename T>
-VX_HD void bond_force(const BondK<T>& k, V3<T> e_w, Q4<T> q1w, Q4<T> q2w, T dnom, T half_bond_z, T dt_inv, bool sym_mass,
+//   SYM      : the same known at compile time (production family: pack_compact admits such robots only), so the voxel-2
+//              constants are never expanded and Moment2 shares the voxel-1 damping terms
+template <int AX, typename T, bool SYM = false>
+VX_HD void bond_force(const BondK<T>& k, V3<T> e_w, Q4<T> q1w, Q4<T> q2w, T dnom, T half_bond_z, T dt_inv, bool sym_mass_rt,
                       bool& small, BondHist<T>& hist, BondOut<T>& out) {
+    const bool sym_mass = SYM || sym_mass_rt;
+    const T c_a2i2 = SYM ? k.c_a2i1 : k.c_a2i2, c_b2fm2 = SYM ? k.c_b2fm1 : k.c_b2fm2, c_b3i2 = SYM ? k.c_b3i1 : k.c_b3i2;
     const T D = k.nom_dist;
     V3<T> e = to_xdir_c<AX>(e_w);
     V3<T> u1 = to_xdir_c<AX>(mk3<T>(q1w.x, q1w.y, q1w.z));
@@ -382,9 +386,9 @@ VX_HD void bond_force(const BondK<T>& k, V3<T> e_w, Q4<T> q1w, Q4<T> q2w, T dnom
     V3<T> M1 = mk3<T>(k.a2 * (an1.x - an2.x) - hz * (k.c_a2i1 * tw),
                       my + k.b3 * ((T)2 * an1.y + an2.y) + hz * (k.c_b2fm1 * rv.z + k.c_b3i1 * ((T)2 * w1.y + w2.y)),
                       mz + k.b3 * ((T)2 * an1.z + an2.z) + hz * (-k.c_b2fm1 * rv.y + k.c_b3i1 * ((T)2 * w1.z + w2.z)));
-    V3<T> M2 = mk3<T>(k.a2 * (an2.x - an1.x) + hz * (k.c_a2i2 * tw),
-                      my + k.b3 * (an1.y + (T)2 * an2.y) + hz * (k.c_b2fm2 * rv.z + k.c_b3i2 * (w1.y + (T)2 * w2.y)),
-                      mz + k.b3 * (an1.z + (T)2 * an2.z) + hz * (-k.c_b2fm2 * rv.y + k.c_b3i2 * (w1.z + (T)2 * w2.z)));
+    V3<T> M2 = mk3<T>(k.a2 * (an2.x - an1.x) + hz * (c_a2i2 * tw),
+                      my + k.b3 * (an1.y + (T)2 * an2.y) + hz * (c_b2fm2 * rv.z + c_b3i2 * (w1.y + (T)2 * w2.y)),
+                      mz + k.b3 * (an1.z + (T)2 * an2.z) + hz * (-c_b2fm2 * rv.y + c_b3i2 * (w1.z + (T)2 * w2.z)));
     hist.p2 = p2; hist.a1 = an1; hist.a2 = an2;
 
     // back to the world frame (:161-170): one rotation matrix for the four vectors

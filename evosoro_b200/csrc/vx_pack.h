@@ -32,6 +32,9 @@ inline bool pack_compact(const vxg_robot_desc* d, BondKc<Real>* bkc, double* len
     for (int i = 0; i < d->n_bclass; i++) {
         const vxg_bond_class& c = d->bclasses[i];
         if (!(c.len > 0) || !near(c.len, L) || !(c.b1 > 0) || !(c.b3 > 0) || !(c.a2 > 0)) { ok = false; continue; }
+        // the production family takes Force2 = -Force1 and shared damping constants for granted: both voxels of every bond
+        // must have the same mass and inertia (uniform density, as in every evosoro palette)
+        if (c.c_a1m1 != c.c_a1m2 || c.c_a2i1 != c.c_a2i2 || c.c_b1m1 != c.c_b1m2 || c.c_b2fm1 != c.c_b2fm2 || c.c_b3i1 != c.c_b3i2) ok = false;
         const double ec = c.b1 / L, th = c.a2 / c.b3, sq = sqrt(th), s1 = c.c_a1m1, s2 = c.c_a1m2;
         ok = ok && near(c.b2, ec * L * L / 2) && near(c.b3, ec * L * L * L / 6);
         ok = ok && near(c.c_b1m1, s1) && near(c.c_b1m2, s2) && near(c.c_b2fm1, s1 * L / 2) && near(c.c_b2fm2, s2 * L / 2);

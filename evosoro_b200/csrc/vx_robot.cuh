@@ -225,7 +225,7 @@ VX_HD bool bond_eval(const RobotView<Real>& R, const RobotConsts<Real>& C, int v
         h.a2 = mk3<Real>(b.z, b.w, c);
     }
     BondOut<Real> o;
-    bond_force<AX, Real>(k, e, q1, q2, dnom, C.half_bond_z, dt_inv, C.sym_mass, small, h, o);
+    bond_force<AX, Real, COMPACT>(k, e, q1, q2, dnom, C.half_bond_z, dt_inv, C.sym_mass, small, h, o);
     if (!o.changed) {   // _LastPos2/_LastAngle* keep their values on a mode-flip step (VXS_BondInternal.cpp:157)
         R4<Real> a, b;
         a.x = h.p2.x; a.y = h.p2.y; a.z = h.p2.z; a.w = h.a1.x;
