@@ -13,6 +13,48 @@
 
 namespace vx {
 
+// Bond classes re-keyed by (bond class, voxel class of either end): every bond of a class then joins the same pair of voxel
+// classes, so NomDistance - L = 0.5 (dScale_1 + dScale_2) is one number per bond class and step (BondPairs / dnom_bc in the
+// kernels) instead of two dependent table look-ups per bond.  With one voxel class per material (every evosoro palette robot)
+// the count does not grow; robots whose per-voxel fields multiply the voxel classes beyond `max_bclass` keep the original
+// classes (ok = false) and run the wide family.
+struct RekeyedBonds {
+    bool ok = false;
+    std::vector<vxg_bond_class> bclasses;
+    std::vector<int32_t> bond_class;
+    std::vector<uint32_t> pair;      // per new class: voxel class of voxel 1 | voxel class of voxel 2 << 16
+    vxg_robot_desc desc;             // the descriptor with the re-keyed arrays swapped in (valid while this object lives)
+};
+inline void rekey_bond_classes(const vxg_robot_desc* d, int max_bclass, RekeyedBonds& out) {
+    out.ok = false; out.bclasses.clear(); out.bond_class.assign(d->n_bond, 0); out.pair.clear();
+    out.desc = *d;
+    // (bond class, voxel class 1, voxel class 2) -> new class: a direct table while the key space is small (palette robots:
+    // 16 x 4 x 4), a map otherwise
+    const size_t nvc = (size_t)d->n_vclass, space = (size_t)(d->n_bclass > 0 ? d->n_bclass : 1) * nvc * nvc;
+    const bool direct = space <= (1u << 16);
+    std::vector<int> table(direct ? space : 0, -1);
+    std::map<size_t, int> keys;
+    for (int j = 0; j < d->n_bond; j++) {
+        const int vc1 = d->vox_class[d->bond_v1[j]], vc2 = d->vox_class[d->bond_v2[j]];
+        const size_t key = ((size_t)d->bond_class[j] * nvc + (size_t)vc1) * nvc + (size_t)vc2;
+        int id = -1;
+        if (direct) id = table[key];
+        else { auto it = keys.find(key); if (it != keys.end()) id = it->second; }
+        if (id < 0) {
+            if ((int)out.bclasses.size() >= max_bclass || vc1 > 0xFFFF || vc2 > 0xFFFF) return;
+            id = (int)out.bclasses.size();
+            if (direct) table[key] = id; else keys.emplace(key, id);
+            out.bclasses.push_back(d->bclasses[d->bond_class[j]]);
+            out.pair.push_back((uint32_t)vc1 | ((uint32_t)vc2 << 16));
+        }
+        out.bond_class[j] = id;
+    }
+    out.ok = true;
+    out.desc.n_bclass = (int)out.bclasses.size();
+    out.desc.bclasses = out.bclasses.data();
+    out.desc.bond_class = out.bond_class.data();
+}
+
 // Compact bond classes (BondKc): returns false when some class is not of the equal-cubic-voxel beam form
 // (relative deviation above 1e-9), the classes do not share one bond length, or a voxel class carries boundary conditions;
 // *len_out = the bond length.
@@ -22,8 +64,9 @@ inline bool pack_compact(const vxg_robot_desc* d, BondKc<Real>* bkc, double* len
     double L = d->n_bclass > 0 ? d->bclasses[0].len : 1.0;
     *len_out = L;
     bool ok = true;
-    // the production family is compiled without the boundary-condition code (fixed DOFs, external loads): robots that use it
-    // run the wide-table family
+    // the production family is compiled without the boundary-condition code (fixed DOFs, external loads) and the sticky floor:
+    // robots that use them run the wide-table family
+    if (d->sim.flags & VXG_F_STICKY_FLOOR) ok = false;
     for (int i = 0; i < d->n_vclass; i++) {
         const vxg_vox_class& c = d->vclasses[i];
         if (c.dof_fixed != 0) ok = false;

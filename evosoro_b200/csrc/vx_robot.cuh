@@ -168,6 +168,7 @@ template <typename Real> struct RobotConsts {
     const VoxK<Real>* vk;       // [n_vclass]
     const double* scale_c;      // [n_vclass] Scale of each class as left by the previous step
     const Real* dsc_c;          // [n_vclass] Scale - NominalSize, narrowed
+    const Real* dnom_bc;        // [n_bclass] 0.5 (dsc_c[class of voxel 1] + dsc_c[class of voxel 2]) of the re-keyed bond classes (compact family)
     const double* nom;          // [3][nv] NominalPosition (global; read for fixed DOFs only)
     const Real* ext_disp;       // [n_vclass][3]
     const Real* ext_tdisp;      // [n_vclass][3]
@@ -214,7 +215,9 @@ VX_HD bool bond_eval(const RobotView<Real>& R, const RobotConsts<Real>& C, int v
     Q4<Real> q1, q2;
     q1.w = qa.x; q1.x = qa.y; q1.y = qa.z; q1.z = qa.w;
     q2.w = qb.x; q2.x = qb.y; q2.y = qb.z; q2.z = qb.w;
-    Real dnom = (Real)0.5 * (C.dsc_c[st.vcls] + C.dsc_c[R.stat[w].vcls]);
+    Real dnom;   // NomDistance - L (VXS_BondInternal.cpp:71)
+    if (COMPACT) dnom = C.dnom_bc[bc];
+    else dnom = (Real)0.5 * (C.dsc_c[st.vcls] + C.dsc_c[R.stat[w].vcls]);
     bool small = (fl >> AX) & 1u;
     R4<Real>* hA = R.histA(AX) + v; R4<Real>* hB = R.histB(AX) + v; Real* hC = R.histC(AX) + v;
     BondHist<Real> h;
@@ -424,7 +427,7 @@ VX_HD Real voxel_task(const RobotView<Real>& R, const RobotConsts<Real>& C, int 
     }
     double nom[3] = {0, 0, 0};
     if (BC && k.has_bc) { nom[0] = C.nom[v]; nom[1] = C.nom[nv + v]; nom[2] = C.nom[2 * nv + v]; }
-    bool sf = voxel_integrate<Real, BC>(k, F, M, 0.5 * C.scale_c[vc], C.floor_on, C.sticky, C.dt, nom,
+    bool sf = voxel_integrate<Real, BC>(k, F, M, 0.5 * C.scale_c[vc], C.floor_on, BC && C.sticky, C.dt, nom,
                                     C.ext_disp + 3 * vc, C.ext_tdisp + 3 * vc, s);
     R.pos[v] = s.px; R.pos[nv + v] = s.py; R.pos[2 * nv + v] = s.pz;
     {

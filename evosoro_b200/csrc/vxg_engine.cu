@@ -48,6 +48,7 @@ struct vxg_batch {
     void* d_bk = nullptr; double* d_bk_dist = nullptr; void* d_vk = nullptr; ScaleK* d_sk = nullptr;
     double* d_scale_c = nullptr; void* d_ext_disp = nullptr; void* d_ext_tdisp = nullptr; double* d_nom = nullptr;
     void* d_bond_rec = nullptr; StatsDev* d_stats = nullptr;
+    uint32_t* d_bpair = nullptr; uint32_t* h_bpair = nullptr;   // voxel-class pair of every re-keyed bond class (compact family)
     // self-collision (allocated when limits.max_col_pairs > 0)
     ColPair* d_col_pairs = nullptr; int16_t* d_col_surf = nullptr; int8_t* d_col_lat4 = nullptr; unsigned long long* d_col_near = nullptr;
     ColPair* h_col_pairs = nullptr; int16_t* h_col_surf = nullptr; int8_t* h_col_lat4 = nullptr; unsigned long long* h_col_near = nullptr;
@@ -102,7 +103,7 @@ template <typename Real> static BatchDev<Real> dev_view(const vxg_batch* b) {
     B.blobs = b->d_blobs; B.L = b->L; B.ctl = b->d_ctl;
     B.bk = (unsigned char*)b->d_bk; B.bk_dist = b->d_bk_dist; B.vk = (VoxK<Real>*)b->d_vk; B.sk = b->d_sk;
     B.scale_c = b->d_scale_c; B.ext_disp = (Real*)b->d_ext_disp; B.ext_tdisp = (Real*)b->d_ext_tdisp; B.nom = b->d_nom;
-    B.bond_rec = (Real*)b->d_bond_rec;
+    B.bond_rec = (Real*)b->d_bond_rec; B.bpair = b->d_bpair;
     B.max_vclass = b->lim.max_vclass; B.max_bclass = b->lim.max_bclass; B.n_robots = b->n_robots;
     B.col_pairs = b->d_col_pairs; B.col_surf = b->d_col_surf; B.col_lat4 = b->d_col_lat4; B.col_near = b->d_col_near;
     B.max_col = b->lim.max_col_pairs;
@@ -124,7 +125,7 @@ static cudaError_t launch_step_p(vxg_batch* b, int n_steps, int record) {
 
 static void free_all(vxg_batch* b) {
     cudaFree(b->d_blobs); cudaFree(b->d_ctl); cudaFree(b->d_bk); cudaFree(b->d_bk_dist); cudaFree(b->d_vk); cudaFree(b->d_sk);
-    cudaFree(b->d_scale_c); cudaFree(b->d_ext_disp); cudaFree(b->d_ext_tdisp); cudaFree(b->d_nom); cudaFree(b->d_bond_rec);
+    cudaFree(b->d_scale_c); cudaFree(b->d_ext_disp); cudaFree(b->d_ext_tdisp); cudaFree(b->d_nom); cudaFree(b->d_bond_rec); cudaFree(b->d_bpair); cudaFreeHost(b->h_bpair);
     cudaFree(b->d_stats);
     cudaFree(b->d_col_pairs); cudaFree(b->d_col_surf); cudaFree(b->d_col_lat4); cudaFree(b->d_col_near);
     cudaFreeHost(b->h_col_pairs); cudaFreeHost(b->h_col_surf); cudaFreeHost(b->h_col_lat4); cudaFreeHost(b->h_col_near);
@@ -182,7 +183,7 @@ extern "C" int vxg_create(vxg_batch** out, int device, int n_robots, const vxg_l
 #define HA(ptr, bytes) if (e == cudaSuccess) { e = cudaMallocHost((void**)&(ptr), (bytes)); if (e == cudaSuccess) memset((ptr), 0, (bytes)); }
     DA(b->d_blobs, nr * b->L.total_bytes); DA(b->d_ctl, nr * sizeof(RobotCtl));
     DA(b->d_bk, nr * mb * b->bk_sz()); DA(b->d_bk_dist, nr * mb * sizeof(double)); DA(b->d_vk, nr * mv * b->vk_sz());
-    DA(b->d_sk, nr * mv * sizeof(ScaleK)); DA(b->d_scale_c, nr * mv * sizeof(double));
+    DA(b->d_sk, nr * mv * sizeof(ScaleK)); DA(b->d_scale_c, nr * mv * sizeof(double)); DA(b->d_bpair, nr * mb * sizeof(uint32_t));
     DA(b->d_ext_disp, nr * mv * 3 * b->rs()); DA(b->d_ext_tdisp, nr * mv * 3 * b->rs()); DA(b->d_nom, nr * 3 * nv * sizeof(double));
     DA(b->d_stats, nr * sizeof(StatsDev));
     if (mc > 0) {
@@ -192,7 +193,7 @@ extern "C" int vxg_create(vxg_batch** out, int device, int n_robots, const vxg_l
     HA(b->h_blobs, nr * b->L.total_bytes); HA(b->h_ctl, nr * sizeof(RobotCtl));
     HA(b->h_bkc, nr * mb * b->bkc_sz());
     HA(b->h_bk, nr * mb * b->bk_sz()); HA(b->h_bk_dist, nr * mb * sizeof(double)); HA(b->h_vk, nr * mv * b->vk_sz());
-    HA(b->h_sk, nr * mv * sizeof(ScaleK)); HA(b->h_scale_c, nr * mv * sizeof(double));
+    HA(b->h_sk, nr * mv * sizeof(ScaleK)); HA(b->h_scale_c, nr * mv * sizeof(double)); HA(b->h_bpair, nr * mb * sizeof(uint32_t));
     HA(b->h_ext_disp, nr * mv * 3 * b->rs()); HA(b->h_ext_tdisp, nr * mv * 3 * b->rs()); HA(b->h_nom, nr * 3 * nv * sizeof(double));
     HA(b->h_stats, nr * sizeof(StatsDev));
     if (mc > 0) {
@@ -277,6 +278,16 @@ extern "C" int vxg_upload(vxg_batch* b, int robot, const vxg_robot_desc* d) {
         const vxg_vox_class& c = d->vclasses[i];
         if (!(c.mass > 0) || !(c.inertia > 0) || !(c.nom_size > 0)) return fail(VXG_ERR_ARG, "vxg_upload: voxel class %d has non-positive mass/inertia/size", i);
     }
+    // bond classes re-keyed by the voxel classes they join (one rest-length deviation per class and step in the compact family);
+    // when that would outgrow the table the robot keeps its classes and the batch runs the wide family
+    RekeyedBonds rk;
+    rekey_bond_classes(d, b->lim.max_bclass, rk);
+    const vxg_robot_desc* d_in = d;
+    if (rk.ok) {
+        d = &rk.desc;
+        memset(b->h_bpair + (size_t)robot * b->lim.max_bclass, 0, (size_t)b->lim.max_bclass * sizeof(uint32_t));
+        memcpy(b->h_bpair + (size_t)robot * b->lim.max_bclass, rk.pair.data(), rk.pair.size() * sizeof(uint32_t));
+    }
     if (b->prec == VXG_PREC_F64) { fill_classes<double>(b, robot, d); reset_blob<double>(b, robot, d); }
     else { fill_classes<float>(b, robot, d); reset_blob<float>(b, robot, d); }
     init_ctl(d, b->h_ctl[robot]);
@@ -304,9 +315,10 @@ extern "C" int vxg_upload(vxg_batch* b, int robot, const vxg_robot_desc* d) {
     {
         double len = 1.0;
         bool ok = b->prec == VXG_PREC_F64 ? fill_compact<double>(b, robot, d, &len) : fill_compact<float>(b, robot, d, &len);
-        b->h_ctl[robot].compact_ok = ok ? 1 : 0;
+        b->h_ctl[robot].compact_ok = (ok && rk.ok) ? 1 : 0;
         b->h_ctl[robot].bond_len = len;
     }
+    d = d_in;
     b->bond_v1[robot].assign(d->bond_v1, d->bond_v1 + d->n_bond);
     b->bond_v2[robot].assign(d->bond_v2, d->bond_v2 + d->n_bond);
     b->bond_axis[robot].assign(d->bond_axis, d->bond_axis + d->n_bond);
@@ -383,6 +395,7 @@ static int flush(vxg_batch* b) {
         }
         }
         if (compact) CK(cudaMemcpyAsync(b->d_bk, b->h_bkc, nr * mb * b->bkc_sz(), cudaMemcpyHostToDevice, b->stream));
+        if (compact) CK(cudaMemcpyAsync(b->d_bpair, b->h_bpair, nr * mb * sizeof(uint32_t), cudaMemcpyHostToDevice, b->stream));
         else CK(cudaMemcpyAsync(b->d_bk, b->h_bk, nr * mb * b->bk_sz(), cudaMemcpyHostToDevice, b->stream));
         CK(cudaMemcpyAsync(b->d_bk_dist, b->h_bk_dist, nr * mb * sizeof(double), cudaMemcpyHostToDevice, b->stream));
         CK(cudaMemcpyAsync(b->d_vk, b->h_vk, nr * mv * b->vk_sz(), cudaMemcpyHostToDevice, b->stream));

@@ -47,6 +47,7 @@ template <typename Real> struct BatchDev {
     VoxK<Real>* vk;             // [n_robots][max_vclass]
     ScaleK* sk;                 // [n_robots][max_vclass]
     double* scale_c;            // [n_robots][max_vclass]  Scale per class as left by the last step
+    uint32_t* bpair;            // [n_robots][max_bclass] voxel-class pair of each re-keyed bond class (compact family)
     Real* ext_disp;             // [n_robots][max_vclass][3]
     Real* ext_tdisp;            // [n_robots][max_vclass][3]
     double* nom;                // [n_robots][3][nv]
@@ -70,6 +71,8 @@ template <typename Real> struct SmemTables {
     double* red;      // [4][32] reduction scratch
     unsigned long long* mbar;   // split-phase barrier between the axis sub-phases
     unsigned int* maxvel;       // [2] max |Vel|^2 of a step as float bits (double-buffered by step parity)
+    uint32_t* bpair;            // [max_bclass] voxel-class pair of each bond class (compact family)
+    Real* dnom_bc;              // [2][max_bclass] rest-length deviation per bond class, double-buffered like dsc_c
     ScaleSim* sl;               // the robot's scale-law constants (read by the few threads that evaluate the law)
     ColPair* pairs;             // [max_col] contact bonds
 };
@@ -88,6 +91,7 @@ __host__ __device__ inline size_t tables_bytes(int max_vclass, int max_bclass, b
     o = vx_align16(o + sizeof(double) * 4 * 32);
     o = vx_align16(o + sizeof(unsigned long long) + 2 * sizeof(unsigned int));
     o = vx_align16(o + sizeof(ScaleSim));
+    if (compact) { o = vx_align16(o + sizeof(uint32_t) * max_bclass); o = vx_align16(o + sizeof(Real) * 2 * max_bclass); }
     o = vx_align16(o + sizeof(ColPair) * max_col);
     return o;
 }
@@ -108,6 +112,11 @@ __device__ inline SmemTables<Real> carve_tables(unsigned char* p, int max_vclass
     t.maxvel = (unsigned int*)(p + o + sizeof(unsigned long long));
     o = vx_align16(o + sizeof(unsigned long long) + 2 * sizeof(unsigned int));
     t.sl = (ScaleSim*)(p + o);      o = vx_align16(o + sizeof(ScaleSim));
+    t.bpair = nullptr; t.dnom_bc = nullptr;
+    if (compact) {
+        t.bpair = (uint32_t*)(p + o);   o = vx_align16(o + sizeof(uint32_t) * max_bclass);
+        t.dnom_bc = (Real*)(p + o);     o = vx_align16(o + sizeof(Real) * 2 * max_bclass);
+    }
     t.pairs = (ColPair*)(p + o);
     return t;
 }
@@ -134,16 +143,19 @@ __device__ inline void mbar_arrive_warp(unsigned long long* bar, bool lane0) {
     __syncwarp();
     if (lane0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or the hint, in ns, runs out)
+// instead of polling -- without the hint a waiting warp re-issues try_wait + branch ~20 times per wait and takes those
+// issue slots from the warps that still work (8 % of all executed instructions in the 1024-thread kernel, ncu)
 __device__ inline void mbar_wait(unsigned long long* bar, unsigned int parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "VX_MBAR_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra VX_MBAR_DONE;\n"
         "bra VX_MBAR_WAIT;\n"
         "VX_MBAR_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
 }
 
 __device__ inline double warp_max(double x) {
@@ -256,7 +268,12 @@ __global__ void __launch_bounds__(NV / VPT, vx_min_ctas(NV, NV / VPT, FLUID || C
     if (tid == 0) mbar_init(S.mbar, T / 32);
     __syncthreads();
     for (int i = tid; i < n_vc; i += T) S.dsc_c[i] = (Real)(S.scale_c[i] - S.sk[i].nom_size);
+    if (COMPACT) for (int i = tid; i < n_bc; i += T) S.bpair[i] = B.bpair[(size_t)robot * B.max_bclass + i];
     __syncthreads();
+    if (COMPACT) {
+        for (int i = tid; i < n_bc; i += T) { const uint32_t pr = S.bpair[i]; S.dnom_bc[i] = (Real)0.5 * (S.dsc_c[pr & 0xFFFFu] + S.dsc_c[pr >> 16]); }
+        __syncthreads();
+    }
     unsigned int mpar = 0;
 
     RobotView<Real> R = make_view<Real>(base, L, n_vox);
@@ -332,6 +349,7 @@ __global__ void __launch_bounds__(NV / VPT, vx_min_ctas(NV, NV / VPT, FLUID || C
         }
         C.scale_c = S.scale_c + cur * B.max_vclass;
         C.dsc_c = S.dsc_c + cur * B.max_vclass;
+        if (COMPACT) C.dnom_bc = S.dnom_bc + cur * B.max_bclass;
         const Real dt_inv = (s == 0) ? (Real)0 : dt_inv_run;   // dt == 0 during the very first bond pass (VX_Sim.cpp:373)
         Real* rec = (!COMPACT && k == nsteps - 1) ? rec_base : nullptr;
 
@@ -404,6 +422,13 @@ __global__ void __launch_bounds__(NV / VPT, vx_min_ctas(NV, NV / VPT, FLUID || C
         }
         if (__syncthreads_or(div)) { diverged = true; break; }   // Integrate() returns before the voxel loop (VX_Sim.cpp:1777)
 
+        if (COMPACT) {   // rest-length deviation of every bond class for the NEXT step: the classes' new Scale was written before the barrier
+            for (int i = tid; i < n_bc; i += T) {
+                const uint32_t pr = S.bpair[i];
+                const Real* dn = S.dsc_c + (cur ^ 1) * B.max_vclass;
+                S.dnom_bc[(cur ^ 1) * B.max_bclass + i] = (Real)0.5 * (dn[pr & 0xFFFFu] + dn[pr >> 16]);
+            }
+        }
         Real sp2 = (Real)0;
 #pragma unroll
         for (int j = 0; j < VPT; j++) {

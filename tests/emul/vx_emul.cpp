@@ -30,7 +30,8 @@ template <typename Real, bool COMPACT = false, bool FLUID = false, bool COLLIDE 
     bool compact_ok = false;
     std::vector<VoxK<Real>> vk;
     std::vector<ScaleK> sk;
-    std::vector<Real> dsc_c[2], ext_disp, ext_tdisp, rec;
+    std::vector<Real> dsc_c[2], dnom_bc[2], ext_disp, ext_tdisp, rec;
+    RekeyedBonds rk;
     std::vector<int32_t> bv1, bax;
     RobotCtl ctl;
     int cur = 0;
@@ -42,6 +43,10 @@ template <typename Real, bool COMPACT = false, bool FLUID = false, bool COLLIDE 
     int n_rebuilds = 0;
 
     Emul(const vxg_robot_desc* d) {
+        if (COMPACT) {   // the compact family works on bond classes re-keyed by voxel-class pair (vx_pack.h), like the engine
+            rekey_bond_classes(d, 1 << 20, rk);
+            d = &rk.desc;
+        }
         L = make_layout(stride_for(d->n_vox), (int)sizeof(Real), FLUID ? ((mesh_vertex_count(d) + 31) & ~31) : 0);
         blob.resize(L.total_bytes);
         nom.resize(3 * (size_t)L.nv);
@@ -57,6 +62,8 @@ template <typename Real, bool COMPACT = false, bool FLUID = false, bool COLLIDE 
         if (FLUID) ctl.n_vert = pack_mesh<Real>(d, L, blob.data(), &ctl.n_facet);
         if (COLLIDE && (ctl.flags & VXG_F_COLLISIONS)) pack_collision_tables(d, ctl.col_hops, surf, lat4, near);
         for (int i = 0; i < nvc; i++) dsc_c[0][i] = (Real)(scale_c[0][i] - sk[i].nom_size);
+        dnom_bc[0].assign(nbc, (Real)0); dnom_bc[1].assign(nbc, (Real)0);
+        if (COMPACT) for (size_t i = 0; i < rk.pair.size(); i++) dnom_bc[0][i] = (Real)0.5 * (dsc_c[0][rk.pair[i] & 0xFFFFu] + dsc_c[0][rk.pair[i] >> 16]);
         rec.assign((size_t)39 * L.nv, (Real)0);
         bv1.assign(d->bond_v1, d->bond_v1 + d->n_bond);
         bax.assign(d->bond_axis, d->bond_axis + d->n_bond);
@@ -79,7 +86,7 @@ template <typename Real, bool COMPACT = false, bool FLUID = false, bool COLLIDE 
         int64_t k;
         for (k = 0; k < n; k++) {
             if (div) break;
-            C.scale_c = scale_c[cur].data(); C.dsc_c = dsc_c[cur].data();
+            C.scale_c = scale_c[cur].data(); C.dsc_c = dsc_c[cur].data(); C.dnom_bc = dnom_bc[cur].data();
             const Real dt_inv = ctl.step == 0 ? (Real)0 : dt_inv_run;
             const bool col_on = COLLIDE && (ctl.flags & VXG_F_COLLISIONS);
             if (col_on) {   // UpdateCollisions (VX_Sim.cpp:1729-1755), same order of operations as the kernel
@@ -120,6 +127,7 @@ template <typename Real, bool COMPACT = false, bool FLUID = false, bool COLLIDE 
                 scale_c[cur ^ 1][i] = ns;
                 dsc_c[cur ^ 1][i] = (Real)(ns - sk[i].nom_size);
             }
+            if (COMPACT) for (size_t i = 0; i < rk.pair.size(); i++) dnom_bc[cur ^ 1][i] = (Real)0.5 * (dsc_c[cur ^ 1][rk.pair[i] & 0xFFFFu] + dsc_c[cur ^ 1][rk.pair[i] >> 16]);
             cur ^= 1;
             ctl.cur_time += ctl.dt;
             ctl.step++;
