@@ -349,6 +349,40 @@ __global__ void __launch_bounds__(256) vx_reset_kernel(unsigned char* blobs, Blo
     for (int i = tid; i < 3 * L.nv; i += T) nm[i] = R.pos[i];
 }
 
+// Dynamic state, host mirrors -> device: the slots the host changed since the last flush only (slot_dirty); the others keep
+// what the device computed.  Whole-population case (every slot a fresh reset image -- the GA's evaluate_all): positions +
+// static section in two strided copies, the rest of the reset image is written by vx_reset_kernel.
+static int flush_state(vxg_batch* b) {
+    size_t nr = (size_t)b->n_robots, mv = (size_t)b->lim.max_vclass, nv = (size_t)b->L.nv;
+    size_t n_dirty = 0; bool all_reset = true;
+    for (size_t r = 0; r < nr; r++) if (b->slot_dirty[r]) { n_dirty++; if (b->uploaded[r] && !b->reset_image[r]) all_reset = false; }
+    b->last_upload_bytes = 0;
+    const size_t tb = b->L.total_bytes;
+    if (n_dirty == nr && all_reset) {
+        const size_t pos_bytes = 3 * nv * sizeof(double), st_bytes = b->L.stat_bytes - b->L.off_stat;
+        CK(cudaMemcpy2DAsync(b->d_blobs + b->L.off_pos, tb, b->h_blobs + b->L.off_pos, tb, pos_bytes, nr, cudaMemcpyHostToDevice, b->stream));
+        CK(cudaMemcpy2DAsync(b->d_blobs + b->L.off_stat, tb, b->h_blobs + b->L.off_stat, tb, st_bytes, nr, cudaMemcpyHostToDevice, b->stream));
+        CK(cudaMemcpyAsync(b->d_ctl, b->h_ctl, nr * sizeof(RobotCtl), cudaMemcpyHostToDevice, b->stream));
+        if (b->prec == VXG_PREC_F64) vx_reset_kernel<double><<<(unsigned)nr, 256, 0, b->stream>>>(b->d_blobs, b->L, b->d_ctl, b->d_nom);
+        else vx_reset_kernel<float><<<(unsigned)nr, 256, 0, b->stream>>>(b->d_blobs, b->L, b->d_ctl, b->d_nom);
+        CK(cudaGetLastError());
+        b->launches++;
+        CK(cudaMemcpyAsync(b->d_scale_c, b->h_scale_c, nr * mv * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+        b->last_upload_bytes += nr * (pos_bytes + st_bytes);
+    } else {
+        for (size_t r = 0; r < nr; r++) {
+            if (!b->slot_dirty[r]) continue;
+            if (b->uploaded[r]) complete_mirror(b, r);
+            CK(cudaMemcpyAsync(b->d_blobs + r * tb, b->h_blobs + r * tb, tb, cudaMemcpyHostToDevice, b->stream));
+            CK(cudaMemcpyAsync(b->d_nom + r * 3 * nv, b->h_nom + r * 3 * nv, 3 * nv * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+            CK(cudaMemcpyAsync(b->d_scale_c + r * mv, b->h_scale_c + r * mv, mv * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+            CK(cudaMemcpyAsync(b->d_ctl + r, b->h_ctl + r, sizeof(RobotCtl), cudaMemcpyHostToDevice, b->stream));
+            b->last_upload_bytes += tb + 3 * nv * sizeof(double);
+        }
+    }
+    return VXG_OK;
+}
+
 // make the device copy current (host mirrors -> device) on the batch stream
 static int flush(vxg_batch* b) {
     CK(cudaSetDevice(b->device));
@@ -363,37 +397,7 @@ static int flush(vxg_batch* b) {
         if (b->L.nv == 1024) { b->vpt = compact ? 1 : 2; b->threads = b->L.nv / b->vpt; }
         if (compact) { b->smem_mode = true; b->smem_bytes = b->L.total_bytes + b->tb_compact; }
         else { b->smem_mode = b->smem_wide_fits; b->smem_bytes = b->smem_wide_fits ? b->L.total_bytes + b->tb_wide : b->tb_wide; }
-        if (b->dirty) {
-        // Dynamic state travels for the slots the host changed since the last flush only (slot_dirty): the others keep what the
-        // device computed.  Whole-population case (every slot a fresh reset image -- the GA's evaluate_all): positions + static
-        // section in two strided copies, the rest of the reset image is written by vx_reset_kernel.
-        size_t n_dirty = 0; bool all_reset = true;
-        for (size_t r = 0; r < nr; r++) if (b->slot_dirty[r]) { n_dirty++; if (b->uploaded[r] && !b->reset_image[r]) all_reset = false; }
-        b->last_upload_bytes = 0;
-        const size_t tb = b->L.total_bytes;
-        if (n_dirty == nr && all_reset) {
-            const size_t pos_bytes = 3 * nv * sizeof(double), st_bytes = b->L.stat_bytes - b->L.off_stat;
-            CK(cudaMemcpy2DAsync(b->d_blobs + b->L.off_pos, tb, b->h_blobs + b->L.off_pos, tb, pos_bytes, nr, cudaMemcpyHostToDevice, b->stream));
-            CK(cudaMemcpy2DAsync(b->d_blobs + b->L.off_stat, tb, b->h_blobs + b->L.off_stat, tb, st_bytes, nr, cudaMemcpyHostToDevice, b->stream));
-            CK(cudaMemcpyAsync(b->d_ctl, b->h_ctl, nr * sizeof(RobotCtl), cudaMemcpyHostToDevice, b->stream));
-            if (b->prec == VXG_PREC_F64) vx_reset_kernel<double><<<(unsigned)nr, 256, 0, b->stream>>>(b->d_blobs, b->L, b->d_ctl, b->d_nom);
-            else vx_reset_kernel<float><<<(unsigned)nr, 256, 0, b->stream>>>(b->d_blobs, b->L, b->d_ctl, b->d_nom);
-            CK(cudaGetLastError());
-            b->launches++;
-            CK(cudaMemcpyAsync(b->d_scale_c, b->h_scale_c, nr * mv * sizeof(double), cudaMemcpyHostToDevice, b->stream));
-            b->last_upload_bytes += nr * (pos_bytes + st_bytes);
-        } else {
-            for (size_t r = 0; r < nr; r++) {
-                if (!b->slot_dirty[r]) continue;
-                if (b->uploaded[r]) complete_mirror(b, r);
-                CK(cudaMemcpyAsync(b->d_blobs + r * tb, b->h_blobs + r * tb, tb, cudaMemcpyHostToDevice, b->stream));
-                CK(cudaMemcpyAsync(b->d_nom + r * 3 * nv, b->h_nom + r * 3 * nv, 3 * nv * sizeof(double), cudaMemcpyHostToDevice, b->stream));
-                CK(cudaMemcpyAsync(b->d_scale_c + r * mv, b->h_scale_c + r * mv, mv * sizeof(double), cudaMemcpyHostToDevice, b->stream));
-                CK(cudaMemcpyAsync(b->d_ctl + r, b->h_ctl + r, sizeof(RobotCtl), cudaMemcpyHostToDevice, b->stream));
-                b->last_upload_bytes += tb + 3 * nv * sizeof(double);
-            }
-        }
-        }
+        if (b->dirty) { int rc = flush_state(b); if (rc) return rc; }
         if (compact) CK(cudaMemcpyAsync(b->d_bk, b->h_bkc, nr * mb * b->bkc_sz(), cudaMemcpyHostToDevice, b->stream));
         if (compact) CK(cudaMemcpyAsync(b->d_bpair, b->h_bpair, nr * mb * sizeof(uint32_t), cudaMemcpyHostToDevice, b->stream));
         else CK(cudaMemcpyAsync(b->d_bk, b->h_bk, nr * mb * b->bk_sz(), cudaMemcpyHostToDevice, b->stream));
