@@ -216,7 +216,7 @@ __device__ __noinline__ int col_rebuild(const RobotView<Real>& R, const RobotCon
 // (128 registers at 512 threads, 64 at 1024).  Stride 512: two robots fit -> 2 x 512 threads, 64 registers (the fluid and
 // self-collision variants need more registers and room: 1).  Smaller robots: 768 resident threads, i.e. 80 registers -- what one voxel per thread needs without spilling.
 __host__ __device__ constexpr int vx_min_ctas(int nv, int threads, bool extras) {   // extras: fluid / self-collision variants (more registers)
-    return nv >= 1024 ? 1 : (nv >= 512 ? (extras ? 1 : VX_CTAS_512) : 768 / threads);
+    return nv >= 1024 ? 1 : (nv >= 512 ? (extras ? 1 : VX_CTAS_512) : (threads == 224 ? 4 : 768 / threads));   // 4 x 224: 72 registers
 }
 //       FLUID        : blob layout with the land/water surface-mesh arrays; robots with VXG_F_FLUID get the drag phase.
 //       COLLIDE      : self-collision support compiled in (contact-bond list, rebuild, max-velocity reduction); kept out

@@ -30,6 +30,7 @@ inline cudaError_t launch_by_stride(const BatchDev<Real>& B, const LaunchCfg& c)
     switch (c.nv) {
         case 64: return launch_one<Real, 64, 1, SMEM, COMPACT, FLUID, COLLIDE>(B, c);
         case 128: return launch_one<Real, 128, 1, SMEM, COMPACT, FLUID, COLLIDE>(B, c);
+        case 224: return launch_one<Real, 224, 1, SMEM, COMPACT, FLUID, COLLIDE>(B, c);
         case 256: return launch_one<Real, 256, 1, SMEM, COMPACT, FLUID, COLLIDE>(B, c);
         case 512: return launch_one<Real, 512, 1, SMEM, COMPACT, FLUID, COLLIDE>(B, c);
         case 1024:
