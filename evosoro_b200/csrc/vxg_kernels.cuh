@@ -215,14 +215,18 @@ __device__ __noinline__ int col_rebuild(const RobotView<Real>& R, const RobotCon
 // Resident CTAs per SM the register allocation is sized for.  Stride 1024 and up: one robot fills the SM's shared memory -> 1
 // (128 registers at 512 threads, 64 at 1024).  Stride 512: two robots fit -> 2 x 512 threads, 64 registers (the fluid and
 // self-collision variants need more registers and room: 1).  Smaller robots: 768 resident threads, i.e. 80 registers -- what one voxel per thread needs without spilling.
-__host__ __device__ constexpr int vx_min_ctas(int nv, int threads, bool extras) {   // extras: fluid / self-collision variants (more registers)
-    return nv >= 1024 ? 1 : (nv >= 512 ? (extras ? 1 : VX_CTAS_512) : (threads == 224 ? 4 : 768 / threads));   // 4 x 224: 72 registers
+__host__ __device__ constexpr int vx_min_ctas(int nv, int threads, bool extras, bool fp64) {   // extras: fluid / self-collision variants
+    return fp64 ? 1                                        // the logic-parity mode needs its registers, not occupancy
+         : nv >= 1024 ? 1
+         : nv >= 512 ? (extras ? 1 : VX_CTAS_512)
+         : (threads == 224 && !extras) ? 4                 // 4 x 224 threads: 72 registers
+         : 768 / threads;
 }
 //       FLUID        : blob layout with the land/water surface-mesh arrays; robots with VXG_F_FLUID get the drag phase.
 //       COLLIDE      : self-collision support compiled in (contact-bond list, rebuild, max-velocity reduction); kept out
 //                     of the other instantiations so that they do not pay its registers.
 template <typename Real, int NV, int VPT, bool SMEM, bool COMPACT, bool FLUID = false, bool COLLIDE = false>
-__global__ void __launch_bounds__(NV / VPT, vx_min_ctas(NV, NV / VPT, FLUID || COLLIDE)) vx_step_kernel(BatchDev<Real> B, int n_steps, int record_bonds) {
+__global__ void __launch_bounds__(NV / VPT, vx_min_ctas(NV, NV / VPT, FLUID || COLLIDE, sizeof(Real) == 8)) vx_step_kernel(BatchDev<Real> B, int n_steps, int record_bonds) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int T = NV / VPT;
     constexpr BlobLayout LC = make_layout(NV, (int)sizeof(Real));
