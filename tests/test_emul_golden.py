@@ -66,8 +66,8 @@ def test_emulated_f32_kernel_arithmetic(name, prec):
             pytest.skip("the self-collision kernels use the wide bond table")
         prec = 6   # fp32 with the self-collision list
     e = emul_lib.EmulSim(g.robot(), prec)
-    if prec == 2 and name.startswith("bc_"):
-        assert not e.h   # robots with fixed / forced voxels are kept out of the production family (compiled without that code)
+    if prec == 2 and (name.startswith("bc_") or name == "dense3_density"):
+        assert not e.h   # robots with fixed / forced voxels or bonds between voxels of different mass are kept out of the production family
         return
     assert e.h, "bond classes did not qualify for the compact form"
     for f in range(1, d.vstate.shape[0]):

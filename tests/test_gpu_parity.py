@@ -227,6 +227,30 @@ def test_largest_supported_robot_and_the_size_limit():
     assert ei.value.code > 0   # unsupported size: the caller must abort
 
 
+def test_robots_outside_the_production_family_run_the_wide_one():
+    """The production kernels take equal end-voxel masses, no boundary conditions and no sticky floor for granted; a batch with
+    one robot outside that set (here: materials of different density) must run the full-feature family -- visible in the launch
+    shape of a 10^3 batch (512 x 2 instead of 1024 x 1) -- and still agree with the oracle."""
+    sim = vxa.SimParams(init_cm_time=0.01, stop_condition_value=0.2)
+    pal = vxa.four_material_palette()
+    pal[1].density, pal[2].density = 3e6, 5e5
+    plain = engine.Model(text=vxa.vxa_text(vxa.dense_lattice(10, 5), sim=sim)).robot
+    heavy = engine.Model(text=vxa.vxa_text(vxa.dense_lattice(10, 5), sim=sim, palette=pal)).robot
+    a = engine.Batch([plain, plain])
+    assert a.kernel_config()["threads"] == 1024
+    a.close()
+    b = engine.Batch([plain, heavy], max_bclass=max(len(plain.bclasses), len(heavy.bclasses)))
+    cfg = b.kernel_config()
+    assert cfg["threads"] == 512 and cfg["voxels_per_thread"] == 2 and cfg["smem_resident"]
+    b.step(200)
+    assert not b.sync().any()
+    for r, rob in enumerate((plain, heavy)):
+        o = oracle_lib.OracleSim(rob)
+        o.step(200)
+        assert common.max_abs(b.download(r).pos, o.state().pos) <= 1e-5 * LAT
+    b.close()
+
+
 def test_step_chunking_is_exact():
     """K steps in one launch == K single-step launches (state round-trips through HBM exactly)."""
     rob = engine.Model(text=vxa.vxa_text(vxa.dense_lattice(4, 11))).robot

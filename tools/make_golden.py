@@ -81,6 +81,11 @@ def main():
     case("dense6_s1_full", vxa.dense_lattice(6, 1), 0, 1, full=True)
     # the headline shape: dense 10^3, whole 5 s CLI run (78 054 steps x 1000 voxels): final COM / fitness only
     case("dense10_s3_full", vxa.dense_lattice(10, 3), 0, 1, full=True)
+    # materials of different density: the two voxels of a bond have different mass, so Force2 != -Force1 in the damping terms
+    # (VXS_BondInternal.cpp:310-346) -- such robots run the wide kernel family
+    pal = vxa.four_material_palette()
+    pal[0].density, pal[1].density, pal[2].density, pal[3].density = 1e6, 3e6, 5e5, 2e6
+    case("dense3_density", vxa.dense_lattice(3, 14), 1200, 100, sim=S(init_cm_time=0.02, stop_condition_value=0.2), palette=pal)
     # single voxel / no bonds (edge case: empty bond list)
     one = np.zeros((2, 2, 2), dtype=np.int32); one[0, 0, 0] = 1
     case("single_voxel", one, 300, 100, sim=S(init_cm_time=0.01, stop_condition_value=0.1))
@@ -191,7 +196,11 @@ def evosoro_cases():
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "evosoro":
+    if len(sys.argv) > 1 and sys.argv[1] == "density":
+        pal = vxa.four_material_palette()
+        pal[0].density, pal[1].density, pal[2].density, pal[3].density = 1e6, 3e6, 5e5, 2e6
+        case("dense3_density", vxa.dense_lattice(3, 14), 1200, 100, sim=vxa.SimParams(init_cm_time=0.02, stop_condition_value=0.2), palette=pal)
+    elif len(sys.argv) > 1 and sys.argv[1] == "evosoro":
         evosoro_cases()
     elif len(sys.argv) > 1 and sys.argv[1] == "big":
         case("dense10_s3_full", vxa.dense_lattice(10, 3), 0, 1, full=True)
