@@ -49,12 +49,13 @@ def algorithmic_bytes_per_voxel_step(n_vox: int, n_bond: int) -> float:
     return 115.0 + 72.0 * n_bond / n_vox
 
 
+SELFCOL = False  # --selfcol: SelfColEnabled=1 in every .vxa
 WATER = False   # --workload water: BASELINE.json config 5 (land/water fork, fluid drag) instead of the headline config
 
 
 def synthetic_vxa(n: int, seed: int) -> str:
     from evosoro_b200 import vxa
-    sim = vxa.SimParams(init_cm_time=INIT_CM_TIME, stop_condition_value=5.0)
+    sim = vxa.SimParams(init_cm_time=INIT_CM_TIME, stop_condition_value=5.0, self_col_enabled=1 if SELFCOL else 0)
     if WATER:   # evosoro/examples/swimming_basic.py:68-70,137-138
         env = vxa.EnvParams(fluid_environment=1, aggregate_drag_coefficient=750.0)
         return vxa.vxa_text(vxa.dense_lattice(n, seed), sim=sim, env=env)
@@ -66,7 +67,7 @@ def workload_name(n: int, robots: int) -> str:
         return (f"land/water fork: dense{n}^3 x {robots} robots per GPU ({n ** 3} voxels / {3 * n * n * (n - 1)} bonds each), 4 materials, "
                 "fluid environment (surface drag, C_d 750), thermal actuation")
     return (f"dense{n}^3 x {robots} robots per GPU ({n ** 3} voxels / {3 * n * n * (n - 1)} bonds each), 4 materials, "
-            "gravity+floor+thermal actuation, SelfCol 0")
+            "gravity+floor+thermal actuation, SelfCol " + ("1 (contact-bond list rebuilt on the device)" if SELFCOL else "0"))
 
 
 def measured_peak_gbs():
@@ -376,10 +377,12 @@ def main():
     ap.add_argument("--cpu-timesteps", type=int, default=10000, help="timed timesteps of the cpu_baseline sample")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--selfcol", action="store_true", help="SelfColEnabled=1 (evosoro's GA default): the self-collision kernel family; our arm only")
     ap.add_argument("--workload", default="land", choices=["land", "water"], help="water = BASELINE config 5 (use --lattice 8 --robots 2048)")
     args = ap.parse_args()
-    global WATER
+    global WATER, SELFCOL
     WATER = args.workload == "water"
+    SELFCOL = bool(args.selfcol)
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":

@@ -283,32 +283,41 @@ inline int pack_mesh(const vxg_robot_desc* d, const BlobLayout& L, unsigned char
 // VX_Voxel.cpp:171-209): the surface voxels (any of the 6 faces without a bond), every voxel's lattice
 // coordinates, and per voxel a 64-bit mask over the lattice offsets with |dx|+|dy|+|dz| <= 3 telling which of
 // those voxels are within `hops` bond hops (NearbyVoxInds).  Returns false if hops > 3.
-inline int near_code_host(int dx, int dy, int dz) {
-    int code = 0;
-    for (int z = -3; z <= 3; z++) for (int y = -3; y <= 3; y++) for (int x = -3; x <= 3; x++) {
-        if (abs(x) + abs(y) + abs(z) > 3) continue;
-        if (x == dx && y == dy && z == dz) return code;
-        code++;
-    }
-    return -1;
+inline int near_code_host(int dx, int dy, int dz) {   // rank of (dx,dy,dz) among the offsets with |dx|+|dy|+|dz| <= 3, z slowest (as near_code on the device)
+    struct Table {
+        signed char code[7][7][7];
+        Table() {
+            int c = 0;
+            for (int z = -3; z <= 3; z++) for (int y = -3; y <= 3; y++) for (int x = -3; x <= 3; x++)
+                code[z + 3][y + 3][x + 3] = (abs(x) + abs(y) + abs(z) > 3) ? (signed char)-1 : (signed char)c++;
+        }
+    };
+    static const Table t;
+    if (dx < -3 || dx > 3 || dy < -3 || dy > 3 || dz < -3 || dz > 3) return -1;
+    return t.code[dz + 3][dy + 3][dx + 3];
 }
 inline bool pack_collision_tables(const vxg_robot_desc* d, int hops, std::vector<int16_t>& surf, std::vector<int8_t>& lat4, std::vector<unsigned long long>& near) {
     if (hops > 3) return false;
     std::vector<int> ijk; lattice_coords(d, ijk);
     int lo[3] = {1 << 30, 1 << 30, 1 << 30};
     for (int i = 0; i < d->n_vox; i++) for (int a = 0; a < 3; a++) if (ijk[3 * i + a] < lo[a]) lo[a] = ijk[3 * i + a];
-    std::vector<std::vector<int>> adj(d->n_vox);
-    std::vector<int> nb(d->n_vox, 0);
-    for (int j = 0; j < d->n_bond; j++) { adj[d->bond_v1[j]].push_back(d->bond_v2[j]); adj[d->bond_v2[j]].push_back(d->bond_v1[j]); nb[d->bond_v1[j]]++; nb[d->bond_v2[j]]++; }
+    std::vector<int> adj((size_t)6 * d->n_vox, -1), nb(d->n_vox, 0);   // a voxel has at most one bond per direction
+    for (int j = 0; j < d->n_bond; j++) { const int a = d->bond_v1[j], b = d->bond_v2[j]; adj[6 * a + nb[a]++] = b; adj[6 * b + nb[b]++] = a; }
     surf.clear(); lat4.assign((size_t)4 * d->n_vox, 0); near.assign(d->n_vox, 0ULL);
+    std::vector<int> mark(d->n_vox, -1), seen;
+    seen.reserve(128);
     for (int i = 0; i < d->n_vox; i++) {
         if (nb[i] < 6) surf.push_back((int16_t)i);   // IsSurfaceVoxel (VX_Voxel.h:80)
         for (int a = 0; a < 3; a++) { int c = ijk[3 * i + a] - lo[a]; if (c > 120) return false; lat4[4 * i + a] = (int8_t)c; }
-        std::vector<int> cur(1, i), seen(1, i);   // breadth-first over the permanent bonds
+        seen.clear(); seen.push_back(i); mark[i] = i;   // breadth-first over the permanent bonds, `hops` levels
+        size_t begin = 0;
         for (int h = 0; h < hops; h++) {
-            std::vector<int> nxt;
-            for (int u : cur) for (int w : adj[u]) { bool s = false; for (int x : seen) if (x == w) { s = true; break; } if (!s) { seen.push_back(w); nxt.push_back(w); } }
-            cur.swap(nxt);
+            const size_t end = seen.size();
+            for (size_t k = begin; k < end; k++) {
+                const int u = seen[k];
+                for (int e = 0; e < nb[u]; e++) { const int w = adj[6 * u + e]; if (mark[w] != i) { mark[w] = i; seen.push_back(w); } }
+            }
+            begin = end;
         }
         for (int w : seen) {
             int code = near_code_host(ijk[3 * w] - ijk[3 * i], ijk[3 * w + 1] - ijk[3 * i + 1], ijk[3 * w + 2] - ijk[3 * i + 2]);

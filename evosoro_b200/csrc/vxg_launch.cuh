@@ -46,6 +46,7 @@ cudaError_t launch_f32_compact(const BatchDev<float>& B, const LaunchCfg& c);   
 cudaError_t launch_f32_wide(const BatchDev<float>& B, const LaunchCfg& c, bool smem);         // fp32, wide table, smem or global blob
 cudaError_t launch_f64(const BatchDev<double>& B, const LaunchCfg& c, bool smem);             // logic-parity mode
 cudaError_t launch_f32_collide(const BatchDev<float>& B, const LaunchCfg& c);                 // + self-collision
+cudaError_t launch_f32_collide_compact(const BatchDev<float>& B, const LaunchCfg& c);         // + self-collision, production form
 cudaError_t launch_f32_fluid(const BatchDev<float>& B, const LaunchCfg& c, bool collide);     // land/water layouts (+ self-collision)
 void launch_stats_f32(const BatchDev<float>& B, StatsDev* out, int n_robots, cudaStream_t s);
 void launch_stats_f64(const BatchDev<double>& B, StatsDev* out, int n_robots, cudaStream_t s);
