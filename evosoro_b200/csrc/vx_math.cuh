@@ -246,7 +246,8 @@ template <typename T> struct alignas(16) BondK {   // from vxg_bond_class
 // Two 128-bit loads per bond instead of five; the host verifies the relations per class at upload
 // (pack_classes) and the batch falls back to the wide table if any class deviates.
 template <typename T> struct alignas(16) BondKc {
-    T ec, k_axial, s1, s2;                      // composite E; axial force per unit _Pos2.x; 2 sqrt(E L m1), 2 sqrt(E L m2)
+    T ec, k_axial, s1, sf1;                     // composite E; axial force per unit _Pos2.x; 2 sqrt(E L m) (both voxels of a bond have
+                                                // the same mass in this form); voxel 1's share of the axial strain (voxel 2's = 2 - sf1)
     T tnu_half, sq_tnu, nom_dist, len_minus_dist;   // 1/(2(1+nu)) and its square root; pitch; L.x - pitch
 };
 template <typename T> struct BondGeo { T L, L2h, L3s, Lh, L2s, inv_len; };   // L, L^2/2, L^3/6, L/2, L^2/6, 1/L
@@ -259,11 +260,11 @@ template <typename T> VX_HD BondK<T> expand_bond(const BondKc<T>& c, const BondG
     BondK<T> k;
     k.b1 = c.ec * g.L; k.b2 = c.ec * g.L2h; k.b3 = c.ec * g.L3s; k.a2 = k.b3 * c.tnu_half;
     k.inv_len = g.inv_len; k.k_axial = c.k_axial; k.nom_dist = c.nom_dist; k.len_minus_dist = c.len_minus_dist;
-    k.c_a1m1 = c.s1; k.c_a1m2 = c.s2; k.c_b1m1 = c.s1; k.c_b1m2 = c.s2;
-    k.c_b2fm1 = c.s1 * g.Lh; k.c_b2fm2 = c.s2 * g.Lh;
-    k.c_b3i1 = c.s1 * g.L2s; k.c_b3i2 = c.s2 * g.L2s;
+    k.c_a1m1 = c.s1; k.c_a1m2 = c.s1; k.c_b1m1 = c.s1; k.c_b1m2 = c.s1;
+    k.c_b2fm1 = c.s1 * g.Lh; k.c_b2fm2 = k.c_b2fm1;
+    k.c_b3i1 = c.s1 * g.L2s; k.c_b3i2 = k.c_b3i1;
     k.c_a2i1 = k.c_b3i1 * c.sq_tnu; k.c_a2i2 = k.c_b3i2 * c.sq_tnu;
-    k.sf1 = (T)1; k.sf2 = (T)1;   // the compact form is not used by the fluid kernels (they need the real factors)
+    k.sf1 = c.sf1; k.sf2 = (T)2 - c.sf1;   // the two shares add up to 2 (UpdateBondStrain's balancing step), both 1 for equal moduli
     k.homogeneous = 0;
     return k;
 }

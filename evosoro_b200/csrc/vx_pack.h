@@ -84,7 +84,11 @@ inline bool pack_compact(const vxg_robot_desc* d, BondKc<Real>* bkc, double* len
         ok = ok && near(c.c_b3i1, s1 * L * L / 6) && near(c.c_b3i2, s2 * L * L / 6);
         ok = ok && near(c.c_a2i1, s1 * L * L / 6 * sq) && near(c.c_a2i2, s2 * L * L / 6 * sq);
         BondKc<Real>& k = bkc[i];
-        k.ec = (Real)ec; k.s1 = (Real)s1; k.s2 = (Real)s2; k.tnu_half = (Real)th; k.sq_tnu = (Real)sq;
+        k.ec = (Real)ec; k.s1 = (Real)s1; k.tnu_half = (Real)th; k.sq_tnu = (Real)sq;
+        {   // strain share of voxel 1 (-> SetStrainDir, VXS_BondInternal.cpp:300-304): 1 unless the stress-balancing iteration ran
+            const double diff = c.e1 >= c.e2 ? c.e1 - c.e2 : c.e2 - c.e1, sum = c.e1 + c.e2;
+            k.sf1 = (Real)((!c.homogeneous && diff > sum * .0005) ? 2.0 * c.e2 / sum : 1.0);
+        }
         k.nom_dist = (Real)c.nom_dist; k.len_minus_dist = (Real)(c.len - c.nom_dist);
         double e_eff = c.e1;
         if (!c.homogeneous) {

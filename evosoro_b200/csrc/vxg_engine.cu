@@ -117,7 +117,8 @@ static cudaError_t launch_step_p(vxg_batch* b, int n_steps, int record) {
     c.vpt = b->vpt;
     if (b->prec == VXG_PREC_F64) return launch_f64(dev_view<double>(b), c, b->smem_mode);
     const BatchDev<float> B = dev_view<float>(b);
-    if (b->L.nvert_cap > 0) return launch_f32_fluid(B, c, b->lim.max_col_pairs > 0);
+    if (b->L.nvert_cap > 0)
+        return (b->compact && b->smem_mode) ? launch_f32_fluid_compact(B, c, b->lim.max_col_pairs > 0) : launch_f32_fluid(B, c, b->lim.max_col_pairs > 0);
     if (b->lim.max_col_pairs > 0) return (b->compact && b->smem_mode) ? launch_f32_collide_compact(B, c) : launch_f32_collide(B, c);
     if (!b->smem_mode) return launch_f32_wide(B, c, false);
     return b->compact ? launch_f32_compact(B, c) : launch_f32_wide(B, c, true);
@@ -170,8 +171,7 @@ extern "C" int vxg_create(vxg_batch** out, int device, int n_robots, const vxg_l
     b->smem_wide_fits = b->L.total_bytes + tb <= (size_t)max_smem;
     b->smem_mode_wide_or_compact = b->prec == VXG_PREC_F32 && b->L.total_bytes + b->tb_compact <= (size_t)max_smem;
     if (mc > 0 && lim->precision != VXG_PREC_F32) { delete b; return fail(VXG_UNSUPPORTED_FEATURE, "vxg_create: the self-collision kernels exist in fp32 only"); }
-    if (mc > 0 || b->L.nvert_cap > 0) {   // these layouts run shared-memory resident only; the fluid ones with the wide table only
-        if (b->L.nvert_cap > 0) b->smem_mode_wide_or_compact = false;
+    if (mc > 0 || b->L.nvert_cap > 0) {   // these layouts run shared-memory resident only
         if (!b->smem_wide_fits) { delete b; return fail(VXG_UNSUPPORTED_SIZE, "vxg_create: robot blob with collision list / surface mesh (%zu B) exceeds shared memory", b->L.total_bytes + tb); }
     }
     b->smem_mode = b->smem_wide_fits || b->smem_mode_wide_or_compact;   // final choice is made at flush, when the classes are known
@@ -394,7 +394,7 @@ static int flush(vxg_batch* b) {
         b->compact = compact;
         // stride 1024 (10^3 robots): the production family runs 1024 threads x 1 voxel (32 warps, 64 registers: measured 3 % faster
         // than 512 x 2 at 128 registers -- more warps hide the barrier and shared-memory latency); the other families keep 512 x 2
-        if (b->L.nv == 1024) { b->vpt = (compact && b->lim.max_col_pairs == 0) ? 1 : 2; b->threads = b->L.nv / b->vpt; }
+        if (b->L.nv == 1024) { b->vpt = (compact && b->lim.max_col_pairs == 0 && b->L.nvert_cap == 0) ? 1 : 2; b->threads = b->L.nv / b->vpt; }
         if (compact) { b->smem_mode = true; b->smem_bytes = b->L.total_bytes + b->tb_compact; }
         else { b->smem_mode = b->smem_wide_fits; b->smem_bytes = b->smem_wide_fits ? b->L.total_bytes + b->tb_wide : b->tb_wide; }
         if (b->dirty) { int rc = flush_state(b); if (rc) return rc; }

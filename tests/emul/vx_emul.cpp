@@ -173,6 +173,14 @@ void* vxe_create(const vxg_robot_desc* d, int prec) {
     if (prec == 6) return new Emul<float, false, false, true>(d);    // fp32 with self-collision
     if (prec == 3) return new Emul<float, false, true>(d);    // fp32, land/water layout with the fluid-drag phase
     if (prec == 4) return new Emul<double, false, true>(d);   // fp64, same (logic parity of the drag phase on the CPU)
+    if (prec == 9 || prec == 10 || prec == 11) {   // fp32 compact form with the land/water drag phase (10: and the self-collision list; 11: list only)
+        EmulBase* e; bool ok;
+        if (prec == 9) { auto* x = new Emul<float, true, true>(d); ok = x->compact_ok; e = x; }
+        else if (prec == 10) { auto* x = new Emul<float, true, true, true>(d); ok = x->compact_ok; e = x; }
+        else { auto* x = new Emul<float, true, false, true>(d); ok = x->compact_ok; e = x; }
+        if (!ok) { delete e; return nullptr; }
+        return e;
+    }
     if (prec == 2) {   // fp32 with the compact bond table (what the production kernel uses when every class qualifies)
         Emul<float, true>* e = new Emul<float, true>(d);
         if (!e->compact_ok) { delete e; return nullptr; }

@@ -57,14 +57,10 @@ def test_emulated_f32_kernel_arithmetic(name, prec):
     g = golden_lib.Golden(name)
     d = g.dump
     LAT = float(d.sim[14])   # the fixture's own lattice pitch
-    if FLUID(name):
-        if prec == 2:
-            pytest.skip("the fluid kernels use the wide bond table")
-        prec = 8 if COLLIDE(name) else 3   # fp32 with the land/water drag phase (8: and the self-collision list)
+    if FLUID(name):   # fp32 with the land/water drag phase (8 / 10: and the self-collision list); 9 / 10 = the compact form
+        prec = (10 if COLLIDE(name) else 9) if prec == 2 else (8 if COLLIDE(name) else 3)
     elif COLLIDE(name):
-        if prec == 2:
-            pytest.skip("the self-collision kernels use the wide bond table")
-        prec = 6   # fp32 with the self-collision list
+        prec = 11 if prec == 2 else 6   # fp32 with the self-collision list (11: compact form)
     e = emul_lib.EmulSim(g.robot(), prec)
     if prec == 2 and (name.startswith("bc_") or name == "dense3_density"):
         assert not e.h   # robots with fixed / forced voxels or bonds between voxels of different mass are kept out of the production family
