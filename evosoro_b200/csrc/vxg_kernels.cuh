@@ -71,6 +71,7 @@ template <typename Real> struct SmemTables {
     double* red;      // [4][32] reduction scratch
     unsigned long long* mbar;   // split-phase barrier between the axis sub-phases
     unsigned int* maxvel;       // [2] max |Vel|^2 of a step as float bits (double-buffered by step parity)
+    unsigned int* colflag;      // [2] thread 0's verdict for this step: rebuild the contact-bond list (by step parity)
     uint32_t* bpair;            // [max_bclass] voxel-class pair of each bond class (compact family)
     Real* dnom_bc;              // [2][max_bclass] rest-length deviation per bond class, double-buffered like dsc_c
     ScaleSim* sl;               // the robot's scale-law constants (read by the few threads that evaluate the law)
@@ -89,7 +90,7 @@ __host__ __device__ inline size_t tables_bytes(int max_vclass, int max_bclass, b
     o = vx_align16(o + sizeof(Real) * 3 * max_vclass);
     o = vx_align16(o + sizeof(Real) * 3 * max_vclass);
     o = vx_align16(o + sizeof(double) * 4 * 32);
-    o = vx_align16(o + sizeof(unsigned long long) + 2 * sizeof(unsigned int));
+    o = vx_align16(o + sizeof(unsigned long long) + 4 * sizeof(unsigned int));
     o = vx_align16(o + sizeof(ScaleSim));
     if (compact) { o = vx_align16(o + sizeof(uint32_t) * max_bclass); o = vx_align16(o + sizeof(Real) * 2 * max_bclass); }
     o = vx_align16(o + sizeof(ColPair) * max_col);
@@ -110,7 +111,8 @@ __device__ inline SmemTables<Real> carve_tables(unsigned char* p, int max_vclass
     t.red = (double*)(p + o);       o = vx_align16(o + sizeof(double) * 4 * 32);
     t.mbar = (unsigned long long*)(p + o);
     t.maxvel = (unsigned int*)(p + o + sizeof(unsigned long long));
-    o = vx_align16(o + sizeof(unsigned long long) + 2 * sizeof(unsigned int));
+    t.colflag = t.maxvel + 2;
+    o = vx_align16(o + sizeof(unsigned long long) + 4 * sizeof(unsigned int));
     t.sl = (ScaleSim*)(p + o);      o = vx_align16(o + sizeof(ScaleSim));
     t.bpair = nullptr; t.dnom_bc = nullptr;
     if (compact) {
@@ -323,7 +325,7 @@ __global__ void __launch_bounds__(NV / VPT, vx_min_ctas(NV, NV / VPT, FLUID || C
     bool col_overflow = false;
     if (COLLIDE && col_on) {
         for (int i = tid; i < n_col; i += T) S.pairs[i] = B.col_pairs[(size_t)robot * B.max_col + i];
-        if (tid == 0) { S.maxvel[0] = 0u; S.maxvel[1] = 0u; }
+        if (tid == 0) { S.maxvel[0] = 0u; S.maxvel[1] = 0u; S.colflag[0] = 0u; S.colflag[1] = 0u; }
         __syncthreads();
     }
 
@@ -357,18 +359,16 @@ __global__ void __launch_bounds__(NV / VPT, vx_min_ctas(NV, NV / VPT, FLUID || C
         const Real dt_inv = (s == 0) ? (Real)0 : dt_inv_run;   // dt == 0 during the very first bond pass (VX_Sim.cpp:373)
         Real* rec = (!COMPACT && k == nsteps - 1) ? rec_base : nullptr;
 
-        if (COLLIDE && col_on) {   // UpdateCollisions (VX_Sim.cpp:1729-1755): dt is still 0 in the very first step
+        if (COLLIDE && col_on && tid == 0) {
+            // UpdateCollisions (VX_Sim.cpp:1729-1755), the bookkeeping: one thread keeps MaxDispSinceLastBondUpdate in fp64 and posts
+            // its verdict; the CTA acts on it after the first axis barrier below (dt is still 0 in the very first step)
             const unsigned int mvb = S.maxvel[(k + 1) & 1];            // written by the previous step's voxel phase
             if (k > 0) max_vel = sqrt((double)__uint_as_float(mvb));
-            if (tid == 0) S.maxvel[k & 1] = 0u;                        // this step's slot; next read after two barriers
+            S.maxvel[k & 1] = 0u;                                      // this step's slot; next read after two barriers
             col_acc += fabs(max_vel * (s == 0 ? 0.0 : dt) / lat_dim);
-            if (!col_host && (col_acc > (col_h - 1.0) / 2 || col_first)) {
-                col_first = false;
-                C.scale_c = S.scale_c + cur * B.max_vclass;
-                n_col = col_rebuild<Real>(R, C, CT, (Real)col_h, (Real)lat_dim, S.pairs, B.max_col, (int*)S.red);
-                col_acc = 0.0;
-                if (n_col > B.max_col) { col_overflow = true; break; }
-            }
+            const bool rebuild = !col_host && (col_acc > (col_h - 1.0) / 2 || col_first);
+            if (rebuild) { col_first = false; col_acc = 0.0; }
+            S.colflag[k & 1] = rebuild ? 1u : 0u;
         }
         V3<Real> F[VPT], M[VPT];
         VoxStat st[VPT];
@@ -412,6 +412,11 @@ __global__ void __launch_bounds__(NV / VPT, vx_min_ctas(NV, NV / VPT, FLUID || C
 #pragma unroll
         for (int j = 0; j < VPT; j++) { P[j].w = -1; if (tid + j * T < n_vox) div |= bond_eval<Real, 1, COMPACT, FLUID>(R, C, tid + j * T, st[j], own[j], fl[j], dt_inv, F[j], M[j], rec, P[j]) ? 1 : 0; }
         mbar_wait(S.mbar, mpar); mpar ^= 1u;
+        if (COLLIDE && col_on && S.colflag[k & 1]) {   // rebuild the contact-bond list (positions are still those of the previous step)
+            C.scale_c = S.scale_c + cur * B.max_vclass;
+            n_col = col_rebuild<Real>(R, C, CT, (Real)col_h, (Real)lat_dim, S.pairs, B.max_col, (int*)S.red);
+            if (n_col > B.max_col) { col_overflow = true; break; }
+        }
 #pragma unroll
         for (int j = 0; j < VPT; j++) bond_push<Real>(R, P[j]);
         mbar_arrive_warp(S.mbar, (tid & 31) == 0);
