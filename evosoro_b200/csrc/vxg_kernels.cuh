@@ -72,6 +72,8 @@ template <typename Real> struct SmemTables {
     unsigned long long* mbar;   // split-phase barrier between the axis sub-phases
     unsigned int* maxvel;       // [2] max |Vel|^2 of a step as float bits (double-buffered by step parity)
     unsigned int* colflag;      // [2] thread 0's verdict for this step: rebuild the contact-bond list (by step parity)
+    double* colstate;           // [4] MaxDispSinceLastBondUpdate, SS.MaxVoxVel, CollisionHorizon, lattice pitch: thread 0's working set,
+                                //     kept out of every other thread's registers
     uint32_t* bpair;            // [max_bclass] voxel-class pair of each bond class (compact family)
     Real* dnom_bc;              // [2][max_bclass] rest-length deviation per bond class, double-buffered like dsc_c
     ScaleSim* sl;               // the robot's scale-law constants (read by the few threads that evaluate the law)
@@ -91,6 +93,7 @@ __host__ __device__ inline size_t tables_bytes(int max_vclass, int max_bclass, b
     o = vx_align16(o + sizeof(Real) * 3 * max_vclass);
     o = vx_align16(o + sizeof(double) * 4 * 32);
     o = vx_align16(o + sizeof(unsigned long long) + 4 * sizeof(unsigned int));
+    o = vx_align16(o + 4 * sizeof(double));
     o = vx_align16(o + sizeof(ScaleSim));
     if (compact) { o = vx_align16(o + sizeof(uint32_t) * max_bclass); o = vx_align16(o + sizeof(Real) * 2 * max_bclass); }
     o = vx_align16(o + sizeof(ColPair) * max_col);
@@ -113,6 +116,7 @@ __device__ inline SmemTables<Real> carve_tables(unsigned char* p, int max_vclass
     t.maxvel = (unsigned int*)(p + o + sizeof(unsigned long long));
     t.colflag = t.maxvel + 2;
     o = vx_align16(o + sizeof(unsigned long long) + 4 * sizeof(unsigned int));
+    t.colstate = (double*)(p + o);  o = vx_align16(o + 4 * sizeof(double));
     t.sl = (ScaleSim*)(p + o);      o = vx_align16(o + sizeof(ScaleSim));
     t.bpair = nullptr; t.dnom_bc = nullptr;
     if (compact) {
@@ -320,12 +324,13 @@ __global__ void __launch_bounds__(NV / VPT, vx_min_ctas(NV, NV / VPT, FLUID || C
     int n_col = col_on ? ctlp->n_col : 0;
     bool col_first = ctlp->col_first != 0;
     const bool col_host = ctlp->col_host != 0;
-    double col_acc = ctlp->col_acc, max_vel = ctlp->max_vel;
-    const double col_h = ctlp->col_horizon, lat_dim = ctlp->lattice_dim;
     bool col_overflow = false;
     if (COLLIDE && col_on) {
         for (int i = tid; i < n_col; i += T) S.pairs[i] = B.col_pairs[(size_t)robot * B.max_col + i];
-        if (tid == 0) { S.maxvel[0] = 0u; S.maxvel[1] = 0u; S.colflag[0] = 0u; S.colflag[1] = 0u; }
+        if (tid == 0) {
+            S.maxvel[0] = 0u; S.maxvel[1] = 0u; S.colflag[0] = 0u; S.colflag[1] = 0u;
+            S.colstate[0] = ctlp->col_acc; S.colstate[1] = ctlp->max_vel; S.colstate[2] = ctlp->col_horizon; S.colstate[3] = ctlp->lattice_dim;
+        }
         __syncthreads();
     }
 
@@ -363,11 +368,13 @@ __global__ void __launch_bounds__(NV / VPT, vx_min_ctas(NV, NV / VPT, FLUID || C
             // UpdateCollisions (VX_Sim.cpp:1729-1755), the bookkeeping: one thread keeps MaxDispSinceLastBondUpdate in fp64 and posts
             // its verdict; the CTA acts on it after the first axis barrier below (dt is still 0 in the very first step)
             const unsigned int mvb = S.maxvel[(k + 1) & 1];            // written by the previous step's voxel phase
+            double col_acc = S.colstate[0], max_vel = S.colstate[1];
             if (k > 0) max_vel = sqrt((double)__uint_as_float(mvb));
             S.maxvel[k & 1] = 0u;                                      // this step's slot; next read after two barriers
-            col_acc += fabs(max_vel * (s == 0 ? 0.0 : dt) / lat_dim);
-            const bool rebuild = !col_host && (col_acc > (col_h - 1.0) / 2 || col_first);
+            col_acc += fabs(max_vel * (s == 0 ? 0.0 : dt) / S.colstate[3]);
+            const bool rebuild = !col_host && (col_acc > (S.colstate[2] - 1.0) / 2 || col_first);
             if (rebuild) { col_first = false; col_acc = 0.0; }
+            S.colstate[0] = col_acc; S.colstate[1] = max_vel;
             S.colflag[k & 1] = rebuild ? 1u : 0u;
         }
         V3<Real> F[VPT], M[VPT];
@@ -414,7 +421,7 @@ __global__ void __launch_bounds__(NV / VPT, vx_min_ctas(NV, NV / VPT, FLUID || C
         mbar_wait(S.mbar, mpar); mpar ^= 1u;
         if (COLLIDE && col_on && S.colflag[k & 1]) {   // rebuild the contact-bond list (positions are still those of the previous step)
             C.scale_c = S.scale_c + cur * B.max_vclass;
-            n_col = col_rebuild<Real>(R, C, CT, (Real)col_h, (Real)lat_dim, S.pairs, B.max_col, (int*)S.red);
+            n_col = col_rebuild<Real>(R, C, CT, (Real)S.colstate[2], (Real)S.colstate[3], S.pairs, B.max_col, (int*)S.red);
             if (n_col > B.max_col) { col_overflow = true; break; }
         }
 #pragma unroll
@@ -462,12 +469,14 @@ __global__ void __launch_bounds__(NV / VPT, vx_min_ctas(NV, NV / VPT, FLUID || C
     if (COLLIDE && col_on) {
         const int nc = n_col < B.max_col ? n_col : B.max_col;
         for (int i = tid; i < nc; i += T) B.col_pairs[(size_t)robot * B.max_col + i] = S.pairs[i];
-        if (done > 0) max_vel = sqrt((double)__uint_as_float(S.maxvel[(done - 1) & 1]));
     }
     if (tid == 0) {
         ctlp->cur_time = t;
         ctlp->step = step0 + done;
-        if (COLLIDE && col_on) { ctlp->n_col = n_col < B.max_col ? n_col : B.max_col; ctlp->col_first = col_first ? 1 : 0; ctlp->col_acc = col_acc; ctlp->max_vel = max_vel; }
+        if (COLLIDE && col_on) {
+            ctlp->n_col = n_col < B.max_col ? n_col : B.max_col; ctlp->col_first = col_first ? 1 : 0; ctlp->col_acc = S.colstate[0];
+            ctlp->max_vel = done > 0 ? sqrt((double)__uint_as_float(S.maxvel[(done - 1) & 1])) : S.colstate[1];
+        }
         unsigned int st2 = status0;
         if (col_overflow) st2 |= VXG_ST_COL_OVERFLOW_ | VXG_ST_DIVERGED_;
         if (diverged) st2 |= VXG_ST_DIVERGED_;
