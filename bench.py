@@ -314,8 +314,9 @@ def gpu_arm(args):
     stride = 64
     while stride < eb.limits.max_vox:
         stride *= 2
-    if 128 < eb.limits.max_vox <= 224:
-        stride = 224   # stride_for(), csrc/vx_robot.cuh
+    for lo, hi in ((128, 224), (256, 352), (512, 736)):   # stride_for(), csrc/vx_robot.cuh
+        if lo < eb.limits.max_vox <= hi:
+            stride = hi
     d2h = R * stride * 3 * 8   # the position planes of every blob at the device stride (the per-robot control blocks, ~0.3 KB each, not counted)
     if not np.isfinite(pos).all():
         raise SystemExit("bench.py: non-finite positions from the e2e path")

@@ -75,9 +75,12 @@ VX_HD constexpr size_t vx_align16(size_t x) { return (x + 15) & ~(size_t)15; }
 VX_HD constexpr size_t vx_align32(size_t x) { return (x + 31) & ~(size_t)31; }
 
 // voxel stride used for a robot of up to max_vox voxels: the kernels are instantiated for these strides
-// (powers of two, plus 224 = 7 warps for evosoro's default 6^3 workspace: four such robots share an SM instead of three)
+// (powers of two, plus 224 = 7 warps for evosoro's default 6^3 workspace -- four such robots share an SM instead of three --
+// and 352 / 736 so that 7^3 and 9^3 robots do not pay for 512 / 1024 voxel slots)
 inline int stride_for(int max_vox) {
     if (max_vox > 128 && max_vox <= 224) return 224;
+    if (max_vox > 256 && max_vox <= 352) return 352;
+    if (max_vox > 512 && max_vox <= 736) return 736;
     int nv = 64;
     while (nv < max_vox) nv *= 2;
     return nv;

@@ -223,8 +223,8 @@ __device__ __noinline__ int col_rebuild(const RobotView<Real>& R, const RobotCon
 // self-collision variants need more registers and room: 1).  Smaller robots: 768 resident threads, i.e. 80 registers -- what one voxel per thread needs without spilling.
 __host__ __device__ constexpr int vx_min_ctas(int nv, int threads, bool extras, bool fp64) {   // extras: fluid / self-collision variants
     return fp64 ? 1                                        // the logic-parity mode needs its registers, not occupancy
-         : nv >= 1024 ? 1
-         : nv >= 512 ? (extras ? 1 : VX_CTAS_512)
+         : nv > 512 ? 1                                    // one robot per SM (shared memory)
+         : nv == 512 ? (extras ? 1 : VX_CTAS_512)
          : (threads == 224 && !extras) ? 4                 // 4 x 224 threads: 72 registers
          : 768 / threads;
 }

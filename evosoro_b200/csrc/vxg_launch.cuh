@@ -32,7 +32,9 @@ inline cudaError_t launch_by_stride(const BatchDev<Real>& B, const LaunchCfg& c)
         case 128: return launch_one<Real, 128, 1, SMEM, COMPACT, FLUID, COLLIDE>(B, c);
         case 224: return launch_one<Real, 224, 1, SMEM, COMPACT, FLUID, COLLIDE>(B, c);
         case 256: return launch_one<Real, 256, 1, SMEM, COMPACT, FLUID, COLLIDE>(B, c);
+        case 352: return launch_one<Real, 352, 1, SMEM, COMPACT, FLUID, COLLIDE>(B, c);
         case 512: return launch_one<Real, 512, 1, SMEM, COMPACT, FLUID, COLLIDE>(B, c);
+        case 736: return launch_one<Real, 736, 1, SMEM, COMPACT, FLUID, COLLIDE>(B, c);
         case 1024:
             if constexpr (COMPACT && SMEM && !FLUID && !COLLIDE && sizeof(Real) == 4) { if (c.vpt == 1) return launch_one<Real, 1024, 1, true, true, false, false>(B, c); }
             return launch_one<Real, 1024, 2, SMEM, COMPACT, FLUID, COLLIDE>(B, c);

@@ -251,6 +251,24 @@ def test_robots_outside_the_production_family_run_the_wide_one():
     b.close()
 
 
+@pytest.mark.parametrize("n,threads", [(7, 352), (9, 736)])
+def test_strides_between_the_powers_of_two(n, threads):
+    """7^3 and 9^3 robots run with 352 / 736 voxel slots (not 512 / 1024): same results as the oracle, and a batch of mixed
+    seeds stays independent."""
+    sim = vxa.SimParams(init_cm_time=0.01, stop_condition_value=0.2)
+    robots = [engine.Model(text=vxa.vxa_text(vxa.dense_lattice(n, 80 + s), sim=sim)).robot for s in range(3)]
+    b = engine.Batch(robots + robots[:1])
+    assert b.kernel_config()["threads"] == threads
+    b.step(250)
+    assert not b.sync().any()
+    for r in (0, 2):
+        o = oracle_lib.OracleSim(robots[r])
+        o.step(250)
+        assert common.max_abs(b.download(r).pos, o.state().pos) <= 1e-5 * LAT
+    assert np.array_equal(b.download(0).pos, b.download(3).pos)
+    b.close()
+
+
 def test_step_chunking_is_exact():
     """K steps in one launch == K single-step launches (state round-trips through HBM exactly)."""
     rob = engine.Model(text=vxa.vxa_text(vxa.dense_lattice(4, 11))).robot
