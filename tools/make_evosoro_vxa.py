@@ -51,33 +51,15 @@ def main(out_dir, pop_size):
     from evosoro.tools.utils import count_occurrences, make_material_tree
     from evosoro.tools.read_write_voxelyze import write_voxelyze_file
 
-    ind_size = (6, 6, 6)                        # examples/basic.py:60-63, :80-82
-    random.seed(1); np.random.seed(1)
-
-    class MyGenotype(Genotype):                 # examples/basic.py:85-113
-        def __init__(self):
-            Genotype.__init__(self, orig_size_xyz=ind_size)
-            self.add_network(CPPN(output_node_names=["shape", "muscleOrTissue", "muscleType", "tissueType"]))
-            m = self.to_phenotype_mapping
-            m.add_map(name="material", tag="<Data>", func=make_material_tree,
-                      dependency_order=["shape", "muscleOrTissue", "muscleType", "tissueType"], output_type=int)
-            m.add_output_dependency(name="shape", dependency_name=None, requirement=None, material_if_true=None, material_if_false="0")
-            m.add_output_dependency(name="muscleOrTissue", dependency_name="shape", requirement=True, material_if_true=None, material_if_false=None)
-            m.add_output_dependency(name="tissueType", dependency_name="muscleOrTissue", requirement=False, material_if_true="1", material_if_false="2")
-            m.add_output_dependency(name="muscleType", dependency_name="muscleOrTissue", requirement=True, material_if_true="3", material_if_false="4")
-
-    class MyPhenotype(Phenotype):               # examples/basic.py:117-132
-        def is_valid(self, min_percent_full=0.3, min_percent_muscle=0.1):
-            for name, details in self.genotype.to_phenotype_mapping.items():
-                if np.isnan(details["state"]).any():
-                    return False
-                if name == "material":
-                    state = details["state"]
-                    if np.sum(state > 0) < np.prod(self.genotype.orig_size_xyz) * min_percent_full:
-                        return False
-                    if count_occurrences(state, [3, 4]) < np.prod(self.genotype.orig_size_xyz) * min_percent_muscle:
-                        return False
-            return True
+    # The genotype -> phenotype mapping and the validity rule of the experiment are taken from evosoro's own example at run time
+    # (the class definitions of examples/basic.py, executed here; the rest of that script launches the GA and is not run).
+    src = open(os.path.join(REF, "examples", "basic.py")).read()
+    block = src[src.index("class MyGenotype(Genotype):"):src.index("# Setting up the simulation object")]
+    ns = dict(Genotype=Genotype, Phenotype=Phenotype, CPPN=CPPN, make_material_tree=make_material_tree, count_occurrences=count_occurrences,
+              np=np, IND_SIZE=(6, 6, 6))
+    exec(block, ns)
+    MyGenotype, MyPhenotype = ns["MyGenotype"], ns["MyPhenotype"]
+    random.seed(1); np.random.seed(1)           # SEED = 1, examples/basic.py:78-80
 
     sim = Sim(dt_frac=0.9, simulation_time=5, fitness_eval_init_time=1)     # examples/basic.py:135
     env = Env(sticky_floor=0, time_between_traces=0)                        # :138
