@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define VXG_ABI_VERSION 3
+#define VXG_ABI_VERSION 3   /* 3: development fields in vxg_vox_class / vxg_sim_params, vxg_robot_state.vox_strain, vxg_robot_stats.mesh_volume */
 
 /* ---- return codes ------------------------------------------------------------------------------ */
 enum {
