@@ -5,15 +5,19 @@
 //
 // Every file is imported (LoadVXAFile + Import), the whole set is simulated as ONE batch on the GPU until
 // each robot's stop condition, and each robot's <FitnessFileName> is written with the reference's tag set
-// (CVX_SimGA::WriteResultFile).  Exit code: 1 = completed, 0 = could not complete -- the reference's own
-// convention (main.cpp:28,57,132) that evosoro's subprocess call relies on.  There is no CPU path: a file the
-// kernels cannot simulate (or a missing GPU) is an error (exit 0 with a message), never a silent fallback.
+// (CVX_SimGA::WriteResultFile).  Exit code: 1 = every robot completed and wrote its result, 0 = at least one did not -- the
+// reference's own convention (main.cpp:28,57,132).  Failures are per robot: an unreadable / unsupported file or a diverged
+// simulation costs that robot its result file (which is how evosoro recognises it, evaluation.py:107-119, 213-215) and nothing
+// else.  There is no CPU path: a file the kernels cannot simulate (or a missing GPU) is an error with a message, never a silent
+// fallback.
 #include <dirent.h>
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/vxhost.h"
@@ -42,34 +46,68 @@ int main(int argc, char** argv) {
     }
     if (files.empty()) { printf("\nInput file required. Quitting.\n"); return 0; }
 
-    const int n = (int)files.size();
+    // Import every file on the host cores (LoadVXAFile + Import + the step plan are independent per file).  A file that cannot
+    // be read or that enables something the kernels do not implement is dropped WITH a message and the others still run: the
+    // reference runs one process per robot (evaluation.py:89-90), so one bad individual never costs its batch-mates their result.
+    const int n_files = (int)files.size();
+    std::vector<vxh_model*> loaded(n_files, nullptr);
+    std::vector<int64_t> f_total(n_files), f_latch(n_files), f_eol(n_files);
+    std::vector<std::string> why(n_files);
+    {
+        int nt = (int)std::thread::hardware_concurrency();
+        if (const char* e = getenv("VXG_HOST_THREADS")) nt = atoi(e);
+        nt = std::max(1, std::min(nt, std::min(n_files, 64)));
+        std::atomic<int> next(0);
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++)
+            th.emplace_back([&]() {
+                for (int r; (r = next.fetch_add(1)) < n_files;) {
+                    int rc = vxh_load_vxa_file(files[r].c_str(), lw ? VXH_VARIANT_LAND_WATER : VXH_VARIANT_VOXCAD, ignore_col ? 1 : 0, &loaded[r]);
+                    if (!rc) rc = vxh_step_plan_ex(loaded[r], &f_total[r], &f_latch[r], &f_eol[r], nullptr);
+                    if (rc) { why[r] = vxh_last_error(); if (loaded[r]) { vxh_free(loaded[r]); loaded[r] = nullptr; } }
+                }
+            });
+        for (auto& x : th) x.join();
+    }
+    int n_failed = 0;
+    std::vector<int> src;   // batch slot -> index into files
+    for (int r = 0; r < n_files; r++) {
+        if (loaded[r]) { src.push_back(r); continue; }
+        n_failed++;
+        fprintf(stderr, "\nProblem importing VXA file %s: %s. Skipped\n", files[r].c_str(), why[r].c_str());
+    }
+    const int n = (int)src.size();
+    if (n == 0) { fprintf(stderr, "voxelyze: no input could be imported. Quitting\n"); return 0; }
     std::vector<vxh_model*> models(n, nullptr);
     std::vector<vxg_robot_desc> descs(n);
     std::vector<int64_t> total(n), latch(n), eol(n);
     vxg_limits lim; memset(&lim, 0, sizeof lim);
     lim.max_vox = lim.max_vclass = lim.max_bclass = 1; lim.precision = VXG_PREC_F32;
     int64_t max_total = 0;
+    int col_cap = 0;
     for (int r = 0; r < n; r++) {
-        int rc = vxh_load_vxa_file(files[r].c_str(), lw ? VXH_VARIANT_LAND_WATER : VXH_VARIANT_VOXCAD, ignore_col ? 1 : 0, &models[r]);
-        if (rc) {
-            if (print_scrn || rc > 0) fprintf(stderr, "\nProblem importing VXA file %s: %s. Quitting\n", files[r].c_str(), vxh_last_error());
-            return 0;
-        }
+        models[r] = loaded[src[r]]; total[r] = f_total[src[r]]; latch[r] = f_latch[src[r]]; eol[r] = f_eol[src[r]];
         descs[r] = *vxh_desc(models[r]);
-        rc = vxh_step_plan_ex(models[r], &total[r], &latch[r], &eol[r], nullptr);
-        if (rc) { fprintf(stderr, "voxelyze: %s: %s\n", files[r].c_str(), vxh_last_error()); return 0; }
         lim.max_vox = std::max(lim.max_vox, descs[r].n_vox);
         lim.max_vclass = std::max(lim.max_vclass, descs[r].n_vclass);
         lim.max_bclass = std::max(lim.max_bclass, descs[r].n_bclass);
-        if (descs[r].sim.flags & VXG_F_COLLISIONS) lim.max_col_pairs = 512;   // contact-bond list capacity (overflow is reported, never truncated)
+        // contact-bond list capacity, sized from the robot (a folded robot holds a few candidate pairs per surface voxel;
+        // overflow is reported per robot, never truncated)
+        if (descs[r].sim.flags & VXG_F_COLLISIONS) col_cap = std::max(col_cap, std::min(16384, std::max(512, 4 * descs[r].n_vox)));
         // the land/water result file reports the volume of the deformed surface mesh at the end: every robot of that fork needs the
         // mesh tables, not only those in a fluid environment
         if (descs[r].sim.flags & (VXG_F_FLUID | VXG_F_LW_SCALE)) lim.max_mesh_verts = std::max(lim.max_mesh_verts, vxg_mesh_vertex_count(&descs[r]));
         max_total = std::max(max_total, total[r]);
-        if (print_scrn) printf("Imported %s: %d voxels, %d bonds, %lld steps\n", files[r].c_str(), descs[r].n_vox, descs[r].n_bond, (long long)total[r]);
+        if (print_scrn) printf("Imported %s: %d voxels, %d bonds, %lld steps\n", files[src[r]].c_str(), descs[r].n_vox, descs[r].n_bond, (long long)total[r]);
     }
     vxg_batch* b = nullptr;
-    int rc = vxg_create(&b, device, n, &lim);
+    int rc;
+    for (;;) {   // the list is shared-memory resident next to the robot: halve the capacity until both fit
+        lim.max_col_pairs = col_cap;
+        rc = vxg_create(&b, device, n, &lim);
+        if (rc != VXG_UNSUPPORTED_SIZE || col_cap <= 512) break;
+        col_cap /= 2;
+    }
     for (int r = 0; r < n && !rc; r++) rc = vxg_upload(b, r, &descs[r]);
     if (!rc) rc = vxg_set_step_budget(b, total.data(), latch.data());
     if (!rc) rc = vxg_set_eol_step(b, eol.data());
@@ -83,17 +121,24 @@ int main(int argc, char** argv) {
     std::vector<vxg_robot_stats> stats(n);
     if (!rc) rc = vxg_reduce_stats(b, stats.data());
     if (rc) { fprintf(stderr, "voxelyze: %s\n", vxg_last_error()); return 0; }
-    int ok = 1;
     for (int r = 0; r < n; r++) {
         vxh_info info; vxh_get_info(models[r], &info);
-        if (status[r] & VXG_ST_COL_OVERFLOW) { fprintf(stderr, "%s: more than %d self-collision contact bonds\n", files[r].c_str(), lim.max_col_pairs); ok = 0; }
-        else if (status[r] & VXG_ST_DIVERGED) { fprintf(stderr, "%s: Simulation Diverged. Please reduce forces or accelerations.\n", files[r].c_str()); }
+        const char* file = files[src[r]].c_str();
+        // A robot whose simulation diverged never reaches its stop condition in the reference (TimeStep keeps returning false,
+        // VX_Sim.cpp:1147-1150, so CurTime stands still and main.cpp:89 never leaves its loop): no result file is ever written and
+        // evosoro leaves the worst fitness on that individual (evaluation.py:107-110, 213-215).  Same here, without the hang:
+        // no file (a stale one is removed), a message, and the others are unaffected.
+        const bool failed = (status[r] & (VXG_ST_COL_OVERFLOW | VXG_ST_DIVERGED)) != 0;
+        if (status[r] & VXG_ST_COL_OVERFLOW) fprintf(stderr, "%s: more than %d self-collision contact bonds. No result written\n", file, lim.max_col_pairs);
+        else if (status[r] & VXG_ST_DIVERGED) fprintf(stderr, "%s: Simulation Diverged. Please reduce forces or accelerations. No result written\n", file);
         if (print_scrn) printf("Ended at: %g\n", stats[r].time);
-        if (info.fitness_file_name[0]) {   // SaveResultFile(FitnessFileName), main.cpp:130
-            if (vxh_format_result(models[r], &stats[r], nullptr, 0, info.fitness_file_name) < 0) { fprintf(stderr, "voxelyze: %s\n", vxh_last_error()); ok = 0; }
+        if (failed) { n_failed++; if (info.fitness_file_name[0]) remove(info.fitness_file_name); }
+        else if (info.fitness_file_name[0]) {   // SaveResultFile(FitnessFileName), main.cpp:130
+            if (vxh_format_result(models[r], &stats[r], nullptr, 0, info.fitness_file_name) < 0) { fprintf(stderr, "voxelyze: %s\n", vxh_last_error()); n_failed++; }
         }
         vxh_free(models[r]);
     }
     vxg_destroy(b);
-    return ok ? 1 : 0;
+    if (n_failed) fprintf(stderr, "voxelyze: %d of %d robots did not produce a result\n", n_failed, n_files);
+    return n_failed ? 0 : 1;
 }

@@ -406,11 +406,24 @@ static int flush(vxg_batch* b) {
         CK(cudaMemcpyAsync(b->d_sk, b->h_sk, nr * mv * sizeof(ScaleK), cudaMemcpyHostToDevice, b->stream));
         CK(cudaMemcpyAsync(b->d_ext_disp, b->h_ext_disp, nr * mv * 3 * b->rs(), cudaMemcpyHostToDevice, b->stream));
         CK(cudaMemcpyAsync(b->d_ext_tdisp, b->h_ext_tdisp, nr * mv * 3 * b->rs(), cudaMemcpyHostToDevice, b->stream));
-        if (b->lim.max_col_pairs > 0) {
-            CK(cudaMemcpyAsync(b->d_col_pairs, b->h_col_pairs, nr * (size_t)b->lim.max_col_pairs * sizeof(ColPair), cudaMemcpyHostToDevice, b->stream));
-            CK(cudaMemcpyAsync(b->d_col_surf, b->h_col_surf, nr * nv * sizeof(int16_t), cudaMemcpyHostToDevice, b->stream));
-            CK(cudaMemcpyAsync(b->d_col_lat4, b->h_col_lat4, nr * nv * 4, cudaMemcpyHostToDevice, b->stream));
-            CK(cudaMemcpyAsync(b->d_col_near, b->h_col_near, nr * nv * sizeof(unsigned long long), cudaMemcpyHostToDevice, b->stream));
+        if (b->lim.max_col_pairs > 0 && b->dirty) {
+            // Contact-bond lists are device-managed state (the rebuild writes them, only vxg_set_collision_pairs pulls them): only the
+            // rows of the slots the host changed travel, the other robots' live lists stay as the device left them.
+            const size_t mc = (size_t)b->lim.max_col_pairs;
+            size_t n_dirty = 0;
+            for (size_t r = 0; r < nr; r++) n_dirty += b->slot_dirty[r] ? 1 : 0;
+            if (n_dirty == nr) {   // whole population (the GA's evaluate_all): four bulk copies
+                CK(cudaMemcpyAsync(b->d_col_pairs, b->h_col_pairs, nr * mc * sizeof(ColPair), cudaMemcpyHostToDevice, b->stream));
+                CK(cudaMemcpyAsync(b->d_col_surf, b->h_col_surf, nr * nv * sizeof(int16_t), cudaMemcpyHostToDevice, b->stream));
+                CK(cudaMemcpyAsync(b->d_col_lat4, b->h_col_lat4, nr * nv * 4, cudaMemcpyHostToDevice, b->stream));
+                CK(cudaMemcpyAsync(b->d_col_near, b->h_col_near, nr * nv * sizeof(unsigned long long), cudaMemcpyHostToDevice, b->stream));
+            } else for (size_t r = 0; r < nr; r++) {
+                if (!b->slot_dirty[r]) continue;
+                CK(cudaMemcpyAsync(b->d_col_pairs + r * mc, b->h_col_pairs + r * mc, mc * sizeof(ColPair), cudaMemcpyHostToDevice, b->stream));
+                CK(cudaMemcpyAsync(b->d_col_surf + r * nv, b->h_col_surf + r * nv, nv * sizeof(int16_t), cudaMemcpyHostToDevice, b->stream));
+                CK(cudaMemcpyAsync(b->d_col_lat4 + r * nv * 4, b->h_col_lat4 + r * nv * 4, nv * 4, cudaMemcpyHostToDevice, b->stream));
+                CK(cudaMemcpyAsync(b->d_col_near + r * nv, b->h_col_near + r * nv, nv * sizeof(unsigned long long), cudaMemcpyHostToDevice, b->stream));
+            }
         }
     }
     if (b->ctl_dirty) CK(cudaMemcpyAsync(b->d_ctl, b->h_ctl, nr * sizeof(RobotCtl), cudaMemcpyHostToDevice, b->stream));   // the setters pulled it first
@@ -423,17 +436,14 @@ static int flush(vxg_batch* b) {
 static int pull(vxg_batch* b, bool blobs, int robot) {
     CK(cudaSetDevice(b->device));
     size_t nr = (size_t)b->n_robots, mv = (size_t)b->lim.max_vclass;
-    if (!b->dirty) {
-        CK(cudaMemcpyAsync(b->h_ctl, b->d_ctl, nr * sizeof(RobotCtl), cudaMemcpyDeviceToHost, b->stream));
-        if (blobs) {
-            size_t r0 = robot < 0 ? 0 : (size_t)robot, cnt = robot < 0 ? nr : 1;
-            CK(cudaMemcpyAsync(b->h_blobs + r0 * b->L.total_bytes, b->d_blobs + r0 * b->L.total_bytes, cnt * b->L.total_bytes, cudaMemcpyDeviceToHost, b->stream));
-            for (size_t r = r0; r < r0 + cnt; r++) b->reset_image[r] = 0;
-            CK(cudaMemcpyAsync(b->h_scale_c + r0 * mv, b->d_scale_c + r0 * mv, cnt * mv * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
-        }
-    } else if (blobs) {   // nothing ran since the host wrote the mirrors: they are the current state, make them whole before they are read
+    // pending host-side changes go down first: dirtiness is per slot, so the device may still hold the newer state of the others
+    if (b->dirty) { int rc = flush(b); if (rc) return rc; }
+    CK(cudaMemcpyAsync(b->h_ctl, b->d_ctl, nr * sizeof(RobotCtl), cudaMemcpyDeviceToHost, b->stream));
+    if (blobs) {
         size_t r0 = robot < 0 ? 0 : (size_t)robot, cnt = robot < 0 ? nr : 1;
-        for (size_t r = r0; r < r0 + cnt; r++) if (b->uploaded[r]) complete_mirror(b, r);
+        CK(cudaMemcpyAsync(b->h_blobs + r0 * b->L.total_bytes, b->d_blobs + r0 * b->L.total_bytes, cnt * b->L.total_bytes, cudaMemcpyDeviceToHost, b->stream));
+        for (size_t r = r0; r < r0 + cnt; r++) b->reset_image[r] = 0;
+        CK(cudaMemcpyAsync(b->h_scale_c + r0 * mv, b->d_scale_c + r0 * mv, cnt * mv * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
     }
     CK(cudaStreamSynchronize(b->stream));
     return VXG_OK;
@@ -626,11 +636,15 @@ template <typename Real> static void pack_state(vxg_batch* b, int robot, const v
 extern "C" int vxg_upload_state(vxg_batch* b, int robot, const vxg_robot_state* in, double cur_time, int64_t cur_step) {
     if (!b || !in) return fail(VXG_ERR_ARG, "vxg_upload_state: null argument");
     if (robot < 0 || robot >= b->n_robots || !b->uploaded[robot]) return fail(VXG_ERR_ARG, "vxg_upload_state: robot %d not present", robot);
-    int rc = pull(b, true, -1);   // whole batch: the next flush re-uploads every blob
+    int rc = pull(b, true, robot);   // this slot's mirror becomes current; the others keep running from their device state
     if (rc) return rc;
+    if (b->lim.max_col_pairs > 0) {   // its live contact-bond list travels back with it
+        const size_t mc = (size_t)b->lim.max_col_pairs;
+        CK(cudaMemcpy(b->h_col_pairs + (size_t)robot * mc, b->d_col_pairs + (size_t)robot * mc, mc * sizeof(ColPair), cudaMemcpyDeviceToHost));
+    }
     if (b->prec == VXG_PREC_F64) pack_state<double>(b, robot, in); else pack_state<float>(b, robot, in);
     b->reset_image[robot] = 0;
-    std::fill(b->slot_dirty.begin(), b->slot_dirty.end(), 1);   // every mirror is current (pulled above) and travels again
+    b->slot_dirty[robot] = 1;
     b->h_ctl[robot].cur_time = cur_time;
     b->h_ctl[robot].step = cur_step;
     b->dirty = true;
@@ -658,9 +672,8 @@ extern "C" int vxg_set_collision_pairs(vxg_batch* b, int robot, int n_pairs, con
     if (b->lim.max_col_pairs <= 0) return fail(VXG_UNSUPPORTED_SIZE, "vxg_set_collision_pairs: the batch was created with limits.max_col_pairs = 0");
     if (n_pairs > b->lim.max_col_pairs) return fail(VXG_UNSUPPORTED_SIZE, "vxg_set_collision_pairs: %d pairs > max_col_pairs %d", n_pairs, b->lim.max_col_pairs);
     if (n_pairs > 0 && (!v1 || !v2)) return fail(VXG_ERR_ARG, "vxg_set_collision_pairs: null pair arrays");
-    int rc = pull(b, true, -1);   // keep the device state; the whole batch is re-uploaded by the next flush
+    int rc = pull(b, true, robot);   // keep the device state of this slot; the others are not touched
     if (rc) return rc;
-    if (!b->dirty) CK(cudaMemcpy(b->h_col_pairs, b->d_col_pairs, (size_t)b->n_robots * b->lim.max_col_pairs * sizeof(ColPair), cudaMemcpyDeviceToHost));
     RobotCtl& c = b->h_ctl[robot];
     if (n_pairs < 0) { c.col_host = 0; c.col_first = 1; c.n_col = 0; }
     else {

@@ -71,6 +71,7 @@ template <typename Real> struct SmemTables {
     double* red;      // [4][32] reduction scratch
     unsigned long long* mbar;   // split-phase barrier between the axis sub-phases
     unsigned int* maxvel;       // [2] max |Vel|^2 of a step as float bits (double-buffered by step parity)
+    unsigned int* arrcnt;       // warps that have arrived at the current axis barrier (VX_BAR_MODE 2)
     unsigned int* colflag;      // [2] thread 0's verdict for this step: rebuild the contact-bond list (by step parity)
     double* colstate;           // [4] MaxDispSinceLastBondUpdate, SS.MaxVoxVel, CollisionHorizon, lattice pitch: thread 0's working set,
                                 //     kept out of every other thread's registers
@@ -92,7 +93,7 @@ __host__ __device__ inline size_t tables_bytes(int max_vclass, int max_bclass, b
     o = vx_align16(o + sizeof(Real) * 3 * max_vclass);
     o = vx_align16(o + sizeof(Real) * 3 * max_vclass);
     o = vx_align16(o + sizeof(double) * 4 * 32);
-    o = vx_align16(o + sizeof(unsigned long long) + 4 * sizeof(unsigned int));
+    o = vx_align16(o + sizeof(unsigned long long) + 6 * sizeof(unsigned int));
     o = vx_align16(o + 4 * sizeof(double));
     o = vx_align16(o + sizeof(ScaleSim));
     if (compact) { o = vx_align16(o + sizeof(uint32_t) * max_bclass); o = vx_align16(o + sizeof(Real) * 2 * max_bclass); }
@@ -115,7 +116,8 @@ __device__ inline SmemTables<Real> carve_tables(unsigned char* p, int max_vclass
     t.mbar = (unsigned long long*)(p + o);
     t.maxvel = (unsigned int*)(p + o + sizeof(unsigned long long));
     t.colflag = t.maxvel + 2;
-    o = vx_align16(o + sizeof(unsigned long long) + 4 * sizeof(unsigned int));
+    t.arrcnt = t.maxvel + 4;
+    o = vx_align16(o + sizeof(unsigned long long) + 6 * sizeof(unsigned int));
     t.colstate = (double*)(p + o);  o = vx_align16(o + 4 * sizeof(double));
     t.sl = (ScaleSim*)(p + o);      o = vx_align16(o + sizeof(ScaleSim));
     t.bpair = nullptr; t.dnom_bc = nullptr;
@@ -162,6 +164,41 @@ __device__ inline void mbar_wait(unsigned long long* bar, unsigned int parity) {
         "bra VX_MBAR_WAIT;\n"
         "VX_MBAR_DONE:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+}
+
+// VX_BAR_MODE selects how the axis sub-phases are ordered (tuning switch; 0 = split-phase mbarrier with one arrival per warp):
+//   1 : plain CTA barrier at the wait point (hardware BAR.SYNC, no split phase)
+//   2 : split phase with ONE mbarrier arrival per phase: the warps count themselves in on a shared-memory counter and the last
+//       one arrives, so that sleeping waiters are woken once per phase instead of once per arriving warp
+#ifndef VX_BAR_MODE
+#define VX_BAR_MODE 0
+#endif
+__device__ inline void axis_arrive(unsigned long long* bar, unsigned int* cnt, int nwarps, bool lane0) {
+#if VX_BAR_MODE == 1
+    (void)bar; (void)cnt; (void)nwarps; (void)lane0;
+#elif VX_BAR_MODE == 2
+    __syncwarp();
+    if (lane0) {
+        __threadfence_block();
+        const unsigned int old = atomicAdd(cnt, 1u);
+        if (old == (unsigned int)(nwarps - 1)) {
+            *cnt = 0u;
+            __threadfence_block();
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+        }
+    }
+#else
+    (void)cnt; (void)nwarps;
+    mbar_arrive_warp(bar, lane0);
+#endif
+}
+__device__ inline void axis_wait(unsigned long long* bar, unsigned int parity) {
+#if VX_BAR_MODE == 1
+    (void)bar; (void)parity;
+    __syncthreads();
+#else
+    mbar_wait(bar, parity);
+#endif
 }
 
 __device__ inline double warp_max(double x) {
@@ -275,7 +312,7 @@ __global__ void __launch_bounds__(NV / VPT, vx_min_ctas(NV, NV / VPT, FLUID || C
         S.ext_disp[i] = B.ext_disp[(size_t)robot * B.max_vclass * 3 + i];
         S.ext_tdisp[i] = B.ext_tdisp[(size_t)robot * B.max_vclass * 3 + i];
     }
-    if (tid == 0) mbar_init(S.mbar, T / 32);
+    if (tid == 0) { mbar_init(S.mbar, VX_BAR_MODE == 2 ? 1 : T / 32); *S.arrcnt = 0u; }
     __syncthreads();
     for (int i = tid; i < n_vc; i += T) S.dsc_c[i] = (Real)(S.scale_c[i] - S.sk[i].nom_size);
     if (COMPACT) for (int i = tid; i < n_bc; i += T) S.bpair[i] = B.bpair[(size_t)robot * B.max_bclass + i];
@@ -415,10 +452,10 @@ __global__ void __launch_bounds__(NV / VPT, vx_min_ctas(NV, NV / VPT, FLUID || C
         for (int j = 0; j < VPT; j++) { P[j].w = -1; if (tid + j * T < n_vox) div |= bond_eval<Real, 0, COMPACT, FLUID>(R, C, tid + j * T, st[j], own[j], fl[j], dt_inv, F[j], M[j], rec, P[j]) ? 1 : 0; }
 #pragma unroll
         for (int j = 0; j < VPT; j++) bond_push<Real>(R, P[j]);
-        mbar_arrive_warp(S.mbar, (tid & 31) == 0);
+        axis_arrive(S.mbar, S.arrcnt, T / 32, (tid & 31) == 0);
 #pragma unroll
         for (int j = 0; j < VPT; j++) { P[j].w = -1; if (tid + j * T < n_vox) div |= bond_eval<Real, 1, COMPACT, FLUID>(R, C, tid + j * T, st[j], own[j], fl[j], dt_inv, F[j], M[j], rec, P[j]) ? 1 : 0; }
-        mbar_wait(S.mbar, mpar); mpar ^= 1u;
+        axis_wait(S.mbar, mpar); mpar ^= 1u;
         if (COLLIDE && col_on && S.colflag[k & 1]) {   // rebuild the contact-bond list (positions are still those of the previous step)
             C.scale_c = S.scale_c + cur * B.max_vclass;
             n_col = col_rebuild<Real>(R, C, CT, (Real)S.colstate[2], (Real)S.colstate[3], S.pairs, B.max_col, (int*)S.red);
@@ -426,10 +463,10 @@ __global__ void __launch_bounds__(NV / VPT, vx_min_ctas(NV, NV / VPT, FLUID || C
         }
 #pragma unroll
         for (int j = 0; j < VPT; j++) bond_push<Real>(R, P[j]);
-        mbar_arrive_warp(S.mbar, (tid & 31) == 0);
+        axis_arrive(S.mbar, S.arrcnt, T / 32, (tid & 31) == 0);
 #pragma unroll
         for (int j = 0; j < VPT; j++) { P[j].w = -1; if (tid + j * T < n_vox) div |= bond_eval<Real, 2, COMPACT, FLUID>(R, C, tid + j * T, st[j], own[j], fl[j], dt_inv, F[j], M[j], rec, P[j]) ? 1 : 0; }
-        mbar_wait(S.mbar, mpar); mpar ^= 1u;
+        axis_wait(S.mbar, mpar); mpar ^= 1u;
 #pragma unroll
         for (int j = 0; j < VPT; j++) bond_push<Real>(R, P[j]);
         if (COLLIDE && col_on && n_col > 0) {   // contact bonds: positions are still those of the previous step here

@@ -193,7 +193,7 @@ struct Parsed {
     // <Environment>  (VX_Environment.cpp:123-293)
     std::vector<Region> bcs;
     bool grav_on = false, floor_on = false, temp_on = false, vary_temp = false, sticky = false, falling_prohibited = false;
-    bool limited_floor = false, sources = false, fluid = false, needle = false, norm_by_vol = false, save_traces = false;
+    bool limited_floor = false, sources = false, fluid = false, fluid_in_voxcad = false, needle = false, norm_by_vol = false, save_traces = false;
     double grav_acc = -9.81, temp_base = 25, temp_amplitude = 0, temp_period = 0.1, growth_amp = 0, drag = 0;
     // <VXC>  (VX_Object.cpp:435-490, :1064-1074, :1733-1930, :2495-2513)
     double lat = 0.001, adj[3] = {1, 1, 1}, line_off[2] = {0, 0}, layer_off[2] = {0, 0};
@@ -350,6 +350,9 @@ int parse_vxa(const XNode* root, int variant, Parsed& P) {
             load(E, "FluidEnvironment", &P.fluid);
             load(E, "AggregateDragCoefficient", &P.drag);
         }
+        // _voxcad has no fluid environment: it would read such a file as a terrestrial one.  A caller that hands a swimming
+        // experiment's file to the wrong fork gets an error instead of a plausible but wrong fitness.
+        if (!lw) { double fl = 0; if (load(E, "FluidEnvironment", &fl) && fl != 0) P.fluid_in_voxcad = true; }
     }
     const XNode* O = root->child("VXC");
     if (!O) O = root->child("DMF");
@@ -421,6 +424,7 @@ int parse_vxa(const XNode* root, int variant, Parsed& P) {
 }
 
 int check_supported(const Parsed& P, int ignore_collisions) {
+    if (P.fluid_in_voxcad) return hfail(VXG_UNSUPPORTED_FEATURE, "<FluidEnvironment>1 is a land/water-fork feature: import the file with VXH_VARIANT_LAND_WATER (voxelyze --lw)");
     if (P.max_vel) return hfail(VXG_UNSUPPORTED_FEATURE, "MaxVelLimitEnabled is not supported");
     if (P.blending) return hfail(VXG_UNSUPPORTED_FEATURE, "BlendingEnabled is not supported");
     if (P.volume_fx) return hfail(VXG_UNSUPPORTED_FEATURE, "VolumeEffectsEnabled is not supported");

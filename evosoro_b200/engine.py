@@ -16,7 +16,8 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libvxgpu.so")
+# VXG_LIB points the binding at another build of the same library (kernel tuning builds, `make OUT=../lib_x EXTRA=-D...`)
+LIB_PATH = os.environ.get("VXG_LIB") or os.path.join(_HERE, "lib", "libvxgpu.so")
 CSRC = os.path.join(_HERE, "csrc")
 _LIB = None
 

@@ -44,10 +44,19 @@ def run_batch(vxa_paths, devices=(0,), voxelyze=VOXELYZE, extra_args=()):
 
 
 def evaluate_all(sim, env, pop, print_log, save_vxa_every, run_directory, run_name, max_eval_time=60,
-                 time_to_try_again=10, save_lineages=False, devices=(0,), io=None):
+                 time_to_try_again=10, save_lineages=False, devices=(0,), io=None, variant="voxcad", extra_args=()):
     """Same signature and side effects as evosoro.tools.evaluation.evaluate_all (the two timing arguments are
     accepted and unused: there is nothing to poll for).  ``io`` may carry ``write_voxelyze_file`` and
-    ``read_voxlyze_results``; by default they come from evosoro's own ``read_write_voxelyze`` module."""
+    ``read_voxlyze_results``; by default they come from evosoro's own ``read_write_voxelyze`` module.
+
+    ``variant`` names the engine fork whose binary the experiment would have copied next to it: ``"voxcad"``
+    (evosoro/_voxcad) or ``"land_water"`` (evosoro/_voxcad_land_water: the swimming_* and land/water experiments; adds
+    ``--lw``).  A file with <FluidEnvironment>1 handed to the voxcad variant is rejected by the importer, not simulated dry.
+    An individual whose simulation produces no result file (diverged, unsupported, unreadable) keeps the objective's worst
+    value, as in the reference (evaluation.py:107-110, 213-215)."""
+    if variant not in ("voxcad", "land_water"):
+        raise ValueError("variant must be 'voxcad' or 'land_water'")
+    extra_args = list(extra_args) + (["--lw"] if variant == "land_water" else [])
     if io is None:
         import read_write_voxelyze as io   # evosoro/tools/read_write_voxelyze.py, on the GA's import path
     start_time = time.time()
@@ -75,10 +84,13 @@ def evaluate_all(sim, env, pop, print_log, save_vxa_every, run_directory, run_na
             to_run.append(ind)
 
     print_log.message("Launched one batched voxelyze call for {0} out of {1} individuals".format(len(to_run), len(pop)))
-    codes = run_batch([run_directory + "/voxelyzeFiles/" + run_name + "--id_%05i.vxa" % ind.id for ind in to_run], devices)
-    if any(c != 1 for c in codes):
-        print_log.message("WARNING: a voxelyze batch did not complete (exit codes {0}); "
-                          "the min fitness stays assigned for its individuals".format(codes))
+    run_batch([run_directory + "/voxelyzeFiles/" + run_name + "--id_%05i.vxa" % ind.id for ind in to_run], devices,
+              extra_args=extra_args)
+    missing = [ind.id for ind in to_run
+               if not os.path.exists(run_directory + "/fitnessFiles/softbotsOutput--id_%05i.xml" % ind.id)]
+    if missing:
+        print_log.message("WARNING: {0} individuals did not produce a result (ids {1}). "
+                          "The min fitness was assigned for these individuals".format(len(missing), missing))
 
     for ind in to_run:                                                     # evaluation.py:128-207
         result = run_directory + "/fitnessFiles/softbotsOutput--id_%05i.xml" % ind.id

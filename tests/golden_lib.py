@@ -36,6 +36,17 @@ class Golden:
     def collide(self):
         return bool(self.dump.sim[15])
 
+    @property
+    def fluid(self):
+        return self.lw and bool(self.dump.sim[22])
+
+
+def flags(name: str):
+    """(fluid, collide) of a fixture, read from its header (not from its name)."""
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    lw, sim = bool(z["lw"]), z["sim"]
+    return (lw and bool(sim[22])), bool(sim[15])
+
 
 def parse_result(xml: str) -> dict:
     """tag -> float of a <Voxelyze_Sim_Result>, read the way evosoro does (line-wise <tag>value</tag>,

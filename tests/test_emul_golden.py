@@ -18,8 +18,8 @@ from evosoro_b200 import abi
 
 LAT = 0.01
 CASES = [n for n in golden_lib.names() if not n.endswith("_full")]
-FLUID = lambda n: n.startswith("lw_fluid")
-COLLIDE = lambda n: "col_" in n
+FLUID = lambda n: golden_lib.flags(n)[0]
+COLLIDE = lambda n: golden_lib.flags(n)[1]
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -72,3 +72,29 @@ def test_emulated_f32_kernel_arithmetic(name, prec):
         assert np.abs(s.pos - d.pos[f]).max() <= 2e-5 * LAT, (name, f, np.abs(s.pos - d.pos[f]).max() / LAT)
         assert np.abs(s.quat - d.quat[f]).max() <= 1e-5
         assert np.abs(s.scale - d.scale[f]).max() <= 1e-15
+
+
+@pytest.mark.parametrize("name,prec", [("ex_example_1_full", 5), ("ex_example_1_full", 11), ("ex_phase_offset_full", 11),
+                                       ("ex_lw_hopper_full", 5), ("ex_lw_hexapus_full", 10)])
+def test_emulated_whole_runs_of_the_reference_example_inputs(name, prec):
+    """The inputs the reference ships, as shipped (SelfColEnabled=1, evolved morphologies, fluid), over their WHOLE lifetimes
+    (5 059 .. 68 319 steps) on the kernels' own arithmetic: final centre of mass within 1e-6 pitch (fp64: 5 / 7) or 1e-3 pitch
+    (fp32 production forms: 10 / 11) of the unmodified reference's.  The GPU suite runs all 13 through the CLI."""
+    from evosoro_b200 import engine
+    g = golden_lib.Golden(name)
+    m = engine.Model(text=g.vxa_text, variant=engine.VARIANT_LAND_WATER if g.lw else engine.VARIANT_VOXCAD)
+    total, latch, _ = m.step_plan()
+    assert total == int(g.full_tail[0])
+    rob = m.robot
+    LAT = float(g.dump.sim[14])
+    mass = np.array([c.mass for c in rob.vclasses])[rob.vox_class][:, None]
+    e = emul_lib.EmulSim(rob, prec)
+    assert e.h
+    e.step(latch)
+    ini = (e.state().pos * mass).sum(0) / mass.sum()
+    e.step(total - latch)
+    com = (e.state().pos * mass).sum(0) / mass.sum()
+    assert not e.diverged
+    tol = 1e-6 if prec in (5, 7) else 1e-3
+    assert np.abs(ini - g.full_hdr[-1, 6:9]).max() <= tol * LAT
+    assert np.abs(com - g.full_hdr[-1, 3:6]).max() <= tol * LAT

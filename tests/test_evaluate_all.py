@@ -42,7 +42,8 @@ class Pop(list):
 
 def make_io(sim_params):
     def write_voxelyze_file(sim, env, ind, run_directory, run_name):
-        s = vxa.SimParams(**{**sim_params, "fitness_file": run_directory + "/fitnessFiles/softbotsOutput--id_%05i.xml" % ind.id})
+        s = vxa.SimParams(**{**sim_params, **getattr(ind, "sim_overrides", {}),
+                             "fitness_file": run_directory + "/fitnessFiles/softbotsOutput--id_%05i.xml" % ind.id})
         text = vxa.vxa_text(ind.phenotype.st if ind.phenotype.is_valid() else np.ones((1, 1, 1), dtype=np.int32), sim=s)
         with open(run_directory + "/voxelyzeFiles/" + run_name + "--id_%05i.vxa" % ind.id, "w") as f:
             f.write(text)
@@ -95,3 +96,23 @@ def test_evaluate_all_hook_end_to_end(tmp_path):
     pop2.already_evaluated = pop.already_evaluated
     evaluation.evaluate_all(None, env, pop2, log, 0, run, "t", io=io)
     assert pop2[0].fitness == inds[0].fitness and pop2.total_evaluations == 0
+
+
+@pytest.mark.gpu
+def test_evaluate_all_leaves_the_worst_fitness_on_a_diverged_individual(tmp_path):
+    """evaluation.py:107-110, 213-215 of the reference: an individual whose simulation diverges never yields a result file and keeps
+    the objective's worst value; it is not cached as evaluated, and the rest of the population is unaffected."""
+    run = str(tmp_path)
+    for d in ("voxelyzeFiles", "fitnessFiles", "bestSoFar/fitOnly", "Gen_0000", "ancestors"):
+        os.makedirs(os.path.join(run, d))
+    inds = [Ind(0, vxa.dense_lattice(3, 5)), Ind(1, vxa.dense_lattice(3, 7)), Ind(2, vxa.dense_lattice(3, 6))]
+    inds[1].sim_overrides = {"dt_frac": 4.0}          # unstable integration: strain > 100 after ~90 steps
+    pop = Pop(inds)
+    log = Log()
+    io = make_io(dict(init_cm_time=0.01, stop_condition_value=0.1))
+    evaluation.evaluate_all(None, types.SimpleNamespace(actuation_variance=0), pop, log, 0, run, "t", io=io)
+    assert inds[1].fitness == -1e9 and inds[1].md5 not in pop.already_evaluated
+    assert inds[0].fitness > -1e9 and inds[2].fitness > -1e9
+    assert pop.all_evaluated_individuals_ids == [0, 2]
+    assert any("did not produce a result" in l for l in log.lines)
+    assert not os.listdir(os.path.join(run, "fitnessFiles"))

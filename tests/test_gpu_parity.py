@@ -41,7 +41,7 @@ def _run_gpu(rob, prec, frames, every, bonds=True):
 
 
 # ---- (a) golden fixtures, imported by the product importer ---------------------------------------
-@pytest.mark.parametrize("name", [n for n in TRAJ if not n.startswith("lw_fluid") and "col_" not in n])
+@pytest.mark.parametrize("name", [n for n in TRAJ if not any(golden_lib.flags(n))])
 def test_golden_f64_logic_parity(name):
     """P1: fp64 instantiation vs the reference, per-frame state: positions <= 1e-9 pitch."""
     g = golden_lib.Golden(name)
@@ -180,6 +180,24 @@ def test_reuploading_one_slot_leaves_the_others_running():
     assert np.array_equal(a.download(1).pos, fresh.download(0).pos)
     st = a.stats()
     assert [int(s.steps) for s in st] == [500, 200, 500]
+    for b in (a, ref, fresh):
+        b.close()
+
+
+def test_reuploading_one_slot_keeps_the_live_contact_lists_of_the_others():
+    """The same with SelfColEnabled=1 and live contact bonds: the contact-bond lists are device-managed state, so re-uploading
+    slot 1 must not replace the lists of slots 0 and 2 with the host's (empty) mirror."""
+    g = golden_lib.Golden("col_pincer")
+    rob = engine.Model(text=g.vxa_text).robot
+    a = engine.Batch([rob] * 3); a.step(500); assert not a.sync().any()      # contacts are live from ~step 300 on
+    a.reupload(1)
+    a.step(300); assert not a.sync().any()
+    ref = engine.Batch([rob]); ref.step(800); ref.sync()
+    fresh = engine.Batch([rob]); fresh.step(300); fresh.sync()
+    for r in (0, 2):
+        assert np.array_equal(a.download(r).pos, ref.download(0).pos)
+    assert np.array_equal(a.download(1).pos, fresh.download(0).pos)
+    assert np.isfinite(a.download(0).pos).all()
     for b in (a, ref, fresh):
         b.close()
 
@@ -409,6 +427,37 @@ def test_cli_drop_in_writes_reference_result_file(name, tmp_path):
     _check_result(out.read_text(), g)
 
 
+def test_cli_reference_example_inputs_hit_the_recorded_reference_values(tmp_path):
+    """BASELINE.md section 4 (values recorded from the reference before any of this existed): Example_1.vxa -> NormFinalDist
+    0.0795605 after 49 366 steps; sample_vxa/hexapus.vxa -> normAbsoluteDisplacement 17.1761.  Both files as shipped
+    (SelfColEnabled=1), one batch per fork through the drop-in CLI."""
+    for name, lw, tag, want in (("ex_example_1_full", False, "NormFinalDist", 0.0795605), ("ex_lw_hexapus_full", True, "normAbsoluteDisplacement", 17.1761)):
+        g = golden_lib.Golden(name)
+        out = tmp_path / (name + ".xml")
+        p = tmp_path / (name + ".vxa")
+        p.write_text(g.vxa_text.replace(g.fitness_file, str(out)))
+        assert subprocess.run([CLI, "-f", str(p)] + (["--lw"] if lw else [])).returncode == 1
+        got = golden_lib.parse_result(out.read_text())
+        assert got[tag] == pytest.approx(want, abs=1e-2), (name, got[tag])
+        assert golden_lib.parse_result(g.result_xml)[tag] == pytest.approx(want, abs=5e-5)   # the fixture is that same run
+    assert int(golden_lib.Golden("ex_example_1_full").full_tail[0]) == 49366
+
+
+def test_cli_all_reference_example_inputs_in_one_batch(tmp_path):
+    """Every input the reference ships for one fork as ONE ragged batch (98 .. 743 voxels, 5 520 .. 49 366 steps, live
+    self-collision): each robot's result file equals the one it gets alone (checked against the reference's by the test above)."""
+    names = [n for n in FULL_XML if n.startswith("ex_") and not golden_lib.Golden(n).lw]
+    args, outs = [], []
+    for n in names:
+        g = golden_lib.Golden(n)
+        out = tmp_path / (n + ".xml"); p = tmp_path / (n + ".vxa")
+        p.write_text(g.vxa_text.replace(g.fitness_file, str(out)))
+        args += ["-f", str(p)]; outs.append((out, g))
+    assert subprocess.run([CLI] + args).returncode == 1
+    for out, g in outs:
+        _check_result(out.read_text(), g)
+
+
 def test_cli_batch_mode_many_files(tmp_path):
     """The batched form: several -f files in one process = one GPU batch; every robot gets its own result file,
     identical to running it alone."""
@@ -426,6 +475,44 @@ def test_cli_batch_mode_many_files(tmp_path):
     assert outs[0][0].read_text() == outs[2][0].read_text()     # same robot in two slots: identical file
 
 
+def _diverging_vxa(fit):
+    """DtFrac 4: the explicit integrator is unstable, a bond passes strain 100 after ~90 steps.  The reference CLI never returns
+    on this input (TimeStep keeps failing, CurTime stands still) and writes no result -- checked with oracle/_ref/voxelyze_ref."""
+    return vxa.vxa_text(vxa.dense_lattice(3, 7), sim=vxa.SimParams(dt_frac=4.0, init_cm_time=0.01, stop_condition_value=0.1, fitness_file=str(fit)))
+
+
+def test_cli_diverged_robot_writes_no_result_and_spares_its_batch_mates(tmp_path):
+    """VX_Sim.cpp:1147-1150 + main.cpp:89: a diverged simulation never reaches its stop condition, so no result file appears and
+    evosoro keeps the worst fitness for it (evaluation.py:107-110, 213-215).  Here: no file for that robot (a stale one is
+    removed), exit code 0, and the other robots of the batch get exactly the result they get alone."""
+    g = golden_lib.Golden("dense3_full")
+    good, bad = tmp_path / "good.xml", tmp_path / "bad.xml"
+    bad.write_text("<stale/>")
+    (tmp_path / "a.vxa").write_text(g.vxa_text.replace(g.fitness_file, str(good)))
+    (tmp_path / "b.vxa").write_text(_diverging_vxa(bad))
+    r = subprocess.run([CLI, "-f", str(tmp_path / "b.vxa"), "-f", str(tmp_path / "a.vxa")], capture_output=True, text=True)
+    assert r.returncode == 0 and "Simulation Diverged" in r.stderr
+    assert not bad.exists()
+    _check_result(good.read_text(), g)
+    r = subprocess.run([CLI, "-f", str(tmp_path / "b.vxa")], capture_output=True, text=True)   # alone: the reference hangs, we report
+    assert r.returncode == 0 and not bad.exists()
+
+
+def test_cli_bad_file_does_not_cost_the_others_their_results(tmp_path):
+    """One unreadable and one unsupported file in a batch: both are reported and skipped, the rest run."""
+    g = golden_lib.Golden("dense3_full")
+    good = tmp_path / "good.xml"
+    (tmp_path / "a.vxa").write_text(g.vxa_text.replace(g.fitness_file, str(good)))
+    (tmp_path / "eq.vxa").write_text(vxa.vxa_text(vxa.dense_lattice(2, 1), sim=vxa.SimParams(equilibrium_mode=1, fitness_file=str(tmp_path / "eq.xml"))))
+    (tmp_path / "junk.vxa").write_text("<VXA><Simulator>")
+    r = subprocess.run([CLI, "-f", str(tmp_path / "junk.vxa"), "-f", str(tmp_path / "a.vxa"), "-f", str(tmp_path / "eq.vxa"),
+                        "-f", str(tmp_path / "missing.vxa")], capture_output=True, text=True)
+    assert r.returncode == 0
+    assert r.stderr.count("Problem importing VXA file") == 3 and "not supported" in r.stderr
+    _check_result(good.read_text(), g)
+    assert not (tmp_path / "eq.xml").exists()
+
+
 def test_cli_rejects_unsupported_instead_of_falling_back(tmp_path):
     p = tmp_path / "eq.vxa"
     p.write_text(vxa.vxa_text(vxa.dense_lattice(2, 1), sim=vxa.SimParams(equilibrium_mode=1, fitness_file=str(tmp_path / "f.xml"))))
@@ -441,7 +528,8 @@ needs_adapter = pytest.mark.skipif(not os.access(ADAPTER, os.X_OK), reason="orac
 
 @needs_adapter
 @pytest.mark.parametrize("name,f64", [("dense3_full", False), ("dense3_full", True), ("dense3_afterlife_full", False), ("col_pincer_full", False),
-                                      ("dev_growth3_full", False), ("dev_growth3_full", True), ("evosoro_basic_id1_full", False)])
+                                      ("dev_growth3_full", False), ("dev_growth3_full", True), ("evosoro_basic_id1_full", False),
+                                      ("ex_example_1_full", False), ("ex_phase_offset_full", False)])
 def test_class_api_adapter_reference_cli_on_the_engine(name, f64, tmp_path):
     """voxelyzeMain/main.cpp, LoadVXAFile/Import, TimeStep's latches, UpdateCollisions (host-side contact list ->
     vxg_set_collision_pairs), UpdateStats and WriteResultFile are all the UNMODIFIED reference; only Integrate() is
@@ -465,7 +553,7 @@ ADAPTER_LW = os.path.join(refdump.REF_DIR, "voxelyze_gpu_adapter_lw")
 
 
 @pytest.mark.skipif(not os.access(ADAPTER_LW, os.X_OK), reason="oracle/_ref/voxelyze_gpu_adapter_lw did not travel with the snapshot")
-@pytest.mark.parametrize("name", ["lw_dense3_full", "lw_fluid_dense3_full"])
+@pytest.mark.parametrize("name", ["lw_dense3_full", "lw_fluid_dense3_full", "ex_lw_hopper_full"])
 def test_class_api_adapter_land_water_fork(name, tmp_path):
     """The same seam under the land/water fork's CLI + library: its Integrate() (bonds, surface-mesh fluid drag, voxels) runs on
     the device; the per-voxel strains are written back too, so the reference's own deformable mesh yields RobotVolumeEnd."""

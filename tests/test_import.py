@@ -116,3 +116,16 @@ def test_boundary_conditions_legacy_and_current_layouts_agree():
     assert (dof == 0x3F).sum() == 9 and a.n_bond == 54 - 12      # the 12 bonds inside the clamped face are not created
     fz = np.array([c.ext_force[2] for c in _expand_v(a)])
     assert (fz != 0).sum() == 9 and abs(fz.sum() + 1.0) < 1e-15   # the region's force is shared by the voxels it touches
+
+
+def test_fluid_environment_file_is_rejected_by_the_voxcad_variant():
+    """_voxcad has no fluid environment: a swimming experiment's file imported with the wrong fork would be simulated dry and
+    yield a plausible but wrong fitness.  The importer rejects it; the land/water variant takes it."""
+    text = vxa.vxa_text(vxa.dense_lattice(2, 3), env=vxa.EnvParams(fluid_environment=1, aggregate_drag_coefficient=750.0))
+    with pytest.raises(engine.EngineError) as e:
+        engine.Model(text=text, variant=engine.VARIANT_VOXCAD)
+    assert e.value.code == abi.VXG_UNSUPPORTED_FEATURE and "land/water" in str(e.value)
+    m = engine.Model(text=text, variant=engine.VARIANT_LAND_WATER)
+    assert m.robot.sim.flags & abi.VXG_F_FLUID
+    dry = vxa.vxa_text(vxa.dense_lattice(2, 3), env=vxa.EnvParams(fluid_environment=0))
+    assert not (engine.Model(text=dry, variant=engine.VARIANT_VOXCAD).robot.sim.flags & abi.VXG_F_FLUID)

@@ -195,6 +195,40 @@ def evosoro_cases():
         case_text("evosoro_basic_id%d_full" % idx, text, 0, 1, full=True, col=True, fitness_file=fit)
 
 
+REF = "/root/reference/evosoro"
+EXAMPLES = [   # (fixture name, file, land/water fork, short-horizon steps, frame spacing)
+    ("ex_example_1", "_voxcad/voxelyzeMain/Example_1.vxa", False, 1000, 250),
+    ("ex_example_2", "_voxcad/voxelyzeMain/Example_2.vxa", False, 800, 400),
+    ("ex_example_3", "_voxcad/voxelyzeMain/Example_3.vxa", False, 800, 400),
+    ("ex_no_actuation", "_voxcad/voxelyzeMain/Example_no_actuation.vxa", False, 1000, 250),
+    ("ex_phase_offset", "_voxcad/voxelyzeMain/Example_withPhaseOffset.vxa", False, 1000, 250),
+    ("ex_lw_flapping", "_voxcad_land_water/sample_vxa/flapping_passive_tissue.vxa", True, 1000, 250),
+    ("ex_lw_full_cross", "_voxcad_land_water/sample_vxa/full_cross.vxa", True, 800, 400),
+    ("ex_lw_hexapus", "_voxcad_land_water/sample_vxa/hexapus.vxa", True, 1000, 250),
+    ("ex_lw_hopper", "_voxcad_land_water/sample_vxa/hopper.vxa", True, 1200, 300),
+    ("ex_lw_land_stiffness", "_voxcad_land_water/sample_vxa/land_stiffness_phaseoffset.vxa", True, 1000, 250),
+    ("ex_lw_pusher", "_voxcad_land_water/sample_vxa/pusher_land.vxa", True, 1200, 300),
+    ("ex_lw_quadruped", "_voxcad_land_water/sample_vxa/quadruped_land.vxa", True, 1200, 300),
+    ("ex_lw_quadrupus", "_voxcad_land_water/sample_vxa/quadrupus_passive_tissue.vxa", True, 1000, 250),
+]
+
+
+def example_cases(only=None):
+    """The inputs the reference ships (voxelyzeMain/Example_*.vxa and _voxcad_land_water/sample_vxa/*.vxa), as shipped
+    (SelfColEnabled=1, evolved morphologies, per-voxel phase offsets / stiffness, fluid environments): a short-horizon
+    trajectory (<name>.npz) and the whole CLI run with the reference CLI's own result file (<name>_full.npz, final state and
+    fitness block only).  Only <FitnessFileName> is redirected."""
+    import re
+    for name, rel, lw, n_steps, every in EXAMPLES:
+        if only and name not in only:
+            continue
+        text = open(os.path.join(REF, rel), encoding="latin-1").read()
+        fit = os.path.join(TMP, name + "_result.xml")
+        text = re.sub(r"<FitnessFileName>[^<]*</FitnessFileName>", "<FitnessFileName>" + fit + "</FitnessFileName>", text)
+        case_text(name, text, n_steps, every, lw=lw, col=True)
+        case_text(name + "_full", text, 0, 1, lw=lw, full=True, col=True, fitness_file=fit)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "density":
         pal = vxa.four_material_palette()
@@ -202,6 +236,8 @@ if __name__ == "__main__":
         case("dense3_density", vxa.dense_lattice(3, 14), 1200, 100, sim=vxa.SimParams(init_cm_time=0.02, stop_condition_value=0.2), palette=pal)
     elif len(sys.argv) > 1 and sys.argv[1] == "evosoro":
         evosoro_cases()
+    elif len(sys.argv) > 1 and sys.argv[1] == "examples":
+        example_cases(sys.argv[2:])
     elif len(sys.argv) > 1 and sys.argv[1] == "big":
         case("dense10_s3_full", vxa.dense_lattice(10, 3), 0, 1, full=True)
     elif len(sys.argv) > 1 and sys.argv[1] == "dev":
@@ -219,3 +255,4 @@ if __name__ == "__main__":
         bc_cases()
         dev_cases()
         evosoro_cases()
+        example_cases()
