@@ -93,6 +93,14 @@ class Limits(C.Structure):
     ]
 
 
+class PopOptions(C.Structure):
+    _fields_ = [("precision", C.c_int32), ("chunk_robots", C.c_int32), ("want_mesh", C.c_int32), ("col_pairs_per_vox", C.c_int32),
+                ("reserved", C.c_int32 * 4)]
+
+
+VXG_FAM_COMPACT, VXG_FAM_COLLIDE, VXG_FAM_MESH = 1, 2, 4
+
+
 class RobotStats(C.Structure):
     _fields_ = [
         ("com", C.c_double * 3), ("ini_com", C.c_double * 3), ("max_vel", C.c_double),

@@ -81,46 +81,27 @@ int main(int argc, char** argv) {
     std::vector<vxh_model*> models(n, nullptr);
     std::vector<vxg_robot_desc> descs(n);
     std::vector<int64_t> total(n), latch(n), eol(n);
-    vxg_limits lim; memset(&lim, 0, sizeof lim);
-    lim.max_vox = lim.max_vclass = lim.max_bclass = 1; lim.precision = VXG_PREC_F32;
-    int64_t max_total = 0;
-    int col_cap = 0;
     for (int r = 0; r < n; r++) {
         models[r] = loaded[src[r]]; total[r] = f_total[src[r]]; latch[r] = f_latch[src[r]]; eol[r] = f_eol[src[r]];
         descs[r] = *vxh_desc(models[r]);
-        lim.max_vox = std::max(lim.max_vox, descs[r].n_vox);
-        lim.max_vclass = std::max(lim.max_vclass, descs[r].n_vclass);
-        lim.max_bclass = std::max(lim.max_bclass, descs[r].n_bclass);
-        // contact-bond list capacity, sized from the robot (a folded robot holds a few candidate pairs per surface voxel;
-        // overflow is reported per robot, never truncated)
-        if (descs[r].sim.flags & VXG_F_COLLISIONS) col_cap = std::max(col_cap, std::min(16384, std::max(512, 4 * descs[r].n_vox)));
-        // the land/water result file reports the volume of the deformed surface mesh at the end: every robot of that fork needs the
-        // mesh tables, not only those in a fluid environment
-        if (descs[r].sim.flags & (VXG_F_FLUID | VXG_F_LW_SCALE)) lim.max_mesh_verts = std::max(lim.max_mesh_verts, vxg_mesh_vertex_count(&descs[r]));
-        max_total = std::max(max_total, total[r]);
         if (print_scrn) printf("Imported %s: %d voxels, %d bonds, %lld steps\n", files[src[r]].c_str(), descs[r].n_vox, descs[r].n_bond, (long long)total[r]);
     }
-    vxg_batch* b = nullptr;
-    int rc;
-    for (;;) {   // the list is shared-memory resident next to the robot: halve the capacity until both fit
-        lim.max_col_pairs = col_cap;
-        rc = vxg_create(&b, device, n, &lim);
-        if (rc != VXG_UNSUPPORTED_SIZE || col_cap <= 512) break;
-        col_cap /= 2;
-    }
-    for (int r = 0; r < n && !rc; r++) rc = vxg_upload(b, r, &descs[r]);
-    if (!rc) rc = vxg_set_step_budget(b, total.data(), latch.data());
-    if (!rc) rc = vxg_set_eol_step(b, eol.data());
+    // The whole set is one ragged population: the library buckets it by voxel stride and kernel family (a 40-voxel CPPN robot
+    // does not pay for a 216-voxel batch-mate's stride, nor a plain robot for a self-colliding one's kernel) and runs the
+    // buckets concurrently; every robot stops at its own step budget.
+    vxg_pop_options opt; memset(&opt, 0, sizeof opt);
+    opt.precision = VXG_PREC_F32;
+    opt.want_mesh = 1;   // the land/water result file reports the volume of the deformed surface mesh for every robot of that fork
+    vxg_population* pop = nullptr;
+    int rc = vxg_pop_create(&pop, device, descs.data(), n, &opt);
+    if (!rc) rc = vxg_pop_set_plan(pop, total.data(), latch.data(), eol.data());
+    if (!rc) rc = vxg_pop_run(pop);   // whole lifetimes on the device
     std::vector<uint32_t> status(n, 0);
-    for (int64_t done = 0; done < max_total && !rc;) {   // whole lifetimes on the device; robots stop at their own budgets
-        int chunk = (int)std::min<int64_t>(max_total - done, 1 << 20);
-        rc = vxg_step(b, chunk);
-        done += chunk;
-    }
-    if (!rc) rc = vxg_sync(b, status.data());
+    if (!rc) rc = vxg_pop_sync(pop, status.data());
     std::vector<vxg_robot_stats> stats(n);
-    if (!rc) rc = vxg_reduce_stats(b, stats.data());
+    if (!rc) rc = vxg_pop_reduce_stats(pop, stats.data());
     if (rc) { fprintf(stderr, "voxelyze: %s\n", vxg_last_error()); return 0; }
+    if (print_scrn) printf("%d robots in %d batches, %lld kernel launches\n", n, vxg_pop_n_batches(pop), (long long)vxg_pop_launch_count(pop));
     for (int r = 0; r < n; r++) {
         vxh_info info; vxh_get_info(models[r], &info);
         const char* file = files[src[r]].c_str();
@@ -129,7 +110,7 @@ int main(int argc, char** argv) {
         // evosoro leaves the worst fitness on that individual (evaluation.py:107-110, 213-215).  Same here, without the hang:
         // no file (a stale one is removed), a message, and the others are unaffected.
         const bool failed = (status[r] & (VXG_ST_COL_OVERFLOW | VXG_ST_DIVERGED)) != 0;
-        if (status[r] & VXG_ST_COL_OVERFLOW) fprintf(stderr, "%s: more than %d self-collision contact bonds. No result written\n", file, lim.max_col_pairs);
+        if (status[r] & VXG_ST_COL_OVERFLOW) fprintf(stderr, "%s: the self-collision contact-bond list outgrew its capacity. No result written\n", file);
         else if (status[r] & VXG_ST_DIVERGED) fprintf(stderr, "%s: Simulation Diverged. Please reduce forces or accelerations. No result written\n", file);
         if (print_scrn) printf("Ended at: %g\n", stats[r].time);
         if (failed) { n_failed++; if (info.fitness_file_name[0]) remove(info.fitness_file_name); }
@@ -138,7 +119,7 @@ int main(int argc, char** argv) {
         }
         vxh_free(models[r]);
     }
-    vxg_destroy(b);
+    vxg_pop_destroy(pop);
     if (n_failed) fprintf(stderr, "voxelyze: %d of %d robots did not produce a result\n", n_failed, n_files);
     return n_failed ? 0 : 1;
 }

@@ -341,24 +341,24 @@ VX_HD void bond_force(const BondK<T>& k, V3<T> e_w, Q4<T> q1w, Q4<T> q2w, T dnom
     const bool changed = to_small | to_large;
     small = (small | to_small) & !to_large;
 
-    V3<T> p2, an1, an2;
-    Q4<T> back;                               // conj(TotalRot): local -> world rotation
-    if (small) {                              // :87-95
-        an1 = mk3<T>(0, 0, 0);
-        an2 = rotvec(q12);
-        p2 = mk3<T>(rr.x - nomrel, rr.y, rr.z);
-        back = q1;
-    } else {                                  // :101-118
+    // The two modes differ in WHICH quaternion Angle2 is taken from and in Pos2 / Angle1 / the frame; what is then done with
+    // them is the same.  Only the mode-specific part sits inside the branch, so a warp whose lanes are in both modes (most warps of
+    // an actuated robot) issues the shared part -- the rotation vector of Angle2 -- once, not once per mode.
+    V3<T> p2 = mk3<T>(rr.x - nomrel, rr.y, rr.z), an1 = mk3<T>(0, 0, 0);   // small angle, :87-95
+    Q4<T> a2q = q12;
+    Q4<T> back = q1;                          // conj(TotalRot): local -> world rotation
+    if (!small) {                             // :101-118
         Q4<T> pa = from_angle_to_posx(mk3<T>(rx, rr.y, rr.z));
         // |dp| - pitch without cancellation
         T d2 = (T)2 * D * e.x + (e.x * e.x + e.y * e.y + e.z * e.z);
         T len = vx_fsqrt(D * D + d2);
         p2 = mk3<T>(d2 * vx_rcp(len + D) - nomrel, 0, 0);
         an1 = rotvec(pa);
-        an2 = rotvec(qmul(pa, q12));          // (pa * conj(q1)) * q2
+        a2q = qmul(pa, q12);                  // (pa * conj(q1)) * q2
         Q4<T> cpa; cpa.w = pa.w; cpa.x = -pa.x; cpa.y = -pa.y; cpa.z = -pa.z;
         back = qmul(q1, cpa);                 // conj(pa * conj(q1))
     }
+    const V3<T> an2 = rotvec(a2q);
 
     // axial stress (:120, :189-307; MDL_LINEAR: VX_Object.cpp:1472-1482).  For linear materials the
     // heterogeneous fixed-point iteration (:226-258) converges in one pass to sigma = 2 E1 E2/(E1+E2) eps

@@ -2,6 +2,7 @@
 // into the device blob layout, kernel dispatch, state download.  No CPU compute path exists here:
 // every compute entry point fails with VXG_ERR_NO_DEVICE when no CUDA device is present.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <chrono>
 #include <climits>
 #include <cmath>
@@ -12,75 +13,21 @@
 #include <thread>
 #include <vector>
 
-#include "../../include/vxgpu.h"
-#include "vxg_launch.cuh"
+#include "vxg_batch.h"
 #include "vx_pack.h"
 
 using namespace vx;
 
 static thread_local std::string g_err;
-static int fail(int code, const char* fmt, ...) {
+int vxg_i_fail(int code, const char* fmt, ...) {
     char buf[512];
     va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
     g_err = buf;
     return code;
 }
-#define CK(call)                                                                                   \
-    do {                                                                                           \
-        cudaError_t e_ = (call);                                                                   \
-        if (e_ != cudaSuccess) return fail(VXG_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
-    } while (0)
+#define fail vxg_i_fail
 
 static_assert(sizeof(StatsDev) == sizeof(vxg_robot_stats), "StatsDev must mirror vxg_robot_stats");
-
-struct vxg_batch {
-    int device = 0, n_robots = 0, prec = 0;
-    vxg_limits lim{};
-    BlobLayout L{};
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    cudaEvent_t marks[VXG_N_MARKS] = {};
-    bool mark_set[VXG_N_MARKS] = {};
-    bool timed = false;
-    // device
-    unsigned char* d_blobs = nullptr;
-    RobotCtl* d_ctl = nullptr;
-    void* d_bk = nullptr; double* d_bk_dist = nullptr; void* d_vk = nullptr; ScaleK* d_sk = nullptr;
-    double* d_scale_c = nullptr; void* d_ext_disp = nullptr; void* d_ext_tdisp = nullptr; double* d_nom = nullptr;
-    void* d_bond_rec = nullptr; StatsDev* d_stats = nullptr;
-    uint32_t* d_bpair = nullptr; uint32_t* h_bpair = nullptr;   // voxel-class pair of every re-keyed bond class (compact family)
-    // self-collision (allocated when limits.max_col_pairs > 0)
-    ColPair* d_col_pairs = nullptr; int16_t* d_col_surf = nullptr; int8_t* d_col_lat4 = nullptr; unsigned long long* d_col_near = nullptr;
-    ColPair* h_col_pairs = nullptr; int16_t* h_col_surf = nullptr; int8_t* h_col_lat4 = nullptr; unsigned long long* h_col_near = nullptr;
-    // pinned host mirrors (whole batch, uploaded in one go before the first step after a change)
-    unsigned char* h_blobs = nullptr;
-    RobotCtl* h_ctl = nullptr;
-    unsigned char* h_bkc = nullptr;   // compact bond classes of every robot (BondKc), used when the whole batch qualifies
-    bool compact = false;             // mode of the tables currently on the device
-    unsigned char* h_bk = nullptr; double* h_bk_dist = nullptr; unsigned char* h_vk = nullptr; ScaleK* h_sk = nullptr;
-    double* h_scale_c = nullptr; unsigned char* h_ext_disp = nullptr; unsigned char* h_ext_tdisp = nullptr; double* h_nom = nullptr;
-    StatsDev* h_stats = nullptr;
-    bool dirty = false;          // host mirrors newer than device
-    bool ctl_dirty = false;      // only h_ctl newer (step budget)
-    bool tables_dirty = false;   // the class tables must travel again in the other form (bond recording switched on / off)
-    std::vector<char> uploaded;
-    std::vector<char> slot_dirty;    // the slot's host mirror (blob, Scale, control block) is newer than the device copy
-    std::vector<char> reset_image;   // the slot's host mirror is the plain reset image vxg_upload packed (nothing pulled or edited since);
-                                     // 2 = only its position planes and static section are filled in (pack_blob partial)
-    std::vector<std::vector<int32_t>> bond_v1, bond_v2, bond_axis;   // for download mapping
-    int64_t launches = 0;
-    size_t last_upload_bytes = 0;    // blob + NominalPosition bytes the last population upload copied host -> device
-    int vpt = 1, threads = 32;
-    bool smem_mode = true;
-    size_t smem_bytes = 0;
-    size_t tb_wide = 0, tb_compact = 0;          // shared-memory table bytes with the wide / compact bond classes
-    bool smem_wide_fits = false;                 // blob + wide tables fit in shared memory
-    bool smem_mode_wide_or_compact = false;      // blob + compact tables fit
-    size_t rs() const { return prec == VXG_PREC_F64 ? 8 : 4; }
-    size_t bk_sz() const { return prec == VXG_PREC_F64 ? sizeof(BondK<double>) : sizeof(BondK<float>); }
-    size_t bkc_sz() const { return prec == VXG_PREC_F64 ? sizeof(BondKc<double>) : sizeof(BondKc<float>); }
-    size_t vk_sz() const { return prec == VXG_PREC_F64 ? sizeof(VoxK<double>) : sizeof(VoxK<float>); }
-};
 
 extern "C" int vxg_abi_version(void) { return VXG_ABI_VERSION; }
 extern "C" const char* vxg_last_error(void) { return g_err.c_str(); }
@@ -117,6 +64,7 @@ static cudaError_t launch_step_p(vxg_batch* b, int n_steps, int record) {
     c.vpt = b->vpt;
     if (b->prec == VXG_PREC_F64) return launch_f64(dev_view<double>(b), c, b->smem_mode);
     const BatchDev<float> B = dev_view<float>(b);
+    if ((b->L.nvert_cap > 0 || b->lim.max_col_pairs > 0) && !b->smem_mode) return launch_f32_extras_global(B, c, b->L.nvert_cap > 0, b->lim.max_col_pairs > 0);
     if (b->L.nvert_cap > 0)
         return (b->compact && b->smem_mode) ? launch_f32_fluid_compact(B, c, b->lim.max_col_pairs > 0) : launch_f32_fluid(B, c, b->lim.max_col_pairs > 0);
     if (b->lim.max_col_pairs > 0) return (b->compact && b->smem_mode) ? launch_f32_collide_compact(B, c) : launch_f32_collide(B, c);
@@ -171,9 +119,6 @@ extern "C" int vxg_create(vxg_batch** out, int device, int n_robots, const vxg_l
     b->smem_wide_fits = b->L.total_bytes + tb <= (size_t)max_smem;
     b->smem_mode_wide_or_compact = b->prec == VXG_PREC_F32 && b->L.total_bytes + b->tb_compact <= (size_t)max_smem;
     if (mc > 0 && lim->precision != VXG_PREC_F32) { delete b; return fail(VXG_UNSUPPORTED_FEATURE, "vxg_create: the self-collision kernels exist in fp32 only"); }
-    if (mc > 0 || b->L.nvert_cap > 0) {   // these layouts run shared-memory resident only
-        if (!b->smem_wide_fits) { delete b; return fail(VXG_UNSUPPORTED_SIZE, "vxg_create: robot blob with collision list / surface mesh (%zu B) exceeds shared memory", b->L.total_bytes + tb); }
-    }
     b->smem_mode = b->smem_wide_fits || b->smem_mode_wide_or_compact;   // final choice is made at flush, when the classes are known
     b->smem_bytes = b->smem_mode ? b->L.total_bytes + tb : tb;
 
@@ -384,7 +329,7 @@ static int flush_state(vxg_batch* b) {
 }
 
 // make the device copy current (host mirrors -> device) on the batch stream
-static int flush(vxg_batch* b) {
+int vxg_i_flush(vxg_batch* b) {
     CK(cudaSetDevice(b->device));
     size_t nr = (size_t)b->n_robots, mv = (size_t)b->lim.max_vclass, mb = (size_t)b->lim.max_bclass, nv = (size_t)b->L.nv;
     if (b->dirty || b->tables_dirty) {
@@ -437,7 +382,8 @@ static int pull(vxg_batch* b, bool blobs, int robot) {
     CK(cudaSetDevice(b->device));
     size_t nr = (size_t)b->n_robots, mv = (size_t)b->lim.max_vclass;
     // pending host-side changes go down first: dirtiness is per slot, so the device may still hold the newer state of the others
-    if (b->dirty) { int rc = flush(b); if (rc) return rc; }
+    // (and so do control-block edits of an earlier setter: two setters in a row must not lose the first one's values)
+    if (b->dirty || b->ctl_dirty) { int rc = vxg_i_flush(b); if (rc) return rc; }
     CK(cudaMemcpyAsync(b->h_ctl, b->d_ctl, nr * sizeof(RobotCtl), cudaMemcpyDeviceToHost, b->stream));
     if (blobs) {
         size_t r0 = robot < 0 ? 0 : (size_t)robot, cnt = robot < 0 ? nr : 1;
@@ -496,7 +442,7 @@ extern "C" int vxg_step(vxg_batch* b, int n_steps) {
     if (n_steps < 0) return fail(VXG_ERR_ARG, "vxg_step: negative step count");
     for (int r = 0; r < b->n_robots; r++)
         if (!b->uploaded[r]) return fail(VXG_ERR_STATE, "vxg_step: robot slot %d was never uploaded", r);
-    int rc = flush(b);
+    int rc = vxg_i_flush(b);
     if (rc) return rc;
     CK(cudaEventRecord(b->ev0, b->stream));
     const int chunk = 4096;   // steps per launch: bounds single-kernel run time, state stays resident inside a chunk
@@ -555,7 +501,7 @@ extern "C" int vxg_kernel_config(vxg_batch* b, int* threads, int* vpt, int* smem
     {   // the table form (wide / compact) and with it the shared-memory size is decided when the classes are flushed
         bool all = true;
         for (int r = 0; r < b->n_robots; r++) all = all && b->uploaded[r];
-        if (all) { int rc = flush(b); if (rc) return rc; }
+        if (all) { int rc = vxg_i_flush(b); if (rc) return rc; }
     }
     if (threads) *threads = b->threads;
     if (vpt) *vpt = b->vpt;
@@ -653,7 +599,7 @@ extern "C" int vxg_upload_state(vxg_batch* b, int robot, const vxg_robot_state* 
 
 extern "C" int vxg_reduce_stats(vxg_batch* b, vxg_robot_stats* out) {
     if (!b || !out) return fail(VXG_ERR_ARG, "vxg_reduce_stats: null argument");
-    int rc = flush(b);
+    int rc = vxg_i_flush(b);
     if (rc) return rc;
     if (b->prec == VXG_PREC_F64) launch_stats_f64(dev_view<double>(b), b->d_stats, b->n_robots, b->stream);
     else launch_stats_f32(dev_view<float>(b), b->d_stats, b->n_robots, b->stream);
@@ -708,58 +654,89 @@ extern "C" int64_t vxg_upload_bytes(vxg_batch* b) {
 
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
+// One process per GPU shares the box's cores with its sibling ranks: LOCAL_WORLD_SIZE (torchrun) divides them, VXG_HOST_THREADS
+// overrides.  (8 ranks x 32 flatten threads on a 32-core box was what held the 1 -> 8 GPU end-to-end curve at 0.84.)
+int vxg_i_host_threads(int cap) {
+    int nt = (int)std::thread::hardware_concurrency();
+    if (nt < 1) nt = 1;
+    if (const char* e = getenv("VXG_HOST_THREADS")) { int v = atoi(e); if (v > 0) nt = v; }
+    else {
+        int ranks = 1;
+        if (const char* w = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(w);
+        if (ranks > 1) nt = std::max(1, nt / ranks);
+    }
+    if (nt > 64) nt = 64;
+    if (cap > 0 && nt > cap) nt = cap;
+    return nt;
+}
+
+bool vxg_i_compact_ok(const vxg_robot_desc* d, int* n_bclass) {
+    RekeyedBonds rk;
+    rekey_bond_classes(d, 65535, rk);
+    if (!rk.ok) return false;
+    std::vector<BondKc<float>> tmp((size_t)std::max(1, rk.desc.n_bclass));
+    double len = 1.0;
+    if (!pack_compact<float>(&rk.desc, tmp.data(), &len)) return false;
+    if (n_bclass) *n_bclass = rk.desc.n_bclass;
+    return true;
+}
+
+int vxg_i_enqueue_positions(vxg_batch* b) {
+    // positions only: first 3*nv doubles of every blob (strided device -> host copy)
+    const size_t w = (size_t)3 * b->L.nv * sizeof(double);
+    CK(cudaMemcpy2DAsync(b->h_blobs, b->L.total_bytes, b->d_blobs, b->L.total_bytes, w, (size_t)b->n_robots, cudaMemcpyDeviceToHost, b->stream));
+    std::fill(b->reset_image.begin(), b->reset_image.end(), 0);
+    CK(cudaMemcpyAsync(b->h_ctl, b->d_ctl, (size_t)b->n_robots * sizeof(RobotCtl), cudaMemcpyDeviceToHost, b->stream));
+    return VXG_OK;
+}
+
+void vxg_i_unpack_positions(const vxg_batch* b, int r, double* o) {   // plane layout -> the caller's [voxel][xyz] rows
+    const int nv = b->L.nv;
+    const double* p = (const double*)(b->h_blobs + (size_t)r * b->L.total_bytes);
+    const int n = b->h_ctl[r].n_vox;
+    for (int i = 0; i < n; i++) { o[3 * i] = p[i]; o[3 * i + 1] = p[nv + i]; o[3 * i + 2] = p[2 * nv + i]; }
+}
+
+// flatten descriptors into the pinned mirrors of slots [0, n) on the host cores (slots are independent)
+static int upload_all(vxg_batch* b, const vxg_robot_desc* descs, int n_descs) {
+    const int nt = vxg_i_host_threads(n_descs);
+    std::vector<int> rcs((size_t)nt, 0);
+    std::vector<std::string> msgs((size_t)nt);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++)
+        th.emplace_back([&, t]() {
+            for (int r = t; r < n_descs; r += nt) {
+                int rc = vxg_upload(b, r, &descs[r]);
+                if (rc) { rcs[t] = rc; msgs[t] = g_err; return; }
+            }
+        });
+    for (auto& x : th) x.join();
+    for (int t = 0; t < nt; t++) if (rcs[t]) { g_err = msgs[t]; return rcs[t]; }
+    return VXG_OK;
+}
+
 extern "C" int vxg_run_batch_host(vxg_batch* b, const vxg_robot_desc* descs, int n_descs, int n_steps, double* pos_out) {
     if (!b || !descs || n_descs != b->n_robots) return fail(VXG_ERR_ARG, "vxg_run_batch_host: need one descriptor per robot slot");
     const bool timing = getenv("VXG_TIMING") != nullptr;
     const double t0 = now_ms();
-    // flatten the descriptors into the pinned mirrors on all host cores (slots are independent)
-    {
-        int nt = (int)std::thread::hardware_concurrency();
-        if (nt < 1) nt = 1;
-        if (nt > 32) nt = 32;
-        if (nt > n_descs) nt = n_descs;
-        std::vector<int> rcs((size_t)nt, 0);
-        std::vector<std::string> msgs((size_t)nt);
-        std::vector<std::thread> th;
-        for (int t = 0; t < nt; t++)
-            th.emplace_back([&, t]() {
-                for (int r = t; r < n_descs; r += nt) {
-                    int rc = vxg_upload(b, r, &descs[r]);
-                    if (rc) { rcs[t] = rc; msgs[t] = g_err; return; }
-                }
-            });
-        for (auto& x : th) x.join();
-        for (int t = 0; t < nt; t++) if (rcs[t]) { g_err = msgs[t]; return rcs[t]; }
-    }
+    int rc = upload_all(b, descs, n_descs);
+    if (rc) return rc;
     const double t1 = now_ms();
-    int rc = vxg_step(b, n_steps);
+    rc = vxg_step(b, n_steps);
     if (rc) return rc;
     if (timing) { cudaStreamSynchronize(b->stream); }
     const double t2 = now_ms();
     if (pos_out) {
-        // positions only: first 3*nv doubles of every blob (strided device -> host copy)
-        size_t w = (size_t)3 * b->L.nv * sizeof(double);
-        CK(cudaMemcpy2DAsync(b->h_blobs, b->L.total_bytes, b->d_blobs, b->L.total_bytes, w, (size_t)b->n_robots, cudaMemcpyDeviceToHost, b->stream));
-        std::fill(b->reset_image.begin(), b->reset_image.end(), 0);
-        CK(cudaMemcpyAsync(b->h_ctl, b->d_ctl, (size_t)b->n_robots * sizeof(RobotCtl), cudaMemcpyDeviceToHost, b->stream));
+        rc = vxg_i_enqueue_positions(b);
+        if (rc) return rc;
         CK(cudaStreamSynchronize(b->stream));
-        const int nv = b->L.nv, mv = b->lim.max_vox;
+        const int mv = b->lim.max_vox;
         for (int r = 0; r < b->n_robots; r++)
             if (b->h_ctl[r].status & VXG_ST_DIVERGED) return fail(VXG_ERR_STATE, "vxg_run_batch_host: robot %d diverged (strain > 100)", r);
-        int nt = (int)std::thread::hardware_concurrency();   // plane layout -> the caller's [voxel][xyz] rows, on all host cores
-        if (nt < 1) nt = 1;
-        if (nt > 16) nt = 16;
-        if (nt > b->n_robots) nt = b->n_robots;
+        const int nt = vxg_i_host_threads(std::min(16, b->n_robots));
         std::vector<std::thread> th;
         for (int t = 0; t < nt; t++)
-            th.emplace_back([&, t]() {
-                for (int r = t; r < b->n_robots; r += nt) {
-                    const double* p = (const double*)(b->h_blobs + (size_t)r * b->L.total_bytes);
-                    double* o = pos_out + (size_t)r * mv * 3;
-                    int n = b->h_ctl[r].n_vox;
-                    for (int i = 0; i < n; i++) { o[3 * i] = p[i]; o[3 * i + 1] = p[nv + i]; o[3 * i + 2] = p[2 * nv + i]; }
-                }
-            });
+            th.emplace_back([&, t]() { for (int r = t; r < b->n_robots; r += nt) vxg_i_unpack_positions(b, r, pos_out + (size_t)r * mv * 3); });
         for (auto& x : th) x.join();
     } else CK(cudaStreamSynchronize(b->stream));
     if (timing) fprintf(stderr, "vxg_run_batch_host: flatten %.2f ms, upload+step %.2f ms, download+unpack %.2f ms\n", t1 - t0, t2 - t1, now_ms() - t2);

@@ -1,0 +1,351 @@
+// vxg_gather.cuh -- the production step kernel in its "gather" form (fp32, compact bond table, one voxel per thread).
+//
+// Same arithmetic as vx_step_kernel<float, NV, 1, true, true> (bond_force / voxel_integrate of vx_math.cuh, same summation
+// order, bit-identical results), different data movement:
+//
+//   * Tensor memory as per-thread scratch.  The damping history of a voxel's three owned bonds (_LastPos2, _LastAngle1,
+//     _LastAngle2: 27 words, half of the robot blob) is read and written by its owner only, so it does not need to be in
+//     shared memory at all: it lives in TMEM (tcgen05.alloc; every warp owns 32 lanes x 32 columns, one column set per
+//     thread) and moves with tcgen05.ld / tcgen05.st (LDTM / STTM), which neither occupy shared-memory bandwidth nor cost
+//     address arithmetic.  That frees 108 B per voxel of shared memory for ...
+//   * ... a staging area for the neighbour's share of every bond (Force1, Moment2 of the owned +X/+Y/+Z bonds, 72 B per voxel):
+//     the -axis neighbour GATHERS them in the voxel phase instead of the owner pushing them into the neighbour's accumulator.
+//     No read-modify-write, no accumulator zeroing, and above all no ordering between the three axes: a timestep has two
+//     CTA-wide barriers (bonds -> voxels, voxels -> bonds, both hardware BAR) instead of four, two of which were mbarrier
+//     waits whose sleep/wake traffic alone was 10 % of all issued instructions (profiles/r01_ncu_step_kernel_*.txt: SYNCS +
+//     NANOSLEEP).
+//   * A voxel's own position, orientation, static word and flags stay in registers from step to step.
+//   * Voxels without a +axis neighbour evaluate a "zero class" bond (all stiffnesses 0, pitch 0: every output is exactly 0), so
+//     the bond phase has no per-lane branch around the warp-collective TMEM operations; warps in which no lane has a bond on an
+//     axis skip it.
+//
+// Replaces CVX_Sim::Integrate (VX_Sim.cpp:1763-1933) for robots of the production family (pack_compact, vx_pack.h).
+#pragma once
+#include "vxg_kernels.cuh"
+
+namespace vx {
+
+// shared-memory image of one robot in the gather kernel (byte offsets; the dynamic part keeps the blob's order so that it
+// stages in and out with two straight copies)
+struct GLayout {
+    size_t off_pos, off_quat, off_momA, off_momB;   // as in the blob: [off_pos, dyn_front) is one contiguous copy
+    size_t dyn_front;                               // bytes of pos .. momB
+    size_t off_stat;                                // VoxStat [nv]
+    size_t off_nbm;                                 // int16 [nv][4]: the -X/-Y/-Z neighbour of each voxel (nv = "none": the zero slot)
+    size_t off_stA[3], off_stB[3];                  // per axis: R4 [nv + 1] (Force1.xyz, Moment2.x), R2 [nv + 1] (Moment2.y, Moment2.z)
+    size_t total;
+};
+VX_HD constexpr GLayout make_glayout(int nv_in) {
+    GLayout G{};
+    const BlobLayout L = make_layout(nv_in, 4);
+    const size_t nv = (size_t)nv_in;
+    G.off_pos = L.off_pos; G.off_quat = L.off_quat; G.off_momA = L.off_momA; G.off_momB = L.off_momB;
+    G.dyn_front = L.off_hist;
+    size_t o = G.dyn_front;
+    G.off_stat = o; o = vx_align32(o + nv * sizeof(VoxStat));
+    G.off_nbm = o;  o = vx_align32(o + nv * 8);
+    for (int a = 0; a < 3; a++) {
+        G.off_stA[a] = o; o = vx_align32(o + (nv + 1) * 16);
+        G.off_stB[a] = o; o = vx_align32(o + (nv + 1) * 8);
+    }
+    G.total = o;
+    return G;
+}
+
+// ---- tensor memory as scratch: 32 lanes x 32 columns per warp, lane = thread, columns = that thread's words -----------------
+#define VXG_TM_COLS_PER_WARP 32
+__device__ inline void tm_ld8(uint32_t taddr, float (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(taddr) : "memory");
+}
+__device__ inline void tm_ld1(uint32_t taddr, float& v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=f"(v) : "r"(taddr) : "memory");
+}
+__device__ inline void tm_st8(uint32_t taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+__device__ inline void tm_st1(uint32_t taddr, float v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "f"(v) : "memory");
+}
+__device__ inline void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ inline void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// columns a CTA of `threads` threads needs: its warps share the four 32-lane quarters, each warp gets its own 32 columns
+__host__ __device__ constexpr int tm_cols_for(int threads) {
+    const int per_quarter = ((threads + 31) / 32 + 3) / 4;
+    const int need = per_quarter * VXG_TM_COLS_PER_WARP;
+    return need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
+}
+
+// history words of the bond on axis AX of this thread's voxel: columns [8 AX, 8 AX + 8) and 24 + AX
+template <int AX> __device__ inline void hist_load(uint32_t tm, BondHist<float>& h) {
+    float a[8], c;
+    tm_ld8(tm + 8 * AX, a);
+    tm_ld1(tm + 24 + AX, c);
+    tm_wait_ld();
+    h.p2 = mk3<float>(a[0], a[1], a[2]); h.a1 = mk3<float>(a[3], a[4], a[5]); h.a2 = mk3<float>(a[6], a[7], c);
+}
+template <int AX> __device__ inline void hist_store(uint32_t tm, const BondHist<float>& h) {
+    const float a[8] = {h.p2.x, h.p2.y, h.p2.z, h.a1.x, h.a1.y, h.a1.z, h.a2.x, h.a2.y};
+    tm_st8(tm + 8 * AX, a);
+    tm_st1(tm + 24 + AX, h.a2.z);
+}
+
+// One owned bond in the gather form.  `st` carries the zero class for a missing neighbour (patched once per launch), so every
+// lane runs the same code; the warp skips the axis when none of its lanes has a bond there.
+template <int AX>
+__device__ __forceinline__ bool bond_eval_g(unsigned char* smem, const GLayout& G, int NV, const RobotConsts<float>& C, int tid, const VoxStat& st,
+                                            const OwnState<float>& own, uint32_t& fl, float dt_inv, uint32_t tm, V3<float>& F, V3<float>& M) {
+    const int w = st.nbr[AX];
+    if (!__any_sync(0xffffffffu, w >= 0)) return false;
+    const int wq = w >= 0 ? w : tid;
+    const int bc = st.bcls[AX];
+    BondHist<float> h;
+    hist_load<AX>(tm, h);
+    const BondKc<float> kc = C.bkc[bc];
+    const BondK<float> k = expand_bond<float>(kc, C.geo);
+    const double* pos = (const double*)(smem + G.off_pos);
+    double dpa[3] = {pos[wq] - own.px, pos[NV + wq] - own.py, pos[2 * NV + wq] - own.pz};
+    dpa[AX] -= C.bk_dist[bc];
+    const V3<float> e = mk3<float>((float)dpa[0], (float)dpa[1], (float)dpa[2]);
+    const R4<float> qa = own.q, qb = ((const R4<float>*)(smem + G.off_quat))[wq];
+    Q4<float> q1, q2;
+    q1.w = qa.x; q1.x = qa.y; q1.y = qa.z; q1.z = qa.w;
+    q2.w = qb.x; q2.x = qb.y; q2.y = qb.z; q2.z = qb.w;
+    bool small = (fl >> AX) & 1u;
+    BondOut<float> o;
+    bond_force<AX, float, true>(k, e, q1, q2, C.dnom_bc[bc], C.half_bond_z, dt_inv, true, small, h, o);
+    // _LastPos2/_LastAngle* keep their values on a mode-flip step (VXS_BondInternal.cpp:157): rare, so the old values are
+    // fetched again (they are still in tensor memory) behind a warp-uniform test instead of being kept in registers
+    if (__any_sync(0xffffffffu, o.changed)) { BondHist<float> old; hist_load<AX>(tm, old); if (o.changed) h = old; }
+    hist_store<AX>(tm, h);
+    fl = (fl & ~(1u << AX)) | ((small ? 1u : 0u) << AX);
+    F = F + o.f1; M = M + o.m1;
+    R4<float> a; a.x = o.f1.x; a.y = o.f1.y; a.z = o.f1.z; a.w = o.m2.x;
+    R2<float> b; b.x = o.m2.y; b.y = o.m2.z;
+    ((R4<float>*)(smem + G.off_stA[AX]))[tid] = a;
+    ((R2<float>*)(smem + G.off_stB[AX]))[tid] = b;
+    return o.strain > 100.0f;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, false, false)) vx_step_kernel_g(BatchDev<float> B, int n_steps) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int T = NV;
+    constexpr BlobLayout L = make_layout(NV, 4);
+    constexpr GLayout G = make_glayout(NV);
+    constexpr int TM_COLS = tm_cols_for(NV);
+    const int robot = blockIdx.x;
+    int tid;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    RobotCtl* ctlp = B.ctl + robot;
+    const unsigned int status0 = ctlp->status;
+    if (status0 & (VXG_ST_DIVERGED_ | VXG_ST_FINISHED_)) return;
+    const long long step0 = ctlp->step, total = ctlp->total_steps, latch = ctlp->latch_step, eol = ctlp->eol_step;
+    long long remaining = total - step0;
+    int nsteps = remaining < (long long)n_steps ? (int)remaining : n_steps;
+    if (nsteps <= 0) { if (tid == 0) ctlp->status = status0 | VXG_ST_FINISHED_; return; }
+
+    unsigned char* gblob = B.blobs + (size_t)robot * L.total_bytes;
+    const int MB = B.max_bclass + 1;   // one more bond class than the batch's limit: the zero class
+    SmemTables<float> S = carve_tables<float>(smem + G.total, B.max_vclass, MB, true, 0);
+    const int n_vox = ctlp->n_vox, n_vc = ctlp->n_vclass, n_bc = ctlp->n_bclass;
+    const unsigned int flags = ctlp->flags;
+    const int ZC = n_bc;               // index of the zero class
+
+    // ---- tensor memory -------------------------------------------------------------------------------------------------
+    uint32_t* tm_slot = (uint32_t*)S.red;   // the reduction scratch is idle until the first latch
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tm_slot)), "n"(TM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // ---- stage in ------------------------------------------------------------------------------------------------------
+    copy16(smem, gblob, G.dyn_front, tid, T);
+    copy16(smem + G.off_stat, gblob + L.off_stat, (size_t)NV * sizeof(VoxStat), tid, T);
+    {
+        uint2 none; none.x = none.y = (uint32_t)NV | ((uint32_t)NV << 16);
+        ((uint2*)(smem + G.off_nbm))[tid] = none;
+        if (tid == 0) {
+            R4<float> za; za.x = za.y = za.z = za.w = 0.0f; R2<float> zb; zb.x = zb.y = 0.0f;
+#pragma unroll
+            for (int a = 0; a < 3; a++) { ((R4<float>*)(smem + G.off_stA[a]))[NV] = za; ((R2<float>*)(smem + G.off_stB[a]))[NV] = zb; }
+        }
+    }
+    copy4(S.bk, B.bk + (size_t)robot * B.max_bclass * sizeof(BondKc<float>), sizeof(BondKc<float>) * n_bc, tid, T);
+    copy4(S.vk, B.vk + (size_t)robot * B.max_vclass, sizeof(VoxK<float>) * n_vc, tid, T);
+    copy4(S.sk, B.sk + (size_t)robot * B.max_vclass, sizeof(ScaleK) * n_vc, tid, T);
+    for (int i = tid; i < n_bc; i += T) { S.bk_dist[i] = B.bk_dist[(size_t)robot * B.max_bclass + i]; S.bpair[i] = B.bpair[(size_t)robot * B.max_bclass + i]; }
+    for (int i = tid; i < n_vc; i += T) S.scale_c[i] = B.scale_c[(size_t)robot * B.max_vclass + i];
+    if (tid < (int)(sizeof(BondKc<float>) / 4)) ((uint32_t*)((BondKc<float>*)S.bk + ZC))[tid] = 0u;
+    if (tid == 0) { S.bk_dist[ZC] = 0.0; S.dnom_bc[ZC] = 0.0f; S.dnom_bc[MB + ZC] = 0.0f; }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tm = *tm_slot + ((uint32_t)((tid >> 5) & 3) << 21) + (uint32_t)(tid >> 7) * VXG_TM_COLS_PER_WARP;   // lane (warp % 4) * 32, this warp's columns
+    for (int i = tid; i < n_vc; i += T) S.dsc_c[i] = (float)(S.scale_c[i] - S.sk[i].nom_size);
+    // own static word (zero class for the missing bonds), own state, and the -axis neighbour table
+    VoxStat st = ((const VoxStat*)(smem + G.off_stat))[tid];
+    if (tid >= n_vox) st.nbr[0] = st.nbr[1] = st.nbr[2] = -1;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        if (st.nbr[a] < 0) st.bcls[a] = (uint16_t)ZC;
+        else ((int16_t*)(smem + G.off_nbm))[4 * st.nbr[a] + a] = (int16_t)tid;
+    }
+    uint32_t fl = ((const uint32_t*)(gblob + L.off_flags))[tid];
+    {   // damping history: blob -> this thread's tensor-memory columns
+        const RobotView<float> Rg = make_view<float>(gblob, L, n_vox);
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const R4<float> x = Rg.histA(a)[tid], y = Rg.histB(a)[tid]; const float z = Rg.histC(a)[tid];
+            BondHist<float> h; h.p2 = mk3<float>(x.x, x.y, x.z); h.a1 = mk3<float>(x.w, y.x, y.y); h.a2 = mk3<float>(y.z, y.w, z);
+            if (a == 0) hist_store<0>(tm, h); else if (a == 1) hist_store<1>(tm, h); else hist_store<2>(tm, h);
+        }
+        tm_wait_st();
+    }
+    __syncthreads();
+    for (int i = tid; i < n_bc; i += T) { const uint32_t pr = S.bpair[i]; S.dnom_bc[i] = 0.5f * (S.dsc_c[pr & 0xFFFFu] + S.dsc_c[pr >> 16]); }
+
+    RobotView<float> R = make_view<float>(smem, L, n_vox);   // pos / quat / momA / momB views are valid (same offsets as the blob)
+    R.stat = (VoxStat*)(smem + G.off_stat);
+    RobotConsts<float> C;
+    C.bk = nullptr; C.bkc = (const BondKc<float>*)S.bk;
+    C.geo = make_geo<float>(ctlp->bond_len);
+    C.bk_dist = S.bk_dist; C.vk = S.vk;
+    C.nom = nullptr; C.ext_disp = S.ext_disp; C.ext_tdisp = S.ext_tdisp;
+    C.half_bond_z = (float)ctlp->half_bond_z;
+    const double dt = ctlp->dt;
+    C.dt = (float)dt;
+    C.fluid = false; C.drag_coeff = 0.0f; C.n_vert = 0; C.n_facet = 0;
+    C.floor_on = (flags & VXG_F_FLOOR_) != 0;
+    C.sticky = false; C.sym_mass = true;
+    if (tid == 0) {
+        ScaleSim SL;
+        SL.init_cm_time = ctlp->init_cm_time; SL.temp_period = ctlp->temp_period; SL.temp_amplitude = ctlp->temp_amplitude;
+        SL.min_fact = ctlp->min_fact; SL.max_fact = ctlp->max_fact; SL.growth_amp = ctlp->growth_amp;
+        SL.midlife_freeze = ctlp->midlife_freeze; SL.stop_value = ctlp->stop_value;
+        SL.temp_on = (flags & VXG_F_TEMPERATURE_) != 0; SL.lw = (flags & VXG_F_LW_SCALE_) != 0;
+        *S.sl = SL;
+    }
+    OwnState<float> own = load_own<float>(R, tid);
+    __syncthreads();
+    const uint2 nb = ((const uint2*)(smem + G.off_nbm))[tid];   // -X | -Y << 16, -Z
+    const float dt_inv_run = (float)(1.0 / dt);
+
+    double t = ctlp->cur_time;
+    int cur = 0, done = 0;
+    bool diverged = false;
+    for (int k = 0; k < nsteps; ++k) {
+        const long long s = step0 + k;
+        if (s == latch) {   // IniCM = SS.CurCM at TimeStep entry (VX_Sim.cpp:1064-1075): COM after the previous step
+            double mx = 0, my = 0, mz = 0, mm = 0;
+            if (tid < n_vox) { const double m = (double)S.vk[st.vcls].mass; mx = own.px * m; my = own.py * m; mz = own.pz * m; mm = m; }
+            block_sum4(mx, my, mz, mm, S.red);
+            if (tid == 0) { ctlp->ini_com[0] = mx / mm; ctlp->ini_com[1] = my / mm; ctlp->ini_com[2] = mz / mm; ctlp->ini_latched = 1; }
+        }
+        if (s == eol) {     // SS.EndOfLifetimePosteriorY = getPosteriorY() at TimeStep entry (VX_Sim.cpp:1078-1082)
+            double lo = 1e300;
+            if (tid < n_vox && S.sk[st.vcls].mat_index != 5) lo = own.py;
+            lo = -warp_max(-lo);
+            __syncthreads();
+            if ((tid & 31) == 0) S.red[tid >> 5] = lo;
+            __syncthreads();
+            if (tid == 0) { for (int i = 1; i < T / 32; i++) lo = fmin(lo, S.red[i]); ctlp->eol_post_y = lo; }
+        }
+        C.scale_c = S.scale_c + cur * B.max_vclass;
+        C.dsc_c = S.dsc_c + cur * B.max_vclass;
+        C.dnom_bc = S.dnom_bc + cur * MB;
+        const float dt_inv = (s == 0) ? 0.0f : dt_inv_run;   // dt == 0 during the very first bond pass (VX_Sim.cpp:373)
+
+        // Scale of every class for the NEXT step (VXS_Voxel.cpp:224-336), by the highest threads, into the other buffer half
+        for (int i = T - 1 - tid; i < n_vc; i += T) {
+            const double last = S.scale_c[cur * B.max_vclass + i];
+            const double ns = scale_law(S.sk[i], last, t, *S.sl);
+            S.scale_c[(cur ^ 1) * B.max_vclass + i] = ns;
+            S.dsc_c[(cur ^ 1) * B.max_vclass + i] = (float)(ns - S.sk[i].nom_size);
+        }
+        // ---- bond phase: reads positions / orientations of the previous step, writes only what this thread owns --------------
+        V3<float> F = mk3<float>(0, 0, 0), M = mk3<float>(0, 0, 0);
+        int div = 0;
+        div |= bond_eval_g<0>(smem, G, NV, C, tid, st, own, fl, dt_inv, tm, F, M) ? 1 : 0;
+        div |= bond_eval_g<1>(smem, G, NV, C, tid, st, own, fl, dt_inv, tm, F, M) ? 1 : 0;
+        div |= bond_eval_g<2>(smem, G, NV, C, tid, st, own, fl, dt_inv, tm, F, M) ? 1 : 0;
+        tm_wait_st();
+        if (__syncthreads_or(div)) { diverged = true; break; }   // Integrate() returns before the voxel loop (VX_Sim.cpp:1777)
+
+        // rest-length deviation of every bond class for the NEXT step
+        for (int i = tid; i < n_bc; i += T) {
+            const uint32_t pr = S.bpair[i];
+            const float* dn = S.dsc_c + (cur ^ 1) * B.max_vclass;
+            S.dnom_bc[(cur ^ 1) * MB + i] = 0.5f * (dn[pr & 0xFFFFu] + dn[pr >> 16]);
+        }
+        // ---- voxel phase: gather the shares of the -X/-Y/-Z bonds (Force2 = -Force1, Moment2), integrate -------------------
+        if (tid < n_vox) {
+            const int mX = nb.x & 0xFFFFu, mY = nb.x >> 16, mZ = nb.y & 0xFFFFu;
+            const R4<float> ax = ((const R4<float>*)(smem + G.off_stA[0]))[mX], ay = ((const R4<float>*)(smem + G.off_stA[1]))[mY], az = ((const R4<float>*)(smem + G.off_stA[2]))[mZ];
+            const R2<float> bx = ((const R2<float>*)(smem + G.off_stB[0]))[mX], by = ((const R2<float>*)(smem + G.off_stB[1]))[mY], bz = ((const R2<float>*)(smem + G.off_stB[2]))[mZ];
+            // the accumulator of the push form received -Force1 of the X, Y, Z bond in that order, starting from zero
+            F = F + mk3<float>(((0.0f - ax.x) - ay.x) - az.x, ((0.0f - ax.y) - ay.y) - az.y, ((0.0f - ax.z) - ay.z) - az.z);
+            M = M + mk3<float>(((0.0f + ax.w) + ay.w) + az.w, ((0.0f + bx.x) + by.x) + bz.x, ((0.0f + bx.y) + by.y) + bz.y);
+            const int vc = st.vcls;
+            const VoxK<float> kv = C.vk[vc];
+            VoxState<float> vs;
+            vs.px = own.px; vs.py = own.py; vs.pz = own.pz;
+            const R4<float> ma = R.momA[tid]; const R2<float> mb = R.momB[tid];
+            vs.q.w = own.q.x; vs.q.x = own.q.y; vs.q.y = own.q.z; vs.q.z = own.q.w;
+            vs.lm = mk3<float>(ma.x, ma.y, ma.z);
+            vs.am = mk3<float>(ma.w, mb.x, mb.y);
+            const bool sf = voxel_integrate<float, false>(kv, F, M, 0.5 * C.scale_c[vc], C.floor_on, false, C.dt, nullptr, nullptr, nullptr, vs);
+            own.px = vs.px; own.py = vs.py; own.pz = vs.pz;
+            own.q.x = vs.q.w; own.q.y = vs.q.x; own.q.z = vs.q.y; own.q.w = vs.q.z;
+            R.pos[tid] = vs.px; R.pos[NV + tid] = vs.py; R.pos[2 * NV + tid] = vs.pz;
+            R.quat[tid] = own.q;
+            R4<float> na; na.x = vs.lm.x; na.y = vs.lm.y; na.z = vs.lm.z; na.w = vs.am.x;
+            R2<float> nb2; nb2.x = vs.am.y; nb2.y = vs.am.z;
+            R.momA[tid] = na; R.momB[tid] = nb2;
+            fl = sf ? (fl | VX_FL_STATIC_FRIC) : (fl & ~VX_FL_STATIC_FRIC);
+        }
+        __syncthreads();
+        cur ^= 1;
+        t += dt;                                                 // CurTime += dt (VX_Sim.cpp:1929)
+        done = k + 1;
+    }
+
+    // ---- stage out -------------------------------------------------------------------------------------------------------
+    __syncthreads();
+    copy16(gblob, smem, G.dyn_front, tid, T);
+    if (tid < n_vox) ((uint32_t*)(gblob + L.off_flags))[tid] = fl;
+    {
+        const RobotView<float> Rg = make_view<float>(gblob, L, n_vox);
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            BondHist<float> h;
+            if (a == 0) hist_load<0>(tm, h); else if (a == 1) hist_load<1>(tm, h); else hist_load<2>(tm, h);
+            if (st.nbr[a] >= 0) {   // slots of bonds that do not exist were never touched
+                R4<float> x, y;
+                x.x = h.p2.x; x.y = h.p2.y; x.z = h.p2.z; x.w = h.a1.x;
+                y.x = h.a1.y; y.y = h.a1.z; y.z = h.a2.x; y.w = h.a2.y;
+                Rg.histA(a)[tid] = x; Rg.histB(a)[tid] = y; Rg.histC(a)[tid] = h.a2.z;
+            }
+        }
+    }
+    for (int i = tid; i < n_vc; i += T) B.scale_c[(size_t)robot * B.max_vclass + i] = S.scale_c[cur * B.max_vclass + i];
+    if (tid == 0) {
+        ctlp->cur_time = t;
+        ctlp->step = step0 + done;
+        unsigned int st2 = status0;
+        if (diverged) st2 |= VXG_ST_DIVERGED_;
+        if (step0 + done >= total) st2 |= VXG_ST_FINISHED_;
+        ctlp->status = st2;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    // warp 0's own address IS the allocation's base (lane quarter 0, column block 0); the slot it was published through has been
+    // reused as reduction scratch since
+    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "n"(TM_COLS) : "memory");
+}
+
+inline size_t gather_smem_bytes(int nv, int max_vclass, int max_bclass) {
+    return make_glayout(nv).total + tables_bytes<float>(max_vclass, max_bclass + 1, true, 0);
+}
+
+}  // namespace vx

@@ -87,6 +87,24 @@ def lib():
         L.vxh_step_plan_ex.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double)]
         L.vxh_format_result.argtypes = [vp, C.POINTER(abi.RobotStats), C.c_char_p, C.c_int, C.c_char_p]
         L.vxg_set_eol_step.argtypes = [vp, C.POINTER(C.c_int64)]
+        i64p, i32p = C.POINTER(C.c_int64), C.POINTER(C.c_int32)
+        L.vxg_pop_create.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(abi.RobotDesc), C.c_int, C.POINTER(abi.PopOptions)]
+        L.vxg_pop_destroy.argtypes = [vp]
+        L.vxg_pop_destroy.restype = None
+        L.vxg_pop_upload.argtypes = [vp, C.POINTER(abi.RobotDesc)]
+        L.vxg_pop_set_plan.argtypes = [vp, i64p, i64p, i64p]
+        L.vxg_pop_step.argtypes = [vp, C.c_int64]
+        L.vxg_pop_run.argtypes = [vp]
+        L.vxg_pop_sync.argtypes = [vp, C.POINTER(C.c_uint32)]
+        L.vxg_pop_reduce_stats.argtypes = [vp, C.POINTER(abi.RobotStats)]
+        L.vxg_pop_download_state.argtypes = [vp, C.c_int, C.POINTER(abi.RobotState)]
+        L.vxg_pop_run_host.argtypes = [vp, C.POINTER(abi.RobotDesc), C.c_int, abi.c_double_p, C.c_int]
+        L.vxg_pop_n_batches.argtypes = [vp]
+        L.vxg_pop_batch_info.argtypes = [vp, C.c_int, i32p, i32p, i32p, i32p]
+        L.vxg_pop_locate.argtypes = [vp, C.c_int, i32p, i32p]
+        for f in ("vxg_pop_launch_count", "vxg_pop_upload_bytes", "vxg_pop_download_bytes"):
+            getattr(L, f).argtypes = [vp]
+            getattr(L, f).restype = C.c_int64
         _LIB = L
     return _LIB
 
@@ -288,6 +306,107 @@ class Batch:
     def close(self):
         if self.h:
             lib().vxg_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Population:
+    """A ragged population on one GPU (``vxg_population``): robots of any mix of sizes and features, bucketed by the library
+    into homogeneous batches that run concurrently.  Robot indices are positions in ``robots``."""
+
+    def __init__(self, robots: Sequence[abi.HostRobot], device: int = 0, precision: int = abi.VXG_PREC_F32, chunk_robots: int = 0,
+                 want_mesh: bool = False, col_pairs_per_vox: int = 0):
+        self.robots: List[abi.HostRobot] = list(robots)
+        if not self.robots:
+            raise ValueError("empty population")
+        self._descs = (abi.RobotDesc * len(self.robots))(*[r.desc() for r in self.robots])
+        opt = abi.PopOptions()
+        opt.precision, opt.chunk_robots, opt.want_mesh, opt.col_pairs_per_vox = precision, chunk_robots, int(want_mesh), col_pairs_per_vox
+        self.h = C.c_void_p()
+        _ck(lib().vxg_pop_create(C.byref(self.h), device, self._descs, len(self.robots), C.byref(opt)))
+        self.max_vox = max(r.n_vox for r in self.robots)
+
+    @property
+    def n_robots(self) -> int:
+        return len(self.robots)
+
+    def upload(self):
+        _ck(lib().vxg_pop_upload(self.h, self._descs))
+
+    def set_plan(self, total_steps=None, latch_step=None, eol_step=None):
+        keep = []
+
+        def arr(x):
+            if x is None:
+                return None
+            a = np.ascontiguousarray(x, dtype=np.int64)
+            assert a.shape == (self.n_robots,)
+            keep.append(a)
+            return a.ctypes.data_as(C.POINTER(C.c_int64))
+        _ck(lib().vxg_pop_set_plan(self.h, arr(total_steps), arr(latch_step), arr(eol_step)))
+
+    def step(self, n: int):
+        _ck(lib().vxg_pop_step(self.h, int(n)))
+
+    def run(self):
+        _ck(lib().vxg_pop_run(self.h))
+
+    def sync(self) -> np.ndarray:
+        st = np.zeros(self.n_robots, dtype=np.uint32)
+        _ck(lib().vxg_pop_sync(self.h, st.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return st
+
+    def stats(self):
+        out = (abi.RobotStats * self.n_robots)()
+        _ck(lib().vxg_pop_reduce_stats(self.h, out))
+        return out
+
+    def download(self, robot: int) -> abi.StateBuffers:
+        r = self.robots[robot]
+        buf = abi.StateBuffers(r.n_vox, r.n_bond)
+        v = buf.view()
+        v.bond_force1 = v.bond_force2 = v.bond_moment1 = v.bond_moment2 = v.bond_strain = None
+        _ck(lib().vxg_pop_download_state(self.h, robot, C.byref(v)))
+        return buf
+
+    def run_host(self, n_steps: int, pos_out: Optional[np.ndarray] = None) -> np.ndarray:
+        """End-to-end call with host buffers: flatten + upload every descriptor, step, positions back (pipelined per batch)."""
+        if pos_out is None:
+            pos_out = np.zeros((self.n_robots, self.max_vox, 3))
+        _ck(lib().vxg_pop_run_host(self.h, self._descs, int(n_steps), pos_out.ctypes.data_as(abi.c_double_p), pos_out.shape[1]))
+        return pos_out
+
+    def batches(self):
+        """[(n_robots, stride, threads, family bits)] of the homogeneous batches the population was bucketed into."""
+        out = []
+        for i in range(lib().vxg_pop_n_batches(self.h)):
+            n, s, t, f = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+            _ck(lib().vxg_pop_batch_info(self.h, i, C.byref(n), C.byref(s), C.byref(t), C.byref(f)))
+            out.append((n.value, s.value, t.value, f.value))
+        return out
+
+    def locate(self, robot: int):
+        b, s = C.c_int32(), C.c_int32()
+        _ck(lib().vxg_pop_locate(self.h, robot, C.byref(b), C.byref(s)))
+        return b.value, s.value
+
+    def launch_count(self) -> int:
+        return int(lib().vxg_pop_launch_count(self.h))
+
+    def h2d_bytes(self) -> int:
+        return int(lib().vxg_pop_upload_bytes(self.h))
+
+    def d2h_bytes(self) -> int:
+        return int(lib().vxg_pop_download_bytes(self.h))
+
+    def close(self):
+        if self.h:
+            lib().vxg_pop_destroy(self.h)
             self.h = C.c_void_p()
 
     def __del__(self):

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define VXG_ABI_VERSION 3   /* 3: development fields in vxg_vox_class / vxg_sim_params, vxg_robot_state.vox_strain, vxg_robot_stats.mesh_volume */
+#define VXG_ABI_VERSION 4   /* 4: vxg_pop_* (ragged populations); 3: development fields, vxg_robot_state.vox_strain, vxg_robot_stats.mesh_volume */
 
 /* ---- return codes ------------------------------------------------------------------------------ */
 enum {
@@ -315,6 +315,47 @@ int vxg_run_batch_host(vxg_batch* b, const vxg_robot_desc* descs, int n_descs, i
 int vxg_mesh_vertex_count(const vxg_robot_desc* desc);
 /* Bytes one full population upload copies host -> device (for the benchmark's h2d accounting). */
 int64_t vxg_upload_bytes(vxg_batch* b);
+
+/* ---- ragged populations ---------------------------------------------------------------------------------------------------
+ * Replaces evosoro's fan-out of one `voxelyze` process per individual (evosoro/tools/evaluation.py:89-90) for a population whose
+ * members differ in size and features.  The robots are bucketed by what the kernels specialise on (voxel stride, self-collision,
+ * surface mesh, production / wide kernel family, class-table size); every bucket is a vxg_batch of its own on its own stream, so
+ * the buckets' grids run concurrently and no robot pays for the largest member's stride or the most general member's family.
+ * Results are bit-identical to running each robot alone.  Robot indices below are positions in the `descs` array. */
+typedef struct vxg_population vxg_population;
+typedef struct vxg_pop_options {
+    int32_t precision;          /* VXG_PREC_*                                                                                  */
+    int32_t chunk_robots;       /* > 0: buckets are cut into batches of at most this many robots -- the granularity at which
+                                   vxg_pop_run_host pipelines flatten / upload / simulate / download; 0 = one batch per bucket */
+    int32_t want_mesh;          /* 1: surface-mesh tables for every VXG_F_LW_SCALE robot, not only the VXG_F_FLUID ones (the
+                                   land/water result file reports RobotVolumeEnd for all of them)                               */
+    int32_t col_pairs_per_vox;  /* contact-bond capacity of a self-colliding robot = this x n_vox (at least 512); 0 = 4         */
+    int32_t reserved[4];
+} vxg_pop_options;
+#define VXG_FAM_COMPACT 0x1  /* production family (compact bond table, gather form) */
+#define VXG_FAM_COLLIDE 0x2
+#define VXG_FAM_MESH    0x4
+int vxg_pop_create(vxg_population** out, int device, const vxg_robot_desc* descs, int n_robots, const vxg_pop_options* opt);
+void vxg_pop_destroy(vxg_population* p);
+/* Reset every robot from its descriptor (same array shape as at create; ResetSimulation for the whole population). */
+int vxg_pop_upload(vxg_population* p, const vxg_robot_desc* descs);
+/* vxg_set_step_budget + vxg_set_eol_step with population indices; any pointer may be NULL. */
+int vxg_pop_set_plan(vxg_population* p, const int64_t* total_steps, const int64_t* latch_step, const int64_t* eol_step);
+int vxg_pop_step(vxg_population* p, int64_t n_steps);   /* asynchronous; batches whose robots have all finished are skipped */
+int vxg_pop_run(vxg_population* p);                     /* to the end of every robot's budget (asynchronous)                */
+int vxg_pop_sync(vxg_population* p, uint32_t* status_per_robot);
+int vxg_pop_reduce_stats(vxg_population* p, vxg_robot_stats* out);
+int vxg_pop_download_state(vxg_population* p, int robot, vxg_robot_state* out);
+/* Host-buffer end-to-end call (what bench.py's `e2e` times): flatten + upload every descriptor, n_steps, positions of robot r into
+ * pos_out[r][pos_stride_vox][3]; pipelined over the population's batches. */
+int vxg_pop_run_host(vxg_population* p, const vxg_robot_desc* descs, int n_steps, double* pos_out, int pos_stride_vox);
+/* introspection */
+int vxg_pop_n_batches(const vxg_population* p);
+int vxg_pop_batch_info(vxg_population* p, int batch, int32_t* n_robots, int32_t* stride, int32_t* threads, int32_t* family);
+int vxg_pop_locate(const vxg_population* p, int robot, int32_t* batch, int32_t* slot);
+int64_t vxg_pop_launch_count(const vxg_population* p);
+int64_t vxg_pop_upload_bytes(const vxg_population* p);    /* host -> device bytes of one whole-population upload */
+int64_t vxg_pop_download_bytes(const vxg_population* p);  /* device -> host bytes of one vxg_pop_run_host        */
 
 #ifdef __cplusplus
 }
