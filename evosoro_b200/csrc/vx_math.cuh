@@ -173,6 +173,25 @@ template <typename T> VX_HD Q4<T> qmul(Q4<T> a, Q4<T> f) {
     return r;
 }
 
+// The same products when one factor has no x component (FromAngleToPosX's result, Vec3D.h:208-237): the terms dropped are
+// exact zeros, so the results are those of qmul bit for bit.
+template <typename T> VX_HD Q4<T> qmul_x0_left(Q4<T> a, Q4<T> f) {    // a.x == 0
+    Q4<T> r;
+    r.w = a.w * f.w - a.y * f.y - a.z * f.z;
+    r.x = a.w * f.x + a.y * f.z - a.z * f.y;
+    r.y = a.w * f.y + a.y * f.w + a.z * f.x;
+    r.z = a.w * f.z - a.y * f.x + a.z * f.w;
+    return r;
+}
+template <typename T> VX_HD Q4<T> qmul_x0_right(Q4<T> a, Q4<T> f) {   // f.x == 0
+    Q4<T> r;
+    r.w = a.w * f.w - a.y * f.y - a.z * f.z;
+    r.x = a.x * f.w + a.y * f.z - a.z * f.y;
+    r.y = a.w * f.y - a.x * f.z + a.y * f.w;
+    r.z = a.w * f.z + a.x * f.y + a.z * f.w;
+    return r;
+}
+
 // CQuat::ToRotationVector (Vec3D.h:270-285) in cancellation-free form: the vector part scaled by
 // 2 sqrt(2/(1+w)) (sqrt branch) or 2 atan2(|v|, w)/|v| (acos branch); zero when the vector part is zero or
 // |w| >= 1.  The acos branch (relative rotation above ~5.6 degrees) is rare and kept out of line.
@@ -308,7 +327,10 @@ template <typename T> struct BondHist {  // _LastPos2, _LastAngle1, _LastAngle2 
 //              palettes): Force2 == -Force1 exactly, so its evaluation and rotation are skipped (robot-uniform flag)
 //   SYM      : the same known at compile time (production family: pack_compact admits such robots only), so the voxel-2
 //              constants are never expanded and Moment2 shares the voxel-1 damping terms
-template <int AX, typename T, bool SYM = false>
+//   HOIST    : take the rotation vector of Angle2 out of the mode branch (one evaluation for a warp whose lanes are in both modes
+//              instead of one per mode).  Pays where the kernel has registers to spare (+1.4 % at 72 registers, 6^3); at the
+//              64-register cap of the 1024-thread kernels the longer live ranges cost more than the instructions saved (-3 %).
+template <int AX, typename T, bool SYM = false, bool HOIST = true>
 VX_HD void bond_force(const BondK<T>& k, V3<T> e_w, Q4<T> q1w, Q4<T> q2w, T dnom, T half_bond_z, T dt_inv, bool sym_mass_rt,
                       bool& small, BondHist<T>& hist, BondOut<T>& out) {
     const bool sym_mass = SYM || sym_mass_rt;
@@ -341,12 +363,15 @@ VX_HD void bond_force(const BondK<T>& k, V3<T> e_w, Q4<T> q1w, Q4<T> q2w, T dnom
     const bool changed = to_small | to_large;
     small = (small | to_small) & !to_large;
 
+    V3<T> p2, an1, an2;
+    Q4<T> back;                               // conj(TotalRot): local -> world rotation
+    if (HOIST) {
     // The two modes differ in WHICH quaternion Angle2 is taken from and in Pos2 / Angle1 / the frame; what is then done with
     // them is the same.  Only the mode-specific part sits inside the branch, so a warp whose lanes are in both modes (most warps of
     // an actuated robot) issues the shared part -- the rotation vector of Angle2 -- once, not once per mode.
-    V3<T> p2 = mk3<T>(rr.x - nomrel, rr.y, rr.z), an1 = mk3<T>(0, 0, 0);   // small angle, :87-95
+    p2 = mk3<T>(rr.x - nomrel, rr.y, rr.z); an1 = mk3<T>(0, 0, 0);   // small angle, :87-95
     Q4<T> a2q = q12;
-    Q4<T> back = q1;                          // conj(TotalRot): local -> world rotation
+    back = q1;
     if (!small) {                             // :101-118
         Q4<T> pa = from_angle_to_posx(mk3<T>(rx, rr.y, rr.z));
         // |dp| - pitch without cancellation
@@ -354,11 +379,26 @@ VX_HD void bond_force(const BondK<T>& k, V3<T> e_w, Q4<T> q1w, Q4<T> q2w, T dnom
         T len = vx_fsqrt(D * D + d2);
         p2 = mk3<T>(d2 * vx_rcp(len + D) - nomrel, 0, 0);
         an1 = rotvec(pa);
-        a2q = qmul(pa, q12);                  // (pa * conj(q1)) * q2
-        Q4<T> cpa; cpa.w = pa.w; cpa.x = -pa.x; cpa.y = -pa.y; cpa.z = -pa.z;
-        back = qmul(q1, cpa);                 // conj(pa * conj(q1))
+        a2q = qmul_x0_left(pa, q12);          // (pa * conj(q1)) * q2
+        Q4<T> cpa; cpa.w = pa.w; cpa.x = (T)0; cpa.y = -pa.y; cpa.z = -pa.z;
+        back = qmul_x0_right(q1, cpa);        // conj(pa * conj(q1))
     }
-    const V3<T> an2 = rotvec(a2q);
+    an2 = rotvec(a2q);
+    } else if (small) {                       // :87-95
+        an1 = mk3<T>(0, 0, 0);
+        an2 = rotvec(q12);
+        p2 = mk3<T>(rr.x - nomrel, rr.y, rr.z);
+        back = q1;
+    } else {                                  // :101-118
+        Q4<T> pa = from_angle_to_posx(mk3<T>(rx, rr.y, rr.z));
+        T d2 = (T)2 * D * e.x + (e.x * e.x + e.y * e.y + e.z * e.z);
+        T len = vx_fsqrt(D * D + d2);
+        p2 = mk3<T>(d2 * vx_rcp(len + D) - nomrel, 0, 0);
+        an1 = rotvec(pa);
+        an2 = rotvec(qmul_x0_left(pa, q12));
+        Q4<T> cpa; cpa.w = pa.w; cpa.x = (T)0; cpa.y = -pa.y; cpa.z = -pa.z;
+        back = qmul_x0_right(q1, cpa);
+    }
 
     // axial stress (:120, :189-307; MDL_LINEAR: VX_Object.cpp:1472-1482).  For linear materials the
     // heterogeneous fixed-point iteration (:226-258) converges in one pass to sigma = 2 E1 E2/(E1+E2) eps

@@ -382,28 +382,32 @@ VX_HD bool col_pair_hit(const RobotView<Real>& R, const RobotConsts<Real>& C, co
     const Real act = horizon * (Real)C.scale_c[R.stat[vi].vcls];
     return d2 < act * act;
 }
-// CVXS_BondCollision::CalcContactForce, the share of voxel v: both ends of a pair are pushed apart along the line
-// of centres with a1 * overlap, a1 = composite E * mean size (CVX_Bond::LinkVoxels / UpdateConstants)
+// CVXS_BondCollision::CalcContactForce, the share of voxel v of its contact bond with voxel o: both ends of a pair are pushed
+// apart along the line of centres with a1 * overlap, a1 = composite E * mean size (CVX_Bond::LinkVoxels / UpdateConstants)
+template <typename Real>
+VX_HD void col_contact(const RobotView<Real>& R, const RobotConsts<Real>& C, const VoxStat& st, const OwnState<Real>& own, int o, V3<Real>& f) {
+    const int nv = R.nv;
+    const Real dx = (Real)(R.pos[o] - own.px), dy = (Real)(R.pos[nv + o] - own.py), dz = (Real)(R.pos[2 * nv + o] - own.pz);
+    const int vco = R.stat[o].vcls;
+    const Real nomd = (Real)((C.scale_c[st.vcls] + C.scale_c[vco]) * 0.75);
+    const Real len = vx_sqrt(dx * dx + dy * dy + dz * dz);
+    const Real rel = nomd - len;
+    if (rel > (Real)0) {
+        const VoxK<Real>& k1 = C.vk[st.vcls]; const VoxK<Real>& k2 = C.vk[vco];
+        const Real a1 = ((k1.e_mod * k2.e_mod / (k1.e_mod + k2.e_mod)) * (Real)2) * (k1.half_nom + k2.half_nom);
+        const Real g = a1 * rel / len;
+        f.x -= dx * g; f.y -= dy * g; f.z -= dz * g;
+    }
+}
+// ... summed over the contact-bond list in its order (every voxel scans the list: the push-form kernels and the CPU emulation)
 template <typename Real>
 VX_HD V3<Real> col_force_on(const RobotView<Real>& R, const RobotConsts<Real>& C, int v, const VoxStat& st, const OwnState<Real>& own,
                             const ColPair* pairs, int n_col) {
     V3<Real> f = mk3<Real>(0, 0, 0);
-    const int nv = R.nv;
     for (int k = 0; k < n_col; k++) {
         const ColPair p = pairs[k];
         if (p.v1 != v && p.v2 != v) continue;
-        const int o = p.v1 == v ? p.v2 : p.v1;
-        const Real dx = (Real)(R.pos[o] - own.px), dy = (Real)(R.pos[nv + o] - own.py), dz = (Real)(R.pos[2 * nv + o] - own.pz);
-        const int vco = R.stat[o].vcls;
-        const Real nomd = (Real)((C.scale_c[st.vcls] + C.scale_c[vco]) * 0.75);
-        const Real len = vx_sqrt(dx * dx + dy * dy + dz * dz);
-        const Real rel = nomd - len;
-        if (rel > (Real)0) {
-            const VoxK<Real>& k1 = C.vk[st.vcls]; const VoxK<Real>& k2 = C.vk[vco];
-            const Real a1 = ((k1.e_mod * k2.e_mod / (k1.e_mod + k2.e_mod)) * (Real)2) * (k1.half_nom + k2.half_nom);
-            const Real g = a1 * rel / len;
-            f.x -= dx * g; f.y -= dy * g; f.z -= dz * g;
-        }
+        col_contact<Real>(R, C, st, own, p.v1 == v ? p.v2 : p.v1, f);
     }
     return f;
 }

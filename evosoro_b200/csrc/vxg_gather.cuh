@@ -21,6 +21,7 @@
 //
 // Replaces CVX_Sim::Integrate (VX_Sim.cpp:1763-1933) for robots of the production family (pack_compact, vx_pack.h).
 #pragma once
+#include <cstdio>
 #include "vxg_kernels.cuh"
 
 namespace vx {
@@ -50,6 +51,24 @@ VX_HD constexpr GLayout make_glayout(int nv_in) {
     }
     G.total = o;
     return G;
+}
+
+// A bond class as the gather kernel reads it: the constants bond_force needs when both voxels of every bond have the same mass
+// (the production family), already expanded from the compact form (expand_bond) once per launch -- three 128-bit loads per
+// bond, no per-bond expansion arithmetic, no geometry constants held in registers.
+struct alignas(16) BondKm {
+    float a2, b1, b2, b3;
+    float inv_len, k_axial, nom_dist, len_minus_dist;
+    float s1, c_a2i1, c_b2fm1, c_b3i1;     // 2 sqrt(a1 m) = 2 sqrt(b1 m), 2 sqrt(a2 I), 2 sqrt(b2 FM), 2 sqrt(b3 I)
+};
+__device__ __forceinline__ BondK<float> bond_from_km(const BondKm& m) {
+    BondK<float> k;
+    k.a2 = m.a2; k.b1 = m.b1; k.b2 = m.b2; k.b3 = m.b3;
+    k.inv_len = m.inv_len; k.k_axial = m.k_axial; k.nom_dist = m.nom_dist; k.len_minus_dist = m.len_minus_dist;
+    k.c_a1m1 = m.s1; k.c_a1m2 = m.s1; k.c_b1m1 = m.s1; k.c_b1m2 = m.s1;
+    k.c_a2i1 = m.c_a2i1; k.c_a2i2 = m.c_a2i1; k.c_b2fm1 = m.c_b2fm1; k.c_b2fm2 = m.c_b2fm1; k.c_b3i1 = m.c_b3i1; k.c_b3i2 = m.c_b3i1;
+    k.sf1 = 1.0f; k.sf2 = 1.0f; k.homogeneous = 0;   // (the per-voxel strain shares feed the land/water surface mesh only)
+    return k;
 }
 
 // ---- tensor memory as scratch: 32 lanes x 32 columns per warp, lane = thread, columns = that thread's words -----------------
@@ -85,6 +104,12 @@ template <int AX> __device__ inline void hist_load(uint32_t tm, BondHist<float>&
     tm_wait_ld();
     h.p2 = mk3<float>(a[0], a[1], a[2]); h.a1 = mk3<float>(a[3], a[4], a[5]); h.a2 = mk3<float>(a[6], a[7], c);
 }
+// the same in two halves: issue the loads, do something else, wait
+template <int AX> __device__ inline void hist_issue(uint32_t tm, float (&a)[8], float& c) { tm_ld8(tm + 8 * AX, a); tm_ld1(tm + 24 + AX, c); }
+__device__ inline void hist_take(const float (&a)[8], float c, BondHist<float>& h) {
+    tm_wait_ld();
+    h.p2 = mk3<float>(a[0], a[1], a[2]); h.a1 = mk3<float>(a[3], a[4], a[5]); h.a2 = mk3<float>(a[6], a[7], c);
+}
 template <int AX> __device__ inline void hist_store(uint32_t tm, const BondHist<float>& h) {
     const float a[8] = {h.p2.x, h.p2.y, h.p2.z, h.a1.x, h.a1.y, h.a1.z, h.a2.x, h.a2.y};
     tm_st8(tm + 8 * AX, a);
@@ -93,17 +118,16 @@ template <int AX> __device__ inline void hist_store(uint32_t tm, const BondHist<
 
 // One owned bond in the gather form.  `st` carries the zero class for a missing neighbour (patched once per launch), so every
 // lane runs the same code; the warp skips the axis when none of its lanes has a bond there.
-template <int AX>
-__device__ __forceinline__ bool bond_eval_g(unsigned char* smem, const GLayout& G, int NV, const RobotConsts<float>& C, int tid, const VoxStat& st,
-                                            const OwnState<float>& own, uint32_t& fl, float dt_inv, uint32_t tm, V3<float>& F, V3<float>& M) {
+template <int AX, bool HOIST>
+__device__ __forceinline__ bool bond_eval_g(unsigned char* smem, const GLayout& G, int NV, const RobotConsts<float>& C, const BondKm* bkm, int tid, const VoxStat& st,
+                                            const OwnState<float>& own, uint32_t& fl, float dt_inv, uint32_t tm, V3<float>& M) {
     const int w = st.nbr[AX];
     if (!__any_sync(0xffffffffu, w >= 0)) return false;
     const int wq = w >= 0 ? w : tid;
     const int bc = st.bcls[AX];
-    BondHist<float> h;
-    hist_load<AX>(tm, h);
-    const BondKc<float> kc = C.bkc[bc];
-    const BondK<float> k = expand_bond<float>(kc, C.geo);
+    float ha[8], hc;
+    hist_issue<AX>(tm, ha, hc);   // the history is on its way from tensor memory while the neighbour's state is fetched
+    const BondK<float> k = bond_from_km(bkm[bc]);
     const double* pos = (const double*)(smem + G.off_pos);
     double dpa[3] = {pos[wq] - own.px, pos[NV + wq] - own.py, pos[2 * NV + wq] - own.pz};
     dpa[AX] -= C.bk_dist[bc];
@@ -113,14 +137,16 @@ __device__ __forceinline__ bool bond_eval_g(unsigned char* smem, const GLayout& 
     q1.w = qa.x; q1.x = qa.y; q1.y = qa.z; q1.z = qa.w;
     q2.w = qb.x; q2.x = qb.y; q2.y = qb.z; q2.z = qb.w;
     bool small = (fl >> AX) & 1u;
+    BondHist<float> h;
+    hist_take(ha, hc, h);
     BondOut<float> o;
-    bond_force<AX, float, true>(k, e, q1, q2, C.dnom_bc[bc], C.half_bond_z, dt_inv, true, small, h, o);
+    bond_force<AX, float, true, HOIST>(k, e, q1, q2, C.dnom_bc[bc], C.half_bond_z, dt_inv, true, small, h, o);
     // _LastPos2/_LastAngle* keep their values on a mode-flip step (VXS_BondInternal.cpp:157): rare, so the old values are
     // fetched again (they are still in tensor memory) behind a warp-uniform test instead of being kept in registers
     if (__any_sync(0xffffffffu, o.changed)) { BondHist<float> old; hist_load<AX>(tm, old); if (o.changed) h = old; }
     hist_store<AX>(tm, h);
     fl = (fl & ~(1u << AX)) | ((small ? 1u : 0u) << AX);
-    F = F + o.f1; M = M + o.m1;
+    M = M + o.m1;   // (the own share of the force is read back from the staging slot in the voxel phase: three registers less)
     R4<float> a; a.x = o.f1.x; a.y = o.f1.y; a.z = o.f1.z; a.w = o.m2.x;
     R2<float> b; b.x = o.m2.y; b.y = o.m2.z;
     ((R4<float>*)(smem + G.off_stA[AX]))[tid] = a;
@@ -128,13 +154,75 @@ __device__ __forceinline__ bool bond_eval_g(unsigned char* smem, const GLayout& 
     return o.strain > 100.0f;
 }
 
-template <int NV>
+// Voxel phase of the gather form: the shares of the -X/-Y/-Z bonds (Force2 = -Force1, Moment2) from their owners' staging slots,
+// then EulerStep; the new position / orientation go to shared memory for the neighbours and stay in `own` for the next step.
+__device__ __forceinline__ void voxel_phase_g(unsigned char* smem, const GLayout& G, int NV, const RobotConsts<float>& C, const RobotView<float>& R, int tid,
+                                              const VoxStat& st, uint2 nb, OwnState<float>& own, uint32_t& fl, V3<float> M) {
+    V3<float> F;
+    const int mX = nb.x & 0xFFFFu, mY = nb.x >> 16, mZ = nb.y & 0xFFFFu;
+    const R4<float> ax = ((const R4<float>*)(smem + G.off_stA[0]))[mX], ay = ((const R4<float>*)(smem + G.off_stA[1]))[mY], az = ((const R4<float>*)(smem + G.off_stA[2]))[mZ];
+    const R2<float> bx = ((const R2<float>*)(smem + G.off_stB[0]))[mX], by = ((const R2<float>*)(smem + G.off_stB[1]))[mY], bz = ((const R2<float>*)(smem + G.off_stB[2]))[mZ];
+    // own shares: Force1 of the owned X, Y, Z bonds, as staged by this very thread (axes the voxel has no bond on staged zeros)
+    {
+        const R4<float> ox = ((const R4<float>*)(smem + G.off_stA[0]))[tid], oy = ((const R4<float>*)(smem + G.off_stA[1]))[tid], oz = ((const R4<float>*)(smem + G.off_stA[2]))[tid];
+        F = mk3<float>(((0.0f + ox.x) + oy.x) + oz.x, ((0.0f + ox.y) + oy.y) + oz.y, ((0.0f + ox.z) + oy.z) + oz.z);
+    }
+    // the accumulator of the push form received -Force1 of the X, Y, Z bond in that order, starting from zero
+    F = F + mk3<float>(((0.0f - ax.x) - ay.x) - az.x, ((0.0f - ax.y) - ay.y) - az.y, ((0.0f - ax.z) - ay.z) - az.z);
+    M = M + mk3<float>(((0.0f + ax.w) + ay.w) + az.w, ((0.0f + bx.x) + by.x) + bz.x, ((0.0f + bx.y) + by.y) + bz.y);
+    const int vc = st.vcls;
+    const VoxK<float> kv = C.vk[vc];
+    VoxState<float> vs;
+    vs.px = own.px; vs.py = own.py; vs.pz = own.pz;
+    const R4<float> ma = R.momA[tid]; const R2<float> mb = R.momB[tid];
+    vs.q.w = own.q.x; vs.q.x = own.q.y; vs.q.y = own.q.z; vs.q.z = own.q.w;
+    vs.lm = mk3<float>(ma.x, ma.y, ma.z);
+    vs.am = mk3<float>(ma.w, mb.x, mb.y);
+    const bool sf = voxel_integrate<float, false>(kv, F, M, 0.5 * C.scale_c[vc], C.floor_on, false, C.dt, nullptr, nullptr, nullptr, vs);
+    own.px = vs.px; own.py = vs.py; own.pz = vs.pz;
+    own.q.x = vs.q.w; own.q.y = vs.q.x; own.q.z = vs.q.y; own.q.w = vs.q.z;
+    R.pos[tid] = vs.px; R.pos[NV + tid] = vs.py; R.pos[2 * NV + tid] = vs.pz;
+    R.quat[tid] = own.q;
+    R4<float> na; na.x = vs.lm.x; na.y = vs.lm.y; na.z = vs.lm.z; na.w = vs.am.x;
+    R2<float> nb2; nb2.x = vs.am.y; nb2.y = vs.am.z;
+    R.momA[tid] = na; R.momB[tid] = nb2;
+    fl = sf ? (fl | VX_FL_STATIC_FRIC) : (fl & ~VX_FL_STATIC_FRIC);
+}
+
+// Dataflow form (FLOW): within a window of up to VXG_FLOW_R timesteps the warps are not held together by CTA-wide barriers at all.
+// A warp's bond phase needs the positions its +axis neighbours' owners wrote in their last voxel phase, its voxel phase needs the
+// shares its -axis neighbours' owners staged in their bond phase -- a handful of warps in either case (at 10^3: the warp itself, the
+// next / previous one and the ones 100 voxels away).  Every warp therefore has two mbarriers (bond phase done, voxel phase done; one
+// arrival per phase) and waits only on those of the warps its voxels' neighbours live in.  The same waits cover the write-after-read
+// hazards (the dependency sets are each other's mirror image), which also keeps any two dependent warps within one phase of each
+// other -- the condition for parity waits.  Warps drift apart by whole phases and fill each other's stalls: the per-step CTA
+// barriers cost 29 % of the issue slots in the barrier form (ncu: smsp__issue_active 71 %; profiles/).
+// What needs the whole CTA -- the per-class Scale tables, the IniCM / end-of-life latches, the divergence verdict -- happens once
+// per window: Scale is computed VXG_FLOW_R steps ahead into a ring, the rest-length table of a window is derived between the two
+// barriers that open it, latches end a window early, and a diverged bond is recorded with its step and acted on at the window's end.
+#define VXG_FLOW_R 8
+#define VXG_FLOW_RING (2 * VXG_FLOW_R)
+__host__ __device__ inline size_t flow_bytes(int max_vclass, int mb) {
+    return vx_align16(sizeof(double) * VXG_FLOW_RING * max_vclass) + vx_align16(sizeof(float) * VXG_FLOW_RING * max_vclass) +
+           vx_align16(sizeof(float) * VXG_FLOW_RING * mb) + 64 * sizeof(unsigned long long) + 16 + vx_align16(sizeof(double) * (2 + max_vclass));
+}
+// wait until, for every warp u in `mask`, bar[u] has completed the phase of the given parity (lane u waits on bar[u])
+__device__ inline void flow_wait(unsigned long long* bar, uint32_t mask, uint32_t parity, int lane) {
+    if ((mask >> lane) & 1u) mbar_wait(bar + lane, parity);
+    __syncwarp();
+}
+
+//   CV, CB : compile-time capacities of the voxel / bond class tables in shared memory (0 = the batch's run-time limits).  With them
+//            every shared-memory address in the step loop is the CTA's base plus an immediate; with run-time capacities the
+//            table pointers were rematerialised over and over at 64 registers (5 % of the executed instructions, ncu).
+template <int NV, bool FLOW, int CV, int CB>
 __global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, false, false)) vx_step_kernel_g(BatchDev<float> B, int n_steps) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int T = NV;
     constexpr BlobLayout L = make_layout(NV, 4);
     constexpr GLayout G = make_glayout(NV);
     constexpr int TM_COLS = tm_cols_for(NV);
+    constexpr bool HOIST = !(NV == 1024 || NV == 512);   // bond_force: only where there are more than 64 registers per thread
     const int robot = blockIdx.x;
     int tid;
     asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
@@ -147,8 +235,11 @@ __global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, false, false)) vx_step
     if (nsteps <= 0) { if (tid == 0) ctlp->status = status0 | VXG_ST_FINISHED_; return; }
 
     unsigned char* gblob = B.blobs + (size_t)robot * L.total_bytes;
-    const int MB = B.max_bclass + 1;   // one more bond class than the batch's limit: the zero class
-    SmemTables<float> S = carve_tables<float>(smem + G.total, B.max_vclass, MB, true, 0);
+    const int MB = CB > 0 ? CB : B.max_bclass + 1;   // one more bond class than the batch's limit: the zero class
+    const int mv = CV > 0 ? CV : B.max_vclass;
+    BondKm* bkm = (BondKm*)(smem + G.total);
+    unsigned char* tabp = smem + G.total + sizeof(BondKm) * (size_t)MB;
+    SmemTables<float> S = carve_tables<float>(tabp, mv, MB, true, 0);
     const int n_vox = ctlp->n_vox, n_vc = ctlp->n_vclass, n_bc = ctlp->n_bclass;
     const unsigned int flags = ctlp->flags;
     const int ZC = n_bc;               // index of the zero class
@@ -165,11 +256,10 @@ __global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, false, false)) vx_step
     {
         uint2 none; none.x = none.y = (uint32_t)NV | ((uint32_t)NV << 16);
         ((uint2*)(smem + G.off_nbm))[tid] = none;
-        if (tid == 0) {
-            R4<float> za; za.x = za.y = za.z = za.w = 0.0f; R2<float> zb; zb.x = zb.y = 0.0f;
-#pragma unroll
-            for (int a = 0; a < 3; a++) { ((R4<float>*)(smem + G.off_stA[a]))[NV] = za; ((R2<float>*)(smem + G.off_stB[a]))[NV] = zb; }
-        }
+        // staging slots start as zeros and stay so where nothing is ever staged: the "no neighbour" slot [NV] and the slots of
+        // warps that skip an axis altogether (the voxel phase reads its own slots unconditionally)
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        for (size_t i = tid; i < ((G.total - G.off_stA[0]) >> 4); i += T) ((uint4*)(smem + G.off_stA[0]))[i] = z;
     }
     copy4(S.bk, B.bk + (size_t)robot * B.max_bclass * sizeof(BondKc<float>), sizeof(BondKc<float>) * n_bc, tid, T);
     copy4(S.vk, B.vk + (size_t)robot * B.max_vclass, sizeof(VoxK<float>) * n_vc, tid, T);
@@ -183,6 +273,16 @@ __global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, false, false)) vx_step
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tm = *tm_slot + ((uint32_t)((tid >> 5) & 3) << 21) + (uint32_t)(tid >> 7) * VXG_TM_COLS_PER_WARP;   // lane (warp % 4) * 32, this warp's columns
     for (int i = tid; i < n_vc; i += T) S.dsc_c[i] = (float)(S.scale_c[i] - S.sk[i].nom_size);
+    if (tid <= n_bc) {   // expanded bond classes (the zero class: all zeros)
+        BondKm m; memset(&m, 0, sizeof m);
+        if (tid < n_bc) {
+            const BondK<float> k = expand_bond<float>(((const BondKc<float>*)S.bk)[tid], make_geo<float>(ctlp->bond_len));
+            m.a2 = k.a2; m.b1 = k.b1; m.b2 = k.b2; m.b3 = k.b3;
+            m.inv_len = k.inv_len; m.k_axial = k.k_axial; m.nom_dist = k.nom_dist; m.len_minus_dist = k.len_minus_dist;
+            m.s1 = k.c_a1m1; m.c_a2i1 = k.c_a2i1; m.c_b2fm1 = k.c_b2fm1; m.c_b3i1 = k.c_b3i1;
+        }
+        bkm[tid] = m;
+    }
     // own static word (zero class for the missing bonds), own state, and the -axis neighbour table
     VoxStat st = ((const VoxStat*)(smem + G.off_stat))[tid];
     if (tid >= n_vox) st.nbr[0] = st.nbr[1] = st.nbr[2] = -1;
@@ -209,7 +309,7 @@ __global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, false, false)) vx_step
     R.stat = (VoxStat*)(smem + G.off_stat);
     RobotConsts<float> C;
     C.bk = nullptr; C.bkc = (const BondKc<float>*)S.bk;
-    C.geo = make_geo<float>(ctlp->bond_len);
+    C.geo = make_geo<float>(1.0);
     C.bk_dist = S.bk_dist; C.vk = S.vk;
     C.nom = nullptr; C.ext_disp = S.ext_disp; C.ext_tdisp = S.ext_tdisp;
     C.half_bond_z = (float)ctlp->half_bond_z;
@@ -230,84 +330,185 @@ __global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, false, false)) vx_step
     __syncthreads();
     const uint2 nb = ((const uint2*)(smem + G.off_nbm))[tid];   // -X | -Y << 16, -Z
     const float dt_inv_run = (float)(1.0 / dt);
+    // ---- dataflow form: table ring, per-warp phase barriers, dependency masks --------------------------------------------
+    unsigned char* fp = tabp + tables_bytes<float>(mv, MB, true, 0);
+    double* r_scale = (double*)fp;                      fp += vx_align16(sizeof(double) * VXG_FLOW_RING * mv);
+    float* r_dsc = (float*)fp;                          fp += vx_align16(sizeof(float) * VXG_FLOW_RING * mv);
+    float* r_dnom = (float*)fp;                         fp += vx_align16(sizeof(float) * VXG_FLOW_RING * MB);
+    unsigned long long* bondbar = (unsigned long long*)fp; unsigned long long* voxbar = bondbar + 32;   fp += 64 * sizeof(unsigned long long);
+    int* f_div = (int*)fp;                              fp += 16;
+    double* f_time = (double*)fp;                       // [0] CurTime (thread 0's), [2 + c] time of the step after class c's newest ring entry
+    uint32_t plus_mask = 0, minus_mask = 0;
+    const int my_class = T - 1 - tid;                   // the voxel class whose Scale this thread computes (if < n_vc)
+    if (FLOW) {
+        const int lane = tid & 31, warp = tid >> 5;
+        uint32_t pm = 0, mm = 0;
+#pragma unroll
+        for (int a = 0; a < 3; a++) if (st.nbr[a] >= 0) pm |= 1u << (st.nbr[a] >> 5);
+        if (tid < n_vox) {
+            const int m0 = nb.x & 0xFFFFu, m1 = nb.x >> 16, m2 = nb.y & 0xFFFFu;
+            if (m0 < NV) mm |= 1u << (m0 >> 5);
+            if (m1 < NV) mm |= 1u << (m1 >> 5);
+            if (m2 < NV) mm |= 1u << (m2 >> 5);
+        }
+        plus_mask = __reduce_or_sync(0xffffffffu, pm) & ~(1u << warp);
+        minus_mask = __reduce_or_sync(0xffffffffu, mm) & ~(1u << warp);
+        if (lane == 0) { mbar_init(bondbar + warp, 1); mbar_init(voxbar + warp, 1); }
+        if (tid == 0) *f_div = 0x7fffffff;
+        for (int i = tid; i < VXG_FLOW_RING; i += T) r_dnom[i * MB + ZC] = 0.0f;
+        if (my_class < n_vc) {   // ring entries of the first window: Scale of step j from the Scale and the time of step j - 1
+            double sc_last = S.scale_c[my_class], sc_t = ctlp->cur_time;
+            r_scale[my_class] = sc_last; r_dsc[my_class] = (float)(sc_last - S.sk[my_class].nom_size);
+            for (int j = 1; j < VXG_FLOW_R; j++) {
+                sc_last = scale_law(S.sk[my_class], sc_last, sc_t, *S.sl); sc_t += dt;
+                r_scale[j * mv + my_class] = sc_last; r_dsc[j * mv + my_class] = (float)(sc_last - S.sk[my_class].nom_size);
+            }
+            f_time[2 + my_class] = sc_t;
+        }
+        if (tid == 0) f_time[0] = ctlp->cur_time;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncthreads();
+    }
 
     double t = ctlp->cur_time;
     int cur = 0, done = 0;
     bool diverged = false;
-    for (int k = 0; k < nsteps; ++k) {
-        const long long s = step0 + k;
-        if (s == latch) {   // IniCM = SS.CurCM at TimeStep entry (VX_Sim.cpp:1064-1075): COM after the previous step
-            double mx = 0, my = 0, mz = 0, mm = 0;
-            if (tid < n_vox) { const double m = (double)S.vk[st.vcls].mass; mx = own.px * m; my = own.py * m; mz = own.pz * m; mm = m; }
-            block_sum4(mx, my, mz, mm, S.red);
-            if (tid == 0) { ctlp->ini_com[0] = mx / mm; ctlp->ini_com[1] = my / mm; ctlp->ini_com[2] = mz / mm; ctlp->ini_latched = 1; }
-        }
-        if (s == eol) {     // SS.EndOfLifetimePosteriorY = getPosteriorY() at TimeStep entry (VX_Sim.cpp:1078-1082)
-            double lo = 1e300;
-            if (tid < n_vox && S.sk[st.vcls].mat_index != 5) lo = own.py;
-            lo = -warp_max(-lo);
+    if (FLOW) {
+        const int lane = tid & 31, warp = tid >> 5;
+        int k = 0;
+        while (k < nsteps) {
+            const long long s0 = step0 + k;
+            __syncthreads();                                 // every warp has finished the previous window
+            if (*f_div != 0x7fffffff) break;
+            if (tid == 0) { f_time[1] = f_time[0]; f_div[1] = k; }   // where this window starts, for the divergence rewind
+            if (s0 == latch) {   // IniCM = SS.CurCM at TimeStep entry (VX_Sim.cpp:1064-1075): COM after the previous step
+                double mx = 0, my = 0, mz = 0, mm = 0;
+                if (tid < n_vox) { const double m = (double)S.vk[st.vcls].mass; mx = own.px * m; my = own.py * m; mz = own.pz * m; mm = m; }
+                block_sum4(mx, my, mz, mm, S.red);
+                if (tid == 0) { ctlp->ini_com[0] = mx / mm; ctlp->ini_com[1] = my / mm; ctlp->ini_com[2] = mz / mm; ctlp->ini_latched = 1; }
+            }
+            if (s0 == eol) {     // SS.EndOfLifetimePosteriorY = getPosteriorY() at TimeStep entry (VX_Sim.cpp:1078-1082)
+                double lo = 1e300;
+                if (tid < n_vox && S.sk[st.vcls].mat_index != 5) lo = own.py;
+                lo = -warp_max(-lo);
+                __syncthreads();
+                if ((tid & 31) == 0) S.red[tid >> 5] = lo;
+                __syncthreads();
+                if (tid == 0) { for (int i = 1; i < T / 32; i++) lo = fmin(lo, S.red[i]); ctlp->eol_post_y = lo; }
+            }
+            int wlen = nsteps - k < VXG_FLOW_R ? nsteps - k : VXG_FLOW_R;          // a latch ends the window before its step
+            if (latch > s0 && latch - s0 < (long long)wlen) wlen = (int)(latch - s0);
+            if (eol > s0 && eol - s0 < (long long)wlen) wlen = (int)(eol - s0);
+            // rest-length deviation of every bond class for the steps of this window (their Scale entries were written >= one window ago)
+            for (int i = tid; i < wlen * n_bc; i += T) {
+                const int j = i / n_bc, b = i - j * n_bc, e = (k + j) & (VXG_FLOW_RING - 1);
+                const uint32_t pr = S.bpair[b];
+                r_dnom[e * MB + b] = 0.5f * (r_dsc[e * mv + (pr & 0xFFFFu)] + r_dsc[e * mv + (pr >> 16)]);
+            }
             __syncthreads();
-            if ((tid & 31) == 0) S.red[tid >> 5] = lo;
+            for (int j = 0; j < wlen; ++j, ++k) {
+                const int e = k & (VXG_FLOW_RING - 1);
+                C.scale_c = r_scale + e * mv; C.dsc_c = r_dsc + e * mv; C.dnom_bc = r_dnom + e * MB;
+                const float dt_inv = (step0 + k == 0) ? 0.0f : dt_inv_run;   // dt == 0 during the very first bond pass (VX_Sim.cpp:373)
+                // +axis neighbours' owners must have integrated step k - 1 (and read the shares this warp is about to overwrite)
+                if (j > 0) flow_wait(voxbar, plus_mask, (uint32_t)(k - 1) & 1u, lane);
+                if (my_class < n_vc) {   // Scale of step k + R (VXS_Voxel.cpp:224-336) into the ring, R steps ahead of its readers
+                    const int ea = (k + VXG_FLOW_R) & (VXG_FLOW_RING - 1), el = (k + VXG_FLOW_R - 1) & (VXG_FLOW_RING - 1);
+                    const double sc_t = f_time[2 + my_class];
+                    const double ns = scale_law(S.sk[my_class], r_scale[el * mv + my_class], sc_t, *S.sl);
+                    f_time[2 + my_class] = sc_t + dt;
+                    r_scale[ea * mv + my_class] = ns; r_dsc[ea * mv + my_class] = (float)(ns - S.sk[my_class].nom_size);
+                }
+                V3<float> M = mk3<float>(0, 0, 0);
+                bool dv = bond_eval_g<0, HOIST>(smem, G, NV, C, bkm, tid, st, own, fl, dt_inv, tm, M);
+                dv |= bond_eval_g<1, HOIST>(smem, G, NV, C, bkm, tid, st, own, fl, dt_inv, tm, M);
+                dv |= bond_eval_g<2, HOIST>(smem, G, NV, C, bkm, tid, st, own, fl, dt_inv, tm, M);
+                if (dv) atomicMin(f_div, k);                 // Integrate() fails in this step (VX_Sim.cpp:1775-1777): acted on at the window's end
+                tm_wait_st();
+                mbar_arrive_warp(bondbar + warp, lane == 0);
+                // -axis neighbours' owners must have staged their shares of step k (and read the positions this warp is about to overwrite)
+                flow_wait(bondbar, minus_mask, (uint32_t)k & 1u, lane);
+                if (tid < n_vox) voxel_phase_g(smem, G, NV, C, R, tid, st, nb, own, fl, M);
+                mbar_arrive_warp(voxbar + warp, lane == 0);
+                if (tid == 0) f_time[0] += dt;               // CurTime += dt (VX_Sim.cpp:1929)
+            }
+            done = k;
+        }
+        const int dstep = *f_div;
+        if (dstep != 0x7fffffff) {   // the robot stops where the reference's Integrate() first returned false
+            diverged = true; done = dstep;
+            if (tid == 0) { double tt = f_time[1]; for (int i = f_div[1]; i < dstep; i++) tt += dt; f_time[0] = tt; }
+        }
+        if (tid == 0) t = f_time[0];
+        cur = done & (VXG_FLOW_RING - 1);
+    } else {
+        for (int k = 0; k < nsteps; ++k) {
+            const long long s = step0 + k;
+            if (s == latch) {   // IniCM = SS.CurCM at TimeStep entry (VX_Sim.cpp:1064-1075): COM after the previous step
+                double mx = 0, my = 0, mz = 0, mm = 0;
+                if (tid < n_vox) { const double m = (double)S.vk[st.vcls].mass; mx = own.px * m; my = own.py * m; mz = own.pz * m; mm = m; }
+                block_sum4(mx, my, mz, mm, S.red);
+                if (tid == 0) { ctlp->ini_com[0] = mx / mm; ctlp->ini_com[1] = my / mm; ctlp->ini_com[2] = mz / mm; ctlp->ini_latched = 1; }
+            }
+            if (s == eol) {     // SS.EndOfLifetimePosteriorY = getPosteriorY() at TimeStep entry (VX_Sim.cpp:1078-1082)
+                double lo = 1e300;
+                if (tid < n_vox && S.sk[st.vcls].mat_index != 5) lo = own.py;
+                lo = -warp_max(-lo);
+                __syncthreads();
+                if ((tid & 31) == 0) S.red[tid >> 5] = lo;
+                __syncthreads();
+                if (tid == 0) { for (int i = 1; i < T / 32; i++) lo = fmin(lo, S.red[i]); ctlp->eol_post_y = lo; }
+            }
+            C.scale_c = S.scale_c + cur * mv;
+            C.dsc_c = S.dsc_c + cur * mv;
+            C.dnom_bc = S.dnom_bc + cur * MB;
+            const float dt_inv = (s == 0) ? 0.0f : dt_inv_run;   // dt == 0 during the very first bond pass (VX_Sim.cpp:373)
+
+            // Scale of every class for the NEXT step (VXS_Voxel.cpp:224-336), by the highest threads, into the other buffer half
+            for (int i = T - 1 - tid; i < n_vc; i += T) {
+                const double last = S.scale_c[cur * mv + i];
+                const double ns = scale_law(S.sk[i], last, t, *S.sl);
+                S.scale_c[(cur ^ 1) * mv + i] = ns;
+                S.dsc_c[(cur ^ 1) * mv + i] = (float)(ns - S.sk[i].nom_size);
+            }
+            // ---- bond phase: reads positions / orientations of the previous step, writes only what this thread owns --------------
+            V3<float> M = mk3<float>(0, 0, 0);
+            int div = 0;
+#ifdef VXG_TRACE
+            const long long tr0 = clock64();
+#endif
+            div |= bond_eval_g<0, HOIST>(smem, G, NV, C, bkm, tid, st, own, fl, dt_inv, tm, M) ? 1 : 0;
+            div |= bond_eval_g<1, HOIST>(smem, G, NV, C, bkm, tid, st, own, fl, dt_inv, tm, M) ? 1 : 0;
+            div |= bond_eval_g<2, HOIST>(smem, G, NV, C, bkm, tid, st, own, fl, dt_inv, tm, M) ? 1 : 0;
+            tm_wait_st();
+#ifdef VXG_TRACE
+            const long long tr1 = clock64();
+#endif
+            if (__syncthreads_or(div)) { diverged = true; break; }   // Integrate() returns before the voxel loop (VX_Sim.cpp:1777)
+#ifdef VXG_TRACE
+            const long long tr2 = clock64();
+#endif
+
+            // rest-length deviation of every bond class for the NEXT step
+            for (int i = tid; i < n_bc; i += T) {
+                const uint32_t pr = S.bpair[i];
+                const float* dn = S.dsc_c + (cur ^ 1) * mv;
+                S.dnom_bc[(cur ^ 1) * MB + i] = 0.5f * (dn[pr & 0xFFFFu] + dn[pr >> 16]);
+            }
+            // ---- voxel phase: gather the shares of the -X/-Y/-Z bonds (Force2 = -Force1, Moment2), integrate -------------------
+            if (tid < n_vox) voxel_phase_g(smem, G, NV, C, R, tid, st, nb, own, fl, M);
+#ifdef VXG_TRACE
+            const long long tr3 = clock64();
+#endif
             __syncthreads();
-            if (tid == 0) { for (int i = 1; i < T / 32; i++) lo = fmin(lo, S.red[i]); ctlp->eol_post_y = lo; }
+#ifdef VXG_TRACE
+            if (robot == 0 && (tid & 31) == 0 && (k == 50 || k == 51) && step0 > 2500)
+                printf("TRACE k %d warp %2d bond_start %lld bond_end %lld bar1_exit %lld vox_end %lld bar2_exit %lld\n", k, tid >> 5, tr0 % 10000000, tr1 % 10000000, tr2 % 10000000, tr3 % 10000000, clock64() % 10000000);
+#endif
+            cur ^= 1;
+            t += dt;                                                 // CurTime += dt (VX_Sim.cpp:1929)
+            done = k + 1;
         }
-        C.scale_c = S.scale_c + cur * B.max_vclass;
-        C.dsc_c = S.dsc_c + cur * B.max_vclass;
-        C.dnom_bc = S.dnom_bc + cur * MB;
-        const float dt_inv = (s == 0) ? 0.0f : dt_inv_run;   // dt == 0 during the very first bond pass (VX_Sim.cpp:373)
-
-        // Scale of every class for the NEXT step (VXS_Voxel.cpp:224-336), by the highest threads, into the other buffer half
-        for (int i = T - 1 - tid; i < n_vc; i += T) {
-            const double last = S.scale_c[cur * B.max_vclass + i];
-            const double ns = scale_law(S.sk[i], last, t, *S.sl);
-            S.scale_c[(cur ^ 1) * B.max_vclass + i] = ns;
-            S.dsc_c[(cur ^ 1) * B.max_vclass + i] = (float)(ns - S.sk[i].nom_size);
-        }
-        // ---- bond phase: reads positions / orientations of the previous step, writes only what this thread owns --------------
-        V3<float> F = mk3<float>(0, 0, 0), M = mk3<float>(0, 0, 0);
-        int div = 0;
-        div |= bond_eval_g<0>(smem, G, NV, C, tid, st, own, fl, dt_inv, tm, F, M) ? 1 : 0;
-        div |= bond_eval_g<1>(smem, G, NV, C, tid, st, own, fl, dt_inv, tm, F, M) ? 1 : 0;
-        div |= bond_eval_g<2>(smem, G, NV, C, tid, st, own, fl, dt_inv, tm, F, M) ? 1 : 0;
-        tm_wait_st();
-        if (__syncthreads_or(div)) { diverged = true; break; }   // Integrate() returns before the voxel loop (VX_Sim.cpp:1777)
-
-        // rest-length deviation of every bond class for the NEXT step
-        for (int i = tid; i < n_bc; i += T) {
-            const uint32_t pr = S.bpair[i];
-            const float* dn = S.dsc_c + (cur ^ 1) * B.max_vclass;
-            S.dnom_bc[(cur ^ 1) * MB + i] = 0.5f * (dn[pr & 0xFFFFu] + dn[pr >> 16]);
-        }
-        // ---- voxel phase: gather the shares of the -X/-Y/-Z bonds (Force2 = -Force1, Moment2), integrate -------------------
-        if (tid < n_vox) {
-            const int mX = nb.x & 0xFFFFu, mY = nb.x >> 16, mZ = nb.y & 0xFFFFu;
-            const R4<float> ax = ((const R4<float>*)(smem + G.off_stA[0]))[mX], ay = ((const R4<float>*)(smem + G.off_stA[1]))[mY], az = ((const R4<float>*)(smem + G.off_stA[2]))[mZ];
-            const R2<float> bx = ((const R2<float>*)(smem + G.off_stB[0]))[mX], by = ((const R2<float>*)(smem + G.off_stB[1]))[mY], bz = ((const R2<float>*)(smem + G.off_stB[2]))[mZ];
-            // the accumulator of the push form received -Force1 of the X, Y, Z bond in that order, starting from zero
-            F = F + mk3<float>(((0.0f - ax.x) - ay.x) - az.x, ((0.0f - ax.y) - ay.y) - az.y, ((0.0f - ax.z) - ay.z) - az.z);
-            M = M + mk3<float>(((0.0f + ax.w) + ay.w) + az.w, ((0.0f + bx.x) + by.x) + bz.x, ((0.0f + bx.y) + by.y) + bz.y);
-            const int vc = st.vcls;
-            const VoxK<float> kv = C.vk[vc];
-            VoxState<float> vs;
-            vs.px = own.px; vs.py = own.py; vs.pz = own.pz;
-            const R4<float> ma = R.momA[tid]; const R2<float> mb = R.momB[tid];
-            vs.q.w = own.q.x; vs.q.x = own.q.y; vs.q.y = own.q.z; vs.q.z = own.q.w;
-            vs.lm = mk3<float>(ma.x, ma.y, ma.z);
-            vs.am = mk3<float>(ma.w, mb.x, mb.y);
-            const bool sf = voxel_integrate<float, false>(kv, F, M, 0.5 * C.scale_c[vc], C.floor_on, false, C.dt, nullptr, nullptr, nullptr, vs);
-            own.px = vs.px; own.py = vs.py; own.pz = vs.pz;
-            own.q.x = vs.q.w; own.q.y = vs.q.x; own.q.z = vs.q.y; own.q.w = vs.q.z;
-            R.pos[tid] = vs.px; R.pos[NV + tid] = vs.py; R.pos[2 * NV + tid] = vs.pz;
-            R.quat[tid] = own.q;
-            R4<float> na; na.x = vs.lm.x; na.y = vs.lm.y; na.z = vs.lm.z; na.w = vs.am.x;
-            R2<float> nb2; nb2.x = vs.am.y; nb2.y = vs.am.z;
-            R.momA[tid] = na; R.momB[tid] = nb2;
-            fl = sf ? (fl | VX_FL_STATIC_FRIC) : (fl & ~VX_FL_STATIC_FRIC);
-        }
-        __syncthreads();
-        cur ^= 1;
-        t += dt;                                                 // CurTime += dt (VX_Sim.cpp:1929)
-        done = k + 1;
     }
 
     // ---- stage out -------------------------------------------------------------------------------------------------------
@@ -328,7 +529,7 @@ __global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, false, false)) vx_step
             }
         }
     }
-    for (int i = tid; i < n_vc; i += T) B.scale_c[(size_t)robot * B.max_vclass + i] = S.scale_c[cur * B.max_vclass + i];
+    for (int i = tid; i < n_vc; i += T) B.scale_c[(size_t)robot * B.max_vclass + i] = FLOW ? r_scale[cur * mv + i] : S.scale_c[cur * mv + i];
     if (tid == 0) {
         ctlp->cur_time = t;
         ctlp->step = step0 + done;
@@ -344,8 +545,9 @@ __global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, false, false)) vx_step
     if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "n"(TM_COLS) : "memory");
 }
 
-inline size_t gather_smem_bytes(int nv, int max_vclass, int max_bclass) {
-    return make_glayout(nv).total + tables_bytes<float>(max_vclass, max_bclass + 1, true, 0);
+// shared memory of one CTA: mv / mb = capacities of the class tables as the kernel instantiation has them (mb includes the zero class)
+inline size_t gather_smem_bytes(int nv, int mv, int mb, bool flow) {
+    return make_glayout(nv).total + sizeof(BondKm) * (size_t)mb + tables_bytes<float>(mv, mb, true, 0) + (flow ? flow_bytes(mv, mb) : 0);
 }
 
 }  // namespace vx

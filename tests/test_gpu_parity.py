@@ -168,25 +168,27 @@ def test_batch_of_identical_robots_is_uniform():
 @pytest.mark.parametrize("n,steps", [(3, 700), (6, 2500), (8, 2500), (10, 3000)])
 def test_gather_form_is_bit_identical_to_the_push_form(n, steps, monkeypatch):
     """The production kernel's two forms (vxg_gather.cuh: damping history in tensor memory, shares gathered by the -axis
-    neighbour; vxg_kernels.cuh: shares pushed into shared-memory accumulators) run the same arithmetic in the same order: every
-    word of the state agrees after thousands of actuated steps, in one launch or many."""
+    neighbour, with CTA-wide barriers or as a per-warp dataflow; vxg_kernels.cuh: shares pushed into shared-memory accumulators) run
+    the same arithmetic in the same order: every word of the state agrees after thousands of actuated steps, in one launch or many."""
     sim = vxa.SimParams(init_cm_time=0.01, stop_condition_value=1.0)
     robots = [engine.Model(text=vxa.vxa_text(vxa.dense_lattice(n, 80 + s) if s % 2 == 0 else vxa.sparse_lattice(n, 80 + s, fill=0.6), sim=sim)).robot for s in range(4)]
     latch = [steps // 3] * 4    # IniCM latch in the middle of a launch: the block reduction shares scratch with other users
-    monkeypatch.setenv("VXG_PUSH_KERNEL", "1")
+    monkeypatch.setenv("VXG_KERNEL_FORM", "push")
     a = engine.Batch(robots); a.set_step_budget(None, latch); a.step(steps); assert not a.sync().any()
-    monkeypatch.delenv("VXG_PUSH_KERNEL")
-    b = engine.Batch(robots); b.set_step_budget(None, latch)
-    for _ in range(5):
-        b.step(steps // 5)
-    assert not b.sync().any()
-    assert [list(x.ini_com) for x in a.stats()] == [list(x.ini_com) for x in b.stats()]
-    for r in range(4):
-        sa, sb = a.download(r), b.download(r)
-        for f in ("pos", "quat", "lin_mom", "ang_mom", "scale", "static_fric", "bond_small_angle"):
-            assert np.array_equal(getattr(sa, f), getattr(sb, f)), (r, f)
-    assert [int(s.steps) for s in b.stats()] == [steps] * 4
-    a.close(); b.close()
+    for form in ("barrier", "flow"):
+        monkeypatch.setenv("VXG_KERNEL_FORM", form)
+        b = engine.Batch(robots); b.set_step_budget(None, latch)
+        for i in range(5):
+            b.step(steps // 5 + (3 if i == 0 else -3 if i == 4 else 0))      # launch lengths that are not multiples of the window
+        assert not b.sync().any()
+        assert [list(x.ini_com) for x in a.stats()] == [list(x.ini_com) for x in b.stats()]
+        for r in range(4):
+            sa, sb = a.download(r), b.download(r)
+            for f in ("pos", "quat", "lin_mom", "ang_mom", "scale", "static_fric", "bond_small_angle"):
+                assert np.array_equal(getattr(sa, f), getattr(sb, f)), (form, r, f)
+        assert [int(s.steps) for s in b.stats()] == [steps] * 4 and [s.time for s in b.stats()] == [s.time for s in a.stats()]
+        b.close()
+    a.close()
 
 
 def test_reuploading_one_slot_leaves_the_others_running():
