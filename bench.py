@@ -12,8 +12,11 @@ damping/material palette.  One bench "step" = one pass of the hot path over the 
 Printed JSON (one line, rank 0):
   value      voxel-timesteps/s, all GPUs, state already resident in HBM, CUDA events on the batch stream,
              max over ranks.
-  e2e        same metric through the C-ABI host-buffer call vxg_run_batch_host: descriptor flattening,
-             H2D of the whole population, the same number of timesteps, D2H of every voxel position.
+  e2e        same metric through the C-ABI host-buffer call vxg_pop_run_host: descriptor flattening on the host
+             cores, H2D of the whole population, --e2e-timesteps timesteps from the reset state, D2H of every voxel
+             position; pipelined over chunks of robots (flatten / upload / simulate / download overlap).
+  configs    the same two legs for the other BASELINE.json configurations and for evosoro's GA default
+             (6^3 workspace, CPPN-like sparse morphologies, SelfColEnabled=1); N = 1 only.
   roofline   algorithmic HBM bytes (115 + 72*bonds/voxels bytes per voxel-timestep) per
              launch / average launch duration, against MEASURED_PEAKS.json.
   cpu_baseline  the UNMODIFIED reference engine (oracle/_ref/ref_dump, built from /root/reference at
@@ -41,7 +44,8 @@ sys.path.insert(0, ROOT)
 METRIC = "voxel-timesteps/sec"
 UNIT = "voxel-timesteps/s"
 REF_DUMP = os.path.join(ROOT, "oracle", "_ref", "ref_dump")
-INIT_CM_TIME = 0.1   # s: actuation onset of the synthetic inputs (1561 steps), so the timed window covers thermal actuation
+INIT_CM_TIME = 0.02  # s: actuation onset of the synthetic inputs (timestep 313).  Both legs simulate the same window -- timesteps [0, steps x timesteps)
+                     # of a fresh population, 97 % of it thermally actuated at the default 10 x 1000
 
 
 def algorithmic_bytes_per_voxel_step(n_vox: int, n_bond: int) -> float:
@@ -53,13 +57,27 @@ SELFCOL = False  # --selfcol: SelfColEnabled=1 in every .vxa
 WATER = False   # --workload water: BASELINE.json config 5 (land/water fork, fluid drag) instead of the headline config
 
 
-def synthetic_vxa(n: int, seed: int) -> str:
+# the other configurations bench.py reports next to the headline (BASELINE.json configs 1-2, 3, 5 and evosoro's actual GA default)
+OTHER_CONFIGS = [
+    ("BASELINE config 2: 6^3 x 1024, terrestrial", dict(lattice=6, robots=1024)),
+    ("BASELINE config 3: 10^3 x 4096, thermal actuation + floor", dict(lattice=10, robots=4096)),
+    ("BASELINE config 5: land/water 8^3 x 2048, fluid drag", dict(lattice=8, robots=2048, water=True)),
+    ("evosoro GA default: 6^3 workspace, CPPN-like morphologies >= 30 % full (examples/basic.py:114-127), SelfColEnabled=1", dict(lattice=6, robots=1024, selfcol=True, sparse=0.55)),
+]
+
+
+def synthetic_vxa(n: int, seed: int, water=None, selfcol=None, sparse: float = 0.0) -> str:
     from evosoro_b200 import vxa
-    sim = vxa.SimParams(init_cm_time=INIT_CM_TIME, stop_condition_value=5.0, self_col_enabled=1 if SELFCOL else 0)
-    if WATER:   # evosoro/examples/swimming_basic.py:68-70,137-138
+    water = WATER if water is None else water
+    selfcol = SELFCOL if selfcol is None else selfcol
+    sim = vxa.SimParams(init_cm_time=INIT_CM_TIME, stop_condition_value=5.0, self_col_enabled=1 if selfcol else 0)
+    # sparse > 0: a connected blob filling that fraction of the n^3 workspace (fill varies +-0.2 with the seed, never below 0.3)
+    fill = max(0.3, min(1.0, sparse + 0.2 * (((seed * 2654435761) % 1000) / 500.0 - 1.0))) if sparse > 0 else 0.0
+    st = vxa.sparse_lattice(n, seed, fill=fill) if sparse > 0 else vxa.dense_lattice(n, seed)
+    if water:   # evosoro/examples/swimming_basic.py:68-70,137-138
         env = vxa.EnvParams(fluid_environment=1, aggregate_drag_coefficient=750.0)
-        return vxa.vxa_text(vxa.dense_lattice(n, seed), sim=sim, env=env)
-    return vxa.vxa_text(vxa.dense_lattice(n, seed), sim=sim)
+        return vxa.vxa_text(st, sim=sim, env=env)
+    return vxa.vxa_text(st, sim=sim)
 
 
 def workload_name(n: int, robots: int) -> str:
@@ -107,7 +125,8 @@ def run_reference_cpu(lattice: int, warm_ts: int, timed_ts: int, procs: int, tmp
                 f.write(synthetic_vxa(lattice, seed0 + i))
             paths.append(p)
         exe = REF_DUMP + "_lw" if WATER else REF_DUMP
-        ps = [subprocess.Popen([exe, "time", p, str(warm_ts), str(timed_ts), "nocol"], stdout=subprocess.PIPE, text=True) for p in paths]
+        # (the reference arm runs with self-collision exactly when the robots ask for it: --selfcol)
+        ps = [subprocess.Popen([exe, "time", p, str(warm_ts), str(timed_ts)] + ([] if SELFCOL else ["nocol"]), stdout=subprocess.PIPE, text=True) for p in paths]
         outs = [p.communicate()[0] for p in ps]
         vox_steps, worst = 0.0, 0.0
         for o in outs:
@@ -204,10 +223,93 @@ class ClockSampler:
                 "power_w_max": max(pw)}
 
 
+def build_robots(n, count, seed0, water=False, selfcol=False, sparse=0.0):
+    """`count` distinct synthetic robots imported from .vxa text by the product importer (seed = global robot index)."""
+    from evosoro_b200 import engine
+    robots = []
+    for r in range(count):
+        m = engine.Model(text=synthetic_vxa(n, seed0 + r, water=water, selfcol=selfcol, sparse=sparse),
+                         variant=engine.VARIANT_LAND_WATER if water else engine.VARIANT_VOXCAD)
+        robots.append(m.robot)
+        m.close()
+    return robots
+
+
+def _resident_leg(robots, local, TS, K, W, barrier, allreduce_max, sampler, chunk_robots):
+    """The population resident in HBM, as the same chunked batches the e2e call uses (one stream per chunk: the chunks' grids
+    overlap, so a launch's last, partly filled wave of CTAs does not idle SMs); device time from CUDA events on those streams."""
+    import numpy as np
+    from evosoro_b200 import abi, engine
+    rp = engine.Population(robots, device=local, chunk_robots=chunk_robots)
+    rp.step(1); rp.sync()                 # first step (dt = 0 pass)
+    for _ in range(W):                    # warm-up launches: actuated steps of the same robots
+        rp.step(TS)
+    rp.sync()
+    rp.upload(); rp.sync()                # ResetSimulation for the whole population, upload completed here (untimed): the timed
+    launches0 = rp.launch_count()         # launches cover timesteps [0, K * TS) of a fresh population, like an e2e call
+    barrier()
+    if sampler is not None:
+        sampler.start()
+    t_wall0 = time.perf_counter()
+    rp.mark(0)
+    for _ in range(K):
+        rp.step(TS)
+    rp.mark(1)
+    dev_ms = rp.mark_elapsed_ms(0, 1)
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall0) * 1e3
+    clocks = sampler.stop() if sampler is not None else None
+    launches = rp.launch_count() - launches0
+    status = rp.sync()
+    if (status & abi.VXG_ST_DIVERGED).any():
+        raise SystemExit("bench.py: a robot diverged during the timed region")
+    dev_ms, wall_ms = allreduce_max([dev_ms, wall_ms])
+    info = rp.batches()
+    cfg = {"threads": info[0][2], "stride": info[0][1], "family_bits": info[0][3], "robots_per_batch": info[0][0], "batches": len(info),
+           "strides": sorted({b[1] for b in info})}
+    st = rp.stats()
+    fit = np.array([[x.com[0], x.com[1], x.com[2]] for x in st])
+    rp.close()
+    return dev_ms, wall_ms, launches, clocks, cfg, fit
+
+
+def measure(robots, local, TS, K, W, e2e_ts, e2e_calls, barrier, allreduce_max, chunk_robots, sampler=None, ragged=False):
+    """One workload on this rank's GPU.  `value` leg: population resident in HBM; after W warm-up launches the population is
+    reset (untimed) and K launches of TS timesteps are timed with CUDA events on the batch stream -- timesteps [0, K*TS) of a
+    fresh population (actuation starts at timestep init_cm_time / dt).  `e2e` leg: the host-buffer call vxg_pop_run_host --
+    descriptors flattened on the host cores, H2D of the population, e2e_ts timesteps from the reset state (by default the SAME
+    window as the `value` leg), D2H of every voxel position -- pipelined over chunks of `chunk_robots` robots, wall clock
+    around the call."""
+    import numpy as np
+    from evosoro_b200 import abi, engine
+    R = len(robots)
+    vox_total = float(sum(r.n_vox for r in robots))
+    bond_total = float(sum(r.n_bond for r in robots))
+    dev_ms, wall_ms, launches, clocks, cfg, fit = _resident_leg(robots, local, TS, K, W, barrier, allreduce_max, sampler, chunk_robots)
+
+    pop = engine.Population(robots, device=local, chunk_robots=chunk_robots)
+    pos = np.zeros((R, pop.max_vox, 3))
+    pop.run_host(e2e_ts, pos)             # warm-up call (first-touch of the pinned mirrors, kernel attributes)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_calls):
+        pop.run_host(e2e_ts, pos)
+    barrier()
+    e2e_s, = allreduce_max([time.perf_counter() - t0])
+    if not np.isfinite(pos).all():
+        raise SystemExit("bench.py: non-finite positions from the e2e path")
+    out = {"dev_ms": dev_ms, "wall_ms": wall_ms, "launches": launches, "clocks": clocks, "cfg": cfg, "fit": fit,
+           "vox_steps_per_step": vox_total * TS, "n_vox_mean": vox_total / R, "bonds_per_voxel": bond_total / vox_total,
+           "e2e_s": e2e_s, "e2e_units": vox_total * e2e_ts * e2e_calls, "h2d": pop.h2d_bytes(), "d2h": pop.d2h_bytes(),
+           "batches": len(pop.batches()), "e2e_launches": None}
+    pop.close()
+    return out
+
+
 def gpu_arm(args):
     import numpy as np
     import torch
-    from evosoro_b200 import abi, engine
+    from evosoro_b200 import engine
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -241,86 +343,48 @@ def gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    n, R, TS, K, W = args.lattice, args.robots, args.timesteps, args.steps, args.warmup
-    # ---- inputs: R distinct robots per GPU, imported from .vxa text by the product importer ------
-    robots = []
-    for r in range(R):
-        m = engine.Model(text=synthetic_vxa(n, rank * R + r), variant=engine.VARIANT_LAND_WATER if WATER else engine.VARIANT_VOXCAD)
-        robots.append(m.robot)
-        m.close()
-    n_vox, n_bond = robots[0].n_vox, robots[0].n_bond
-    batch = engine.Batch(robots, device=local)
-    cfg = batch.kernel_config()
-
-    # ---- value: state resident in HBM, K launches of TS timesteps --------------------------------
-    batch.step(1); batch.sync()           # uploads the population (untimed), first step (dt = 0 pass)
-    for _ in range(W):
-        batch.step(TS)
-    batch.sync()
-    launches0 = batch.launch_count()
-    sampler = ClockSampler(local)
-    barrier()
-    if rank == 0:
-        sampler.start()
-    t_wall0 = time.perf_counter()
-    batch.mark(0)
-    for _ in range(K):
-        batch.step(TS)
-    batch.mark(1)
-    dev_ms = batch.mark_elapsed_ms(0, 1)
-    barrier()
-    wall_ms = (time.perf_counter() - t_wall0) * 1e3
-    clocks = sampler.stop() if rank == 0 else None
-    launches = batch.launch_count() - launches0
-    status = batch.sync()
-    if (status & abi.VXG_ST_DIVERGED).any():
-        raise SystemExit("bench.py: a robot diverged during the timed region")
-    if dist is not None:
-        t = torch.tensor([dev_ms, wall_ms], device="cuda", dtype=torch.float64)
+    def allreduce_max(vals):
+        if dist is None:
+            return list(vals)
+        t = torch.tensor(list(vals), device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, wall_ms = float(t[0]), float(t[1])
-    units_per_step = float(world) * R * n_vox * TS
-    value = units_per_step * K / (dev_ms * 1e-3)
+        return [float(x) for x in t]
+
+    n, R, TS, K, W = args.lattice, args.robots, args.timesteps, args.steps, args.warmup
+    if args.e2e_timesteps <= 0:
+        args.e2e_timesteps = K * TS
+    robots = build_robots(n, R, rank * R, water=WATER, selfcol=SELFCOL, sparse=args.sparse)
+    n_vox, n_bond = robots[0].n_vox, robots[0].n_bond
+    sampler = ClockSampler(local) if rank == 0 else None
+    m = measure(robots, local, TS, K, W, args.e2e_timesteps, max(1, min(K, args.e2e_steps)), barrier, allreduce_max, args.chunk_robots, sampler,
+                ragged=args.sparse > 0)
+    value = float(world) * m["vox_steps_per_step"] * K / (m["dev_ms"] * 1e-3)
+    e2e_value = float(world) * m["e2e_units"] / m["e2e_s"]
 
     # ---- the trivial end-of-job exchange: per-robot fitness scalars gathered on every rank (not timed) ---
-    st = batch.stats()
-    fit = np.array([[s.com[0], s.com[1], s.com[2]] for s in st])
+    fit = m["fit"]
     if dist is not None:
         tf = torch.from_numpy(fit).cuda()
         allf = [torch.empty_like(tf) for _ in range(world)]
         dist.all_gather(allf, tf)
         fit = torch.cat(allf).cpu().numpy()
     fitness_checksum = float(np.sum(fit))
-    batch.close()
 
-    # ---- e2e: host descriptors -> flatten -> H2D -> TS timesteps -> D2H positions, every step -------
-    eb = engine.Batch(robots, device=local, upload=False)
-    pos = np.zeros((R, eb.limits.max_vox, 3))
-    ke = max(1, min(K, args.e2e_steps))
-    for _ in range(min(W, 2)):
-        eb.run_batch_host(TS, pos)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(ke):
-        eb.run_batch_host(TS, pos)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    if dist is not None:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t[0])
-    e2e_value = units_per_step * ke / e2e_s
-    h2d = eb.h2d_bytes_per_upload()
-    stride = 64
-    while stride < eb.limits.max_vox:
-        stride *= 2
-    for lo, hi in ((128, 224), (256, 352), (512, 736)):   # stride_for(), csrc/vx_robot.cuh
-        if lo < eb.limits.max_vox <= hi:
-            stride = hi
-    d2h = R * stride * 3 * 8   # the position planes of every blob at the device stride (the per-robot control blocks, ~0.3 KB each, not counted)
-    if not np.isfinite(pos).all():
-        raise SystemExit("bench.py: non-finite positions from the e2e path")
-    eb.close()
+    # ---- the other BASELINE.json configurations and evosoro's GA default, same legs, fewer repetitions (N = 1 only) -------
+    configs = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        peak, _ = measured_peak_gbs()
+        configs = []
+        for name, kw in OTHER_CONFIGS:
+            t0 = time.perf_counter()
+            rb = build_robots(kw["lattice"], kw["robots"], 0, water=kw.get("water", False), selfcol=kw.get("selfcol", False), sparse=kw.get("sparse", 0.0))
+            c = measure(rb, local, TS, 3, 3, 3 * TS, 1, barrier, allreduce_max, args.chunk_robots, ragged=kw.get("sparse", 0.0) > 0)
+            v = c["vox_steps_per_step"] * 3 / (c["dev_ms"] * 1e-3)
+            bpv = 115.0 + 72.0 * c["bonds_per_voxel"]
+            configs.append({"config": name, **{k: kw[k] for k in kw}, "voxels_per_robot": c["n_vox_mean"], "value": v, "unit": UNIT,
+                            "ms_per_step": c["dev_ms"] / 3, "roofline_frac": v * bpv / 1e9 / peak, "algorithmic_bytes_per_voxel_step": bpv,
+                            "e2e": c["e2e_units"] / c["e2e_s"], "kernel": c["cfg"], "batches": c["batches"], "wall_s": time.perf_counter() - t0})
+            del rb
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------------
     cpu = None
@@ -334,9 +398,10 @@ def gpu_arm(args):
                          f"{warm_ts} warm-up + {timed_ts} timed TimeStep() calls, {wall:.1f} s"}
 
     if rank == 0:
-        bpv = algorithmic_bytes_per_voxel_step(n_vox, n_bond)
+        launches, dev_ms, cfg = m["launches"], m["dev_ms"], m["cfg"]
+        bpv = algorithmic_bytes_per_voxel_step(n_vox, n_bond) if args.sparse <= 0 else 115.0 + 72.0 * m["bonds_per_voxel"]
         launch_s = dev_ms * 1e-3 / max(1, launches)
-        alg_bytes_per_launch = bpv * R * n_vox * TS * (K / max(1, launches))
+        alg_bytes_per_launch = bpv * m["vox_steps_per_step"] * (K / max(1, launches))
         peak, peak_src = measured_peak_gbs()
         achieved = alg_bytes_per_launch / launch_s / 1e9
         line = {
@@ -345,18 +410,24 @@ def gpu_arm(args):
             "dtype": "f32 (forces, moments, quaternions, momenta) + f64 (positions, time, scale law)", "data": "synthetic",
             "config": {"workload": workload_name(n, R),
                        "lattice": n, "robots_per_gpu": R, "timesteps_per_step": TS, "init_cm_time_s": INIT_CM_TIME,
-                       "l2": f"inputs larger than L2: {R} robot blobs x {cfg['blob_bytes']} B = {R * cfg['blob_bytes'] / 1e6:.0f} MB streamed per launch (L2 126 MB)",
+                       "l2": f"inputs larger than L2: {R} robot blobs of {216 * cfg['stride']} B = {R * 216 * cfg['stride'] / 1e6:.0f} MB streamed through per launch wave (L2 126 MB); state on chip inside a launch",
                        "kernel": cfg, "parallelism": f"{world} x independent shards, no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic_per_launch(n, R, TS), "peak_source": peak_src,
                          "algorithmic_bytes_per_voxel_step": bpv, "algorithmic_bytes_per_launch": alg_bytes_per_launch,
-                         "launch_ms": launch_s * 1e3, "kernel": "vx_step_kernel",
-                         "note": "state is shared-memory resident inside a launch, so achieved is EFFECTIVE algorithmic bandwidth; physical DRAM bytes are in `traffic`"},
+                         "launch_ms": launch_s * 1e3, "kernel": "vx_step_kernel_g" if not (SELFCOL or WATER) and cfg["stride"] <= 1024 else "vx_step_kernel",
+                         "launches_overlap": f"{cfg['batches']} batches on their own streams: achieved = algorithmic bytes of all launches / device time of the region",
+                         "note": "state is on-chip (shared + tensor memory) inside a launch, so achieved is EFFECTIVE algorithmic bandwidth; physical DRAM bytes are in `traffic`"},
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": ke,
-                    "call": "vxg_run_batch_host (flatten + upload + step + download positions)"},
-            "gpu_launches": launches, "wall_ms_per_step": wall_ms / K, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"], "steps": max(1, min(K, args.e2e_steps)),
+                    "timesteps_per_step": args.e2e_timesteps,
+                    "call": f"vxg_pop_run_host (flatten + upload + {args.e2e_timesteps} timesteps from the reset state + download positions), "
+                            f"pipelined over {m['batches']} chunks of <= {args.chunk_robots} robots",
+                    "regime": f"timesteps 0..{args.e2e_timesteps - 1} of a fresh population; actuation starts at timestep {int(INIT_CM_TIME / 6.405863e-05) + 1}; "
+                              f"`value` is timed on timesteps 0..{K * TS - 1} of the same population"},
+            "gpu_launches": launches, "wall_ms_per_step": m["wall_ms"] / K, "clocks": m["clocks"],
             "fitness_gather": {"robots": int(fit.shape[0]), "checksum": fitness_checksum},
+            "configs": configs,
         }
         print(json.dumps(line))
     if dist is not None:
@@ -376,7 +447,11 @@ def main():
     ap.add_argument("--timesteps", type=int, default=1000, help="simulation timesteps per bench step (one launch)")
     ap.add_argument("--ref-timesteps", type=int, default=300, help="timesteps per bench step of the CPU reference arm")
     ap.add_argument("--cpu-timesteps", type=int, default=10000, help="timed timesteps of the cpu_baseline sample")
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=2, help="timed e2e calls")
+    ap.add_argument("--e2e-timesteps", type=int, default=0, help="timesteps per e2e call (from the reset state); 0 = steps x timesteps, the window `value` is timed on")
+    ap.add_argument("--chunk-robots", type=int, default=128, help="pipelining granularity of the e2e call")
+    ap.add_argument("--sparse", type=float, default=0.0, help="> 0: CPPN-like connected blobs filling about this fraction of the workspace")
+    ap.add_argument("--no-configs", action="store_true", help="skip the `configs` block (other BASELINE configurations)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--selfcol", action="store_true", help="SelfColEnabled=1 (evosoro's GA default): the self-collision kernel family; our arm only")
     ap.add_argument("--workload", default="land", choices=["land", "water"], help="water = BASELINE config 5 (use --lattice 8 --robots 2048)")

@@ -1,7 +1,7 @@
 // voxelyze_main.cpp -- drop-in for the reference CLI `./voxelyze -f <file.vxa> [-p]`
 // (evosoro/_voxcad/voxelyzeMain/main.cpp:9-133) on top of libvxgpu.so, plus the batched form the GPU wants:
 //
-//     voxelyze -f a.vxa [-f b.vxa ...] [--batch <dir>] [-p] [--device N] [--lw] [--ignore-collisions]
+//     voxelyze -f a.vxa [-f b.vxa ...] [--batch <dir>] [-p] [--device N | --devices 0,1,..] [--lw] [--ignore-collisions] [--plan]
 //
 // Every file is imported (LoadVXAFile + Import), the whole set is simulated as ONE batch on the GPU until
 // each robot's stop condition, and each robot's <FitnessFileName> is written with the reference's tag set
@@ -24,8 +24,8 @@
 
 int main(int argc, char** argv) {
     std::vector<std::string> files;
-    bool print_scrn = false, lw = false, ignore_col = false;
-    int device = 0;
+    bool print_scrn = false, lw = false, ignore_col = false, plan_only = false;
+    std::vector<int> devices;
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "-f") && i + 1 < argc) files.push_back(argv[++i]);
         else if (!strcmp(argv[i], "--batch") && i + 1 < argc) {
@@ -41,10 +41,15 @@ int main(int argc, char** argv) {
         else if (!strcmp(argv[i], "-p")) print_scrn = true;
         else if (!strcmp(argv[i], "--lw")) lw = true;
         else if (!strcmp(argv[i], "--ignore-collisions")) ignore_col = true;
-        else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--device") && i + 1 < argc) devices.push_back(atoi(argv[++i]));
+        else if (!strcmp(argv[i], "--devices") && i + 1 < argc) {   // --devices 0,1,2,3: the population is sharded over these GPUs
+            for (char* t = strtok(argv[++i], ","); t; t = strtok(nullptr, ",")) devices.push_back(atoi(t));
+        }
+        else if (!strcmp(argv[i], "--plan")) plan_only = true;     // import only: print "<file> <voxels> <bonds> <timesteps>" per input
         else if (!strcmp(argv[i], "--computeShapeDescriptors")) { fprintf(stderr, "voxelyze: --computeShapeDescriptors (qhull) is not supported\n"); return 0; }
     }
     if (files.empty()) { printf("\nInput file required. Quitting.\n"); return 0; }
+    if (devices.empty()) devices.push_back(0);
 
     // Import every file on the host cores (LoadVXAFile + Import + the step plan are independent per file).  A file that cannot
     // be read or that enables something the kernels do not implement is dropped WITH a message and the others still run: the
@@ -86,22 +91,55 @@ int main(int argc, char** argv) {
         descs[r] = *vxh_desc(models[r]);
         if (print_scrn) printf("Imported %s: %d voxels, %d bonds, %lld steps\n", files[src[r]].c_str(), descs[r].n_vox, descs[r].n_bond, (long long)total[r]);
     }
-    // The whole set is one ragged population: the library buckets it by voxel stride and kernel family (a 40-voxel CPPN robot
-    // does not pay for a 216-voxel batch-mate's stride, nor a plain robot for a self-colliding one's kernel) and runs the
-    // buckets concurrently; every robot stops at its own step budget.
+    if (plan_only) {
+        for (int r = 0; r < n; r++) printf("%s %d %d %lld\n", files[src[r]].c_str(), descs[r].n_vox, descs[r].n_bond, (long long)total[r]);
+        for (int r = 0; r < n; r++) vxh_free(models[r]);
+        return n_failed ? 0 : 1;
+    }
+    // The whole set is one ragged population per GPU: the library buckets it by voxel stride and kernel family (a 40-voxel CPPN
+    // robot does not pay for a 216-voxel batch-mate's stride, nor a plain robot for a self-colliding one's kernel) and runs the
+    // buckets concurrently; every robot stops at its own step budget.  Over several GPUs the robots are dealt out by cost --
+    // timesteps x voxels, largest first onto the least loaded device (a robot with a bone-bone bond takes ten
+    // times the steps of an all-tissue one) -- not by count.  No exchange between the devices: robots are independent.
+    const int n_dev = (int)devices.size();
+    std::vector<std::vector<int>> shard(n_dev);
+    {
+        std::vector<int> order(n);
+        for (int r = 0; r < n; r++) order[r] = r;
+        auto cost = [&](int r) { return (double)total[r] * (double)descs[r].n_vox; };
+        std::sort(order.begin(), order.end(), [&](int a, int b) { return cost(a) != cost(b) ? cost(a) > cost(b) : a < b; });
+        std::vector<double> load(n_dev, 0.0);
+        for (int r : order) { int d = (int)(std::min_element(load.begin(), load.end()) - load.begin()); shard[d].push_back(r); load[d] += cost(r); }
+        for (auto& sh : shard) std::sort(sh.begin(), sh.end());
+    }
     vxg_pop_options opt; memset(&opt, 0, sizeof opt);
     opt.precision = VXG_PREC_F32;
     opt.want_mesh = 1;   // the land/water result file reports the volume of the deformed surface mesh for every robot of that fork
-    vxg_population* pop = nullptr;
-    int rc = vxg_pop_create(&pop, device, descs.data(), n, &opt);
-    if (!rc) rc = vxg_pop_set_plan(pop, total.data(), latch.data(), eol.data());
-    if (!rc) rc = vxg_pop_run(pop);   // whole lifetimes on the device
+    std::vector<vxg_population*> pops(n_dev, nullptr);
     std::vector<uint32_t> status(n, 0);
-    if (!rc) rc = vxg_pop_sync(pop, status.data());
     std::vector<vxg_robot_stats> stats(n);
-    if (!rc) rc = vxg_pop_reduce_stats(pop, stats.data());
+    int rc = 0;
+    for (int d = 0; d < n_dev && !rc; d++) {   // create + start every device's share (asynchronous), then collect
+        const std::vector<int>& sh = shard[d];
+        if (sh.empty()) continue;
+        std::vector<vxg_robot_desc> dd; std::vector<int64_t> t, l, e;
+        for (int r : sh) { dd.push_back(descs[r]); t.push_back(total[r]); l.push_back(latch[r]); e.push_back(eol[r]); }
+        rc = vxg_pop_create(&pops[d], devices[d], dd.data(), (int)sh.size(), &opt);
+        if (!rc) rc = vxg_pop_set_plan(pops[d], t.data(), l.data(), e.data());
+        if (!rc) rc = vxg_pop_run(pops[d]);   // whole lifetimes on the device
+    }
+    long long n_batches = 0, n_launches = 0;
+    for (int d = 0; d < n_dev && !rc; d++) {
+        if (!pops[d]) continue;
+        const std::vector<int>& sh = shard[d];
+        std::vector<uint32_t> st(sh.size()); std::vector<vxg_robot_stats> ss(sh.size());
+        rc = vxg_pop_sync(pops[d], st.data());
+        if (!rc) rc = vxg_pop_reduce_stats(pops[d], ss.data());
+        for (size_t i = 0; i < sh.size() && !rc; i++) { status[sh[i]] = st[i]; stats[sh[i]] = ss[i]; }
+        n_batches += vxg_pop_n_batches(pops[d]); n_launches += vxg_pop_launch_count(pops[d]);
+    }
     if (rc) { fprintf(stderr, "voxelyze: %s\n", vxg_last_error()); return 0; }
-    if (print_scrn) printf("%d robots in %d batches, %lld kernel launches\n", n, vxg_pop_n_batches(pop), (long long)vxg_pop_launch_count(pop));
+    if (print_scrn) printf("%d robots on %d device(s) in %lld batches, %lld kernel launches\n", n, n_dev, n_batches, n_launches);
     for (int r = 0; r < n; r++) {
         vxh_info info; vxh_get_info(models[r], &info);
         const char* file = files[src[r]].c_str();
@@ -119,7 +157,7 @@ int main(int argc, char** argv) {
         }
         vxh_free(models[r]);
     }
-    vxg_pop_destroy(pop);
+    for (auto* p : pops) vxg_pop_destroy(p);
     if (n_failed) fprintf(stderr, "voxelyze: %d of %d robots did not produce a result\n", n_failed, n_files);
     return n_failed ? 0 : 1;
 }

@@ -201,7 +201,7 @@ template <typename Real> struct BondPush { int w; V3<Real> f2, m2; };   // w < 0
 // registers across the three axes by the caller).  rec != nullptr: also store the bond outputs
 // ([39][nv] planes, vxg_download_state).  Touches no accumulator, so it needs no ordering against the
 // other voxels' pushes.  Returns true when the bond diverged (strain > 100, VX_Sim.cpp:1775).
-template <typename Real, int AX, bool COMPACT = false, bool FLUID = false>
+template <typename Real, int AX, bool COMPACT = false, bool FLUID = false, bool HOIST = true>
 VX_HD bool bond_eval(const RobotView<Real>& R, const RobotConsts<Real>& C, int v, const VoxStat& st, const OwnState<Real>& own,
                      uint32_t& fl, Real dt_inv, V3<Real>& F, V3<Real>& M, Real* rec, BondPush<Real>& p) {
     const int nv = R.nv;
@@ -233,7 +233,7 @@ VX_HD bool bond_eval(const RobotView<Real>& R, const RobotConsts<Real>& C, int v
         h.a2 = mk3<Real>(b.z, b.w, c);
     }
     BondOut<Real> o;
-    bond_force<AX, Real, COMPACT>(k, e, q1, q2, dnom, C.half_bond_z, dt_inv, C.sym_mass, small, h, o);
+    bond_force<AX, Real, COMPACT, HOIST>(k, e, q1, q2, dnom, C.half_bond_z, dt_inv, C.sym_mass, small, h, o);
     if (!o.changed) {   // _LastPos2/_LastAngle* keep their values on a mode-flip step (VXS_BondInternal.cpp:157)
         R4<Real> a, b;
         a.x = h.p2.x; a.y = h.p2.y; a.z = h.p2.z; a.w = h.a1.x;

@@ -62,7 +62,12 @@ template <typename Real> static BatchDev<Real> dev_view(const vxg_batch* b) {
 static cudaError_t launch_step_p(vxg_batch* b, int n_steps, int record) {
     LaunchCfg c; c.n_robots = b->n_robots; c.nv = b->L.nv; c.smem_bytes = b->smem_bytes; c.stream = b->stream; c.n_steps = n_steps; c.record = record;
     c.vpt = b->vpt;
-    if (b->prec == VXG_PREC_F64) return launch_f64(dev_view<double>(b), c, b->smem_mode);
+    if (b->prec == VXG_PREC_F64) {
+        // fluid drag / self-collision in fp64 run on the blob in global memory (one code path for every robot size: this is the
+        // logic-parity mode, not a production one)
+        if (b->L.nvert_cap > 0 || b->lim.max_col_pairs > 0) return launch_f64_extras_global(dev_view<double>(b), c, b->L.nvert_cap > 0, b->lim.max_col_pairs > 0);
+        return launch_f64(dev_view<double>(b), c, b->smem_mode);
+    }
     const BatchDev<float> B = dev_view<float>(b);
     if ((b->L.nvert_cap > 0 || b->lim.max_col_pairs > 0) && !b->smem_mode) return launch_f32_extras_global(B, c, b->L.nvert_cap > 0, b->lim.max_col_pairs > 0);
     if (b->L.nvert_cap > 0)
@@ -103,7 +108,6 @@ extern "C" int vxg_create(vxg_batch** out, int device, int n_robots, const vxg_l
     b->device = device; b->n_robots = n_robots; b->lim = *lim; b->prec = lim->precision;
     if (lim->max_vox > 2048) { delete b; return fail(VXG_UNSUPPORTED_SIZE, "vxg_create: more than 2048 voxels per robot is not supported yet"); }
     if (lim->max_mesh_verts < 0 || lim->max_mesh_verts > 32767) { delete b; return fail(VXG_ERR_ARG, "vxg_create: max_mesh_verts out of range"); }
-    if (lim->max_mesh_verts > 0 && lim->precision != VXG_PREC_F32) { delete b; return fail(VXG_UNSUPPORTED_FEATURE, "vxg_create: the fluid-drag kernels exist in fp32 only"); }
     b->L = make_layout(stride_for(lim->max_vox), (int)b->rs(), (lim->max_mesh_verts + 31) & ~31);
     // thread mapping: <= 512 threads per CTA, VPT voxels per thread
     b->vpt = b->L.nv <= 512 ? 1 : b->L.nv / 512;
@@ -118,7 +122,6 @@ extern "C" int vxg_create(vxg_batch** out, int device, int n_robots, const vxg_l
     b->tb_compact = tables_bytes<float>(lim->max_vclass, lim->max_bclass, true, mc);
     b->smem_wide_fits = b->L.total_bytes + tb <= (size_t)max_smem;
     b->smem_mode_wide_or_compact = b->prec == VXG_PREC_F32 && b->L.total_bytes + b->tb_compact <= (size_t)max_smem;
-    if (mc > 0 && lim->precision != VXG_PREC_F32) { delete b; return fail(VXG_UNSUPPORTED_FEATURE, "vxg_create: the self-collision kernels exist in fp32 only"); }
     b->smem_mode = b->smem_wide_fits || b->smem_mode_wide_or_compact;   // final choice is made at flush, when the classes are known
     b->smem_bytes = b->smem_mode ? b->L.total_bytes + tb : tb;
 
@@ -251,7 +254,8 @@ extern "C" int vxg_upload(vxg_batch* b, int robot, const vxg_robot_desc* d) {
     }
     if (b->L.nvert_cap > 0) {   // surface-mesh tables (also for non-fluid robots of a fluid batch: cheap, keeps one code path)
         int nfc = 0;
-        int nvx = pack_mesh<float>(d, b->L, b->h_blobs + (size_t)robot * b->L.total_bytes, &nfc);
+        int nvx = b->prec == VXG_PREC_F64 ? pack_mesh<double>(d, b->L, b->h_blobs + (size_t)robot * b->L.total_bytes, &nfc)
+                                          : pack_mesh<float>(d, b->L, b->h_blobs + (size_t)robot * b->L.total_bytes, &nfc);
         if (nvx == -2) return fail(VXG_UNSUPPORTED_SIZE, "vxg_upload: robot %d has more surface facets than the batch's mesh capacity holds (raise limits.max_mesh_verts)", robot);
         b->h_ctl[robot].n_facet = nfc;
         if (nvx < 0) return fail(VXG_UNSUPPORTED_SIZE, "vxg_upload: robot %d has more than max_mesh_verts = %d surface-mesh vertices", robot, b->lim.max_mesh_verts);
@@ -341,7 +345,11 @@ int vxg_i_flush(vxg_batch* b) {
         // than 512 x 2 at 128 registers -- more warps hide the barrier and shared-memory latency); the other families keep 512 x 2
         if (b->L.nv == 1024) { b->vpt = (compact && b->lim.max_col_pairs == 0 && b->L.nvert_cap == 0) ? 1 : 2; b->threads = b->L.nv / b->vpt; }
         if (compact) { b->smem_mode = true; b->smem_bytes = b->L.total_bytes + b->tb_compact; }
-        else { b->smem_mode = b->smem_wide_fits; b->smem_bytes = b->smem_wide_fits ? b->L.total_bytes + b->tb_wide : b->tb_wide; }
+        else {
+            const bool f64_extras = b->prec == VXG_PREC_F64 && (b->L.nvert_cap > 0 || b->lim.max_col_pairs > 0);   // global-memory path only
+            b->smem_mode = b->smem_wide_fits && !f64_extras;
+            b->smem_bytes = b->smem_mode ? b->L.total_bytes + b->tb_wide : b->tb_wide;
+        }
         if (b->dirty) { int rc = flush_state(b); if (rc) return rc; }
         if (compact) CK(cudaMemcpyAsync(b->d_bk, b->h_bkc, nr * mb * b->bkc_sz(), cudaMemcpyHostToDevice, b->stream));
         if (compact) CK(cudaMemcpyAsync(b->d_bpair, b->h_bpair, nr * mb * sizeof(uint32_t), cudaMemcpyHostToDevice, b->stream));

@@ -23,6 +23,7 @@
 #pragma once
 #include <cstdio>
 #include "vxg_kernels.cuh"
+#include "vxg_launch.cuh"
 
 namespace vx {
 
@@ -118,15 +119,18 @@ template <int AX> __device__ inline void hist_store(uint32_t tm, const BondHist<
 
 // One owned bond in the gather form.  `st` carries the zero class for a missing neighbour (patched once per launch), so every
 // lane runs the same code; the warp skips the axis when none of its lanes has a bond there.
-template <int AX, bool HOIST>
+//   F_REGS : the own share of the force accumulates in registers (else it is re-read from this thread's staging slots in the voxel
+//            phase: three registers less across the bond phase).  Measured: registers +0.7 % at 10^3, re-read +0.5 % at 8^3.
+template <int AX, bool HOIST, bool F_REGS>
 __device__ __forceinline__ bool bond_eval_g(unsigned char* smem, const GLayout& G, int NV, const RobotConsts<float>& C, const BondKm* bkm, int tid, const VoxStat& st,
-                                            const OwnState<float>& own, uint32_t& fl, float dt_inv, uint32_t tm, V3<float>& M) {
+                                            const OwnState<float>& own, uint32_t& fl, float dt_inv, uint32_t tm, V3<float>& F, V3<float>& M) {
     const int w = st.nbr[AX];
     if (!__any_sync(0xffffffffu, w >= 0)) return false;
     const int wq = w >= 0 ? w : tid;
     const int bc = st.bcls[AX];
     float ha[8], hc;
     hist_issue<AX>(tm, ha, hc);   // the history is on its way from tensor memory while the neighbour's state is fetched
+
     const BondK<float> k = bond_from_km(bkm[bc]);
     const double* pos = (const double*)(smem + G.off_pos);
     double dpa[3] = {pos[wq] - own.px, pos[NV + wq] - own.py, pos[2 * NV + wq] - own.pz};
@@ -146,7 +150,8 @@ __device__ __forceinline__ bool bond_eval_g(unsigned char* smem, const GLayout& 
     if (__any_sync(0xffffffffu, o.changed)) { BondHist<float> old; hist_load<AX>(tm, old); if (o.changed) h = old; }
     hist_store<AX>(tm, h);
     fl = (fl & ~(1u << AX)) | ((small ? 1u : 0u) << AX);
-    M = M + o.m1;   // (the own share of the force is read back from the staging slot in the voxel phase: three registers less)
+    if (F_REGS) F = F + o.f1;   // (else the own share of the force is read back from the staging slot in the voxel phase)
+    M = M + o.m1;
     R4<float> a; a.x = o.f1.x; a.y = o.f1.y; a.z = o.f1.z; a.w = o.m2.x;
     R2<float> b; b.x = o.m2.y; b.y = o.m2.z;
     ((R4<float>*)(smem + G.off_stA[AX]))[tid] = a;
@@ -156,14 +161,14 @@ __device__ __forceinline__ bool bond_eval_g(unsigned char* smem, const GLayout& 
 
 // Voxel phase of the gather form: the shares of the -X/-Y/-Z bonds (Force2 = -Force1, Moment2) from their owners' staging slots,
 // then EulerStep; the new position / orientation go to shared memory for the neighbours and stay in `own` for the next step.
-__device__ __forceinline__ void voxel_phase_g(unsigned char* smem, const GLayout& G, int NV, const RobotConsts<float>& C, const RobotView<float>& R, int tid,
-                                              const VoxStat& st, uint2 nb, OwnState<float>& own, uint32_t& fl, V3<float> M) {
-    V3<float> F;
+template <bool F_REGS>
+__device__ __forceinline__ float voxel_phase_g(unsigned char* smem, const GLayout& G, int NV, const RobotConsts<float>& C, const RobotView<float>& R, int tid,
+                                              const VoxStat& st, uint2 nb, OwnState<float>& own, uint32_t& fl, V3<float> F, V3<float> M) {
     const int mX = nb.x & 0xFFFFu, mY = nb.x >> 16, mZ = nb.y & 0xFFFFu;
     const R4<float> ax = ((const R4<float>*)(smem + G.off_stA[0]))[mX], ay = ((const R4<float>*)(smem + G.off_stA[1]))[mY], az = ((const R4<float>*)(smem + G.off_stA[2]))[mZ];
     const R2<float> bx = ((const R2<float>*)(smem + G.off_stB[0]))[mX], by = ((const R2<float>*)(smem + G.off_stB[1]))[mY], bz = ((const R2<float>*)(smem + G.off_stB[2]))[mZ];
     // own shares: Force1 of the owned X, Y, Z bonds, as staged by this very thread (axes the voxel has no bond on staged zeros)
-    {
+    if (!F_REGS) {
         const R4<float> ox = ((const R4<float>*)(smem + G.off_stA[0]))[tid], oy = ((const R4<float>*)(smem + G.off_stA[1]))[tid], oz = ((const R4<float>*)(smem + G.off_stA[2]))[tid];
         F = mk3<float>(((0.0f + ox.x) + oy.x) + oz.x, ((0.0f + ox.y) + oy.y) + oz.y, ((0.0f + ox.z) + oy.z) + oz.z);
     }
@@ -187,6 +192,33 @@ __device__ __forceinline__ void voxel_phase_g(unsigned char* smem, const GLayout
     R2<float> nb2; nb2.x = vs.am.y; nb2.y = vs.am.z;
     R.momA[tid] = na; R.momB[tid] = nb2;
     fl = sf ? (fl | VX_FL_STATIC_FRIC) : (fl & ~VX_FL_STATIC_FRIC);
+    const V3<float> vel = vs.lm * kv.mass_inv;
+    return dot(vel, vel);   // |Vel|^2 after the step (SS.MaxVoxVel, VX_Sim.cpp:1626-1649)
+}
+
+// Per-voxel view of the contact-bond list (CSR): seg[v] = begin | end << 16 into adj[], the partners of voxel v in list order (the
+// list is sorted by (v1, v2) with v1 < v2, so that is ascending partner index).  Built once per list rebuild -- a fraction of a
+// percent to a few percent of the steps -- so that a step costs a voxel one word and its own contacts instead of a scan of every
+// pair of the robot (CVXS_Voxel's ColBondInds, VXS_Voxel.cpp:516-528).
+static __device__ __noinline__ void col_csr_build(const ColPair* pairs, int n_col, uint32_t* seg, uint16_t* adj, int* scratch /* [33] */) {
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = T >> 5;
+    int cnt = 0;
+    for (int k = 0; k < n_col; k++) { const ColPair p = pairs[k]; cnt += (p.v1 == tid ? 1 : 0) + (p.v2 == tid ? 1 : 0); }
+    int inc = cnt;
+    for (int o = 1; o < 32; o <<= 1) { int x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
+    __syncthreads();
+    if (lane == 31) scratch[wid] = inc;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < wid && w < nw; w++) base += scratch[w];
+    int off = base + inc - cnt;
+    seg[tid] = (uint32_t)off | ((uint32_t)(off + cnt) << 16);
+    if (cnt > 0)
+        for (int k = 0; k < n_col; k++) {
+            const ColPair p = pairs[k];
+            if (p.v1 == tid) adj[off++] = (uint16_t)p.v2; else if (p.v2 == tid) adj[off++] = (uint16_t)p.v1;
+        }
+    __syncthreads();
 }
 
 // Dataflow form (FLOW): within a window of up to VXG_FLOW_R timesteps the warps are not held together by CTA-wide barriers at all.
@@ -215,14 +247,17 @@ __device__ inline void flow_wait(unsigned long long* bar, uint32_t mask, uint32_
 //   CV, CB : compile-time capacities of the voxel / bond class tables in shared memory (0 = the batch's run-time limits).  With them
 //            every shared-memory address in the step loop is the CTA's base plus an immediate; with run-time capacities the
 //            table pointers were rematerialised over and over at 64 registers (5 % of the executed instructions, ncu).
-template <int NV, bool FLOW, int CV, int CB>
-__global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, false, false)) vx_step_kernel_g(BatchDev<float> B, int n_steps) {
+//   COLLIDE: self-collision (contact-bond list in shared memory, rebuilt on the device, contact forces through the per-voxel CSR)
+template <int NV, bool FLOW, int CV, int CB, bool COLLIDE = false>
+__global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, COLLIDE, false)) vx_step_kernel_g(BatchDev<float> B, int n_steps) {
+    static_assert(!(FLOW && COLLIDE), "the dataflow form has no per-step CTA-wide reduction");
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int T = NV;
     constexpr BlobLayout L = make_layout(NV, 4);
     constexpr GLayout G = make_glayout(NV);
     constexpr int TM_COLS = tm_cols_for(NV);
     constexpr bool HOIST = !(NV == 1024 || NV == 512);   // bond_force: only where there are more than 64 registers per thread
+    constexpr bool F_REGS = NV == 1024 || COLLIDE;        // (contact forces join the own share before the barrier)
     const int robot = blockIdx.x;
     int tid;
     asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
@@ -239,7 +274,8 @@ __global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, false, false)) vx_step
     const int mv = CV > 0 ? CV : B.max_vclass;
     BondKm* bkm = (BondKm*)(smem + G.total);
     unsigned char* tabp = smem + G.total + sizeof(BondKm) * (size_t)MB;
-    SmemTables<float> S = carve_tables<float>(tabp, mv, MB, true, 0);
+    const int max_col = COLLIDE ? B.max_col : 0;
+    SmemTables<float> S = carve_tables<float>(tabp, mv, MB, true, max_col);
     const int n_vox = ctlp->n_vox, n_vc = ctlp->n_vclass, n_bc = ctlp->n_bclass;
     const unsigned int flags = ctlp->flags;
     const int ZC = n_bc;               // index of the zero class
@@ -331,7 +367,9 @@ __global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, false, false)) vx_step
     const uint2 nb = ((const uint2*)(smem + G.off_nbm))[tid];   // -X | -Y << 16, -Z
     const float dt_inv_run = (float)(1.0 / dt);
     // ---- dataflow form: table ring, per-warp phase barriers, dependency masks --------------------------------------------
-    unsigned char* fp = tabp + tables_bytes<float>(mv, MB, true, 0);
+    unsigned char* fp = tabp + tables_bytes<float>(mv, MB, true, max_col);
+    uint32_t* c_seg = (uint32_t*)fp;                    // self-collision: per-voxel segments of c_adj (the flow ring shares the address: never both)
+    uint16_t* c_adj = (uint16_t*)(fp + sizeof(uint32_t) * NV);
     double* r_scale = (double*)fp;                      fp += vx_align16(sizeof(double) * VXG_FLOW_RING * mv);
     float* r_dsc = (float*)fp;                          fp += vx_align16(sizeof(float) * VXG_FLOW_RING * mv);
     float* r_dnom = (float*)fp;                         fp += vx_align16(sizeof(float) * VXG_FLOW_RING * MB);
@@ -368,6 +406,24 @@ __global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, false, false)) vx_step
         if (tid == 0) f_time[0] = ctlp->cur_time;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         __syncthreads();
+    }
+
+    // self-collision state (CVX_Sim::UpdateCollisions, VX_Sim.cpp:1729-1755): the list lives in shared memory during the launch
+    const bool col_on = COLLIDE && (flags & VXG_F_COLLISIONS_) != 0 && max_col > 0;
+    ColTables CT;
+    CT.surf = B.col_surf + (size_t)robot * NV; CT.lat4 = B.col_lat4 + (size_t)robot * NV * 4; CT.near = B.col_near + (size_t)robot * NV;
+    CT.n_surf = ctlp->n_surf; CT.hops = ctlp->col_hops;
+    int n_col = col_on ? ctlp->n_col : 0;
+    bool col_first = ctlp->col_first != 0, col_overflow = false;
+    const bool col_host = ctlp->col_host != 0;
+    if (COLLIDE && col_on) {
+        for (int i = tid; i < n_col; i += T) S.pairs[i] = B.col_pairs[(size_t)robot * max_col + i];
+        if (tid == 0) {
+            S.maxvel[0] = 0u; S.maxvel[1] = 0u; S.colflag[0] = 0u; S.colflag[1] = 0u;
+            S.colstate[0] = ctlp->col_acc; S.colstate[1] = ctlp->max_vel; S.colstate[2] = ctlp->col_horizon; S.colstate[3] = ctlp->lattice_dim;
+        }
+        __syncthreads();
+        if (n_col > 0) col_csr_build(S.pairs, n_col, c_seg, c_adj, (int*)S.red);
     }
 
     double t = ctlp->cur_time;
@@ -419,16 +475,16 @@ __global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, false, false)) vx_step
                     f_time[2 + my_class] = sc_t + dt;
                     r_scale[ea * mv + my_class] = ns; r_dsc[ea * mv + my_class] = (float)(ns - S.sk[my_class].nom_size);
                 }
-                V3<float> M = mk3<float>(0, 0, 0);
-                bool dv = bond_eval_g<0, HOIST>(smem, G, NV, C, bkm, tid, st, own, fl, dt_inv, tm, M);
-                dv |= bond_eval_g<1, HOIST>(smem, G, NV, C, bkm, tid, st, own, fl, dt_inv, tm, M);
-                dv |= bond_eval_g<2, HOIST>(smem, G, NV, C, bkm, tid, st, own, fl, dt_inv, tm, M);
+                V3<float> F = mk3<float>(0, 0, 0), M = mk3<float>(0, 0, 0);
+                bool dv = bond_eval_g<0, HOIST, F_REGS>(smem, G, NV, C, bkm, tid, st, own, fl, dt_inv, tm, F, M);
+                dv |= bond_eval_g<1, HOIST, F_REGS>(smem, G, NV, C, bkm, tid, st, own, fl, dt_inv, tm, F, M);
+                dv |= bond_eval_g<2, HOIST, F_REGS>(smem, G, NV, C, bkm, tid, st, own, fl, dt_inv, tm, F, M);
                 if (dv) atomicMin(f_div, k);                 // Integrate() fails in this step (VX_Sim.cpp:1775-1777): acted on at the window's end
                 tm_wait_st();
                 mbar_arrive_warp(bondbar + warp, lane == 0);
                 // -axis neighbours' owners must have staged their shares of step k (and read the positions this warp is about to overwrite)
                 flow_wait(bondbar, minus_mask, (uint32_t)k & 1u, lane);
-                if (tid < n_vox) voxel_phase_g(smem, G, NV, C, R, tid, st, nb, own, fl, M);
+                if (tid < n_vox) voxel_phase_g<F_REGS>(smem, G, NV, C, R, tid, st, nb, own, fl, F, M);
                 mbar_arrive_warp(voxbar + warp, lane == 0);
                 if (tid == 0) f_time[0] += dt;               // CurTime += dt (VX_Sim.cpp:1929)
             }
@@ -472,15 +528,46 @@ __global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, false, false)) vx_step
                 S.dsc_c[(cur ^ 1) * mv + i] = (float)(ns - S.sk[i].nom_size);
             }
             // ---- bond phase: reads positions / orientations of the previous step, writes only what this thread owns --------------
-            V3<float> M = mk3<float>(0, 0, 0);
+            if (COLLIDE && col_on && tid == 0) {
+                // UpdateCollisions, the bookkeeping (VX_Sim.cpp:1729-1755): one thread keeps MaxDispSinceLastBondUpdate in fp64 and posts
+                // its verdict, tagged with the step, where the others pick it up once their bonds are done (dt is still 0 in step 0)
+                const unsigned int mvb = S.maxvel[(k + 1) & 1];            // written by the previous step's voxel phase
+                double col_acc = S.colstate[0], max_vel = S.colstate[1];
+                if (k > 0) max_vel = sqrt((double)__uint_as_float(mvb));
+                S.maxvel[k & 1] = 0u;                                      // this step's slot; next read after two barriers
+                col_acc += fabs(max_vel * (s == 0 ? 0.0 : dt) / S.colstate[3]);
+                const bool rebuild = !col_host && (col_acc > (S.colstate[2] - 1.0) / 2 || col_first);
+                if (rebuild) { col_first = false; col_acc = 0.0; }
+                S.colstate[0] = col_acc; S.colstate[1] = max_vel;
+                *(volatile unsigned int*)S.colflag = ((unsigned int)(k + 1) << 1) | (rebuild ? 1u : 0u);
+            }
+            V3<float> F = mk3<float>(0, 0, 0), M = mk3<float>(0, 0, 0);
             int div = 0;
 #ifdef VXG_TRACE
             const long long tr0 = clock64();
 #endif
-            div |= bond_eval_g<0, HOIST>(smem, G, NV, C, bkm, tid, st, own, fl, dt_inv, tm, M) ? 1 : 0;
-            div |= bond_eval_g<1, HOIST>(smem, G, NV, C, bkm, tid, st, own, fl, dt_inv, tm, M) ? 1 : 0;
-            div |= bond_eval_g<2, HOIST>(smem, G, NV, C, bkm, tid, st, own, fl, dt_inv, tm, M) ? 1 : 0;
+            div |= bond_eval_g<0, HOIST, F_REGS>(smem, G, NV, C, bkm, tid, st, own, fl, dt_inv, tm, F, M) ? 1 : 0;
+            div |= bond_eval_g<1, HOIST, F_REGS>(smem, G, NV, C, bkm, tid, st, own, fl, dt_inv, tm, F, M) ? 1 : 0;
+            div |= bond_eval_g<2, HOIST, F_REGS>(smem, G, NV, C, bkm, tid, st, own, fl, dt_inv, tm, F, M) ? 1 : 0;
             tm_wait_st();
+            if (COLLIDE && col_on) {   // positions are still those of the previous step here
+                unsigned int verdict;
+                do { verdict = *(volatile unsigned int*)S.colflag; } while ((verdict >> 1) != (unsigned int)(k + 1));
+                if (verdict & 1u) {    // CalcL1Bonds (VX_Sim.cpp:2357-2413), by the whole CTA
+                    // (copies: the out-of-line rebuild takes its views by reference, and what it is handed must live in memory --
+                    // the step loop's own R and C stay in registers)
+                    const RobotView<float> R2 = R; const RobotConsts<float> C2 = C; const ColTables CT2 = CT;
+                    n_col = col_rebuild<float>(R2, C2, CT2, (float)S.colstate[2], (float)S.colstate[3], S.pairs, max_col, (int*)S.red);
+                    if (n_col > max_col) { col_overflow = true; break; }
+                    if (n_col > 0) col_csr_build(S.pairs, n_col, c_seg, c_adj, (int*)S.red);
+                }
+                if (n_col > 0 && tid < n_vox) {   // CVXS_BondCollision::CalcContactForce for this voxel's contact bonds, in list order
+                    const uint32_t sg = c_seg[tid];
+                    V3<float> fc = mk3<float>(0, 0, 0);
+                    for (uint32_t i = sg & 0xFFFFu; i < (sg >> 16); i++) col_contact<float>(R, C, st, own, c_adj[i], fc);
+                    F = F + fc;
+                }
+            }
 #ifdef VXG_TRACE
             const long long tr1 = clock64();
 #endif
@@ -496,7 +583,12 @@ __global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, false, false)) vx_step
                 S.dnom_bc[(cur ^ 1) * MB + i] = 0.5f * (dn[pr & 0xFFFFu] + dn[pr >> 16]);
             }
             // ---- voxel phase: gather the shares of the -X/-Y/-Z bonds (Force2 = -Force1, Moment2), integrate -------------------
-            if (tid < n_vox) voxel_phase_g(smem, G, NV, C, R, tid, st, nb, own, fl, M);
+            float sp2 = 0.0f;
+            if (tid < n_vox) sp2 = voxel_phase_g<F_REGS>(smem, G, NV, C, R, tid, st, nb, own, fl, F, M);
+            if (COLLIDE && col_on) {   // SS.MaxVoxVel for the next UpdateCollisions
+                for (int o = 16; o > 0; o >>= 1) sp2 = fmaxf(sp2, __shfl_xor_sync(0xffffffffu, sp2, o));
+                if ((tid & 31) == 0) atomicMax(&S.maxvel[k & 1], __float_as_uint(sp2));
+            }
 #ifdef VXG_TRACE
             const long long tr3 = clock64();
 #endif
@@ -530,10 +622,19 @@ __global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, false, false)) vx_step
         }
     }
     for (int i = tid; i < n_vc; i += T) B.scale_c[(size_t)robot * B.max_vclass + i] = FLOW ? r_scale[cur * mv + i] : S.scale_c[cur * mv + i];
+    if (COLLIDE && col_on) {
+        const int nc = n_col < max_col ? n_col : max_col;
+        for (int i = tid; i < nc; i += T) B.col_pairs[(size_t)robot * max_col + i] = S.pairs[i];
+    }
     if (tid == 0) {
         ctlp->cur_time = t;
         ctlp->step = step0 + done;
         unsigned int st2 = status0;
+        if (COLLIDE && col_on) {
+            ctlp->n_col = n_col < max_col ? n_col : max_col; ctlp->col_first = col_first ? 1 : 0; ctlp->col_acc = S.colstate[0];
+            ctlp->max_vel = done > 0 ? sqrt((double)__uint_as_float(S.maxvel[(done - 1) & 1])) : S.colstate[1];
+        }
+        if (col_overflow) st2 |= VXG_ST_COL_OVERFLOW_ | VXG_ST_DIVERGED_;
         if (diverged) st2 |= VXG_ST_DIVERGED_;
         if (step0 + done >= total) st2 |= VXG_ST_FINISHED_;
         ctlp->status = st2;
@@ -546,8 +647,42 @@ __global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, false, false)) vx_step
 }
 
 // shared memory of one CTA: mv / mb = capacities of the class tables as the kernel instantiation has them (mb includes the zero class)
-inline size_t gather_smem_bytes(int nv, int mv, int mb, bool flow) {
-    return make_glayout(nv).total + sizeof(BondKm) * (size_t)mb + tables_bytes<float>(mv, mb, true, 0) + (flow ? flow_bytes(mv, mb) : 0);
+inline size_t gather_smem_bytes(int nv, int mv, int mb, bool flow, int max_col = 0) {
+    return make_glayout(nv).total + sizeof(BondKm) * (size_t)mb + tables_bytes<float>(mv, mb, true, max_col) + (flow ? flow_bytes(mv, mb) : 0) +
+           (max_col > 0 ? vx_align16(sizeof(uint32_t) * nv + sizeof(uint16_t) * 2 * (size_t)max_col) : 0);
+}
+
+// ---- launch plumbing (host) ----------------------------------------------------------------------------------------------------
+// class-table capacities the step loop is specialised for (palette robots: <= 8 voxel classes, <= 63 bond classes after
+// re-keying by voxel-class pair); larger tables run the instantiation with run-time capacities
+#define VXG_CV 8
+#define VXG_CB 64
+template <int NV, bool FLOW, int CV, int CB, bool COLLIDE = false> inline cudaError_t launch_gather_form(const BatchDev<float>& B, const LaunchCfg& c) {
+    auto kern = vx_step_kernel_g<NV, FLOW, CV, CB, COLLIDE>;
+    const size_t smem = gather_smem_bytes(NV, CV > 0 ? CV : B.max_vclass, CB > 0 ? CB : B.max_bclass + 1, FLOW, COLLIDE ? B.max_col : 0);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<c.n_robots, NV, smem, c.stream>>>(B, c.n_steps);
+    return cudaGetLastError();
+}
+// does a CTA of this form fit next to the others the launch bounds ask for (227 KB per CTA, 228 KB per SM with 1 KB reserved per CTA)?
+template <int NV> inline bool gather_fits(int mv, int mb, bool flow, int max_col = 0) {
+    const size_t per_cta = gather_smem_bytes(NV, mv, mb, flow, max_col);
+    const int ctas = vx_min_ctas(NV, NV, max_col > 0, false);
+    return per_cta <= 227u * 1024u && (per_cta + 1024u) * (size_t)ctas <= 228u * 1024u;
+}
+template <int NV> inline cudaError_t launch_gather(const BatchDev<float>& B, const LaunchCfg& c, bool flow) {
+    const bool fixed = B.max_vclass <= VXG_CV && B.max_bclass + 1 <= VXG_CB && gather_fits<NV>(VXG_CV, VXG_CB, false);
+    if (flow) {   // experiment form, run-time capacities only
+        if (gather_fits<NV>(B.max_vclass, B.max_bclass + 1, true)) return launch_gather_form<NV, true, 0, 0>(B, c);
+    }
+    return fixed ? launch_gather_form<NV, false, VXG_CV, VXG_CB>(B, c) : launch_gather_form<NV, false, 0, 0>(B, c);
+}
+// the same with self-collision: 0 = launched, 1 = this stride / table size has no gather instantiation that fits (caller falls back)
+template <int NV> inline int launch_gather_collide(const BatchDev<float>& B, const LaunchCfg& c, cudaError_t* err) {
+    if (B.max_vclass <= VXG_CV && B.max_bclass + 1 <= VXG_CB && gather_fits<NV>(VXG_CV, VXG_CB, false, B.max_col)) { *err = launch_gather_form<NV, false, VXG_CV, VXG_CB, true>(B, c); return 0; }
+    if (gather_fits<NV>(B.max_vclass, B.max_bclass + 1, false, B.max_col)) { *err = launch_gather_form<NV, false, 0, 0, true>(B, c); return 0; }
+    return 1;
 }
 
 }  // namespace vx

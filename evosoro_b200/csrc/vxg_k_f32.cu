@@ -4,31 +4,6 @@
 #include "vxg_launch.cuh"
 #include "vxg_gather.cuh"
 namespace vx {
-// class-table capacities the step loop is specialised for (palette robots: <= 8 voxel classes, <= 63 bond classes after
-// re-keying by voxel-class pair); larger tables run the instantiation with run-time capacities
-#define VXG_CV 8
-#define VXG_CB 64
-template <int NV, bool FLOW, int CV, int CB> static cudaError_t launch_gather_form(const BatchDev<float>& B, const LaunchCfg& c) {
-    auto kern = vx_step_kernel_g<NV, FLOW, CV, CB>;
-    const size_t smem = gather_smem_bytes(NV, CV > 0 ? CV : B.max_vclass, CB > 0 ? CB : B.max_bclass + 1, FLOW);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    kern<<<c.n_robots, NV, smem, c.stream>>>(B, c.n_steps);
-    return cudaGetLastError();
-}
-// does a CTA of this form fit next to the others the launch bounds ask for (227 KB per CTA, 228 KB per SM with 1 KB reserved per CTA)?
-template <int NV> static bool gather_fits(int mv, int mb, bool flow) {
-    const size_t per_cta = gather_smem_bytes(NV, mv, mb, flow);
-    const int ctas = vx_min_ctas(NV, NV, false, false);
-    return per_cta <= 227u * 1024u && (per_cta + 1024u) * (size_t)ctas <= 228u * 1024u;
-}
-template <int NV> static cudaError_t launch_gather(const BatchDev<float>& B, const LaunchCfg& c, bool flow) {
-    const bool fixed = B.max_vclass <= VXG_CV && B.max_bclass + 1 <= VXG_CB && gather_fits<NV>(VXG_CV, VXG_CB, false);
-    if (flow) {   // experiment form, run-time capacities only
-        if (gather_fits<NV>(B.max_vclass, B.max_bclass + 1, true)) return launch_gather_form<NV, true, 0, 0>(B, c);
-    }
-    return fixed ? launch_gather_form<NV, false, VXG_CV, VXG_CB>(B, c) : launch_gather_form<NV, false, 0, 0>(B, c);
-}
 // The gather form (vxg_gather.cuh: damping history in tensor memory, shares gathered by the -axis neighbour) runs every stride
 // that has one voxel per thread.  VXG_KERNEL_FORM selects another form of the same arithmetic for A/B measurements and
 // bit-for-bit comparisons (read per launch: the tests flip it inside one process):

@@ -272,6 +272,7 @@ template <typename Real, int NV, int VPT, bool SMEM, bool COMPACT, bool FLUID = 
 __global__ void __launch_bounds__(NV / VPT, vx_min_ctas(NV, NV / VPT, FLUID || COLLIDE, sizeof(Real) == 8)) vx_step_kernel(BatchDev<Real> B, int n_steps, int record_bonds) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int T = NV / VPT;
+    constexpr bool HOIST = !(COMPACT && (NV == 1024 || NV == 512));   // bond_force: as in the gather form of the same stride, bit for bit
     constexpr BlobLayout LC = make_layout(NV, (int)sizeof(Real));
     const BlobLayout L = FLUID ? B.L : LC;   // with the mesh arrays the capacity is a run-time size
     const int robot = blockIdx.x;
@@ -449,23 +450,25 @@ __global__ void __launch_bounds__(NV / VPT, vx_min_ctas(NV, NV / VPT, FLUID || C
         // the split-phase barrier orders without stalling the evaluations.
         int div = 0;
 #pragma unroll
-        for (int j = 0; j < VPT; j++) { P[j].w = -1; if (tid + j * T < n_vox) div |= bond_eval<Real, 0, COMPACT, FLUID>(R, C, tid + j * T, st[j], own[j], fl[j], dt_inv, F[j], M[j], rec, P[j]) ? 1 : 0; }
+        for (int j = 0; j < VPT; j++) { P[j].w = -1; if (tid + j * T < n_vox) div |= bond_eval<Real, 0, COMPACT, FLUID, HOIST>(R, C, tid + j * T, st[j], own[j], fl[j], dt_inv, F[j], M[j], rec, P[j]) ? 1 : 0; }
 #pragma unroll
         for (int j = 0; j < VPT; j++) bond_push<Real>(R, P[j]);
         axis_arrive(S.mbar, S.arrcnt, T / 32, (tid & 31) == 0);
 #pragma unroll
-        for (int j = 0; j < VPT; j++) { P[j].w = -1; if (tid + j * T < n_vox) div |= bond_eval<Real, 1, COMPACT, FLUID>(R, C, tid + j * T, st[j], own[j], fl[j], dt_inv, F[j], M[j], rec, P[j]) ? 1 : 0; }
+        for (int j = 0; j < VPT; j++) { P[j].w = -1; if (tid + j * T < n_vox) div |= bond_eval<Real, 1, COMPACT, FLUID, HOIST>(R, C, tid + j * T, st[j], own[j], fl[j], dt_inv, F[j], M[j], rec, P[j]) ? 1 : 0; }
         axis_wait(S.mbar, mpar); mpar ^= 1u;
         if (COLLIDE && col_on && S.colflag[k & 1]) {   // rebuild the contact-bond list (positions are still those of the previous step)
             C.scale_c = S.scale_c + cur * B.max_vclass;
-            n_col = col_rebuild<Real>(R, C, CT, (Real)S.colstate[2], (Real)S.colstate[3], S.pairs, B.max_col, (int*)S.red);
+            // (copies: the out-of-line rebuild takes its views by reference; the step loop's own R and C stay in registers)
+            const RobotView<Real> R2 = R; const RobotConsts<Real> C2 = C; const ColTables CT2 = CT;
+            n_col = col_rebuild<Real>(R2, C2, CT2, (Real)S.colstate[2], (Real)S.colstate[3], S.pairs, B.max_col, (int*)S.red);
             if (n_col > B.max_col) { col_overflow = true; break; }
         }
 #pragma unroll
         for (int j = 0; j < VPT; j++) bond_push<Real>(R, P[j]);
         axis_arrive(S.mbar, S.arrcnt, T / 32, (tid & 31) == 0);
 #pragma unroll
-        for (int j = 0; j < VPT; j++) { P[j].w = -1; if (tid + j * T < n_vox) div |= bond_eval<Real, 2, COMPACT, FLUID>(R, C, tid + j * T, st[j], own[j], fl[j], dt_inv, F[j], M[j], rec, P[j]) ? 1 : 0; }
+        for (int j = 0; j < VPT; j++) { P[j].w = -1; if (tid + j * T < n_vox) div |= bond_eval<Real, 2, COMPACT, FLUID, HOIST>(R, C, tid + j * T, st[j], own[j], fl[j], dt_inv, F[j], M[j], rec, P[j]) ? 1 : 0; }
         axis_wait(S.mbar, mpar); mpar ^= 1u;
 #pragma unroll
         for (int j = 0; j < VPT; j++) bond_push<Real>(R, P[j]);

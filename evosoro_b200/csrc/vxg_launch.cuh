@@ -52,6 +52,7 @@ cudaError_t launch_f32_collide_compact(const BatchDev<float>& B, const LaunchCfg
 cudaError_t launch_f32_fluid(const BatchDev<float>& B, const LaunchCfg& c, bool collide);     // land/water layouts (+ self-collision)
 cudaError_t launch_f32_fluid_compact(const BatchDev<float>& B, const LaunchCfg& c, bool collide);   // the same on the production form
 cudaError_t launch_f32_extras_global(const BatchDev<float>& B, const LaunchCfg& c, bool fluid, bool collide);   // the same on the blob in global memory
+cudaError_t launch_f64_extras_global(const BatchDev<double>& B, const LaunchCfg& c, bool fluid, bool collide);  // fp64, blob in global memory
 void launch_stats_f32(const BatchDev<float>& B, StatsDev* out, int n_robots, cudaStream_t s);
 void launch_stats_f64(const BatchDev<double>& B, StatsDev* out, int n_robots, cudaStream_t s);
 

@@ -266,6 +266,30 @@ extern "C" int64_t vxg_pop_launch_count(const vxg_population* p) {
     return n;
 }
 
+// Benchmark markers over all the batches' streams.  Device time between two marks = (latest of the second mark's events) -
+// (earliest of the first mark's), measured with CUDA events on the streams the kernels run on.
+extern "C" int vxg_pop_mark(vxg_population* p, int slot) {
+    if (!p) return fail(VXG_ERR_ARG, "vxg_pop_mark: null population");
+    for (auto& s : p->subs) { int rc = vxg_mark(s.b, slot); if (rc) return rc; }
+    return VXG_OK;
+}
+extern "C" int vxg_pop_mark_elapsed_ms(vxg_population* p, int s0, int s1, float* ms) {
+    if (!p || !ms || s0 < 0 || s1 < 0 || s0 >= VXG_N_MARKS || s1 >= VXG_N_MARKS || p->subs.empty()) return fail(VXG_ERR_ARG, "vxg_pop_mark_elapsed_ms: bad argument");
+    CK(cudaSetDevice(p->device));
+    for (auto& s : p->subs) if (!s.b->mark_set[s0] || !s.b->mark_set[s1]) return fail(VXG_ERR_STATE, "vxg_pop_mark_elapsed_ms: marker not recorded");
+    cudaEvent_t ref = p->subs[0].b->marks[s0];
+    float first = 0.f, last = -1e30f;
+    for (auto& s : p->subs) {
+        CK(cudaEventSynchronize(s.b->marks[s1]));
+        float a = 0.f, b = 0.f;
+        CK(cudaEventElapsedTime(&a, ref, s.b->marks[s0]));
+        CK(cudaEventElapsedTime(&b, ref, s.b->marks[s1]));
+        first = std::min(first, a); last = std::max(last, b);
+    }
+    *ms = last - first;
+    return VXG_OK;
+}
+
 extern "C" int64_t vxg_pop_upload_bytes(const vxg_population* p) {
     int64_t n = 0;
     if (p) for (auto& s : p->subs) n += vxg_upload_bytes(s.b);

@@ -102,6 +102,8 @@ def lib():
         L.vxg_pop_n_batches.argtypes = [vp]
         L.vxg_pop_batch_info.argtypes = [vp, C.c_int, i32p, i32p, i32p, i32p]
         L.vxg_pop_locate.argtypes = [vp, C.c_int, i32p, i32p]
+        L.vxg_pop_mark.argtypes = [vp, C.c_int]
+        L.vxg_pop_mark_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]
         for f in ("vxg_pop_launch_count", "vxg_pop_upload_bytes", "vxg_pop_download_bytes"):
             getattr(L, f).argtypes = [vp]
             getattr(L, f).restype = C.c_int64
@@ -397,6 +399,14 @@ class Population:
 
     def launch_count(self) -> int:
         return int(lib().vxg_pop_launch_count(self.h))
+
+    def mark(self, slot: int):
+        _ck(lib().vxg_pop_mark(self.h, slot))
+
+    def mark_elapsed_ms(self, slot0: int, slot1: int) -> float:
+        ms = C.c_float()
+        _ck(lib().vxg_pop_mark_elapsed_ms(self.h, slot0, slot1, C.byref(ms)))
+        return float(ms.value)
 
     def h2d_bytes(self) -> int:
         return int(lib().vxg_pop_upload_bytes(self.h))

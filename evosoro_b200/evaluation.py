@@ -23,24 +23,19 @@ VOXELYZE = os.path.join(_HERE, "lib", "voxelyze")
 
 
 def run_batch(vxa_paths, devices=(0,), voxelyze=VOXELYZE, extra_args=()):
-    """Simulate every .vxa in ``vxa_paths`` (each writes its own <FitnessFileName>): contiguous shards, one CLI
-    process per device, all running concurrently.  Returns the list of exit codes (1 = completed, the
-    reference's convention)."""
+    """Simulate every .vxa in ``vxa_paths`` (each writes its own <FitnessFileName>) as ONE call of the drop-in CLI: it imports
+    the files on the host cores, deals the robots out over ``devices`` by cost (timesteps x voxels, largest first onto the
+    least loaded GPU -- not by file count: a robot with a bone-bone bond takes ten times the steps of an all-tissue one) and
+    runs each device's share as a ragged population.  Returns the list with the exit code (1 = every robot wrote its
+    result, the reference's convention)."""
     vxa_paths = list(vxa_paths)
     if not vxa_paths:
         return []
     devices = list(devices) or [0]
-    per = (len(vxa_paths) + len(devices) - 1) // len(devices)
-    procs = []
-    for k, dev in enumerate(devices):
-        shard = vxa_paths[k * per:(k + 1) * per]
-        if not shard:
-            continue
-        cmd = [voxelyze, "--device", str(dev)] + list(extra_args)
-        for p in shard:
-            cmd += ["-f", p]
-        procs.append(sub.Popen(cmd))
-    return [p.wait() for p in procs]
+    cmd = [voxelyze, "--devices", ",".join(str(d) for d in devices)] + list(extra_args)
+    for p in vxa_paths:
+        cmd += ["-f", p]
+    return [sub.call(cmd)]
 
 
 def evaluate_all(sim, env, pop, print_log, save_vxa_every, run_directory, run_name, max_eval_time=60,

@@ -354,6 +354,9 @@ int vxg_pop_n_batches(const vxg_population* p);
 int vxg_pop_batch_info(vxg_population* p, int batch, int32_t* n_robots, int32_t* stride, int32_t* threads, int32_t* family);
 int vxg_pop_locate(const vxg_population* p, int robot, int32_t* batch, int32_t* slot);
 int64_t vxg_pop_launch_count(const vxg_population* p);
+/* vxg_mark / vxg_mark_elapsed_ms over all the batches' streams: device time from the earliest event of mark slot0 to the latest of slot1 */
+int vxg_pop_mark(vxg_population* p, int slot);
+int vxg_pop_mark_elapsed_ms(vxg_population* p, int slot0, int slot1, float* ms);
 int64_t vxg_pop_upload_bytes(const vxg_population* p);    /* host -> device bytes of one whole-population upload */
 int64_t vxg_pop_download_bytes(const vxg_population* p);  /* device -> host bytes of one vxg_pop_run_host        */
 

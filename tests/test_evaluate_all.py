@@ -116,3 +116,17 @@ def test_evaluate_all_leaves_the_worst_fitness_on_a_diverged_individual(tmp_path
     assert pop.all_evaluated_individuals_ids == [0, 2]
     assert any("did not produce a result" in l for l in log.lines)
     assert not os.listdir(os.path.join(run, "fitnessFiles"))
+
+
+def test_cli_plan_mode_reports_cost_without_a_gpu(tmp_path):
+    """`voxelyze --plan`: import only (host code), one "<file> <voxels> <bonds> <timesteps>" line per input -- what cost-balanced
+    sharding over several GPUs is based on (timesteps x voxels: a bone-bone bond makes a robot take ten times the steps)."""
+    import subprocess
+    soft = tmp_path / "soft.vxa"; hard = tmp_path / "hard.vxa"
+    soft.write_text(vxa.vxa_text(vxa.dense_lattice(4, 0, materials=(1, 3, 4))))
+    hard.write_text(vxa.vxa_text(vxa.dense_lattice(5, 1, materials=(1, 2, 3, 4))))
+    r = subprocess.run([evaluation.VOXELYZE, "--plan", "-f", str(soft), "-f", str(tmp_path / "missing.vxa"), "-f", str(hard)], capture_output=True, text=True)
+    rows = [l.split() for l in r.stdout.strip().splitlines()]
+    assert r.returncode == 0 and "missing.vxa" in r.stderr          # one input could not be imported: reported, the others planned
+    assert [row[0] for row in rows] == [str(soft), str(hard)]
+    assert [int(row[1]) for row in rows] == [64, 125] and int(rows[1][3]) == 78054 and int(rows[1][3]) // int(rows[0][3]) == 10

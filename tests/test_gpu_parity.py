@@ -41,20 +41,23 @@ def _run_gpu(rob, prec, frames, every, bonds=True):
 
 
 # ---- (a) golden fixtures, imported by the product importer ---------------------------------------
-@pytest.mark.parametrize("name", [n for n in TRAJ if not any(golden_lib.flags(n))])
+@pytest.mark.parametrize("name", TRAJ)
 def test_golden_f64_logic_parity(name):
-    """P1: fp64 instantiation vs the reference, per-frame state: positions <= 1e-9 pitch."""
+    """P1: fp64 instantiation vs the reference, per-frame state: positions <= 1e-9 pitch (<= 1e-7 with live contacts: overlap x
+    stiffness amplifies the rounding differences of two fp64 evaluation orders).  Covers the fluid-drag and self-collision phases
+    too (fp64 on the device, blob in global memory), including the reference's own shipped example inputs."""
     g = golden_lib.Golden(name)
     d = g.dump
     LAT = float(d.sim[14])   # the fixture's own lattice pitch
     rob = engine.Model(text=g.vxa_text, variant=_variant(g)).robot
-    got = _run_gpu(rob, abi.VXG_PREC_F64, d.vstate.shape[0] - 1, g.every)
+    fluid, collide = golden_lib.flags(name)
+    got = _run_gpu(rob, abi.VXG_PREC_F64, d.vstate.shape[0] - 1, g.every, bonds=not (fluid or collide))
     for f, s in enumerate(got, start=1):
-        assert common.max_abs(s.pos, d.pos[f]) <= 1e-9 * LAT, (name, f)
-        assert common.max_abs(s.quat, d.quat[f]) <= 1e-8
+        assert common.max_abs(s.pos, d.pos[f]) <= (1e-7 if collide else 1e-9) * LAT, (name, f, common.max_abs(s.pos, d.pos[f]) / LAT)
+        assert common.max_abs(s.quat, d.quat[f]) <= (1e-6 if collide else 1e-8)
         assert common.max_abs(s.scale, d.scale[f]) <= 1e-15
         assert np.array_equal(s.static_fric, d.sfric[f].astype(np.int32))
-        if d.n_bond:
+        if d.n_bond and not (fluid or collide):
             assert np.array_equal(s.bond_small_angle, d.bstate[f, :, 13].astype(np.int32))
             if g.every * f > 100:   # before that the reference's rotation vectors are rounding noise (tests/test_emul_golden.py)
                 fmax = np.abs(d.bstate[f, :, 0:3]).max()
@@ -189,6 +192,25 @@ def test_gather_form_is_bit_identical_to_the_push_form(n, steps, monkeypatch):
         assert [int(s.steps) for s in b.stats()] == [steps] * 4 and [s.time for s in b.stats()] == [s.time for s in a.stats()]
         b.close()
     a.close()
+
+
+@pytest.mark.parametrize("name,steps", [("col_pincer", 800), ("ex_example_2", 1500), ("ex_example_1", 3000)])
+def test_gather_form_with_self_collision_is_bit_identical_to_the_push_form(name, steps, monkeypatch):
+    """The same for the self-collision variants: contact-bond list rebuilds, live contacts (the pincer's 22, Example_2's folds)
+    and the per-voxel contact lists of the gather form against the list scan of the push form."""
+    g = golden_lib.Golden(name)
+    rob = engine.Model(text=g.vxa_text).robot
+    monkeypatch.setenv("VXG_KERNEL_FORM", "push")
+    a = engine.Batch([rob, rob]); a.step(steps); assert not a.sync().any()
+    monkeypatch.setenv("VXG_KERNEL_FORM", "barrier")
+    b = engine.Batch([rob, rob])
+    for i in range(4):
+        b.step(steps // 4)
+    assert not b.sync().any()
+    sa, sb = a.download(1), b.download(1)
+    for f in ("pos", "quat", "lin_mom", "ang_mom", "scale", "static_fric", "bond_small_angle"):
+        assert np.array_equal(getattr(sa, f), getattr(sb, f)), f
+    assert a.stats()[0].max_vel == b.stats()[0].max_vel
 
 
 def test_reuploading_one_slot_leaves_the_others_running():
