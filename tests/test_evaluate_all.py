@@ -129,4 +129,4 @@ def test_cli_plan_mode_reports_cost_without_a_gpu(tmp_path):
     rows = [l.split() for l in r.stdout.strip().splitlines()]
     assert r.returncode == 0 and "missing.vxa" in r.stderr          # one input could not be imported: reported, the others planned
     assert [row[0] for row in rows] == [str(soft), str(hard)]
-    assert [int(row[1]) for row in rows] == [64, 125] and int(rows[1][3]) == 78054 and int(rows[1][3]) // int(rows[0][3]) == 10
+    assert [int(row[1]) for row in rows] == [64, 125] and int(rows[1][3]) == 78054 and 9.9 < int(rows[1][3]) / int(rows[0][3]) < 10.1
