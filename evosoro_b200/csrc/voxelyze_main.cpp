@@ -13,6 +13,7 @@
 #include <dirent.h>
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -22,7 +23,11 @@
 
 #include "../../include/vxhost.h"
 
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 int main(int argc, char** argv) {
+    const bool timing = getenv("VXG_TIMING") != nullptr;   // phase times on stderr
+    const double t_start = now_s();
     std::vector<std::string> files;
     bool print_scrn = false, lw = false, ignore_col = false, plan_only = false;
     std::vector<int> devices;
@@ -74,6 +79,7 @@ int main(int argc, char** argv) {
             });
         for (auto& x : th) x.join();
     }
+    const double t_imported = now_s();
     int n_failed = 0;
     std::vector<int> src;   // batch slot -> index into files
     for (int r = 0; r < n_files; r++) {
@@ -128,6 +134,7 @@ int main(int argc, char** argv) {
         if (!rc) rc = vxg_pop_set_plan(pops[d], t.data(), l.data(), e.data());
         if (!rc) rc = vxg_pop_run(pops[d]);   // whole lifetimes on the device
     }
+    const double t_launched = now_s();
     long long n_batches = 0, n_launches = 0;
     for (int d = 0; d < n_dev && !rc; d++) {
         if (!pops[d]) continue;
@@ -139,6 +146,7 @@ int main(int argc, char** argv) {
         n_batches += vxg_pop_n_batches(pops[d]); n_launches += vxg_pop_launch_count(pops[d]);
     }
     if (rc) { fprintf(stderr, "voxelyze: %s\n", vxg_last_error()); return 0; }
+    const double t_simulated = now_s();
     if (print_scrn) printf("%d robots on %d device(s) in %lld batches, %lld kernel launches\n", n, n_dev, n_batches, n_launches);
     for (int r = 0; r < n; r++) {
         vxh_info info; vxh_get_info(models[r], &info);
@@ -157,7 +165,11 @@ int main(int argc, char** argv) {
         }
         vxh_free(models[r]);
     }
+    const double t_written = now_s();
     for (auto* p : pops) vxg_pop_destroy(p);
+    if (timing) fprintf(stderr, "voxelyze: %d files: import %.3f s, populations (CUDA context, bucketing, flatten, upload, launches) %.3f s, simulation %.3f s, "
+                                "result files %.3f s, teardown %.3f s\n", n_files, t_imported - t_start, t_launched - t_imported, t_simulated - t_launched,
+                        t_written - t_simulated, now_s() - t_written);
     if (n_failed) fprintf(stderr, "voxelyze: %d of %d robots did not produce a result\n", n_failed, n_files);
     return n_failed ? 0 : 1;
 }

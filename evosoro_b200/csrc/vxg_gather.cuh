@@ -121,8 +121,8 @@ template <int AX> __device__ inline void hist_store(uint32_t tm, const BondHist<
 // lane runs the same code; the warp skips the axis when none of its lanes has a bond there.
 //   F_REGS : the own share of the force accumulates in registers (else it is re-read from this thread's staging slots in the voxel
 //            phase: three registers less across the bond phase).  Measured: registers +0.7 % at 10^3, re-read +0.5 % at 8^3.
-template <int AX, bool HOIST, bool F_REGS>
-__device__ __forceinline__ bool bond_eval_g(unsigned char* smem, const GLayout& G, int NV, const RobotConsts<float>& C, const BondKm* bkm, int tid, const VoxStat& st,
+template <int AX, bool HOIST, bool F_REGS, bool FLUID>
+__device__ __forceinline__ bool bond_eval_g(unsigned char* smem, const GLayout& G, int NV, const RobotConsts<float>& C, const BondKm* bkm, float* strain, int tid, const VoxStat& st,
                                             const OwnState<float>& own, uint32_t& fl, float dt_inv, uint32_t tm, V3<float>& F, V3<float>& M) {
     const int w = st.nbr[AX];
     if (!__any_sync(0xffffffffu, w >= 0)) return false;
@@ -131,7 +131,8 @@ __device__ __forceinline__ bool bond_eval_g(unsigned char* smem, const GLayout& 
     float ha[8], hc;
     hist_issue<AX>(tm, ha, hc);   // the history is on its way from tensor memory while the neighbour's state is fetched
 
-    const BondK<float> k = bond_from_km(bkm[bc]);
+    BondK<float> k = bond_from_km(bkm[bc]);
+    if (FLUID) { k.sf1 = C.bkc[bc].sf1; k.sf2 = 2.0f - k.sf1; }   // per-voxel shares of the axial strain: they shape the surface mesh
     const double* pos = (const double*)(smem + G.off_pos);
     double dpa[3] = {pos[wq] - own.px, pos[NV + wq] - own.py, pos[2 * NV + wq] - own.pz};
     dpa[AX] -= C.bk_dist[bc];
@@ -150,6 +151,10 @@ __device__ __forceinline__ bool bond_eval_g(unsigned char* smem, const GLayout& 
     if (__any_sync(0xffffffffu, o.changed)) { BondHist<float> old; hist_load<AX>(tm, old); if (o.changed) h = old; }
     hist_store<AX>(tm, h);
     fl = (fl & ~(1u << AX)) | ((small ? 1u : 0u) << AX);
+    if (FLUID && w >= 0) {   // SetStrainDir(BD_P<axis>, CurStrainV1) on voxel 1, (BD_N<axis>, CurStrainV2) on voxel 2: one writer per slot
+        strain[AX * NV + tid] = o.strain1;
+        strain[(3 + AX) * NV + w] = o.strain2;
+    }
     if (F_REGS) F = F + o.f1;   // (else the own share of the force is read back from the staging slot in the voxel phase)
     M = M + o.m1;
     R4<float> a; a.x = o.f1.x; a.y = o.f1.y; a.z = o.f1.z; a.w = o.m2.x;
@@ -248,16 +253,18 @@ __device__ inline void flow_wait(unsigned long long* bar, uint32_t mask, uint32_
 //            every shared-memory address in the step loop is the CTA's base plus an immediate; with run-time capacities the
 //            table pointers were rematerialised over and over at 64 registers (5 % of the executed instructions, ncu).
 //   COLLIDE: self-collision (contact-bond list in shared memory, rebuilt on the device, contact forces through the per-voxel CSR)
-template <int NV, bool FLOW, int CV, int CB, bool COLLIDE = false>
-__global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, COLLIDE, false)) vx_step_kernel_g(BatchDev<float> B, int n_steps) {
-    static_assert(!(FLOW && COLLIDE), "the dataflow form has no per-step CTA-wide reduction");
+//   FLUID  : land/water layouts: the deformable surface mesh (vertex -> voxels, facets) and the per-voxel strains live in shared memory
+//            behind the class tables (run-time capacities), fluid drag is evaluated at the start of every step
+template <int NV, bool FLOW, int CV, int CB, bool COLLIDE = false, bool FLUID = false>
+__global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, COLLIDE || FLUID, false)) vx_step_kernel_g(BatchDev<float> B, int n_steps) {
+    static_assert(!(FLOW && (COLLIDE || FLUID)), "the dataflow form has no per-step CTA-wide phases");
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int T = NV;
     constexpr BlobLayout L = make_layout(NV, 4);
     constexpr GLayout G = make_glayout(NV);
     constexpr int TM_COLS = tm_cols_for(NV);
     constexpr bool HOIST = !(NV == 1024 || NV == 512);   // bond_force: only where there are more than 64 registers per thread
-    constexpr bool F_REGS = NV == 1024 || COLLIDE;        // (contact forces join the own share before the barrier)
+    constexpr bool F_REGS = NV == 1024 || COLLIDE || FLUID;   // (contact / drag forces join the own share before the barrier)
     const int robot = blockIdx.x;
     int tid;
     asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
@@ -269,13 +276,17 @@ __global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, COLLIDE, false)) vx_st
     int nsteps = remaining < (long long)n_steps ? (int)remaining : n_steps;
     if (nsteps <= 0) { if (tid == 0) ctlp->status = status0 | VXG_ST_FINISHED_; return; }
 
-    unsigned char* gblob = B.blobs + (size_t)robot * L.total_bytes;
+    unsigned char* gblob = B.blobs + (size_t)robot * (FLUID ? B.L.total_bytes : L.total_bytes);
     const int MB = CB > 0 ? CB : B.max_bclass + 1;   // one more bond class than the batch's limit: the zero class
     const int mv = CV > 0 ? CV : B.max_vclass;
     BondKm* bkm = (BondKm*)(smem + G.total);
     unsigned char* tabp = smem + G.total + sizeof(BondKm) * (size_t)MB;
     const int max_col = COLLIDE ? B.max_col : 0;
     SmemTables<float> S = carve_tables<float>(tabp, mv, MB, true, max_col);
+    unsigned char* fp = tabp + tables_bytes<float>(mv, MB, true, max_col);
+    uint32_t* c_seg = (uint32_t*)fp;                    // self-collision: per-voxel segments of c_adj (the flow ring shares the address: never both)
+    uint16_t* c_adj = (uint16_t*)(fp + sizeof(uint32_t) * NV);
+    unsigned char* flp = fp + (max_col > 0 ? vx_align16(sizeof(uint32_t) * NV + sizeof(uint16_t) * 2 * (size_t)max_col) : 0);   // land/water arrays
     const int n_vox = ctlp->n_vox, n_vc = ctlp->n_vclass, n_bc = ctlp->n_bclass;
     const unsigned int flags = ctlp->flags;
     const int ZC = n_bc;               // index of the zero class
@@ -287,8 +298,15 @@ __global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, COLLIDE, false)) vx_st
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     // ---- stage in ------------------------------------------------------------------------------------------------------
-    copy16(smem, gblob, G.dyn_front, tid, T);
-    copy16(smem + G.off_stat, gblob + L.off_stat, (size_t)NV * sizeof(VoxStat), tid, T);
+    // positions .. momenta (one contiguous run of the blob) and the static words: two bulk copies by the TMA engine, in flight while
+    // the CTA fills the class tables and allocates tensor memory; waited for right before the first read
+    if (tid == 0) {
+        mbar_init(S.mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(S.mbar, (unsigned int)(G.dyn_front + (size_t)NV * sizeof(VoxStat)));
+        bulk_g2s(smem, gblob, (unsigned int)G.dyn_front, S.mbar);
+        bulk_g2s(smem + G.off_stat, gblob + (FLUID ? B.L.off_stat : L.off_stat), (unsigned int)((size_t)NV * sizeof(VoxStat)), S.mbar);   // (the strains sit before it in a land/water blob)
+    }
     {
         uint2 none; none.x = none.y = (uint32_t)NV | ((uint32_t)NV << 16);
         ((uint2*)(smem + G.off_nbm))[tid] = none;
@@ -307,6 +325,7 @@ __global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, COLLIDE, false)) vx_st
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    mbar_wait(S.mbar, 0);   // the bulk copies have landed
     const uint32_t tm = *tm_slot + ((uint32_t)((tid >> 5) & 3) << 21) + (uint32_t)(tid >> 7) * VXG_TM_COLS_PER_WARP;   // lane (warp % 4) * 32, this warp's columns
     for (int i = tid; i < n_vc; i += T) S.dsc_c[i] = (float)(S.scale_c[i] - S.sk[i].nom_size);
     if (tid <= n_bc) {   // expanded bond classes (the zero class: all zeros)
@@ -343,6 +362,23 @@ __global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, COLLIDE, false)) vx_st
 
     RobotView<float> R = make_view<float>(smem, L, n_vox);   // pos / quat / momA / momB views are valid (same offsets as the blob)
     R.stat = (VoxStat*)(smem + G.off_stat);
+    const BlobLayout LF = B.L;   // (the batch's layout: the blob of a land/water batch carries the mesh arrays and the strains)
+    if (FLUID) {
+        const size_t nvc = (size_t)LF.nvert_cap, nfc = (size_t)LF.nfacet_cap;
+        unsigned char* q = flp;
+        R.strain = (float*)q;     q += vx_align16(sizeof(float) * 6 * NV);
+        R.fbase = (uint16_t*)q;   q += vx_align16(sizeof(uint16_t) * NV);
+        R.facet = (Facet*)q;      q += vx_align16(sizeof(Facet) * nfc);
+        R.vcon = (Corner8*)q;     q += vx_align16(sizeof(Corner8) * nvc);
+        R.vpos = (double*)q;      q += vx_align16(sizeof(double) * 3 * nvc);
+        R.fdrag = (float*)q;
+        R.nvert_cap = LF.nvert_cap; R.nfacet_cap = LF.nfacet_cap;
+        unsigned char* gb = B.blobs + (size_t)robot * LF.total_bytes;
+        copy4(R.strain, gb + LF.off_strain, sizeof(float) * 6 * NV, tid, T);
+        copy4(R.fbase, gb + LF.off_fbase, (sizeof(uint16_t) * NV) & ~(size_t)3, tid, T);
+        copy4(R.facet, gb + LF.off_facet, sizeof(Facet) * nfc, tid, T);
+        copy4(R.vcon, gb + LF.off_vcon, sizeof(Corner8) * nvc, tid, T);
+    }
     RobotConsts<float> C;
     C.bk = nullptr; C.bkc = (const BondKc<float>*)S.bk;
     C.geo = make_geo<float>(1.0);
@@ -351,8 +387,9 @@ __global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, COLLIDE, false)) vx_st
     C.half_bond_z = (float)ctlp->half_bond_z;
     const double dt = ctlp->dt;
     C.dt = (float)dt;
-    C.fluid = false; C.drag_coeff = 0.0f; C.n_vert = 0; C.n_facet = 0;
-    C.floor_on = (flags & VXG_F_FLOOR_) != 0;
+    const bool fluid = FLUID && (flags & VXG_F_FLUID_) != 0;
+    C.fluid = fluid; C.drag_coeff = (float)ctlp->drag_coeff; C.n_vert = ctlp->n_vert; C.n_facet = ctlp->n_facet;
+    C.floor_on = (flags & VXG_F_FLOOR_) != 0 && !fluid;
     C.sticky = false; C.sym_mass = true;
     if (tid == 0) {
         ScaleSim SL;
@@ -367,9 +404,6 @@ __global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, COLLIDE, false)) vx_st
     const uint2 nb = ((const uint2*)(smem + G.off_nbm))[tid];   // -X | -Y << 16, -Z
     const float dt_inv_run = (float)(1.0 / dt);
     // ---- dataflow form: table ring, per-warp phase barriers, dependency masks --------------------------------------------
-    unsigned char* fp = tabp + tables_bytes<float>(mv, MB, true, max_col);
-    uint32_t* c_seg = (uint32_t*)fp;                    // self-collision: per-voxel segments of c_adj (the flow ring shares the address: never both)
-    uint16_t* c_adj = (uint16_t*)(fp + sizeof(uint32_t) * NV);
     double* r_scale = (double*)fp;                      fp += vx_align16(sizeof(double) * VXG_FLOW_RING * mv);
     float* r_dsc = (float*)fp;                          fp += vx_align16(sizeof(float) * VXG_FLOW_RING * mv);
     float* r_dnom = (float*)fp;                         fp += vx_align16(sizeof(float) * VXG_FLOW_RING * MB);
@@ -476,9 +510,9 @@ __global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, COLLIDE, false)) vx_st
                     r_scale[ea * mv + my_class] = ns; r_dsc[ea * mv + my_class] = (float)(ns - S.sk[my_class].nom_size);
                 }
                 V3<float> F = mk3<float>(0, 0, 0), M = mk3<float>(0, 0, 0);
-                bool dv = bond_eval_g<0, HOIST, F_REGS>(smem, G, NV, C, bkm, tid, st, own, fl, dt_inv, tm, F, M);
-                dv |= bond_eval_g<1, HOIST, F_REGS>(smem, G, NV, C, bkm, tid, st, own, fl, dt_inv, tm, F, M);
-                dv |= bond_eval_g<2, HOIST, F_REGS>(smem, G, NV, C, bkm, tid, st, own, fl, dt_inv, tm, F, M);
+                bool dv = bond_eval_g<0, HOIST, F_REGS, FLUID>(smem, G, NV, C, bkm, R.strain, tid, st, own, fl, dt_inv, tm, F, M);
+                dv |= bond_eval_g<1, HOIST, F_REGS, FLUID>(smem, G, NV, C, bkm, R.strain, tid, st, own, fl, dt_inv, tm, F, M);
+                dv |= bond_eval_g<2, HOIST, F_REGS, FLUID>(smem, G, NV, C, bkm, R.strain, tid, st, own, fl, dt_inv, tm, F, M);
                 if (dv) atomicMin(f_div, k);                 // Integrate() fails in this step (VX_Sim.cpp:1775-1777): acted on at the window's end
                 tm_wait_st();
                 mbar_arrive_warp(bondbar + warp, lane == 0);
@@ -543,12 +577,19 @@ __global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, COLLIDE, false)) vx_st
             }
             V3<float> F = mk3<float>(0, 0, 0), M = mk3<float>(0, 0, 0);
             int div = 0;
+            if (FLUID && fluid) {   // DragForce of this step from the state and bond strains of the previous one (LW/VX_Sim.cpp:1516-1597)
+                for (int u = tid; u < C.n_vert; u += T) mesh_vertex<float>(R, C, u);
+                __syncthreads();
+                for (int i = tid; i < C.n_facet; i += T) facet_task<float>(R, C, i);
+                __syncthreads();
+                if (tid < n_vox) F = voxel_drag<float>(R, tid, st);
+            }
 #ifdef VXG_TRACE
             const long long tr0 = clock64();
 #endif
-            div |= bond_eval_g<0, HOIST, F_REGS>(smem, G, NV, C, bkm, tid, st, own, fl, dt_inv, tm, F, M) ? 1 : 0;
-            div |= bond_eval_g<1, HOIST, F_REGS>(smem, G, NV, C, bkm, tid, st, own, fl, dt_inv, tm, F, M) ? 1 : 0;
-            div |= bond_eval_g<2, HOIST, F_REGS>(smem, G, NV, C, bkm, tid, st, own, fl, dt_inv, tm, F, M) ? 1 : 0;
+            div |= bond_eval_g<0, HOIST, F_REGS, FLUID>(smem, G, NV, C, bkm, R.strain, tid, st, own, fl, dt_inv, tm, F, M) ? 1 : 0;
+            div |= bond_eval_g<1, HOIST, F_REGS, FLUID>(smem, G, NV, C, bkm, R.strain, tid, st, own, fl, dt_inv, tm, F, M) ? 1 : 0;
+            div |= bond_eval_g<2, HOIST, F_REGS, FLUID>(smem, G, NV, C, bkm, R.strain, tid, st, own, fl, dt_inv, tm, F, M) ? 1 : 0;
             tm_wait_st();
             if (COLLIDE && col_on) {   // positions are still those of the previous step here
                 unsigned int verdict;
@@ -605,7 +646,7 @@ __global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, COLLIDE, false)) vx_st
 
     // ---- stage out -------------------------------------------------------------------------------------------------------
     __syncthreads();
-    copy16(gblob, smem, G.dyn_front, tid, T);
+    if (tid == 0) { fence_async_smem(); bulk_s2g(gblob, smem, (unsigned int)G.dyn_front); bulk_s2g_finish(); }   // positions .. momenta back to the blob
     if (tid < n_vox) ((uint32_t*)(gblob + L.off_flags))[tid] = fl;
     {
         const RobotView<float> Rg = make_view<float>(gblob, L, n_vox);
@@ -622,6 +663,7 @@ __global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, COLLIDE, false)) vx_st
         }
     }
     for (int i = tid; i < n_vc; i += T) B.scale_c[(size_t)robot * B.max_vclass + i] = FLOW ? r_scale[cur * mv + i] : S.scale_c[cur * mv + i];
+    if (FLUID) copy4(B.blobs + (size_t)robot * LF.total_bytes + LF.off_strain, R.strain, sizeof(float) * 6 * NV, tid, T);
     if (COLLIDE && col_on) {
         const int nc = n_col < max_col ? n_col : max_col;
         for (int i = tid; i < nc; i += T) B.col_pairs[(size_t)robot * max_col + i] = S.pairs[i];
@@ -647,9 +689,13 @@ __global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, COLLIDE, false)) vx_st
 }
 
 // shared memory of one CTA: mv / mb = capacities of the class tables as the kernel instantiation has them (mb includes the zero class)
-inline size_t gather_smem_bytes(int nv, int mv, int mb, bool flow, int max_col = 0) {
+inline size_t gather_smem_bytes(int nv, int mv, int mb, bool flow, int max_col = 0, int nvert_cap = 0, int nfacet_cap = 0) {
+    size_t fl = 0;
+    if (nvert_cap > 0)
+        fl = vx_align16(sizeof(float) * 6 * nv) + vx_align16(sizeof(uint16_t) * nv) + vx_align16(sizeof(Facet) * (size_t)nfacet_cap) + vx_align16(sizeof(Corner8) * (size_t)nvert_cap) +
+             vx_align16(sizeof(double) * 3 * (size_t)nvert_cap) + vx_align16(sizeof(float) * 3 * (size_t)nfacet_cap);
     return make_glayout(nv).total + sizeof(BondKm) * (size_t)mb + tables_bytes<float>(mv, mb, true, max_col) + (flow ? flow_bytes(mv, mb) : 0) +
-           (max_col > 0 ? vx_align16(sizeof(uint32_t) * nv + sizeof(uint16_t) * 2 * (size_t)max_col) : 0);
+           (max_col > 0 ? vx_align16(sizeof(uint32_t) * nv + sizeof(uint16_t) * 2 * (size_t)max_col) : 0) + fl;
 }
 
 // ---- launch plumbing (host) ----------------------------------------------------------------------------------------------------
@@ -657,18 +703,19 @@ inline size_t gather_smem_bytes(int nv, int mv, int mb, bool flow, int max_col =
 // re-keying by voxel-class pair); larger tables run the instantiation with run-time capacities
 #define VXG_CV 8
 #define VXG_CB 64
-template <int NV, bool FLOW, int CV, int CB, bool COLLIDE = false> inline cudaError_t launch_gather_form(const BatchDev<float>& B, const LaunchCfg& c) {
-    auto kern = vx_step_kernel_g<NV, FLOW, CV, CB, COLLIDE>;
-    const size_t smem = gather_smem_bytes(NV, CV > 0 ? CV : B.max_vclass, CB > 0 ? CB : B.max_bclass + 1, FLOW, COLLIDE ? B.max_col : 0);
+template <int NV, bool FLOW, int CV, int CB, bool COLLIDE = false, bool FLUID = false> inline cudaError_t launch_gather_form(const BatchDev<float>& B, const LaunchCfg& c) {
+    auto kern = vx_step_kernel_g<NV, FLOW, CV, CB, COLLIDE, FLUID>;
+    const size_t smem = gather_smem_bytes(NV, CV > 0 ? CV : B.max_vclass, CB > 0 ? CB : B.max_bclass + 1, FLOW, COLLIDE ? B.max_col : 0,
+                                          FLUID ? B.L.nvert_cap : 0, FLUID ? B.L.nfacet_cap : 0);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<c.n_robots, NV, smem, c.stream>>>(B, c.n_steps);
     return cudaGetLastError();
 }
 // does a CTA of this form fit next to the others the launch bounds ask for (227 KB per CTA, 228 KB per SM with 1 KB reserved per CTA)?
-template <int NV> inline bool gather_fits(int mv, int mb, bool flow, int max_col = 0) {
-    const size_t per_cta = gather_smem_bytes(NV, mv, mb, flow, max_col);
-    const int ctas = vx_min_ctas(NV, NV, max_col > 0, false);
+template <int NV> inline bool gather_fits(int mv, int mb, bool flow, int max_col = 0, int nvert_cap = 0, int nfacet_cap = 0) {
+    const size_t per_cta = gather_smem_bytes(NV, mv, mb, flow, max_col, nvert_cap, nfacet_cap);
+    const int ctas = vx_min_ctas(NV, NV, max_col > 0 || nvert_cap > 0, false);
     return per_cta <= 227u * 1024u && (per_cta + 1024u) * (size_t)ctas <= 228u * 1024u;
 }
 template <int NV> inline cudaError_t launch_gather(const BatchDev<float>& B, const LaunchCfg& c, bool flow) {
@@ -683,6 +730,12 @@ template <int NV> inline int launch_gather_collide(const BatchDev<float>& B, con
     if (B.max_vclass <= VXG_CV && B.max_bclass + 1 <= VXG_CB && gather_fits<NV>(VXG_CV, VXG_CB, false, B.max_col)) { *err = launch_gather_form<NV, false, VXG_CV, VXG_CB, true>(B, c); return 0; }
     if (gather_fits<NV>(B.max_vclass, B.max_bclass + 1, false, B.max_col)) { *err = launch_gather_form<NV, false, 0, 0, true>(B, c); return 0; }
     return 1;
+}
+// land/water layouts (with or without self-collision); run-time table capacities
+template <int NV> inline int launch_gather_fluid(const BatchDev<float>& B, const LaunchCfg& c, bool collide, cudaError_t* err) {
+    if (!gather_fits<NV>(B.max_vclass, B.max_bclass + 1, false, collide ? B.max_col : 0, B.L.nvert_cap, B.L.nfacet_cap)) return 1;
+    *err = collide ? launch_gather_form<NV, false, 0, 0, true, true>(B, c) : launch_gather_form<NV, false, 0, 0, false, true>(B, c);
+    return 0;
 }
 
 }  // namespace vx

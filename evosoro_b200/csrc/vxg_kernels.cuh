@@ -201,6 +201,24 @@ __device__ inline void axis_wait(unsigned long long* bar, unsigned int parity) {
 #endif
 }
 
+// ---- bulk asynchronous copies (TMA engine, 1-D form): a robot's sections travel between HBM and shared memory as a few large
+// transfers issued by one thread and tracked by an mbarrier, instead of a loop of 128-bit loads and stores through registers.
+__device__ inline void mbar_expect_tx(unsigned long long* bar, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ inline void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned int bytes, unsigned long long* bar) {   // bytes % 16 == 0, 16 B aligned
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ inline void bulk_s2g(void* gmem_dst, const void* smem_src, unsigned int bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ inline void bulk_s2g_finish() {   // the source may be reused / the CTA may exit once the engine has read it
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ inline void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }   // generic-proxy writes -> async proxy
+
 __device__ inline double warp_max(double x) {
     for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
     return x;

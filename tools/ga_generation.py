@@ -42,6 +42,7 @@ def main():
         t_write = time.perf_counter() - t0
         plan = subprocess.run([evaluation.VOXELYZE, "--plan"] + sum((["-f", p] for p in paths), []), capture_output=True, text=True).stdout
         work = sum(int(l.split()[1]) * int(l.split()[3]) for l in plan.strip().splitlines())
+        os.environ["VXG_TIMING"] = "1"    # the CLI prints its phase times on stderr
         t0 = time.perf_counter()
         codes = evaluation.run_batch(paths, devices=devices)
         t_ours = time.perf_counter() - t0
