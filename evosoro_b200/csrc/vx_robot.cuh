@@ -16,6 +16,7 @@
 // three sub-phases separated by barriers, so every accumulator word has exactly one writer per
 // sub-phase -- no atomics, deterministic summation order.  In the voxel phase the owner integrates.
 #pragma once
+#include <stdlib.h>
 #include "vx_math.cuh"
 
 namespace vx {
@@ -75,13 +76,15 @@ VX_HD constexpr size_t vx_align16(size_t x) { return (x + 15) & ~(size_t)15; }
 VX_HD constexpr size_t vx_align32(size_t x) { return (x + 31) & ~(size_t)31; }
 
 // voxel stride used for a robot of up to max_vox voxels: the kernels are instantiated for these strides
-// (powers of two, plus 224 = 7 warps for evosoro's default 6^3 workspace -- four such robots share an SM instead of three --
-// and 352 / 736 so that 7^3 and 9^3 robots do not pay for 512 / 1024 voxel slots)
+// (every multiple of a warp up to 256 but the last one -- CPPN morphologies in evosoro's default 6^3 workspace have 65 .. 216 voxels,
+// and a CTA's idle warps cost the SM resident robots --, then 352 / 736 so that 7^3 and 9^3 robots do not pay for 512 / 1024 slots)
 inline int stride_for(int max_vox) {
-    if (max_vox > 128 && max_vox <= 224) return 224;
-    if (max_vox > 256 && max_vox <= 352) return 352;
-    if (max_vox > 512 && max_vox <= 736) return 736;
-    int nv = 64;
+    static const int strides[] = {64, 96, 128, 160, 192, 224, 256, 352, 512, 736, 1024, 2048};
+    if (const char* e = getenv("VXG_STRIDES")) {   // tuning: restrict the strides in use, e.g. "128,224,512,1024" (must be instantiated ones)
+        for (const char* p = e; *p;) { const int v = atoi(p); if (v >= max_vox) { for (int s : strides) if (s == v) return v; } while (*p && *p != ',') p++; if (*p) p++; }
+    }
+    for (int s : strides) if (max_vox <= s) return s;
+    int nv = 4096;
     while (nv < max_vox) nv *= 2;
     return nv;
 }

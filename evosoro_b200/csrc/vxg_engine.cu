@@ -108,7 +108,12 @@ extern "C" int vxg_create(vxg_batch** out, int device, int n_robots, const vxg_l
     b->device = device; b->n_robots = n_robots; b->lim = *lim; b->prec = lim->precision;
     if (lim->max_vox > 2048) { delete b; return fail(VXG_UNSUPPORTED_SIZE, "vxg_create: more than 2048 voxels per robot is not supported yet"); }
     if (lim->max_mesh_verts < 0 || lim->max_mesh_verts > 32767) { delete b; return fail(VXG_ERR_ARG, "vxg_create: max_mesh_verts out of range"); }
-    b->L = make_layout(stride_for(lim->max_vox), (int)b->rs(), (lim->max_mesh_verts + 31) & ~31);
+    int stride = stride_for(lim->max_vox);
+    if (lim->reserved[0] > 0) {   // a wider stride asked for by the population layer (one kernel image for all small robots of a family)
+        if (lim->reserved[0] < stride || stride_for(lim->reserved[0]) != lim->reserved[0]) { delete b; return fail(VXG_ERR_ARG, "vxg_create: limits.reserved[0] = %d is not a stride that holds %d voxels", lim->reserved[0], lim->max_vox); }
+        stride = lim->reserved[0];
+    }
+    b->L = make_layout(stride, (int)b->rs(), (lim->max_mesh_verts + 31) & ~31);
     // thread mapping: <= 512 threads per CTA, VPT voxels per thread
     b->vpt = b->L.nv <= 512 ? 1 : b->L.nv / 512;
     b->threads = b->L.nv / b->vpt;

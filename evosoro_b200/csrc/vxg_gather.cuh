@@ -72,6 +72,12 @@ __device__ __forceinline__ BondK<float> bond_from_km(const BondKm& m) {
     return k;
 }
 
+// Resident CTAs per SM the register allocation of the gather kernels is sized for: one 10^3 robot, two 8^3 robots (with or without
+// the land/water mesh, which shares memory with the staging slots), four robots of 129 .. 224 voxels, 768 threads' worth of smaller ones.
+__host__ __device__ constexpr int vxg_ctas(int nv, bool collide, bool fluid) {
+    return nv > 512 ? 1 : nv == 512 ? 2 : nv >= 160 && nv <= 256 ? ((collide || fluid) && nv == 256 ? 3 : 4) : 768 / nv;
+}
+
 // ---- tensor memory as scratch: 32 lanes x 32 columns per warp, lane = thread, columns = that thread's words -----------------
 #define VXG_TM_COLS_PER_WARP 32
 __device__ inline void tm_ld8(uint32_t taddr, float (&v)[8]) {
@@ -201,6 +207,12 @@ __device__ __forceinline__ float voxel_phase_g(unsigned char* smem, const GLayou
     return dot(vel, vel);   // |Vel|^2 after the step (SS.MaxVoxVel, VX_Sim.cpp:1626-1649)
 }
 
+// do the land/water scratch arrays (vertex positions fp64, facet drags) fit into the staging region they can share memory with?
+__host__ __device__ inline bool fluid_scratch_aliases(int nv, int nvert_cap, int nfacet_cap) {
+    const GLayout G = make_glayout(nv);
+    return vx_align16(sizeof(double) * 3 * (size_t)nvert_cap) + vx_align16(sizeof(float) * 3 * (size_t)nfacet_cap) <= G.total - G.off_stA[0];
+}
+
 // Per-voxel view of the contact-bond list (CSR): seg[v] = begin | end << 16 into adj[], the partners of voxel v in list order (the
 // list is sorted by (v1, v2) with v1 < v2, so that is ascending partner index).  Built once per list rebuild -- a fraction of a
 // percent to a few percent of the steps -- so that a step costs a voxel one word and its own contacts instead of a scan of every
@@ -256,7 +268,7 @@ __device__ inline void flow_wait(unsigned long long* bar, uint32_t mask, uint32_
 //   FLUID  : land/water layouts: the deformable surface mesh (vertex -> voxels, facets) and the per-voxel strains live in shared memory
 //            behind the class tables (run-time capacities), fluid drag is evaluated at the start of every step
 template <int NV, bool FLOW, int CV, int CB, bool COLLIDE = false, bool FLUID = false>
-__global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, COLLIDE || FLUID, false)) vx_step_kernel_g(BatchDev<float> B, int n_steps) {
+__global__ void __launch_bounds__(NV, vxg_ctas(NV, COLLIDE, FLUID)) vx_step_kernel_g(BatchDev<float> B, int n_steps) {
     static_assert(!(FLOW && (COLLIDE || FLUID)), "the dataflow form has no per-step CTA-wide phases");
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int T = NV;
@@ -328,15 +340,15 @@ __global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, COLLIDE || FLUID, fals
     mbar_wait(S.mbar, 0);   // the bulk copies have landed
     const uint32_t tm = *tm_slot + ((uint32_t)((tid >> 5) & 3) << 21) + (uint32_t)(tid >> 7) * VXG_TM_COLS_PER_WARP;   // lane (warp % 4) * 32, this warp's columns
     for (int i = tid; i < n_vc; i += T) S.dsc_c[i] = (float)(S.scale_c[i] - S.sk[i].nom_size);
-    if (tid <= n_bc) {   // expanded bond classes (the zero class: all zeros)
+    for (int i = tid; i <= n_bc; i += T) {   // expanded bond classes (a robot with a class per voxel has more of them than threads); [n_bc] = the zero class
         BondKm m; memset(&m, 0, sizeof m);
-        if (tid < n_bc) {
-            const BondK<float> k = expand_bond<float>(((const BondKc<float>*)S.bk)[tid], make_geo<float>(ctlp->bond_len));
+        if (i < n_bc) {
+            const BondK<float> k = expand_bond<float>(((const BondKc<float>*)S.bk)[i], make_geo<float>(ctlp->bond_len));
             m.a2 = k.a2; m.b1 = k.b1; m.b2 = k.b2; m.b3 = k.b3;
             m.inv_len = k.inv_len; m.k_axial = k.k_axial; m.nom_dist = k.nom_dist; m.len_minus_dist = k.len_minus_dist;
             m.s1 = k.c_a1m1; m.c_a2i1 = k.c_a2i1; m.c_b2fm1 = k.c_b2fm1; m.c_b3i1 = k.c_b3i1;
         }
-        bkm[tid] = m;
+        bkm[i] = m;
     }
     // own static word (zero class for the missing bonds), own state, and the -axis neighbour table
     VoxStat st = ((const VoxStat*)(smem + G.off_stat))[tid];
@@ -363,6 +375,7 @@ __global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, COLLIDE || FLUID, fals
     RobotView<float> R = make_view<float>(smem, L, n_vox);   // pos / quat / momA / momB views are valid (same offsets as the blob)
     R.stat = (VoxStat*)(smem + G.off_stat);
     const BlobLayout LF = B.L;   // (the batch's layout: the blob of a land/water batch carries the mesh arrays and the strains)
+    const bool fluid_alias = FLUID && fluid_scratch_aliases(NV, LF.nvert_cap, LF.nfacet_cap);
     if (FLUID) {
         const size_t nvc = (size_t)LF.nvert_cap, nfc = (size_t)LF.nfacet_cap;
         unsigned char* q = flp;
@@ -370,8 +383,11 @@ __global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, COLLIDE || FLUID, fals
         R.fbase = (uint16_t*)q;   q += vx_align16(sizeof(uint16_t) * NV);
         R.facet = (Facet*)q;      q += vx_align16(sizeof(Facet) * nfc);
         R.vcon = (Corner8*)q;     q += vx_align16(sizeof(Corner8) * nvc);
-        R.vpos = (double*)q;      q += vx_align16(sizeof(double) * 3 * nvc);
-        R.fdrag = (float*)q;
+        // The deformed vertex positions and the per-facet drag only live from the start of a step to the per-voxel drag sum, the
+        // staging slots from the bond phase to the voxel phase: they share memory where they fit (a barrier after the drag sum keeps
+        // a fast warp's staging writes off a slow warp's reads).  That is what lets two 8^3 swimmers share an SM.
+        if (fluid_alias) { R.vpos = (double*)(smem + G.off_stA[0]); R.fdrag = (float*)(smem + G.off_stA[0] + vx_align16(sizeof(double) * 3 * nvc)); }
+        else { R.vpos = (double*)q; q += vx_align16(sizeof(double) * 3 * nvc); R.fdrag = (float*)q; }
         R.nvert_cap = LF.nvert_cap; R.nfacet_cap = LF.nfacet_cap;
         unsigned char* gb = B.blobs + (size_t)robot * LF.total_bytes;
         copy4(R.strain, gb + LF.off_strain, sizeof(float) * 6 * NV, tid, T);
@@ -583,6 +599,14 @@ __global__ void __launch_bounds__(NV, vx_min_ctas(NV, NV, COLLIDE || FLUID, fals
                 for (int i = tid; i < C.n_facet; i += T) facet_task<float>(R, C, i);
                 __syncthreads();
                 if (tid < n_vox) F = voxel_drag<float>(R, tid, st);
+                if (fluid_alias) {   // the facet drags share memory with the staging slots the bond phase writes next
+                    __syncthreads();
+                    if (tid == 0) {  // ... and with the "no neighbour" slots, which have to read as zeros again
+                        R4<float> za; za.x = za.y = za.z = za.w = 0.0f; R2<float> zb; zb.x = zb.y = 0.0f;
+#pragma unroll
+                        for (int a = 0; a < 3; a++) { ((R4<float>*)(smem + G.off_stA[a]))[NV] = za; ((R2<float>*)(smem + G.off_stB[a]))[NV] = zb; }
+                    }
+                }
             }
 #ifdef VXG_TRACE
             const long long tr0 = clock64();
@@ -693,7 +717,7 @@ inline size_t gather_smem_bytes(int nv, int mv, int mb, bool flow, int max_col =
     size_t fl = 0;
     if (nvert_cap > 0)
         fl = vx_align16(sizeof(float) * 6 * nv) + vx_align16(sizeof(uint16_t) * nv) + vx_align16(sizeof(Facet) * (size_t)nfacet_cap) + vx_align16(sizeof(Corner8) * (size_t)nvert_cap) +
-             vx_align16(sizeof(double) * 3 * (size_t)nvert_cap) + vx_align16(sizeof(float) * 3 * (size_t)nfacet_cap);
+             (fluid_scratch_aliases(nv, nvert_cap, nfacet_cap) ? 0 : vx_align16(sizeof(double) * 3 * (size_t)nvert_cap) + vx_align16(sizeof(float) * 3 * (size_t)nfacet_cap));
     return make_glayout(nv).total + sizeof(BondKm) * (size_t)mb + tables_bytes<float>(mv, mb, true, max_col) + (flow ? flow_bytes(mv, mb) : 0) +
            (max_col > 0 ? vx_align16(sizeof(uint32_t) * nv + sizeof(uint16_t) * 2 * (size_t)max_col) : 0) + fl;
 }
@@ -713,10 +737,9 @@ template <int NV, bool FLOW, int CV, int CB, bool COLLIDE = false, bool FLUID = 
     return cudaGetLastError();
 }
 // does a CTA of this form fit next to the others the launch bounds ask for (227 KB per CTA, 228 KB per SM with 1 KB reserved per CTA)?
+// (the launch bounds size the registers for vxg_ctas() CTAs per SM; when shared memory allows fewer, fewer are resident -- no error)
 template <int NV> inline bool gather_fits(int mv, int mb, bool flow, int max_col = 0, int nvert_cap = 0, int nfacet_cap = 0) {
-    const size_t per_cta = gather_smem_bytes(NV, mv, mb, flow, max_col, nvert_cap, nfacet_cap);
-    const int ctas = vx_min_ctas(NV, NV, max_col > 0 || nvert_cap > 0, false);
-    return per_cta <= 227u * 1024u && (per_cta + 1024u) * (size_t)ctas <= 228u * 1024u;
+    return gather_smem_bytes(NV, mv, mb, flow, max_col, nvert_cap, nfacet_cap) <= 227u * 1024u;
 }
 template <int NV> inline cudaError_t launch_gather(const BatchDev<float>& B, const LaunchCfg& c, bool flow) {
     const bool fixed = B.max_vclass <= VXG_CV && B.max_bclass + 1 <= VXG_CB && gather_fits<NV>(VXG_CV, VXG_CB, false);

@@ -11,7 +11,10 @@ cudaError_t launch_f32_collide_compact(const BatchDev<float>& B, const LaunchCfg
         cudaError_t e = cudaSuccess; int miss = 1;
         switch (c.nv) {
             case 64: miss = launch_gather_collide<64>(B, c, &e); break;
+            case 96: miss = launch_gather_collide<96>(B, c, &e); break;
             case 128: miss = launch_gather_collide<128>(B, c, &e); break;
+            case 160: miss = launch_gather_collide<160>(B, c, &e); break;
+            case 192: miss = launch_gather_collide<192>(B, c, &e); break;
             case 224: miss = launch_gather_collide<224>(B, c, &e); break;
             case 256: miss = launch_gather_collide<256>(B, c, &e); break;
             case 352: miss = launch_gather_collide<352>(B, c, &e); break;

@@ -17,7 +17,10 @@ cudaError_t launch_f32_compact(const BatchDev<float>& B, const LaunchCfg& c) {
     const bool push = form && !strcmp(form, "push"), flow = form && !strcmp(form, "flow");
     if (!push) switch (c.nv) {
         case 64: return launch_gather<64>(B, c, flow);
+        case 96: return launch_gather<96>(B, c, flow);
         case 128: return launch_gather<128>(B, c, flow);
+        case 160: return launch_gather<160>(B, c, flow);
+        case 192: return launch_gather<192>(B, c, flow);
         case 224: return launch_gather<224>(B, c, flow);
         case 256: return launch_gather<256>(B, c, flow);
         case 352: return launch_gather<352>(B, c, flow);

@@ -11,7 +11,10 @@ cudaError_t launch_f32_fluid_compact(const BatchDev<float>& B, const LaunchCfg& 
         cudaError_t e = cudaSuccess; int miss = 1;
         switch (c.nv) {
             case 64: miss = launch_gather_fluid<64>(B, c, collide, &e); break;
+            case 96: miss = launch_gather_fluid<96>(B, c, collide, &e); break;
             case 128: miss = launch_gather_fluid<128>(B, c, collide, &e); break;
+            case 160: miss = launch_gather_fluid<160>(B, c, collide, &e); break;
+            case 192: miss = launch_gather_fluid<192>(B, c, collide, &e); break;
             case 224: miss = launch_gather_fluid<224>(B, c, collide, &e); break;
             case 256: miss = launch_gather_fluid<256>(B, c, collide, &e); break;
             case 352: miss = launch_gather_fluid<352>(B, c, collide, &e); break;

@@ -7,9 +7,4 @@ cudaError_t launch_f32_extras_global(const BatchDev<float>& B, const LaunchCfg& 
     if (fluid) return collide ? launch_by_stride<float, false, false, true, true>(B, c) : launch_by_stride<float, false, false, true, false>(B, c);
     return launch_by_stride<float, false, false, false, true>(B, c);
 }
-// the logic-parity (fp64) instantiation of the same: the reference's arithmetic type for the fluid-drag and self-collision phases
-cudaError_t launch_f64_extras_global(const BatchDev<double>& B, const LaunchCfg& c, bool fluid, bool collide) {
-    if (fluid) return collide ? launch_by_stride<double, false, false, true, true>(B, c) : launch_by_stride<double, false, false, true, false>(B, c);
-    return launch_by_stride<double, false, false, false, true>(B, c);
-}
 }

@@ -29,7 +29,10 @@ template <typename Real, bool SMEM, bool COMPACT, bool FLUID, bool COLLIDE>
 inline cudaError_t launch_by_stride(const BatchDev<Real>& B, const LaunchCfg& c) {
     switch (c.nv) {
         case 64: return launch_one<Real, 64, 1, SMEM, COMPACT, FLUID, COLLIDE>(B, c);
+        case 96: return launch_one<Real, 96, 1, SMEM, COMPACT, FLUID, COLLIDE>(B, c);
         case 128: return launch_one<Real, 128, 1, SMEM, COMPACT, FLUID, COLLIDE>(B, c);
+        case 160: return launch_one<Real, 160, 1, SMEM, COMPACT, FLUID, COLLIDE>(B, c);
+        case 192: return launch_one<Real, 192, 1, SMEM, COMPACT, FLUID, COLLIDE>(B, c);
         case 224: return launch_one<Real, 224, 1, SMEM, COMPACT, FLUID, COLLIDE>(B, c);
         case 256: return launch_one<Real, 256, 1, SMEM, COMPACT, FLUID, COLLIDE>(B, c);
         case 352: return launch_one<Real, 352, 1, SMEM, COMPACT, FLUID, COLLIDE>(B, c);

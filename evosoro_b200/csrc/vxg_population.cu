@@ -88,6 +88,17 @@ extern "C" int vxg_pop_create(vxg_population** out, int device, const vxg_robot_
         cls[r] = c;
     });
     for (int r = 0; r < n_robots; r++) if (bad[r]) return fail(VXG_ERR_ARG, "vxg_pop_create: robot %d has a malformed descriptor", r);
+    // Small robots (strides up to 256) of one family share ONE stride, the largest any of them needs.  Measured (1024 CPPN-like
+    // robots of 75 .. 161 voxels, SelfColEnabled=1): one bucket per 32-voxel stride 6.1e9 voxel-timesteps/s, strides 128 + 224
+    // 7.7e9, everything at stride 192 9.5e9 -- every stride is its own kernel image, and several images resident on an SM at once
+    // evict each other from the instruction cache (the step loop is ~25 KB of code; ncu: stall_no_instruction).  A CTA's idle
+    // warps cost no issue slots, so the wider stride is the smaller tax.  Robots beyond 256 voxels keep a bucket per stride: there
+    // the shared memory a robot occupies decides how many are resident.
+    if (!getenv("VXG_POP_FINE_STRIDES")) {
+        std::map<std::tuple<int, int, int>, int> widest;   // (collide, mesh, compact) -> widest small stride
+        for (int r = 0; r < n_robots; r++) if (cls[r].stride <= 256) { int& w = widest[std::make_tuple(cls[r].collide, cls[r].mesh, cls[r].compact)]; w = std::max(w, cls[r].stride); }
+        for (int r = 0; r < n_robots; r++) if (cls[r].stride <= 256) cls[r].stride = widest[std::make_tuple(cls[r].collide, cls[r].mesh, cls[r].compact)];
+    }
 
     // ---- bucket, chunk ------------------------------------------------------------------------------------------------------
     typedef std::tuple<int, int, int, int, int, int> Key;
@@ -116,6 +127,7 @@ extern "C" int vxg_pop_create(vxg_population** out, int device, const vxg_robot_
             s.family = std::get<3>(kv.first) | (std::get<1>(kv.first) << 1) | (std::get<2>(kv.first) << 2);
             vxg_limits lim; memset(&lim, 0, sizeof lim);
             lim.precision = opt.precision; lim.max_vox = lim.max_vclass = lim.max_bclass = 1;
+            lim.reserved[0] = s.stride;   // the bucket's stride (may be wider than its own largest robot needs, see above)
             int col_cap = 0;
             for (int r : s.robots) {
                 lim.max_vox = std::max(lim.max_vox, descs[r].n_vox);

@@ -200,7 +200,8 @@ typedef struct vxg_limits {
     int32_t max_col_pairs;/* capacity for contact bonds per robot (0 = self-collision unused)        */
     int32_t max_mesh_verts;/* capacity for surface-mesh vertices per robot: needed (>= vxg_mesh_vertex_count of every
                               robot) to upload VXG_F_FLUID robots; 0 = no fluid-drag support in this batch      */
-    int32_t reserved[2];
+    int32_t reserved[2];  /* [0]: 0, or the voxel stride to lay the batch out with (one of the kernels' strides, >= what max_vox needs):
+                             lets batches of differently sized small robots share one kernel image; [1]: 0                      */
 } vxg_limits;
 
 /* status bits written by vxg_sync */

@@ -31,13 +31,13 @@ def test_mixed_population_runs_each_bucket_in_its_own_family_bit_identical_to_so
     pop = engine.Population(robots)
     info = pop.batches()
     where = [pop.locate(r) for r in range(len(robots))]
-    assert where[0][0] == where[4][0] == where[7][0]                       # the three 6^3 plain robots share a batch ...
-    assert len({w[0] for w in where}) == 6 and len(info) == 6              # ... and nothing else does
     fam = lambda r: info[where[r][0]]
-    assert fam(0)[0] == 3 and fam(0)[1] == 224 and fam(0)[3] == abi.VXG_FAM_COMPACT
-    assert fam(1)[1] == 128 and fam(2)[1] == 1024 and fam(2)[2] == 1024     # own strides; 10^3 on the 1024 x 1 production kernel
-    assert fam(3)[3] & abi.VXG_FAM_COLLIDE and fam(6)[3] & abi.VXG_FAM_COLLIDE and fam(6)[1] == 224
-    assert not (fam(5)[3] & abi.VXG_FAM_COMPACT)                            # different voxel masses: the wide family, alone
+    # small robots of one family share a batch at the widest stride any of them needs (one kernel image per family) ...
+    assert where[0][0] == where[1][0] == where[4][0] == where[7][0] and fam(0)[0] == 4 and fam(0)[1] == 224 and fam(0)[3] == abi.VXG_FAM_COMPACT
+    assert where[3][0] == where[6][0] and fam(3)[3] & abi.VXG_FAM_COLLIDE and fam(6)[1] == 224      # ... the self-colliding ones among themselves
+    assert fam(2)[0] == 1 and fam(2)[1] == 1024 and fam(2)[2] == 1024       # the 10^3 robot: its own batch on the 1024 x 1 production kernel
+    assert fam(5)[0] == 1 and not (fam(5)[3] & abi.VXG_FAM_COMPACT)         # different voxel masses: the wide family, alone
+    assert len(info) == 4
     total = np.array([700, 650, 600, 800, 700, 500, 640, 333], dtype=np.int64)
     pop.set_plan(total, np.full(8, 200, dtype=np.int64), None)
     pop.run()
