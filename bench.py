@@ -97,14 +97,14 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic_per_launch(lattice: int, robots: int, timesteps: int):
-    """dram bytes per launch of the step kernel from the committed ncu capture, if one matches this shape."""
+def ncu_traffic_per_launch(lattice: int, robots_per_launch: int, timesteps: int):
+    """dram bytes per launch of the step kernel from the committed ncu capture (bytes per robot and launch x robots in a launch)."""
     p = os.path.join(ROOT, "profiles", "dram_traffic.json")
     try:
         with open(p) as f:
             for e in json.load(f):
-                if e["lattice"] == lattice and e["robots"] == robots and e["timesteps"] == timesteps:
-                    return float(e["dram_bytes_per_launch"])
+                if e["lattice"] == lattice and e["timesteps"] == timesteps:
+                    return float(e["dram_bytes_per_robot_launch"]) * robots_per_launch
     except Exception:
         pass
     return None
@@ -413,7 +413,7 @@ def gpu_arm(args):
                        "l2": f"inputs larger than L2: {R} robot blobs of {216 * cfg['stride']} B = {R * 216 * cfg['stride'] / 1e6:.0f} MB streamed through per launch wave (L2 126 MB); state on chip inside a launch",
                        "kernel": cfg, "parallelism": f"{world} x independent shards, no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic_per_launch(n, R, TS), "peak_source": peak_src,
+                         "traffic": ncu_traffic_per_launch(n, cfg["robots_per_batch"], TS) if not (SELFCOL or WATER or args.sparse > 0) else None, "peak_source": peak_src,
                          "algorithmic_bytes_per_voxel_step": bpv, "algorithmic_bytes_per_launch": alg_bytes_per_launch,
                          "launch_ms": launch_s * 1e3, "kernel": "vx_step_kernel_g" if not (SELFCOL or WATER) and cfg["stride"] <= 1024 else "vx_step_kernel",
                          "launches_overlap": f"{cfg['batches']} batches on their own streams: achieved = algorithmic bytes of all launches / device time of the region",

@@ -12,7 +12,9 @@
 // Host code only (the device work is the batches').  Replaces evosoro's per-robot process fan-out (evaluation.py:89-90).
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <climits>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -26,6 +28,8 @@ using namespace vx;
 #define fail vxg_i_fail
 
 namespace {
+
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 struct Sub {                    // one homogeneous batch of the population
     vxg_batch* b = nullptr;
@@ -68,6 +72,10 @@ extern "C" int vxg_pop_create(vxg_population** out, int device, const vxg_robot_
     if (opt.precision != VXG_PREC_F32 && opt.precision != VXG_PREC_F64) return fail(VXG_ERR_ARG, "vxg_pop_create: unknown precision");
     const int per_vox = opt.col_pairs_per_vox > 0 ? opt.col_pairs_per_vox : 4;
     const int nt = vxg_i_host_threads(n_robots);
+    const bool timing = getenv("VXG_TIMING") != nullptr;
+    const double t0 = now_s();
+    if (timing) { cudaSetDevice(device); cudaFree(nullptr); }   // context creation, timed on its own
+    const double t_ctx = now_s();
 
     // ---- classify ---------------------------------------------------------------------------------------------------------
     struct Cls { int stride, collide, mesh, compact, vbin, bbin, nbc, nverts; };
@@ -100,6 +108,7 @@ extern "C" int vxg_pop_create(vxg_population** out, int device, const vxg_robot_
         for (int r = 0; r < n_robots; r++) if (cls[r].stride <= 256) cls[r].stride = widest[std::make_tuple(cls[r].collide, cls[r].mesh, cls[r].compact)];
     }
 
+    const double t_cls = now_s();
     // ---- bucket, chunk ------------------------------------------------------------------------------------------------------
     typedef std::tuple<int, int, int, int, int, int> Key;
     std::map<Key, std::vector<int>> buckets;
@@ -152,8 +161,11 @@ extern "C" int vxg_pop_create(vxg_population** out, int device, const vxg_robot_
         }
     }
     // ---- upload ---------------------------------------------------------------------------------------------------------------
+    const double t_alloc = now_s();
     int rc = vxg_pop_upload(p, descs);
     if (rc) { vxg_pop_destroy(p); return rc; }
+    if (timing) fprintf(stderr, "vxg_pop_create: %d robots, %d batches: CUDA context %.3f s, classify + bucket %.3f s, batches (device + pinned allocations) %.3f s, flatten %.3f s (%d host threads)\n",
+                        n_robots, (int)p->subs.size(), t_ctx - t0, t_cls - t_ctx, t_alloc - t_cls, now_s() - t_alloc, nt);
     *out = p;
     return VXG_OK;
 }
