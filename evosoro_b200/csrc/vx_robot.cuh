@@ -361,15 +361,14 @@ struct ColTables {              // per-robot static tables in global memory, rea
     const unsigned long long* near;   // [nv] mask over lattice offsets: within col_hops bond hops (CalcNearby)
     int n_surf, hops;
 };
-VX_HD int near_code(int dx, int dy, int dz) {   // rank of (dx,dy,dz) among the offsets with |dx|+|dy|+|dz| <= 3, z slowest
+VX_HD int near_code(int dx, int dy, int dz) {   // rank of (dx,dy,dz) among the offsets with |dx|+|dy|+|dz| <= 3, z slowest, then y, then x
+    // closed form of the enumeration: a z-layer holds the (x, y) with |x|+|y| <= r = 3-|z|, i.e. 2r^2+2r+1 offsets, a y-row of it 2(r-|y|)+1
+    const int az = dz < 0 ? -dz : dz, ay = dy < 0 ? -dy : dy;
     int code = 0;
-    for (int z = -3; z <= 3; z++) for (int y = -3; y <= 3; y++) for (int x = -3; x <= 3; x++) {
-        int l1 = (x < 0 ? -x : x) + (y < 0 ? -y : y) + (z < 0 ? -z : z);
-        if (l1 > 3) continue;
-        if (x == dx && y == dy && z == dz) return code;
-        code++;
-    }
-    return -1;
+    for (int z = -3; z < dz; z++) { const int r = 3 - (z < 0 ? -z : z); code += 2 * r * r + 2 * r + 1; }
+    const int r = 3 - az;
+    for (int y = -r; y < dy; y++) code += 2 * (r - (y < 0 ? -y : y)) + 1;
+    return code + dx + (r - ay);
 }
 // CalcL1Bonds' pair test (VX_Sim.cpp:2376-2386): inside the filter radius, not a lattice-near neighbour, and
 // closer than CollisionHorizon * Scale_1 (the reference uses voxel 1's scale twice)

@@ -110,7 +110,8 @@ extern "C" int vxg_create(vxg_batch** out, int device, int n_robots, const vxg_l
     if (lim->max_mesh_verts < 0 || lim->max_mesh_verts > 32767) { delete b; return fail(VXG_ERR_ARG, "vxg_create: max_mesh_verts out of range"); }
     int stride = stride_for(lim->max_vox);
     if (lim->reserved[0] > 0) {   // a wider stride asked for by the population layer (one kernel image for all small robots of a family)
-        if (lim->reserved[0] < stride || stride_for(lim->reserved[0]) != lim->reserved[0]) { delete b; return fail(VXG_ERR_ARG, "vxg_create: limits.reserved[0] = %d is not a stride that holds %d voxels", lim->reserved[0], lim->max_vox); }
+        const bool warp_multiple = lim->reserved[0] >= 64 && lim->reserved[0] <= 256 && lim->reserved[0] % 32 == 0;   // every family has these
+        if (lim->reserved[0] < lim->max_vox || !(warp_multiple || stride_for(lim->reserved[0]) == lim->reserved[0])) { delete b; return fail(VXG_ERR_ARG, "vxg_create: limits.reserved[0] = %d is not a stride that holds %d voxels", lim->reserved[0], lim->max_vox); }
         stride = lim->reserved[0];
     }
     b->L = make_layout(stride, (int)b->rs(), (lim->max_mesh_verts + 31) & ~31);

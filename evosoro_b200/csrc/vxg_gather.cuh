@@ -22,6 +22,7 @@
 // Replaces CVX_Sim::Integrate (VX_Sim.cpp:1763-1933) for robots of the production family (pack_compact, vx_pack.h).
 #pragma once
 #include <cstdio>
+#include <cstdlib>
 #include "vxg_kernels.cuh"
 #include "vxg_launch.cuh"
 
@@ -267,19 +268,35 @@ __device__ inline void flow_wait(unsigned long long* bar, uint32_t mask, uint32_
 //   COLLIDE: self-collision (contact-bond list in shared memory, rebuilt on the device, contact forces through the per-voxel CSR)
 //   FLUID  : land/water layouts: the deformable surface mesh (vertex -> voxels, facets) and the per-voxel strains live in shared memory
 //            behind the class tables (run-time capacities), fluid drag is evaluated at the start of every step
-template <int NV, bool FLOW, int CV, int CB, bool COLLIDE = false, bool FLUID = false>
-__global__ void __launch_bounds__(NV, vxg_ctas(NV, COLLIDE, FLUID)) vx_step_kernel_g(BatchDev<float> B, int n_steps) {
+template <int NV_, bool FLOW, int CV, int CB, bool COLLIDE = false, bool FLUID = false>
+__global__ void __launch_bounds__(NV_ ? NV_ : 256, NV_ ? vxg_ctas(NV_, COLLIDE, FLUID) : 3) vx_step_kernel_g(BatchDev<float> B, int n_steps) {
     static_assert(!(FLOW && (COLLIDE || FLUID)), "the dataflow form has no per-step CTA-wide phases");
     extern __shared__ __align__(128) unsigned char smem[];
-    constexpr int T = NV;
-    constexpr BlobLayout L = make_layout(NV, 4);
-    constexpr GLayout G = make_glayout(NV);
-    constexpr int TM_COLS = tm_cols_for(NV);
-    constexpr bool HOIST = !(NV == 1024 || NV == 512);   // bond_force: only where there are more than 64 registers per thread
-    constexpr bool F_REGS = NV == 1024 || COLLIDE || FLUID;   // (contact / drag forces join the own share before the barrier)
+    // NV_ == 0: the voxel stride is a RUN-TIME value (a multiple of 32 up to 256, = the CTA's thread count): one kernel image for
+    // every small robot, each with exactly the warps it needs (several images resident on an SM evict each other from the
+    // instruction cache -- profiles/r02_sizes.txt).  NV_ > 0: compile-time stride, every offset an immediate.
+    const int NV = NV_ ? NV_ : B.L.nv;
+    const int T = NV;
+    const BlobLayout L = NV_ ? make_layout(NV_, 4) : make_layout(NV, 4);
+    const GLayout G = make_glayout(NV);
+    const int TM_COLS = tm_cols_for(NV);
+    constexpr bool HOIST = !(NV_ == 1024 || NV_ == 512);   // bond_force: only where there are more than 64 registers per thread
+    constexpr bool F_REGS = NV_ == 1024 || COLLIDE || FLUID;   // (contact / drag forces join the own share before the barrier)
+    // PERM (-DVXG_PERM, off): thread t of the 1024-thread kernel owns voxel (t % 32) * 32 + t / 32 -- the transpose of the warp x lane
+    // grid -- and every on-chip array is indexed by THREAD, so that a warp's voxels are spread over the whole robot instead of being
+    // 32 consecutive ones.  Motivation: the layers of a 10^3 robot differ in how much they deform, and the calm top-layer warps reach
+    // the bonds -> voxels barrier thousands of cycles before the others (clock64 trace).  Measured: balanced, bit-identical, and 8 %
+    // SLOWER (1.82e10 vs 1.97e10): the calm warps were cheap precisely because all their lanes were in small-angle mode and some
+    // skipped an axis; spread out, every warp pays for both modes and all three axes.  Kept as the record of that experiment.
+#ifdef VXG_PERM
+    constexpr bool PERM = NV_ == 1024 && !FLOW && !COLLIDE && !FLUID;
+#else
+    constexpr bool PERM = false;
+#endif
     const int robot = blockIdx.x;
     int tid;
     asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    const int vme = PERM ? (((tid & 31) << 5) | (tid >> 5)) : tid;   // the voxel this thread owns
     RobotCtl* ctlp = B.ctl + robot;
     const unsigned int status0 = ctlp->status;
     if (status0 & (VXG_ST_DIVERGED_ | VXG_ST_FINISHED_)) return;
@@ -306,13 +323,13 @@ __global__ void __launch_bounds__(NV, vxg_ctas(NV, COLLIDE, FLUID)) vx_step_kern
     // ---- tensor memory -------------------------------------------------------------------------------------------------
     uint32_t* tm_slot = (uint32_t*)S.red;   // the reduction scratch is idle until the first latch
     if (tid < 32) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tm_slot)), "n"(TM_COLS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tm_slot)), "r"(TM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     // ---- stage in ------------------------------------------------------------------------------------------------------
     // positions .. momenta (one contiguous run of the blob) and the static words: two bulk copies by the TMA engine, in flight while
     // the CTA fills the class tables and allocates tensor memory; waited for right before the first read
-    if (tid == 0) {
+    if (!PERM && tid == 0) {
         mbar_init(S.mbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mbar_expect_tx(S.mbar, (unsigned int)(G.dyn_front + (size_t)NV * sizeof(VoxStat)));
@@ -337,7 +354,7 @@ __global__ void __launch_bounds__(NV, vxg_ctas(NV, COLLIDE, FLUID)) vx_step_kern
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    mbar_wait(S.mbar, 0);   // the bulk copies have landed
+    if (!PERM) mbar_wait(S.mbar, 0);   // the bulk copies have landed
     const uint32_t tm = *tm_slot + ((uint32_t)((tid >> 5) & 3) << 21) + (uint32_t)(tid >> 7) * VXG_TM_COLS_PER_WARP;   // lane (warp % 4) * 32, this warp's columns
     for (int i = tid; i < n_vc; i += T) S.dsc_c[i] = (float)(S.scale_c[i] - S.sk[i].nom_size);
     for (int i = tid; i <= n_bc; i += T) {   // expanded bond classes (a robot with a class per voxel has more of them than threads); [n_bc] = the zero class
@@ -351,19 +368,30 @@ __global__ void __launch_bounds__(NV, vxg_ctas(NV, COLLIDE, FLUID)) vx_step_kern
         bkm[i] = m;
     }
     // own static word (zero class for the missing bonds), own state, and the -axis neighbour table
-    VoxStat st = ((const VoxStat*)(smem + G.off_stat))[tid];
-    if (tid >= n_vox) st.nbr[0] = st.nbr[1] = st.nbr[2] = -1;
+    const bool active = vme < n_vox;
+    VoxStat st = PERM ? ((const VoxStat*)(gblob + L.off_stat))[vme] : ((const VoxStat*)(smem + G.off_stat))[tid];
+    if (!active) st.nbr[0] = st.nbr[1] = st.nbr[2] = -1;
+    if (PERM) {   // neighbour indices become thread indices; this voxel's state goes to this thread's slots (gathered from the blob once per launch)
+#pragma unroll
+        for (int a = 0; a < 3; a++) if (st.nbr[a] >= 0) st.nbr[a] = (int16_t)(((st.nbr[a] & 31) << 5) | (st.nbr[a] >> 5));
+        const RobotView<float> Rg = make_view<float>(gblob, L, n_vox);
+        double* sp = (double*)(smem + G.off_pos);
+        sp[tid] = Rg.pos[vme]; sp[NV + tid] = Rg.pos[NV + vme]; sp[2 * NV + tid] = Rg.pos[2 * NV + vme];
+        ((R4<float>*)(smem + G.off_quat))[tid] = Rg.quat[vme];
+        ((R4<float>*)(smem + G.off_momA))[tid] = Rg.momA[vme];
+        ((R2<float>*)(smem + G.off_momB))[tid] = Rg.momB[vme];
+    }
 #pragma unroll
     for (int a = 0; a < 3; a++) {
         if (st.nbr[a] < 0) st.bcls[a] = (uint16_t)ZC;
         else ((int16_t*)(smem + G.off_nbm))[4 * st.nbr[a] + a] = (int16_t)tid;
     }
-    uint32_t fl = ((const uint32_t*)(gblob + L.off_flags))[tid];
+    uint32_t fl = ((const uint32_t*)(gblob + L.off_flags))[vme];
     {   // damping history: blob -> this thread's tensor-memory columns
         const RobotView<float> Rg = make_view<float>(gblob, L, n_vox);
 #pragma unroll
         for (int a = 0; a < 3; a++) {
-            const R4<float> x = Rg.histA(a)[tid], y = Rg.histB(a)[tid]; const float z = Rg.histC(a)[tid];
+            const R4<float> x = Rg.histA(a)[vme], y = Rg.histB(a)[vme]; const float z = Rg.histC(a)[vme];
             BondHist<float> h; h.p2 = mk3<float>(x.x, x.y, x.z); h.a1 = mk3<float>(x.w, y.x, y.y); h.a2 = mk3<float>(y.z, y.w, z);
             if (a == 0) hist_store<0>(tm, h); else if (a == 1) hist_store<1>(tm, h); else hist_store<2>(tm, h);
         }
@@ -433,7 +461,7 @@ __global__ void __launch_bounds__(NV, vxg_ctas(NV, COLLIDE, FLUID)) vx_step_kern
         uint32_t pm = 0, mm = 0;
 #pragma unroll
         for (int a = 0; a < 3; a++) if (st.nbr[a] >= 0) pm |= 1u << (st.nbr[a] >> 5);
-        if (tid < n_vox) {
+        if (active) {
             const int m0 = nb.x & 0xFFFFu, m1 = nb.x >> 16, m2 = nb.y & 0xFFFFu;
             if (m0 < NV) mm |= 1u << (m0 >> 5);
             if (m1 < NV) mm |= 1u << (m1 >> 5);
@@ -489,13 +517,13 @@ __global__ void __launch_bounds__(NV, vxg_ctas(NV, COLLIDE, FLUID)) vx_step_kern
             if (tid == 0) { f_time[1] = f_time[0]; f_div[1] = k; }   // where this window starts, for the divergence rewind
             if (s0 == latch) {   // IniCM = SS.CurCM at TimeStep entry (VX_Sim.cpp:1064-1075): COM after the previous step
                 double mx = 0, my = 0, mz = 0, mm = 0;
-                if (tid < n_vox) { const double m = (double)S.vk[st.vcls].mass; mx = own.px * m; my = own.py * m; mz = own.pz * m; mm = m; }
+                if (active) { const double m = (double)S.vk[st.vcls].mass; mx = own.px * m; my = own.py * m; mz = own.pz * m; mm = m; }
                 block_sum4(mx, my, mz, mm, S.red);
                 if (tid == 0) { ctlp->ini_com[0] = mx / mm; ctlp->ini_com[1] = my / mm; ctlp->ini_com[2] = mz / mm; ctlp->ini_latched = 1; }
             }
             if (s0 == eol) {     // SS.EndOfLifetimePosteriorY = getPosteriorY() at TimeStep entry (VX_Sim.cpp:1078-1082)
                 double lo = 1e300;
-                if (tid < n_vox && S.sk[st.vcls].mat_index != 5) lo = own.py;
+                if (active && S.sk[st.vcls].mat_index != 5) lo = own.py;
                 lo = -warp_max(-lo);
                 __syncthreads();
                 if ((tid & 31) == 0) S.red[tid >> 5] = lo;
@@ -534,7 +562,7 @@ __global__ void __launch_bounds__(NV, vxg_ctas(NV, COLLIDE, FLUID)) vx_step_kern
                 mbar_arrive_warp(bondbar + warp, lane == 0);
                 // -axis neighbours' owners must have staged their shares of step k (and read the positions this warp is about to overwrite)
                 flow_wait(bondbar, minus_mask, (uint32_t)k & 1u, lane);
-                if (tid < n_vox) voxel_phase_g<F_REGS>(smem, G, NV, C, R, tid, st, nb, own, fl, F, M);
+                if (active) voxel_phase_g<F_REGS>(smem, G, NV, C, R, tid, st, nb, own, fl, F, M);
                 mbar_arrive_warp(voxbar + warp, lane == 0);
                 if (tid == 0) f_time[0] += dt;               // CurTime += dt (VX_Sim.cpp:1929)
             }
@@ -552,13 +580,13 @@ __global__ void __launch_bounds__(NV, vxg_ctas(NV, COLLIDE, FLUID)) vx_step_kern
             const long long s = step0 + k;
             if (s == latch) {   // IniCM = SS.CurCM at TimeStep entry (VX_Sim.cpp:1064-1075): COM after the previous step
                 double mx = 0, my = 0, mz = 0, mm = 0;
-                if (tid < n_vox) { const double m = (double)S.vk[st.vcls].mass; mx = own.px * m; my = own.py * m; mz = own.pz * m; mm = m; }
+                if (active) { const double m = (double)S.vk[st.vcls].mass; mx = own.px * m; my = own.py * m; mz = own.pz * m; mm = m; }
                 block_sum4(mx, my, mz, mm, S.red);
                 if (tid == 0) { ctlp->ini_com[0] = mx / mm; ctlp->ini_com[1] = my / mm; ctlp->ini_com[2] = mz / mm; ctlp->ini_latched = 1; }
             }
             if (s == eol) {     // SS.EndOfLifetimePosteriorY = getPosteriorY() at TimeStep entry (VX_Sim.cpp:1078-1082)
                 double lo = 1e300;
-                if (tid < n_vox && S.sk[st.vcls].mat_index != 5) lo = own.py;
+                if (active && S.sk[st.vcls].mat_index != 5) lo = own.py;
                 lo = -warp_max(-lo);
                 __syncthreads();
                 if ((tid & 31) == 0) S.red[tid >> 5] = lo;
@@ -598,7 +626,7 @@ __global__ void __launch_bounds__(NV, vxg_ctas(NV, COLLIDE, FLUID)) vx_step_kern
                 __syncthreads();
                 for (int i = tid; i < C.n_facet; i += T) facet_task<float>(R, C, i);
                 __syncthreads();
-                if (tid < n_vox) F = voxel_drag<float>(R, tid, st);
+                if (active) F = voxel_drag<float>(R, tid, st);
                 if (fluid_alias) {   // the facet drags share memory with the staging slots the bond phase writes next
                     __syncthreads();
                     if (tid == 0) {  // ... and with the "no neighbour" slots, which have to read as zeros again
@@ -626,7 +654,7 @@ __global__ void __launch_bounds__(NV, vxg_ctas(NV, COLLIDE, FLUID)) vx_step_kern
                     if (n_col > max_col) { col_overflow = true; break; }
                     if (n_col > 0) col_csr_build(S.pairs, n_col, c_seg, c_adj, (int*)S.red);
                 }
-                if (n_col > 0 && tid < n_vox) {   // CVXS_BondCollision::CalcContactForce for this voxel's contact bonds, in list order
+                if (n_col > 0 && active) {   // CVXS_BondCollision::CalcContactForce for this voxel's contact bonds, in list order
                     const uint32_t sg = c_seg[tid];
                     V3<float> fc = mk3<float>(0, 0, 0);
                     for (uint32_t i = sg & 0xFFFFu; i < (sg >> 16); i++) col_contact<float>(R, C, st, own, c_adj[i], fc);
@@ -649,7 +677,7 @@ __global__ void __launch_bounds__(NV, vxg_ctas(NV, COLLIDE, FLUID)) vx_step_kern
             }
             // ---- voxel phase: gather the shares of the -X/-Y/-Z bonds (Force2 = -Force1, Moment2), integrate -------------------
             float sp2 = 0.0f;
-            if (tid < n_vox) sp2 = voxel_phase_g<F_REGS>(smem, G, NV, C, R, tid, st, nb, own, fl, F, M);
+            if (active) sp2 = voxel_phase_g<F_REGS>(smem, G, NV, C, R, tid, st, nb, own, fl, F, M);
             if (COLLIDE && col_on) {   // SS.MaxVoxVel for the next UpdateCollisions
                 for (int o = 16; o > 0; o >>= 1) sp2 = fmaxf(sp2, __shfl_xor_sync(0xffffffffu, sp2, o));
                 if ((tid & 31) == 0) atomicMax(&S.maxvel[k & 1], __float_as_uint(sp2));
@@ -670,8 +698,15 @@ __global__ void __launch_bounds__(NV, vxg_ctas(NV, COLLIDE, FLUID)) vx_step_kern
 
     // ---- stage out -------------------------------------------------------------------------------------------------------
     __syncthreads();
-    if (tid == 0) { fence_async_smem(); bulk_s2g(gblob, smem, (unsigned int)G.dyn_front); bulk_s2g_finish(); }   // positions .. momenta back to the blob
-    if (tid < n_vox) ((uint32_t*)(gblob + L.off_flags))[tid] = fl;
+    if (PERM) {
+        if (active) {   // this thread's voxel back to its place in the blob
+            const RobotView<float> Rg = make_view<float>(gblob, L, n_vox);
+            Rg.pos[vme] = own.px; Rg.pos[NV + vme] = own.py; Rg.pos[2 * NV + vme] = own.pz;
+            Rg.quat[vme] = own.q;
+            Rg.momA[vme] = R.momA[tid]; Rg.momB[vme] = R.momB[tid];
+        }
+    } else if (tid == 0) { fence_async_smem(); bulk_s2g(gblob, smem, (unsigned int)G.dyn_front); bulk_s2g_finish(); }   // positions .. momenta back to the blob
+    if (active) ((uint32_t*)(gblob + L.off_flags))[vme] = fl;
     {
         const RobotView<float> Rg = make_view<float>(gblob, L, n_vox);
 #pragma unroll
@@ -682,7 +717,7 @@ __global__ void __launch_bounds__(NV, vxg_ctas(NV, COLLIDE, FLUID)) vx_step_kern
                 R4<float> x, y;
                 x.x = h.p2.x; x.y = h.p2.y; x.z = h.p2.z; x.w = h.a1.x;
                 y.x = h.a1.y; y.y = h.a1.z; y.z = h.a2.x; y.w = h.a2.y;
-                Rg.histA(a)[tid] = x; Rg.histB(a)[tid] = y; Rg.histC(a)[tid] = h.a2.z;
+                Rg.histA(a)[vme] = x; Rg.histB(a)[vme] = y; Rg.histC(a)[vme] = h.a2.z;
             }
         }
     }
@@ -709,7 +744,7 @@ __global__ void __launch_bounds__(NV, vxg_ctas(NV, COLLIDE, FLUID)) vx_step_kern
     __syncthreads();
     // warp 0's own address IS the allocation's base (lane quarter 0, column block 0); the slot it was published through has been
     // reused as reduction scratch since
-    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "n"(TM_COLS) : "memory");
+    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(TM_COLS) : "memory");
 }
 
 // shared memory of one CTA: mv / mb = capacities of the class tables as the kernel instantiation has them (mb includes the zero class)
@@ -729,34 +764,42 @@ inline size_t gather_smem_bytes(int nv, int mv, int mb, bool flow, int max_col =
 #define VXG_CB 64
 template <int NV, bool FLOW, int CV, int CB, bool COLLIDE = false, bool FLUID = false> inline cudaError_t launch_gather_form(const BatchDev<float>& B, const LaunchCfg& c) {
     auto kern = vx_step_kernel_g<NV, FLOW, CV, CB, COLLIDE, FLUID>;
-    const size_t smem = gather_smem_bytes(NV, CV > 0 ? CV : B.max_vclass, CB > 0 ? CB : B.max_bclass + 1, FLOW, COLLIDE ? B.max_col : 0,
+    const size_t smem = gather_smem_bytes(NV ? NV : c.nv, CV > 0 ? CV : B.max_vclass, CB > 0 ? CB : B.max_bclass + 1, FLOW, COLLIDE ? B.max_col : 0,
                                           FLUID ? B.L.nvert_cap : 0, FLUID ? B.L.nfacet_cap : 0);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<c.n_robots, NV, smem, c.stream>>>(B, c.n_steps);
+    kern<<<c.n_robots, NV ? NV : c.nv, smem, c.stream>>>(B, c.n_steps);
     return cudaGetLastError();
 }
 // does a CTA of this form fit next to the others the launch bounds ask for (227 KB per CTA, 228 KB per SM with 1 KB reserved per CTA)?
 // (the launch bounds size the registers for vxg_ctas() CTAs per SM; when shared memory allows fewer, fewer are resident -- no error)
-template <int NV> inline bool gather_fits(int mv, int mb, bool flow, int max_col = 0, int nvert_cap = 0, int nfacet_cap = 0) {
-    return gather_smem_bytes(NV, mv, mb, flow, max_col, nvert_cap, nfacet_cap) <= 227u * 1024u;
+inline bool gather_fits(int nv, int mv, int mb, bool flow, int max_col = 0, int nvert_cap = 0, int nfacet_cap = 0) {
+    return gather_smem_bytes(nv, mv, mb, flow, max_col, nvert_cap, nfacet_cap) <= 227u * 1024u;
+}
+// VXG_RT_STRIDE=1: small robots run the run-time-stride image (NV = 0): one image, exactly the warps a robot needs.  Measured
+// SLOWER than the compile-time strides (dense 6^3: 1.80e10 vs 2.13e10; CPPN-like blobs with self-collision at their exact
+// strides 8.3e9 vs 1.00e10 at one shared compile-time stride): the run-time offsets cost registers and address arithmetic in
+// every access, and a CTA's idle warps were never the expensive part.  Kept selectable as the record of that experiment.
+inline bool vxg_use_rt(int nv) {
+    const char* e = getenv("VXG_RT_STRIDE");
+    return e && e[0] == '1' && nv <= 256 && nv % 32 == 0;
 }
 template <int NV> inline cudaError_t launch_gather(const BatchDev<float>& B, const LaunchCfg& c, bool flow) {
-    const bool fixed = B.max_vclass <= VXG_CV && B.max_bclass + 1 <= VXG_CB && gather_fits<NV>(VXG_CV, VXG_CB, false);
+    const bool fixed = B.max_vclass <= VXG_CV && B.max_bclass + 1 <= VXG_CB && gather_fits(NV ? NV : c.nv, VXG_CV, VXG_CB, false);
     if (flow) {   // experiment form, run-time capacities only
-        if (gather_fits<NV>(B.max_vclass, B.max_bclass + 1, true)) return launch_gather_form<NV, true, 0, 0>(B, c);
+        if (gather_fits(NV ? NV : c.nv, B.max_vclass, B.max_bclass + 1, true)) return launch_gather_form<NV, true, 0, 0>(B, c);
     }
     return fixed ? launch_gather_form<NV, false, VXG_CV, VXG_CB>(B, c) : launch_gather_form<NV, false, 0, 0>(B, c);
 }
 // the same with self-collision: 0 = launched, 1 = this stride / table size has no gather instantiation that fits (caller falls back)
 template <int NV> inline int launch_gather_collide(const BatchDev<float>& B, const LaunchCfg& c, cudaError_t* err) {
-    if (B.max_vclass <= VXG_CV && B.max_bclass + 1 <= VXG_CB && gather_fits<NV>(VXG_CV, VXG_CB, false, B.max_col)) { *err = launch_gather_form<NV, false, VXG_CV, VXG_CB, true>(B, c); return 0; }
-    if (gather_fits<NV>(B.max_vclass, B.max_bclass + 1, false, B.max_col)) { *err = launch_gather_form<NV, false, 0, 0, true>(B, c); return 0; }
+    if (B.max_vclass <= VXG_CV && B.max_bclass + 1 <= VXG_CB && gather_fits(NV ? NV : c.nv, VXG_CV, VXG_CB, false, B.max_col)) { *err = launch_gather_form<NV, false, VXG_CV, VXG_CB, true>(B, c); return 0; }
+    if (gather_fits(NV ? NV : c.nv, B.max_vclass, B.max_bclass + 1, false, B.max_col)) { *err = launch_gather_form<NV, false, 0, 0, true>(B, c); return 0; }
     return 1;
 }
 // land/water layouts (with or without self-collision); run-time table capacities
 template <int NV> inline int launch_gather_fluid(const BatchDev<float>& B, const LaunchCfg& c, bool collide, cudaError_t* err) {
-    if (!gather_fits<NV>(B.max_vclass, B.max_bclass + 1, false, collide ? B.max_col : 0, B.L.nvert_cap, B.L.nfacet_cap)) return 1;
+    if (!gather_fits(NV ? NV : c.nv, B.max_vclass, B.max_bclass + 1, false, collide ? B.max_col : 0, B.L.nvert_cap, B.L.nfacet_cap)) return 1;
     *err = collide ? launch_gather_form<NV, false, 0, 0, true, true>(B, c) : launch_gather_form<NV, false, 0, 0, false, true>(B, c);
     return 0;
 }

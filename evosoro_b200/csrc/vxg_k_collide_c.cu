@@ -9,7 +9,8 @@ cudaError_t launch_f32_collide_compact(const BatchDev<float>& B, const LaunchCfg
     const char* form = getenv("VXG_KERNEL_FORM");
     if (!(form && !strcmp(form, "push"))) {
         cudaError_t e = cudaSuccess; int miss = 1;
-        switch (c.nv) {
+        if (vxg_use_rt(c.nv)) miss = launch_gather_collide<0>(B, c, &e);
+        else switch (c.nv) {
             case 64: miss = launch_gather_collide<64>(B, c, &e); break;
             case 96: miss = launch_gather_collide<96>(B, c, &e); break;
             case 128: miss = launch_gather_collide<128>(B, c, &e); break;

@@ -15,6 +15,7 @@ namespace vx {
 cudaError_t launch_f32_compact(const BatchDev<float>& B, const LaunchCfg& c) {
     const char* form = getenv("VXG_KERNEL_FORM");
     const bool push = form && !strcmp(form, "push"), flow = form && !strcmp(form, "flow");
+    if (!push && vxg_use_rt(c.nv)) return launch_gather<0>(B, c, flow);
     if (!push) switch (c.nv) {
         case 64: return launch_gather<64>(B, c, flow);
         case 96: return launch_gather<96>(B, c, flow);

@@ -102,10 +102,17 @@ extern "C" int vxg_pop_create(vxg_population** out, int device, const vxg_robot_
     // evict each other from the instruction cache (the step loop is ~25 KB of code; ncu: stall_no_instruction).  A CTA's idle
     // warps cost no issue slots, so the wider stride is the smaller tax.  Robots beyond 256 voxels keep a bucket per stride: there
     // the shared memory a robot occupies decides how many are resident.
+    // (VXG_RT_STRIDE=1: the gather family's run-time-stride image instead -- one image, exact strides; measured slower, vxg_gather.cuh)
+    const char* rt_env = getenv("VXG_RT_STRIDE");
+    const bool rt = rt_env && rt_env[0] == '1';
     if (!getenv("VXG_POP_FINE_STRIDES")) {
         std::map<std::tuple<int, int, int>, int> widest;   // (collide, mesh, compact) -> widest small stride
         for (int r = 0; r < n_robots; r++) if (cls[r].stride <= 256) { int& w = widest[std::make_tuple(cls[r].collide, cls[r].mesh, cls[r].compact)]; w = std::max(w, cls[r].stride); }
-        for (int r = 0; r < n_robots; r++) if (cls[r].stride <= 256) cls[r].stride = widest[std::make_tuple(cls[r].collide, cls[r].mesh, cls[r].compact)];
+        for (int r = 0; r < n_robots; r++) {
+            if (cls[r].stride > 256) continue;
+            if (rt && cls[r].compact) cls[r].stride = std::max(64, (descs[r].n_vox + 31) & ~31);
+            else cls[r].stride = widest[std::make_tuple(cls[r].collide, cls[r].mesh, cls[r].compact)];
+        }
     }
 
     const double t_cls = now_s();
