@@ -343,6 +343,20 @@ inline void init_ctl(const vxg_robot_desc* d, RobotCtl& c) {
     c.drag_coeff = P.drag_coeff; c.n_vert = 0;
     c.col_horizon = P.col_horizon; c.lattice_dim = P.lattice_dim; c.col_acc = 0; c.max_vel = 0;
     c.n_col = 0; c.col_first = 1; c.col_host = 0; c.n_surf = 0; c.col_hops = (int)(P.col_horizon * 1.5);
+    {   // where the two-CTA cluster form cuts the robot: the work of a step -- ~6 units per owned bond (v1 owns it), ~5 per voxel --
+        // as even as the 512 slots per CTA allow (a dense 10^3 robot: 488 | 512, the top layer has no +Z bonds); even, because the
+        // halves travel as bulk copies of 8-byte words on 16-byte boundaries
+        std::vector<int> cost(d->n_vox, 5);
+        for (int j = 0; j < d->n_bond; j++) cost[d->bond_v1[j]] += 6;
+        long long tot = 0; for (int v = 0; v < d->n_vox; v++) tot += cost[v];
+        int lo = d->n_vox > 512 ? ((d->n_vox - 512 + 1) & ~1) : 0, hi = (d->n_vox < 512 ? d->n_vox : 512) & ~1;
+        long long pre = 0, best = -1; int split = lo;
+        for (int v = 0; v <= hi; v++) {
+            if (v >= lo && (v & 1) == 0) { const long long diff = pre > tot - pre ? 2 * pre - tot : tot - 2 * pre; if (best < 0 || diff < best) { best = diff; split = v; } }
+            if (v < d->n_vox) pre += cost[v];
+        }
+        c.c2_split = split;
+    }
     c.sym_mass = 1;
     for (int i = 0; i < d->n_bclass; i++) {
         const vxg_bond_class& b = d->bclasses[i];

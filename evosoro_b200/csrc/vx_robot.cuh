@@ -478,7 +478,8 @@ struct RobotCtl {
     int n_col;              // contact bonds in the list
     int col_first;          // ColEnableChanged: rebuild at the next step
     int col_host;           // the host manages the list (vxg_set_collision_pairs): no device rebuild
-    int n_surf, col_hops, pad3;
+    int n_surf, col_hops;
+    int c2_split;           // two-CTA cluster form (vxg_cluster.cuh): CTA 0 owns voxels [0, c2_split), CTA 1 the rest (even; <= 512 on either side)
     long long eol_step;     // CurStepCount at which EndOfLifetimePosteriorY is latched (-1 never)
     double eol_post_y;      // min Pos.y over material != 5 at that step (metres); 0 = not latched
     double growth_amp, midlife_freeze, stop_value;   // development terms of the scale law (ScaleSim)

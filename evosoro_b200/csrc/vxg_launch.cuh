@@ -48,6 +48,7 @@ inline cudaError_t launch_by_stride(const BatchDev<Real>& B, const LaunchCfg& c)
 
 // one per translation unit
 cudaError_t launch_f32_compact(const BatchDev<float>& B, const LaunchCfg& c);                 // production: fp32, smem, compact table
+int launch_f32_cluster(const BatchDev<float>& B, const LaunchCfg& c, cudaError_t* err);       // production, stride 1024: one robot per two-CTA cluster (0 = launched)
 cudaError_t launch_f32_wide(const BatchDev<float>& B, const LaunchCfg& c, bool smem);         // fp32, wide table, smem or global blob
 cudaError_t launch_f64(const BatchDev<double>& B, const LaunchCfg& c, bool smem);             // logic-parity mode
 cudaError_t launch_f32_collide(const BatchDev<float>& B, const LaunchCfg& c);                 // + self-collision

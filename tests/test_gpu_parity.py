@@ -169,17 +169,20 @@ def test_batch_of_identical_robots_is_uniform():
     b.close()
 
 
-@pytest.mark.parametrize("n,steps", [(3, 700), (6, 2500), (8, 2500), (10, 3000)])
+@pytest.mark.parametrize("n,steps", [(3, 700), (6, 2500), (8, 2500), (10, 3000), (11, 1500)])
 def test_gather_form_is_bit_identical_to_the_push_form(n, steps, monkeypatch):
     """The production kernel's two forms (vxg_gather.cuh: damping history in tensor memory, shares gathered by the -axis
     neighbour, with CTA-wide barriers or as a per-warp dataflow; vxg_kernels.cuh: shares pushed into shared-memory accumulators) run
     the same arithmetic in the same order: every word of the state agrees after thousands of actuated steps, in one launch or many."""
     sim = vxa.SimParams(init_cm_time=0.01, stop_condition_value=1.0)
-    robots = [engine.Model(text=vxa.vxa_text(vxa.dense_lattice(n, 80 + s) if s % 2 == 0 else vxa.sparse_lattice(n, 80 + s, fill=0.6), sim=sim)).robot for s in range(4)]
+    # (n = 11: sparse only, ~800 voxels each -- a dense 11^3 would move the whole batch to stride 2048)
+    robots = [engine.Model(text=vxa.vxa_text(vxa.dense_lattice(n, 80 + s) if s % 2 == 0 and n < 11 else vxa.sparse_lattice(n, 80 + s, fill=0.6), sim=sim)).robot for s in range(4)]
     latch = [steps // 3] * 4    # IniCM latch in the middle of a launch: the block reduction shares scratch with other users
     monkeypatch.setenv("VXG_KERNEL_FORM", "push")
     a = engine.Batch(robots); a.set_step_budget(None, latch); a.step(steps); assert not a.sync().any()
-    for form in ("barrier", "flow"):
+    # ("cluster": stride-1024 robots split over a two-CTA cluster, vxg_cluster.cuh -- the dense 10^3 ones, cut between two z layers, and
+    # the sparse 11^3 ones, cut wherever voxel 512 happens to be; other strides run the single-CTA kernel under that name too)
+    for form in ("barrier", "flow", "cluster"):
         monkeypatch.setenv("VXG_KERNEL_FORM", form)
         b = engine.Batch(robots); b.set_step_budget(None, latch)
         for i in range(5):
