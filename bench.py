@@ -113,7 +113,7 @@ def ncu_traffic_per_launch(lattice: int, robots_per_launch: int, timesteps: int)
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the unmodified reference engine, one process per core
 # ------------------------------------------------------------------------------------------------
-def run_reference_cpu(lattice: int, warm_ts: int, timed_ts: int, procs: int, tmpdir: str, seed0: int = 0):
+def run_reference_cpu(lattice: int, warm_ts: int, timed_ts: int, procs: int, tmpdir: str, seed0: int = 0, exe_suffix: str = ""):
     """Run `procs` concurrent single-threaded reference processes (evosoro's execution model,
     evosoro/tools/evaluation.py:89-90), each on its own robot: warm_ts untimed + timed_ts timed TimeStep()
     calls (StatToCalc default, exactly voxelyzeMain's loop).  Returns (voxel_steps_per_s, wall_s, kind)."""
@@ -124,7 +124,7 @@ def run_reference_cpu(lattice: int, warm_ts: int, timed_ts: int, procs: int, tmp
             with open(p, "w") as f:
                 f.write(synthetic_vxa(lattice, seed0 + i))
             paths.append(p)
-        exe = REF_DUMP + "_lw" if WATER else REF_DUMP
+        exe = REF_DUMP + "_lw" if WATER else REF_DUMP + exe_suffix
         # (the reference arm runs with self-collision exactly when the robots ask for it: --selfcol)
         ps = [subprocess.Popen([exe, "time", p, str(warm_ts), str(timed_ts)] + ([] if SELFCOL else ["nocol"]), stdout=subprocess.PIPE, text=True) for p in paths]
         outs = [p.communicate()[0] for p in ps]
@@ -396,6 +396,15 @@ def gpu_arm(args):
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
                "sample": f"{cores} concurrent single-threaded reference processes (evosoro's execution model), one distinct dense {n}^3 robot each, "
                          f"{warm_ts} warm-up + {timed_ts} timed TimeStep() calls, {wall:.1f} s"}
+        if kind == "reference" and not WATER:
+            # two more data points BASELINE.md sections 3.1 / 3.3 ask for: ONE reference process (the engine is single-threaded: this
+            # is what one evaluation costs), and the same with the library compiled as the reference ships it (no optimisation flags)
+            with tempfile.TemporaryDirectory() as td:
+                v1, w1, _ = run_reference_cpu(n, 100, max(200, timed_ts // 10), 1, td)
+                cpu["single_process"] = {"value": v1, "cores": 1, "build": "-O3", "wall_s": round(w1, 2)}
+                if os.access(REF_DUMP + "_O0", os.X_OK):
+                    v0, w0, _ = run_reference_cpu(n, 50, max(100, timed_ts // 30), 1, td, exe_suffix="_O0")
+                    cpu["as_shipped_O0"] = {"value": v0, "cores": 1, "build": "-O0 (Voxelyze/Makefile:92-95 leaves CXXFLAGS unset)", "wall_s": round(w0, 2)}
 
     if rank == 0:
         launches, dev_ms, cfg = m["launches"], m["dev_ms"], m["cfg"]

@@ -77,16 +77,15 @@ VX_HD constexpr size_t vx_align32(size_t x) { return (x + 31) & ~(size_t)31; }
 
 // voxel stride used for a robot of up to max_vox voxels: the kernels are instantiated for these strides
 // (every multiple of a warp up to 256 but the last one -- CPPN morphologies in evosoro's default 6^3 workspace have 65 .. 216 voxels,
-// and a CTA's idle warps cost the SM resident robots --, then 352 / 736 so that 7^3 and 9^3 robots do not pay for 512 / 1024 slots)
+// and a CTA's idle warps cost the SM resident robots --, then 352 / 736 so that 7^3 and 9^3 robots do not pay for 512 / 1024 slots;
+// above 2048 voxels two strides, 8192 and 32768, on the blob in global memory)
 inline int stride_for(int max_vox) {
     static const int strides[] = {64, 96, 128, 160, 192, 224, 256, 352, 512, 736, 1024, 2048};
     if (const char* e = getenv("VXG_STRIDES")) {   // tuning: restrict the strides in use, e.g. "128,224,512,1024" (must be instantiated ones)
         for (const char* p = e; *p;) { const int v = atoi(p); if (v >= max_vox) { for (int s : strides) if (s == v) return v; } while (*p && *p != ',') p++; if (*p) p++; }
     }
     for (int s : strides) if (max_vox <= s) return s;
-    int nv = 4096;
-    while (nv < max_vox) nv *= 2;
-    return nv;
+    return max_vox <= 8192 ? 8192 : 32768;   // global-memory path, 16 / 64 voxels per thread (voxel indices are 16-bit: 32767 voxels at most)
 }
 
 VX_HD constexpr BlobLayout make_layout(int nv_in, int real_size, int nvert_cap = 0) {

@@ -106,7 +106,6 @@ extern "C" int vxg_create(vxg_batch** out, int device, int n_robots, const vxg_l
     CK(cudaSetDevice(device));
     vxg_batch* b = new vxg_batch;
     b->device = device; b->n_robots = n_robots; b->lim = *lim; b->prec = lim->precision;
-    if (lim->max_vox > 2048) { delete b; return fail(VXG_UNSUPPORTED_SIZE, "vxg_create: more than 2048 voxels per robot is not supported yet"); }
     if (lim->max_mesh_verts < 0 || lim->max_mesh_verts > 32767) { delete b; return fail(VXG_ERR_ARG, "vxg_create: max_mesh_verts out of range"); }
     int stride = stride_for(lim->max_vox);
     if (lim->reserved[0] > 0) {   // a wider stride asked for by the population layer (one kernel image for all small robots of a family)

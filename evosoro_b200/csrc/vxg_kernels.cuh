@@ -14,7 +14,10 @@
 //                     Small robots run with fewer threads per CTA; the launch bounds ask for 512 resident threads per SM
 //                     whatever the CTA size (<= 128 registers per thread), so that several small CTAs share an SM.
 //       VPT          : voxels per thread (thread t owns voxels t, t+T, ...), so a 10^3 robot (NV = 1024) runs
-//                     with 512 threads x 2 voxels and <=128 registers per thread.
+//                     with 512 threads x 2 voxels and <=128 registers per thread.  Robots above 2048 voxels (strides 8192 and
+//                     32768, blob in global memory) run 16 / 64 voxels per thread as rolled loops: the per-voxel working set of a
+//                     step (own state, force sums, pending pushes) is then a thread-local array, not registers -- a functional
+//                     path for sizes the reference has no limit on (VX_Sim.cpp:530-600), not a tuned one.
 //   vx_stats_kernel<Real>            one CTA per robot; reductions for the result writer.
 //
 // Replaces CVX_Sim::Integrate (VX_Sim.cpp:1763-1933); see vx_robot.cuh / vx_math.cuh for the
@@ -438,7 +441,7 @@ __global__ void __launch_bounds__(NV / VPT, vx_min_ctas(NV, NV / VPT, FLUID || C
         OwnState<Real> own[VPT];
         BondPush<Real> P[VPT];
         uint32_t fl[VPT];
-#pragma unroll
+#pragma unroll(VPT <= 4 ? VPT : 1)
         for (int j = 0; j < VPT; j++) {
             F[j] = mk3<Real>(0, 0, 0); M[j] = mk3<Real>(0, 0, 0);
             st[j] = R.stat[tid + j * T];
@@ -450,7 +453,7 @@ __global__ void __launch_bounds__(NV / VPT, vx_min_ctas(NV, NV / VPT, FLUID || C
             __syncthreads();
             for (int i = tid; i < C.n_facet; i += T) facet_task<Real>(R, C, i);
             __syncthreads();
-#pragma unroll
+#pragma unroll(VPT <= 4 ? VPT : 1)
             for (int j = 0; j < VPT; j++) if (tid + j * T < n_vox) F[j] = voxel_drag<Real>(R, tid + j * T, st[j]);
         }
         // Scale of every class for the NEXT step, from CurTime before the increment (VXS_Voxel.cpp:224-336).
@@ -467,12 +470,12 @@ __global__ void __launch_bounds__(NV / VPT, vx_min_ctas(NV, NV / VPT, FLUID || C
         // complete before the pushes of the next axis start (same accumulator, different writer), which
         // the split-phase barrier orders without stalling the evaluations.
         int div = 0;
-#pragma unroll
+#pragma unroll(VPT <= 4 ? VPT : 1)
         for (int j = 0; j < VPT; j++) { P[j].w = -1; if (tid + j * T < n_vox) div |= bond_eval<Real, 0, COMPACT, FLUID, HOIST>(R, C, tid + j * T, st[j], own[j], fl[j], dt_inv, F[j], M[j], rec, P[j]) ? 1 : 0; }
-#pragma unroll
+#pragma unroll(VPT <= 4 ? VPT : 1)
         for (int j = 0; j < VPT; j++) bond_push<Real>(R, P[j]);
         axis_arrive(S.mbar, S.arrcnt, T / 32, (tid & 31) == 0);
-#pragma unroll
+#pragma unroll(VPT <= 4 ? VPT : 1)
         for (int j = 0; j < VPT; j++) { P[j].w = -1; if (tid + j * T < n_vox) div |= bond_eval<Real, 1, COMPACT, FLUID, HOIST>(R, C, tid + j * T, st[j], own[j], fl[j], dt_inv, F[j], M[j], rec, P[j]) ? 1 : 0; }
         axis_wait(S.mbar, mpar); mpar ^= 1u;
         if (COLLIDE && col_on && S.colflag[k & 1]) {   // rebuild the contact-bond list (positions are still those of the previous step)
@@ -482,16 +485,16 @@ __global__ void __launch_bounds__(NV / VPT, vx_min_ctas(NV, NV / VPT, FLUID || C
             n_col = col_rebuild<Real>(R2, C2, CT2, (Real)S.colstate[2], (Real)S.colstate[3], S.pairs, B.max_col, (int*)S.red);
             if (n_col > B.max_col) { col_overflow = true; break; }
         }
-#pragma unroll
+#pragma unroll(VPT <= 4 ? VPT : 1)
         for (int j = 0; j < VPT; j++) bond_push<Real>(R, P[j]);
         axis_arrive(S.mbar, S.arrcnt, T / 32, (tid & 31) == 0);
-#pragma unroll
+#pragma unroll(VPT <= 4 ? VPT : 1)
         for (int j = 0; j < VPT; j++) { P[j].w = -1; if (tid + j * T < n_vox) div |= bond_eval<Real, 2, COMPACT, FLUID, HOIST>(R, C, tid + j * T, st[j], own[j], fl[j], dt_inv, F[j], M[j], rec, P[j]) ? 1 : 0; }
         axis_wait(S.mbar, mpar); mpar ^= 1u;
-#pragma unroll
+#pragma unroll(VPT <= 4 ? VPT : 1)
         for (int j = 0; j < VPT; j++) bond_push<Real>(R, P[j]);
         if (COLLIDE && col_on && n_col > 0) {   // contact bonds: positions are still those of the previous step here
-#pragma unroll
+#pragma unroll(VPT <= 4 ? VPT : 1)
             for (int j = 0; j < VPT; j++) if (tid + j * T < n_vox) F[j] = F[j] + col_force_on<Real>(R, C, tid + j * T, st[j], own[j], S.pairs, n_col);
         }
         if (__syncthreads_or(div)) { diverged = true; break; }   // Integrate() returns before the voxel loop (VX_Sim.cpp:1777)
@@ -504,7 +507,7 @@ __global__ void __launch_bounds__(NV / VPT, vx_min_ctas(NV, NV / VPT, FLUID || C
             }
         }
         Real sp2 = (Real)0;
-#pragma unroll
+#pragma unroll(VPT <= 4 ? VPT : 1)
         for (int j = 0; j < VPT; j++) {
             int v = tid + j * T;
             if (v < n_vox) { Real x = voxel_task<Real, !COMPACT>(R, C, v, st[j], own[j], fl[j], F[j], M[j]); sp2 = x > sp2 ? x : sp2; }

@@ -42,6 +42,9 @@ inline cudaError_t launch_by_stride(const BatchDev<Real>& B, const LaunchCfg& c)
             if constexpr (COMPACT && SMEM && !FLUID && !COLLIDE && sizeof(Real) == 4) { if (c.vpt == 1) return launch_one<Real, 1024, 1, true, true, false, false>(B, c); }
             return launch_one<Real, 1024, 2, SMEM, COMPACT, FLUID, COLLIDE>(B, c);
         case 2048: return launch_one<Real, 2048, 4, SMEM, COMPACT, FLUID, COLLIDE>(B, c);
+        // above 2048 voxels: blob in global memory, wide tables, 512 threads x 16 / 64 voxels (rolled loops)
+        case 8192: if constexpr (!SMEM && !COMPACT) return launch_one<Real, 8192, 16, false, false, FLUID, COLLIDE>(B, c); break;
+        case 32768: if constexpr (!SMEM && !COMPACT) return launch_one<Real, 32768, 64, false, false, FLUID, COLLIDE>(B, c); break;
     }
     return cudaErrorInvalidValue;
 }

@@ -281,8 +281,10 @@ def test_large_robot_with_a_class_per_voxel_runs_from_global_memory():
 
 
 def test_largest_supported_robot_and_the_size_limit():
-    """Maximum size: a 12^3 robot (1728 voxels, stride 2048) does not fit in shared memory and runs from global memory; it
-    must agree with the fp64 C oracle like the resident path.  One size up (13^3 = 2197 voxels) is refused, not truncated."""
+    """A 12^3 robot (1728 voxels, stride 2048) does not fit in shared memory and runs from global memory; it must agree with the
+    fp64 C oracle like the resident path.  Above 2048 voxels (the reference has no limit, VX_Sim.cpp:530-600) the strides are 8192 and
+    32768 at 16 / 64 voxels per thread: 13^3 and 21^3 robots against the oracle, in fp32 and in fp64.  Voxel indices are 16-bit:
+    32^3 = 32768 voxels is refused, not truncated."""
     sim = vxa.SimParams(init_cm_time=0.01, stop_condition_value=0.2)
     rob = engine.Model(text=vxa.vxa_text(vxa.dense_lattice(12, 3), sim=sim)).robot
     assert rob.n_vox == 1728
@@ -294,9 +296,22 @@ def test_largest_supported_robot_and_the_size_limit():
     o.step(200)
     assert common.max_abs(b.download(0).pos, o.state().pos) <= 1e-5 * LAT
     b.close()
-    big = engine.Model(text=vxa.vxa_text(vxa.dense_lattice(13, 3), sim=sim)).robot
+    for n, steps in ((13, 200), (21, 120)):
+        big = engine.Model(text=vxa.vxa_text(vxa.dense_lattice(n, 3), sim=sim)).robot
+        assert big.n_vox == n ** 3
+        o = oracle_lib.OracleSim(big)
+        o.step(steps)
+        for prec, tol in ((abi.VXG_PREC_F32, 1e-5), (abi.VXG_PREC_F64, 1e-9)):
+            b = engine.Batch([big, big], precision=prec)
+            assert b.kernel_config()["voxels_per_thread"] == (16 if n == 13 else 64) and not b.kernel_config()["smem_resident"]
+            b.step(steps)
+            assert not b.sync().any()
+            assert common.max_abs(b.download(1).pos, o.state().pos) <= tol * LAT, (n, prec)
+            assert [int(x.steps) for x in b.stats()] == [steps, steps]
+            b.close()
+    huge = engine.Model(text=vxa.vxa_text(vxa.dense_lattice(32, 3), sim=sim)).robot
     with pytest.raises(engine.EngineError) as ei:
-        engine.Batch([big])
+        engine.Batch([huge])
     assert ei.value.code > 0   # unsupported size: the caller must abort
 
 
