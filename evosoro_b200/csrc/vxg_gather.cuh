@@ -217,25 +217,37 @@ __host__ __device__ inline bool fluid_scratch_aliases(int nv, int nvert_cap, int
 // Per-voxel view of the contact-bond list (CSR): seg[v] = begin | end << 16 into adj[], the partners of voxel v in list order (the
 // list is sorted by (v1, v2) with v1 < v2, so that is ascending partner index).  Built once per list rebuild -- a fraction of a
 // percent to a few percent of the steps -- so that a step costs a voxel one word and its own contacts instead of a scan of every
-// pair of the robot (CVXS_Voxel's ColBondInds, VXS_Voxel.cpp:516-528).
+// pair of the robot (CVXS_Voxel's ColBondInds, VXS_Voxel.cpp:516-528).  One pair per thread and round: shared-memory atomics count
+// and place, then every voxel sorts its own few partners -- O(pairs / threads) per thread where a scan of the whole list by every
+// thread cost ten timesteps' worth of instructions per rebuild on a dense robot (a thousand pairs inside the horizon).
 static __device__ __noinline__ void col_csr_build(const ColPair* pairs, int n_col, uint32_t* seg, uint16_t* adj, int* scratch /* [33] */) {
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = T >> 5;
-    int cnt = 0;
-    for (int k = 0; k < n_col; k++) { const ColPair p = pairs[k]; cnt += (p.v1 == tid ? 1 : 0) + (p.v2 == tid ? 1 : 0); }
+    seg[tid] = 0u;
+    __syncthreads();
+    for (int k = tid; k < n_col; k += T) { const ColPair p = pairs[k]; atomicAdd(&seg[p.v1], 1u); atomicAdd(&seg[p.v2], 1u); }
+    __syncthreads();
+    const int cnt = (int)seg[tid];
     int inc = cnt;
     for (int o = 1; o < 32; o <<= 1) { int x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
-    __syncthreads();
     if (lane == 31) scratch[wid] = inc;
     __syncthreads();
     int base = 0;
     for (int w = 0; w < wid && w < nw; w++) base += scratch[w];
-    int off = base + inc - cnt;
-    seg[tid] = (uint32_t)off | ((uint32_t)(off + cnt) << 16);
-    if (cnt > 0)
-        for (int k = 0; k < n_col; k++) {
-            const ColPair p = pairs[k];
-            if (p.v1 == tid) adj[off++] = (uint16_t)p.v2; else if (p.v2 == tid) adj[off++] = (uint16_t)p.v1;
-        }
+    const int off = base + inc - cnt;
+    seg[tid] = (uint32_t)off | ((uint32_t)off << 16);   // the end doubles as the fill cursor
+    __syncthreads();
+    for (int k = tid; k < n_col; k += T) {
+        const ColPair p = pairs[k];
+        adj[atomicAdd(&seg[p.v1], 0x10000u) >> 16] = (uint16_t)p.v2;
+        adj[atomicAdd(&seg[p.v2], 0x10000u) >> 16] = (uint16_t)p.v1;
+    }
+    __syncthreads();
+    for (int a = off + 1; a < off + cnt; a++) {   // list order = ascending partner: insertion sort of this voxel's segment
+        const uint16_t x = adj[a];
+        int b = a - 1;
+        while (b >= off && adj[b] > x) { adj[b + 1] = adj[b]; b--; }
+        adj[b + 1] = x;
+    }
     __syncthreads();
 }
 

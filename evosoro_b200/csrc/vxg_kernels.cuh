@@ -243,8 +243,10 @@ __device__ inline void block_sum4(double& a, double& b, double& c, double& d, do
 }
 
 // CVX_Sim::CalcL1Bonds (VX_Sim.cpp:2357-2413): rebuild the contact-bond list from the current positions.
-// Every thread owns a contiguous block of rows i of the surface-voxel pair triangle (i < j); two passes
-// (count, block-wide exclusive scan, write) keep the list in the reference's creation order (i, then j).
+// The surface-voxel pair triangle (i < j), flattened in the reference's creation order (i, then j), is cut into T equal runs of
+// pairs, one per thread -- not into runs of rows: row i has S - 1 - i pairs, and with about one row per thread (S ~ T for the GA's
+// robots) the thread that owned row 0 tested three times the average number of pairs while half the CTA waited.  Two passes
+// (count, block-wide exclusive scan in thread order, write) keep the list in creation order.
 // Returns the number of contact bonds found (the caller treats > cap as an overflow error).
 template <typename Real>
 __device__ __noinline__ int col_rebuild(const RobotView<Real>& R, const RobotConsts<Real>& C, const ColTables& ct, Real horizon, Real lattice,
@@ -253,11 +255,27 @@ __device__ __noinline__ int col_rebuild(const RobotView<Real>& R, const RobotCon
     const Real filt = horizon * (Real)1.5 * lattice;
     const Real filt2 = filt * filt;
     const int S = ct.n_surf;
-    const int rpt = (S + T - 1) / T;
-    const int r0 = tid * rpt, r1 = (r0 + rpt < S) ? r0 + rpt : S;
+    const long long P = (long long)S * (S - 1) / 2;
+    const int p0 = (int)(P * tid / T), p1 = (int)(P * (tid + 1) / T);
+    // row of pair p0: the largest i with i (2S - i - 1) / 2 <= p0
+    int i0 = 0, j0 = 1;
+    if (p0 < p1) {
+        const double b = 2.0 * S - 1.0;
+        i0 = (int)((b - sqrt(b * b - 8.0 * (double)p0)) * 0.5);
+        if (i0 < 0) i0 = 0;
+        while (i0 > 0 && (long long)i0 * (2 * S - i0 - 1) / 2 > p0) i0--;
+        while ((long long)(i0 + 1) * (2 * S - i0 - 2) / 2 <= p0) i0++;
+        j0 = i0 + 1 + (p0 - (int)((long long)i0 * (2 * S - i0 - 1) / 2));
+    }
     int cnt = 0;
-    for (int i = r0; i < r1; i++) { const int vi = ct.surf[i]; for (int j = i + 1; j < S; j++) cnt += col_pair_hit<Real>(R, C, ct, vi, ct.surf[j], horizon, filt2) ? 1 : 0; }
-    int inc = cnt;   // inclusive scan across the block, in thread (= row) order
+    {
+        int i = i0, j = j0, vi = p0 < p1 ? ct.surf[i0] : 0;
+        for (int p = p0; p < p1; p++) {
+            cnt += col_pair_hit<Real>(R, C, ct, vi, ct.surf[j], horizon, filt2) ? 1 : 0;
+            if (++j == S) { i++; j = i + 1; if (p + 1 < p1) vi = ct.surf[i]; }
+        }
+    }
+    int inc = cnt;   // inclusive scan across the block, in thread (= creation) order
     for (int o = 1; o < 32; o <<= 1) { int x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
     __syncthreads();
     if (lane == 31) scratch[wid] = inc;
@@ -265,11 +283,12 @@ __device__ __noinline__ int col_rebuild(const RobotView<Real>& R, const RobotCon
     int base = 0, total = 0;
     for (int w = 0; w < nw; w++) { int x = scratch[w]; if (w < wid) base += x; total += x; }
     int off = base + inc - cnt;
-    for (int i = r0; i < r1; i++) {
-        const int vi = ct.surf[i];
-        for (int j = i + 1; j < S; j++) {
+    if (cnt > 0) {
+        int i = i0, j = j0, vi = ct.surf[i0];
+        for (int p = p0; p < p1; p++) {
             const int vj = ct.surf[j];
-            if (col_pair_hit<Real>(R, C, ct, vi, vj, horizon, filt2)) { if (off < cap) { ColPair p; p.v1 = (int16_t)vi; p.v2 = (int16_t)vj; pairs[off] = p; } off++; }
+            if (col_pair_hit<Real>(R, C, ct, vi, vj, horizon, filt2)) { if (off < cap) { ColPair q; q.v1 = (int16_t)vi; q.v2 = (int16_t)vj; pairs[off] = q; } off++; }
+            if (++j == S) { i++; j = i + 1; if (p + 1 < p1) vi = ct.surf[i]; }
         }
     }
     __syncthreads();
