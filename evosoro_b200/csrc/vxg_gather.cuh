@@ -669,6 +669,7 @@ __global__ void __launch_bounds__(NV_ ? NV_ : 256, NV_ ? vxg_ctas(NV_, COLLIDE, 
                 if (n_col > 0 && active) {   // CVXS_BondCollision::CalcContactForce for this voxel's contact bonds, in list order
                     const uint32_t sg = c_seg[tid];
                     V3<float> fc = mk3<float>(0, 0, 0);
+#pragma unroll 1   // (four inlined copies of the contact force were 7 KB of the step loop: the SM's instruction cache holds 32 KB)
                     for (uint32_t i = sg & 0xFFFFu; i < (sg >> 16); i++) col_contact<float>(R, C, st, own, c_adj[i], fc);
                     F = F + fc;
                 }
@@ -809,7 +810,8 @@ template <int NV> inline int launch_gather_collide(const BatchDev<float>& B, con
     if (gather_fits(NV ? NV : c.nv, B.max_vclass, B.max_bclass + 1, false, B.max_col)) { *err = launch_gather_form<NV, false, 0, 0, true>(B, c); return 0; }
     return 1;
 }
-// land/water layouts (with or without self-collision); run-time table capacities
+// land/water layouts (with or without self-collision); run-time table capacities (measured: with the compile-time capacities of the
+// plain kernels -- 64 bond classes' worth of tables -- an 8^3 swimmer no longer fits twice on an SM: 1.12e10 instead of 1.40e10)
 template <int NV> inline int launch_gather_fluid(const BatchDev<float>& B, const LaunchCfg& c, bool collide, cudaError_t* err) {
     if (!gather_fits(NV ? NV : c.nv, B.max_vclass, B.max_bclass + 1, false, collide ? B.max_col : 0, B.L.nvert_cap, B.L.nfacet_cap)) return 1;
     *err = collide ? launch_gather_form<NV, false, 0, 0, true, true>(B, c) : launch_gather_form<NV, false, 0, 0, false, true>(B, c);
