@@ -5,6 +5,7 @@
 // What it does follows the reference's loader/importer (file:line cited per function); the code is
 // our own: a small DOM parser instead of tinyxml/XML_Rip, and class de-duplication instead of
 // per-voxel/per-bond objects.
+#include <zlib.h>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -32,6 +33,22 @@ int hfail(int code, const char* fmt, ...) {
 // ---------------------------------------------------------------------------------------------------
 // Minimal XML DOM: elements, attributes, text and CDATA; comments / declarations / DOCTYPE skipped.
 // ---------------------------------------------------------------------------------------------------
+// base64 as the reference decodes it (CVXC_Structure::FromBase64, VX_Object.cpp:2357: stops at '=' or at the first character
+// outside the alphabet; white space inside the element text therefore ends the data, as it does there)
+std::string from_base64(const std::string& in) {
+    static const char* abc = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
+    int val[256]; for (int i = 0; i < 256; i++) val[i] = -1;
+    for (int i = 0; i < 64; i++) val[(unsigned char)abc[i]] = i;
+    std::string out;
+    unsigned int acc = 0; int bits = 0;
+    for (unsigned char c : in) {
+        if (c == '=' || val[c] < 0) break;
+        acc = (acc << 6) | (unsigned int)val[c]; bits += 6;
+        if (bits >= 8) { bits -= 8; out.push_back((char)((acc >> bits) & 0xFF)); }
+    }
+    return out;
+}
+
 struct XNode {
     std::string name;
     std::vector<std::pair<std::string, std::string>> attrs;
@@ -385,8 +402,11 @@ int parse_vxa(const XNode* root, int variant, Parsed& P) {
     const XNode* st = O->child("Structure");
     if (!st) return hfail(VXG_ERR_ARG, "no <Structure> element");
     if (!(version == "" || version == "0.93" || version == "0.94")) return hfail(VXG_UNSUPPORTED_FEATURE, "VXC version %s is not supported", version.c_str());
+    // layer encodings of CVXC_Structure::ReadXML (VX_Object.cpp:1755-1798): ASCII_READABLE (digit = material + '0': what evosoro
+    // writes), BASE64 (the default branch: raw material bytes, base64), ZLIB (the same deflated -- the reference needs
+    // USE_ZLIB_COMPRESSION defined to read it, which its shipped Makefile does not do), RAW_DATA (deprecated: bytes as they are)
     std::string comp = st->attr("Compression");
-    if (comp != "ASCII_READABLE") return hfail(VXG_UNSUPPORTED_FEATURE, "structure compression '%s' is not supported (evosoro writes ASCII_READABLE)", comp.c_str());
+    if (comp == "QT_ZLIB") return hfail(VXG_UNSUPPORTED_FEATURE, "structure compression 'QT_ZLIB' is not supported (deprecated Qt encoding; VX_Object.cpp:1756-1769 refuses it without Qt as well)");
     if (!load(st, "X_Voxels", &P.nx)) P.nx = 1; if (!load(st, "Y_Voxels", &P.ny)) P.ny = 1; if (!load(st, "Z_Voxels", &P.nz)) P.nz = 1;
     if (P.nx <= 0 || P.ny <= 0 || P.nz <= 0 || (long long)P.nx * P.ny * P.nz > 100000000LL) return hfail(VXG_ERR_ARG, "bad structure dimensions");
     const XNode* data = st->child("Data");
@@ -395,10 +415,18 @@ int parse_vxa(const XNode* root, int variant, Parsed& P) {
     if ((int)layers.size() < P.nz) return hfail(VXG_ERR_ARG, "structure has %d layers, expected %d", (int)layers.size(), P.nz);
     P.cells.assign((size_t)P.nx * P.ny * P.nz, 0);
     for (int z = 0; z < P.nz; z++) {
-        const std::string& raw = layers[z]->text;
+        std::string raw = layers[z]->text;
+        const int bias = comp == "ASCII_READABLE" ? 48 : 0;
+        if (comp == "ZLIB") {
+            const std::string packed = from_base64(raw);
+            raw.assign((size_t)P.nx * P.ny, '\0');
+            uLongf dest = (uLongf)raw.size();
+            if (uncompress((Bytef*)&raw[0], &dest, (const Bytef*)packed.data(), (uLong)packed.size()) != Z_OK) return hfail(VXG_ERR_ARG, "layer %d: ZLIB data does not inflate", z);
+            raw.resize(dest);
+        } else if (comp != "ASCII_READABLE" && comp != "RAW_DATA") raw = from_base64(raw);   // BASE64 and anything unnamed, as the reference's default branch
         if ((int)raw.size() != P.nx * P.ny) return hfail(VXG_ERR_ARG, "Voxel layer data not present or does not match expected size.");
         for (int k = 0; k < P.nx * P.ny; k++) {
-            int m = (int)(signed char)(raw[k] - 48);   // VX_Object.cpp:1785
+            int m = (int)(signed char)(raw[k] - bias);   // VX_Object.cpp:1789
             if (m < 0 || m >= (int)P.palette.size()) return hfail(VXG_ERR_ARG, "cell (layer %d, %d) refers to material %d outside the palette", z, k, m);
             P.cells[(size_t)z * P.nx * P.ny + k] = m;
         }

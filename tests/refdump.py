@@ -79,15 +79,15 @@ def have_ref(lw: bool = False) -> bool:
     return os.access(REF_DUMP_LW if lw else REF_DUMP, os.X_OK)
 
 
-def run_ref_dump(vxa_path: str, out_path: str, n_steps: int, every: int = 1, nocol: bool = True, lw: bool = False) -> RefDump:
-    exe = REF_DUMP_LW if lw else REF_DUMP
+def run_ref_dump(vxa_path: str, out_path: str, n_steps: int, every: int = 1, nocol: bool = True, lw: bool = False, suffix: str = "") -> RefDump:
+    exe = REF_DUMP_LW if lw else REF_DUMP + suffix   # suffix "_zlib": the build that reads Compression="ZLIB" (oracle/Makefile)
     cmd = [exe, "dump", vxa_path, out_path, str(n_steps), str(every)] + (["nocol"] if nocol else [])
     subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
     return load_dump(out_path)
 
 
-def run_ref_full(vxa_path: str, out_path: str, nocol: bool = True, lw: bool = False) -> RefDump:
-    exe = REF_DUMP_LW if lw else REF_DUMP
+def run_ref_full(vxa_path: str, out_path: str, nocol: bool = True, lw: bool = False, suffix: str = "") -> RefDump:
+    exe = REF_DUMP_LW if lw else REF_DUMP + suffix
     cmd = [exe, "full", vxa_path, out_path] + (["nocol"] if nocol else [])
     subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
     return load_dump(out_path)

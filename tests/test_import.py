@@ -66,7 +66,8 @@ def test_class_deduplication_is_compact():
     (lambda t: t.replace("<MatModel>0", "<MatModel>2"), 1),
     (lambda t: t.replace("<NumFixed>0", "<NumFixed>1"), -1),                                   # count without its <FRegion>
     (lambda t: t.replace("<NumFixed>0</NumFixed>", "<NumFixed>1</NumFixed><FRegion><PrimType>3</PrimType></FRegion>"), 1),   # mesh region
-    (lambda t: t.replace('Compression="ASCII_READABLE"', 'Compression="ZLIB"'), 1),
+    (lambda t: t.replace('Compression="ASCII_READABLE"', 'Compression="QT_ZLIB"'), 1),         # Qt's deprecated encoding (refused upstream too)
+    (lambda t: t.replace('Compression="ASCII_READABLE"', 'Compression="ZLIB"'), -1),           # digits are not deflated data
     (lambda t: t.replace("</VXA>", ""), -1),
     (lambda t: t.replace("<X_Voxels>3", "<X_Voxels>4"), -1),
 ])
@@ -129,3 +130,22 @@ def test_fluid_environment_file_is_rejected_by_the_voxcad_variant():
     assert m.robot.sim.flags & abi.VXG_F_FLUID
     dry = vxa.vxa_text(vxa.dense_lattice(2, 3), env=vxa.EnvParams(fluid_environment=0))
     assert not (engine.Model(text=dry, variant=engine.VARIANT_VOXCAD).robot.sim.flags & abi.VXG_F_FLUID)
+
+
+def test_structure_layer_encodings_decode_to_the_same_robot():
+    """CVXC_Structure::ReadXML (VX_Object.cpp:1755-1798): ASCII_READABLE, BASE64 and ZLIB layers of the same lattice import to the
+    same model (the reference ships one ZLIB input, voxelyzeMain/Example_stickyFloorBC.vxa: fixture ex_sticky_floor_bc)."""
+    import base64, re, zlib
+    text = vxa.vxa_text(vxa.dense_lattice(4, 3))
+    ref = engine.Model(text=text).robot
+
+    def recode(enc, how):
+        t = text.replace('Compression="ASCII_READABLE"', 'Compression="%s"' % enc)
+        return re.sub(r"<Layer><!\[CDATA\[([0-9]+)\]\]></Layer>", lambda m: "<Layer><![CDATA[" + how(bytes(int(c) for c in m.group(1))) + "]]></Layer>", t)
+
+    for enc, how in (("BASE64", lambda b: base64.b64encode(b).decode()), ("ZLIB", lambda b: base64.b64encode(zlib.compress(b)).decode())):
+        t = recode(enc, how)
+        assert t != text.replace("ASCII_READABLE", enc)   # the layers were rewritten
+        r = engine.Model(text=t).robot
+        assert r.n_vox == ref.n_vox and r.n_bond == ref.n_bond
+        assert np.array_equal(np.asarray(r.vox_class), np.asarray(ref.vox_class)) and np.array_equal(np.asarray(r.nom_pos), np.asarray(ref.nom_pos))

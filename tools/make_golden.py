@@ -32,22 +32,22 @@ def case(name, structure, n_steps, every, sim=None, env=None, palette=None, phas
     case_text(name, text, n_steps, every, lw=lw, full=full, col=col, fitness_file=sim.fitness_file if full else None)
 
 
-def case_text(name, text, n_steps, every, lw=False, full=False, col=False, fitness_file=None):
+def case_text(name, text, n_steps, every, lw=False, full=False, col=False, fitness_file=None, suffix=""):
     class _S: pass
     sim = _S(); sim.fitness_file = fitness_file
     os.makedirs(TMP, exist_ok=True)
     path = os.path.join(TMP, name + ".vxa")
     with open(path, "w") as f:
         f.write(text)
-    d = refdump.run_ref_dump(path, path + ".bin", n_steps, every, nocol=not col, lw=lw)
+    d = refdump.run_ref_dump(path, path + ".bin", n_steps, every, nocol=not col, lw=lw, suffix=suffix)
     out = dict(vxa=np.frombuffer(text.encode("latin-1"), dtype=np.uint8), lw=np.int32(lw), n_steps=np.int64(n_steps), every=np.int64(every),
                sim=d.sim, vox=d.vox, bond=d.bond, frame_hdr=d.frame_hdr, vstate=d.vstate, bstate=d.bstate)
     if full:
-        f = refdump.run_ref_full(path, path + ".full.bin", nocol=not col, lw=lw)
+        f = refdump.run_ref_full(path, path + ".full.bin", nocol=not col, lw=lw, suffix=suffix)
         out.update(full_hdr=f.frame_hdr, full_vstate=f.vstate[-1], full_tail=f.tail)
         # the unmodified reference CLI (voxelyzeMain/main.cpp) on the same file: its result XML is the P5 pin
         import subprocess
-        exe = os.path.join(ROOT, "oracle", "_ref", "voxelyze_ref_lw" if lw else "voxelyze_ref")
+        exe = os.path.join(ROOT, "oracle", "_ref", "voxelyze_ref_lw" if lw else "voxelyze_ref" + suffix)
         if os.path.exists(sim.fitness_file):
             os.remove(sim.fitness_file)
         rc = subprocess.run([exe, "-f", path]).returncode
@@ -202,6 +202,8 @@ EXAMPLES = [   # (fixture name, file, land/water fork, short-horizon steps, fram
     ("ex_example_3", "_voxcad/voxelyzeMain/Example_3.vxa", False, 800, 400),
     ("ex_no_actuation", "_voxcad/voxelyzeMain/Example_no_actuation.vxa", False, 1000, 250),
     ("ex_phase_offset", "_voxcad/voxelyzeMain/Example_withPhaseOffset.vxa", False, 1000, 250),
+    # <Structure Compression="ZLIB"> + a fixed region: read by the reference built with USE_ZLIB_COMPRESSION (oracle/Makefile: *_zlib)
+    ("ex_sticky_floor_bc", "_voxcad/voxelyzeMain/Example_stickyFloorBC.vxa", False, 800, 400),
     ("ex_lw_flapping", "_voxcad_land_water/sample_vxa/flapping_passive_tissue.vxa", True, 1000, 250),
     ("ex_lw_full_cross", "_voxcad_land_water/sample_vxa/full_cross.vxa", True, 800, 400),
     ("ex_lw_hexapus", "_voxcad_land_water/sample_vxa/hexapus.vxa", True, 1000, 250),
@@ -225,8 +227,11 @@ def example_cases(only=None):
         text = open(os.path.join(REF, rel), encoding="latin-1").read()
         fit = os.path.join(TMP, name + "_result.xml")
         text = re.sub(r"<FitnessFileName>[^<]*</FitnessFileName>", "<FitnessFileName>" + fit + "</FitnessFileName>", text)
-        case_text(name, text, n_steps, every, lw=lw, col=True)
-        case_text(name + "_full", text, 0, 1, lw=lw, full=True, col=True, fitness_file=fit)
+        if "<FitnessFileName>" not in text:   # (Example_stickyFloorBC.vxa names no result file: it gets the <GA> block of the other examples)
+            text = text.replace("</Simulator>", "<GA><FitnessFileName>" + fit + "</FitnessFileName><WriteFitnessFile>true</WriteFitnessFile></GA>\n  </Simulator>", 1)
+        suffix = "_zlib" if 'Compression="ZLIB"' in text else ""
+        case_text(name, text, n_steps, every, lw=lw, col=True, suffix=suffix)
+        case_text(name + "_full", text, 0, 1, lw=lw, full=True, col=True, fitness_file=fit, suffix=suffix)
 
 
 if __name__ == "__main__":
