@@ -130,3 +130,39 @@ def test_cli_plan_mode_reports_cost_without_a_gpu(tmp_path):
     assert r.returncode == 0 and "missing.vxa" in r.stderr          # one input could not be imported: reported, the others planned
     assert [row[0] for row in rows] == [str(soft), str(hard)]
     assert [int(row[1]) for row in rows] == [64, 125] and int(rows[1][3]) == 78054 and 9.9 < int(rows[1][3]) / int(rows[0][3]) < 10.1
+
+
+@pytest.mark.gpu
+def test_evaluate_all_through_the_resident_engine(tmp_path):
+    """`voxelyze --serve` (evaluation.ResidentEngine): two generations through ONE engine process give the fitness the one-shot
+    call gives, a diverging individual of the second generation costs only itself, and the process is still up afterwards."""
+    run = str(tmp_path)
+    for d in ("voxelyzeFiles", "fitnessFiles", "bestSoFar/fitOnly", "Gen_0000", "ancestors"):
+        os.makedirs(os.path.join(run, d))
+    env = types.SimpleNamespace(actuation_variance=0)
+    io = make_io(dict(init_cm_time=0.01, stop_condition_value=0.1))
+    a = Pop([Ind(0, vxa.dense_lattice(3, 5)), Ind(1, vxa.dense_lattice(3, 6))])
+    b = Pop([Ind(0, vxa.dense_lattice(3, 5)), Ind(1, vxa.dense_lattice(3, 6))])
+    evaluation.evaluate_all(None, env, a, Log(), 0, run, "t", io=io)
+    evaluation.evaluate_all(None, env, b, Log(), 0, run, "t", io=io, resident=True)
+    assert [i.fitness for i in b] == [i.fitness for i in a]
+    eng = evaluation._resident_engine([0], evaluation.VOXELYZE, [])
+    pid = eng.proc.pid
+    inds = [Ind(10, vxa.dense_lattice(3, 7)), Ind(11, vxa.dense_lattice(3, 8)), Ind(12, vxa.dense_lattice(3, 5))]
+    inds[1].sim_overrides = {"dt_frac": 4.0}
+    c = Pop(inds); log = Log()
+    evaluation.evaluate_all(None, env, c, log, 0, run, "t", io=io, resident=True)
+    assert inds[1].fitness == -1e9 and inds[0].fitness > -1e9 and inds[2].fitness == a[0].fitness
+    assert eng.proc.pid == pid and eng.proc.poll() is None          # same process, still serving
+    eng.close()
+    assert eng.proc is None
+
+
+def test_resident_engine_refuses_to_start_without_a_gpu():
+    """No CPU path behind the server either: without a device `voxelyze --serve` exits with a message instead of answering "ready"."""
+    from evosoro_b200 import engine
+    if engine.device_count() > 0:
+        pytest.skip("a GPU is visible")
+    eng = evaluation.ResidentEngine()
+    with pytest.raises(RuntimeError):
+        eng.run(["/nonexistent.vxa"])
