@@ -811,7 +811,8 @@ template <int NV> inline int launch_gather_collide(const BatchDev<float>& B, con
     return 1;
 }
 // land/water layouts (with or without self-collision); run-time table capacities (measured: with the compile-time capacities of the
-// plain kernels -- 64 bond classes' worth of tables -- an 8^3 swimmer no longer fits twice on an SM: 1.12e10 instead of 1.40e10)
+// plain kernels -- 64 bond classes' worth of tables -- an 8^3 swimmer no longer fits twice on an SM: 1.12e10 instead of 1.40e10;
+// with 32, which do fit, 1.40e10: no gain over the run-time capacities here)
 template <int NV> inline int launch_gather_fluid(const BatchDev<float>& B, const LaunchCfg& c, bool collide, cudaError_t* err) {
     if (!gather_fits(NV ? NV : c.nv, B.max_vclass, B.max_bclass + 1, false, collide ? B.max_col : 0, B.L.nvert_cap, B.L.nfacet_cap)) return 1;
     *err = collide ? launch_gather_form<NV, false, 0, 0, true, true>(B, c) : launch_gather_form<NV, false, 0, 0, false, true>(B, c);
