@@ -63,6 +63,7 @@ int main(int argc, char** argv) {
     if (devices.empty()) devices.push_back(0);
     Options o; o.print_scrn = print_scrn; o.lw = lw; o.ignore_col = ignore_col; o.plan_only = plan_only; o.devices = devices;
     if (serve) {
+        vxg_set_pooling(1);   // a population is built and torn down per request: its device / pinned blocks are reused, not reallocated
         // create the CUDA context of every device now (the first engine object does it), so that the first request does not pay for it
         for (int d : devices) {
             vxg_limits lim; memset(&lim, 0, sizeof lim);
@@ -207,32 +208,42 @@ static int run_files(const std::vector<std::string>& files, const Options& o, in
     }
     const double t_simulated = now_s();
     if (print_scrn) printf("%d robots on %d device(s) in %lld batches, %lld kernel launches\n", n, n_dev, n_batches, n_launches);
-    double t_fmt = 0.0, t_free = 0.0;
-    for (int r = 0; r < n; r++) {
-        vxh_info info; vxh_get_info(models[r], &info);
-        const char* file = files[src[r]].c_str();
-        // A robot whose simulation diverged never reaches its stop condition in the reference (TimeStep keeps returning false,
-        // VX_Sim.cpp:1147-1150, so CurTime stands still and main.cpp:89 never leaves its loop): no result file is ever written and
-        // evosoro leaves the worst fitness on that individual (evaluation.py:107-110, 213-215).  Same here, without the hang:
-        // no file (a stale one is removed), a message, and the others are unaffected.
-        const bool failed = (status[r] & (VXG_ST_COL_OVERFLOW | VXG_ST_DIVERGED)) != 0;
-        if (status[r] & VXG_ST_COL_OVERFLOW) fprintf(stderr, "%s: the self-collision contact-bond list outgrew its capacity. No result written\n", file);
-        else if (status[r] & VXG_ST_DIVERGED) fprintf(stderr, "%s: Simulation Diverged. Please reduce forces or accelerations. No result written\n", file);
-        if (print_scrn) printf("Ended at: %g\n", stats[r].time);
-        const double tw0 = timing ? now_s() : 0.0;
-        if (failed) { n_failed++; if (info.fitness_file_name[0]) remove(info.fitness_file_name); }
-        else if (info.fitness_file_name[0]) {   // SaveResultFile(FitnessFileName), main.cpp:130
-            if (vxh_format_result(models[r], &stats[r], nullptr, 0, info.fitness_file_name) < 0) { fprintf(stderr, "voxelyze: %s\n", vxh_last_error()); n_failed++; }
-        }
-        const double tw1 = timing ? now_s() : 0.0;
-        vxh_free(models[r]);
-        if (timing) { t_fmt += tw1 - tw0; t_free += now_s() - tw1; }
+    // result files, on the host cores like the import (1024 small files: 0.015 s, but up to 0.23 s on a file system that has just
+    // had the previous generation's files deleted from the same directory)
+    if (print_scrn) for (int r = 0; r < n; r++) printf("Ended at: %g\n", stats[r].time);
+    {
+        int nt = (int)std::thread::hardware_concurrency();
+        if (const char* e = getenv("VXG_HOST_THREADS")) nt = atoi(e);
+        nt = std::max(1, std::min(nt, std::min(n, 64)));
+        std::atomic<int> next(0), bad(0);
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++)
+            th.emplace_back([&]() {
+                for (int r; (r = next.fetch_add(1)) < n;) {
+                    vxh_info info; vxh_get_info(models[r], &info);
+                    const char* file = files[src[r]].c_str();
+                    // A robot whose simulation diverged never reaches its stop condition in the reference (TimeStep keeps returning false,
+                    // VX_Sim.cpp:1147-1150, so CurTime stands still and main.cpp:89 never leaves its loop): no result file is ever written and
+                    // evosoro leaves the worst fitness on that individual (evaluation.py:107-110, 213-215).  Same here, without the hang:
+                    // no file (a stale one is removed), a message, and the others are unaffected.
+                    const bool failed = (status[r] & (VXG_ST_COL_OVERFLOW | VXG_ST_DIVERGED)) != 0;
+                    if (status[r] & VXG_ST_COL_OVERFLOW) fprintf(stderr, "%s: the self-collision contact-bond list outgrew its capacity. No result written\n", file);
+                    else if (status[r] & VXG_ST_DIVERGED) fprintf(stderr, "%s: Simulation Diverged. Please reduce forces or accelerations. No result written\n", file);
+                    if (failed) { bad++; if (info.fitness_file_name[0]) remove(info.fitness_file_name); }
+                    else if (info.fitness_file_name[0]) {   // SaveResultFile(FitnessFileName), main.cpp:130
+                        if (vxh_format_result(models[r], &stats[r], nullptr, 0, info.fitness_file_name) < 0) { fprintf(stderr, "voxelyze: %s\n", vxh_last_error()); bad++; }
+                    }
+                    vxh_free(models[r]);
+                }
+            });
+        for (auto& x : th) x.join();
+        n_failed += bad.load();
     }
     const double t_written = now_s();
     for (auto* p : pops) { if (!p) continue; if (defer) defer->push_back(p); else vxg_pop_destroy(p); }
     if (timing) fprintf(stderr, "voxelyze: %d files: import %.3f s, populations (CUDA context, bucketing, flatten, upload, launches) %.3f s, simulation %.3f s, "
-                                "result files %.3f s (write %.3f, free models %.3f), teardown %.3f s\n", n_files, t_imported - t_start, t_launched - t_imported, t_simulated - t_launched,
-                        t_written - t_simulated, t_fmt, t_free, now_s() - t_written);
+                                "result files %.3f s, teardown %.3f s\n", n_files, t_imported - t_start, t_launched - t_imported, t_simulated - t_launched,
+                        t_written - t_simulated, now_s() - t_written);
     if (n_failed) fprintf(stderr, "voxelyze: %d of %d robots did not produce a result\n", n_failed, n_files);
     if (failed_out) *failed_out = n_failed;
     return n_failed ? 0 : 1;

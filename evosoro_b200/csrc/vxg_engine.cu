@@ -9,8 +9,10 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "vxg_batch.h"
@@ -77,16 +79,93 @@ static cudaError_t launch_step_p(vxg_batch* b, int n_steps, int record) {
     return b->compact ? launch_f32_compact(B, c) : launch_f32_wide(B, c, true);
 }
 
+// ---- block cache behind vxg_create / vxg_destroy (vxg_set_pooling) --------------------------------------------------------------
+// A resident engine process (voxelyze --serve) creates and destroys a population of batches per GA generation: ~35 device and pinned
+// allocations each, 0.05 - 0.8 s of cudaMalloc / cudaMallocHost / cudaFree / cudaFreeHost per generation, all of which serialise with
+// the next generation's launches inside the driver.  With pooling on, a destroyed batch's blocks go to a free list (sizes rounded up
+// to 1/8 of the next power of two, so that a generation whose largest robot differs a little still hits) and the next vxg_create
+// takes them from there; the one-shot CLI and the library's other users never switch it on.
+namespace {
+struct PoolBlock { void* p; size_t bytes; int where; };   // where: device ordinal, -1 = pinned host memory
+std::mutex g_pool_mu;
+std::unordered_map<void*, PoolBlock> g_pool_live;
+std::vector<PoolBlock> g_pool_free;
+size_t g_pool_free_bytes = 0;
+bool g_pooling = false;
+const size_t POOL_CAP_BYTES = (size_t)16 << 30;
+
+size_t pool_round(size_t bytes) {
+    size_t g = 4096;
+    while (g * 8 < bytes) g <<= 1;
+    return (bytes + g - 1) / g * g;
+}
+void pool_release(const PoolBlock& b) { if (b.where < 0) cudaFreeHost(b.p); else { cudaSetDevice(b.where); cudaFree(b.p); } }
+}  // namespace
+
+static cudaError_t vx_alloc(void** out, size_t bytes, int where) {
+    *out = nullptr;
+    if (bytes == 0) return cudaSuccess;
+    bool pooling;
+    {
+        std::lock_guard<std::mutex> g(g_pool_mu);
+        pooling = g_pooling;
+        if (pooling) {
+            const size_t want = pool_round(bytes);
+            for (size_t i = 0; i < g_pool_free.size(); i++)
+                if (g_pool_free[i].where == where && g_pool_free[i].bytes == want) {
+                    PoolBlock b = g_pool_free[i];
+                    g_pool_free[i] = g_pool_free.back(); g_pool_free.pop_back(); g_pool_free_bytes -= b.bytes;
+                    g_pool_live[b.p] = b; *out = b.p;
+                    return cudaSuccess;
+                }
+        }
+    }
+    const size_t n = pooling ? pool_round(bytes) : bytes;
+    cudaError_t e = where < 0 ? cudaMallocHost(out, n) : cudaMalloc(out, n);
+    if (e == cudaSuccess && pooling) { std::lock_guard<std::mutex> g(g_pool_mu); g_pool_live[*out] = PoolBlock{*out, n, where}; }
+    return e;
+}
+static void vx_free(void* p, int where) {
+    if (!p) return;
+    std::vector<PoolBlock> drop;
+    {
+        std::lock_guard<std::mutex> g(g_pool_mu);
+        auto it = g_pool_live.find(p);
+        if (it == g_pool_live.end()) drop.push_back(PoolBlock{p, 0, where});          // allocated while pooling was off
+        else {
+            PoolBlock b = it->second; g_pool_live.erase(it);
+            if (!g_pooling) drop.push_back(b);
+            else {
+                g_pool_free.push_back(b); g_pool_free_bytes += b.bytes;
+                while (g_pool_free_bytes > POOL_CAP_BYTES && !g_pool_free.empty()) {   // oldest first
+                    drop.push_back(g_pool_free.front()); g_pool_free_bytes -= g_pool_free.front().bytes; g_pool_free.erase(g_pool_free.begin());
+                }
+            }
+        }
+    }
+    for (const PoolBlock& b : drop) pool_release(b);
+}
+extern "C" int vxg_set_pooling(int on) {
+    std::vector<PoolBlock> drop;
+    {
+        std::lock_guard<std::mutex> g(g_pool_mu);
+        g_pooling = on != 0;
+        if (!g_pooling) { drop.swap(g_pool_free); g_pool_free_bytes = 0; }
+    }
+    for (const PoolBlock& b : drop) pool_release(b);
+    return VXG_OK;
+}
+
 static void free_all(vxg_batch* b) {
-    cudaFree(b->d_blobs); cudaFree(b->d_ctl); cudaFree(b->d_bk); cudaFree(b->d_bk_dist); cudaFree(b->d_vk); cudaFree(b->d_sk);
-    cudaFree(b->d_scale_c); cudaFree(b->d_ext_disp); cudaFree(b->d_ext_tdisp); cudaFree(b->d_nom); cudaFree(b->d_bond_rec); cudaFree(b->d_bpair); cudaFreeHost(b->h_bpair);
-    cudaFree(b->d_stats);
-    cudaFree(b->d_col_pairs); cudaFree(b->d_col_surf); cudaFree(b->d_col_lat4); cudaFree(b->d_col_near);
-    cudaFreeHost(b->h_col_pairs); cudaFreeHost(b->h_col_surf); cudaFreeHost(b->h_col_lat4); cudaFreeHost(b->h_col_near);
-    cudaFreeHost(b->h_bkc);
-    cudaFreeHost(b->h_blobs); cudaFreeHost(b->h_ctl); cudaFreeHost(b->h_bk); cudaFreeHost(b->h_bk_dist); cudaFreeHost(b->h_vk);
-    cudaFreeHost(b->h_sk); cudaFreeHost(b->h_scale_c); cudaFreeHost(b->h_ext_disp); cudaFreeHost(b->h_ext_tdisp); cudaFreeHost(b->h_nom);
-    cudaFreeHost(b->h_stats);
+    vx_free(b->d_blobs, b->device); vx_free(b->d_ctl, b->device); vx_free(b->d_bk, b->device); vx_free(b->d_bk_dist, b->device); vx_free(b->d_vk, b->device); vx_free(b->d_sk, b->device);
+    vx_free(b->d_scale_c, b->device); vx_free(b->d_ext_disp, b->device); vx_free(b->d_ext_tdisp, b->device); vx_free(b->d_nom, b->device); vx_free(b->d_bond_rec, b->device); vx_free(b->d_bpair, b->device); vx_free(b->h_bpair, -1);
+    vx_free(b->d_stats, b->device);
+    vx_free(b->d_col_pairs, b->device); vx_free(b->d_col_surf, b->device); vx_free(b->d_col_lat4, b->device); vx_free(b->d_col_near, b->device);
+    vx_free(b->h_col_pairs, -1); vx_free(b->h_col_surf, -1); vx_free(b->h_col_lat4, -1); vx_free(b->h_col_near, -1);
+    vx_free(b->h_bkc, -1);
+    vx_free(b->h_blobs, -1); vx_free(b->h_ctl, -1); vx_free(b->h_bk, -1); vx_free(b->h_bk_dist, -1); vx_free(b->h_vk, -1);
+    vx_free(b->h_sk, -1); vx_free(b->h_scale_c, -1); vx_free(b->h_ext_disp, -1); vx_free(b->h_ext_tdisp, -1); vx_free(b->h_nom, -1);
+    vx_free(b->h_stats, -1);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
     for (int i = 0; i < VXG_N_MARKS; i++) if (b->marks[i]) cudaEventDestroy(b->marks[i]);
@@ -132,8 +211,8 @@ extern "C" int vxg_create(vxg_batch** out, int device, int n_robots, const vxg_l
 
     size_t nr = (size_t)n_robots, mv = (size_t)lim->max_vclass, mb = (size_t)lim->max_bclass, nv = (size_t)b->L.nv;
     cudaError_t e = cudaSuccess;
-#define DA(ptr, bytes) if (e == cudaSuccess) { e = cudaMalloc((void**)&(ptr), (bytes)); if (e == cudaSuccess) e = cudaMemset((ptr), 0, (bytes)); }
-#define HA(ptr, bytes) if (e == cudaSuccess) { e = cudaMallocHost((void**)&(ptr), (bytes)); if (e == cudaSuccess) memset((ptr), 0, (bytes)); }
+#define DA(ptr, bytes) if (e == cudaSuccess) { e = vx_alloc((void**)&(ptr), (bytes), device); if (e == cudaSuccess) e = cudaMemset((ptr), 0, (bytes)); }
+#define HA(ptr, bytes) if (e == cudaSuccess) { e = vx_alloc((void**)&(ptr), (bytes), -1); if (e == cudaSuccess) memset((ptr), 0, (bytes)); }
     DA(b->d_blobs, nr * b->L.total_bytes); DA(b->d_ctl, nr * sizeof(RobotCtl));
     DA(b->d_bk, nr * mb * b->bk_sz()); DA(b->d_bk_dist, nr * mb * sizeof(double)); DA(b->d_vk, nr * mv * b->vk_sz());
     DA(b->d_sk, nr * mv * sizeof(ScaleK)); DA(b->d_scale_c, nr * mv * sizeof(double)); DA(b->d_bpair, nr * mb * sizeof(uint32_t));
@@ -439,12 +518,12 @@ extern "C" int vxg_enable_bond_record(vxg_batch* b, int on) {
     CK(cudaSetDevice(b->device));
     if (on && !b->d_bond_rec) {
         size_t bytes = (size_t)b->n_robots * 39 * b->L.nv * b->rs();
-        CK(cudaMalloc(&b->d_bond_rec, bytes));
+        CK(vx_alloc(&b->d_bond_rec, bytes, b->device));
         CK(cudaMemset(b->d_bond_rec, 0, bytes));
         b->tables_dirty = true;   // the production family does not record: the wide tables travel before the next step
     } else if (!on && b->d_bond_rec) {
         CK(cudaStreamSynchronize(b->stream));
-        cudaFree(b->d_bond_rec); b->d_bond_rec = nullptr;
+        vx_free(b->d_bond_rec, b->device); b->d_bond_rec = nullptr;
         b->tables_dirty = true;
     }
     return VXG_OK;

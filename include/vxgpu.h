@@ -242,6 +242,9 @@ typedef struct vxg_batch vxg_batch; /* opaque; owns all device memory */
 int vxg_abi_version(void);
 int vxg_device_count(void);
 const char* vxg_last_error(void);
+/* on != 0: vxg_destroy keeps a batch's device and pinned blocks on a free list and vxg_create reuses them (a resident process that
+ * builds a population per GA generation: `voxelyze --serve`); 0 (the default) releases the list.  Process-wide. */
+int vxg_set_pooling(int on);
 
 /* Replaces: construction of CVX_Sim::VoxArray / BondArrayInternal storage (VX_Sim.cpp:488-717). */
 int vxg_create(vxg_batch** out, int device, int n_robots, const vxg_limits* lim);

@@ -14,4 +14,4 @@ PY
 for SHAPE in "--lattice 10 --robots 1024" "--lattice 6 --robots 1024" "--lattice 8 --robots 2048" "--lattice 6 --robots 1024 --selfcol --sparse 0.55" "--lattice 6 --robots 1024 --selfcol" "--lattice 8 --robots 2048 --workload water"; do
   run "$SHAPE"
 done 2>&1 | tee -a gpurun_out/exp_e31.txt
-timeout 900 python tools/ga_generation.py --robots 1024 --resident 4 --ref-sample 0 > gpurun_out/ga_e31.log 2>&1; grep -E "voxelyze:" gpurun_out/ga_e31.log | cut -c100-230; grep -A6 "wall_s_per_generation" gpurun_out/ga_e31.log | head -8
+timeout 900 python tools/ga_generation.py --robots 1024 --resident 7 --ref-sample 0 > gpurun_out/ga_e31.log 2>&1; grep -E "voxelyze:" gpurun_out/ga_e31.log | cut -c100-230; grep -A6 "wall_s_per_generation" gpurun_out/ga_e31.log | head -8
