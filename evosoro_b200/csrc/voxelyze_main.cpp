@@ -176,6 +176,7 @@ static int run_files(const std::vector<std::string>& files, const Options& o, in
     vxg_pop_options opt; memset(&opt, 0, sizeof opt);
     opt.precision = VXG_PREC_F32;
     opt.want_mesh = 1;   // the land/water result file reports the volume of the deformed surface mesh for every robot of that fork
+    if (const char* e = getenv("VXG_COL_PAIRS_PER_VOX")) opt.col_pairs_per_vox = atoi(e);   // contact-bond capacity of the first pass (default 4 x voxels)
     std::vector<vxg_population*> pops(n_dev, nullptr);
     std::vector<uint32_t> status(n, 0);
     std::vector<vxg_robot_stats> stats(n);
@@ -199,6 +200,30 @@ static int run_files(const std::vector<std::string>& files, const Options& o, in
         if (!rc) rc = vxg_pop_reduce_stats(pops[d], ss.data());
         for (size_t i = 0; i < sh.size() && !rc; i++) { status[sh[i]] = st[i]; stats[sh[i]] = ss[i]; }
         n_batches += vxg_pop_n_batches(pops[d]); n_launches += vxg_pop_launch_count(pops[d]);
+    }
+    // The reference's contact-bond list has no capacity (VX_Sim.cpp:2357-2413 grows a vector); ours is sized 4 x voxels, shared-memory
+    // resident.  A robot that outgrows it stopped with VXG_ST_COL_OVERFLOW -- it is run again, from the start, in a population of
+    // its own with sixteen times the room (the engine's limit is 16 384 bonds; beyond that the robot fails like a diverged one).
+    if (!rc) {
+        std::vector<int> again;
+        for (int r = 0; r < n; r++) if (status[r] & VXG_ST_COL_OVERFLOW) again.push_back(r);
+        if (!again.empty()) {
+            fprintf(stderr, "voxelyze: %d robot(s) outgrew the contact-bond list; running them again with a larger one\n", (int)again.size());
+            std::vector<vxg_robot_desc> dd; std::vector<int64_t> t, l, e;
+            for (int r : again) { dd.push_back(descs[r]); t.push_back(total[r]); l.push_back(latch[r]); e.push_back(eol[r]); }
+            vxg_pop_options big = opt;
+            big.col_pairs_per_vox = 16 * (opt.col_pairs_per_vox > 0 ? opt.col_pairs_per_vox : 4);
+            vxg_population* p2 = nullptr;
+            std::vector<uint32_t> st(again.size()); std::vector<vxg_robot_stats> ss(again.size());
+            int rc2 = vxg_pop_create(&p2, devices[0], dd.data(), (int)again.size(), &big);
+            if (!rc2) rc2 = vxg_pop_set_plan(p2, t.data(), l.data(), e.data());
+            if (!rc2) rc2 = vxg_pop_run(p2);
+            if (!rc2) rc2 = vxg_pop_sync(p2, st.data());
+            if (!rc2) rc2 = vxg_pop_reduce_stats(p2, ss.data());
+            if (!rc2) for (size_t i = 0; i < again.size(); i++) { status[again[i]] = st[i]; stats[again[i]] = ss[i]; }
+            else fprintf(stderr, "voxelyze: %s\n", vxg_last_error());
+            if (p2) { n_batches += vxg_pop_n_batches(p2); n_launches += vxg_pop_launch_count(p2); vxg_pop_destroy(p2); }
+        }
     }
     if (rc) {
         fprintf(stderr, "voxelyze: %s\n", vxg_last_error());

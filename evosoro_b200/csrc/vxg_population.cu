@@ -150,7 +150,7 @@ extern "C" int vxg_pop_create(vxg_population** out, int device, const vxg_robot_
                 lim.max_vclass = std::max(lim.max_vclass, descs[r].n_vclass);
                 lim.max_bclass = std::max(lim.max_bclass, cls[r].nbc);
                 lim.max_mesh_verts = std::max(lim.max_mesh_verts, cls[r].nverts);
-                if (cls[r].collide) col_cap = std::max(col_cap, std::min(16384, std::max(512, per_vox * descs[r].n_vox)));
+                if (cls[r].collide) col_cap = std::max(col_cap, opt.col_pairs_per_vox < 0 ? std::min(16384, -opt.col_pairs_per_vox) : std::min(16384, std::max(512, per_vox * descs[r].n_vox)));
             }
             int rc;
             for (;;) {   // the contact-bond list is shared-memory resident next to the robot: halve the capacity until both fit

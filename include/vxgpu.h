@@ -333,7 +333,8 @@ typedef struct vxg_pop_options {
                                    vxg_pop_run_host pipelines flatten / upload / simulate / download; 0 = one batch per bucket */
     int32_t want_mesh;          /* 1: surface-mesh tables for every VXG_F_LW_SCALE robot, not only the VXG_F_FLUID ones (the
                                    land/water result file reports RobotVolumeEnd for all of them)                               */
-    int32_t col_pairs_per_vox;  /* contact-bond capacity of a self-colliding robot = this x n_vox (at least 512); 0 = 4         */
+    int32_t col_pairs_per_vox;  /* contact-bond capacity of a self-colliding robot = this x n_vox (at least 512); 0 = 4;
+                                   negative: exactly -this bonds (tests of the overflow path)                            */
     int32_t reserved[4];
 } vxg_pop_options;
 #define VXG_FAM_COMPACT 0x1  /* production family (compact bond table, gather form) */

@@ -771,3 +771,21 @@ def test_randomized_population_vs_c_oracle():
         worst = max(worst, common.max_abs(b.download(r).pos, o.state().pos) / LAT)
     assert worst <= 2e-5, worst
     b.close()
+
+
+def test_cli_reruns_a_robot_that_outgrew_its_contact_list(tmp_path):
+    """The reference's contact-bond list grows without bound (VX_Sim.cpp:2357-2413); the engine's has a capacity.  A robot that
+    outgrows it is not failed: the CLI runs it again with more room.  Forced here by a first pass with room for 8 bonds on the
+    reference's Example_2.vxa (743 voxels, folds onto itself: the list outgrows 8 bonds at step 494): same result file as with the
+    default capacity, which is the reference's."""
+    g = golden_lib.Golden("ex_example_2_full")
+    outs = []
+    for tag, env in (("a", {}), ("b", {"VXG_COL_PAIRS_PER_VOX": "-8"})):
+        out = tmp_path / (tag + ".xml"); p = tmp_path / (tag + ".vxa")
+        p.write_text(g.vxa_text.replace(g.fitness_file, str(out)))
+        r = subprocess.run([CLI, "-f", str(p)], env=dict(os.environ, **env), capture_output=True, text=True)
+        assert r.returncode == 1, r.stderr
+        assert ("outgrew the contact-bond list" in r.stderr) == bool(env)
+        outs.append(golden_lib.parse_result(out.read_text()))
+    assert outs[0] == outs[1]
+    _check_result((tmp_path / "b.xml").read_text(), g)
