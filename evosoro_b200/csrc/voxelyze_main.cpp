@@ -176,6 +176,10 @@ static int run_files(const std::vector<std::string>& files, const Options& o, in
     vxg_pop_options opt; memset(&opt, 0, sizeof opt);
     opt.precision = VXG_PREC_F32;
     opt.want_mesh = 1;   // the land/water result file reports the volume of the deformed surface mesh for every robot of that fork
+    // batches of 128 robots on their own streams: a launch ends when its last CTA does, so one 1024-robot batch pays for two whole
+    // waves of CTAs in every launch where 1.7 would do, and for its stragglers; eight batches fill each other's gaps
+    opt.chunk_robots = 128;
+    if (const char* e = getenv("VXG_CHUNK_ROBOTS")) opt.chunk_robots = atoi(e);
     if (const char* e = getenv("VXG_COL_PAIRS_PER_VOX")) opt.col_pairs_per_vox = atoi(e);   // contact-bond capacity of the first pass (default 4 x voxels)
     std::vector<vxg_population*> pops(n_dev, nullptr);
     std::vector<uint32_t> status(n, 0);
