@@ -232,6 +232,8 @@ extern "C" int vxg_create(vxg_batch** out, int device, int n_robots, const vxg_l
         HA(b->h_col_pairs, nr * (size_t)mc * sizeof(ColPair)); HA(b->h_col_surf, nr * nv * sizeof(int16_t));
         HA(b->h_col_lat4, nr * nv * 4); HA(b->h_col_near, nr * nv * sizeof(unsigned long long));
     }
+    // the zero fills above went to the default stream; the batch's own stream does not wait for that one (cudaStreamNonBlocking)
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev1);
