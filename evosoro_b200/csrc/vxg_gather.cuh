@@ -173,7 +173,8 @@ __device__ __forceinline__ bool bond_eval_g(unsigned char* smem, const GLayout& 
 
 // Voxel phase of the gather form: the shares of the -X/-Y/-Z bonds (Force2 = -Force1, Moment2) from their owners' staging slots,
 // then EulerStep; the new position / orientation go to shared memory for the neighbours and stay in `own` for the next step.
-template <bool F_REGS>
+//   F_EXTRA : with !F_REGS, F arrives holding what joined the own share after the bonds (the contact forces) instead of zero
+template <bool F_REGS, bool F_EXTRA = false>
 __device__ __forceinline__ float voxel_phase_g(unsigned char* smem, const GLayout& G, int NV, const RobotConsts<float>& C, const RobotView<float>& R, int tid,
                                               const VoxStat& st, uint2 nb, OwnState<float>& own, uint32_t& fl, V3<float> F, V3<float> M) {
     const int mX = nb.x & 0xFFFFu, mY = nb.x >> 16, mZ = nb.y & 0xFFFFu;
@@ -182,7 +183,8 @@ __device__ __forceinline__ float voxel_phase_g(unsigned char* smem, const GLayou
     // own shares: Force1 of the owned X, Y, Z bonds, as staged by this very thread (axes the voxel has no bond on staged zeros)
     if (!F_REGS) {
         const R4<float> ox = ((const R4<float>*)(smem + G.off_stA[0]))[tid], oy = ((const R4<float>*)(smem + G.off_stA[1]))[tid], oz = ((const R4<float>*)(smem + G.off_stA[2]))[tid];
-        F = mk3<float>(((0.0f + ox.x) + oy.x) + oz.x, ((0.0f + ox.y) + oy.y) + oz.y, ((0.0f + ox.z) + oy.z) + oz.z);
+        const V3<float> own_f = mk3<float>(((0.0f + ox.x) + oy.x) + oz.x, ((0.0f + ox.y) + oy.y) + oz.y, ((0.0f + ox.z) + oy.z) + oz.z);
+        F = F_EXTRA ? own_f + F : own_f;
     }
     // the accumulator of the push form received -Force1 of the X, Y, Z bond in that order, starting from zero
     F = F + mk3<float>(((0.0f - ax.x) - ay.x) - az.x, ((0.0f - ax.y) - ay.y) - az.y, ((0.0f - ax.z) - ay.z) - az.z);
@@ -293,7 +295,11 @@ __global__ void __launch_bounds__(NV_ ? NV_ : 256, NV_ ? vxg_ctas(NV_, COLLIDE, 
     const GLayout G = make_glayout(NV);
     const int TM_COLS = tm_cols_for(NV);
     constexpr bool HOIST = !(NV_ == 1024 || NV_ == 512);   // bond_force: only where there are more than 64 registers per thread
-    constexpr bool F_REGS = NV_ == 1024 || COLLIDE || FLUID;   // (contact / drag forces join the own share before the barrier)
+    // (the drag force is the START of a swimmer's force sum, so there the sum stays in registers; contact forces join the finished own
+    // share, so the self-collision variants of the 64-register strides re-read it like the plain ones and add the contacts to it: the
+    // sum's three registers across the bond phase were spilled -- a local load and store per axis, profiles/r02b: 42 LDL per voxel-step)
+    constexpr bool F_REGS = FLUID || (COLLIDE ? !(NV_ == 1024 || NV_ == 512) : NV_ == 1024);
+    constexpr bool F_EXTRA = COLLIDE && !F_REGS;
     // PERM (-DVXG_PERM, off): thread t of the 1024-thread kernel owns voxel (t % 32) * 32 + t / 32 -- the transpose of the warp x lane
     // grid -- and every on-chip array is indexed by THREAD, so that a warp's voxels are spread over the whole robot instead of being
     // 32 consecutive ones.  Motivation: the layers of a 10^3 robot differ in how much they deform, and the calm top-layer warps reach
@@ -500,16 +506,15 @@ __global__ void __launch_bounds__(NV_ ? NV_ : 256, NV_ ? vxg_ctas(NV_, COLLIDE, 
 
     // self-collision state (CVX_Sim::UpdateCollisions, VX_Sim.cpp:1729-1755): the list lives in shared memory during the launch
     const bool col_on = COLLIDE && (flags & VXG_F_COLLISIONS_) != 0 && max_col > 0;
-    ColTables CT;
-    CT.surf = B.col_surf + (size_t)robot * NV; CT.lat4 = B.col_lat4 + (size_t)robot * NV * 4; CT.near = B.col_near + (size_t)robot * NV;
-    CT.n_surf = ctlp->n_surf; CT.hops = ctlp->col_hops;
+    // (what only the rare rebuild or thread 0's bookkeeping needs is not carried in registers through the loop: the 1024-thread variant
+    // runs at 64 registers, and its spills were 4 % of the executed instructions and most of its long-scoreboard stalls)
     int n_col = col_on ? ctlp->n_col : 0;
-    bool col_first = ctlp->col_first != 0, col_overflow = false;
-    const bool col_host = ctlp->col_host != 0;
+    bool col_overflow = false;
     if (COLLIDE && col_on) {
         for (int i = tid; i < n_col; i += T) S.pairs[i] = B.col_pairs[(size_t)robot * max_col + i];
         if (tid == 0) {
-            S.maxvel[0] = 0u; S.maxvel[1] = 0u; S.colflag[0] = 0u; S.colflag[1] = 0u;
+            S.maxvel[0] = 0u; S.maxvel[1] = 0u; S.colflag[0] = 0u;
+            S.colflag[1] = (ctlp->col_first != 0 ? 1u : 0u) | (ctlp->col_host != 0 ? 2u : 0u);   // ColEnableChanged; the host manages the list
             S.colstate[0] = ctlp->col_acc; S.colstate[1] = ctlp->max_vel; S.colstate[2] = ctlp->col_horizon; S.colstate[3] = ctlp->lattice_dim;
         }
         __syncthreads();
@@ -626,8 +631,9 @@ __global__ void __launch_bounds__(NV_ ? NV_ : 256, NV_ ? vxg_ctas(NV_, COLLIDE, 
                 if (k > 0) max_vel = sqrt((double)__uint_as_float(mvb));
                 S.maxvel[k & 1] = 0u;                                      // this step's slot; next read after two barriers
                 col_acc += fabs(max_vel * (s == 0 ? 0.0 : dt) / S.colstate[3]);
-                const bool rebuild = !col_host && (col_acc > (S.colstate[2] - 1.0) / 2 || col_first);
-                if (rebuild) { col_first = false; col_acc = 0.0; }
+                const unsigned int cf = S.colflag[1];
+                const bool rebuild = !(cf & 2u) && (col_acc > (S.colstate[2] - 1.0) / 2 || (cf & 1u));
+                if (rebuild) { S.colflag[1] = cf & ~1u; col_acc = 0.0; }
                 S.colstate[0] = col_acc; S.colstate[1] = max_vel;
                 *(volatile unsigned int*)S.colflag = ((unsigned int)(k + 1) << 1) | (rebuild ? 1u : 0u);
             }
@@ -661,7 +667,16 @@ __global__ void __launch_bounds__(NV_ ? NV_ : 256, NV_ ? vxg_ctas(NV_, COLLIDE, 
                 if (verdict & 1u) {    // CalcL1Bonds (VX_Sim.cpp:2357-2413), by the whole CTA
                     // (copies: the out-of-line rebuild takes its views by reference, and what it is handed must live in memory --
                     // the step loop's own R and C stay in registers)
-                    const RobotView<float> R2 = R; const RobotConsts<float> C2 = C; const ColTables CT2 = CT;
+                    // (views for the out-of-line rebuild, which takes them by reference so that they live in memory: built here from
+                    // scratch with the few members it reads -- a copy of the step loop's own R and C made ptxas keep THOSE in local
+                    // memory and reload their members all through the loop: 42 local loads per voxel-timestep at 10^3)
+                    RobotView<float> R2; memset(&R2, 0, sizeof R2);
+                    R2.n_vox = n_vox; R2.nv = NV; R2.pos = (double*)(smem + G.off_pos); R2.stat = (VoxStat*)(smem + G.off_stat);
+                    RobotConsts<float> C2; memset(&C2, 0, sizeof C2);
+                    C2.scale_c = S.scale_c + cur * mv;
+                    ColTables CT2;
+                    CT2.surf = B.col_surf + (size_t)blockIdx.x * NV; CT2.lat4 = B.col_lat4 + (size_t)blockIdx.x * NV * 4; CT2.near = B.col_near + (size_t)blockIdx.x * NV;
+                    CT2.n_surf = ctlp->n_surf; CT2.hops = ctlp->col_hops;
                     n_col = col_rebuild<float>(R2, C2, CT2, (float)S.colstate[2], (float)S.colstate[3], S.pairs, max_col, (int*)S.red);
                     if (n_col > max_col) { col_overflow = true; break; }
                     if (n_col > 0) col_csr_build(S.pairs, n_col, c_seg, c_adj, (int*)S.red);
@@ -690,7 +705,7 @@ __global__ void __launch_bounds__(NV_ ? NV_ : 256, NV_ ? vxg_ctas(NV_, COLLIDE, 
             }
             // ---- voxel phase: gather the shares of the -X/-Y/-Z bonds (Force2 = -Force1, Moment2), integrate -------------------
             float sp2 = 0.0f;
-            if (active) sp2 = voxel_phase_g<F_REGS>(smem, G, NV, C, R, tid, st, nb, own, fl, F, M);
+            if (active) sp2 = voxel_phase_g<F_REGS, F_EXTRA>(smem, G, NV, C, R, tid, st, nb, own, fl, F, M);
             if (COLLIDE && col_on) {   // SS.MaxVoxVel for the next UpdateCollisions
                 for (int o = 16; o > 0; o >>= 1) sp2 = fmaxf(sp2, __shfl_xor_sync(0xffffffffu, sp2, o));
                 if ((tid & 31) == 0) atomicMax(&S.maxvel[k & 1], __float_as_uint(sp2));
@@ -745,7 +760,7 @@ __global__ void __launch_bounds__(NV_ ? NV_ : 256, NV_ ? vxg_ctas(NV_, COLLIDE, 
         ctlp->step = step0 + done;
         unsigned int st2 = status0;
         if (COLLIDE && col_on) {
-            ctlp->n_col = n_col < max_col ? n_col : max_col; ctlp->col_first = col_first ? 1 : 0; ctlp->col_acc = S.colstate[0];
+            ctlp->n_col = n_col < max_col ? n_col : max_col; ctlp->col_first = (S.colflag[1] & 1u) ? 1 : 0; ctlp->col_acc = S.colstate[0];
             ctlp->max_vel = done > 0 ? sqrt((double)__uint_as_float(S.maxvel[(done - 1) & 1])) : S.colstate[1];
         }
         if (col_overflow) st2 |= VXG_ST_COL_OVERFLOW_ | VXG_ST_DIVERGED_;
