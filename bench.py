@@ -63,6 +63,10 @@ OTHER_CONFIGS = [
     ("BASELINE config 3: 10^3 x 4096, thermal actuation + floor", dict(lattice=10, robots=4096)),
     ("BASELINE config 5: land/water 8^3 x 2048, fluid drag", dict(lattice=8, robots=2048, water=True)),
     ("evosoro GA default: 6^3 workspace, CPPN-like morphologies >= 30 % full (examples/basic.py:114-127), SelfColEnabled=1", dict(lattice=6, robots=1024, selfcol=True, sparse=0.55)),
+    # the same shapes with evosoro's default SelfColEnabled=1 (base.py:24): the self-collision kernel family
+    ("6^3 x 1024 dense, SelfColEnabled=1", dict(lattice=6, robots=1024, selfcol=True)),
+    ("10^3 x 1024, SelfColEnabled=1", dict(lattice=10, robots=1024, selfcol=True)),
+    ("land/water 8^3 x 2048, fluid drag, SelfColEnabled=1", dict(lattice=8, robots=2048, water=True, selfcol=True)),
 ]
 
 
