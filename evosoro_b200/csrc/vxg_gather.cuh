@@ -282,7 +282,9 @@ __device__ inline void flow_wait(unsigned long long* bar, uint32_t mask, uint32_
 //   COLLIDE: self-collision (contact-bond list in shared memory, rebuilt on the device, contact forces through the per-voxel CSR)
 //   FLUID  : land/water layouts: the deformable surface mesh (vertex -> voxels, facets) and the per-voxel strains live in shared memory
 //            behind the class tables (run-time capacities), fluid drag is evaluated at the start of every step
-template <int NV_, bool FLOW, int CV, int CB, bool COLLIDE = false, bool FLUID = false>
+//   NVC    : land/water layouts: compile-time capacity of the surface-mesh arrays in shared memory (vertices; 0 = the batch's).  With CV, CB
+//            and NVC fixed every shared-memory address of the mesh phases is an immediate as well
+template <int NV_, bool FLOW, int CV, int CB, bool COLLIDE = false, bool FLUID = false, int NVC = 0>
 __global__ void __launch_bounds__(NV_ ? NV_ : 256, NV_ ? vxg_ctas(NV_, COLLIDE, FLUID) : 3) vx_step_kernel_g(BatchDev<float> B, int n_steps) {
     static_assert(!(FLOW && (COLLIDE || FLUID)), "the dataflow form has no per-step CTA-wide phases");
     extern __shared__ __align__(128) unsigned char smem[];
@@ -421,9 +423,10 @@ __global__ void __launch_bounds__(NV_ ? NV_ : 256, NV_ ? vxg_ctas(NV_, COLLIDE, 
     RobotView<float> R = make_view<float>(smem, L, n_vox);   // pos / quat / momA / momB views are valid (same offsets as the blob)
     R.stat = (VoxStat*)(smem + G.off_stat);
     const BlobLayout LF = B.L;   // (the batch's layout: the blob of a land/water batch carries the mesh arrays and the strains)
-    const bool fluid_alias = FLUID && fluid_scratch_aliases(NV, LF.nvert_cap, LF.nfacet_cap);
+    const int nvert_cap = NVC ? NVC : LF.nvert_cap, nfacet_cap = NVC ? ((2 * NVC + 64 + 31) & ~31) : LF.nfacet_cap;   // (make_layout's rule)
+    const bool fluid_alias = FLUID && fluid_scratch_aliases(NV, nvert_cap, nfacet_cap);
     if (FLUID) {
-        const size_t nvc = (size_t)LF.nvert_cap, nfc = (size_t)LF.nfacet_cap;
+        const size_t nvc = (size_t)nvert_cap, nfc = (size_t)nfacet_cap;
         unsigned char* q = flp;
         R.strain = (float*)q;     q += vx_align16(sizeof(float) * 6 * NV);
         R.fbase = (uint16_t*)q;   q += vx_align16(sizeof(uint16_t) * NV);
@@ -434,12 +437,12 @@ __global__ void __launch_bounds__(NV_ ? NV_ : 256, NV_ ? vxg_ctas(NV_, COLLIDE, 
         // a fast warp's staging writes off a slow warp's reads).  That is what lets two 8^3 swimmers share an SM.
         if (fluid_alias) { R.vpos = (double*)(smem + G.off_stA[0]); R.fdrag = (float*)(smem + G.off_stA[0] + vx_align16(sizeof(double) * 3 * nvc)); }
         else { R.vpos = (double*)q; q += vx_align16(sizeof(double) * 3 * nvc); R.fdrag = (float*)q; }
-        R.nvert_cap = LF.nvert_cap; R.nfacet_cap = LF.nfacet_cap;
+        R.nvert_cap = nvert_cap; R.nfacet_cap = nfacet_cap;   // (the shared-memory arrays' strides; the blob keeps the batch's)
         unsigned char* gb = B.blobs + (size_t)robot * LF.total_bytes;
         copy4(R.strain, gb + LF.off_strain, sizeof(float) * 6 * NV, tid, T);
         copy4(R.fbase, gb + LF.off_fbase, (sizeof(uint16_t) * NV) & ~(size_t)3, tid, T);
-        copy4(R.facet, gb + LF.off_facet, sizeof(Facet) * nfc, tid, T);
-        copy4(R.vcon, gb + LF.off_vcon, sizeof(Corner8) * nvc, tid, T);
+        copy4(R.facet, gb + LF.off_facet, sizeof(Facet) * (size_t)LF.nfacet_cap, tid, T);
+        copy4(R.vcon, gb + LF.off_vcon, sizeof(Corner8) * (size_t)LF.nvert_cap, tid, T);
     }
     RobotConsts<float> C;
     C.bk = nullptr; C.bkc = (const BondKc<float>*)S.bk;
@@ -790,10 +793,10 @@ inline size_t gather_smem_bytes(int nv, int mv, int mb, bool flow, int max_col =
 // re-keying by voxel-class pair); larger tables run the instantiation with run-time capacities
 #define VXG_CV 8
 #define VXG_CB 64
-template <int NV, bool FLOW, int CV, int CB, bool COLLIDE = false, bool FLUID = false> inline cudaError_t launch_gather_form(const BatchDev<float>& B, const LaunchCfg& c) {
-    auto kern = vx_step_kernel_g<NV, FLOW, CV, CB, COLLIDE, FLUID>;
+template <int NV, bool FLOW, int CV, int CB, bool COLLIDE = false, bool FLUID = false, int NVC = 0> inline cudaError_t launch_gather_form(const BatchDev<float>& B, const LaunchCfg& c) {
+    auto kern = vx_step_kernel_g<NV, FLOW, CV, CB, COLLIDE, FLUID, NVC>;
     const size_t smem = gather_smem_bytes(NV ? NV : c.nv, CV > 0 ? CV : B.max_vclass, CB > 0 ? CB : B.max_bclass + 1, FLOW, COLLIDE ? B.max_col : 0,
-                                          FLUID ? B.L.nvert_cap : 0, FLUID ? B.L.nfacet_cap : 0);
+                                          FLUID ? (NVC ? NVC : B.L.nvert_cap) : 0, FLUID ? (NVC ? ((2 * NVC + 64 + 31) & ~31) : B.L.nfacet_cap) : 0);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<c.n_robots, NV ? NV : c.nv, smem, c.stream>>>(B, c.n_steps);
@@ -828,7 +831,17 @@ template <int NV> inline int launch_gather_collide(const BatchDev<float>& B, con
 // land/water layouts (with or without self-collision); run-time table capacities (measured: with the compile-time capacities of the
 // plain kernels -- 64 bond classes' worth of tables -- an 8^3 swimmer no longer fits twice on an SM: 1.12e10 instead of 1.40e10;
 // with 32, which do fit, 1.40e10: no gain over the run-time capacities here)
+#define VXG_CB_FLUID 32
+#define VXG_NVC_512 416    // mesh vertices of an 8^3 cube's surface (386), rounded up to make_layout's granularity
 template <int NV> inline int launch_gather_fluid(const BatchDev<float>& B, const LaunchCfg& c, bool collide, cudaError_t* err) {
+    if constexpr (NV == 512) {   // 8^3 swimmers (BASELINE config 5): everything compile-time, sized so that two robots still share an SM
+        const size_t two_per_sm = (228u * 1024u) / 2 - 1024u;
+        if (!collide && B.max_vclass <= VXG_CV && B.max_bclass + 1 <= VXG_CB_FLUID && B.L.nvert_cap <= VXG_NVC_512 &&
+            gather_smem_bytes(NV, VXG_CV, VXG_CB_FLUID, false, 0, VXG_NVC_512, (2 * VXG_NVC_512 + 64 + 31) & ~31) <= two_per_sm) {
+            *err = launch_gather_form<NV, false, VXG_CV, VXG_CB_FLUID, false, true, VXG_NVC_512>(B, c);
+            return 0;
+        }
+    }
     if (!gather_fits(NV ? NV : c.nv, B.max_vclass, B.max_bclass + 1, false, collide ? B.max_col : 0, B.L.nvert_cap, B.L.nfacet_cap)) return 1;
     *err = collide ? launch_gather_form<NV, false, 0, 0, true, true>(B, c) : launch_gather_form<NV, false, 0, 0, false, true>(B, c);
     return 0;

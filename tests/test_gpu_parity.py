@@ -789,3 +789,25 @@ def test_cli_reruns_a_robot_that_outgrew_its_contact_list(tmp_path):
         outs.append(golden_lib.parse_result(out.read_text()))
     assert outs[0] == outs[1]
     _check_result((tmp_path / "b.xml").read_text(), g)
+
+
+def test_gather_form_of_an_8_cubed_swimmer_is_bit_identical_to_the_push_form(monkeypatch):
+    """BASELINE config 5's shape (dense 8^3 in the fluid environment) runs the land/water kernel whose class-table and surface-mesh
+    capacities are compile-time constants (two robots per SM); a sparser swimmer in the same stride has more mesh vertices than that
+    instantiation holds and runs the run-time one: both against the push form, every word of the state."""
+    env = vxa.EnvParams(fluid_environment=1, aggregate_drag_coefficient=750.0)
+    sim = vxa.SimParams(init_cm_time=0.01, stop_condition_value=1.0)
+    for st in (vxa.dense_lattice(8, 21), vxa.sparse_lattice(8, 22, fill=0.75)):
+        rob = engine.Model(text=vxa.vxa_text(st, sim=sim, env=env), variant=engine.VARIANT_LAND_WATER).robot
+        monkeypatch.setenv("VXG_KERNEL_FORM", "push")
+        a = engine.Batch([rob, rob]); a.step(900); assert not a.sync().any()
+        monkeypatch.setenv("VXG_KERNEL_FORM", "barrier")
+        b = engine.Batch([rob, rob])
+        for i in range(3):
+            b.step(300)
+        assert not b.sync().any()
+        assert b.kernel_config()["threads"] == 512
+        sa, sb = a.download(1), b.download(1)
+        for f in ("pos", "quat", "lin_mom", "ang_mom", "scale", "static_fric", "bond_small_angle"):
+            assert np.array_equal(getattr(sa, f), getattr(sb, f)), f
+        a.close(); b.close()
