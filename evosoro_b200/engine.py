@@ -120,6 +120,12 @@ def device_count() -> int:
     return lib().vxg_device_count()
 
 
+def set_pooling(on: bool) -> None:
+    """``vxg_set_pooling``: destroyed batches leave their device / pinned blocks on a free list for the next ``Batch`` (a resident
+    process that builds a population per GA generation); ``False`` releases the list."""
+    _ck(lib().vxg_set_pooling(1 if on else 0))
+
+
 VARIANT_VOXCAD = 0
 VARIANT_LAND_WATER = 1
 

@@ -811,3 +811,28 @@ def test_gather_form_of_an_8_cubed_swimmer_is_bit_identical_to_the_push_form(mon
         for f in ("pos", "quat", "lin_mom", "ang_mom", "scale", "static_fric", "bond_small_angle"):
             assert np.array_equal(getattr(sa, f), getattr(sb, f)), f
         a.close(); b.close()
+
+
+def test_block_cache_recycles_a_destroyed_batch_without_changing_results():
+    """vxg_set_pooling (the resident engine's allocator): batches created from recycled device / pinned blocks -- same sizes, smaller,
+    other kernel families -- compute what freshly allocated ones compute (recycled blocks are zero-filled like new ones)."""
+    sim = vxa.SimParams(init_cm_time=0.01, stop_condition_value=1.0)
+    robots = [engine.Model(text=vxa.vxa_text(vxa.dense_lattice(5, 30 + s), sim=sim)).robot for s in range(3)]
+    small = [engine.Model(text=vxa.vxa_text(vxa.sparse_lattice(5, 40, fill=0.5), sim=vxa.SimParams(init_cm_time=0.01, stop_condition_value=1.0, self_col_enabled=1))).robot]
+
+    def run(rs):
+        b = engine.Batch(rs); b.step(700); assert not b.sync().any()
+        out = [b.download(i).pos.copy() for i in range(len(rs))]
+        b.close()
+        return out
+
+    ref_a, ref_b = run(robots), run(small)
+    engine.set_pooling(True)
+    try:
+        for _ in range(3):
+            for got, want in zip(run(robots), ref_a):
+                assert np.array_equal(got, want)
+            for got, want in zip(run(small), ref_b):
+                assert np.array_equal(got, want)
+    finally:
+        engine.set_pooling(False)
