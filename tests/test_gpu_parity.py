@@ -836,3 +836,25 @@ def test_block_cache_recycles_a_destroyed_batch_without_changing_results():
                 assert np.array_equal(got, want)
     finally:
         engine.set_pooling(False)
+
+
+def test_cli_shards_a_population_over_devices_by_cost(tmp_path):
+    """`voxelyze --devices a,b`: robots are dealt out by timesteps x voxels, largest first onto the least loaded device, one population
+    per device, all started before any is waited for.  With one GPU in the box the same device is named twice:
+    two populations side by side.  Every robot's result file equals the one a single-device run writes -- through the one-shot CLI
+    and through the resident engine."""
+    from evosoro_b200 import evaluation
+    sims = [vxa.SimParams(init_cm_time=0.01, stop_condition_value=0.05 + 0.01 * (i % 3)) for i in range(7)]
+    mats = [(1, 3, 4), (1, 2, 3, 4)]          # without / with the stiff material: ten times the timesteps
+    runs = {}
+    for tag, devs, resident in (("one", (0,), False), ("two", (0, 0), False), ("srv", (0, 0), True)):
+        paths = []
+        for i, sim in enumerate(sims):
+            sim.fitness_file = str(tmp_path / ("%s_%d.xml" % (tag, i)))
+            p = tmp_path / ("%s_%d.vxa" % (tag, i))
+            p.write_text(vxa.vxa_text(vxa.dense_lattice(3 + i % 3, 60 + i, materials=mats[i % 2]), sim=sim))
+            paths.append(str(p))
+        assert evaluation.run_batch(paths, devices=devs, resident=resident) == [1]
+        runs[tag] = [golden_lib.parse_result((tmp_path / ("%s_%d.xml" % (tag, i))).read_text()) for i in range(len(sims))]
+    assert runs["two"] == runs["one"] and runs["srv"] == runs["one"]
+    evaluation._resident_engine([0, 0], evaluation.VOXELYZE, []).close()
