@@ -540,9 +540,9 @@ extern "C" int vxg_step(vxg_batch* b, int n_steps) {
     if (rc) return rc;
     CK(cudaEventRecord(b->ev0, b->stream));
     // steps per launch: the state stays on chip inside a launch, and a launch is the granularity at which the CTAs of the other batches /
-    // chunk streams of a population get the SMs.  Measured with 8 chunk streams: 1024 instead of 4096 steps per launch packs the waves of
+    // chunk streams of a population get the SMs.  Measured with 8 chunk streams: 1000 instead of 4096 steps per launch packs the waves of
     // small robots better (6^3 x 1024 end to end 1.69e10 -> 1.90e10) at no cost for large ones.
-    const int chunk = 1024;
+    const int chunk = 1000;
     int left = n_steps;
     while (left > 0) {
         int n = left < chunk ? left : chunk;
