@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define VXG_ABI_VERSION 4   /* 4: vxg_pop_* (ragged populations); 3: development fields, vxg_robot_state.vox_strain, vxg_robot_stats.mesh_volume */
+#define VXG_ABI_VERSION 5   /* 5: vxg_set_pooling, robots up to 32 767 voxels, negative vxg_pop_options.col_pairs_per_vox; 4: vxg_pop_* (ragged populations); 3: development fields, vxg_robot_state.vox_strain, vxg_robot_stats.mesh_volume */
 
 /* ---- return codes ------------------------------------------------------------------------------ */
 enum {

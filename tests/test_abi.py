@@ -34,7 +34,7 @@ def test_struct_sizes_match_ctypes_mirror():
     assert n == len(want)
     for i, t in enumerate(want):
         assert out[i] == C.sizeof(t), (t.__name__, out[i], C.sizeof(t))
-    assert lib.vxg_abi_version() == 4
+    assert lib.vxg_abi_version() == 5
 
 
 def test_headers_compile_as_plain_c(tmp_path):
